@@ -1,0 +1,97 @@
+"""ctypes binding of the deepsee_b200 C ABI (include/deepsee_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` / ``build.sh`` into
+``deepsee_b200/lib/libdeepsee_b200.so``.  There is no fallback: if the library is missing,
+importing a compute op raises, and every entry point fails on a non-sm_100 device.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdeepsee_b200.so")
+
+# every symbol include/deepsee_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "dsee_version", "dsee_last_error", "dsee_launch_count",
+    "dsee_onehot_from_labels", "dsee_labels_from_onehot", "dsee_resize_labels",
+    "dsee_shared_mlp_fwd", "dsee_style_gather_fwd",
+    "dsee_prep_conv_weight", "dsee_split_f16",
+    "dsee_conv3x3_fwd", "dsee_conv3x3_stats_tiles", "dsee_spade_modulate_fwd",
+    "dsee_bn_stats", "dsee_bn_finalize", "dsee_bn_eval_affine",
+    "dsee_stem_fwd", "dsee_head_fwd",
+]
+
+
+class ConvOperands(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("a_hi", C.c_void_p * 2), ("a_lo", C.c_void_p * 2), ("a_channels", C.c_int * 2),
+        ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("w_inv_scale", C.c_void_p),
+        ("n_total", C.c_int), ("passes", C.c_int),
+    ]
+
+
+class ModulateArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_ups", C.c_int),
+        ("noise", C.c_void_p), ("noise_w", C.c_void_p),
+        ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
+        ("gamma_bias", C.c_void_p), ("beta_bias", C.c_void_p),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+        ("C", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once). Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "deepsee_b200: %s not found - run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or ./build.sh). There is no CPU / PyTorch fallback for the hot path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.dsee_version.restype = C.c_int
+    lib.dsee_last_error.restype = C.c_char_p
+    lib.dsee_launch_count.restype = C.c_int64
+    vp, i, f, d, i64 = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_int64
+    sig = {
+        "dsee_onehot_from_labels": [vp, vp, i, i, i, i, vp, vp],
+        "dsee_labels_from_onehot": [vp, vp, i, i, i, i, vp, vp],
+        "dsee_resize_labels": [vp, vp, i, i, i, i, i, vp],
+        "dsee_shared_mlp_fwd": [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp],
+        "dsee_style_gather_fwd": [vp, vp, vp, vp, i, i, i, i, i, vp],
+        "dsee_prep_conv_weight": [vp, vp, vp, vp, i, i, vp],
+        "dsee_split_f16": [vp, vp, vp, i64, vp],
+        "dsee_conv3x3_fwd": [C.POINTER(ConvOperands), vp, vp, i, vp, vp, vp],
+        "dsee_conv3x3_stats_tiles": [i, i, i],
+        "dsee_spade_modulate_fwd": [C.POINTER(ConvOperands), C.POINTER(ModulateArgs), vp],
+        "dsee_bn_stats": [vp, i, vp, vp, i, i, i, i, vp, C.POINTER(C.c_int), vp],
+        "dsee_bn_finalize": [vp, i, i, d, f, f, vp, vp, vp, vp, vp, vp, vp],
+        "dsee_bn_eval_affine": [vp, vp, f, i, vp, vp, vp],
+        "dsee_stem_fwd": [vp, vp, vp, vp, i, i, i, i, vp],
+        "dsee_head_fwd": [vp, vp, vp, vp, i, i, i, i, vp],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    if lib.dsee_version() != 1:
+        raise RuntimeError("deepsee_b200: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().dsee_last_error()
+        raise RuntimeError("deepsee_b200 C-ABI call failed (rc=%d): %s" %
+                           (rc, msg.decode() if msg else "?"))
+
+
+def launch_count():
+    return int(load().dsee_launch_count())

@@ -1,0 +1,511 @@
+// Implicit-GEMM 3x3 convolution on 5th-gen tensor cores (tcgen05 + TMEM), operands fed by TMA.
+//
+//   D[pixel, n] = sum_{pass, tap, c}  A_plane(pass)[pixel + tap, c] * W_plane(pass)[n, tap, c]
+//
+// * M = 128 output pixels = an 8 x 16 spatial tile of one image. For filter tap (dy,dx) the A tile
+//   is the same box shifted by (dy,dx): one 4-D TMA load {64 ch, 16 w, 8 h, 1 b} with signed
+//   coordinates; the zero padding of the convolution is the TMA out-of-bounds fill. No im2col
+//   buffer exists anywhere.
+// * N = 256 output channels per tile, K block = 64 input channels of one tap (128 B rows,
+//   128B-swizzled K-major operands for tcgen05.mma kind::f16, M=128 N=256 K=16).
+// * fp32 accumulators live in TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i
+//   overlaps the main loop of tile i+1. Persistent CTAs, one per SM, static round-robin tiles.
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM
+//   allocator, warps 2..5 = epilogue (one TMEM lane quarter each; thread == output pixel).
+//
+// Two epilogues share the main loop:
+//   EPI_CONV      K2: + bias (+ residual, optionally read through a folded 2x nearest upsample)
+//                 -> fp32 NHWC, optional per-channel sum / sum-of-squares tile partials.
+//   EPI_MODULATE  K1: the accumulator columns are [gamma(128) | beta(128)]; the epilogue applies
+//                 batch-norm scale/shift, x_hat*(gamma)+beta, LeakyReLU(0.2) and emits the fp16
+//                 split planes that the next conv consumes.
+//
+// Reference semantics: architecture.py:75-130, normalization.py:105-120,167-213,254-286.
+#include "common.cuh"
+#include "../../include/deepsee_b200.h"
+#include "launch_count.h"
+#include <string.h>
+
+namespace dsee {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;
+constexpr int TILE_W = 16;
+constexpr int TILE_H = 8;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+enum { EPI_CONV = 0, EPI_MODULATE = 1 };
+
+struct alignas(64) ConvParams {
+    CUtensorMap tmA[4];  // [source*2 + plane]
+    CUtensorMap tmB[2];  // [plane]
+    int B, H, W;
+    int tiles_w, tiles_h, n_tiles, num_tiles;
+    int cb0, cb_total;  // 64-channel blocks in source 0 / in total
+    int passes;
+    uint32_t idesc;
+    int n_total;
+    const float* w_inv_scale;
+    // EPI_CONV
+    const float* bias;
+    const float* residual;
+    int res_ups;
+    float* out;
+    float* stats_partial;
+    // EPI_MODULATE
+    const float* x;
+    int x_ups;
+    const float* noise;
+    const float* noise_w;
+    const float* bn_scale;
+    const float* bn_shift;
+    const float* gamma_bias;
+    const float* beta_bias;
+    __half* out_hi;
+    __half* out_lo;
+    int C;
+};
+
+__device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& b, int& h0, int& w0,
+                                            int& nt) {
+    nt = tile % p.n_tiles;
+    int mt = tile / p.n_tiles;
+    int tw = mt % p.tiles_w;
+    mt /= p.tiles_w;
+    int th = mt % p.tiles_h;
+    b = mt / p.tiles_h;
+    h0 = th * TILE_H;
+    w0 = tw * TILE_W;
+}
+
+__device__ __forceinline__ void store_split8(__half* hi, __half* lo, const float* a) {
+    // 8 consecutive channels -> one 16-byte store per plane
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a0 = fminf(fmaxf(a[2 * j], -65504.f), 65504.f);
+        float a1 = fminf(fmaxf(a[2 * j + 1], -65504.f), 65504.f);
+        __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
+        __half l0 = __float2half_rn(a0 - __half2float(h0));
+        __half l1 = __float2half_rn(a1 - __half2float(h1));
+        ph[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        pl[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4*>(hi) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+// Column sums of a 32(lanes) x 32(values) register tile: afterwards lane l holds sum_lanes v[l].
+// 31 shuffles instead of 32*5 (recursive halving: each step trades half of the live values).
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            // keep j (lower lanes) or j+half (upper lanes); send the other one across
+            float keep = upper ? v[j + half] : v[j];
+            float send = upper ? v[j] : v[j + half];
+            float recv = __shfl_xor_sync(0xffffffffu, send, half);
+            v[j] = keep + recv;
+        }
+    }
+    return v[0];
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128B swizzle needs 1024-byte aligned tiles
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;                  // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmA[i]);
+        tma_prefetch_desc(&p.tmB[0]);
+        tma_prefetch_desc(&p.tmB[1]);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int k_iters = p.passes * 9 * p.cb_total;
+    const int cin_total = p.cb_total * BLOCK_K;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int b, h0, w0, nt;
+                decode_tile(p, tile, b, h0, w0, nt);
+                const int n0 = nt * BLOCK_N;
+                for (int pass = 0; pass < p.passes; ++pass) {
+                    const int pa = (pass == 1) ? 1 : 0;
+                    const int pb = (pass == 2) ? 1 : 0;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        for (int cb = 0; cb < p.cb_total; ++cb, ++it) {
+                            const int s = it % STAGES;
+                            const uint32_t ph = (it / STAGES) & 1;
+                            mbar_wait(&empty_bar[s], ph ^ 1);
+                            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                            uint8_t* sa = smem + s * STAGE_BYTES;
+                            uint8_t* sb = sa + A_BYTES;
+                            const int src = (cb >= p.cb0) ? 1 : 0;
+                            const int cl = src ? cb - p.cb0 : cb;
+                            tma_load_4d(&p.tmA[src * 2 + pa], &full_bar[s], sa, cl * BLOCK_K,
+                                        w0 + dx, h0 + dy, b);
+                            tma_load_2d(&p.tmB[pb], &full_bar[s], sb, tap * cin_total + cb * BLOCK_K,
+                                        n0);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            int lt = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+                const int as = lt & 1;
+                const uint32_t aph = (lt >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+                for (int kit = 0; kit < k_iters; ++kit, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
+                    const uint64_t da = umma_desc_sw128(sa, 1024);
+                    const uint64_t db = umma_desc_sw128(sb, 1024);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                        // advance 16 elements (32 B) along K inside the swizzle atom: +2 (16 B units)
+                        umma_f16(tmem_d, da + 2 * k, db + 2 * k, p.idesc, (kit | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+                }
+                umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may touch
+        const int m = q * 32 + lane;
+        const int ly = m / TILE_W, lx = m % TILE_W;
+        const float inv_scale = __ldg(p.w_inv_scale);
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+            const int as = lt & 1;
+            const uint32_t aph = (lt >> 1) & 1;
+            int b, h0, w0, nt;
+            decode_tile(p, tile, b, h0, w0, nt);
+            const int y = h0 + ly, x = w0 + lx;
+            const bool valid = (y < p.H) && (x < p.W);
+            mbar_wait(&tfull_bar[as], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
+
+            if (EPI == EPI_CONV) {
+                const int n0 = nt * BLOCK_N;
+                const size_t pix = ((size_t)b * p.H + y) * p.W + x;
+                float* orow = p.out + pix * p.n_total;
+                const float* rrow = nullptr;
+                if (p.residual) {
+                    const int Hr = p.H >> p.res_ups, Wr = p.W >> p.res_ups;
+                    const size_t rp = ((size_t)b * Hr + (y >> p.res_ups)) * Wr + (x >> p.res_ups);
+                    rrow = p.residual + rp * p.n_total;
+                }
+#pragma unroll 1
+                for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+                    const int n = n0 + ch * 32;
+                    if (n >= p.n_total) break;  // warp-uniform
+                    uint32_t v[32];
+                    tmem_ld32(taddr + ch * 32, v);
+                    tmem_ld_wait();
+                    float o[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        o[j] = __uint_as_float(v[j]) * inv_scale + __ldg(p.bias + n + j);
+                    if (valid) {
+                        if (rrow) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float4 r = __ldg(reinterpret_cast<const float4*>(rrow + n) + j);
+                                o[4 * j] += r.x;
+                                o[4 * j + 1] += r.y;
+                                o[4 * j + 2] += r.z;
+                                o[4 * j + 3] += r.w;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            reinterpret_cast<float4*>(orow + n)[j] =
+                                make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    }
+                    if (p.stats_partial) {
+                        // tile partial of sum / sum^2 per channel, one slot per (m-tile, quarter)
+                        float s1[32], s2[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float t = valid ? o[j] : 0.f;
+                            s1[j] = t;
+                            s2[j] = t * t;
+                        }
+                        float r1 = warp_transpose_reduce(s1, lane);
+                        float r2 = warp_transpose_reduce(s2, lane);
+                        const size_t slot = (size_t)(tile / p.n_tiles) * 4 + q;
+                        float* sp = p.stats_partial + (slot * p.n_total + n + lane) * 2;
+                        sp[0] = r1;
+                        sp[1] = r2;
+                    }
+                }
+            } else {
+                // EPI_MODULATE: columns [0,128) gamma, [128,256) beta for channels nt*128 + j
+                const int c0 = nt * 128;
+                const size_t pix = ((size_t)b * p.H + y) * p.W + x;
+                const int Hx = p.H >> p.x_ups, Wx = p.W >> p.x_ups;
+                const size_t xp = ((size_t)b * Hx + (y >> p.x_ups)) * Wx + (x >> p.x_ups);
+                const float* xrow = p.x + xp * p.C;
+                const float* nrow = p.noise ? p.noise + pix * p.C : nullptr;
+                __half* hrow = p.out_hi + pix * p.C;
+                __half* lrow = p.out_lo ? p.out_lo + pix * p.C : nullptr;
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    const int c = c0 + ch * 32;
+                    uint32_t g[32], bt[32];
+                    tmem_ld32(taddr + ch * 32, g);
+                    tmem_ld32(taddr + 128 + ch * 32, bt);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            float a[8];
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int j = j8 * 8 + h * 4;
+                                float4 xv = __ldg(reinterpret_cast<const float4*>(xrow + c + j));
+                                float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                                if (nrow) {
+                                    float4 nv = __ldg(reinterpret_cast<const float4*>(nrow + c + j));
+                                    float ns[4] = {nv.x, nv.y, nv.z, nv.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        xs[e] += __ldg(p.noise_w + c + j + e) * ns[e];
+                                }
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int cc = c + j + e;
+                                    float xh = xs[e] * __ldg(p.bn_scale + cc) + __ldg(p.bn_shift + cc);
+                                    float G = __uint_as_float(g[j + e]) * inv_scale +
+                                              __ldg(p.gamma_bias + cc);
+                                    float Bv = __uint_as_float(bt[j + e]) * inv_scale +
+                                               __ldg(p.beta_bias + cc);
+                                    float t = xh * G + Bv;
+                                    a[h * 4 + e] = t > 0.f ? t : 0.2f * t;
+                                }
+                            }
+                            store_split8(hrow + c + j8 * 8, lrow ? lrow + c + j8 * 8 : nullptr, a);
+                        }
+                    }
+                }
+            }
+            // all TMEM reads of this accumulator stage are complete (wait::ld above)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int fill_common(ConvParams& p, const dsee_conv_operands* ops) {
+    DSEE_CHECK_ARG(ops != nullptr, "conv operands are NULL");
+    DSEE_CHECK_ARG(ops->B > 0 && ops->H > 0 && ops->W > 0, "bad geometry B=%d H=%d W=%d", ops->B,
+                   ops->H, ops->W);
+    DSEE_CHECK_ARG(ops->passes == 1 || ops->passes == 3, "passes must be 1 or 3 (got %d)",
+                   ops->passes);
+    DSEE_CHECK_ARG(ops->a_channels[0] > 0 && ops->a_channels[0] % BLOCK_K == 0 &&
+                       ops->a_channels[1] >= 0 && ops->a_channels[1] % BLOCK_K == 0,
+                   "A channel counts must be multiples of %d (got %d, %d)", BLOCK_K,
+                   ops->a_channels[0], ops->a_channels[1]);
+    DSEE_CHECK_ARG(ops->a_hi[0] && ops->w_hi && ops->w_inv_scale, "NULL operand pointer");
+    DSEE_CHECK_ARG(ops->a_channels[1] == 0 || ops->a_hi[1], "second A source is NULL");
+    if (ops->passes == 3) {
+        DSEE_CHECK_ARG(ops->a_lo[0] && ops->w_lo && (ops->a_channels[1] == 0 || ops->a_lo[1]),
+                       "passes=3 needs the lo planes");
+    }
+    DSEE_CHECK_ARG(ops->n_total > 0 && ops->n_total % 32 == 0, "n_total must be a multiple of 32");
+    int rc = require_sm100();
+    if (rc) return rc;
+
+    p.B = ops->B;
+    p.H = ops->H;
+    p.W = ops->W;
+    p.tiles_w = (ops->W + TILE_W - 1) / TILE_W;
+    p.tiles_h = (ops->H + TILE_H - 1) / TILE_H;
+    p.n_tiles = (ops->n_total + BLOCK_N - 1) / BLOCK_N;
+    p.num_tiles = p.B * p.tiles_h * p.tiles_w * p.n_tiles;
+    p.cb0 = ops->a_channels[0] / BLOCK_K;
+    p.cb_total = (ops->a_channels[0] + ops->a_channels[1]) / BLOCK_K;
+    p.passes = ops->passes;
+    p.n_total = ops->n_total;
+    p.w_inv_scale = ops->w_inv_scale;
+    // kind::f16 instruction descriptor: fp32 accumulate, fp16 A/B, K-major both, N=256, M=128
+    p.idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+              ((uint32_t)(BLOCK_M >> 4) << 24);
+
+    for (int src = 0; src < 2; ++src) {
+        const int C = ops->a_channels[src];
+        for (int pl = 0; pl < 2; ++pl) {
+            const void* base = pl ? ops->a_lo[src] : ops->a_hi[src];
+            if (C == 0 || base == nullptr) {
+                // unused slot: alias a valid map so the prefetch stays legal
+                p.tmA[src * 2 + pl] = p.tmA[0];
+                continue;
+            }
+            uint64_t dims[4] = {(uint64_t)C, (uint64_t)ops->W, (uint64_t)ops->H, (uint64_t)ops->B};
+            uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)ops->W * C * 2,
+                                   (uint64_t)ops->H * ops->W * C * 2};
+            uint32_t box[4] = {BLOCK_K, TILE_W, TILE_H, 1};
+            rc = encode_tmap_16b(&p.tmA[src * 2 + pl], base, 4, dims, strides, box, false);
+            if (rc) return rc;
+        }
+    }
+    const uint64_t Ktot = (uint64_t)9 * (ops->a_channels[0] + ops->a_channels[1]);
+    // the weight matrix is padded by the caller to a multiple of BLOCK_N rows? No: TMA zero-fills
+    // rows >= n_total, and the epilogue never stores those columns.
+    for (int pl = 0; pl < 2; ++pl) {
+        const void* base = pl ? ops->w_lo : ops->w_hi;
+        if (!base) {
+            p.tmB[pl] = p.tmB[0];
+            continue;
+        }
+        uint64_t dims[2] = {Ktot, (uint64_t)ops->n_total};
+        uint64_t strides[1] = {Ktot * 2};
+        uint32_t box[2] = {BLOCK_K, BLOCK_N};
+        rc = encode_tmap_16b(&p.tmB[pl], base, 2, dims, strides, box, false);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+template <int EPI>
+static int launch(const ConvParams& p, cudaStream_t stream) {
+    static bool configured[64] = {false};
+    int dev = 0;
+    DSEE_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !configured[dev]) {
+        DSEE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<EPI>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured[dev] = true;
+    }
+    int sms = 0;
+    DSEE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+    conv3x3_tc_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+    count_launch();
+    DSEE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace dsee
+
+using namespace dsee;
+
+extern "C" int dsee_conv3x3_stats_tiles(int B, int H, int W) {
+    return B * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W) * 4;
+}
+
+extern "C" int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const float* bias,
+                                const float* residual, int res_ups, float* out,
+                                float* stats_partial, void* stream) {
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = fill_common(p, ops);
+    if (rc) return rc;
+    DSEE_CHECK_ARG(bias && out, "bias/out is NULL");
+    DSEE_CHECK_ARG(res_ups == 0 || res_ups == 1, "res_ups must be 0 or 1");
+    DSEE_CHECK_ARG(!residual || res_ups == 0 || (ops->H % 2 == 0 && ops->W % 2 == 0),
+                   "folded upsample needs even H, W");
+    p.bias = bias;
+    p.residual = residual;
+    p.res_ups = res_ups;
+    p.out = out;
+    p.stats_partial = stats_partial;
+    return launch<EPI_CONV>(p, (cudaStream_t)stream);
+}
+
+extern "C" int dsee_spade_modulate_fwd(const dsee_conv_operands* ops, const dsee_modulate_args* mod,
+                                       void* stream) {
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = fill_common(p, ops);
+    if (rc) return rc;
+    DSEE_CHECK_ARG(mod != nullptr, "modulate args are NULL");
+    DSEE_CHECK_ARG(mod->C > 0 && mod->C % 128 == 0, "C must be a multiple of 128 (got %d)", mod->C);
+    DSEE_CHECK_ARG(ops->n_total == 2 * mod->C, "n_total (%d) must be 2*C (%d)", ops->n_total,
+                   2 * mod->C);
+    DSEE_CHECK_ARG(mod->x && mod->bn_scale && mod->bn_shift && mod->gamma_bias && mod->beta_bias &&
+                       mod->out_hi,
+                   "NULL modulate pointer");
+    DSEE_CHECK_ARG(mod->x_ups == 0 || mod->x_ups == 1, "x_ups must be 0 or 1");
+    DSEE_CHECK_ARG(mod->x_ups == 0 || (ops->H % 2 == 0 && ops->W % 2 == 0),
+                   "folded upsample needs even H, W");
+    DSEE_CHECK_ARG((mod->noise == nullptr) == (mod->noise_w == nullptr),
+                   "noise and noise_w must be given together");
+    p.x = mod->x;
+    p.x_ups = mod->x_ups;
+    p.noise = mod->noise;
+    p.noise_w = mod->noise_w;
+    p.bn_scale = mod->bn_scale;
+    p.bn_shift = mod->bn_shift;
+    p.gamma_bias = mod->gamma_bias;
+    p.beta_bias = mod->beta_bias;
+    p.out_hi = (__half*)mod->out_hi;
+    p.out_lo = (__half*)mod->out_lo;
+    p.C = mod->C;
+    return launch<EPI_MODULATE>(p, (cudaStream_t)stream);
+}

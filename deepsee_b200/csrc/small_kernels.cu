@@ -1,0 +1,579 @@
+// HBM-bound helper kernels around the two tensor-core kernels: label-map integer work,
+// conditional-norm operand builders (table gather instead of a conv over a one-hot map),
+// weight / activation splitting into fp16 planes, batch-norm statistics, generator stem and head.
+// All are simple coalesced / vectorised streaming kernels; none is reshaped into a GEMM.
+#include "common.cuh"
+#include "launch_count.h"
+#include "../../include/deepsee_b200.h"
+
+#include <math.h>
+
+namespace dsee {
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ void split_f16(float a, __half& hi, __half& lo) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f);
+    hi = __float2half_rn(a);
+    lo = __float2half_rn(a - __half2float(hi));
+}
+__device__ __forceinline__ uint32_t pack2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// label maps
+// ------------------------------------------------------------------------------------------------
+__global__ void onehot_from_labels_kernel(const int64_t* __restrict__ label, float* __restrict__ out,
+                                          int B, int L, int HW, int* bad) {
+    // thread per (b, pixel); writes L planes (coalesced along pixels)
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * HW) return;
+    int b = (int)(i / HW), px = (int)(i % HW);
+    int64_t l = label[i];
+    if (l < 0 || l >= L) {
+        *bad = 1;
+        l = -1;
+    }
+    float* o = out + (size_t)b * L * HW + px;
+    for (int c = 0; c < L; ++c) o[(size_t)c * HW] = (c == l) ? 1.0f : 0.0f;
+}
+
+__global__ void labels_from_onehot_kernel(const float* __restrict__ oh, uint8_t* __restrict__ labels,
+                                          int B, int L, int HW, int* bad) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * HW) return;
+    int b = (int)(i / HW), px = (int)(i % HW);
+    const float* p = oh + (size_t)b * L * HW + px;
+    int found = -1, ones = 0;
+    bool other = false;
+    for (int c = 0; c < L; ++c) {
+        float v = p[(size_t)c * HW];
+        if (v == 1.0f) {
+            ++ones;
+            found = c;
+        } else if (v != 0.0f) {
+            other = true;
+        }
+    }
+    if (ones != 1 || other) {
+        *bad = 1;
+        if (found < 0) found = 0;
+    }
+    labels[i] = (uint8_t)found;
+}
+
+__global__ void resize_labels_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                     int B, int Hin, int Win, int Hout, int Wout, float sh,
+                                     float sw) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * Hout * Wout) return;
+    int x = (int)(i % Wout);
+    int y = (int)((i / Wout) % Hout);
+    int b = (int)(i / ((int64_t)Wout * Hout));
+    // ATen upsample_nearest: src = min(floor(dst * scale), in - 1), scale = in / out (float)
+    int ys = min((int)floorf(y * sh), Hin - 1);
+    int xs = min((int)floorf(x * sw), Win - 1);
+    out[i] = in[((size_t)b * Hin + ys) * Win + xs];
+}
+
+// ------------------------------------------------------------------------------------------------
+// conditional-norm operand builders
+// ------------------------------------------------------------------------------------------------
+// actv = relu(bias + sum_tap table[tap][label(tap)]) ; thread = (pixel, 4 hidden channels)
+__global__ void shared_mlp_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ table,
+                                  const float* __restrict__ bias, __half* __restrict__ out_hi,
+                                  __half* __restrict__ out_lo, int B, int Hl, int Wl, int ups, int L,
+                                  int nh) {
+    const int groups = nh >> 2;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int H = Hl << ups, W = Wl << ups;
+    if (i >= (int64_t)B * H * W * groups) return;
+    int g = (int)(i % groups);
+    int64_t pix = i / groups;
+    int x = (int)(pix % W);
+    int y = (int)((pix / W) % H);
+    int b = (int)(pix / ((int64_t)W * H));
+    const int yl = y >> ups, xl = x >> ups;
+    const uint8_t* lb = labels + (size_t)b * Hl * Wl;
+    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + g);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        int yy = yl + tap / 3 - 1, xx = xl + tap % 3 - 1;
+        if (yy < 0 || yy >= Hl || xx < 0 || xx >= Wl) continue;  // zero padding
+        int l = lb[yy * Wl + xx];
+        float4 t = __ldg(reinterpret_cast<const float4*>(table + ((size_t)tap * L + l) * nh) + g);
+        acc.x += t.x;
+        acc.y += t.y;
+        acc.z += t.z;
+        acc.w += t.w;
+    }
+    float a[4] = {fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f)};
+    __half h[4], l4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_f16(a[e], h[e], l4[e]);
+    size_t o = (size_t)pix * nh + (size_t)g * 4;
+    *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+    if (out_lo)
+        *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack2(l4[0], l4[1]), pack2(l4[2], l4[3]));
+}
+
+__global__ void style_gather_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ style,
+                                    __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B,
+                                    int HW, int L, int d) {
+    const int groups = d >> 2;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * HW * groups) return;
+    int g = (int)(i % groups);
+    int64_t pix = i / groups;
+    int b = (int)(pix / HW);
+    int l = labels[pix];
+    if (l >= L) l = L - 1;
+    float4 s = __ldg(reinterpret_cast<const float4*>(style + ((size_t)b * L + l) * d) + g);
+    float a[4] = {s.x, s.y, s.z, s.w};
+    __half h[4], l4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_f16(a[e], h[e], l4[e]);
+    size_t o = (size_t)pix * d + (size_t)g * 4;
+    *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+    if (out_lo)
+        *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack2(l4[0], l4[1]), pack2(l4[2], l4[3]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand preparation
+// ------------------------------------------------------------------------------------------------
+__global__ void amax_kernel(const float* __restrict__ w, int64_t n, float* scratch) {
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(scratch), __float_as_uint(m));
+}
+
+__device__ __forceinline__ float pow2_scale_for(float amax) {
+    // 2^e with amax * 2^e in [2^13, 2^14)
+    if (!(amax > 0.f) || isinf(amax)) return 1.f;
+    int ex;
+    frexpf(amax, &ex);  // amax = f * 2^ex, f in [0.5, 1)
+    return ldexpf(1.f, 14 - ex);
+}
+
+__global__ void prep_weight_kernel(const float* __restrict__ w, __half* __restrict__ out_hi,
+                                   __half* __restrict__ out_lo, float* inv_scale, int N, int C) {
+    // out[n][tap][c] = w[n][c][tap] * scale
+    const float scale = pow2_scale_for(inv_scale[1]);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) inv_scale[0] = 1.f / scale;
+    if (i >= (int64_t)N * 9 * C) return;
+    int c = (int)(i % C);
+    int tap = (int)((i / C) % 9);
+    int n = (int)(i / ((int64_t)9 * C));
+    float v = w[((size_t)n * C + c) * 9 + tap] * scale;
+    __half h, l;
+    split_f16(v, h, l);
+    out_hi[i] = h;
+    if (out_lo) out_lo[i] = l;
+}
+
+__global__ void split_kernel(const float* __restrict__ in, __half* __restrict__ hi,
+                             __half* __restrict__ lo, int64_t n4) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    float a[4] = {v.x, v.y, v.z, v.w};
+    __half h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_f16(a[e], h[e], l[e]);
+    reinterpret_cast<uint2*>(hi)[i] = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+    if (lo) reinterpret_cast<uint2*>(lo)[i] = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch-norm statistics
+// ------------------------------------------------------------------------------------------------
+constexpr int STAT_PIX = 256;  // pixels per partial
+
+// block = 256 threads: thread t owns channels 4*(t % (C/4)) .. +3 and every (256/(C/4))-th pixel.
+__global__ void bn_stats_kernel(const float* __restrict__ x, int x_ups, const float* __restrict__ noise,
+                                const float* __restrict__ noise_w, int B, int H, int W, int C,
+                                float* __restrict__ partial) {
+    extern __shared__ float red[];  // [pix_lanes][C][2]
+    const int cg = C >> 2;
+    const int pix_lanes = blockDim.x / cg;
+    const int g = threadIdx.x % cg, pl = threadIdx.x / cg;
+    const int64_t npix = (int64_t)B * H * W;
+    const int64_t p0 = (int64_t)blockIdx.x * STAT_PIX;
+    const int Hx = H >> x_ups, Wx = W >> x_ups;
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    float4 nw = make_float4(0, 0, 0, 0);
+    if (noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
+    if (pl < pix_lanes) {
+        for (int i = pl; i < STAT_PIX; i += pix_lanes) {
+            int64_t pix = p0 + i;
+            if (pix >= npix) break;
+            int xx = (int)(pix % W);
+            int yy = (int)((pix / W) % H);
+            int b = (int)(pix / ((int64_t)W * H));
+            size_t xp = ((size_t)b * Hx + (yy >> x_ups)) * Wx + (xx >> x_ups);
+            float4 v = __ldg(reinterpret_cast<const float4*>(x + xp * C) + g);
+            if (noise) {
+                float4 nv = __ldg(reinterpret_cast<const float4*>(noise + (size_t)pix * C) + g);
+                v.x += nw.x * nv.x;
+                v.y += nw.y * nv.y;
+                v.z += nw.z * nv.z;
+                v.w += nw.w * nv.w;
+            }
+            s1[0] += v.x; s2[0] += v.x * v.x;
+            s1[1] += v.y; s2[1] += v.y * v.y;
+            s1[2] += v.z; s2[2] += v.z * v.z;
+            s1[3] += v.w; s2[3] += v.w * v.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            red[((size_t)pl * C + g * 4 + e) * 2] = s1[e];
+            red[((size_t)pl * C + g * 4 + e) * 2 + 1] = s2[e];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, q = 0.f;
+        for (int l = 0; l < pix_lanes; ++l) {  // fixed order -> deterministic
+            a += red[((size_t)l * C + c) * 2];
+            q += red[((size_t)l * C + c) * 2 + 1];
+        }
+        partial[((size_t)blockIdx.x * C + c) * 2] = a;
+        partial[((size_t)blockIdx.x * C + c) * 2 + 1] = q;
+    }
+}
+
+// grid = C/32 blocks, block = 32 channels x 8 partial lanes; double accumulation, fixed order.
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int n_partials, int C,
+                                   double count, float eps, float momentum, float* running_mean,
+                                   float* running_var, float* bn_scale, float* bn_shift,
+                                   float* mean_out, float* var_out) {
+    __shared__ double sh[8][32][2];
+    const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    double a = 0.0, q = 0.0;
+    if (c < C) {
+        for (int s = g; s < n_partials; s += 8) {
+            float2 v = __ldg(reinterpret_cast<const float2*>(partial) + (size_t)s * C + c);
+            a += (double)v.x;
+            q += (double)v.y;
+        }
+    }
+    sh[g][cl][0] = a;
+    sh[g][cl][1] = q;
+    __syncthreads();
+    if (g == 0 && c < C) {
+        double A = 0.0, Q = 0.0;
+        for (int k = 0; k < 8; ++k) {
+            A += sh[k][cl][0];
+            Q += sh[k][cl][1];
+        }
+        double mean = A / count;
+        double var = Q / count - mean * mean;  // biased (batchnorm.py:86-88)
+        if (var < 0.0) var = 0.0;
+        float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        bn_scale[c] = rstd;
+        bn_shift[c] = (float)(-mean) * rstd;
+        if (mean_out) mean_out[c] = (float)mean;
+        if (var_out) var_out[c] = (float)var;
+        if (running_mean) {
+            double unbias = count > 1.0 ? var * count / (count - 1.0) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbias;
+        }
+    }
+}
+
+__global__ void bn_eval_affine_kernel(const float* __restrict__ rm, const float* __restrict__ rv,
+                                      float eps, int C, float* sc, float* sh) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float r = 1.0f / sqrtf(rv[c] + eps);
+    sc[c] = r;
+    sh[c] = -rm[c] * r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generator stem / head
+// ------------------------------------------------------------------------------------------------
+// block per pixel, thread per 4 output channels; weights re-read through L1 (13.8 K floats)
+__global__ void stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                            const float* __restrict__ bias, float* __restrict__ out, int B, int H,
+                            int W, int C) {
+    const int pix = blockIdx.x;
+    const int xx = pix % W, yy = (pix / W) % H, b = pix / (W * H);
+    __shared__ float patch[27];
+    if (threadIdx.x < 27) {
+        int ci = threadIdx.x / 9, tap = threadIdx.x % 9;
+        int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
+        float v = 0.f;
+        if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) v = x[(((size_t)b * 3 + ci) * H + y2) * W + x2];
+        patch[threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = bias[c];
+        const float* wc = w + (size_t)c * 27;
+#pragma unroll
+        for (int k = 0; k < 27; ++k) acc += wc[k] * patch[k];
+        out[(size_t)pix * C + c] = acc;
+    }
+}
+
+// warp per HEAD_PX horizontally adjacent pixels; lanes split the channels (float4 x 4 = 16 ch per
+// 128-channel slab); weights staged in smem as [tap][c][4] (3 outputs + pad).
+constexpr int HEAD_PX = 4;
+__global__ void __launch_bounds__(256)
+head_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+            float* __restrict__ out, int B, int H, int W, int C) {
+    extern __shared__ float4 wsm[];  // [9][C]
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+        int tap = i / C, c = i % C;
+        wsm[i] = make_float4(w[((size_t)0 * C + c) * 9 + tap], w[((size_t)1 * C + c) * 9 + tap],
+                             w[((size_t)2 * C + c) * 9 + tap], 0.f);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wgroups = (W + HEAD_PX - 1) / HEAD_PX;
+    const int64_t ngroups = (int64_t)B * H * wgroups;
+    for (int64_t grp = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; grp < ngroups;
+         grp += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const int xg = (int)(grp % wgroups);
+        const int yy = (int)((grp / wgroups) % H);
+        const int b = (int)(grp / ((int64_t)wgroups * H));
+        const int x0 = xg * HEAD_PX;
+        float acc[HEAD_PX][3];
+#pragma unroll
+        for (int px = 0; px < HEAD_PX; ++px) acc[px][0] = acc[px][1] = acc[px][2] = 0.f;
+        for (int cs = lane * 4; cs < C; cs += 128) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int y2 = yy + ky - 1;
+                if (y2 < 0 || y2 >= H) continue;
+                // columns x0-1 .. x0+HEAD_PX of the activated input, 4 channels each
+                float4 col[HEAD_PX + 2];
+#pragma unroll
+                for (int j = 0; j < HEAD_PX + 2; ++j) {
+                    const int x2 = x0 + j - 1;
+                    float4 v = make_float4(0, 0, 0, 0);
+                    if (x2 >= 0 && x2 < W)
+                        v = __ldg(reinterpret_cast<const float4*>(
+                            x + (((size_t)b * H + y2) * W + x2) * C + cs));
+                    v.x = v.x > 0.f ? v.x : 0.2f * v.x;
+                    v.y = v.y > 0.f ? v.y : 0.2f * v.y;
+                    v.z = v.z > 0.f ? v.z : 0.2f * v.z;
+                    v.w = v.w > 0.f ? v.w : 0.2f * v.w;
+                    col[j] = v;
+                }
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4* wt = wsm + (size_t)(ky * 3 + kx) * C + cs;
+                    const float4 w0 = wt[0], w1 = wt[1], w2 = wt[2], w3 = wt[3];
+#pragma unroll
+                    for (int px = 0; px < HEAD_PX; ++px) {
+                        const float4 v = col[px + kx];
+                        acc[px][0] += v.x * w0.x + v.y * w1.x + v.z * w2.x + v.w * w3.x;
+                        acc[px][1] += v.x * w0.y + v.y * w1.y + v.z * w2.y + v.w * w3.y;
+                        acc[px][2] += v.x * w0.z + v.y * w1.z + v.z * w2.z + v.w * w3.z;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int px = 0; px < HEAD_PX; ++px)
+#pragma unroll
+            for (int o = 0; o < 3; ++o)
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1)
+                    acc[px][o] += __shfl_xor_sync(0xffffffffu, acc[px][o], s);
+        if (lane < HEAD_PX * 3) {
+            const int px = lane / 3, o = lane % 3;
+            float v = 0.f;
+#pragma unroll
+            for (int a = 0; a < HEAD_PX; ++a)
+#pragma unroll
+                for (int c2 = 0; c2 < 3; ++c2)
+                    if (a == px && c2 == o) v = acc[a][c2];
+            const int xo = x0 + px;
+            if (xo < W) out[(((size_t)b * 3 + o) * H + yy) * W + xo] = tanhf(v + bias[o]);
+        }
+    }
+}
+
+}  // namespace dsee
+
+using namespace dsee;
+
+#define LAUNCH_END()              \
+    count_launch();               \
+    DSEE_CUDA(cudaGetLastError()); \
+    return 0
+
+extern "C" int dsee_onehot_from_labels(const int64_t* label, float* out, int B, int L, int H, int W,
+                                       int* bad_flag, void* stream) {
+    DSEE_CHECK_ARG(label && out && bad_flag && B > 0 && L > 0 && H > 0 && W > 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    int64_t n = (int64_t)B * H * W;
+    onehot_from_labels_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(label, out, B, L, H * W,
+                                                                              bad_flag);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_labels_from_onehot(const float* onehot, uint8_t* labels, int B, int L, int H,
+                                       int W, int* bad_flag, void* stream) {
+    DSEE_CHECK_ARG(onehot && labels && bad_flag && B > 0 && L > 0 && L <= 255 && H > 0 && W > 0,
+                   "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    int64_t n = (int64_t)B * H * W;
+    labels_from_onehot_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(onehot, labels, B, L,
+                                                                              H * W, bad_flag);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_resize_labels(const uint8_t* in, uint8_t* out, int B, int Hin, int Win, int Hout,
+                                  int Wout, void* stream) {
+    DSEE_CHECK_ARG(in && out && B > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    int64_t n = (int64_t)B * Hout * Wout;
+    resize_labels_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        in, out, B, Hin, Win, Hout, Wout, (float)Hin / (float)Hout, (float)Win / (float)Wout);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_shared_mlp_fwd(const uint8_t* labels, const float* table, const float* bias,
+                                   void* out_hi, void* out_lo, int B, int Hl, int Wl, int ups, int L,
+                                   int nh, void* stream) {
+    DSEE_CHECK_ARG(labels && table && bias && out_hi, "NULL pointer");
+    DSEE_CHECK_ARG(B > 0 && Hl > 0 && Wl > 0 && (ups == 0 || ups == 1) && L > 0 && nh % 4 == 0,
+                   "bad shape");
+    int rc = require_sm100();
+    if (rc) return rc;
+    int64_t n = (int64_t)B * (Hl << ups) * (Wl << ups) * (nh / 4);
+    shared_mlp_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        labels, table, bias, (__half*)out_hi, (__half*)out_lo, B, Hl, Wl, ups, L, nh);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_style_gather_fwd(const uint8_t* labels, const float* style, void* out_hi,
+                                     void* out_lo, int B, int H, int W, int L, int d, void* stream) {
+    DSEE_CHECK_ARG(labels && style && out_hi && B > 0 && H > 0 && W > 0 && L > 0 && d % 4 == 0,
+                   "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    int64_t n = (int64_t)B * H * W * (d / 4);
+    style_gather_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        labels, style, (__half*)out_hi, (__half*)out_lo, B, H * W, L, d);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_prep_conv_weight(const float* w, void* out_hi, void* out_lo, float* inv_scale,
+                                     int N, int C, void* stream) {
+    DSEE_CHECK_ARG(w && out_hi && inv_scale && N > 0 && C > 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t n = (int64_t)N * C * 9;
+    DSEE_CUDA(cudaMemsetAsync(inv_scale, 0, 2 * sizeof(float), st));
+    int blocks = cdiv(n, 256 * 8);
+    if (blocks > 1024) blocks = 1024;
+    amax_kernel<<<blocks, 256, 0, st>>>(w, n, inv_scale + 1);
+    count_launch();
+    prep_weight_kernel<<<cdiv(n, 256), 256, 0, st>>>(w, (__half*)out_hi, (__half*)out_lo, inv_scale,
+                                                     N, C);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_split_f16(const float* in, void* out_hi, void* out_lo, int64_t n, void* stream) {
+    DSEE_CHECK_ARG(in && out_hi && n > 0 && n % 4 == 0, "bad argument (n must be a multiple of 4)");
+    int rc = require_sm100();
+    if (rc) return rc;
+    split_kernel<<<cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(in, (__half*)out_hi,
+                                                                     (__half*)out_lo, n / 4);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_bn_stats(const float* x, int x_ups, const float* noise, const float* noise_w,
+                             int B, int H, int W, int C, float* stats_partial, int* n_partials,
+                             void* stream) {
+    DSEE_CHECK_ARG(n_partials != nullptr, "n_partials is NULL");
+    int64_t npix = (int64_t)B * H * W;
+    *n_partials = cdiv(npix, STAT_PIX);
+    if (!stats_partial) return 0;  // size query
+    DSEE_CHECK_ARG(x && C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0,
+                   "C must divide 1024 (got %d)", C);
+    DSEE_CHECK_ARG((noise == nullptr) == (noise_w == nullptr), "noise/noise_w mismatch");
+    int rc = require_sm100();
+    if (rc) return rc;
+    int pix_lanes = 256 / (C / 4);
+    size_t sm = (size_t)pix_lanes * C * 2 * sizeof(float);
+    bn_stats_kernel<<<*n_partials, 256, sm, (cudaStream_t)stream>>>(x, x_ups, noise, noise_w, B, H, W,
+                                                                    C, stats_partial);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_bn_finalize(const float* stats_partial, int n_partials, int C, double count,
+                                float eps, float momentum, float* running_mean, float* running_var,
+                                float* bn_scale, float* bn_shift, float* mean_out, float* var_out,
+                                void* stream) {
+    DSEE_CHECK_ARG(stats_partial && n_partials > 0 && C > 0 && count > 0 && bn_scale && bn_shift,
+                   "bad argument");
+    DSEE_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "running stats mismatch");
+    int rc = require_sm100();
+    if (rc) return rc;
+    bn_finalize_kernel<<<cdiv(C, 32), 256, 0, (cudaStream_t)stream>>>(
+        stats_partial, n_partials, C, count, eps, momentum, running_mean, running_var, bn_scale,
+        bn_shift, mean_out, var_out);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_bn_eval_affine(const float* running_mean, const float* running_var, float eps,
+                                   int C, float* bn_scale, float* bn_shift, void* stream) {
+    DSEE_CHECK_ARG(running_mean && running_var && bn_scale && bn_shift && C > 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    bn_eval_affine_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(running_mean, running_var,
+                                                                          eps, C, bn_scale, bn_shift);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_stem_fwd(const float* x, const float* w, const float* bias, float* out, int B,
+                             int H, int W, int C, void* stream) {
+    DSEE_CHECK_ARG(x && w && bias && out && B > 0 && H > 0 && W > 0 && C > 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    stem_kernel<<<B * H * W, 128, 0, (cudaStream_t)stream>>>(x, w, bias, out, B, H, W, C);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_head_fwd(const float* x, const float* w, const float* bias, float* out, int B,
+                             int H, int W, int C, void* stream) {
+    DSEE_CHECK_ARG(x && w && bias && out && B > 0 && H > 0 && W > 0, "bad argument");
+    DSEE_CHECK_ARG(C % 128 == 0 && (size_t)9 * C * 16 <= 200 * 1024, "C must be a multiple of 128 and <= 1408");
+    int rc = require_sm100();
+    if (rc) return rc;
+    static bool configured[64] = {false};
+    int dev = 0;
+    DSEE_CUDA(cudaGetDevice(&dev));
+    size_t sm = (size_t)9 * C * sizeof(float4);
+    if (dev < 64 && !configured[dev]) {
+        DSEE_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024));
+        configured[dev] = true;
+    }
+    int64_t ngroups = (int64_t)B * H * ((W + HEAD_PX - 1) / HEAD_PX);
+    int blocks = cdiv(ngroups, 8);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (blocks > sms * 2) blocks = sms * 2;
+    head_kernel<<<blocks, 256, sm, (cudaStream_t)stream>>>(x, w, bias, out, B, H, W, C);
+    LAUNCH_END();
+}

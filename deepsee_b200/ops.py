@@ -1,0 +1,260 @@
+"""Tensor-level wrappers over the C ABI: PyTorch tensors in, PyTorch tensors out.
+
+PyTorch is used here only for device memory (the caching allocator owns every buffer) and for
+the current CUDA stream; all arithmetic of the hot path happens inside the shared library.
+Every function raises if the library is missing or the device is not a B200 - no fallback.
+"""
+import ctypes as C
+from collections import namedtuple
+
+import torch
+
+from . import _lib
+
+SplitPlanes = namedtuple("SplitPlanes", ["hi", "lo"])  # fp16 NHWC [B,H,W,C]; value = hi + lo
+PreparedWeight = namedtuple("PreparedWeight", ["hi", "lo", "inv_scale", "n_total", "cin"])
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _chk_cuda(*ts):
+    for t in ts:
+        if t is not None:
+            if not t.is_cuda:
+                raise RuntimeError("deepsee_b200 ops need CUDA tensors (no CPU fallback exists)")
+            if not t.is_contiguous():
+                raise RuntimeError("deepsee_b200 ops need contiguous tensors")
+
+
+# ---------------------------------------------------------------------------------------------
+# label maps
+# ---------------------------------------------------------------------------------------------
+def onehot_from_labels(label, num_classes):
+    """Preprocessor.preprocess_label (data/preprocessor.py:35-41). label int64 [B,1,H,W]."""
+    _chk_cuda(label)
+    assert label.dtype == torch.int64 and label.dim() == 4 and label.size(1) == 1
+    B, _, H, W = label.shape
+    out = torch.empty((B, num_classes, H, W), dtype=torch.float32, device=label.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=label.device)
+    _lib.check(_lib.load().dsee_onehot_from_labels(_p(label), _p(out), B, num_classes, H, W, _p(bad),
+                                                   _stream()))
+    return out, bad
+
+
+def labels_from_onehot(onehot):
+    """fp32 one-hot [B,L,H,W] -> uint8 [B,H,W] plus a device flag that is 1 if not one-hot."""
+    _chk_cuda(onehot)
+    assert onehot.dtype == torch.float32 and onehot.dim() == 4
+    B, L, H, W = onehot.shape
+    labels = torch.empty((B, H, W), dtype=torch.uint8, device=onehot.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=onehot.device)
+    _lib.check(_lib.load().dsee_labels_from_onehot(_p(onehot), _p(labels), B, L, H, W, _p(bad),
+                                                   _stream()))
+    return labels, bad
+
+
+def resize_labels(labels, Hout, Wout):
+    _chk_cuda(labels)
+    assert labels.dtype == torch.uint8 and labels.dim() == 3
+    B, Hin, Win = labels.shape
+    if (Hin, Win) == (Hout, Wout):
+        return labels
+    out = torch.empty((B, Hout, Wout), dtype=torch.uint8, device=labels.device)
+    _lib.check(_lib.load().dsee_resize_labels(_p(labels), _p(out), B, Hin, Win, Hout, Wout,
+                                              _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# operand builders
+# ---------------------------------------------------------------------------------------------
+def shared_mlp(labels, table, bias, ups=0, want_lo=True):
+    """relu(conv3x3(onehot(labels), W) + b) as a table gather. table fp32 [9,L,nh]."""
+    _chk_cuda(labels, table, bias)
+    B, Hl, Wl = labels.shape
+    _, L, nh = table.shape
+    H, W = Hl << ups, Wl << ups
+    hi = torch.empty((B, H, W, nh), dtype=torch.float16, device=labels.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    _lib.check(_lib.load().dsee_shared_mlp_fwd(_p(labels), _p(table), _p(bias), _p(hi), _p(lo), B, Hl,
+                                               Wl, ups, L, nh, _stream()))
+    return SplitPlanes(hi, lo)
+
+
+def style_gather(labels, style, want_lo=True):
+    """style_map[b,y,x,:] = style[b, labels[b,y,x], :]. style fp32 [B,L,d]."""
+    _chk_cuda(labels, style)
+    B, H, W = labels.shape
+    _, L, d = style.shape
+    hi = torch.empty((B, H, W, d), dtype=torch.float16, device=labels.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    _lib.check(_lib.load().dsee_style_gather_fwd(_p(labels), _p(style), _p(hi), _p(lo), B, H, W, L, d,
+                                                 _stream()))
+    return SplitPlanes(hi, lo)
+
+
+def prep_conv_weight(w, want_lo=True):
+    """fp32 [N,C,3,3] -> scaled fp16 split planes [N, 9*C] in (tap, c) order."""
+    _chk_cuda(w)
+    assert w.dtype == torch.float32 and w.dim() == 4 and w.shape[2:] == (3, 3)
+    N, Cin = w.shape[:2]
+    hi = torch.empty((N, 9 * Cin), dtype=torch.float16, device=w.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    inv = torch.empty(2, dtype=torch.float32, device=w.device)
+    _lib.check(_lib.load().dsee_prep_conv_weight(_p(w), _p(hi), _p(lo), _p(inv), N, Cin, _stream()))
+    return PreparedWeight(hi, lo, inv, N, Cin)
+
+
+def split_f16(x, want_lo=True):
+    _chk_cuda(x)
+    assert x.dtype == torch.float32
+    hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    _lib.check(_lib.load().dsee_split_f16(_p(x), _p(hi), _p(lo), x.numel(), _stream()))
+    return SplitPlanes(hi, lo)
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core kernels
+# ---------------------------------------------------------------------------------------------
+def _operands(sources, pw, passes):
+    a0 = sources[0]
+    B, H, W, C0 = a0.hi.shape
+    ops = _lib.ConvOperands()
+    ops.B, ops.H, ops.W = B, H, W
+    ctot = 0
+    keep = []
+    for i in range(2):
+        if i < len(sources):
+            s = sources[i]
+            _chk_cuda(s.hi, s.lo)
+            assert s.hi.dtype == torch.float16 and tuple(s.hi.shape[:3]) == (B, H, W)
+            ops.a_hi[i] = s.hi.data_ptr()
+            ops.a_lo[i] = s.lo.data_ptr() if s.lo is not None else 0
+            ops.a_channels[i] = s.hi.shape[3]
+            ctot += s.hi.shape[3]
+            keep.append(s)
+        else:
+            ops.a_hi[i] = 0
+            ops.a_lo[i] = 0
+            ops.a_channels[i] = 0
+    assert ctot == pw.cin, "weight prepared for %d input channels, operands have %d" % (pw.cin, ctot)
+    ops.w_hi = pw.hi.data_ptr()
+    ops.w_lo = pw.lo.data_ptr() if pw.lo is not None else 0
+    ops.w_inv_scale = pw.inv_scale.data_ptr()
+    ops.n_total = pw.n_total
+    ops.passes = passes
+    return ops, (B, H, W)
+
+
+def conv3x3(sources, pw, bias, residual=None, res_ups=0, passes=3, want_stats=False):
+    """K2: 3x3 conv (+bias, +residual through an optional folded 2x upsample) -> fp32 NHWC.
+
+    Returns out, or (out, stats_partial) when want_stats (partials for bn_finalize)."""
+    ops, (B, H, W) = _operands(sources, pw, passes)
+    _chk_cuda(bias, residual)
+    dev = sources[0].hi.device
+    out = torch.empty((B, H, W, pw.n_total), dtype=torch.float32, device=dev)
+    stats = None
+    if want_stats:
+        nt = _lib.load().dsee_conv3x3_stats_tiles(B, H, W)
+        stats = torch.empty((nt, pw.n_total, 2), dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().dsee_conv3x3_fwd(C.byref(ops), _p(bias), _p(residual), res_ups, _p(out),
+                                            _p(stats), _stream()))
+    return (out, stats) if want_stats else out
+
+
+def spade_modulate(sources, pw, x, x_ups, bn_scale, bn_shift, gamma_bias, beta_bias, noise=None,
+                   noise_w=None, passes=3, want_lo=True):
+    """K1: gamma/beta conv + batch-norm apply + modulation + LeakyReLU -> fp16 split planes."""
+    ops, (B, H, W) = _operands(sources, pw, passes)
+    _chk_cuda(x, bn_scale, bn_shift, gamma_bias, beta_bias, noise, noise_w)
+    Cc = x.shape[3]
+    assert tuple(x.shape[:3]) == (B, H >> x_ups, W >> x_ups)
+    dev = x.device
+    hi = torch.empty((B, H, W, Cc), dtype=torch.float16, device=dev)
+    lo = torch.empty_like(hi) if want_lo else None
+    m = _lib.ModulateArgs()
+    m.x, m.x_ups = x.data_ptr(), x_ups
+    m.noise = noise.data_ptr() if noise is not None else 0
+    m.noise_w = noise_w.data_ptr() if noise_w is not None else 0
+    m.bn_scale, m.bn_shift = bn_scale.data_ptr(), bn_shift.data_ptr()
+    m.gamma_bias, m.beta_bias = gamma_bias.data_ptr(), beta_bias.data_ptr()
+    m.out_hi = hi.data_ptr()
+    m.out_lo = lo.data_ptr() if lo is not None else 0
+    m.C = Cc
+    _lib.check(_lib.load().dsee_spade_modulate_fwd(C.byref(ops), C.byref(m), _stream()))
+    return SplitPlanes(hi, lo)
+
+
+# ---------------------------------------------------------------------------------------------
+# batch norm
+# ---------------------------------------------------------------------------------------------
+def bn_stats(x, x_ups=0, noise=None, noise_w=None):
+    """Tile partials [n,C,2] of per-channel sum / sum of squares of x (NHWC fp32)."""
+    _chk_cuda(x, noise, noise_w)
+    B, Hx, Wx, Cc = x.shape
+    H, W = Hx << x_ups, Wx << x_ups
+    n = C.c_int(0)
+    lib = _lib.load()
+    _lib.check(lib.dsee_bn_stats(C.c_void_p(0), x_ups, C.c_void_p(0), C.c_void_p(0), B, H, W, Cc,
+                                 C.c_void_p(0), C.byref(n), _stream()))
+    part = torch.empty((n.value, Cc, 2), dtype=torch.float32, device=x.device)
+    _lib.check(lib.dsee_bn_stats(_p(x), x_ups, _p(noise), _p(noise_w), B, H, W, Cc, _p(part),
+                                 C.byref(n), _stream()))
+    return part
+
+
+def bn_finalize(partials, count, eps, momentum=0.1, running_mean=None, running_var=None):
+    """-> (bn_scale, bn_shift, mean, var); updates running stats in place when given."""
+    _chk_cuda(partials, running_mean, running_var)
+    n, Cc, _ = partials.shape
+    dev = partials.device
+    sc = torch.empty(Cc, dtype=torch.float32, device=dev)
+    sh = torch.empty_like(sc)
+    mean = torch.empty_like(sc)
+    var = torch.empty_like(sc)
+    _lib.check(_lib.load().dsee_bn_finalize(_p(partials), n, Cc, float(count), float(eps),
+                                            float(momentum), _p(running_mean), _p(running_var),
+                                            _p(sc), _p(sh), _p(mean), _p(var), _stream()))
+    return sc, sh, mean, var
+
+
+def bn_eval_affine(running_mean, running_var, eps):
+    _chk_cuda(running_mean, running_var)
+    Cc = running_mean.numel()
+    sc = torch.empty(Cc, dtype=torch.float32, device=running_mean.device)
+    sh = torch.empty_like(sc)
+    _lib.check(_lib.load().dsee_bn_eval_affine(_p(running_mean), _p(running_var), float(eps), Cc,
+                                               _p(sc), _p(sh), _stream()))
+    return sc, sh
+
+
+# ---------------------------------------------------------------------------------------------
+# generator ends
+# ---------------------------------------------------------------------------------------------
+def stem(x_nchw, w, bias):
+    """DeepSEESR.initial: fp32 NCHW [B,3,H,W] -> fp32 NHWC [B,H,W,C]."""
+    _chk_cuda(x_nchw, w, bias)
+    B, _, H, W = x_nchw.shape
+    Cc = w.shape[0]
+    out = torch.empty((B, H, W, Cc), dtype=torch.float32, device=x_nchw.device)
+    _lib.check(_lib.load().dsee_stem_fwd(_p(x_nchw), _p(w), _p(bias), _p(out), B, H, W, Cc,
+                                         _stream()))
+    return out
+
+
+def head(x_nhwc, w, bias):
+    """tanh(conv_img(leaky_relu(x, 0.2))): fp32 NHWC [B,H,W,C] -> fp32 NCHW [B,3,H,W]."""
+    _chk_cuda(x_nhwc, w, bias)
+    B, H, W, Cc = x_nhwc.shape
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=x_nhwc.device)
+    _lib.check(_lib.load().dsee_head_fwd(_p(x_nhwc), _p(w), _p(bias), _p(out), B, H, W, Cc,
+                                         _stream()))
+    return out

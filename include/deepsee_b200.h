@@ -1,0 +1,171 @@
+/*
+ * deepsee_b200 C ABI  —  the drop-in boundary for DeepSEE's data-parallel hot path on B200.
+ *
+ * Every entry point takes raw DEVICE pointers, explicit shapes and a cudaStream_t (passed as
+ * void*), enqueues its work on that stream and returns without synchronising the host.
+ *   return 0   ok
+ *   return <0  invalid argument / unsupported device (message via dsee_last_error())
+ *   return >0  CUDA runtime error code (message via dsee_last_error())
+ * The library never allocates, frees or retains user-visible device memory: inputs, outputs
+ * and workspaces are owned by the caller (PyTorch's caching allocator).  No CPU fallback exists;
+ * on a non-sm_100 device every compute entry point fails with -2.
+ *
+ * Layouts.  Feature maps inside the path are NHWC ("pixels x channels"); the reference's
+ * NCHW fp32 tensors only appear at the two ends (stem input, image-head output, discriminator
+ * input).  Tensor-core operands are 16-bit "split planes": value = hi + lo with
+ * hi = fp16(value), lo = fp16(value - hi)  (3-pass product hi*hi + lo*hi + hi*lo ~ fp32
+ * accuracy; 1-pass hi*hi ~ TF32 accuracy).
+ *
+ * "Replaces" cites the reference interface (file:line under mcbuehler/DeepSEE) that each entry
+ * point stands in for.  The reference has no FFI of its own (it is 100 % Python calling ATen),
+ * so the binding a maintainer adds is the ctypes stub shown in INTEGRATION.md.
+ */
+#ifndef DEEPSEE_B200_H
+#define DEEPSEE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSEE_ABI_VERSION 1
+
+/* ---- library ------------------------------------------------------------------------------ */
+int dsee_version(void);
+/* thread-local, valid until the next failing call on this thread */
+const char* dsee_last_error(void);
+/* number of kernels this library has launched from this process (all threads) */
+int64_t dsee_launch_count(void);
+
+/* ---- label maps (bit-exact integer work) --------------------------------------------------- */
+/* Replaces data/preprocessor.py:35-41 (Preprocessor.preprocess_label):
+ * out[b,c,y,x] = (label[b,0,y,x] == c) ? 1.0f : 0.0f ; label int64 [B,1,H,W], out fp32 [B,L,H,W].
+ * A label outside [0,L) sets *bad_flag (device int) to 1 and writes zeros for that pixel. */
+int dsee_onehot_from_labels(const int64_t* label, float* out, int B, int L, int H, int W,
+                            int* bad_flag, void* stream);
+/* Inverse: fp32 one-hot [B,L,H,W] -> uint8 label map [B,H,W].  Pixels that are not exactly
+ * one-hot set *bad_flag to 1 (the conditional-norm kernels rely on the map being one-hot;
+ * normalization.py:110-114,174-185 consume it as conv input / region mask). */
+int dsee_labels_from_onehot(const float* onehot, uint8_t* labels, int B, int L, int H, int W,
+                            int* bad_flag, void* stream);
+/* Replaces F.interpolate(segmap, size, mode='nearest') normalization.py:110,174,261 and
+ * encoder.py:38,126 on the label map: out[b,y,x] = in[b, floor(y*Hin/Hout), floor(x*Win/Wout)]. */
+int dsee_resize_labels(const uint8_t* in, uint8_t* out, int B, int Hin, int Win, int Hout,
+                       int Wout, void* stream);
+
+/* ---- conditional-norm operand builders ------------------------------------------------------ */
+/* Replaces mlp_shared = Conv2d(L, nh, 3, pad 1) + ReLU over the one-hot map
+ * (normalization.py:98-101,114 / 149-152,175 / 239-242,262) as a 9-tap table gather:
+ *   actv[b,y,x,o] = relu(bias[o] + sum_tap table[tap][labels[b, yl+dy, xl+dx]][o]),
+ *   (yl,xl) = (y >> ups, x >> ups)   [ups=1 reproduces F.interpolate(actv, size=out_size),
+ *   normalization.py:188-189, for feature maps larger than max_fm_size]
+ * table fp32 [9][L][nh] (= weight[o][l][ky][kx] transposed), labels uint8 [B,Hl,Wl],
+ * out_hi/out_lo fp16 NHWC [B, Hl<<ups, Wl<<ups, nh]. out_lo may be NULL. */
+int dsee_shared_mlp_fwd(const uint8_t* labels, const float* table, const float* bias,
+                        void* out_hi, void* out_lo, int B, int Hl, int Wl, int ups, int L, int nh,
+                        void* stream);
+/* Replaces style_map = (style[:,:,:,None,None] * seg[:,:,None]).sum(1)
+ * (normalization.py:182-185 / 269-272): out[b,y,x,:] = style[b, labels[b,y,x], :].
+ * style fp32 [B,L,d]; out_hi/out_lo fp16 NHWC [B,H,W,d]. */
+int dsee_style_gather_fwd(const uint8_t* labels, const float* style, void* out_hi, void* out_lo,
+                          int B, int H, int W, int L, int d, void* stream);
+
+/* ---- tensor-core operand preparation -------------------------------------------------------- */
+/* Conv weight fp32 [N][C][3][3] (PyTorch layout; spectral normalisation already applied,
+ * architecture.py:40-44) -> GEMM B-operand planes fp16 [N][9*C] with k = (ky*3+kx)*C + c,
+ * multiplied by a power of two 2^e chosen so max|w|*2^e is in [2^13, 2^14) (keeps the lo plane
+ * out of the fp16 subnormal range). inv_scale is a device float[2]: [0] receives 2^-e (what the
+ * conv kernels read), [1] is scratch (max|w|). */
+int dsee_prep_conv_weight(const float* w, void* out_hi, void* out_lo, float* inv_scale, int N,
+                          int C, void* stream);
+/* fp32 NHWC [rows][C] -> fp16 split planes (used for tensors not produced by a fused epilogue). */
+int dsee_split_f16(const float* in, void* out_hi, void* out_lo, int64_t n, void* stream);
+
+/* ---- the fused tensor-core kernels ---------------------------------------------------------- */
+typedef struct {
+    /* geometry: stride-1 3x3 conv, zero padding 1, output size == input size */
+    int B, H, W;
+    /* A operand: 1 or 2 NHWC fp16 split-plane tensors concatenated along channels
+     * (channels multiple of 64; a_channels[1] may be 0). lo planes may be NULL iff passes==1. */
+    const void* a_hi[2];
+    const void* a_lo[2];
+    int a_channels[2];
+    /* B operand from dsee_prep_conv_weight: [n_total][9*(a_channels[0]+a_channels[1])] */
+    const void* w_hi;
+    const void* w_lo;
+    const float* w_inv_scale; /* device scalar */
+    int n_total;
+    int passes; /* 1: hi*hi (TF32-class accuracy)   3: hi*hi + lo*hi + hi*lo (fp32-class) */
+} dsee_conv_operands;
+
+/* K2.  Replaces conv_0 / conv_1 of SPADEResnetBlock (architecture.py:34-35,98,122) plus the
+ * residual add `out = x_s + dx` (architecture.py:127) and, in training mode, the first pass of the
+ * next batch norm (sync_batchnorm/batchnorm.py:72-76: sum and sum of squares per channel):
+ *   out[b,y,x,n] = bias[n] + sum_{tap,c} A[b,y+dy,x+dx,c] * w[n,c,tap]
+ *                  (+ residual[b, y>>res_ups, x>>res_ups, n])
+ * out fp32 NHWC [B,H,W,n_total]; residual fp32 NHWC [B,H>>res_ups,W>>res_ups,n_total] or NULL
+ * (res_ups=1 folds nn.Upsample(scale_factor=2) of the shortcut, sr.py:57,69,87);
+ * stats_partial: NULL or fp32 [tiles][n_total][2] workspace (dsee_conv3x3_stats_tiles() tiles),
+ * reduced deterministically by dsee_bn_finalize. */
+int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const float* bias, const float* residual,
+                     int res_ups, float* out, float* stats_partial, void* stream);
+int dsee_conv3x3_stats_tiles(int B, int H, int W);
+
+/* K1.  Replaces SPADE.forward (normalization.py:105-120), SEAN_Block.forward (:167-213) and
+ * PureSEAN_Block.forward (:254-286) together with the following actvn (architecture.py:96,114,147):
+ *   [gamma|beta][b,y,x,c] = conv3x3(A, w)        (n_total = 2*C; rows interleaved per 128 channels:
+ *                                                  [g(0..127) | b(0..127) | g(128..255) | ...])
+ *   xin  = x[b, y>>x_ups, x>>x_ups, c] (+ noise_w[c] * noise[b,y,x,c])     (normalization.py:299-304)
+ *   xhat = xin * bn_scale[c] + bn_shift[c]                                  (batchnorm.py:66,78-93)
+ *   t    = xhat * (gamma + gamma_bias[c]) + (beta + beta_bias[c])
+ *   out  = leaky_relu(t, 0.2) as fp16 split planes NHWC [B,H,W,C]
+ * gamma_bias carries the conv bias, the SEAN alpha blend of the two biases and the "+1"
+ * (absent for PureSEAN, normalization.py:286). The alpha blend of the weights
+ * (normalization.py:208-212) is folded into w by the caller. */
+typedef struct {
+    const float* x;      /* fp32 NHWC [B, H>>x_ups, W>>x_ups, C] */
+    int x_ups;           /* 0 or 1 */
+    const float* noise;  /* fp32 NHWC [B,H,W,C] or NULL */
+    const float* noise_w;/* fp32 [C] or NULL */
+    const float* bn_scale;
+    const float* bn_shift;
+    const float* gamma_bias;
+    const float* beta_bias;
+    void* out_hi;        /* fp16 NHWC [B,H,W,C] */
+    void* out_lo;        /* may be NULL */
+    int C;               /* multiple of 128 */
+} dsee_modulate_args;
+int dsee_spade_modulate_fwd(const dsee_conv_operands* ops, const dsee_modulate_args* mod,
+                            void* stream);
+
+/* ---- batch-norm statistics ------------------------------------------------------------------ */
+/* Per-channel sum / sum of squares of x (+ noise) at the post-upsample resolution, written as
+ * tile partials like the K2 epilogue does.  Replaces the statistics half of
+ * SynchronizedBatchNorm2d.forward (batchnorm.py:72-76) for tensors K2 did not produce. */
+int dsee_bn_stats(const float* x, int x_ups, const float* noise, const float* noise_w, int B, int H,
+                  int W, int C, float* stats_partial, int* n_partials, void* stream);
+/* Reduces partials [n_partials][C][2] in a fixed order (double accumulation) and produces
+ * bn_scale = 1/sqrt(var+eps), bn_shift = -mean*bn_scale; when running_mean/var are non-NULL also
+ * updates them with momentum and the unbiased variance (batchnorm.py:84-93). count = B*H*W. */
+int dsee_bn_finalize(const float* stats_partial, int n_partials, int C, double count, float eps,
+                     float momentum, float* running_mean, float* running_var, float* bn_scale,
+                     float* bn_shift, float* mean_out, float* var_out, void* stream);
+/* Eval mode: bn_scale/bn_shift from running statistics (batchnorm.py:65-68). */
+int dsee_bn_eval_affine(const float* running_mean, const float* running_var, float eps, int C,
+                        float* bn_scale, float* bn_shift, void* stream);
+
+/* ---- generator ends ------------------------------------------------------------------------- */
+/* Replaces DeepSEESR.initial (sr.py:31,65): conv 3->C 3x3 pad 1.
+ * x fp32 NCHW [B,3,H,W]; w fp32 [C,3,3,3]; out fp32 NHWC [B,H,W,C]. */
+int dsee_stem_fwd(const float* x, const float* w, const float* bias, float* out, int B, int H,
+                  int W, int C, void* stream);
+/* Replaces F.tanh(conv_img(F.leaky_relu(x, 0.2))) (sr.py:56,94-95).
+ * x fp32 NHWC [B,H,W,C]; w fp32 [3,C,3,3]; out fp32 NCHW [B,3,H,W]. */
+int dsee_head_fwd(const float* x, const float* w, const float* bias, float* out, int B, int H,
+                  int W, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPSEE_B200_H */

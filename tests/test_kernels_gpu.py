@@ -1,0 +1,180 @@
+"""Kernel-level parity (GPU): each C-ABI kernel against a plain PyTorch fp32 statement of the same
+op (TF32 disabled).  Tolerances are written next to each check."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 64, 256), (2, 16, 16, 128, 512),
+                                            (1, 32, 32, 512, 512), (1, 24, 40, 64, 32)])
+@pytest.mark.parametrize("passes", [1, 3])
+def test_conv3x3_matches_torch(B, H, W, Cin, Cout, passes):
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + H + Cin + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda()
+    bias = torch.randn(Cout, generator=g).cuda()
+    ref = F.conv2d(x, w, bias, padding=1)
+    a = ops.split_f16(_nhwc(x))
+    pw = ops.prep_conv_weight(w)
+    out = _nchw(ops.conv3x3([a], pw, bias, passes=passes))
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    # 3-pass split fp16 is fp32-class; 1-pass is TF32-class (10-bit mantissa operands)
+    tol = 5e-5 * scale if passes == 3 else 4e-3 * scale
+    assert err <= tol, (err, scale)
+
+
+def test_conv3x3_residual_upsample_and_stats():
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(7)
+    B, H, W, C = 2, 16, 32, 128
+    x = torch.randn(B, C, H, W, generator=g).cuda()
+    w = (torch.randn(256, C, 3, 3, generator=g) / (3 * C ** 0.5)).cuda()
+    bias = torch.randn(256, generator=g).cuda()
+    res = torch.randn(B, 256, H // 2, W // 2, generator=g).cuda()
+    ref = F.conv2d(x, w, bias, padding=1) + F.interpolate(res, scale_factor=2, mode="nearest")
+    a = ops.split_f16(_nhwc(x))
+    pw = ops.prep_conv_weight(w)
+    out, part = ops.conv3x3([a], pw, bias, residual=_nhwc(res), res_ups=1, passes=3, want_stats=True)
+    assert (_nchw(out) - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    sc, sh, mean, var = ops.bn_finalize(part, B * H * W, 1e-5)
+    torch.testing.assert_close(mean, ref.mean(dim=(0, 2, 3)), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(var, ref.var(dim=(0, 2, 3), unbiased=False), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("x_ups", [0, 1])
+@pytest.mark.parametrize("two_sources", [False, True])
+def test_spade_modulate_matches_torch(x_ups, two_sources):
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(11 + x_ups)
+    B, H, W, C, nh = 2, 16, 16, 256, 128
+    actv = torch.randn(B, nh, H, W, generator=g).relu().cuda()
+    sty = torch.randn(B, nh, H, W, generator=g).cuda()
+    Cin = nh * (2 if two_sources else 1)
+    wg = (torch.randn(C, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda()
+    wb = (torch.randn(C, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda()
+    gb = torch.randn(C, generator=g).cuda()
+    bb = torch.randn(C, generator=g).cuda()
+    x = torch.randn(B, C, H >> x_ups, W >> x_ups, generator=g).cuda()
+    rm = torch.randn(C, generator=g).cuda() * 0.1
+    rv = (torch.rand(C, generator=g) + 0.5).cuda()
+    noise = torch.randn(B, C, H, W, generator=g).cuda()
+    nw = torch.randn(C, generator=g).cuda() * 0.1
+
+    inp = torch.cat([actv, sty], 1) if two_sources else actv
+    gamma = F.conv2d(inp, wg, gb, padding=1)
+    beta = F.conv2d(inp, wb, bb, padding=1)
+    xin = F.interpolate(x, scale_factor=2, mode="nearest") if x_ups else x
+    xin = xin + nw.view(1, -1, 1, 1) * noise
+    xhat = F.batch_norm(xin, rm, rv, training=False, eps=1e-5)
+    ref = F.leaky_relu(xhat * (1 + gamma) + beta, 0.2)
+
+    # rows interleaved per 128 channels: [gamma(128) | beta(128)] ...
+    wcat = torch.stack([wg.view(C // 128, 128, Cin, 3, 3), wb.view(C // 128, 128, Cin, 3, 3)], 1)
+    wcat = wcat.reshape(2 * C, Cin, 3, 3).contiguous()
+    pw = ops.prep_conv_weight(wcat)
+    srcs = [ops.split_f16(_nhwc(actv))] + ([ops.split_f16(_nhwc(sty))] if two_sources else [])
+    sc, sh = ops.bn_eval_affine(rm, rv, 1e-5)
+    out = ops.spade_modulate(srcs, pw, _nhwc(x), x_ups, sc, sh, gb + 1.0, bb, noise=_nhwc(noise),
+                             noise_w=nw, passes=3)
+    got = _nchw(out.hi.float() + out.lo.float())
+    err = (got - ref).abs().max().item()
+    assert err <= 3e-5 * ref.abs().max().item(), err
+
+
+def test_label_ops_bit_exact():
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    B, L, S = 2, 19, 64
+    lab = torch.randint(0, L, (B, 1, S, S), generator=g).cuda()
+    oh, bad = ops.onehot_from_labels(lab, L)
+    ref = torch.zeros(B, L, S, S, device="cuda").scatter_(1, lab, 1.0)
+    assert torch.equal(oh, ref) and bad.item() == 0
+    back, bad2 = ops.labels_from_onehot(oh)
+    assert torch.equal(back.long(), lab[:, 0]) and bad2.item() == 0
+    for h in (32, 16, 48, 24):
+        small = ops.resize_labels(back, h, h)
+        refs = F.interpolate(oh, size=(h, h), mode="nearest").argmax(1)
+        assert torch.equal(small.long(), refs)
+    # a map that is not one-hot is reported
+    oh2 = oh.clone()
+    oh2[0, :, 0, 0] = 0.5
+    _, bad3 = ops.labels_from_onehot(oh2)
+    assert bad3.item() == 1
+
+
+@pytest.mark.parametrize("ups", [0, 1])
+def test_shared_mlp_and_style_gather(ups):
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, L, S, nh, d = 2, 19, 32, 128, 128
+    lab = torch.randint(0, L, (B, 1, S, S), generator=g).cuda()
+    oh = torch.zeros(B, L, S, S, device="cuda").scatter_(1, lab, 1.0)
+    w = torch.randn(nh, L, 3, 3, generator=g).cuda() * 0.2
+    b = torch.randn(nh, generator=g).cuda() * 0.1
+    ref = F.relu(F.conv2d(oh, w, b, padding=1))
+    if ups:
+        ref = F.interpolate(ref, scale_factor=2, mode="nearest")
+    table = w.permute(2, 3, 1, 0).reshape(9, L, nh).contiguous()
+    labels = lab[:, 0].to(torch.uint8).contiguous()
+    out = ops.shared_mlp(labels, table, b, ups=ups)
+    got = _nchw(out.hi.float() + out.lo.float())
+    assert (got - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())
+
+    style = torch.randn(B, L, d, generator=g).cuda()
+    ref_s = (style[:, :, :, None, None] * oh[:, :, None]).sum(1)
+    sm = ops.style_gather(labels, style)
+    got_s = _nchw(sm.hi.float() + sm.lo.float())
+    assert (got_s - ref_s).abs().max().item() <= 1e-6 * ref_s.abs().max().item()
+
+
+def test_stem_head_and_bn_stats():
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(9)
+    B, S, C = 2, 16, 512
+    x = torch.rand(B, 3, S, S, generator=g).cuda() * 2 - 1
+    w = torch.randn(C, 3, 3, 3, generator=g).cuda() * 0.2
+    b = torch.randn(C, generator=g).cuda() * 0.1
+    ref = F.conv2d(x, w, b, padding=1)
+    out = ops.stem(x, w, b)
+    assert (_nchw(out) - ref).abs().max().item() <= 1e-5
+
+    feat = torch.randn(B, 24, 20, C, generator=g).cuda()
+    wi = torch.randn(3, C, 3, 3, generator=g).cuda() * 0.01
+    bi = torch.randn(3, generator=g).cuda() * 0.1
+    refh = torch.tanh(F.conv2d(F.leaky_relu(_nchw(feat), 0.2), wi, bi, padding=1))
+    outh = ops.head(feat, wi, bi)
+    assert (outh - refh).abs().max().item() <= 2e-5
+
+    noise = torch.randn(B, 48, 40, C, generator=g).cuda()
+    nw = torch.randn(C, generator=g).cuda() * 0.3
+    part = ops.bn_stats(feat, x_ups=1, noise=noise, noise_w=nw)
+    rm = torch.zeros(C, device="cuda")
+    rv = torch.ones(C, device="cuda")
+    sc, sh, mean, var = ops.bn_finalize(part, B * 48 * 40, 1e-5, 0.1, rm, rv)
+    full = F.interpolate(_nchw(feat), scale_factor=2, mode="nearest") + nw.view(1, -1, 1, 1) * _nchw(noise)
+    bn = torch.nn.BatchNorm2d(C, affine=False).cuda().train()
+    bn(full)
+    torch.testing.assert_close(mean, full.mean(dim=(0, 2, 3)), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(var, full.var(dim=(0, 2, 3), unbiased=False), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rm, bn.running_mean, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rv, bn.running_var, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(sc, 1 / torch.sqrt(var + 1e-5), rtol=1e-5, atol=1e-6)
