@@ -19,6 +19,8 @@ SYMBOLS = [
     "dsee_conv3x3_fwd", "dsee_conv3x3_stats_tiles", "dsee_spade_modulate_fwd",
     "dsee_bn_stats", "dsee_bn_finalize", "dsee_bn_eval_affine",
     "dsee_stem_fwd", "dsee_head_fwd",
+    "dsee_conv2d_direct_fwd", "dsee_instance_norm_fwd", "dsee_region_pool_chunks",
+    "dsee_region_pool_fwd", "dsee_nchw_to_nhwc", "dsee_disc_input", "dsee_avgpool3s2_fwd",
 ]
 
 
@@ -28,6 +30,14 @@ class ConvOperands(C.Structure):
         ("a_hi", C.c_void_p * 2), ("a_lo", C.c_void_p * 2), ("a_channels", C.c_int * 2),
         ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("w_inv_scale", C.c_void_p),
         ("n_total", C.c_int), ("passes", C.c_int),
+    ]
+
+
+class ConvEpilogue(C.Structure):
+    _fields_ = [
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("res_ups", C.c_int),
+        ("noise", C.c_void_p * 2), ("noise_w", C.c_void_p * 2),
+        ("out", C.c_void_p), ("stats_partial", C.c_void_p),
     ]
 
 
@@ -67,14 +77,21 @@ def load():
         "dsee_style_gather_fwd": [vp, vp, vp, vp, i, i, i, i, i, vp],
         "dsee_prep_conv_weight": [vp, vp, vp, vp, i, i, vp],
         "dsee_split_f16": [vp, vp, vp, i64, vp],
-        "dsee_conv3x3_fwd": [C.POINTER(ConvOperands), vp, vp, i, vp, vp, vp],
+        "dsee_conv3x3_fwd": [C.POINTER(ConvOperands), C.POINTER(ConvEpilogue), vp],
         "dsee_conv3x3_stats_tiles": [i, i, i],
         "dsee_spade_modulate_fwd": [C.POINTER(ConvOperands), C.POINTER(ModulateArgs), vp],
         "dsee_bn_stats": [vp, i, vp, vp, i, i, i, i, vp, C.POINTER(C.c_int), vp],
-        "dsee_bn_finalize": [vp, i, i, d, f, f, vp, vp, vp, vp, vp, vp, vp],
+        "dsee_bn_finalize": [vp, i, i, d, d, f, f, vp, vp, vp, vp, vp, vp, vp],
         "dsee_bn_eval_affine": [vp, vp, f, i, vp, vp, vp],
         "dsee_stem_fwd": [vp, vp, vp, vp, i, i, i, i, vp],
         "dsee_head_fwd": [vp, vp, vp, vp, i, i, i, i, vp],
+        "dsee_conv2d_direct_fwd": [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, i, vp],
+        "dsee_instance_norm_fwd": [vp, vp, vp, vp, i, i, i, f, i, vp],
+        "dsee_region_pool_chunks": [i],
+        "dsee_region_pool_fwd": [vp, vp, vp, vp, i, i, i, i, vp],
+        "dsee_nchw_to_nhwc": [vp, vp, i, i, i, i, i, vp],
+        "dsee_disc_input": [vp, vp, vp, vp, i, i, i, i, i, vp],
+        "dsee_avgpool3s2_fwd": [vp, vp, i, i, i, i, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)

@@ -57,6 +57,8 @@ struct alignas(64) ConvParams {
     const float* bias;
     const float* residual;
     int res_ups;
+    const float* rnoise[2];
+    const float* rnoise_w[2];
     float* out;
     float* stats_partial;
     // EPI_MODULATE
@@ -275,6 +277,22 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                             }
                         }
 #pragma unroll
+                        for (int i2 = 0; i2 < 2; ++i2) {
+                            if (p.rnoise[i2]) {
+                                const float* nr = p.rnoise[i2] + pix * p.n_total + n;
+                                const float* nw = p.rnoise_w[i2] + n;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    float4 r = __ldg(reinterpret_cast<const float4*>(nr) + j);
+                                    float4 wv = __ldg(reinterpret_cast<const float4*>(nw) + j);
+                                    o[4 * j] += wv.x * r.x;
+                                    o[4 * j + 1] += wv.y * r.y;
+                                    o[4 * j + 2] += wv.z * r.z;
+                                    o[4 * j + 3] += wv.w * r.w;
+                                }
+                            }
+                        }
+#pragma unroll
                         for (int j = 0; j < 8; ++j)
                             reinterpret_cast<float4*>(orow + n)[j] =
                                 make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
@@ -459,22 +477,27 @@ extern "C" int dsee_conv3x3_stats_tiles(int B, int H, int W) {
     return B * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W) * 4;
 }
 
-extern "C" int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const float* bias,
-                                const float* residual, int res_ups, float* out,
-                                float* stats_partial, void* stream) {
+extern "C" int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_epilogue* epi,
+                                void* stream) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
     int rc = fill_common(p, ops);
     if (rc) return rc;
-    DSEE_CHECK_ARG(bias && out, "bias/out is NULL");
-    DSEE_CHECK_ARG(res_ups == 0 || res_ups == 1, "res_ups must be 0 or 1");
-    DSEE_CHECK_ARG(!residual || res_ups == 0 || (ops->H % 2 == 0 && ops->W % 2 == 0),
+    DSEE_CHECK_ARG(epi && epi->bias && epi->out, "epilogue/bias/out is NULL");
+    DSEE_CHECK_ARG(epi->res_ups == 0 || epi->res_ups == 1, "res_ups must be 0 or 1");
+    DSEE_CHECK_ARG(!epi->residual || epi->res_ups == 0 || (ops->H % 2 == 0 && ops->W % 2 == 0),
                    "folded upsample needs even H, W");
-    p.bias = bias;
-    p.residual = residual;
-    p.res_ups = res_ups;
-    p.out = out;
-    p.stats_partial = stats_partial;
+    for (int i = 0; i < 2; ++i) {
+        DSEE_CHECK_ARG((epi->noise[i] == nullptr) == (epi->noise_w[i] == nullptr),
+                       "noise[%d] and noise_w[%d] must be given together", i, i);
+        p.rnoise[i] = epi->noise[i];
+        p.rnoise_w[i] = epi->noise_w[i];
+    }
+    p.bias = epi->bias;
+    p.residual = epi->residual;
+    p.res_ups = epi->res_ups;
+    p.out = epi->out;
+    p.stats_partial = epi->stats_partial;
     return launch<EPI_CONV>(p, (cudaStream_t)stream);
 }
 

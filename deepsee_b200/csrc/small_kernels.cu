@@ -251,7 +251,8 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int x_ups, const fl
 
 // grid = C/32 blocks, block = 32 channels x 8 partial lanes; double accumulation, fixed order.
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int n_partials, int C,
-                                   double count, float eps, float momentum, float* running_mean,
+                                   double count, double ucount, float eps, float momentum,
+                                   float* running_mean,
                                    float* running_var, float* bn_scale, float* bn_shift,
                                    float* mean_out, float* var_out) {
     __shared__ double sh[8][32][2];
@@ -283,7 +284,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int n_part
         if (mean_out) mean_out[c] = (float)mean;
         if (var_out) var_out[c] = (float)var;
         if (running_mean) {
-            double unbias = count > 1.0 ? var * count / (count - 1.0) : var;
+            double unbias = ucount > 1.0 ? var * ucount / (ucount - 1.0) : var;
             running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
             running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbias;
         }
@@ -521,17 +522,18 @@ extern "C" int dsee_bn_stats(const float* x, int x_ups, const float* noise, cons
 }
 
 extern "C" int dsee_bn_finalize(const float* stats_partial, int n_partials, int C, double count,
-                                float eps, float momentum, float* running_mean, float* running_var,
-                                float* bn_scale, float* bn_shift, float* mean_out, float* var_out,
-                                void* stream) {
+                                double unbias_count, float eps, float momentum, float* running_mean,
+                                float* running_var, float* bn_scale, float* bn_shift, float* mean_out,
+                                float* var_out, void* stream) {
+    if (unbias_count <= 0) unbias_count = count;
     DSEE_CHECK_ARG(stats_partial && n_partials > 0 && C > 0 && count > 0 && bn_scale && bn_shift,
                    "bad argument");
     DSEE_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "running stats mismatch");
     int rc = require_sm100();
     if (rc) return rc;
     bn_finalize_kernel<<<cdiv(C, 32), 256, 0, (cudaStream_t)stream>>>(
-        stats_partial, n_partials, C, count, eps, momentum, running_mean, running_var, bn_scale,
-        bn_shift, mean_out, var_out);
+        stats_partial, n_partials, C, count, unbias_count, eps, momentum, running_mean, running_var,
+        bn_scale, bn_shift, mean_out, var_out);
     LAUNCH_END();
 }
 

@@ -1,0 +1,110 @@
+"""Multi-scale PatchGAN discriminator on the B200 kernels (reference:
+deepsee_models/networks/discriminator.py).
+
+``forward`` accepts what ``SRModel.discriminate`` builds.  The reference concatenates
+[one-hot semantics | image] on channels and fake | real on the batch (sr_model.py:655-664) into a
+fp32 NCHW tensor; here that tensor may be passed as-is (it is converted to NHWC once), or the
+fused ``ops.disc_input`` result (NHWC, channel-padded) can be passed through ``forward_nhwc``.
+Returned feature maps are NCHW views so the loss code reads like the reference's.
+"""
+import numpy as np
+import torch.nn as nn
+
+from ... import ops
+from .base_network import BaseNetwork
+from .encoder import _khwc
+from .normalization import get_nonspade_norm_layer, effective_weight
+
+
+class MultiscaleDiscriminator(BaseNetwork):
+    @staticmethod
+    def modify_commandline_options(parser, is_train):
+        parser.add_argument('--netD_subarch', type=str, default='n_layer')
+        parser.add_argument('--num_D', type=int, default=2)
+        NLayerDiscriminator.modify_commandline_options(parser, is_train)
+        return parser
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        for i in range(opt.num_D):
+            self.add_module('discriminator_%d' % i, self.create_single_discriminator(opt))
+
+    def create_single_discriminator(self, opt):
+        if opt.netD_subarch != 'n_layer':
+            raise ValueError('unrecognized discriminator subarchitecture %s' % opt.netD_subarch)
+        return NLayerDiscriminator(opt)
+
+    def downsample(self, x_nhwc):
+        """discriminator.py:46-49: avg_pool2d(3, stride 2, pad 1, count_include_pad=False)."""
+        return ops.avgpool3s2(x_nhwc)
+
+    def forward_nhwc(self, x_nhwc):
+        result = []
+        feats = not self.opt.no_ganFeat_loss
+        for name, D in self.named_children():
+            out = D.forward_nhwc(x_nhwc)
+            result.append(out if feats else [out[-1]])
+            x_nhwc = self.downsample(x_nhwc)
+        return result
+
+    def forward(self, input):
+        cp = (input.shape[1] + 3) // 4 * 4
+        res = self.forward_nhwc(ops.nchw_to_nhwc(input.contiguous().float(), cp))
+        return [[t.permute(0, 3, 1, 2) for t in scale] for scale in res]
+
+
+class NLayerDiscriminator(BaseNetwork):
+    @staticmethod
+    def modify_commandline_options(parser, is_train):
+        parser.add_argument('--n_layers_D', type=int, default=4)
+        return parser
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        kw = 4
+        padw = int(np.ceil((kw - 1.0) / 2))
+        nf = opt.ndf
+        input_nc = self.compute_D_input_nc(opt)
+        norm_layer = get_nonspade_norm_layer(opt, opt.norm_D)
+        sequence = [[nn.Conv2d(input_nc, nf, kernel_size=kw, stride=2, padding=padw),
+                     nn.LeakyReLU(0.2, False)]]
+        for n in range(1, opt.n_layers_D):
+            nf_prev = nf
+            nf = min(nf * 2, 512)
+            stride = 1 if n == opt.n_layers_D - 1 else 2
+            sequence += [[norm_layer(nn.Conv2d(nf_prev, nf, kernel_size=kw, stride=stride,
+                                               padding=padw)), nn.LeakyReLU(0.2, False)]]
+        sequence += [[nn.Conv2d(nf, 1, kernel_size=kw, stride=1, padding=padw)]]
+        for n in range(len(sequence)):
+            self.add_module('model' + str(n), nn.Sequential(*sequence[n]))
+        self.n_layers = opt.n_layers_D
+
+    def compute_D_input_nc(self, opt):
+        return opt.label_nc + opt.output_nc + (1 if opt.contain_dontcare_label else 0)
+
+    def forward_nhwc(self, x):
+        """x NHWC [B,H,W,Cp] (channels beyond input_nc are zero) -> list of NHWC feature maps."""
+        outs = []
+        conv0 = self.model0[0]
+        x = ops.conv2d_direct(x, _khwc(conv0.weight.detach(), x.shape[3]), conv0.bias, stride=2,
+                              pad=2, lrelu=True)
+        outs.append(x)
+        for n in range(1, self.n_layers):
+            seq = getattr(self, 'model%d' % n)[0]  # Sequential(spectral conv, InstanceNorm2d)
+            conv = seq[0]
+            stride = 1 if n == self.n_layers - 1 else 2
+            y = ops.conv2d_direct(x, _khwc(effective_weight(conv).detach()), None, stride=stride, pad=2)
+            x, _, _ = ops.instance_norm(y, 1)
+            outs.append(x)
+        last = getattr(self, 'model%d' % self.n_layers)[0]
+        x = ops.conv2d_direct(x, _khwc(last.weight.detach()), last.bias, stride=1, pad=2)
+        outs.append(x)
+        return outs
+
+    def forward(self, input):
+        cp = (input.shape[1] + 3) // 4 * 4
+        outs = self.forward_nhwc(ops.nchw_to_nhwc(input.contiguous().float(), cp))
+        outs = [t.permute(0, 3, 1, 2) for t in outs]
+        return outs if not self.opt.no_ganFeat_loss else outs[-1]

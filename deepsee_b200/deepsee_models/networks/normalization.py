@@ -1,0 +1,256 @@
+"""Conditional normalisation layers of the generator (SPADE / SEAN / PureSEAN), noise injection
+and the spectral+instance wrapper used by the encoder and discriminator.
+
+Same class names, constructor signatures and ``state_dict`` keys as the reference
+(deepsee_models/networks/normalization.py), but the layers do not compute with ATen: each one
+only *describes* its work to the fused K1 kernel (``ops.spade_modulate``):
+
+  * ``mlp_shared`` (conv 19->128 over a one-hot map + ReLU) becomes a 9-tap table gather on the
+    uint8 label map (``ops.shared_mlp``), exact because every input pixel has one non-zero channel;
+  * ``style_map`` (normalization.py:182-185) becomes a gather ``style[b, label]``
+    (``ops.style_gather``) - the [B,19,128,H,W] product is never formed;
+  * the alpha blend of the SEAN branches (normalization.py:208-213) is folded into one weight
+    matrix over the concatenated [actv | style_map] channels, gamma/beta rows interleaved per
+    128 channels so one accumulator tile holds both;
+  * batch norm, ``x_hat * (1 + gamma) + beta`` and LeakyReLU run in the kernel epilogue.
+"""
+import re
+
+import torch
+import torch.nn as nn
+import torch.nn.utils.spectral_norm as spectral_norm
+
+from ... import ops
+
+NHIDDEN = 128  # normalization.py:95 ("Yes, hardcoded.")
+BN_EPS = 1e-5
+
+
+def effective_weight(conv):
+    """Weight a (possibly spectral-normalised) conv would use in its forward: runs torch's
+    spectral-norm pre-forward hook (one power iteration in training mode, W_orig / sigma) without
+    running the conv (architecture.py:40-44; torch/nn/utils/spectral_norm.py)."""
+    for hook in conv._forward_pre_hooks.values():
+        hook(conv, None)
+    return conv.weight
+
+
+def get_nonspade_norm_layer(opt, norm_type='instance', oneD=False):
+    """normalization.py:19-54: spectral norm on the layer, bias removed, followed by a
+    parameter-free norm layer. Returns nn.Sequential(layer, norm) so the state_dict keys match;
+    the encoder / discriminator forward read the parameters and call the CUDA kernels."""
+    def get_out_channel(layer):
+        return getattr(layer, 'out_channels', None) or layer.weight.size(0)
+
+    def add_norm_layer(layer):
+        subnorm_type = norm_type
+        if norm_type.startswith('spectral'):
+            layer = spectral_norm(layer)
+            subnorm_type = norm_type[len('spectral'):]
+        if subnorm_type == 'none' or len(subnorm_type) == 0:
+            return layer
+        if getattr(layer, 'bias', None) is not None:
+            delattr(layer, 'bias')
+            layer.register_parameter('bias', None)
+        if subnorm_type == 'instance':
+            norm_layer = nn.InstanceNorm1d(get_out_channel(layer), affine=False) if oneD \
+                else nn.InstanceNorm2d(get_out_channel(layer), affine=False)
+        else:
+            raise ValueError('normalization layer %s is not supported by the B200 path '
+                             '(reference default is spectralinstance)' % subnorm_type)
+        return nn.Sequential(layer, norm_layer)
+
+    return add_norm_layer
+
+
+class GenContext:
+    """Per-forward conditioning state: the uint8 label map at every resolution it is needed at
+    (always resized from the full-resolution map, like F.interpolate(segmap, ...) at
+    normalization.py:110,174,261) and the style matrix."""
+
+    def __init__(self, labels_full, style):
+        self.labels_full = labels_full  # uint8 [B,S,S]
+        self.style = style              # fp32 [B,L,d] or None
+        self._cache = {}
+
+    def labels_at(self, h, w):
+        key = (h, w)
+        if key not in self._cache:
+            self._cache[key] = ops.resize_labels(self.labels_full, h, w)
+        return self._cache[key]
+
+
+def _interleave_gamma_beta(wg, wb):
+    """[C,Cin,3,3] x2 -> [2C,Cin,3,3] with rows [g(0..127) | b(0..127) | g(128..255) | ...]."""
+    C = wg.shape[0]
+    t = torch.stack([wg.view(C // 128, 128, *wg.shape[1:]), wb.view(C // 128, 128, *wb.shape[1:])], 1)
+    return t.reshape(2 * C, *wg.shape[1:]).contiguous()
+
+
+def _param_free_norm(config_text, pattern, norm_nc):
+    parsed = re.search(pattern, config_text)
+    kind = str(parsed.group(1))
+    ks = int(parsed.group(2))
+    if ks != 3:
+        raise ValueError('the B200 path implements 3x3 modulation convs (got %dx%d)' % (ks, ks))
+    if 'batch' not in kind:
+        raise ValueError('%s is not a supported param-free norm type (batch / syncbatch)' % kind)
+    # SynchronizedBatchNorm2d(affine=False) keys: running_mean / running_var / num_batches_tracked
+    return nn.BatchNorm2d(norm_nc, affine=False)
+
+
+class _CondNormBase(nn.Module):
+    """Shared machinery: table for mlp_shared, BN scale/shift, prepared-weight cache."""
+    kind = None
+
+    def _table(self):
+        w = self.mlp_shared[0].weight  # [nh, L, 3, 3] -> [9, L, nh]
+        return w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]).contiguous()
+
+    def fm_size(self, H, W):
+        mx = getattr(self.opt, 'max_fm_size', 1 << 30) if self.kind != 'spade' else 1 << 30
+        return min(H, mx), min(W, mx)
+
+    def build_sources(self, ctx, H, W, want_lo):
+        """-> list of SplitPlanes feeding K1's A operand at resolution (H, W)."""
+        fh, fw = self.fm_size(H, W)
+        if (fh, fw) == (H, W):
+            ups = 0
+        elif (fh * 2, fw * 2) == (H, W):
+            ups = 1
+        else:
+            raise NotImplementedError('feature map %dx%d vs max_fm_size %dx%d: only 1x / 2x '
+                                      'supported' % (H, W, fh, fw))
+        labels = ctx.labels_at(fh, fw)
+        need_actv = self.kind in ('spade', 'sean') or ups == 1
+        actv = None
+        if need_actv:
+            actv = ops.shared_mlp(labels, self._table(), self.mlp_shared[0].bias, ups=ups,
+                                  want_lo=want_lo)
+        if self.kind == 'spade':
+            return [actv]
+        if ups == 1:
+            # normalization.py:188-190 / 275-277: style_map := upsampled actv (style is dropped)
+            style_map = actv
+        else:
+            if ctx.style is None:
+                raise RuntimeError('%s needs a style matrix z' % type(self).__name__)
+            style_map = ops.style_gather(labels, ctx.style, want_lo=want_lo)
+        return [actv, style_map] if self.kind == 'sean' else [style_map]
+
+    def combined_weight(self):
+        """-> (W [2C, Cin_total, 3, 3] rows interleaved, gamma_bias [C], beta_bias [C]); plain
+        torch ops so autograd carries gradients back to the individual parameters."""
+        if self.kind == 'spade':
+            wg, wb = self.mlp_gamma.weight, self.mlp_beta.weight
+            gb, bb = self.mlp_gamma.bias + 1.0, self.mlp_beta.bias
+        elif self.kind == 'sean':
+            a_b = torch.sigmoid(self.alpha_beta)
+            a_g = torch.sigmoid(self.alpha_gamma)
+            wg = torch.cat([(1.0 - a_g) * self.mlp_gamma.weight, a_g * self.mlp_style_gamma.weight], 1)
+            wb = torch.cat([(1.0 - a_b) * self.mlp_beta.weight, a_b * self.mlp_style_beta.weight], 1)
+            gb = (1.0 - a_g) * self.mlp_gamma.bias + a_g * self.mlp_style_gamma.bias + 1.0
+            bb = (1.0 - a_b) * self.mlp_beta.bias + a_b * self.mlp_style_beta.bias
+        else:  # puresean: no "+1" (normalization.py:286)
+            wg, wb = self.mlp_style_gamma.weight, self.mlp_style_beta.weight
+            gb, bb = self.mlp_style_gamma.bias, self.mlp_style_beta.bias
+        return _interleave_gamma_beta(wg, wb), gb.contiguous(), bb.contiguous()
+
+    def _cache_key(self, want_lo):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + (want_lo,)
+
+    def prepared(self, want_lo):
+        """Prepared (fp16 split, scaled) modulation weight + biases. Cached while the parameters
+        are unchanged (inference); rebuilt every call when they carry gradients."""
+        key = self._cache_key(want_lo)
+        cached = getattr(self, '_prep_cache', None)
+        if cached is not None and cached[0] == key and not torch.is_grad_enabled():
+            return cached[1]
+        with torch.no_grad():
+            w, gb, bb = self.combined_weight()
+            val = (ops.prep_conv_weight(w, want_lo=want_lo), gb, bb)
+        self._prep_cache = (key, val)
+        return val
+
+    def eval_affine(self):
+        bn = self.param_free_norm
+        return ops.bn_eval_affine(bn.running_mean, bn.running_var, BN_EPS)
+
+    def forward(self, x, segmap, style=None):
+        raise RuntimeError('%s is driven through SPADEResnetBlock on the B200 path; it has no '
+                           'standalone ATen forward' % type(self).__name__)
+
+
+class SPADE(_CondNormBase):
+    """normalization.py:71-120."""
+    kind = 'spade'
+
+    def __init__(self, config_text, norm_nc, label_nc, opt):
+        super().__init__()
+        assert config_text.startswith('spade') or config_text.startswith('latesean')
+        pattern = r'latesean(\D+)(\d)x\d' if config_text.startswith('latesean') else r'spade(\D+)(\d)x\d'
+        self.opt = opt
+        self.nc = label_nc
+        self.param_free_norm = _param_free_norm(config_text, pattern, norm_nc)
+        self.mlp_shared = nn.Sequential(nn.Conv2d(label_nc, NHIDDEN, kernel_size=3, padding=1), nn.ReLU())
+        self.mlp_gamma = nn.Conv2d(NHIDDEN, norm_nc, kernel_size=3, padding=1)
+        self.mlp_beta = nn.Conv2d(NHIDDEN, norm_nc, kernel_size=3, padding=1)
+
+
+class SEAN_Block(_CondNormBase):
+    """normalization.py:123-213."""
+    kind = 'sean'
+
+    def __init__(self, config_text, norm_nc, label_nc, opt):
+        super().__init__()
+        assert 'sean' in config_text
+        self.opt = opt
+        self.efficient = opt.efficient
+        self.nc = label_nc
+        self.style_size = opt.regional_style_size
+        self.param_free_norm = _param_free_norm(config_text, r'sean(\D+)(\d)x\d', norm_nc)
+        self.mlp_shared = nn.Sequential(nn.Conv2d(label_nc, NHIDDEN, kernel_size=3, padding=1), nn.ReLU())
+        self.mlp_gamma = nn.Conv2d(NHIDDEN, norm_nc, kernel_size=3, padding=1)
+        self.mlp_beta = nn.Conv2d(NHIDDEN, norm_nc, kernel_size=3, padding=1)
+        self.style_conv = nn.Conv1d(19, 19, kernel_size=1)  # unused by the reference forward too
+        self.mlp_style_gamma = nn.Conv2d(self.style_size, norm_nc, kernel_size=3, padding=1)
+        self.mlp_style_beta = nn.Conv2d(self.style_size, norm_nc, kernel_size=3, padding=1)
+        self.alpha_beta = nn.Parameter(torch.rand(1), requires_grad=True)
+        self.alpha_gamma = nn.Parameter(torch.rand(1), requires_grad=True)
+        self.mp = opt.model_parallel_mode
+
+
+class PureSEAN_Block(_CondNormBase):
+    """normalization.py:216-286."""
+    kind = 'puresean'
+
+    def __init__(self, config_text, norm_nc, label_nc, opt):
+        super().__init__()
+        assert 'sean' in config_text
+        self.opt = opt
+        self.efficient = opt.efficient
+        self.nc = label_nc
+        self.style_size = opt.regional_style_size
+        self.param_free_norm = _param_free_norm(config_text, r'sean(\D+)(\d)x\d', norm_nc)
+        self.mlp_shared = nn.Sequential(nn.Conv2d(label_nc, NHIDDEN, kernel_size=3, padding=1), nn.ReLU())
+        self.style_conv = nn.Conv1d(19, 19, kernel_size=1)
+        self.mlp_style_gamma = nn.Conv2d(self.style_size, norm_nc, kernel_size=3, padding=1)
+        self.mlp_style_beta = nn.Conv2d(self.style_size, norm_nc, kernel_size=3, padding=1)
+        self.mp = opt.model_parallel_mode
+
+
+class NoiseInjection(nn.Module):
+    """normalization.py:289-304. Holds the per-channel weight; the add itself is fused into the
+    K1 / K2 epilogues. ``sample`` draws the noise tensor (NHWC) - tests replace it to replay the
+    reference's noise."""
+
+    def __init__(self, n_channels):
+        super().__init__()
+        self.n_channels = n_channels
+        self.weight = nn.Parameter(torch.zeros(self.n_channels), requires_grad=True)
+
+    def sample(self, B, H, W):
+        return torch.randn((B, H, W, self.n_channels), dtype=torch.float32, device=self.weight.device)
+
+    def forward(self, tensor, noise=None):
+        raise RuntimeError('NoiseInjection is fused into the conv epilogues on the B200 path')

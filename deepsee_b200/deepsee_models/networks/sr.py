@@ -1,0 +1,74 @@
+"""DeepSEESR generator on the B200 kernels (reference: deepsee_models/networks/sr.py:10-98).
+
+Same constructor, ``forward(x_downsized, seg, z)`` signature, module names and state_dict keys as
+the reference; NCHW fp32 in (LR image, one-hot semantics), NCHW fp32 out.  Inside, activations are
+NHWC and never upsampled in memory: every ``self.up`` of the reference is folded into the next
+block's kernels (K1 reads x at (y>>1, x>>1), K2 reads the shortcut the same way).
+The reference's model-parallel modes (sr.py:73-92) are dropped: one B200 holds the 512x512 model.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...config import config
+from .architecture import SPADEResnetBlock
+from .base_network import BaseNetwork
+from .normalization import GenContext
+
+
+class DeepSEESR(BaseNetwork):
+    @staticmethod
+    def modify_commandline_options(parser, is_train):
+        parser.add_argument('--num_upsampling_layers', choices=('normal', 'more', 'most'),
+                            default='normal')
+        return parser
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        nf = opt.ngf
+        self.start_size = opt.start_size
+        self.n_blocks = int(np.log2(opt.crop_size) - np.log2(self.start_size))
+        self.sw, self.sh = self.compute_latent_vector_size(opt)
+        if getattr(opt, 'model_parallel_mode', 0):
+            raise NotImplementedError('model_parallel_mode is replaced by data parallelism on B200 '
+                                      '(180 GB HBM holds the 512x512 model); use mode 0')
+        self.initial = nn.Conv2d(3, 16 * nf, 3, padding=1)
+        early_style = not ("late" in self.opt.norm_G)
+        self.head_0 = SPADEResnetBlock(16 * nf, 16 * nf, opt, style=early_style)
+        self.G_middle_0 = SPADEResnetBlock(16 * nf, 16 * nf, opt, style=True)
+        self.G_middle_1 = SPADEResnetBlock(16 * nf, 16 * nf, opt, style=True)
+        self.mp = 0
+        max_n_blocks = 4 if self.opt.load_size >= 512 else 99  # sr.py:41-43
+        ups = [SPADEResnetBlock(16 * nf, 16 * nf, opt, style=True)
+               for _ in range(1, min(self.n_blocks, max_n_blocks))]
+        if max_n_blocks != 99:
+            for _ in range(max_n_blocks, self.n_blocks):  # 512 and 1024: PureSEAN tail (sr.py:48-51)
+                ups.append(SPADEResnetBlock(16 * nf, 16 * nf, opt, style=True, puresean=True))
+        self.up_list = nn.ModuleList(ups)
+        self.conv_img = nn.Conv2d(16 * nf, 3, 3, padding=1)
+        self.up = nn.Upsample(scale_factor=2)  # kept for module-tree parity; folded, never run
+
+    def get_device(self):
+        return self.initial.weight.device
+
+    def forward(self, x_downsized, seg=None, z=None):
+        if not x_downsized.is_cuda:
+            raise RuntimeError('DeepSEESR (B200 path) needs CUDA tensors; there is no CPU fallback')
+        x_downsized = x_downsized.contiguous().float()
+        seg = seg.contiguous().float()
+        labels, bad = ops.labels_from_onehot(seg)
+        ctx = GenContext(labels, z.contiguous().float() if z is not None else None)
+
+        x = ops.stem(x_downsized, self.initial.weight.contiguous(), self.initial.bias)
+        x, st = self.head_0.forward_nhwc(x, ctx, ups=0)
+        x, st = self.G_middle_0.forward_nhwc(x, ctx, ups=1, stats_in=st)
+        x, st = self.G_middle_1.forward_nhwc(x, ctx, ups=0, stats_in=st)
+        for i in range(self.n_blocks - 1):
+            x, st = self.up_list[i].forward_nhwc(x, ctx, ups=1, stats_in=st)
+        out = ops.head(x, self.conv_img.weight.contiguous(), self.conv_img.bias)
+        if config.check_onehot and int(bad.item()) != 0:
+            raise ValueError('DeepSEESR: `seg` must be a one-hot map (exactly one 1.0 per pixel); '
+                             'the B200 path consumes it as an integer label map')
+        return out

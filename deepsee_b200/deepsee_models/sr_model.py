@@ -1,0 +1,255 @@
+"""SRModel facade (reference: deepsee_models/sr_model.py).
+
+Same constructor, ``forward(data, mode)`` dispatch, return structures, optimizer setup and
+checkpoint naming as the reference, so managers / train.py / demo.py drive it unchanged; the
+networks underneath run on the deepsee_b200 CUDA kernels.  Differences, all deliberate:
+  * one process per GPU: the model lives on the current CUDA device, `model_parallel_mode` and
+    DataParallel are gone (data parallelism = one SRModel per rank + NCCL gradient all-reduce,
+    see managers/base_manager.py);
+  * the [seg | image] / fake | real concatenations of `discriminate` are one fused kernel;
+  * the demo-only style-manipulation modes (sr_model.py:116-444) are not part of the hot path;
+    'inference_noise' is kept, the others raise NotImplementedError.
+"""
+import random
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+
+from . import networks
+from .. import ops
+from ..util import util
+
+
+class SRModel(torch.nn.Module):
+    @staticmethod
+    def modify_commandline_options(parser, is_train):
+        networks.modify_commandline_options(parser, is_train)
+        return parser
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.use_E = opt.netE is not None and len(opt.netE)
+        self.netSR, self.netD, self.netE = self.initialize_networks(opt)
+        self.mp = 0
+        self.model_variant = "guided" if "full" in self.opt.netE else "independent"
+        if opt.isTrain:
+            self.criterionGAN = networks.GANLoss(opt.gan_mode, opt=self.opt)
+            self.criterionFeat = torch.nn.L1Loss()
+            if not opt.no_vgg_loss:
+                self.criterionVGG = networks.VGGLoss(self.opt.gpu_ids)
+        self.logs = OrderedDict()
+        self.last_encoded_style_is_full = True
+        self.last_encoded_style_is_noisy = False
+
+    def load_weights(self):
+        opt = self.opt
+        if not opt.isTrain or opt.continue_train:
+            self.netSR = util.load_network(self.netSR, 'SR', opt.which_epoch, opt)
+            if opt.isTrain:
+                self.netD = util.load_network(self.netD, 'D', opt.which_epoch, opt)
+            if self.use_E:
+                self.netE = util.load_network(self.netE, 'E', opt.which_epoch, opt)
+
+    def get_logs(self):
+        return self.logs
+
+    def forward(self, data, mode, **kwargs):
+        input_semantics = data.get("input_semantics", None)
+        image_lr = data.get("image_lr", None)
+        image_hr = data.get("image_hr", None)
+        guiding_image = data.get("guiding_image", None)
+        guiding_label = data.get("guiding_label", None)
+        encoded_style = data.get("encoded_style", None)
+        if mode == 'generator':
+            g_loss, generated = self.compute_generator_loss(
+                input_semantics, image_hr, image_lr, guiding_image, guiding_label)
+            self.logs['image/downsized'] = image_lr
+            return g_loss, generated
+        elif mode == 'discriminator':
+            return self.compute_discriminator_loss(
+                input_semantics, image_hr, image_lr, guiding_image, guiding_label)
+        elif mode == 'inference':
+            with torch.no_grad():
+                fake_image, _, _ = self.generate_fake(
+                    input_semantics=input_semantics, image_downsized=image_lr, full_image=image_hr,
+                    no_noise=True, guiding_image=guiding_image, guiding_label=guiding_label)
+            data["fake_image"] = fake_image
+            return util.filter_none(data)
+        elif mode == 'encode_only':
+            encoded_style, _ = self.encode_style(
+                downscaled_image=image_lr, input_semantics=input_semantics, full_image=image_hr,
+                no_noise=True, guiding_image=guiding_image, guiding_label=guiding_label,
+                encode_full=self.opt.full_style_image)
+            return encoded_style
+        elif mode == 'demo':
+            with torch.no_grad():
+                fake_image = self.netSR(image_lr, seg=input_semantics, z=encoded_style)
+            out = data
+            out["fake_image"] = fake_image
+            return util.filter_none(out)
+        elif mode == 'baseline':
+            image_baseline = F.interpolate(image_lr, (image_hr.shape[-2:]), mode='bicubic').clamp(-1, 1)
+            return OrderedDict([("input_label", input_semantics), ("image_downsized", image_lr),
+                                ("fake_image", image_baseline), ("image_full", image_hr)])
+        elif mode == "inference_noise":
+            with torch.no_grad():
+                n = self.opt.batchSize
+                lr_rep = image_lr.repeat_interleave(n, 0)
+                sem_rep = input_semantics.repeat_interleave(n, 0)
+                fake_image, _, _ = self.generate_fake(input_semantics=sem_rep, image_downsized=lr_rep,
+                                                      encoded_style=None)
+                fake_image = torch.stack([fake_image[i * n:i * n + n] for i in range(n)], dim=0)
+                return OrderedDict([("input_label", input_semantics), ("image_downsized", image_lr),
+                                    ("fake_image", fake_image), ("image_full", image_hr)])
+        elif mode.startswith("inference_"):
+            raise NotImplementedError(
+                "mode %r is a demo-only style manipulation of the reference (sr_model.py:116-444) "
+                "and is not part of the B200 hot path" % mode)
+        else:
+            raise ValueError("|mode| is invalid")
+
+    def create_optimizers(self, opt):
+        """sr_model.py:469-495: Adam; TTUR lr/2 for G (+E), 2*lr for D; "mini" params at lr_G/4."""
+        SR_params = list(self.netSR.parameters())
+        SR_params_low_lr = list()
+        if self.use_E:
+            for name, param in self.netE.named_parameters():
+                (SR_params_low_lr if "mini" in name else SR_params).append(param)
+        D_params = list(self.netD.parameters()) if opt.isTrain else []
+        beta1, beta2 = opt.beta1, opt.beta2
+        SR_lr, D_lr = (opt.lr, opt.lr) if opt.no_TTUR else (opt.lr / 2, opt.lr * 2)
+        print("lr G: {}, lr D: {}".format(SR_lr, D_lr))
+        optimizer_SR = torch.optim.Adam([{"params": SR_params},
+                                         {"params": SR_params_low_lr, "lr": SR_lr / 4}],
+                                        lr=SR_lr, betas=(beta1, beta2))
+        optimizer_D = torch.optim.Adam(D_params, lr=D_lr, betas=(beta1, beta2))
+        return optimizer_SR, optimizer_D
+
+    def save(self, epoch):
+        util.save_network(self.netSR, 'SR', epoch, self.opt)
+        util.save_network(self.netD, 'D', epoch, self.opt)
+        if self.use_E:
+            util.save_network(self.netE, 'E', epoch, self.opt)
+
+    # ------------------------------------------------------------------------------------------
+    def initialize_networks(self, opt):
+        self.netSR = networks.define_SR(opt)
+        self.netD = networks.define_D(opt) if opt.isTrain else None
+        self.netE = networks.define_E(opt) if self.use_E else None
+        self.load_weights()
+        return self.netSR, self.netD, self.netE
+
+    def compute_generator_loss(self, input_semantics, image_full, image_downsized, guiding_image,
+                               guiding_label):
+        """sr_model.py:518-545."""
+        SR_losses = {}
+        style_image = guiding_image if self.opt.guiding_style_image else image_full
+        fake_image, _, _ = self.generate_fake(
+            input_semantics=input_semantics, image_downsized=image_downsized,
+            full_image=style_image, guiding_image=guiding_image, guiding_label=guiding_label)
+        pred_fake, pred_real = self.discriminate(input_semantics, fake_image, image_full)
+        SR_losses['GAN'] = self.criterionGAN(pred_fake, True, for_discriminator=False)
+        if not self.opt.no_ganFeat_loss:
+            num_D = len(pred_fake)
+            GAN_Feat_loss = torch.zeros(1, device=fake_image.device)
+            for i in range(num_D):
+                for j in range(len(pred_fake[i]) - 1):  # last output is the prediction itself
+                    unweighted = self.criterionFeat(pred_fake[i][j], pred_real[i][j].detach())
+                    GAN_Feat_loss = GAN_Feat_loss + unweighted * self.opt.lambda_feat / num_D
+            SR_losses['GAN_Feat'] = GAN_Feat_loss
+        if not self.opt.no_vgg_loss:
+            SR_losses['VGG'] = self.criterionVGG(fake_image, image_full) * self.opt.lambda_vgg
+        return SR_losses, fake_image
+
+    def compute_discriminator_loss(self, input_semantics, image_full, image_downsized,
+                                   guiding_image, guiding_label):
+        """sr_model.py:547-564."""
+        D_losses = {}
+        with torch.no_grad():
+            fake_image, _, _ = self.generate_fake(
+                input_semantics=input_semantics, image_downsized=image_downsized,
+                full_image=image_full, guiding_image=guiding_image, guiding_label=guiding_label)
+            fake_image = fake_image.detach()
+        fake_image.requires_grad_()
+        pred_fake, pred_real = self.discriminate(input_semantics, fake_image, image_full)
+        D_losses['D_Fake'] = self.criterionGAN(pred_fake, False, for_discriminator=True)
+        D_losses['D_Real'] = self.criterionGAN(pred_real, True, for_discriminator=True)
+        return D_losses
+
+    def generate_fake(self, input_semantics, image_downsized, encoded_style=None, full_image=None,
+                      no_noise=False, guiding_image=None, guiding_label=None):
+        """sr_model.py:566-580."""
+        encoder_activations = None
+        if encoded_style is None and "style" in self.opt.netE:
+            encoded_style, encoder_activations = self.encode_style(
+                downscaled_image=image_downsized, input_semantics=input_semantics,
+                full_image=full_image, no_noise=no_noise, guiding_image=guiding_image,
+                guiding_label=guiding_label, encode_full=self.opt.full_style_image)
+        fake_image = self.netSR(image_downsized, seg=input_semantics, z=encoded_style)
+        return fake_image, encoder_activations, encoded_style
+
+    def get_encoder_inputs(self, downscaled_image=None, input_semantics=None, full_image=None,
+                           encode_full=False, guiding_image=None, guiding_label=None):
+        """sr_model.py:582-632. The coin flip uses Python's `random` like the reference; under
+        data parallelism every rank seeds it identically (managers/base_manager.py)."""
+        style_semantics = input_semantics
+        style_image = downscaled_image
+        if self.model_variant == "guided":
+            mode = "full"
+            if self.opt.guiding_style_image:
+                style_semantics, style_image = guiding_label, guiding_image
+            else:
+                style_image = full_image
+        elif self.model_variant == "independent":
+            if encode_full or (self.training and random.random() < 0.5):
+                mode = "full"
+                self.last_encoded_style_is_full = True
+                if self.opt.guiding_style_image:
+                    style_semantics, style_image = guiding_label, guiding_image
+                else:
+                    style_image = full_image
+            else:
+                mode = "mini"
+                self.last_encoded_style_is_full = False
+        else:
+            raise NotImplementedError()
+        return style_image, style_semantics, mode
+
+    def encode_style(self, downscaled_image=None, input_semantics=None, full_image=None,
+                     encode_full=False, no_noise=None, guiding_image=None, guiding_label=None):
+        """sr_model.py:634-650."""
+        style_image, style_semantics, mode = self.get_encoder_inputs(
+            downscaled_image=downscaled_image, input_semantics=input_semantics,
+            full_image=full_image, encode_full=encode_full, guiding_image=guiding_image,
+            guiding_label=guiding_label)
+        if self.model_variant == "independent" and not no_noise:
+            no_noise = random.random() < 0.5
+            self.last_encoded_style_is_noisy = not no_noise
+        return self.netE(style_image, style_semantics, mode=mode, no_noise=no_noise)
+
+    def discriminate(self, input_semantics, fake_image, real_image):
+        """sr_model.py:655-668: D sees [seg | fake] and [seg | real] in one batch. The two cats and
+        the NCHW->NHWC conversion are one kernel (ops.disc_input) on the uint8 label map."""
+        labels, _ = ops.labels_from_onehot(input_semantics.contiguous().float())
+        L = input_semantics.shape[1]
+        cp = (L + 3 + 3) // 4 * 4
+        x = ops.disc_input(labels, fake_image.contiguous().float(), real_image.contiguous().float(),
+                           L, cp)
+        out = self.netD.forward_nhwc(x)
+        out = [[t.permute(0, 3, 1, 2) for t in scale] for scale in out]
+        return self.divide_pred(out)
+
+    def divide_pred(self, pred):
+        """sr_model.py:671-683."""
+        if type(pred) == list:
+            fake = [[t[:t.size(0) // 2] for t in p] for p in pred]
+            real = [[t[t.size(0) // 2:] for t in p] for p in pred]
+        else:
+            fake = pred[:pred.size(0) // 2]
+            real = pred[pred.size(0) // 2:]
+        return fake, real
+
+    def use_gpu(self):
+        return True

@@ -19,6 +19,43 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class KernelTimer:
+    """Optional CUDA-event bracket around the tensor-core launches (bench.py's live roofline):
+    records (tag, algorithmic FLOPs, start event, end event) on the launching stream."""
+    active = None
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *a):
+        KernelTimer.active = None
+
+    def summary(self):
+        """-> {tag: (launches, total_ms, total_flops)} (call after a device synchronize)."""
+        out = {}
+        for tag, flops, e0, e1 in self.records:
+            n, ms, fl = out.get(tag, (0, 0.0, 0.0))
+            out[tag] = (n + 1, ms + e0.elapsed_time(e1), fl + flops)
+        return out
+
+
+def _timed(tag, flops, fn):
+    t = KernelTimer.active
+    if t is None:
+        return fn()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    t.records.append((tag, flops, e0, e1))
+    return r
+
+
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -153,8 +190,9 @@ def _operands(sources, pw, passes):
     return ops, (B, H, W)
 
 
-def conv3x3(sources, pw, bias, residual=None, res_ups=0, passes=3, want_stats=False):
-    """K2: 3x3 conv (+bias, +residual through an optional folded 2x upsample) -> fp32 NHWC.
+def conv3x3(sources, pw, bias, residual=None, res_ups=0, noises=(), passes=3, want_stats=False):
+    """K2: 3x3 conv + bias (+ residual through an optional folded 2x upsample, + up to two
+    NoiseInjection terms ``(noise NHWC, weight[C])``) -> fp32 NHWC.
 
     Returns out, or (out, stats_partial) when want_stats (partials for bn_finalize)."""
     ops, (B, H, W) = _operands(sources, pw, passes)
@@ -165,8 +203,25 @@ def conv3x3(sources, pw, bias, residual=None, res_ups=0, passes=3, want_stats=Fa
     if want_stats:
         nt = _lib.load().dsee_conv3x3_stats_tiles(B, H, W)
         stats = torch.empty((nt, pw.n_total, 2), dtype=torch.float32, device=dev)
-    _lib.check(_lib.load().dsee_conv3x3_fwd(C.byref(ops), _p(bias), _p(residual), res_ups, _p(out),
-                                            _p(stats), _stream()))
+    epi = _lib.ConvEpilogue()
+    epi.bias = bias.data_ptr()
+    epi.residual = residual.data_ptr() if residual is not None else 0
+    epi.res_ups = res_ups
+    noises = [n for n in noises if n is not None]
+    assert len(noises) <= 2
+    for i in range(2):
+        if i < len(noises):
+            _chk_cuda(noises[i][0], noises[i][1])
+            epi.noise[i] = noises[i][0].data_ptr()
+            epi.noise_w[i] = noises[i][1].data_ptr()
+        else:
+            epi.noise[i] = 0
+            epi.noise_w[i] = 0
+    epi.out = out.data_ptr()
+    epi.stats_partial = stats.data_ptr() if stats is not None else 0
+    flops = 2.0 * 9 * pw.cin * pw.n_total * B * H * W  # reference-equivalent dense conv FLOPs
+    _timed("conv3x3_%dx%d" % (H, W), flops,
+           lambda: _lib.check(_lib.load().dsee_conv3x3_fwd(C.byref(ops), C.byref(epi), _stream())))
     return (out, stats) if want_stats else out
 
 
@@ -189,7 +244,9 @@ def spade_modulate(sources, pw, x, x_ups, bn_scale, bn_shift, gamma_bias, beta_b
     m.out_hi = hi.data_ptr()
     m.out_lo = lo.data_ptr() if lo is not None else 0
     m.C = Cc
-    _lib.check(_lib.load().dsee_spade_modulate_fwd(C.byref(ops), C.byref(m), _stream()))
+    flops = 2.0 * 9 * pw.cin * pw.n_total * B * H * W
+    _timed("modulate_%dx%d" % (H, W), flops,
+           lambda: _lib.check(_lib.load().dsee_spade_modulate_fwd(C.byref(ops), C.byref(m), _stream())))
     return SplitPlanes(hi, lo)
 
 
@@ -211,7 +268,8 @@ def bn_stats(x, x_ups=0, noise=None, noise_w=None):
     return part
 
 
-def bn_finalize(partials, count, eps, momentum=0.1, running_mean=None, running_var=None):
+def bn_finalize(partials, count, eps, momentum=0.1, running_mean=None, running_var=None,
+                unbias_count=0):
     """-> (bn_scale, bn_shift, mean, var); updates running stats in place when given."""
     _chk_cuda(partials, running_mean, running_var)
     n, Cc, _ = partials.shape
@@ -220,7 +278,8 @@ def bn_finalize(partials, count, eps, momentum=0.1, running_mean=None, running_v
     sh = torch.empty_like(sc)
     mean = torch.empty_like(sc)
     var = torch.empty_like(sc)
-    _lib.check(_lib.load().dsee_bn_finalize(_p(partials), n, Cc, float(count), float(eps),
+    _lib.check(_lib.load().dsee_bn_finalize(_p(partials), n, Cc, float(count), float(unbias_count),
+                                            float(eps),
                                             float(momentum), _p(running_mean), _p(running_var),
                                             _p(sc), _p(sh), _p(mean), _p(var), _stream()))
     return sc, sh, mean, var
@@ -257,4 +316,75 @@ def head(x_nhwc, w, bias):
     out = torch.empty((B, 3, H, W), dtype=torch.float32, device=x_nhwc.device)
     _lib.check(_lib.load().dsee_head_fwd(_p(x_nhwc), _p(w), _p(bias), _p(out), B, H, W, Cc,
                                          _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# style encoder / discriminator layers (fp32 NHWC)
+# ---------------------------------------------------------------------------------------------
+def conv2d_direct(x, w_khwc, bias, stride=1, pad=1, ups=0, lrelu=False):
+    """x NHWC [B,Hi,Wi,Cin]; w_khwc [KH,KW,Cin,Cout] -> NHWC [B,Ho,Wo,Cout]."""
+    _chk_cuda(x, w_khwc, bias)
+    B, Hi, Wi, Cin = x.shape
+    KH, KW, Cin2, Cout = w_khwc.shape
+    assert Cin2 == Cin, (Cin2, Cin)
+    Ho = ((Hi << ups) + 2 * pad - KH) // stride + 1
+    Wo = ((Wi << ups) + 2 * pad - KW) // stride + 1
+    out = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().dsee_conv2d_direct_fwd(_p(x), _p(w_khwc), _p(bias), _p(out), B, Hi, Wi, Cin,
+                                                  Cout, KH, KW, stride, pad, ups, int(lrelu),
+                                                  _stream()))
+    return out
+
+
+def instance_norm(x, act, eps=1e-5):
+    """InstanceNorm2d(affine=False) + activation (0 none, 1 lrelu 0.2, 2 tanh). x NHWC."""
+    _chk_cuda(x)
+    B, H, W, Cc = x.shape
+    out = torch.empty_like(x)
+    mean = torch.empty((B, Cc), dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    _lib.check(_lib.load().dsee_instance_norm_fwd(_p(x), _p(out), _p(mean), _p(rstd), B, H * W, Cc,
+                                                  float(eps), act, _stream()))
+    return out, mean, rstd
+
+
+def region_pool(x, labels, L):
+    """extract_style_matrix: x NHWC [B,H,W,C], labels uint8 [B,H,W] -> [B,L,C]."""
+    _chk_cuda(x, labels)
+    B, H, W, Cc = x.shape
+    lib = _lib.load()
+    chunks = lib.dsee_region_pool_chunks(H * W)
+    ws = torch.empty((B, chunks, L, Cc), dtype=torch.float32, device=x.device)
+    style = torch.empty((B, L, Cc), dtype=torch.float32, device=x.device)
+    _lib.check(lib.dsee_region_pool_fwd(_p(x), _p(labels), _p(style), _p(ws), B, H * W, Cc, L,
+                                        _stream()))
+    return style
+
+
+def nchw_to_nhwc(x, Cp=None):
+    _chk_cuda(x)
+    B, Cc, H, W = x.shape
+    Cp = Cp or Cc
+    out = torch.empty((B, H, W, Cp), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().dsee_nchw_to_nhwc(_p(x), _p(out), B, Cc, H, W, Cp, _stream()))
+    return out
+
+
+def disc_input(labels, fake, real, L, Cp):
+    """[[onehot|fake];[onehot|real]] NHWC [2B,H,W,Cp] from uint8 labels and NCHW images."""
+    _chk_cuda(labels, fake, real)
+    B, H, W = labels.shape
+    out = torch.empty((2 * B, H, W, Cp), dtype=torch.float32, device=fake.device)
+    _lib.check(_lib.load().dsee_disc_input(_p(labels), _p(fake), _p(real), _p(out), B, L, H, W, Cp,
+                                           _stream()))
+    return out
+
+
+def avgpool3s2(x):
+    _chk_cuda(x)
+    B, Hi, Wi, Cc = x.shape
+    Ho, Wo = (Hi - 1) // 2 + 1, (Wi - 1) // 2 + 1
+    out = torch.empty((B, Ho, Wo, Cc), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().dsee_avgpool3s2_fwd(_p(x), _p(out), B, Hi, Wi, Cc, _stream()))
     return out

