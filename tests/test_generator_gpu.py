@@ -172,16 +172,20 @@ def test_encoder_and_discriminator_vs_reference_golden():
     assert torch.equal(res2[0][-1][:2].contiguous(), res[0][-1].permute(0, 3, 1, 2)[:2].contiguous()) or True
 
 
-def test_srmodel_inference_mode_vs_oracle():
-    """SRModel.forward(data, 'inference') through BaseManager.preprocess, like train.py/demo.py."""
+def test_srmodel_inference_mode_vs_oracle(tmp_path):
+    """SRModel.forward(data, 'inference') through BaseManager.preprocess, like train.py/demo.py;
+    the weights arrive the way released checkpoints do: <epoch>_net_{SR,E}.pth files holding
+    {"model": state_dict} (util/util.py:217-237)."""
     from deepsee_b200.managers.base_manager import BaseManager
     o = O.make_opt("8x_independent_256x256", ngf=8, start_size=8, crop_size=64, load_size=64)
-    opt = _mk_opt(o)
+    sdG, sdE = O.make_generator_state(o, 0), O.make_encoder_state(o, 1)
+    ck = tmp_path / o.name
+    ck.mkdir()
+    torch.save({"model": sdG}, str(ck / "latest_net_SR.pth"))
+    torch.save(sdE, str(ck / "latest_net_E.pth"))  # bare state_dict form is accepted too
+    opt = _mk_opt(o, checkpoints_dir=str(tmp_path))
     mgr = BaseManager(opt)
     model = mgr.sr_model.eval()
-    sdG, sdE = O.make_generator_state(o, 0), O.make_encoder_state(o, 1)
-    model.netSR.load_state_dict(sdG, strict=True)
-    model.netE.load_state_dict(sdE, strict=True)
     raw = O.synthetic_batch(o, 2, seed=31)
     ref_in = O.preprocess(o, raw)
     ref_fake, ref_z = O.inference(sdG, sdE, o, ref_in["image_lr"], ref_in["input_semantics"],
