@@ -17,6 +17,10 @@ SYMBOLS = [
     "dsee_shared_mlp_fwd", "dsee_style_gather_fwd",
     "dsee_prep_conv_weight", "dsee_split_f16",
     "dsee_conv3x3_fwd", "dsee_conv3x3_stats_tiles", "dsee_spade_modulate_fwd",
+    "dsee_spade_modulate_bwd", "dsee_grad_prep_blocks", "dsee_grad_prep", "dsee_reduce_partials",
+    "dsee_conv3x3_wgrad_workspace_floats", "dsee_conv3x3_wgrad", "dsee_bn_bwd_blocks", "dsee_bn_bwd",
+    "dsee_shared_mlp_bwd_blocks", "dsee_shared_mlp_bwd", "dsee_style_gather_bwd",
+    "dsee_stem_bwd_blocks", "dsee_stem_bwd", "dsee_head_bwd_blocks", "dsee_head_bwd",
     "dsee_bn_stats", "dsee_bn_finalize", "dsee_bn_eval_affine",
     "dsee_stem_fwd", "dsee_head_fwd",
     "dsee_conv2d_direct_fwd", "dsee_instance_norm_fwd", "dsee_region_pool_chunks",
@@ -29,7 +33,7 @@ class ConvOperands(C.Structure):
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
         ("a_hi", C.c_void_p * 2), ("a_lo", C.c_void_p * 2), ("a_channels", C.c_int * 2),
         ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("w_inv_scale", C.c_void_p),
-        ("n_total", C.c_int), ("passes", C.c_int),
+        ("n_total", C.c_int), ("passes", C.c_int), ("a_dtype", C.c_int), ("w_dtype", C.c_int),
     ]
 
 
@@ -37,7 +41,7 @@ class ConvEpilogue(C.Structure):
     _fields_ = [
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("res_ups", C.c_int),
         ("noise", C.c_void_p * 2), ("noise_w", C.c_void_p * 2),
-        ("out", C.c_void_p), ("stats_partial", C.c_void_p),
+        ("out", C.c_void_p), ("stats_partial", C.c_void_p), ("act_mask", C.c_void_p),
     ]
 
 
@@ -52,6 +56,18 @@ class ModulateArgs(C.Structure):
     ]
 
 
+class ModulateBwdArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_ups", C.c_int),
+        ("noise", C.c_void_p), ("noise_w", C.c_void_p),
+        ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
+        ("gamma_bias", C.c_void_p), ("dt", C.c_void_p),
+        ("dxhat", C.c_void_p), ("dgb_hi", C.c_void_p), ("dgb_lo", C.c_void_p),
+        ("partial", C.c_void_p), ("C", C.c_int),
+    ]
+
+
+ABI_VERSION = 2
 _lib = None
 
 
@@ -75,11 +91,25 @@ def load():
         "dsee_resize_labels": [vp, vp, i, i, i, i, i, vp],
         "dsee_shared_mlp_fwd": [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp],
         "dsee_style_gather_fwd": [vp, vp, vp, vp, i, i, i, i, i, vp],
-        "dsee_prep_conv_weight": [vp, vp, vp, vp, i, i, vp],
+        "dsee_prep_conv_weight": [vp, vp, vp, vp, i, i, i, vp],
         "dsee_split_f16": [vp, vp, vp, i64, vp],
         "dsee_conv3x3_fwd": [C.POINTER(ConvOperands), C.POINTER(ConvEpilogue), vp],
         "dsee_conv3x3_stats_tiles": [i, i, i],
         "dsee_spade_modulate_fwd": [C.POINTER(ConvOperands), C.POINTER(ModulateArgs), vp],
+        "dsee_spade_modulate_bwd": [C.POINTER(ConvOperands), C.POINTER(ModulateBwdArgs), vp],
+        "dsee_grad_prep_blocks": [i64],
+        "dsee_grad_prep": [vp, vp, vp, vp, vp, i64, i, vp, vp],
+        "dsee_reduce_partials": [vp, i, i, i, f, vp, vp],
+        "dsee_conv3x3_wgrad": [vp, vp, i, vp, vp, i, i, i, i, i, i, i, f, vp, vp, i, vp],
+        "dsee_bn_bwd_blocks": [i, i, i],
+        "dsee_bn_bwd": [vp, vp, i, vp, vp, vp, vp, vp, f, vp, i, i, i, i, vp, vp, vp],
+        "dsee_shared_mlp_bwd_blocks": [i, i, i],
+        "dsee_shared_mlp_bwd": [vp, i, i, vp, vp, i, i, i, i, i, i, vp, vp, vp],
+        "dsee_style_gather_bwd": [vp, i, i, vp, vp, vp, i, i, i, i, vp],
+        "dsee_stem_bwd_blocks": [i, i, i],
+        "dsee_stem_bwd": [vp, vp, i, i, i, i, vp, vp, vp],
+        "dsee_head_bwd_blocks": [i, i, i],
+        "dsee_head_bwd": [vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp],
         "dsee_bn_stats": [vp, i, vp, vp, i, i, i, i, vp, C.POINTER(C.c_int), vp],
         "dsee_bn_finalize": [vp, i, i, d, d, f, f, vp, vp, vp, vp, vp, vp, vp],
         "dsee_bn_eval_affine": [vp, vp, f, i, vp, vp, vp],
@@ -97,7 +127,9 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
-    if lib.dsee_version() != 1:
+    lib.dsee_conv3x3_wgrad_workspace_floats.argtypes = [i, i, i, i, i]
+    lib.dsee_conv3x3_wgrad_workspace_floats.restype = C.c_int64
+    if lib.dsee_version() != ABI_VERSION:
         raise RuntimeError("deepsee_b200: ABI version mismatch")
     _lib = lib
     return lib

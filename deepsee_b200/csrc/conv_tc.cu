@@ -25,6 +25,7 @@
 #include "../../include/deepsee_b200.h"
 #include "launch_count.h"
 #include <string.h>
+#include <cuda_bf16.h>
 
 namespace dsee {
 
@@ -41,7 +42,7 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*b
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 
-enum { EPI_CONV = 0, EPI_MODULATE = 1 };
+enum { EPI_CONV = 0, EPI_MODULATE = 1, EPI_MODULATE_BWD = 2 };
 
 struct alignas(64) ConvParams {
     CUtensorMap tmA[4];  // [source*2 + plane]
@@ -61,6 +62,7 @@ struct alignas(64) ConvParams {
     const float* rnoise_w[2];
     float* out;
     float* stats_partial;
+    const __half* act_mask;  // dgrad: multiply by LeakyReLU'(t) read off the saved activation's sign
     // EPI_MODULATE
     const float* x;
     int x_ups;
@@ -73,6 +75,12 @@ struct alignas(64) ConvParams {
     __half* out_hi;
     __half* out_lo;
     int C;
+    // EPI_MODULATE_BWD
+    const float* dt;         // fp32 NHWC [B,H,W,C]: gradient wrt the pre-activation t
+    float* dxhat;            // fp32 NHWC [B,H,W,C]
+    __nv_bfloat16* dgb_hi;   // bf16 NHWC [B,H,W,2C], channels interleaved [dG(128)|dB(128)] per 128
+    __nv_bfloat16* dgb_lo;
+    float* bwd_partial;      // [m_tiles*4][C][4] = sum dxhat, sum dxhat*xhat, sum dG, sum dB
 };
 
 __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& b, int& h0, int& w0,
@@ -264,7 +272,22 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                     float o[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        o[j] = __uint_as_float(v[j]) * inv_scale + __ldg(p.bias + n + j);
+                        o[j] = __uint_as_float(v[j]) * inv_scale + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+                    if (valid && p.act_mask) {
+                        const uint4* mrow = reinterpret_cast<const uint4*>(p.act_mask + pix * p.n_total + n);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 mv = __ldg(mrow + j);
+                            const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                // fp16 > 0  <=>  sign bit clear and magnitude bits non-zero
+                                const uint32_t lo16 = mw[e] & 0xffffu, hi16 = mw[e] >> 16;
+                                if (!(lo16 != 0 && lo16 < 0x8000u)) o[j * 8 + e * 2] *= 0.2f;
+                                if (!(hi16 != 0 && hi16 < 0x8000u)) o[j * 8 + e * 2 + 1] *= 0.2f;
+                            }
+                        }
+                    }
                     if (valid) {
                         if (rrow) {
 #pragma unroll
@@ -313,6 +336,96 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         sp[0] = r1;
                         sp[1] = r2;
                     }
+                }
+            } else if (EPI == EPI_MODULATE_BWD) {
+                // gamma-only GEMM (n_total == C): recompute G = gamma + gamma_bias, then
+                //   dG = dt * xhat, dB = dt, dxhat = dt * G   (+ the per-channel sums BN backward
+                //   and the bias gradients need)
+                const int c0 = nt * BLOCK_N;
+                const size_t pix = ((size_t)b * p.H + y) * p.W + x;
+                const int Hx = p.H >> p.x_ups, Wx = p.W >> p.x_ups;
+                const size_t xp = ((size_t)b * Hx + (y >> p.x_ups)) * Wx + (x >> p.x_ups);
+                const float* xrow = p.x + xp * p.C;
+                const float* nrow = p.noise ? p.noise + pix * p.C : nullptr;
+                const float* dtrow = p.dt + pix * p.C;
+                float* dxrow = p.dxhat + pix * p.C;
+                __nv_bfloat16* ghrow = p.dgb_hi + pix * (size_t)(2 * p.C);
+                __nv_bfloat16* glrow = p.dgb_lo ? p.dgb_lo + pix * (size_t)(2 * p.C) : nullptr;
+#pragma unroll 1
+                for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+                    const int c = c0 + ch * 32;
+                    if (c >= p.C) break;
+                    uint32_t g[32];
+                    tmem_ld32(taddr + ch * 32, g);
+                    tmem_ld_wait();
+                    float s_dx[32], s_dxx[32], s_dg[32], s_db[32];
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float xs[4] = {0, 0, 0, 0}, dts[4] = {0, 0, 0, 0};
+                        if (valid) {
+                            float4 xv = __ldg(reinterpret_cast<const float4*>(xrow + c) + j4);
+                            float4 dv = __ldg(reinterpret_cast<const float4*>(dtrow + c) + j4);
+                            xs[0] = xv.x; xs[1] = xv.y; xs[2] = xv.z; xs[3] = xv.w;
+                            dts[0] = dv.x; dts[1] = dv.y; dts[2] = dv.z; dts[3] = dv.w;
+                            if (nrow) {
+                                float4 nv = __ldg(reinterpret_cast<const float4*>(nrow + c) + j4);
+                                float4 wv = __ldg(reinterpret_cast<const float4*>(p.noise_w + c) + j4);
+                                xs[0] += wv.x * nv.x; xs[1] += wv.y * nv.y;
+                                xs[2] += wv.z * nv.z; xs[3] += wv.w * nv.w;
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = j4 * 4 + e, cc = c + j;
+                            const float xh = xs[e] * __ldg(p.bn_scale + cc) + __ldg(p.bn_shift + cc);
+                            const float G = __uint_as_float(g[j]) * inv_scale + __ldg(p.gamma_bias + cc);
+                            const float dtv = dts[e];
+                            s_dg[j] = valid ? dtv * xh : 0.f;
+                            s_db[j] = dtv;
+                            s_dx[j] = dtv * G;
+                            s_dxx[j] = s_dx[j] * xh;
+                        }
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            reinterpret_cast<float4*>(dxrow + c)[j4] = make_float4(
+                                s_dx[4 * j4], s_dx[4 * j4 + 1], s_dx[4 * j4 + 2], s_dx[4 * j4 + 3]);
+                        // interleaved channel position of c: (c/128)*256 + c%128 (+128 for dB)
+                        const int ng = (c >> 7) * 256 + (c & 127);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const float* src = half ? s_db : s_dg;
+                            __nv_bfloat16* dh = ghrow + ng + half * 128;
+                            __nv_bfloat16* dl = glrow ? glrow + ng + half * 128 : nullptr;
+#pragma unroll
+                            for (int j8 = 0; j8 < 4; ++j8) {
+                                uint32_t ph[4], pl[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float a0 = src[j8 * 8 + 2 * e], a1 = src[j8 * 8 + 2 * e + 1];
+                                    const __nv_bfloat16 h0 = __float2bfloat16_rn(a0);
+                                    const __nv_bfloat16 h1 = __float2bfloat16_rn(a1);
+                                    const __nv_bfloat16 l0 = __float2bfloat16_rn(a0 - __bfloat162float(h0));
+                                    const __nv_bfloat16 l1 = __float2bfloat16_rn(a1 - __bfloat162float(h1));
+                                    ph[e] = (uint32_t)__bfloat16_as_ushort(h0) |
+                                            ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                    pl[e] = (uint32_t)__bfloat16_as_ushort(l0) |
+                                            ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                                }
+                                reinterpret_cast<uint4*>(dh)[j8] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                                if (dl) reinterpret_cast<uint4*>(dl)[j8] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                            }
+                        }
+                    }
+                    // tile partials (invalid pixels contribute zeros: dt was loaded as 0)
+                    const float r0 = warp_transpose_reduce(s_dx, lane);
+                    const float r1 = warp_transpose_reduce(s_dxx, lane);
+                    const float r2 = warp_transpose_reduce(s_dg, lane);
+                    const float r3 = warp_transpose_reduce(s_db, lane);
+                    const size_t slot = (size_t)(tile / p.n_tiles) * 4 + q;
+                    *reinterpret_cast<float4*>(p.bwd_partial + (slot * p.C + c + lane) * 4) =
+                        make_float4(r0, r1, r2, r3);
                 }
             } else {
                 // EPI_MODULATE: columns [0,128) gamma, [128,256) beta for channels nt*128 + j
@@ -412,8 +525,10 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops) {
     p.n_total = ops->n_total;
     p.w_inv_scale = ops->w_inv_scale;
     // kind::f16 instruction descriptor: fp32 accumulate, fp16 A/B, K-major both, N=256, M=128
-    p.idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-              ((uint32_t)(BLOCK_M >> 4) << 24);
+    DSEE_CHECK_ARG((ops->a_dtype == 0 || ops->a_dtype == 1) && (ops->w_dtype == 0 || ops->w_dtype == 1),
+                   "operand dtype must be 0 (fp16) or 1 (bf16)");
+    p.idesc = (1u << 4) | ((uint32_t)ops->a_dtype << 7) | ((uint32_t)ops->w_dtype << 10) |
+              ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 
     for (int src = 0; src < 2; ++src) {
         const int C = ops->a_channels[src];
@@ -428,7 +543,7 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops) {
             uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)ops->W * C * 2,
                                    (uint64_t)ops->H * ops->W * C * 2};
             uint32_t box[4] = {BLOCK_K, TILE_W, TILE_H, 1};
-            rc = encode_tmap_16b(&p.tmA[src * 2 + pl], base, 4, dims, strides, box, false);
+            rc = encode_tmap_16b(&p.tmA[src * 2 + pl], base, 4, dims, strides, box, ops->a_dtype == 1);
             if (rc) return rc;
         }
     }
@@ -444,7 +559,7 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops) {
         uint64_t dims[2] = {Ktot, (uint64_t)ops->n_total};
         uint64_t strides[1] = {Ktot * 2};
         uint32_t box[2] = {BLOCK_K, BLOCK_N};
-        rc = encode_tmap_16b(&p.tmB[pl], base, 2, dims, strides, box, false);
+        rc = encode_tmap_16b(&p.tmB[pl], base, 2, dims, strides, box, ops->w_dtype == 1);
         if (rc) return rc;
     }
     return 0;
@@ -483,7 +598,7 @@ extern "C" int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_e
     memset(&p, 0, sizeof(p));
     int rc = fill_common(p, ops);
     if (rc) return rc;
-    DSEE_CHECK_ARG(epi && epi->bias && epi->out, "epilogue/bias/out is NULL");
+    DSEE_CHECK_ARG(epi && epi->out, "epilogue/out is NULL");
     DSEE_CHECK_ARG(epi->res_ups == 0 || epi->res_ups == 1, "res_ups must be 0 or 1");
     DSEE_CHECK_ARG(!epi->residual || epi->res_ups == 0 || (ops->H % 2 == 0 && ops->W % 2 == 0),
                    "folded upsample needs even H, W");
@@ -498,6 +613,7 @@ extern "C" int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_e
     p.res_ups = epi->res_ups;
     p.out = epi->out;
     p.stats_partial = epi->stats_partial;
+    p.act_mask = (const __half*)epi->act_mask;
     return launch<EPI_CONV>(p, (cudaStream_t)stream);
 }
 
@@ -531,4 +647,34 @@ extern "C" int dsee_spade_modulate_fwd(const dsee_conv_operands* ops, const dsee
     p.out_lo = (__half*)mod->out_lo;
     p.C = mod->C;
     return launch<EPI_MODULATE>(p, (cudaStream_t)stream);
+}
+
+extern "C" int dsee_spade_modulate_bwd(const dsee_conv_operands* ops, const dsee_modulate_bwd_args* a,
+                                       void* stream) {
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = fill_common(p, ops);
+    if (rc) return rc;
+    DSEE_CHECK_ARG(a != nullptr, "modulate bwd args are NULL");
+    DSEE_CHECK_ARG(a->C > 0 && a->C % 128 == 0 && ops->n_total == a->C,
+                   "gamma-only weights expected: n_total (%d) must equal C (%d)", ops->n_total, a->C);
+    DSEE_CHECK_ARG(a->x && a->dt && a->bn_scale && a->bn_shift && a->gamma_bias && a->dxhat &&
+                       a->dgb_hi && a->partial,
+                   "NULL modulate bwd pointer");
+    DSEE_CHECK_ARG(a->x_ups == 0 || a->x_ups == 1, "x_ups must be 0 or 1");
+    DSEE_CHECK_ARG((a->noise == nullptr) == (a->noise_w == nullptr), "noise/noise_w mismatch");
+    p.x = a->x;
+    p.x_ups = a->x_ups;
+    p.noise = a->noise;
+    p.noise_w = a->noise_w;
+    p.bn_scale = a->bn_scale;
+    p.bn_shift = a->bn_shift;
+    p.gamma_bias = a->gamma_bias;
+    p.C = a->C;
+    p.dt = a->dt;
+    p.dxhat = a->dxhat;
+    p.dgb_hi = (__nv_bfloat16*)a->dgb_hi;
+    p.dgb_lo = (__nv_bfloat16*)a->dgb_lo;
+    p.bwd_partial = a->partial;
+    return launch<EPI_MODULATE_BWD>(p, (cudaStream_t)stream);
 }

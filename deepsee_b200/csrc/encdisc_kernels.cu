@@ -200,18 +200,19 @@ __global__ void instnorm_apply_kernel(const float* __restrict__ x, const float* 
 // grid (chunks, B); block = C threads (thread owns a channel column -> no smem conflicts).
 // ------------------------------------------------------------------------------------------------
 constexpr int POOL_CHUNK = 1024;
-__global__ void region_pool_partial_kernel(const float* __restrict__ x, const uint8_t* __restrict__ labels,
-                                           int HW, int C, int L, float* __restrict__ partial) {
+__global__ void region_pool_partial_kernel(const float* __restrict__ x, int ld, int coff,
+                                           const uint8_t* __restrict__ labels, int HW, int C, int L,
+                                           float* __restrict__ partial) {
     extern __shared__ float acc[];  // [L][C]
     const int c = threadIdx.x, b = blockIdx.y;
     for (int l = 0; l < L; ++l) acc[l * C + c] = 0.f;
     const int p0 = blockIdx.x * POOL_CHUNK;
     const int p1 = min(p0 + POOL_CHUNK, HW);
     const uint8_t* lb = labels + (size_t)b * HW;
-    const float* xp = x + (size_t)b * HW * C + c;
+    const float* xp = x + (size_t)b * HW * ld + coff + c;
     for (int p = p0; p < p1; ++p) {
         int l = lb[p];
-        if (l < L) acc[l * C + c] += __ldg(xp + (size_t)p * C);
+        if (l < L) acc[l * C + c] += __ldg(xp + (size_t)p * ld);
     }
     float* out = partial + ((size_t)(b * gridDim.x + blockIdx.x) * L) * C + c;
     for (int l = 0; l < L; ++l) out[(size_t)l * C] = acc[l * C + c];
@@ -347,11 +348,30 @@ extern "C" int dsee_region_pool_fwd(const float* x, const uint8_t* labels, float
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int chunks = dsee_region_pool_chunks(HW);
-    region_pool_partial_kernel<<<dim3(chunks, B), C, (size_t)L * C * 4, st>>>(x, labels, HW, C, L,
+    region_pool_partial_kernel<<<dim3(chunks, B), C, (size_t)L * C * 4, st>>>(x, C, 0, labels, HW, C, L,
                                                                               workspace);
     count_launch();
     region_pool_final_kernel<<<dim3(cdiv2(L * C, 256), B), 256, 0, st>>>(workspace, chunks, L * C,
                                                                          1.0f / (float)HW, style);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_style_gather_bwd(const float* dsrc, int ld, int coff, const uint8_t* labels,
+                                     float* dstyle, float* workspace, int B, int HW, int L, int d,
+                                     void* stream) {
+    DSEE_CHECK_ARG(dsrc && labels && dstyle && workspace && B > 0 && HW > 0 && d > 0 && d <= 1024 &&
+                       L > 0 && coff >= 0 && coff + d <= ld,
+                   "bad argument");
+    DSEE_CHECK_ARG((size_t)L * d * 4 <= 48 * 1024, "L*d too large for the shared-memory accumulator");
+    int rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = dsee_region_pool_chunks(HW);
+    region_pool_partial_kernel<<<dim3(chunks, B), d, (size_t)L * d * 4, st>>>(dsrc, ld, coff, labels, HW,
+                                                                              d, L, workspace);
+    count_launch();
+    region_pool_final_kernel<<<dim3(cdiv2(L * d, 256), B), 256, 0, st>>>(workspace, chunks, L * d, 1.0f,
+                                                                         dstyle);
     LAUNCH_END();
 }
 

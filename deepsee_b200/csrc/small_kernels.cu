@@ -162,8 +162,9 @@ __device__ __forceinline__ float pow2_scale_for(float amax) {
 }
 
 __global__ void prep_weight_kernel(const float* __restrict__ w, __half* __restrict__ out_hi,
-                                   __half* __restrict__ out_lo, float* inv_scale, int N, int C) {
-    // out[n][tap][c] = w[n][c][tap] * scale
+                                   __half* __restrict__ out_lo, float* inv_scale, int N, int C,
+                                   int transpose) {
+    // out[n][tap][c] = w[n][c][tap] * scale      (transpose: out[c][8-tap][n])
     const float scale = pow2_scale_for(inv_scale[1]);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) inv_scale[0] = 1.f / scale;
@@ -174,8 +175,9 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, __half* __restri
     float v = w[((size_t)n * C + c) * 9 + tap] * scale;
     __half h, l;
     split_f16(v, h, l);
-    out_hi[i] = h;
-    if (out_lo) out_lo[i] = l;
+    const size_t o = transpose ? ((size_t)c * 9 + (8 - tap)) * N + n : (size_t)i;
+    out_hi[o] = h;
+    if (out_lo) out_lo[o] = l;
 }
 
 __global__ void split_kernel(const float* __restrict__ in, __half* __restrict__ hi,
@@ -477,7 +479,7 @@ extern "C" int dsee_style_gather_fwd(const uint8_t* labels, const float* style, 
 }
 
 extern "C" int dsee_prep_conv_weight(const float* w, void* out_hi, void* out_lo, float* inv_scale,
-                                     int N, int C, void* stream) {
+                                     int N, int C, int transpose, void* stream) {
     DSEE_CHECK_ARG(w && out_hi && inv_scale && N > 0 && C > 0, "bad argument");
     int rc = require_sm100();
     if (rc) return rc;
@@ -489,7 +491,7 @@ extern "C" int dsee_prep_conv_weight(const float* w, void* out_hi, void* out_lo,
     amax_kernel<<<blocks, 256, 0, st>>>(w, n, inv_scale + 1);
     count_launch();
     prep_weight_kernel<<<cdiv(n, 256), 256, 0, st>>>(w, (__half*)out_hi, (__half*)out_lo, inv_scale,
-                                                     N, C);
+                                                     N, C, transpose);
     LAUNCH_END();
 }
 

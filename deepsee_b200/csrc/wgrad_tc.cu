@@ -1,0 +1,341 @@
+// Weight gradient of the 3x3 convolutions on tcgen05 tensor cores.
+//
+//   dW[n][tap][c] = sum_{b,y,x} dY[b,y,x,n] * A[b,y+dy,x+dx,c]
+//
+// is, for every tap, a GEMM whose reduction dimension is the pixel index.  Both operands are
+// stored channel-contiguous (NHWC), i.e. "MN-major" from the GEMM's point of view, which
+// tcgen05.mma consumes directly (instruction-descriptor a_major = b_major = 1): a 4-D TMA box
+// {64 ch, 16 w, 8 h, 1 b} lands in shared memory as 128 pixel rows of 128 B, which is exactly the
+// canonical 128B-swizzled MN-major layout (8-row swizzle atoms 1024 B apart along K, 64-channel
+// column blocks one box = 16 KB apart along M/N).  The shifted box of the activation supplies the
+// tap offset and, through TMA out-of-bounds zero fill, the convolution's zero padding.
+//
+// Work unit = (128 dY-channels) x (tap) x (<=256 A-channels) x (pixel split); the K loop walks the
+// split's pixel tiles.  Units are spread over persistent CTAs; each writes its fp32 accumulator
+// tile to a per-split partial buffer that a small kernel reduces in a fixed order (deterministic,
+// no atomics).  Same warp roles / mbarrier pipeline as conv_tc.cu.
+//
+// Reference semantics: autograd of nn.Conv2d at architecture.py:98,122 and
+// normalization.py:116-117,198-201,283-284.
+#include "common.cuh"
+#include "../../include/deepsee_b200.h"
+#include "launch_count.h"
+#include <string.h>
+
+namespace dsee {
+
+constexpr int WG_M = 128;        // dY channels per unit
+constexpr int WG_NMAX = 256;     // activation channels per unit
+constexpr int WG_KPIX = 128;     // pixels per K step (8 x 16 tile)
+constexpr int WG_TW = 16, WG_TH = 8;
+constexpr int WG_BOX_BYTES = WG_KPIX * 64 * 2;                 // 16 KB: 128 pixel rows x 64 ch
+constexpr int WG_STAGE_BYTES = (WG_M / 64 + WG_NMAX / 64) * WG_BOX_BYTES;  // 96 KB
+constexpr int WG_STAGES = 2;
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+constexpr int WG_THREADS = 192;
+
+struct alignas(64) WgradParams {
+    CUtensorMap tmD[2];  // dY planes (hi, lo)
+    CUtensorMap tmA[2];  // activation planes (hi, lo)
+    int B, H, W;
+    int tiles_w, tiles_h, ptiles;  // pixel tiles
+    int n_total, c_total;
+    int n_tiles, c_tiles, splits, num_units;
+    int n_cols;  // activation channels per unit (<= 256)
+    int passes;
+    uint32_t idesc;
+    float* partial;  // [splits][n_total][9][c_total]
+    float scale;     // applied to the accumulator (undoes operand pre-scaling)
+};
+
+// MN-major, 128B-swizzled operand descriptor (see header comment).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((WG_BOX_BYTES >> 4) & 0x3FFF) << 16;  // LBO: next 64-channel block
+    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;          // SBO: next 8 pixel rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void wg_decode(const WgradParams& p, int unit, int& nt, int& tap, int& ct,
+                                          int& split) {
+    ct = unit % p.c_tiles;
+    unit /= p.c_tiles;
+    tap = unit % 9;
+    unit /= 9;
+    nt = unit % p.n_tiles;
+    split = unit / p.n_tiles;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + WG_STAGES;
+    uint64_t* tfull_bar = bars + 2 * WG_STAGES;
+    uint64_t* tempty_bar = bars + 2 * WG_STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmD[0]);
+        tma_prefetch_desc(&p.tmA[0]);
+        for (int s = 0; s < WG_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nboxA = p.n_cols / 64;
+    const uint32_t stage_tx = (uint32_t)(WG_M / 64 + nboxA) * WG_BOX_BYTES;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+                int nt, tap, ct, split;
+                wg_decode(p, unit, nt, tap, ct, split);
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                const int pt0 = (int)((int64_t)p.ptiles * split / p.splits);
+                const int pt1 = (int)((int64_t)p.ptiles * (split + 1) / p.splits);
+                for (int pt = pt0; pt < pt1; ++pt) {
+                    const int tw = pt % p.tiles_w;
+                    const int th = (pt / p.tiles_w) % p.tiles_h;
+                    const int b = pt / (p.tiles_w * p.tiles_h);
+                    const int h0 = th * WG_TH, w0 = tw * WG_TW;
+                    for (int pass = 0; pass < p.passes; ++pass, ++it) {
+                        const int pd = (pass == 1) ? 1 : 0;  // dY plane
+                        const int pa = (pass == 2) ? 1 : 0;  // activation plane
+                        const int s = it % WG_STAGES;
+                        const uint32_t ph = (it / WG_STAGES) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_expect_tx(&full_bar[s], stage_tx);
+                        uint8_t* sd = smem + s * WG_STAGE_BYTES;
+                        uint8_t* sa = sd + (WG_M / 64) * WG_BOX_BYTES;
+                        for (int i = 0; i < WG_M / 64; ++i)
+                            tma_load_4d(&p.tmD[pd], &full_bar[s], sd + i * WG_BOX_BYTES,
+                                        nt * WG_M + i * 64, w0, h0, b);
+                        for (int i = 0; i < nboxA; ++i)
+                            tma_load_4d(&p.tmA[pa], &full_bar[s], sa + i * WG_BOX_BYTES,
+                                        ct * WG_NMAX + i * 64, w0 + dx, h0 + dy, b);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            int lu = 0;
+            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++lu) {
+                int nt, tap, ct, split;
+                wg_decode(p, unit, nt, tap, ct, split);
+                const int pt0 = (int)((int64_t)p.ptiles * split / p.splits);
+                const int pt1 = (int)((int64_t)p.ptiles * (split + 1) / p.splits);
+                const int kiters = (pt1 - pt0) * p.passes;
+                const int as = lu & 1;
+                const uint32_t aph = (lu >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * WG_NMAX;
+                for (int kit = 0; kit < kiters; ++kit, ++it) {
+                    const int s = it % WG_STAGES;
+                    const uint32_t ph = (it / WG_STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sd = smem_u32(smem + s * WG_STAGE_BYTES);
+                    const uint32_t sa = sd + (WG_M / 64) * WG_BOX_BYTES;
+                    const uint64_t da = umma_desc_mn_sw128(sd);
+                    const uint64_t db = umma_desc_mn_sw128(sa);
+#pragma unroll
+                    for (int k = 0; k < WG_KPIX / 16; ++k) {
+                        // advance 16 pixel rows = 2048 B = 128 (16 B units) along K
+                        umma_f16(tmem_d, da + 128 * k, db + 128 * k, p.idesc, (kit | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                if (kiters == 0) {
+                    // empty split (fewer pixel tiles than splits): nothing accumulated; the
+                    // epilogue writes zeros (it checks the same condition)
+                }
+                umma_commit(&tfull_bar[as]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        int lu = 0;
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++lu) {
+            int nt, tap, ct, split;
+            wg_decode(p, unit, nt, tap, ct, split);
+            const int pt0 = (int)((int64_t)p.ptiles * split / p.splits);
+            const int pt1 = (int)((int64_t)p.ptiles * (split + 1) / p.splits);
+            const bool empty = pt1 <= pt0;
+            const int as = lu & 1;
+            const uint32_t aph = (lu >> 1) & 1;
+            mbar_wait(&tfull_bar[as], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * WG_NMAX;
+            const int n = nt * WG_M + m;
+            float* orow = p.partial + (((size_t)split * p.n_total + n) * 9 + tap) * p.c_total +
+                          (size_t)ct * WG_NMAX;
+#pragma unroll 1
+            for (int ch = 0; ch < p.n_cols / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(taddr + ch * 32, v);
+                tmem_ld_wait();
+                if (n < p.n_total) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o = make_float4(__uint_as_float(v[4 * j]) * p.scale,
+                                               __uint_as_float(v[4 * j + 1]) * p.scale,
+                                               __uint_as_float(v[4 * j + 2]) * p.scale,
+                                               __uint_as_float(v[4 * j + 3]) * p.scale);
+                        if (empty) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        reinterpret_cast<float4*>(orow + ch * 32)[j] = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// out[i] = sum_s partial[s][i] (fixed order), optionally transposing [n][9][c] -> [n][c][9]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                    int splits, int n_total, int c_total, int to_nc9) {
+    const int64_t total = (int64_t)n_total * 9 * c_total;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float a = 0.f;
+    for (int s = 0; s < splits; ++s) a += partial[(size_t)s * total + i];
+    if (to_nc9) {
+        const int c = (int)(i % c_total);
+        const int tap = (int)((i / c_total) % 9);
+        const int n = (int)(i / ((int64_t)9 * c_total));
+        out[((size_t)n * c_total + c) * 9 + tap] = a;
+    } else {
+        out[i] = a;
+    }
+}
+
+}  // namespace dsee
+
+using namespace dsee;
+
+static int wgrad_plan(int B, int H, int W, int n_total, int c_total, int* splits_out) {
+    const int ptiles = B * ((H + WG_TH - 1) / WG_TH) * ((W + WG_TW - 1) / WG_TW);
+    const int n_tiles = (n_total + WG_M - 1) / WG_M;
+    const int c_tiles = (c_total + WG_NMAX - 1) / WG_NMAX;
+    const int base = n_tiles * 9 * c_tiles;
+    int splits = (2 * 148 + base - 1) / base;  // ~2 units per SM
+    if (splits > ptiles) splits = ptiles;
+    if (splits < 1) splits = 1;
+    if (splits > 16) splits = 16;
+    *splits_out = splits;
+    return ptiles;
+}
+
+extern "C" int64_t dsee_conv3x3_wgrad_workspace_floats(int B, int H, int W, int n_total, int c_total) {
+    int splits;
+    wgrad_plan(B, H, W, n_total, c_total, &splits);
+    return (int64_t)splits * n_total * 9 * c_total;
+}
+
+extern "C" int dsee_conv3x3_wgrad(const void* dy_hi, const void* dy_lo, int dy_dtype,
+                                  const void* a_hi, const void* a_lo, int a_dtype, int B, int H,
+                                  int W, int n_total, int c_total, int passes, float scale,
+                                  float* workspace, float* dw, int layout_nc9, void* stream) {
+    DSEE_CHECK_ARG(dy_hi && a_hi && workspace && dw, "NULL pointer");
+    DSEE_CHECK_ARG(B > 0 && H > 0 && W > 0, "bad geometry");
+    DSEE_CHECK_ARG(n_total % 128 == 0, "n_total must be a multiple of 128 (got %d)", n_total);
+    DSEE_CHECK_ARG(c_total == 64 || c_total == 128 || c_total % 256 == 0,
+                   "c_total must be 64, 128 or a multiple of 256 (got %d)", c_total);
+    DSEE_CHECK_ARG(passes == 1 || (passes == 3 && dy_lo && a_lo), "passes must be 1, or 3 with lo planes");
+    DSEE_CHECK_ARG((dy_dtype | 1) == 1 && (a_dtype | 1) == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+    int rc = require_sm100();
+    if (rc) return rc;
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B;
+    p.H = H;
+    p.W = W;
+    p.tiles_w = (W + WG_TW - 1) / WG_TW;
+    p.tiles_h = (H + WG_TH - 1) / WG_TH;
+    p.n_total = n_total;
+    p.c_total = c_total;
+    p.n_tiles = n_total / WG_M;
+    p.c_tiles = (c_total + WG_NMAX - 1) / WG_NMAX;
+    p.n_cols = c_total < WG_NMAX ? c_total : WG_NMAX;
+    p.ptiles = wgrad_plan(B, H, W, n_total, c_total, &p.splits);
+    p.num_units = p.n_tiles * 9 * p.c_tiles * p.splits;
+    p.passes = passes;
+    p.partial = workspace;
+    p.scale = scale;
+    // kind::f16, fp32 accumulate, both operands MN-major, M = 128, N = n_cols
+    p.idesc = (1u << 4) | ((uint32_t)dy_dtype << 7) | ((uint32_t)a_dtype << 10) | (1u << 15) |
+              (1u << 16) | ((uint32_t)(p.n_cols >> 3) << 17) | ((uint32_t)(WG_M >> 4) << 24);
+    uint32_t box[4] = {64, WG_TW, WG_TH, 1};
+    for (int pl = 0; pl < 2; ++pl) {
+        const void* d = pl ? dy_lo : dy_hi;
+        const void* a = pl ? a_lo : a_hi;
+        if (d) {
+            uint64_t dims[4] = {(uint64_t)n_total, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+            uint64_t st[3] = {(uint64_t)n_total * 2, (uint64_t)W * n_total * 2, (uint64_t)H * W * n_total * 2};
+            rc = encode_tmap_16b(&p.tmD[pl], d, 4, dims, st, box, dy_dtype == 1);
+            if (rc) return rc;
+        } else {
+            p.tmD[pl] = p.tmD[0];
+        }
+        if (a) {
+            uint64_t dims[4] = {(uint64_t)c_total, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+            uint64_t st[3] = {(uint64_t)c_total * 2, (uint64_t)W * c_total * 2, (uint64_t)H * W * c_total * 2};
+            rc = encode_tmap_16b(&p.tmA[pl], a, 4, dims, st, box, a_dtype == 1);
+            if (rc) return rc;
+        } else {
+            p.tmA[pl] = p.tmA[0];
+        }
+    }
+    static bool configured[64] = {false};
+    int dev = 0;
+    DSEE_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !configured[dev]) {
+        DSEE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       WG_SMEM));
+        configured[dev] = true;
+    }
+    int sms = 0;
+    DSEE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = p.num_units < sms ? p.num_units : sms;
+    cudaStream_t st = (cudaStream_t)stream;
+    wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM, st>>>(p);
+    count_launch();
+    DSEE_CUDA(cudaGetLastError());
+    const int64_t total = (int64_t)n_total * 9 * c_total;
+    wgrad_reduce_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(workspace, dw, p.splits, n_total,
+                                                                    c_total, layout_nc9);
+    count_launch();
+    DSEE_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -10,6 +10,13 @@ One block = 2 x (K1 modulate -> K2 conv):
       -> K2[conv_1]: + bias + shortcut (x through the folded upsample, + noise_in/noise_skip)
          -> block output fp32 NHWC and its BN partial sums for the next block's norm_0
 
+The block is ONE autograd node (`_ResBlockFn`): its backward replays the chain with the library's
+backward kernels (dgrad = the same implicit GEMM on the gradient planes with the transposed filter,
+wgrad = pixel-reduction GEMM, K1 backward, batch-norm backward with the folded upsample transposed)
+and hands PyTorch the gradients of the *effective* tensors (spectral-normalised conv weights, the
+alpha-blended modulation weight, the mlp_shared table), so spectral norm, the alpha blend and the
+optimizers stay ordinary PyTorch autograd.
+
 fin == fout everywhere in DeepSEESR, so the learned shortcut (conv_s / norm_s) is never built
 (architecture.py:30,36); asking for it raises.
 """
@@ -23,6 +30,168 @@ from .normalization import (SPADE, SEAN_Block, PureSEAN_Block, NoiseInjection, e
                             BN_EPS)
 
 BN_MOMENTUM = 0.1
+
+
+class _NormState:
+    """What K1's backward needs from one conditional-norm layer's forward."""
+    __slots__ = ("srcs", "meta", "Wm", "gb", "sc", "sh", "inv_count")
+
+
+def _norm_forward(blk, norm, pre, Wm, gb, bb, tab, tb, gctx, style, x, x_ups, H, W, part, count,
+                  ucount, noise, noise_w, passes, want_lo):
+    """BN affine + sources + K1 -> (activation planes, _NormState)."""
+    st = _NormState()
+    bn = norm.param_free_norm
+    if blk.training:
+        st.sc, st.sh, _, _ = ops.bn_finalize(part, count, BN_EPS, BN_MOMENTUM, bn.running_mean,
+                                             bn.running_var, unbias_count=ucount)
+        bn.num_batches_tracked.add_(1)
+        st.inv_count = 1.0 / float(ucount)
+    else:
+        st.sc, st.sh = norm.eval_affine()
+        st.inv_count = 0.0
+    pw = pre if pre is not None else ops.prep_conv_weight(Wm.contiguous(), want_lo=want_lo)
+    st.srcs, st.meta = norm.build_sources(gctx, style, H, W, want_lo, table=tab, bias=tb)
+    st.Wm, st.gb = Wm, gb
+    a = ops.spade_modulate(st.srcs, pw, x, x_ups, st.sc, st.sh, gb, bb, noise=noise, noise_w=noise_w,
+                           passes=passes, want_lo=want_lo)
+    return a, st
+
+
+def _norm_backward(norm, st, dt, x, x_ups, noise, noise_w, L, passes, want_lo):
+    """K1 backward for one layer -> (dxhat, sums[4,C], dWm, dtab, dtb, dstyle)."""
+    C = x.shape[3]
+    Wm = st.Wm
+    cin = Wm.shape[1]
+    w_gamma = Wm.view(C // 128, 2, 128, cin, 3, 3)[:, 0].reshape(C, cin, 3, 3).contiguous()
+    pwg = ops.prep_conv_weight(w_gamma, want_lo=want_lo)
+    dxhat, dgb, sums = ops.spade_modulate_bwd(st.srcs, pwg, x, x_ups, st.sc, st.sh, st.gb, dt,
+                                              noise=noise, noise_w=noise_w, passes=passes,
+                                              want_lo=want_lo)
+    dWm = [ops.conv3x3_wgrad(dgb, src, passes=passes) for src in st.srcs]
+    dWm = dWm[0] if len(dWm) == 1 else torch.cat(dWm, 1)
+    pwT = ops.prep_conv_weight(Wm.contiguous(), want_lo=want_lo, transpose=True)
+    dsrc = ops.conv3x3([dgb], pwT, None, passes=passes, tag="dgrad_mod")
+    del dgb
+    meta = st.meta
+    dtab = dtb = dstyle = None
+    coff = 0
+    for src, kind in zip(st.srcs, meta['kinds']):
+        d = src.hi.shape[3]
+        if kind == 'actv':
+            t, b = ops.shared_mlp_bwd(dsrc, coff, meta['actv'].hi, meta['labels'], meta['ups'], L)
+            dtab = t if dtab is None else dtab + t
+            dtb = b if dtb is None else dtb + b
+        else:
+            g = ops.style_gather_bwd(dsrc, coff, meta['labels'], L, d)
+            dstyle = g if dstyle is None else dstyle + g
+        coff += d
+    return dxhat, sums, dWm, dtab, dtb, dstyle
+
+
+class _ResBlockFn(torch.autograd.Function):
+    """forward / backward of one SPADEResnetBlock (architecture.py:75-147) on the C-ABI kernels."""
+
+    @staticmethod
+    def forward(ctx, blk, gctx, ups, stats_in, noises, pre, x, style, W0, b0, W1, b1, Wm0, gb0, bb0,
+                tab0, tb0, Wm1, gb1, bb1, tab1, tb1, nw_in, nw_skip, nw_mid):
+        B, Hx, Wx, C = x.shape
+        H, W = Hx << ups, Wx << ups
+        passes = config.passes
+        want_lo = passes == 3
+        training = blk.training
+        n_in, n_skip, n_mid = noises if noises is not None else (None, None, None)
+        noisy = noises is not None
+        pre = pre or {}
+
+        # ---- norm_0 + actvn -------------------------------------------------------------------
+        part = None
+        count = ucount = 0
+        if training:
+            if stats_in is not None and not noisy:
+                # statistics of a nearest-upsampled tensor = statistics of its source
+                part, count, ucount = stats_in, B * Hx * Wx, B * H * W
+            else:
+                part = ops.bn_stats(x, ups, n_in, nw_in if noisy else None)
+                count = ucount = B * H * W
+        a0, st0 = _norm_forward(blk, blk.norm_0, pre.get('pwm0'), Wm0, gb0, bb0, tab0, tb0, gctx,
+                                style, x, ups, H, W, part, count, ucount, n_in,
+                                nw_in if noisy else None, passes, want_lo)
+        # ---- conv_0 (+ noise_middle) ----------------------------------------------------------
+        pw0 = pre.get('pw0') or ops.prep_conv_weight(W0.contiguous(), want_lo=want_lo)
+        r = ops.conv3x3([a0], pw0, b0, noises=[(n_mid, nw_mid)] if noisy else (), passes=passes,
+                        want_stats=training)
+        dx1, part1 = r if training else (r, None)
+        # ---- norm_1 + actvn -------------------------------------------------------------------
+        a1, st1 = _norm_forward(blk, blk.norm_1, pre.get('pwm1'), Wm1, gb1, bb1, tab1, tb1, gctx,
+                                style, dx1, 0, H, W, part1, B * H * W, B * H * W, None, None, passes,
+                                want_lo)
+        # ---- conv_1 + shortcut ------------------------------------------------------------------
+        pw1 = pre.get('pw1') or ops.prep_conv_weight(W1.contiguous(), want_lo=want_lo)
+        r = ops.conv3x3([a1], pw1, b1, residual=x, res_ups=ups,
+                        noises=[(n_in, nw_in), (n_skip, nw_skip)] if noisy else (), passes=passes,
+                        want_stats=training)
+        out, stats = r if training else (r, None)
+
+        if any(ctx.needs_input_grad):
+            ctx.s = dict(blk=blk, ups=ups, noises=noises, x=x, W0=W0, W1=W1, a0=a0, a1=a1, dx1=dx1,
+                         st0=st0, st1=st1, nw_in=nw_in, passes=passes, want_lo=want_lo)
+        if stats is None:
+            stats = x.new_zeros(1)
+        ctx.mark_non_differentiable(stats)
+        return out, stats
+
+    @staticmethod
+    def backward(ctx, dout, _dstats):
+        s = ctx.s
+        blk, ups, passes, want_lo = s['blk'], s['ups'], s['passes'], s['want_lo']
+        n_in, n_skip, n_mid = s['noises'] if s['noises'] is not None else (None, None, None)
+        noisy = s['noises'] is not None
+        L = blk.opt.semantic_nc
+        dout = dout.contiguous()
+        x, dx1, a0, a1, st0, st1 = s['x'], s['dx1'], s['a0'], s['a1'], s['st0'], s['st1']
+
+        # ---- conv_1 + shortcut: out = conv(a1, W1) + b1 + x_up + w_in*n_in + w_skip*n_skip ------
+        g1, sums = ops.grad_prep(dout, n_in, n_skip, want_lo=want_lo)
+        db1 = sums[0]
+        dnw_in = sums[1] if noisy else None
+        dnw_skip = sums[2] if noisy else None
+        dW1 = ops.conv3x3_wgrad(g1, a1, passes=passes)
+        pwT = ops.prep_conv_weight(s['W1'].contiguous(), want_lo=want_lo, transpose=True)
+        dt1 = ops.conv3x3([g1], pwT, None, passes=passes, act_mask=a1.hi, tag="dgrad")
+        del g1
+        # ---- norm_1 ----------------------------------------------------------------------------
+        dxhat, nsums, dWm1, dtab1, dtb1, dstyle1 = _norm_backward(
+            blk.norm_1, st1, dt1, dx1, 0, None, None, L, passes, want_lo)
+        del dt1
+        dgb1, dbb1 = nsums[2], nsums[3]
+        ddx1, _ = ops.bn_bwd(dxhat, dx1, 0, st1.sc, st1.sh, nsums, st1.inv_count)
+        del dxhat
+        # ---- conv_0: dx1 = conv(a0, W0) + b0 + w_mid*n_mid --------------------------------------
+        g0, sums = ops.grad_prep(ddx1, n_mid, None, want_lo=want_lo)
+        del ddx1
+        db0 = sums[0]
+        dnw_mid = sums[1] if noisy else None
+        dW0 = ops.conv3x3_wgrad(g0, a0, passes=passes)
+        pwT = ops.prep_conv_weight(s['W0'].contiguous(), want_lo=want_lo, transpose=True)
+        dt0 = ops.conv3x3([g0], pwT, None, passes=passes, act_mask=a0.hi, tag="dgrad")
+        del g0
+        # ---- norm_0 (reads x through the folded upsample, + noise_in) ---------------------------
+        nw_in = s['nw_in'] if noisy else None
+        dxhat, nsums, dWm0, dtab0, dtb0, dstyle0 = _norm_backward(
+            blk.norm_0, st0, dt0, x, ups, n_in, nw_in, L, passes, want_lo)
+        del dt0
+        dgb0, dbb0 = nsums[2], nsums[3]
+        dx, dnw_in_bn = ops.bn_bwd(dxhat, x, ups, st0.sc, st0.sh, nsums, st0.inv_count, noise=n_in,
+                                   noise_w=nw_in, dskip=dout)
+        if noisy:
+            dnw_in = dnw_in + dnw_in_bn
+        dstyle = dstyle0
+        if dstyle1 is not None:
+            dstyle = dstyle1 if dstyle is None else dstyle + dstyle1
+        ctx.s = None
+        return (None, None, None, None, None, None, dx, dstyle, dW0, db0, dW1, db1, dWm0, dgb0, dbb0,
+                dtab0, dtb0, dWm1, dgb1, dbb1, dtab1, dtb1, dnw_in, dnw_skip, dnw_mid)
 
 
 class SPADEResnetBlock(nn.Module):
@@ -62,81 +231,51 @@ class SPADEResnetBlock(nn.Module):
             return SEAN_Block
         return SPADE
 
-    # -- prepared main-conv weights -------------------------------------------------------------
-    def _prepared_conv(self, conv, name, want_lo):
-        w = effective_weight(conv)  # spectral norm: W_orig / sigma (power iteration when training)
-        if torch.is_grad_enabled() and w.requires_grad:
-            return ops.prep_conv_weight(w.detach().contiguous(), want_lo=want_lo)
+    # -- prepared main-conv weights (inference cache) -----------------------------------------------
+    def _prepared_conv(self, conv, w, name, want_lo):
         src = [getattr(conv, n) for n in ('weight_orig', 'weight_u', 'weight_v') if hasattr(conv, n)]
         if not src:
             src = [conv.weight]
-        key = tuple((t.data_ptr(), t._version) for t in src) + (want_lo, self.training)
+        key = tuple((t.data_ptr(), t._version) for t in src) + (want_lo,)
         hit = self._wcache.get(name)
-        if hit is not None and hit[0] == key and not self.training:
+        if hit is not None and hit[0] == key:
             return hit[1]
         pw = ops.prep_conv_weight(w.detach().contiguous(), want_lo=want_lo)
         self._wcache[name] = (key, pw)
         return pw
 
-    # -- batch norm ------------------------------------------------------------------------------
-    def _bn_affine(self, norm, partials, count, unbias_count):
-        bn = norm.param_free_norm
-        if not self.training:
-            return norm.eval_affine()
-        sc, sh, _, _ = ops.bn_finalize(partials, count, BN_EPS, BN_MOMENTUM, bn.running_mean,
-                                       bn.running_var, unbias_count=unbias_count)
-        bn.num_batches_tracked.add_(1)
-        return sc, sh
-
     def forward_nhwc(self, x, ctx, ups=0, stats_in=None):
-        """x fp32 NHWC [B, H>>ups, W>>ups, C] -> (out fp32 NHWC [B,H,W,C], stats partials of out or
+        """x fp32 NHWC [B, H>>ups, W>>ups, C] -> (out fp32 NHWC [B,H,W,C], BN partial sums of out or
         None). ``stats_in``: BN partial sums of x from the producing kernel (training only)."""
         B, Hx, Wx, C = x.shape
         H, W = Hx << ups, Wx << ups
-        passes = config.passes
-        want_lo = passes == 3
-        training = self.training
-        noisy = self.add_noise
-        n_in = n_skip = n_mid = None
-        w_in = w_skip = w_mid = None
-        if noisy:
-            n_in, w_in = self.noise_in.sample(B, H, W), self.noise_in.weight
-            n_skip, w_skip = self.noise_skip.sample(B, H, W), self.noise_skip.weight
-            n_mid, w_mid = self.noise_middle.sample(B, H, W), self.noise_middle.weight
-
-        # ---- norm_0 + actvn -------------------------------------------------------------------
-        part = None
-        count = ucount = 0
-        if training:
-            if stats_in is not None and not noisy:
-                # statistics of a nearest-upsampled tensor = statistics of its source
-                part, count, ucount = stats_in, B * Hx * Wx, B * H * W
-            else:
-                part = ops.bn_stats(x, ups, n_in, w_in)
-                count = ucount = B * H * W
-        sc, sh = self._bn_affine(self.norm_0, part, count, ucount)
-        pw, gb, bb = self.norm_0.prepared(want_lo)
-        srcs = self.norm_0.build_sources(ctx, H, W, want_lo)
-        a0 = ops.spade_modulate(srcs, pw, x, ups, sc, sh, gb, bb, noise=n_in, noise_w=w_in,
-                                passes=passes, want_lo=want_lo)
-        # ---- conv_0 (+ noise_middle) ----------------------------------------------------------
-        pw0 = self._prepared_conv(self.conv_0, 'conv_0', want_lo)
-        r = ops.conv3x3([a0], pw0, self.conv_0.bias, noises=[(n_mid, w_mid)] if noisy else (),
-                        passes=passes, want_stats=training)
-        dx, part1 = r if training else (r, None)
-        del a0
-        # ---- norm_1 + actvn -------------------------------------------------------------------
-        sc1, sh1 = self._bn_affine(self.norm_1, part1, B * H * W, B * H * W)
-        pw, gb, bb = self.norm_1.prepared(want_lo)
-        srcs = self.norm_1.build_sources(ctx, H, W, want_lo)
-        a1 = ops.spade_modulate(srcs, pw, dx, 0, sc1, sh1, gb, bb, passes=passes, want_lo=want_lo)
-        del dx
-        # ---- conv_1 + shortcut ------------------------------------------------------------------
-        pw1 = self._prepared_conv(self.conv_1, 'conv_1', want_lo)
-        r = ops.conv3x3([a1], pw1, self.conv_1.bias, residual=x, res_ups=ups,
-                        noises=[(n_in, w_in), (n_skip, w_skip)] if noisy else (), passes=passes,
-                        want_stats=training)
-        return r if training else (r, None)
+        want_lo = config.passes == 3
+        noises = None
+        nw = (None, None, None)
+        if self.add_noise:
+            noises = (self.noise_in.sample(B, H, W), self.noise_skip.sample(B, H, W),
+                      self.noise_middle.sample(B, H, W))
+            nw = (self.noise_in.weight, self.noise_skip.weight, self.noise_middle.weight)
+        # spectral norm: W_orig / sigma (one power iteration when training), an autograd tensor
+        W0, W1 = effective_weight(self.conv_0), effective_weight(self.conv_1)
+        cached = not self.training and not torch.is_grad_enabled()
+        if cached:
+            pwm0, gb0, bb0 = self.norm_0.prepared(want_lo)
+            pwm1, gb1, bb1 = self.norm_1.prepared(want_lo)
+            pre = {'pwm0': pwm0, 'pwm1': pwm1,
+                   'pw0': self._prepared_conv(self.conv_0, W0, 'conv_0', want_lo),
+                   'pw1': self._prepared_conv(self.conv_1, W1, 'conv_1', want_lo)}
+            Wm0 = Wm1 = None
+        else:
+            pre = None
+            Wm0, gb0, bb0 = self.norm_0.combined_weight()
+            Wm1, gb1, bb1 = self.norm_1.combined_weight()
+        tab0, tb0 = self.norm_0.table_and_bias()
+        tab1, tb1 = self.norm_1.table_and_bias()
+        out, stats = _ResBlockFn.apply(self, ctx, ups, stats_in, noises, pre, x, ctx.style, W0,
+                                       self.conv_0.bias, W1, self.conv_1.bias, Wm0, gb0, bb0, tab0,
+                                       tb0, Wm1, gb1, bb1, tab1, tb1, *nw)
+        return out, (stats if self.training else None)
 
     def forward(self, x, seg, style=None, split_location=-1):
         raise RuntimeError('SPADEResnetBlock is driven by DeepSEESR.forward on the B200 path '

@@ -107,12 +107,19 @@ class _CondNormBase(nn.Module):
         w = self.mlp_shared[0].weight  # [nh, L, 3, 3] -> [9, L, nh]
         return w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]).contiguous()
 
+    def table_and_bias(self):
+        """mlp_shared as a 9-tap table [9,L,nh] + bias; an autograd view of the conv weight, so
+        the table gradient K1's backward returns flows into ``mlp_shared.0.weight``."""
+        return self._table(), self.mlp_shared[0].bias
+
     def fm_size(self, H, W):
         mx = getattr(self.opt, 'max_fm_size', 1 << 30) if self.kind != 'spade' else 1 << 30
         return min(H, mx), min(W, mx)
 
-    def build_sources(self, ctx, H, W, want_lo):
-        """-> list of SplitPlanes feeding K1's A operand at resolution (H, W)."""
+    def build_sources(self, ctx, style, H, W, want_lo, table=None, bias=None):
+        """-> (list of SplitPlanes feeding K1's A operand at resolution (H, W), meta). ``meta``
+        records what each source is ('actv' = mlp_shared output, 'style' = gathered style matrix),
+        the label map and the folded-upsample flag - what the backward pass needs."""
         fh, fw = self.fm_size(H, W)
         if (fh, fw) == (H, W):
             ups = 0
@@ -125,18 +132,25 @@ class _CondNormBase(nn.Module):
         need_actv = self.kind in ('spade', 'sean') or ups == 1
         actv = None
         if need_actv:
-            actv = ops.shared_mlp(labels, self._table(), self.mlp_shared[0].bias, ups=ups,
-                                  want_lo=want_lo)
+            if table is None:
+                table, bias = self.table_and_bias()
+            actv = ops.shared_mlp(labels, table.detach(), bias.detach(), ups=ups, want_lo=want_lo)
+        meta = {'labels': labels, 'ups': ups, 'actv': actv}
         if self.kind == 'spade':
-            return [actv]
+            meta['kinds'] = ['actv']
+            return [actv], meta
         if ups == 1:
             # normalization.py:188-190 / 275-277: style_map := upsampled actv (style is dropped)
-            style_map = actv
+            style_map, skind = actv, 'actv'
         else:
-            if ctx.style is None:
+            if style is None:
                 raise RuntimeError('%s needs a style matrix z' % type(self).__name__)
-            style_map = ops.style_gather(labels, ctx.style, want_lo=want_lo)
-        return [actv, style_map] if self.kind == 'sean' else [style_map]
+            style_map, skind = ops.style_gather(labels, style, want_lo=want_lo), 'style'
+        if self.kind == 'sean':
+            meta['kinds'] = ['actv', skind]
+            return [actv, style_map], meta
+        meta['kinds'] = [skind]
+        return [style_map], meta
 
     def combined_weight(self):
         """-> (W [2C, Cin_total, 3, 3] rows interleaved, gamma_bias [C], beta_bias [C]); plain

@@ -17,6 +17,38 @@ from .base_network import BaseNetwork
 from .normalization import GenContext
 
 
+class _StemFn(torch.autograd.Function):
+    """DeepSEESR.initial (sr.py:31,65). The LR image needs no gradient."""
+
+    @staticmethod
+    def forward(ctx, x_nchw, w, b):
+        ctx.save_for_backward(x_nchw)
+        return ops.stem(x_nchw, w.contiguous(), b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x_nchw,) = ctx.saved_tensors
+        dw, db = ops.stem_bwd(x_nchw, dy.contiguous())
+        return None, dw, db
+
+
+class _HeadFn(torch.autograd.Function):
+    """F.tanh(conv_img(F.leaky_relu(x, 0.2))) (sr.py:56,94-95), NHWC in, NCHW out."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc, w, b):
+        w = w.contiguous()
+        out = ops.head(x_nhwc, w, b)
+        ctx.save_for_backward(x_nhwc, w, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x_nhwc, w, out = ctx.saved_tensors
+        dx, dw, db = ops.head_bwd(x_nhwc, w, out, dout.contiguous())
+        return dx, dw, db
+
+
 class DeepSEESR(BaseNetwork):
     @staticmethod
     def modify_commandline_options(parser, is_train):
@@ -61,13 +93,13 @@ class DeepSEESR(BaseNetwork):
         labels, bad = ops.labels_from_onehot(seg)
         ctx = GenContext(labels, z.contiguous().float() if z is not None else None)
 
-        x = ops.stem(x_downsized, self.initial.weight.contiguous(), self.initial.bias)
+        x = _StemFn.apply(x_downsized, self.initial.weight, self.initial.bias)
         x, st = self.head_0.forward_nhwc(x, ctx, ups=0)
         x, st = self.G_middle_0.forward_nhwc(x, ctx, ups=1, stats_in=st)
         x, st = self.G_middle_1.forward_nhwc(x, ctx, ups=0, stats_in=st)
         for i in range(self.n_blocks - 1):
             x, st = self.up_list[i].forward_nhwc(x, ctx, ups=1, stats_in=st)
-        out = ops.head(x, self.conv_img.weight.contiguous(), self.conv_img.bias)
+        out = _HeadFn.apply(x, self.conv_img.weight, self.conv_img.bias)
         if config.check_onehot and int(bad.item()) != 0:
             raise ValueError('DeepSEESR: `seg` must be a one-hot map (exactly one 1.0 per pixel); '
                              'the B200 path consumes it as an integer label map')

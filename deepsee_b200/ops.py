@@ -136,16 +136,19 @@ def style_gather(labels, style, want_lo=True):
     return SplitPlanes(hi, lo)
 
 
-def prep_conv_weight(w, want_lo=True):
-    """fp32 [N,C,3,3] -> scaled fp16 split planes [N, 9*C] in (tap, c) order."""
+def prep_conv_weight(w, want_lo=True, transpose=False):
+    """fp32 [N,C,3,3] -> scaled fp16 split planes [N, 9*C] in (tap, c) order.
+    transpose=True: the backward-data operand [C, 9*N] (transposed, 180-degree rotated)."""
     _chk_cuda(w)
     assert w.dtype == torch.float32 and w.dim() == 4 and w.shape[2:] == (3, 3)
     N, Cin = w.shape[:2]
-    hi = torch.empty((N, 9 * Cin), dtype=torch.float16, device=w.device)
+    rows, cols = (Cin, N) if transpose else (N, Cin)
+    hi = torch.empty((rows, 9 * cols), dtype=torch.float16, device=w.device)
     lo = torch.empty_like(hi) if want_lo else None
     inv = torch.empty(2, dtype=torch.float32, device=w.device)
-    _lib.check(_lib.load().dsee_prep_conv_weight(_p(w), _p(hi), _p(lo), _p(inv), N, Cin, _stream()))
-    return PreparedWeight(hi, lo, inv, N, Cin)
+    _lib.check(_lib.load().dsee_prep_conv_weight(_p(w), _p(hi), _p(lo), _p(inv), N, Cin,
+                                                 int(transpose), _stream()))
+    return PreparedWeight(hi, lo, inv, rows, cols)
 
 
 def split_f16(x, want_lo=True):
@@ -160,6 +163,9 @@ def split_f16(x, want_lo=True):
 # ---------------------------------------------------------------------------------------------
 # tensor-core kernels
 # ---------------------------------------------------------------------------------------------
+_DTYPE_CODE = {torch.float16: 0, torch.bfloat16: 1}
+
+
 def _operands(sources, pw, passes):
     a0 = sources[0]
     B, H, W, C0 = a0.hi.shape
@@ -171,7 +177,7 @@ def _operands(sources, pw, passes):
         if i < len(sources):
             s = sources[i]
             _chk_cuda(s.hi, s.lo)
-            assert s.hi.dtype == torch.float16 and tuple(s.hi.shape[:3]) == (B, H, W)
+            assert s.hi.dtype == a0.hi.dtype and tuple(s.hi.shape[:3]) == (B, H, W)
             ops.a_hi[i] = s.hi.data_ptr()
             ops.a_lo[i] = s.lo.data_ptr() if s.lo is not None else 0
             ops.a_channels[i] = s.hi.shape[3]
@@ -187,12 +193,17 @@ def _operands(sources, pw, passes):
     ops.w_inv_scale = pw.inv_scale.data_ptr()
     ops.n_total = pw.n_total
     ops.passes = passes
+    ops.a_dtype = _DTYPE_CODE[a0.hi.dtype]
+    ops.w_dtype = _DTYPE_CODE[pw.hi.dtype]
     return ops, (B, H, W)
 
 
-def conv3x3(sources, pw, bias, residual=None, res_ups=0, noises=(), passes=3, want_stats=False):
+def conv3x3(sources, pw, bias, residual=None, res_ups=0, noises=(), passes=3, want_stats=False,
+            act_mask=None, tag="conv3x3"):
     """K2: 3x3 conv + bias (+ residual through an optional folded 2x upsample, + up to two
     NoiseInjection terms ``(noise NHWC, weight[C])``) -> fp32 NHWC.
+    Backward-data use: ``sources`` = gradient planes (bf16), ``pw`` prepared with transpose=True,
+    bias None, ``act_mask`` = fp16 hi plane of the forward activation (LeakyReLU' folded in).
 
     Returns out, or (out, stats_partial) when want_stats (partials for bn_finalize)."""
     ops, (B, H, W) = _operands(sources, pw, passes)
@@ -204,7 +215,8 @@ def conv3x3(sources, pw, bias, residual=None, res_ups=0, noises=(), passes=3, wa
         nt = _lib.load().dsee_conv3x3_stats_tiles(B, H, W)
         stats = torch.empty((nt, pw.n_total, 2), dtype=torch.float32, device=dev)
     epi = _lib.ConvEpilogue()
-    epi.bias = bias.data_ptr()
+    epi.bias = bias.data_ptr() if bias is not None else 0
+    epi.act_mask = act_mask.data_ptr() if act_mask is not None else 0
     epi.residual = residual.data_ptr() if residual is not None else 0
     epi.res_ups = res_ups
     noises = [n for n in noises if n is not None]
@@ -220,7 +232,7 @@ def conv3x3(sources, pw, bias, residual=None, res_ups=0, noises=(), passes=3, wa
     epi.out = out.data_ptr()
     epi.stats_partial = stats.data_ptr() if stats is not None else 0
     flops = 2.0 * 9 * pw.cin * pw.n_total * B * H * W  # reference-equivalent dense conv FLOPs
-    _timed("conv3x3_%dx%d" % (H, W), flops,
+    _timed("%s_%dx%d" % (tag, H, W), flops,
            lambda: _lib.check(_lib.load().dsee_conv3x3_fwd(C.byref(ops), C.byref(epi), _stream())))
     return (out, stats) if want_stats else out
 
@@ -248,6 +260,155 @@ def spade_modulate(sources, pw, x, x_ups, bn_scale, bn_shift, gamma_bias, beta_b
     _timed("modulate_%dx%d" % (H, W), flops,
            lambda: _lib.check(_lib.load().dsee_spade_modulate_fwd(C.byref(ops), C.byref(m), _stream())))
     return SplitPlanes(hi, lo)
+
+
+# ---------------------------------------------------------------------------------------------
+# generator backward
+# ---------------------------------------------------------------------------------------------
+def grad_prep(dy, noise0=None, noise1=None, want_lo=True):
+    """dY fp32 NHWC -> (bf16 SplitPlanes, sums fp32 [nq,C]): sums[0] = sum dY (bias gradient),
+    sums[1+i] = sum dY*noise_i (NoiseInjection.weight gradients)."""
+    _chk_cuda(dy, noise0, noise1)
+    Cc = dy.shape[-1]
+    npix = dy.numel() // Cc
+    lib = _lib.load()
+    hi = torch.empty(dy.shape, dtype=torch.bfloat16, device=dy.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    nq = 1 + (noise0 is not None) + (noise1 is not None)
+    nb = lib.dsee_grad_prep_blocks(npix)
+    part = torch.empty((nb, Cc, nq), dtype=torch.float32, device=dy.device)
+    _lib.check(lib.dsee_grad_prep(_p(dy), _p(hi), _p(lo), _p(noise0), _p(noise1), npix, Cc, _p(part),
+                                  _stream()))
+    return SplitPlanes(hi, lo), reduce_partials(part)
+
+
+def reduce_partials(part, scale=1.0):
+    """[n,C,nq] block partials -> [nq,C] (fixed order, double accumulation)."""
+    _chk_cuda(part)
+    n, Cc, nq = part.shape
+    out = torch.empty((nq, Cc), dtype=torch.float32, device=part.device)
+    _lib.check(_lib.load().dsee_reduce_partials(_p(part), n, Cc, nq, float(scale), _p(out), _stream()))
+    return out
+
+
+def conv3x3_wgrad(dy, a, passes=3, scale=1.0):
+    """dW[n][c][3][3] = sum_pixels dY[.,n] * A[.+tap,c]; dy / a are SplitPlanes NHWC."""
+    _chk_cuda(dy.hi, dy.lo, a.hi, a.lo)
+    B, H, W, N = dy.hi.shape
+    Cc = a.hi.shape[3]
+    assert tuple(a.hi.shape[:3]) == (B, H, W)
+    lib = _lib.load()
+    ws = torch.empty(lib.dsee_conv3x3_wgrad_workspace_floats(B, H, W, N, Cc), dtype=torch.float32,
+                     device=dy.hi.device)
+    dw = torch.empty((N, Cc, 3, 3), dtype=torch.float32, device=dy.hi.device)
+    flops = 2.0 * 9 * Cc * N * B * H * W
+    _timed("wgrad_%dx%d" % (H, W), flops, lambda: _lib.check(lib.dsee_conv3x3_wgrad(
+        _p(dy.hi), _p(dy.lo), _DTYPE_CODE[dy.hi.dtype], _p(a.hi), _p(a.lo), _DTYPE_CODE[a.hi.dtype],
+        B, H, W, N, Cc, passes, float(scale), _p(ws), _p(dw), 1, _stream())))
+    return dw
+
+
+def spade_modulate_bwd(sources, pw_gamma, x, x_ups, bn_scale, bn_shift, gamma_bias, dt, noise=None,
+                       noise_w=None, passes=3, want_lo=True):
+    """K1 backward -> (dxhat fp32 NHWC, dgb bf16 SplitPlanes [B,H,W,2C] interleaved,
+    sums fp32 [4,C] = sum dxhat, sum dxhat*xhat, sum dG, sum dB)."""
+    ops, (B, H, W) = _operands(sources, pw_gamma, passes)
+    _chk_cuda(x, bn_scale, bn_shift, gamma_bias, dt, noise, noise_w)
+    Cc = x.shape[3]
+    assert pw_gamma.n_total == Cc and tuple(dt.shape) == (B, H, W, Cc)
+    dev = x.device
+    lib = _lib.load()
+    dxhat = torch.empty((B, H, W, Cc), dtype=torch.float32, device=dev)
+    ghi = torch.empty((B, H, W, 2 * Cc), dtype=torch.bfloat16, device=dev)
+    glo = torch.empty_like(ghi) if want_lo else None
+    part = torch.empty((lib.dsee_conv3x3_stats_tiles(B, H, W), Cc, 4), dtype=torch.float32, device=dev)
+    m = _lib.ModulateBwdArgs()
+    m.x, m.x_ups = x.data_ptr(), x_ups
+    m.noise = noise.data_ptr() if noise is not None else 0
+    m.noise_w = noise_w.data_ptr() if noise_w is not None else 0
+    m.bn_scale, m.bn_shift = bn_scale.data_ptr(), bn_shift.data_ptr()
+    m.gamma_bias, m.dt = gamma_bias.data_ptr(), dt.data_ptr()
+    m.dxhat, m.dgb_hi = dxhat.data_ptr(), ghi.data_ptr()
+    m.dgb_lo = glo.data_ptr() if glo is not None else 0
+    m.partial = part.data_ptr()
+    m.C = Cc
+    flops = 2.0 * 9 * pw_gamma.cin * pw_gamma.n_total * B * H * W
+    _timed("modulate_bwd_%dx%d" % (H, W), flops,
+           lambda: _lib.check(lib.dsee_spade_modulate_bwd(C.byref(ops), C.byref(m), _stream())))
+    return dxhat, SplitPlanes(ghi, glo), reduce_partials(part)
+
+
+def bn_bwd(dxhat, x, x_ups, bn_scale, bn_shift, sums, inv_count, noise=None, noise_w=None, dskip=None):
+    """-> (dx fp32 NHWC at x's resolution, d noise_w [C] or None)."""
+    _chk_cuda(dxhat, x, bn_scale, bn_shift, sums, noise, noise_w, dskip)
+    B, Hx, Wx, Cc = x.shape
+    lib = _lib.load()
+    dx = torch.empty_like(x)
+    nwp = None
+    if noise is not None:
+        nwp = torch.empty((lib.dsee_bn_bwd_blocks(B, Hx, Wx), Cc, 1), dtype=torch.float32,
+                          device=x.device)
+    _lib.check(lib.dsee_bn_bwd(_p(dxhat), _p(x), x_ups, _p(noise), _p(noise_w), _p(bn_scale),
+                               _p(bn_shift), _p(sums), float(inv_count), _p(dskip), B, Hx, Wx, Cc,
+                               _p(dx), _p(nwp), _stream()))
+    return dx, (reduce_partials(nwp)[0] if nwp is not None else None)
+
+
+def shared_mlp_bwd(dsrc, coff, actv_hi, labels, ups, L):
+    """Gradient of the 9-tap table and the bias: -> (dtable [9,L,nh], dbias [nh])."""
+    _chk_cuda(dsrc, actv_hi, labels)
+    B, Hl, Wl = labels.shape
+    nh = actv_hi.shape[3]
+    ld = dsrc.shape[3]
+    lib = _lib.load()
+    rows = 9 * L + 1
+    part = torch.empty((lib.dsee_shared_mlp_bwd_blocks(B, Hl, Wl), rows, nh), dtype=torch.float32,
+                       device=dsrc.device)
+    out = torch.empty((rows, nh), dtype=torch.float32, device=dsrc.device)
+    _lib.check(lib.dsee_shared_mlp_bwd(_p(dsrc), ld, coff, _p(actv_hi), _p(labels), B, Hl, Wl, ups, L,
+                                       nh, _p(part), _p(out), _stream()))
+    return out[:9 * L].view(9, L, nh), out[9 * L]
+
+
+def style_gather_bwd(dsrc, coff, labels, L, d):
+    """dstyle[b,l,:] = sum over pixels with label l of dsrc[b,y,x,coff:coff+d]."""
+    _chk_cuda(dsrc, labels)
+    B, H, W = labels.shape
+    lib = _lib.load()
+    ws = torch.empty((B, lib.dsee_region_pool_chunks(H * W), L, d), dtype=torch.float32,
+                     device=dsrc.device)
+    out = torch.empty((B, L, d), dtype=torch.float32, device=dsrc.device)
+    _lib.check(lib.dsee_style_gather_bwd(_p(dsrc), dsrc.shape[3], coff, _p(labels), _p(out), _p(ws), B,
+                                         H * W, L, d, _stream()))
+    return out
+
+
+def stem_bwd(x_nchw, dy):
+    """-> (dW [C,3,3,3], dbias [C])."""
+    _chk_cuda(x_nchw, dy)
+    B, _, H, W = x_nchw.shape
+    Cc = dy.shape[3]
+    lib = _lib.load()
+    part = torch.empty((lib.dsee_stem_bwd_blocks(B, H, W), Cc, 28), dtype=torch.float32, device=dy.device)
+    out = torch.empty((Cc, 28), dtype=torch.float32, device=dy.device)
+    _lib.check(lib.dsee_stem_bwd(_p(x_nchw), _p(dy), B, H, W, Cc, _p(part), _p(out), _stream()))
+    return out[:, :27].reshape(Cc, 3, 3, 3), out[:, 27].contiguous()
+
+
+def head_bwd(x_nhwc, w, out, dout):
+    """-> (dx fp32 NHWC, dW [3,C,3,3], dbias [3])."""
+    _chk_cuda(x_nhwc, w, out, dout)
+    B, H, W, Cc = x_nhwc.shape
+    lib = _lib.load()
+    dpre = torch.empty_like(out)
+    dx = torch.empty_like(x_nhwc)
+    part = torch.empty((lib.dsee_head_bwd_blocks(B, H, W), Cc, 28), dtype=torch.float32,
+                       device=dout.device)
+    res = torch.empty((Cc, 28), dtype=torch.float32, device=dout.device)
+    _lib.check(lib.dsee_head_bwd(_p(x_nhwc), _p(w), _p(out), _p(dout), B, H, W, Cc, _p(dpre), _p(dx),
+                                 _p(part), _p(res), _stream()))
+    dw = res[:, :27].reshape(Cc, 3, 9).permute(1, 0, 2).reshape(3, Cc, 3, 3).contiguous()
+    return dx, dw, res[:3, 27].contiguous()
 
 
 # ---------------------------------------------------------------------------------------------

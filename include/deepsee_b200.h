@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DSEE_ABI_VERSION 1
+#define DSEE_ABI_VERSION 2
 
 /* ---- library ------------------------------------------------------------------------------ */
 int dsee_version(void);
@@ -76,9 +76,12 @@ int dsee_style_gather_fwd(const uint8_t* labels, const float* style, void* out_h
  * architecture.py:40-44) -> GEMM B-operand planes fp16 [N][9*C] with k = (ky*3+kx)*C + c,
  * multiplied by a power of two 2^e chosen so max|w|*2^e is in [2^13, 2^14) (keeps the lo plane
  * out of the fp16 subnormal range). inv_scale is a device float[2]: [0] receives 2^-e (what the
- * conv kernels read), [1] is scratch (max|w|). */
+ * conv kernels read), [1] is scratch (max|w|).
+ * transpose=1 builds the backward-data operand instead (autograd of F.conv2d wrt its input =
+ * convolution of the output gradient with the transposed, 180-degree-rotated filter):
+ * planes [C][9*N] with k = (8-tap)*N + n. */
 int dsee_prep_conv_weight(const float* w, void* out_hi, void* out_lo, float* inv_scale, int N,
-                          int C, void* stream);
+                          int C, int transpose, void* stream);
 /* fp32 NHWC [rows][C] -> fp16 split planes (used for tensors not produced by a fused epilogue). */
 int dsee_split_f16(const float* in, void* out_hi, void* out_lo, int64_t n, void* stream);
 
@@ -97,6 +100,8 @@ typedef struct {
     const float* w_inv_scale; /* device scalar */
     int n_total;
     int passes; /* 1: hi*hi (TF32-class accuracy)   3: hi*hi + lo*hi + hi*lo (fp32-class) */
+    int a_dtype; /* element type of the A planes: 0 fp16 (activations), 1 bf16 (gradients) */
+    int w_dtype; /* element type of the weight planes: 0 fp16, 1 bf16 */
 } dsee_conv_operands;
 
 /* K2.  Replaces conv_0 / conv_1 of SPADEResnetBlock (architecture.py:34-35,98,122) plus what the
@@ -120,6 +125,11 @@ typedef struct {
     const float* noise_w[2];
     float* out;
     float* stats_partial;
+    /* backward-data use (the same kernel run on the output gradient with the transposed,
+     * flipped weight): multiply by LeakyReLU'(t), 1 where act_mask > 0 else 0.2
+     * (architecture.py:147 backward). act_mask = the hi plane K1 wrote in the forward pass,
+     * fp16 NHWC [B,H,W,n_total], or NULL. bias may be NULL (= 0). */
+    const void* act_mask;
 } dsee_conv_epilogue;
 int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_epilogue* epi, void* stream);
 int dsee_conv3x3_stats_tiles(int B, int H, int W);
@@ -150,6 +160,99 @@ typedef struct {
 } dsee_modulate_args;
 int dsee_spade_modulate_fwd(const dsee_conv_operands* ops, const dsee_modulate_args* mod,
                             void* stream);
+
+/* K1 backward.  Re-runs the gamma half of the modulation GEMM (weights: the gamma rows only,
+ * n_total == C, prepared with dsee_prep_conv_weight) and, with G = gamma + gamma_bias,
+ * xhat = xin*bn_scale + bn_shift, dt = dL/dt:
+ *   dxhat = dt * G                                 -> fp32 NHWC [B,H,W,C]
+ *   [dG | dB] = [dt * xhat | dt]                   -> bf16 split planes NHWC [B,H,W,2C], channels
+ *                                                     interleaved per 128 like the forward weights
+ *                                                     (A operand of the two following GEMMs)
+ *   partial[tile][c] = (sum dxhat, sum dxhat*xhat, sum dG, sum dB) over the tile's pixels
+ *     (first two: batch-norm backward, batchnorm.py:78-93 differentiated; last two: gradients of
+ *      gamma_bias / beta_bias). partial: fp32 [dsee_conv3x3_stats_tiles()][C][4]. */
+typedef struct {
+    const float* x;
+    int x_ups;
+    const float* noise;
+    const float* noise_w;
+    const float* bn_scale;
+    const float* bn_shift;
+    const float* gamma_bias;
+    const float* dt;
+    float* dxhat;
+    void* dgb_hi;
+    void* dgb_lo; /* may be NULL */
+    float* partial;
+    int C;
+} dsee_modulate_bwd_args;
+int dsee_spade_modulate_bwd(const dsee_conv_operands* ops, const dsee_modulate_bwd_args* args,
+                            void* stream);
+
+/* ---- generator backward (autograd of the fused kernels above) -------------------------------- */
+/* Gradient tensors are fp32 NHWC in HBM; as tensor-core operands they are bf16 split planes
+ * (value = hi + lo; bf16 keeps fp32's exponent range, so no loss scaling is needed).
+ *
+ * Backward-data of K2 / K1's GEMM is dsee_conv3x3_fwd itself, run on the gradient planes
+ * (a_dtype = 1) with a weight from dsee_prep_conv_weight(transpose=1); dsee_conv_epilogue.act_mask
+ * folds in LeakyReLU'. */
+
+/* dY fp32 NHWC [npix][C] -> bf16 split planes, plus per-channel block partials of
+ * (sum dY, sum dY*noise0, sum dY*noise1) = gradients of a conv bias (architecture.py:98,122) and of
+ * NoiseInjection.weight (normalization.py:299-304).  partial fp32 [dsee_grad_prep_blocks()][C][nq],
+ * nq = 1 + (noise0 != NULL) + (noise1 != NULL); reduce with dsee_reduce_partials. */
+int dsee_grad_prep_blocks(int64_t npix);
+int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, const float* noise0,
+                   const float* noise1, int64_t npix, int C, float* partial, void* stream);
+/* out[k][c] = scale * sum_s partial[s][c][k]  (double accumulation, fixed order). */
+int dsee_reduce_partials(const float* partial, int n, int C, int nq, float scale, float* out,
+                         void* stream);
+/* Weight gradient of a 3x3 conv (autograd of architecture.py:98,122 and normalization.py:116-117,
+ * 198-201,283-284): dW[n][c][tap] = scale * sum_{b,y,x} dY[b,y,x,n] * A[b,y+dy,x+dx,c].
+ * dY planes [B,H,W,n_total] (n_total % 128 == 0), A planes [B,H,W,c_total] (c_total = 64, 128 or a
+ * multiple of 256); dtype 0 fp16 / 1 bf16 per operand.  workspace fp32
+ * [dsee_conv3x3_wgrad_workspace_floats()]; dw fp32 [n_total][c_total][3][3] (layout_nc9 = 1, the
+ * PyTorch layout) or [n_total][9][c_total] (layout_nc9 = 0).  Deterministic split-K. */
+int64_t dsee_conv3x3_wgrad_workspace_floats(int B, int H, int W, int n_total, int c_total);
+int dsee_conv3x3_wgrad(const void* dy_hi, const void* dy_lo, int dy_dtype, const void* a_hi,
+                       const void* a_lo, int a_dtype, int B, int H, int W, int n_total, int c_total,
+                       int passes, float scale, float* workspace, float* dw, int layout_nc9,
+                       void* stream);
+/* Batch-norm backward (differentiates batchnorm.py:78-93 / F.batch_norm in training mode) with the
+ * folded 2x upsample transposed into a 2x2 sum and the identity shortcut's gradient added:
+ *   xhat = (x[up] + noise_w*noise) * bn_scale + bn_shift
+ *   dxin = bn_scale * (dxhat - inv_count*sums[0] - xhat * inv_count*sums[1])
+ *   dx[b,y',x',c] = sum over the 2^ups x 2^ups block of (dxin + dskip)
+ * sums fp32 [2][C] = (sum dxhat, sum dxhat*xhat) (pass inv_count = 0 for eval-mode statistics);
+ * dskip fp32 NHWC [B,Hx<<ups,Wx<<ups,C] or NULL; nw_partial NULL or fp32
+ * [dsee_bn_bwd_blocks()][C] = block partials of sum(dxin*noise) (gradient of noise_in.weight). */
+int dsee_bn_bwd_blocks(int B, int Hx, int Wx);
+int dsee_bn_bwd(const float* dxhat, const float* x, int x_ups, const float* noise,
+                const float* noise_w, const float* bn_scale, const float* bn_shift,
+                const float* sums, float inv_count, const float* dskip, int B, int Hx, int Wx, int C,
+                float* dx, float* nw_partial, void* stream);
+/* Backward of dsee_shared_mlp_fwd: gradient of the 9-tap table and bias.  dsrc fp32 NHWC with row
+ * stride ld, the actv gradient in columns [coff, coff+nh).  partial fp32
+ * [dsee_shared_mlp_bwd_blocks()][9*L+1][nh]; dtable_dbias fp32 [9*L+1][nh] (last row = bias). */
+int dsee_shared_mlp_bwd_blocks(int B, int Hl, int Wl);
+int dsee_shared_mlp_bwd(const float* dsrc, int ld, int coff, const void* actv_hi,
+                        const uint8_t* labels, int B, int Hl, int Wl, int ups, int L, int nh,
+                        float* partial, float* dtable_dbias, void* stream);
+/* Backward of dsee_style_gather_fwd: dstyle[b,l,:] = sum_{p: labels[b,p]==l} dsrc[b,p,coff:coff+d].
+ * workspace fp32 [B][dsee_region_pool_chunks(HW)][L][d]. */
+int dsee_style_gather_bwd(const float* dsrc, int ld, int coff, const uint8_t* labels, float* dstyle,
+                          float* workspace, int B, int HW, int L, int d, void* stream);
+/* Backward of dsee_stem_fwd (weights only; the LR image needs no gradient).
+ * partial fp32 [dsee_stem_bwd_blocks()][C][28]; dw_db fp32 [C][28] = 27 weight grads + bias grad. */
+int dsee_stem_bwd_blocks(int B, int H, int W);
+int dsee_stem_bwd(const float* x, const float* dy, int B, int H, int W, int C, float* partial,
+                  float* dw_db, void* stream);
+/* Backward of dsee_head_fwd.  out = the forward result, dout its gradient (NCHW [B,3,H,W]);
+ * dpre scratch fp32 [B,3,H,W]; dx fp32 NHWC [B,H,W,C]; partial fp32 [dsee_head_bwd_blocks()][C][28];
+ * dw_db fp32 [C][28]: [c][o*9+tap] = dW[o][c][tap], [c][27] = dbias[c] for c < 3. */
+int dsee_head_bwd_blocks(int B, int H, int W);
+int dsee_head_bwd(const float* x, const float* w, const float* out, const float* dout, int B, int H,
+                  int W, int C, float* dpre, float* dx, float* partial, float* dw_db, void* stream);
 
 /* ---- batch-norm statistics ------------------------------------------------------------------ */
 /* Per-channel sum / sum of squares of x (+ noise) at the post-upsample resolution, written as

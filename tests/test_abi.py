@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libdeepsee_b200.so does not export %s" % n
     assert sorted(_lib.SYMBOLS) == names, "deepsee_b200/_lib.py SYMBOLS is out of sync with the header"
-    assert lib.dsee_version() == 1
+    assert lib.dsee_version() == _lib.ABI_VERSION
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

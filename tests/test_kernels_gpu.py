@@ -178,3 +178,139 @@ def test_stem_head_and_bn_stats():
     torch.testing.assert_close(rm, bn.running_mean, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(rv, bn.running_var, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(sc, 1 / torch.sqrt(var + 1e-5), rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# backward kernels
+# ---------------------------------------------------------------------------------------------
+def _bf16_planes(t):
+    from deepsee_b200 import ops
+    planes, sums = ops.grad_prep(t)
+    return planes, sums
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 128, 128), (2, 16, 16, 128, 256),
+                                            (1, 24, 40, 512, 512), (2, 12, 20, 64, 128)])
+@pytest.mark.parametrize("passes", [1, 3])
+def test_wgrad_and_dgrad_match_autograd(B, H, W, Cin, Cout, passes):
+    """conv3x3_wgrad (bf16 gradient planes x fp16 activation planes, MN-major tcgen05 operands) and
+    backward-data (the forward kernel on gradient planes with the transposed filter) against
+    torch autograd of F.conv2d."""
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(H * 7 + Cin + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda().requires_grad_(True)
+    dy = torch.randn(B, Cout, H, W, generator=g).cuda()
+    F.conv2d(x, w, None, padding=1).backward(dy)
+    a = ops.split_f16(_nhwc(x.detach()))
+    gp, sums = ops.grad_prep(_nhwc(dy))
+    torch.testing.assert_close(sums[0], dy.sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-3)
+    dw = ops.conv3x3_wgrad(gp, a, passes=passes)
+    tol = 3e-5 if passes == 3 else 2e-2
+    s = w.grad.abs().max().item()
+    err = (dw - w.grad).abs().max().item()
+    assert err <= tol * s, ("wgrad", err, s)
+    pwT = ops.prep_conv_weight(w.detach(), transpose=True)
+    dx = _nchw(ops.conv3x3([gp], pwT, None, passes=passes))
+    s = x.grad.abs().max().item()
+    err = (dx - x.grad).abs().max().item()
+    assert err <= tol * s, ("dgrad", err, s)
+
+
+def test_dgrad_leaky_relu_mask():
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, H, W, C = 1, 16, 16, 128
+    t = torch.randn(B, C, H, W, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(C, C, 3, 3, generator=g) / (3 * C ** 0.5)).cuda()
+    dy = torch.randn(B, C, H, W, generator=g).cuda()
+    act = F.leaky_relu(t, 0.2)
+    F.conv2d(act, w, None, padding=1).backward(dy)
+    a = ops.split_f16(_nhwc(act.detach()))
+    gp, _ = ops.grad_prep(_nhwc(dy))
+    pwT = ops.prep_conv_weight(w, transpose=True)
+    dt = _nchw(ops.conv3x3([gp], pwT, None, passes=3, act_mask=a.hi))
+    assert (dt - t.grad).abs().max().item() <= 3e-5 * t.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("ups,noisy", [(0, False), (1, True), (1, False)])
+def test_bn_bwd_matches_autograd(ups, noisy):
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(11 + ups)
+    B, Hx, Wx, C = 2, 8, 12, 128
+    H, W = Hx << ups, Wx << ups
+    x = torch.randn(B, C, Hx, Wx, generator=g).cuda().requires_grad_(True)
+    noise = torch.randn(B, C, H, W, generator=g).cuda()
+    nw = (torch.randn(C, generator=g) * 0.3).cuda().requires_grad_(True)
+    dxhat = torch.randn(B, C, H, W, generator=g).cuda()
+    dskip = torch.randn(B, C, H, W, generator=g).cuda()
+    xu = F.interpolate(x, scale_factor=2, mode="nearest") if ups else x
+    xin = xu + nw.view(1, -1, 1, 1) * noise if noisy else xu
+    xhat = F.batch_norm(xin, None, None, None, None, True, 0.1, 1e-5)
+    ((xhat * dxhat).sum() + (xu * dskip).sum()).backward()
+    n_ = _nhwc(noise) if noisy else None
+    part = ops.bn_stats(_nhwc(x.detach()), ups, n_, nw.detach() if noisy else None)
+    sc, sh, _, _ = ops.bn_finalize(part, B * H * W, 1e-5)
+    xh = _nhwc(xhat.detach())
+    dxh = _nhwc(dxhat)
+    sums = torch.stack([dxh.sum(dim=(0, 1, 2)), (dxh * xh).sum(dim=(0, 1, 2))]).contiguous()
+    dx, dnw = ops.bn_bwd(dxh, _nhwc(x.detach()), ups, sc, sh, sums, 1.0 / (B * H * W), noise=n_,
+                         noise_w=nw.detach() if noisy else None, dskip=_nhwc(dskip))
+    torch.testing.assert_close(_nchw(dx), x.grad, rtol=1e-3, atol=2e-4)
+    if noisy:
+        torch.testing.assert_close(dnw, nw.grad, rtol=1e-3, atol=2e-3)
+
+
+def test_stem_and_head_backward():
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    B, H, W, C = 2, 12, 20, 128
+    x = torch.randn(B, 3, H, W, generator=g).cuda()
+    w = (torch.randn(C, 3, 3, 3, generator=g) * 0.2).cuda().requires_grad_(True)
+    b = torch.randn(C, generator=g).cuda().requires_grad_(True)
+    dy = torch.randn(B, C, H, W, generator=g).cuda()
+    F.conv2d(x, w, b, padding=1).backward(dy)
+    dw, db = ops.stem_bwd(x, _nhwc(dy))
+    torch.testing.assert_close(dw, w.grad, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(db, b.grad, rtol=1e-4, atol=1e-3)
+
+    xh = torch.randn(B, C, H, W, generator=g).cuda().requires_grad_(True)
+    wh = (torch.randn(3, C, 3, 3, generator=g) / (3 * C ** 0.5)).cuda().requires_grad_(True)
+    bh = torch.randn(3, generator=g).cuda().requires_grad_(True)
+    dout = torch.randn(B, 3, H, W, generator=g).cuda()
+    out = torch.tanh(F.conv2d(F.leaky_relu(xh, 0.2), wh, bh, padding=1))
+    out.backward(dout)
+    dx, dwh, dbh = ops.head_bwd(_nhwc(xh.detach()), wh.detach(), out.detach().contiguous(), dout)
+    torch.testing.assert_close(_nchw(dx), xh.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dwh, wh.grad, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(dbh, bh.grad, rtol=1e-4, atol=1e-3)
+
+
+def test_shared_mlp_and_style_gather_backward():
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(9)
+    B, Hl, Wl, L, nh, d = 2, 10, 14, 19, 128, 128
+    for ups in (0, 1):
+        H, W = Hl << ups, Wl << ups
+        labels = torch.randint(0, L, (B, Hl, Wl), generator=g, dtype=torch.uint8).cuda()
+        wt = (torch.randn(nh, L, 3, 3, generator=g) * 0.5).cuda().requires_grad_(True)
+        bias = torch.randn(nh, generator=g).cuda().requires_grad_(True)
+        style = torch.randn(B, L, d, generator=g).cuda().requires_grad_(True)
+        onehot = F.one_hot(labels.long(), L).permute(0, 3, 1, 2).float()
+        actv = F.relu(F.conv2d(onehot, wt, bias, padding=1))
+        smap = torch.einsum("bld,blhw->bdhw", style, onehot)
+        if ups:
+            actv = F.interpolate(actv, scale_factor=2, mode="nearest")
+            smap = F.interpolate(smap, scale_factor=2, mode="nearest")
+        dsrc = torch.randn(B, H, W, nh + d, generator=g).cuda()
+        (actv * dsrc[..., :nh].permute(0, 3, 1, 2)).sum().backward(retain_graph=True)
+        (smap * dsrc[..., nh:].permute(0, 3, 1, 2)).sum().backward()
+        table = wt.detach().permute(2, 3, 1, 0).reshape(9, L, nh).contiguous()
+        planes = ops.shared_mlp(labels, table, bias.detach(), ups=ups)
+        dtab, dtb = ops.shared_mlp_bwd(dsrc, 0, planes.hi, labels, ups, L)
+        ref_tab = wt.grad.permute(2, 3, 1, 0).reshape(9, L, nh)
+        torch.testing.assert_close(dtab, ref_tab, rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(dtb, bias.grad, rtol=1e-4, atol=1e-3)
+        if not ups:
+            ds = ops.style_gather_bwd(dsrc, nh, labels, L, d)
+            torch.testing.assert_close(ds, style.grad, rtol=1e-4, atol=1e-3)
