@@ -34,6 +34,7 @@ class ConvOperands(C.Structure):
         ("a_hi", C.c_void_p * 2), ("a_lo", C.c_void_p * 2), ("a_channels", C.c_int * 2),
         ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("w_inv_scale", C.c_void_p),
         ("n_total", C.c_int), ("passes", C.c_int), ("a_dtype", C.c_int), ("w_dtype", C.c_int),
+        ("a_inv_scale", C.c_void_p),
     ]
 
 
@@ -42,6 +43,7 @@ class ConvEpilogue(C.Structure):
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("res_ups", C.c_int),
         ("noise", C.c_void_p * 2), ("noise_w", C.c_void_p * 2),
         ("out", C.c_void_p), ("stats_partial", C.c_void_p), ("act_mask", C.c_void_p),
+        ("amax_out", C.c_void_p),
     ]
 
 
@@ -64,6 +66,7 @@ class ModulateBwdArgs(C.Structure):
         ("gamma_bias", C.c_void_p), ("dt", C.c_void_p),
         ("dxhat", C.c_void_p), ("dgb_hi", C.c_void_p), ("dgb_lo", C.c_void_p),
         ("partial", C.c_void_p), ("C", C.c_int),
+        ("dt_amax", C.c_void_p), ("dgb_inv_scale", C.c_void_p),
     ]
 
 
@@ -98,9 +101,9 @@ def load():
         "dsee_spade_modulate_fwd": [C.POINTER(ConvOperands), C.POINTER(ModulateArgs), vp],
         "dsee_spade_modulate_bwd": [C.POINTER(ConvOperands), C.POINTER(ModulateBwdArgs), vp],
         "dsee_grad_prep_blocks": [i64],
-        "dsee_grad_prep": [vp, vp, vp, vp, vp, i64, i, vp, vp],
+        "dsee_grad_prep": [vp, vp, vp, vp, vp, vp, i64, i, vp, vp],
         "dsee_reduce_partials": [vp, i, i, i, f, vp, vp],
-        "dsee_conv3x3_wgrad": [vp, vp, i, vp, vp, i, i, i, i, i, i, i, f, vp, vp, i, vp],
+        "dsee_conv3x3_wgrad": [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp, i, vp],
         "dsee_bn_bwd_blocks": [i, i, i],
         "dsee_bn_bwd": [vp, vp, i, vp, vp, vp, vp, vp, f, vp, i, i, i, i, vp, vp, vp],
         "dsee_shared_mlp_bwd_blocks": [i, i, i],

@@ -13,15 +13,30 @@ namespace dsee {
 static inline int cdivb(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ------------------------------------------------------------------------------------------------
-// dY (fp32 NHWC) -> bf16 split planes, + per-channel partial sums: sum dY, sum dY*noise_i
+// dY (fp32 NHWC) -> fp16 split planes scaled by 2^e (max|dY| * 2^e in [2^13, 2^14)),
+// + per-channel partial sums: sum dY, sum dY*noise_i
 // block = 256 threads = (C/4 channel quads) x pixel lanes, GP_PIX pixels per block
 // ------------------------------------------------------------------------------------------------
 constexpr int GP_PIX = 256;
-__global__ void grad_prep_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ hi,
-                                 __nv_bfloat16* __restrict__ lo, const float* __restrict__ n0,
-                                 const float* __restrict__ n1, int64_t npix, int C,
-                                 float* __restrict__ partial, int nq) {
+__global__ void grad_amax_kernel(const float* __restrict__ x, int64_t n4, float* __restrict__ amax) {
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f && !isinf(m) && !isnan(m)) atomic_max_nonneg(amax, m);
+}
+
+__global__ void grad_prep_kernel(const float* __restrict__ dy, __half* __restrict__ hi,
+                                 __half* __restrict__ lo, float* __restrict__ inv_scale,
+                                 const float* __restrict__ n0, const float* __restrict__ n1,
+                                 int64_t npix, int C, float* __restrict__ partial, int nq) {
     extern __shared__ float red[];  // [lanes][C][nq]
+    const float scale = pow2_scale_for(inv_scale[1], 14);
+    if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[0] = 1.f / scale;
     const int cg = C >> 2;
     const int lanes = blockDim.x / cg;
     const int g = threadIdx.x % cg, pl = threadIdx.x / cg;
@@ -36,11 +51,13 @@ __global__ void grad_prep_kernel(const float* __restrict__ dy, __nv_bfloat16* __
             uint32_t ph[2], plw[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(a[2 * e]), h1 = __float2bfloat16_rn(a[2 * e + 1]);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(a[2 * e] - __bfloat162float(h0));
-                const __nv_bfloat16 l1 = __float2bfloat16_rn(a[2 * e + 1] - __bfloat162float(h1));
-                ph[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                plw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                const float s0 = fminf(fmaxf(a[2 * e] * scale, -65504.f), 65504.f);
+                const float s1 = fminf(fmaxf(a[2 * e + 1] * scale, -65504.f), 65504.f);
+                const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
+                const __half l0 = __float2half_rn(s0 - __half2float(h0));
+                const __half l1 = __float2half_rn(s1 - __half2float(h1));
+                ph[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                plw[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
             }
             *reinterpret_cast<uint2*>(hi + (size_t)pix * C + g * 4) = make_uint2(ph[0], ph[1]);
             if (lo) *reinterpret_cast<uint2*>(lo + (size_t)pix * C + g * 4) = make_uint2(plw[0], plw[1]);
@@ -340,9 +357,10 @@ using namespace dsee;
 
 extern "C" int dsee_grad_prep_blocks(int64_t npix) { return cdivb(npix, GP_PIX); }
 
-extern "C" int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, const float* noise0,
-                              const float* noise1, int64_t npix, int C, float* partial, void* stream) {
-    DSEE_CHECK_ARG(dy && out_hi && partial && npix > 0, "bad argument");
+extern "C" int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, float* inv_scale,
+                              const float* noise0, const float* noise1, int64_t npix, int C,
+                              float* partial, void* stream) {
+    DSEE_CHECK_ARG(dy && out_hi && inv_scale && partial && npix > 0, "bad argument");
     DSEE_CHECK_ARG(C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "C must divide 1024 (got %d)", C);
     DSEE_CHECK_ARG(!(noise1 && !noise0), "noise1 without noise0");
     int rc = require_sm100();
@@ -350,8 +368,16 @@ extern "C" int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, const
     const int nq = 1 + (noise0 ? 1 : 0) + (noise1 ? 1 : 0);
     const int lanes = 256 / (C / 4);
     size_t sm = (size_t)lanes * C * nq * sizeof(float);
-    grad_prep_kernel<<<cdivb(npix, GP_PIX), 256, sm, (cudaStream_t)stream>>>(
-        dy, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, noise0, noise1, npix, C, partial, nq);
+    cudaStream_t st = (cudaStream_t)stream;
+    DSEE_CUDA(cudaMemsetAsync(inv_scale, 0, 2 * sizeof(float), st));
+    const int64_t n4 = npix * C / 4;
+    int ablocks = cdivb(n4, 256 * 8);
+    if (ablocks > 148 * 8) ablocks = 148 * 8;
+    grad_amax_kernel<<<ablocks, 256, 0, st>>>(dy, n4, inv_scale + 1);
+    count_launch();
+    grad_prep_kernel<<<cdivb(npix, GP_PIX), 256, sm, st>>>(dy, (__half*)out_hi, (__half*)out_lo,
+                                                           inv_scale, noise0, noise1, npix, C, partial,
+                                                           nq);
     LAUNCH_END();
 }
 

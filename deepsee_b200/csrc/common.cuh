@@ -187,6 +187,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo
     return d;
 }
 
+// 2^e with amax * 2^e in [2^(top-1), 2^top): the power-of-two operand scale that keeps the hi plane
+// of an fp16 split well inside the normal range (and the lo plane out of the subnormals).
+__device__ __forceinline__ float pow2_scale_for(float amax, int top) {
+    if (!(amax > 0.f) || isinf(amax)) return 1.f;
+    int ex;
+    frexpf(amax, &ex);  // amax = f * 2^ex, f in [0.5, 1)
+    return ldexpf(1.f, top - ex);
+}
+// max over non-negative floats through their (order-preserving) bit patterns
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+    atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -54,6 +54,7 @@ struct alignas(64) ConvParams {
     uint32_t idesc;
     int n_total;
     const float* w_inv_scale;
+    const float* a_inv_scale;  // NULL, or the 2^-e of pre-scaled A planes (gradient operands)
     // EPI_CONV
     const float* bias;
     const float* residual;
@@ -63,6 +64,7 @@ struct alignas(64) ConvParams {
     float* out;
     float* stats_partial;
     const __half* act_mask;  // dgrad: multiply by LeakyReLU'(t) read off the saved activation's sign
+    float* amax_out;         // optional: max |out| (atomic, non-negative float bits)
     // EPI_MODULATE
     const float* x;
     int x_ups;
@@ -78,8 +80,10 @@ struct alignas(64) ConvParams {
     // EPI_MODULATE_BWD
     const float* dt;         // fp32 NHWC [B,H,W,C]: gradient wrt the pre-activation t
     float* dxhat;            // fp32 NHWC [B,H,W,C]
-    __nv_bfloat16* dgb_hi;   // bf16 NHWC [B,H,W,2C], channels interleaved [dG(128)|dB(128)] per 128
-    __nv_bfloat16* dgb_lo;
+    __half* dgb_hi;          // fp16 NHWC [B,H,W,2C] * dgb scale, channels interleaved [dG(128)|dB(128)]
+    __half* dgb_lo;
+    const float* dt_amax;    // device scalar: max |dt| (sets the dgb plane scale)
+    float* dgb_inv_scale;    // out: 2^-e of the dgb planes
     float* bwd_partial;      // [m_tiles*4][C][4] = sum dxhat, sum dxhat*xhat, sum dG, sum dB
 };
 
@@ -239,7 +243,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
         const int q = warp & 3;  // TMEM lane quarter this warp may touch
         const int m = q * 32 + lane;
         const int ly = m / TILE_W, lx = m % TILE_W;
-        const float inv_scale = __ldg(p.w_inv_scale);
+        const float inv_scale = __ldg(p.w_inv_scale) * (p.a_inv_scale ? __ldg(p.a_inv_scale) : 1.f);
         int lt = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
             const int as = lt & 1;
@@ -320,6 +324,17 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                             reinterpret_cast<float4*>(orow + n)[j] =
                                 make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                     }
+                    if (p.amax_out) {
+                        float m = 0.f;
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) m = fmaxf(m, fabsf(o[j]));
+                        }
+#pragma unroll
+                        for (int sft = 16; sft >= 1; sft >>= 1)
+                            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sft));
+                        if (lane == 0 && m > 0.f && !isinf(m) && !isnan(m)) atomic_max_nonneg(p.amax_out, m);
+                    }
                     if (p.stats_partial) {
                         // tile partial of sum / sum^2 per channel, one slot per (m-tile, quarter)
                         float s1[32], s2[32];
@@ -349,8 +364,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                 const float* nrow = p.noise ? p.noise + pix * p.C : nullptr;
                 const float* dtrow = p.dt + pix * p.C;
                 float* dxrow = p.dxhat + pix * p.C;
-                __nv_bfloat16* ghrow = p.dgb_hi + pix * (size_t)(2 * p.C);
-                __nv_bfloat16* glrow = p.dgb_lo ? p.dgb_lo + pix * (size_t)(2 * p.C) : nullptr;
+                __half* ghrow = p.dgb_hi + pix * (size_t)(2 * p.C);
+                __half* glrow = p.dgb_lo ? p.dgb_lo + pix * (size_t)(2 * p.C) : nullptr;
+                // |dG| = |dt * xhat| <= amax(dt) * |xhat|: leave 2^6 of headroom for |xhat|
+                // (store_split8 clamps beyond it)
+                const float gscale = pow2_scale_for(__ldg(p.dt_amax), 10);
+                if (tile == 0 && threadIdx.x == 64) *p.dgb_inv_scale = 1.f / gscale;
 #pragma unroll 1
                 for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
                     const int c = c0 + ch * 32;
@@ -396,25 +415,14 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
                             const float* src = half ? s_db : s_dg;
-                            __nv_bfloat16* dh = ghrow + ng + half * 128;
-                            __nv_bfloat16* dl = glrow ? glrow + ng + half * 128 : nullptr;
+                            __half* dh = ghrow + ng + half * 128;
+                            __half* dl = glrow ? glrow + ng + half * 128 : nullptr;
 #pragma unroll
                             for (int j8 = 0; j8 < 4; ++j8) {
-                                uint32_t ph[4], pl[4];
+                                float a8[8];
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float a0 = src[j8 * 8 + 2 * e], a1 = src[j8 * 8 + 2 * e + 1];
-                                    const __nv_bfloat16 h0 = __float2bfloat16_rn(a0);
-                                    const __nv_bfloat16 h1 = __float2bfloat16_rn(a1);
-                                    const __nv_bfloat16 l0 = __float2bfloat16_rn(a0 - __bfloat162float(h0));
-                                    const __nv_bfloat16 l1 = __float2bfloat16_rn(a1 - __bfloat162float(h1));
-                                    ph[e] = (uint32_t)__bfloat16_as_ushort(h0) |
-                                            ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                                    pl[e] = (uint32_t)__bfloat16_as_ushort(l0) |
-                                            ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                                }
-                                reinterpret_cast<uint4*>(dh)[j8] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                                if (dl) reinterpret_cast<uint4*>(dl)[j8] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                                for (int e = 0; e < 8; ++e) a8[e] = src[j8 * 8 + e] * gscale;
+                                store_split8(dh + j8 * 8, dl ? dl + j8 * 8 : nullptr, a8);
                             }
                         }
                     }
@@ -524,9 +532,11 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops) {
     p.passes = ops->passes;
     p.n_total = ops->n_total;
     p.w_inv_scale = ops->w_inv_scale;
+    p.a_inv_scale = ops->a_inv_scale;
     // kind::f16 instruction descriptor: fp32 accumulate, fp16 A/B, K-major both, N=256, M=128
-    DSEE_CHECK_ARG((ops->a_dtype == 0 || ops->a_dtype == 1) && (ops->w_dtype == 0 || ops->w_dtype == 1),
-                   "operand dtype must be 0 (fp16) or 1 (bf16)");
+    DSEE_CHECK_ARG((ops->a_dtype == 0 || ops->a_dtype == 1) && ops->w_dtype == ops->a_dtype,
+                   "operand dtypes must both be 0 (fp16) or both 1 (bf16): tcgen05 kind::f16 rejects "
+                   "mixed A/B formats");
     p.idesc = (1u << 4) | ((uint32_t)ops->a_dtype << 7) | ((uint32_t)ops->w_dtype << 10) |
               ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 
@@ -614,6 +624,8 @@ extern "C" int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_e
     p.out = epi->out;
     p.stats_partial = epi->stats_partial;
     p.act_mask = (const __half*)epi->act_mask;
+    p.amax_out = epi->amax_out;
+    if (p.amax_out) DSEE_CUDA(cudaMemsetAsync(p.amax_out, 0, sizeof(float), (cudaStream_t)stream));
     return launch<EPI_CONV>(p, (cudaStream_t)stream);
 }
 
@@ -659,7 +671,7 @@ extern "C" int dsee_spade_modulate_bwd(const dsee_conv_operands* ops, const dsee
     DSEE_CHECK_ARG(a->C > 0 && a->C % 128 == 0 && ops->n_total == a->C,
                    "gamma-only weights expected: n_total (%d) must equal C (%d)", ops->n_total, a->C);
     DSEE_CHECK_ARG(a->x && a->dt && a->bn_scale && a->bn_shift && a->gamma_bias && a->dxhat &&
-                       a->dgb_hi && a->partial,
+                       a->dgb_hi && a->partial && a->dt_amax && a->dgb_inv_scale,
                    "NULL modulate bwd pointer");
     DSEE_CHECK_ARG(a->x_ups == 0 || a->x_ups == 1, "x_ups must be 0 or 1");
     DSEE_CHECK_ARG((a->noise == nullptr) == (a->noise_w == nullptr), "noise/noise_w mismatch");
@@ -673,8 +685,10 @@ extern "C" int dsee_spade_modulate_bwd(const dsee_conv_operands* ops, const dsee
     p.C = a->C;
     p.dt = a->dt;
     p.dxhat = a->dxhat;
-    p.dgb_hi = (__nv_bfloat16*)a->dgb_hi;
-    p.dgb_lo = (__nv_bfloat16*)a->dgb_lo;
+    p.dgb_hi = (__half*)a->dgb_hi;
+    p.dgb_lo = (__half*)a->dgb_lo;
+    p.dt_amax = a->dt_amax;
+    p.dgb_inv_scale = a->dgb_inv_scale;
     p.bwd_partial = a->partial;
     return launch<EPI_MODULATE_BWD>(p, (cudaStream_t)stream);
 }

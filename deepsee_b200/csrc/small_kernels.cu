@@ -153,19 +153,11 @@ __global__ void amax_kernel(const float* __restrict__ w, int64_t n, float* scrat
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(scratch), __float_as_uint(m));
 }
 
-__device__ __forceinline__ float pow2_scale_for(float amax) {
-    // 2^e with amax * 2^e in [2^13, 2^14)
-    if (!(amax > 0.f) || isinf(amax)) return 1.f;
-    int ex;
-    frexpf(amax, &ex);  // amax = f * 2^ex, f in [0.5, 1)
-    return ldexpf(1.f, 14 - ex);
-}
-
 __global__ void prep_weight_kernel(const float* __restrict__ w, __half* __restrict__ out_hi,
                                    __half* __restrict__ out_lo, float* inv_scale, int N, int C,
                                    int transpose) {
     // out[n][tap][c] = w[n][c][tap] * scale      (transpose: out[c][8-tap][n])
-    const float scale = pow2_scale_for(inv_scale[1]);
+    const float scale = pow2_scale_for(inv_scale[1], 14);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) inv_scale[0] = 1.f / scale;
     if (i >= (int64_t)N * 9 * C) return;

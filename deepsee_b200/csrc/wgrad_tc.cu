@@ -45,7 +45,7 @@ struct alignas(64) WgradParams {
     int passes;
     uint32_t idesc;
     float* partial;  // [splits][n_total][9][c_total]
-    float scale;     // applied to the accumulator (undoes operand pre-scaling)
+    const float* inv_scale[2];  // device scalars undoing the operand pre-scaling (NULL = 1)
 };
 
 // MN-major, 128B-swizzled operand descriptor (see header comment).
@@ -180,6 +180,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     } else {
         const int q = warp & 3;
         const int m = q * 32 + lane;
+        const float scale = (p.inv_scale[0] ? __ldg(p.inv_scale[0]) : 1.f) *
+                            (p.inv_scale[1] ? __ldg(p.inv_scale[1]) : 1.f);
         int lu = 0;
         for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++lu) {
             int nt, tap, ct, split;
@@ -203,10 +205,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                 if (n < p.n_total) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        float4 o = make_float4(__uint_as_float(v[4 * j]) * p.scale,
-                                               __uint_as_float(v[4 * j + 1]) * p.scale,
-                                               __uint_as_float(v[4 * j + 2]) * p.scale,
-                                               __uint_as_float(v[4 * j + 3]) * p.scale);
+                        float4 o = make_float4(__uint_as_float(v[4 * j]) * scale,
+                                               __uint_as_float(v[4 * j + 1]) * scale,
+                                               __uint_as_float(v[4 * j + 2]) * scale,
+                                               __uint_as_float(v[4 * j + 3]) * scale);
                         if (empty) o = make_float4(0.f, 0.f, 0.f, 0.f);
                         reinterpret_cast<float4*>(orow + ch * 32)[j] = o;
                     }
@@ -263,17 +265,18 @@ extern "C" int64_t dsee_conv3x3_wgrad_workspace_floats(int B, int H, int W, int 
     return (int64_t)splits * n_total * 9 * c_total;
 }
 
-extern "C" int dsee_conv3x3_wgrad(const void* dy_hi, const void* dy_lo, int dy_dtype,
-                                  const void* a_hi, const void* a_lo, int a_dtype, int B, int H,
-                                  int W, int n_total, int c_total, int passes, float scale,
+extern "C" int dsee_conv3x3_wgrad(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale,
+                                  const void* a_hi, const void* a_lo, const float* a_inv_scale,
+                                  int dtype, int B, int H, int W, int n_total, int c_total, int passes,
                                   float* workspace, float* dw, int layout_nc9, void* stream) {
+    const int dy_dtype = dtype, a_dtype = dtype;
     DSEE_CHECK_ARG(dy_hi && a_hi && workspace && dw, "NULL pointer");
     DSEE_CHECK_ARG(B > 0 && H > 0 && W > 0, "bad geometry");
     DSEE_CHECK_ARG(n_total % 128 == 0, "n_total must be a multiple of 128 (got %d)", n_total);
     DSEE_CHECK_ARG(c_total == 64 || c_total == 128 || c_total % 256 == 0,
                    "c_total must be 64, 128 or a multiple of 256 (got %d)", c_total);
     DSEE_CHECK_ARG(passes == 1 || (passes == 3 && dy_lo && a_lo), "passes must be 1, or 3 with lo planes");
-    DSEE_CHECK_ARG((dy_dtype | 1) == 1 && (a_dtype | 1) == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+    DSEE_CHECK_ARG(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
     int rc = require_sm100();
     if (rc) return rc;
     WgradParams p;
@@ -292,7 +295,8 @@ extern "C" int dsee_conv3x3_wgrad(const void* dy_hi, const void* dy_lo, int dy_d
     p.num_units = p.n_tiles * 9 * p.c_tiles * p.splits;
     p.passes = passes;
     p.partial = workspace;
-    p.scale = scale;
+    p.inv_scale[0] = dy_inv_scale;
+    p.inv_scale[1] = a_inv_scale;
     // kind::f16, fp32 accumulate, both operands MN-major, M = 128, N = n_cols
     p.idesc = (1u << 4) | ((uint32_t)dy_dtype << 7) | ((uint32_t)a_dtype << 10) | (1u << 15) |
               (1u << 16) | ((uint32_t)(p.n_cols >> 3) << 17) | ((uint32_t)(WG_M >> 4) << 24);

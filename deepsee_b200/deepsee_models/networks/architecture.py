@@ -58,14 +58,14 @@ def _norm_forward(blk, norm, pre, Wm, gb, bb, tab, tb, gctx, style, x, x_ups, H,
     return a, st
 
 
-def _norm_backward(norm, st, dt, x, x_ups, noise, noise_w, L, passes, want_lo):
+def _norm_backward(norm, st, dt, dt_amax, x, x_ups, noise, noise_w, L, passes, want_lo):
     """K1 backward for one layer -> (dxhat, sums[4,C], dWm, dtab, dtb, dstyle)."""
     C = x.shape[3]
     Wm = st.Wm
     cin = Wm.shape[1]
     w_gamma = Wm.view(C // 128, 2, 128, cin, 3, 3)[:, 0].reshape(C, cin, 3, 3).contiguous()
     pwg = ops.prep_conv_weight(w_gamma, want_lo=want_lo)
-    dxhat, dgb, sums = ops.spade_modulate_bwd(st.srcs, pwg, x, x_ups, st.sc, st.sh, st.gb, dt,
+    dxhat, dgb, sums = ops.spade_modulate_bwd(st.srcs, pwg, x, x_ups, st.sc, st.sh, st.gb, dt, dt_amax,
                                               noise=noise, noise_w=noise_w, passes=passes,
                                               want_lo=want_lo)
     dWm = [ops.conv3x3_wgrad(dgb, src, passes=passes) for src in st.srcs]
@@ -158,11 +158,12 @@ class _ResBlockFn(torch.autograd.Function):
         dnw_skip = sums[2] if noisy else None
         dW1 = ops.conv3x3_wgrad(g1, a1, passes=passes)
         pwT = ops.prep_conv_weight(s['W1'].contiguous(), want_lo=want_lo, transpose=True)
-        dt1 = ops.conv3x3([g1], pwT, None, passes=passes, act_mask=a1.hi, tag="dgrad")
+        dt1, amax1 = ops.conv3x3([g1], pwT, None, passes=passes, act_mask=a1.hi, want_amax=True,
+                                 tag="dgrad")
         del g1
         # ---- norm_1 ----------------------------------------------------------------------------
         dxhat, nsums, dWm1, dtab1, dtb1, dstyle1 = _norm_backward(
-            blk.norm_1, st1, dt1, dx1, 0, None, None, L, passes, want_lo)
+            blk.norm_1, st1, dt1, amax1, dx1, 0, None, None, L, passes, want_lo)
         del dt1
         dgb1, dbb1 = nsums[2], nsums[3]
         ddx1, _ = ops.bn_bwd(dxhat, dx1, 0, st1.sc, st1.sh, nsums, st1.inv_count)
@@ -174,12 +175,13 @@ class _ResBlockFn(torch.autograd.Function):
         dnw_mid = sums[1] if noisy else None
         dW0 = ops.conv3x3_wgrad(g0, a0, passes=passes)
         pwT = ops.prep_conv_weight(s['W0'].contiguous(), want_lo=want_lo, transpose=True)
-        dt0 = ops.conv3x3([g0], pwT, None, passes=passes, act_mask=a0.hi, tag="dgrad")
+        dt0, amax0 = ops.conv3x3([g0], pwT, None, passes=passes, act_mask=a0.hi, want_amax=True,
+                                 tag="dgrad")
         del g0
         # ---- norm_0 (reads x through the folded upsample, + noise_in) ---------------------------
         nw_in = s['nw_in'] if noisy else None
         dxhat, nsums, dWm0, dtab0, dtb0, dstyle0 = _norm_backward(
-            blk.norm_0, st0, dt0, x, ups, n_in, nw_in, L, passes, want_lo)
+            blk.norm_0, st0, dt0, amax0, x, ups, n_in, nw_in, L, passes, want_lo)
         del dt0
         dgb0, dbb0 = nsums[2], nsums[3]
         dx, dnw_in_bn = ops.bn_bwd(dxhat, x, ups, st0.sc, st0.sh, nsums, st0.inv_count, noise=n_in,

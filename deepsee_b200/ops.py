@@ -12,6 +12,8 @@ import torch
 from . import _lib
 
 SplitPlanes = namedtuple("SplitPlanes", ["hi", "lo"])  # fp16 NHWC [B,H,W,C]; value = hi + lo
+# gradient operand: fp16 NHWC planes of g * 2^e plus the device scalar 2^-e
+GradPlanes = namedtuple("GradPlanes", ["hi", "lo", "inv_scale"])
 PreparedWeight = namedtuple("PreparedWeight", ["hi", "lo", "inv_scale", "n_total", "cin"])
 
 
@@ -195,17 +197,20 @@ def _operands(sources, pw, passes):
     ops.passes = passes
     ops.a_dtype = _DTYPE_CODE[a0.hi.dtype]
     ops.w_dtype = _DTYPE_CODE[pw.hi.dtype]
+    inv = getattr(a0, "inv_scale", None)
+    ops.a_inv_scale = inv.data_ptr() if inv is not None else 0
     return ops, (B, H, W)
 
 
 def conv3x3(sources, pw, bias, residual=None, res_ups=0, noises=(), passes=3, want_stats=False,
-            act_mask=None, tag="conv3x3"):
+            act_mask=None, want_amax=False, tag="conv3x3"):
     """K2: 3x3 conv + bias (+ residual through an optional folded 2x upsample, + up to two
     NoiseInjection terms ``(noise NHWC, weight[C])``) -> fp32 NHWC.
     Backward-data use: ``sources`` = gradient planes (bf16), ``pw`` prepared with transpose=True,
     bias None, ``act_mask`` = fp16 hi plane of the forward activation (LeakyReLU' folded in).
 
-    Returns out, or (out, stats_partial) when want_stats (partials for bn_finalize)."""
+    Returns out, or (out, stats_partial) when want_stats (partials for bn_finalize), or
+    (out, amax) when want_amax (device scalar max|out|)."""
     ops, (B, H, W) = _operands(sources, pw, passes)
     _chk_cuda(bias, residual)
     dev = sources[0].hi.device
@@ -231,9 +236,13 @@ def conv3x3(sources, pw, bias, residual=None, res_ups=0, noises=(), passes=3, wa
             epi.noise_w[i] = 0
     epi.out = out.data_ptr()
     epi.stats_partial = stats.data_ptr() if stats is not None else 0
+    amax = torch.empty(1, dtype=torch.float32, device=dev) if want_amax else None
+    epi.amax_out = amax.data_ptr() if amax is not None else 0
     flops = 2.0 * 9 * pw.cin * pw.n_total * B * H * W  # reference-equivalent dense conv FLOPs
     _timed("%s_%dx%d" % (tag, H, W), flops,
            lambda: _lib.check(_lib.load().dsee_conv3x3_fwd(C.byref(ops), C.byref(epi), _stream())))
+    if want_amax:
+        return out, amax
     return (out, stats) if want_stats else out
 
 
@@ -266,20 +275,21 @@ def spade_modulate(sources, pw, x, x_ups, bn_scale, bn_shift, gamma_bias, beta_b
 # generator backward
 # ---------------------------------------------------------------------------------------------
 def grad_prep(dy, noise0=None, noise1=None, want_lo=True):
-    """dY fp32 NHWC -> (bf16 SplitPlanes, sums fp32 [nq,C]): sums[0] = sum dY (bias gradient),
-    sums[1+i] = sum dY*noise_i (NoiseInjection.weight gradients)."""
+    """dY fp32 NHWC -> (scaled fp16 GradPlanes, sums fp32 [nq,C]): sums[0] = sum dY (bias
+    gradient), sums[1+i] = sum dY*noise_i (NoiseInjection.weight gradients)."""
     _chk_cuda(dy, noise0, noise1)
     Cc = dy.shape[-1]
     npix = dy.numel() // Cc
     lib = _lib.load()
-    hi = torch.empty(dy.shape, dtype=torch.bfloat16, device=dy.device)
+    hi = torch.empty(dy.shape, dtype=torch.float16, device=dy.device)
     lo = torch.empty_like(hi) if want_lo else None
+    inv = torch.empty(2, dtype=torch.float32, device=dy.device)
     nq = 1 + (noise0 is not None) + (noise1 is not None)
     nb = lib.dsee_grad_prep_blocks(npix)
     part = torch.empty((nb, Cc, nq), dtype=torch.float32, device=dy.device)
-    _lib.check(lib.dsee_grad_prep(_p(dy), _p(hi), _p(lo), _p(noise0), _p(noise1), npix, Cc, _p(part),
-                                  _stream()))
-    return SplitPlanes(hi, lo), reduce_partials(part)
+    _lib.check(lib.dsee_grad_prep(_p(dy), _p(hi), _p(lo), _p(inv), _p(noise0), _p(noise1), npix, Cc,
+                                  _p(part), _stream()))
+    return GradPlanes(hi, lo, inv), reduce_partials(part)
 
 
 def reduce_partials(part, scale=1.0):
@@ -291,8 +301,8 @@ def reduce_partials(part, scale=1.0):
     return out
 
 
-def conv3x3_wgrad(dy, a, passes=3, scale=1.0):
-    """dW[n][c][3][3] = sum_pixels dY[.,n] * A[.+tap,c]; dy / a are SplitPlanes NHWC."""
+def conv3x3_wgrad(dy, a, passes=3):
+    """dW[n][c][3][3] = sum_pixels dY[.,n] * A[.+tap,c]; dy = GradPlanes, a = SplitPlanes NHWC."""
     _chk_cuda(dy.hi, dy.lo, a.hi, a.lo)
     B, H, W, N = dy.hi.shape
     Cc = a.hi.shape[3]
@@ -302,16 +312,18 @@ def conv3x3_wgrad(dy, a, passes=3, scale=1.0):
                      device=dy.hi.device)
     dw = torch.empty((N, Cc, 3, 3), dtype=torch.float32, device=dy.hi.device)
     flops = 2.0 * 9 * Cc * N * B * H * W
+    assert dy.hi.dtype == a.hi.dtype
     _timed("wgrad_%dx%d" % (H, W), flops, lambda: _lib.check(lib.dsee_conv3x3_wgrad(
-        _p(dy.hi), _p(dy.lo), _DTYPE_CODE[dy.hi.dtype], _p(a.hi), _p(a.lo), _DTYPE_CODE[a.hi.dtype],
-        B, H, W, N, Cc, passes, float(scale), _p(ws), _p(dw), 1, _stream())))
+        _p(dy.hi), _p(dy.lo), _p(getattr(dy, "inv_scale", None)), _p(a.hi), _p(a.lo),
+        _p(getattr(a, "inv_scale", None)), _DTYPE_CODE[dy.hi.dtype], B, H, W, N, Cc, passes, _p(ws),
+        _p(dw), 1, _stream())))
     return dw
 
 
-def spade_modulate_bwd(sources, pw_gamma, x, x_ups, bn_scale, bn_shift, gamma_bias, dt, noise=None,
-                       noise_w=None, passes=3, want_lo=True):
-    """K1 backward -> (dxhat fp32 NHWC, dgb bf16 SplitPlanes [B,H,W,2C] interleaved,
-    sums fp32 [4,C] = sum dxhat, sum dxhat*xhat, sum dG, sum dB)."""
+def spade_modulate_bwd(sources, pw_gamma, x, x_ups, bn_scale, bn_shift, gamma_bias, dt, dt_amax,
+                       noise=None, noise_w=None, passes=3, want_lo=True):
+    """K1 backward -> (dxhat fp32 NHWC, dgb GradPlanes [B,H,W,2C] interleaved,
+    sums fp32 [4,C] = sum dxhat, sum dxhat*xhat, sum dG, sum dB). dt_amax: device max|dt|."""
     ops, (B, H, W) = _operands(sources, pw_gamma, passes)
     _chk_cuda(x, bn_scale, bn_shift, gamma_bias, dt, noise, noise_w)
     Cc = x.shape[3]
@@ -319,8 +331,9 @@ def spade_modulate_bwd(sources, pw_gamma, x, x_ups, bn_scale, bn_shift, gamma_bi
     dev = x.device
     lib = _lib.load()
     dxhat = torch.empty((B, H, W, Cc), dtype=torch.float32, device=dev)
-    ghi = torch.empty((B, H, W, 2 * Cc), dtype=torch.bfloat16, device=dev)
+    ghi = torch.empty((B, H, W, 2 * Cc), dtype=torch.float16, device=dev)
     glo = torch.empty_like(ghi) if want_lo else None
+    ginv = torch.empty(1, dtype=torch.float32, device=dev)
     part = torch.empty((lib.dsee_conv3x3_stats_tiles(B, H, W), Cc, 4), dtype=torch.float32, device=dev)
     m = _lib.ModulateBwdArgs()
     m.x, m.x_ups = x.data_ptr(), x_ups
@@ -332,10 +345,11 @@ def spade_modulate_bwd(sources, pw_gamma, x, x_ups, bn_scale, bn_shift, gamma_bi
     m.dgb_lo = glo.data_ptr() if glo is not None else 0
     m.partial = part.data_ptr()
     m.C = Cc
+    m.dt_amax, m.dgb_inv_scale = dt_amax.data_ptr(), ginv.data_ptr()
     flops = 2.0 * 9 * pw_gamma.cin * pw_gamma.n_total * B * H * W
     _timed("modulate_bwd_%dx%d" % (H, W), flops,
            lambda: _lib.check(lib.dsee_spade_modulate_bwd(C.byref(ops), C.byref(m), _stream())))
-    return dxhat, SplitPlanes(ghi, glo), reduce_partials(part)
+    return dxhat, GradPlanes(ghi, glo, ginv), reduce_partials(part)
 
 
 def bn_bwd(dxhat, x, x_ups, bn_scale, bn_shift, sums, inv_count, noise=None, noise_w=None, dskip=None):

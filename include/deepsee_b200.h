@@ -100,8 +100,11 @@ typedef struct {
     const float* w_inv_scale; /* device scalar */
     int n_total;
     int passes; /* 1: hi*hi (TF32-class accuracy)   3: hi*hi + lo*hi + hi*lo (fp32-class) */
-    int a_dtype; /* element type of the A planes: 0 fp16 (activations), 1 bf16 (gradients) */
-    int w_dtype; /* element type of the weight planes: 0 fp16, 1 bf16 */
+    int a_dtype; /* element type of the A planes: 0 fp16, 1 bf16 */
+    int w_dtype; /* element type of the weight planes; must equal a_dtype (tcgen05 kind::f16
+                    rejects mixed A/B formats) */
+    const float* a_inv_scale; /* NULL, or device scalar 2^-e of pre-scaled A planes (gradient
+                                 operands from dsee_grad_prep / dsee_spade_modulate_bwd) */
 } dsee_conv_operands;
 
 /* K2.  Replaces conv_0 / conv_1 of SPADEResnetBlock (architecture.py:34-35,98,122) plus what the
@@ -130,6 +133,9 @@ typedef struct {
      * (architecture.py:147 backward). act_mask = the hi plane K1 wrote in the forward pass,
      * fp16 NHWC [B,H,W,n_total], or NULL. bias may be NULL (= 0). */
     const void* act_mask;
+    /* optional device float: receives max |out| (what the next gradient-plane scale is chosen
+     * from); zeroed by the call. */
+    float* amax_out;
 } dsee_conv_epilogue;
 int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_epilogue* epi, void* stream);
 int dsee_conv3x3_stats_tiles(int B, int H, int W);
@@ -165,9 +171,12 @@ int dsee_spade_modulate_fwd(const dsee_conv_operands* ops, const dsee_modulate_a
  * n_total == C, prepared with dsee_prep_conv_weight) and, with G = gamma + gamma_bias,
  * xhat = xin*bn_scale + bn_shift, dt = dL/dt:
  *   dxhat = dt * G                                 -> fp32 NHWC [B,H,W,C]
- *   [dG | dB] = [dt * xhat | dt]                   -> bf16 split planes NHWC [B,H,W,2C], channels
+ *   [dG | dB] = [dt * xhat | dt] * 2^e             -> fp16 split planes NHWC [B,H,W,2C], channels
  *                                                     interleaved per 128 like the forward weights
- *                                                     (A operand of the two following GEMMs)
+ *                                                     (A operand of the two following GEMMs);
+ *                                                     2^e is chosen from *dt_amax (max |dt|, e.g.
+ *                                                     dsee_conv_epilogue.amax_out of the kernel that
+ *                                                     produced dt), 2^-e is written to *dgb_inv_scale
  *   partial[tile][c] = (sum dxhat, sum dxhat*xhat, sum dG, sum dB) over the tile's pixels
  *     (first two: batch-norm backward, batchnorm.py:78-93 differentiated; last two: gradients of
  *      gamma_bias / beta_bias). partial: fp32 [dsee_conv3x3_stats_tiles()][C][4]. */
@@ -185,39 +194,45 @@ typedef struct {
     void* dgb_lo; /* may be NULL */
     float* partial;
     int C;
+    const float* dt_amax;
+    float* dgb_inv_scale;
 } dsee_modulate_bwd_args;
 int dsee_spade_modulate_bwd(const dsee_conv_operands* ops, const dsee_modulate_bwd_args* args,
                             void* stream);
 
 /* ---- generator backward (autograd of the fused kernels above) -------------------------------- */
-/* Gradient tensors are fp32 NHWC in HBM; as tensor-core operands they are bf16 split planes
- * (value = hi + lo; bf16 keeps fp32's exponent range, so no loss scaling is needed).
+/* Gradient tensors are fp32 NHWC in HBM; as tensor-core operands they are fp16 split planes like
+ * the activations (tcgen05 kind::f16 needs A and B in the same format), multiplied by a per-tensor
+ * power of two 2^e that places max|g| in [2^13, 2^14); the 2^-e travels with the planes as a device
+ * scalar (dsee_conv_operands.a_inv_scale / dsee_conv3x3_wgrad's dy_inv_scale).
  *
- * Backward-data of K2 / K1's GEMM is dsee_conv3x3_fwd itself, run on the gradient planes
- * (a_dtype = 1) with a weight from dsee_prep_conv_weight(transpose=1); dsee_conv_epilogue.act_mask
- * folds in LeakyReLU'. */
+ * Backward-data of K2 / K1's GEMM is dsee_conv3x3_fwd itself, run on the gradient planes with a
+ * weight from dsee_prep_conv_weight(transpose=1); dsee_conv_epilogue.act_mask folds in LeakyReLU'. */
 
-/* dY fp32 NHWC [npix][C] -> bf16 split planes, plus per-channel block partials of
+/* dY fp32 NHWC [npix][C] -> scaled fp16 split planes (inv_scale: device float[2], [0] receives
+ * 2^-e, [1] is scratch), plus per-channel block partials of
  * (sum dY, sum dY*noise0, sum dY*noise1) = gradients of a conv bias (architecture.py:98,122) and of
  * NoiseInjection.weight (normalization.py:299-304).  partial fp32 [dsee_grad_prep_blocks()][C][nq],
  * nq = 1 + (noise0 != NULL) + (noise1 != NULL); reduce with dsee_reduce_partials. */
 int dsee_grad_prep_blocks(int64_t npix);
-int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, const float* noise0,
-                   const float* noise1, int64_t npix, int C, float* partial, void* stream);
+int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, float* inv_scale,
+                   const float* noise0, const float* noise1, int64_t npix, int C, float* partial,
+                   void* stream);
 /* out[k][c] = scale * sum_s partial[s][c][k]  (double accumulation, fixed order). */
 int dsee_reduce_partials(const float* partial, int n, int C, int nq, float scale, float* out,
                          void* stream);
 /* Weight gradient of a 3x3 conv (autograd of architecture.py:98,122 and normalization.py:116-117,
- * 198-201,283-284): dW[n][c][tap] = scale * sum_{b,y,x} dY[b,y,x,n] * A[b,y+dy,x+dx,c].
+ * 198-201,283-284): dW[n][c][tap] = s * sum_{b,y,x} dY[b,y,x,n] * A[b,y+dy,x+dx,c], s = the product
+ * of *dy_inv_scale and *a_inv_scale (device scalars, NULL = 1).
  * dY planes [B,H,W,n_total] (n_total % 128 == 0), A planes [B,H,W,c_total] (c_total = 64, 128 or a
- * multiple of 256); dtype 0 fp16 / 1 bf16 per operand.  workspace fp32
+ * multiple of 256); dtype 0 fp16 / 1 bf16, the same for both operands.  workspace fp32
  * [dsee_conv3x3_wgrad_workspace_floats()]; dw fp32 [n_total][c_total][3][3] (layout_nc9 = 1, the
  * PyTorch layout) or [n_total][9][c_total] (layout_nc9 = 0).  Deterministic split-K. */
 int64_t dsee_conv3x3_wgrad_workspace_floats(int B, int H, int W, int n_total, int c_total);
-int dsee_conv3x3_wgrad(const void* dy_hi, const void* dy_lo, int dy_dtype, const void* a_hi,
-                       const void* a_lo, int a_dtype, int B, int H, int W, int n_total, int c_total,
-                       int passes, float scale, float* workspace, float* dw, int layout_nc9,
-                       void* stream);
+int dsee_conv3x3_wgrad(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale,
+                       const void* a_hi, const void* a_lo, const float* a_inv_scale, int dtype, int B,
+                       int H, int W, int n_total, int c_total, int passes, float* workspace, float* dw,
+                       int layout_nc9, void* stream);
 /* Batch-norm backward (differentiates batchnorm.py:78-93 / F.batch_norm in training mode) with the
  * folded 2x upsample transposed into a 2x2 sum and the identity shortcut's gradient added:
  *   xhat = (x[up] + noise_w*noise) * bn_scale + bn_shift

@@ -229,7 +229,14 @@ def _norm(kind, x, seg, style, sd, pfx, training, opt):
     return puresean_block(x, seg, style, sd, pfx, training, opt.max_fm_size)
 
 
-def resnet_block(x, seg, style, sd, pfx, kind, opt, training, noise_fn=None, taps=None):
+def _actvn(t, key, act_fn):
+    """architecture.py:146-147 (LeakyReLU 0.2).  ``act_fn(key, t)`` lets a test pin the activation
+    pattern (which side of the kink each element is on) to the one the implementation under test
+    took, so gradients can be compared without measure-zero sign flips dominating the error."""
+    return F.leaky_relu(t, LRELU) if act_fn is None else act_fn(key, t)
+
+
+def resnet_block(x, seg, style, sd, pfx, kind, opt, training, noise_fn=None, taps=None, act_fn=None):
     """SPADEResnetBlock.forward / shortcut / actvn, architecture.py:75-147 (fin == fout: identity
     shortcut; learned shortcut never built by DeepSEESR)."""
     add_noise = opt.add_noise and training
@@ -238,14 +245,14 @@ def resnet_block(x, seg, style, sd, pfx, kind, opt, training, noise_fn=None, tap
         x_s = noise_injection(x, sd[pfx + "noise_skip.weight"], noise_fn(pfx + "noise_skip", x.shape))
     else:
         x_s = x
-    h = F.leaky_relu(_norm(kind, x, seg, style, sd, pfx + "norm_0.", training, opt), LRELU)
+    h = _actvn(_norm(kind, x, seg, style, sd, pfx + "norm_0.", training, opt), pfx + "act_0", act_fn)
     if taps is not None:
         taps[pfx + "act_0"] = h
     dx = F.conv2d(h, conv_weight(sd, pfx + "conv_0.", training), sd[pfx + "conv_0.bias"], padding=1)
     if add_noise:
         dx = noise_injection(dx, sd[pfx + "noise_middle.weight"],
                              noise_fn(pfx + "noise_middle", dx.shape))
-    h = F.leaky_relu(_norm(kind, dx, seg, style, sd, pfx + "norm_1.", training, opt), LRELU)
+    h = _actvn(_norm(kind, dx, seg, style, sd, pfx + "norm_1.", training, opt), pfx + "act_1", act_fn)
     if taps is not None:
         taps[pfx + "act_1"] = h
     dx = F.conv2d(h, conv_weight(sd, pfx + "conv_1.", training), sd[pfx + "conv_1.bias"], padding=1)
@@ -275,16 +282,16 @@ def generator_layout(opt):
     return blocks[:used] if len(blocks) >= used else blocks
 
 
-def generator_forward(sd, opt, x_lr, seg, z, training=False, noise_fn=None, taps=None):
+def generator_forward(sd, opt, x_lr, seg, z, training=False, noise_fn=None, taps=None, act_fn=None):
     """DeepSEESR.forward, sr.py:62-98."""
     x = F.conv2d(x_lr, sd["initial.weight"], sd["initial.bias"], padding=1)
     for pfx, kind, up in generator_layout(opt):
         if up:
             x = F.interpolate(x, scale_factor=2, mode="nearest")
-        x = resnet_block(x, seg, z, sd, pfx, kind, opt, training, noise_fn, taps)
+        x = resnet_block(x, seg, z, sd, pfx, kind, opt, training, noise_fn, taps, act_fn)
         if taps is not None:
             taps[pfx + "out"] = x
-    x = F.conv2d(F.leaky_relu(x, LRELU), sd["conv_img.weight"], sd["conv_img.bias"], padding=1)
+    x = F.conv2d(_actvn(x, "head", act_fn), sd["conv_img.weight"], sd["conv_img.bias"], padding=1)
     return torch.tanh(x)
 
 

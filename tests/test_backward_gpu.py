@@ -1,9 +1,13 @@
 """GPU parity of the generator's backward pass (C-ABI backward kernels driven by the block-level
 autograd node) against CPU autograd through the oracle on the same seeded inputs.
 
-Tolerance: gradients are compared per tensor as max-abs error / max-abs of the reference gradient;
-3-pass operands (fp16/bf16 hi+lo planes, fp32 accumulate) are asserted at 2e-3, the 1-pass
-(TF32-class / bf16-gradient) mode at 5e-2 with the measured figure printed."""
+LeakyReLU's kink makes a raw comparison meaningless at tight tolerances: a forward difference of
+1e-5 flips the side of ~1e-5 of all pre-activations, and each flip changes that element's gradient
+by a factor of 5.  The oracle therefore evaluates its LeakyReLUs with the activation pattern the
+CUDA forward took (``act_fn`` hook of the oracle), which makes both sides differentiate the same
+piecewise-linear function.  Tolerance: per tensor, max-abs error / max(|reference gradient|,
+1e-4 * largest gradient entry of the model): 3-pass operands (fp16 hi+lo planes, fp32 accumulate)
+are asserted at 2e-3, the 1-pass (TF32-class) mode at 5e-2; measured figures are printed."""
 import pytest
 import torch
 
@@ -35,8 +39,22 @@ def _run_case(name, over, passes, batch=2, train=True, seed=31):
         noises[nm] = torch.randn(shape, generator=torch.Generator().manual_seed(len(noises)))
         return noises[nm]
 
-    ref = O.generator_forward(sd_ref, o, d["image_lr"], d["input_semantics"], z_ref, train, noise_fn)
-    (ref * proj).sum().backward()
+    if o.add_noise and train:  # draw the noise tensors (names / shapes) on a throw-away copy
+        with torch.no_grad():
+            O.generator_forward({k: v.clone() for k, v in sd.items()}, o, d["image_lr"],
+                                d["input_semantics"], z_ref, train, noise_fn)
+    from deepsee_b200 import ops
+    masks = []
+    orig_mod, orig_head = ops.spade_modulate, ops.head
+
+    def rec_mod(*a, **k):
+        r = orig_mod(*a, **k)
+        masks.append((r.hi > 0).permute(0, 3, 1, 2).cpu())
+        return r
+
+    def rec_head(x, *a, **k):
+        masks.append((x > 0).permute(0, 3, 1, 2).cpu())
+        return orig_head(x, *a, **k)
 
     old = config.passes
     config.passes = passes
@@ -50,14 +68,39 @@ def _run_case(name, over, passes, batch=2, train=True, seed=31):
                     n = noises[pfx + nm].permute(0, 2, 3, 1).contiguous().cuda()
                     getattr(blk, nm).sample = (lambda t: (lambda B, H, W: t))(n)
         z = z_ref.detach().clone().cuda().requires_grad_(True)
+        ops.spade_modulate, ops.head = rec_mod, rec_head
         out = G(d["image_lr"].cuda(), seg=d["input_semantics"].cuda(), z=z)
         (out * proj.cuda()).sum().backward()
         torch.cuda.synchronize()
     finally:
         config.passes = old
+        ops.spade_modulate, ops.head = orig_mod, orig_head
+    keys = []
+    for pfx, _, _ in O.generator_layout(o):
+        keys += [pfx + "act_0", pfx + "act_1"]
+    keys.append("head")
+    pattern = dict(zip(keys, masks))
+    assert len(masks) == len(keys)
+    flips = [0, 0]
+
+    def act_fn(key, t):
+        m = pattern[key]
+        flips[0] += int(((t > 0) != m).sum())
+        flips[1] += t.numel()
+        return torch.where(m, t, O.LRELU * t)
+
+    ref = O.generator_forward(sd_ref, o, d["image_lr"], d["input_semantics"], z_ref, train,
+                              (lambda nm, shape: noises[nm]) if noises else noise_fn, act_fn=act_fn)
+    (ref * proj).sum().backward()
+    print("   activation-pattern flips vs a free-running oracle: %d of %d" % tuple(flips))
     fwd_err = (out.detach().cpu() - ref.detach()).abs().max().item()
     worst = ("", 0.0)
     checked = 0
+    # a gradient that is mathematically zero (a conv bias in front of a training-mode batch norm) is
+    # rounding noise on both sides: errors are measured against max(|ref grad|, 1e-4 * the largest
+    # gradient entry of the whole model)
+    gmax = max(float(v.grad.abs().max()) for v in sd_ref.values() if getattr(v, "grad", None) is not None)
+    report = []
     for k, p in G.named_parameters():
         rg = sd_ref[k].grad
         if rg is None:
@@ -68,10 +111,13 @@ def _run_case(name, over, passes, batch=2, train=True, seed=31):
         assert p.grad is not None, "missing gradient for %s" % k
         scale = rg.abs().max().item()
         err = (p.grad.cpu() - rg).abs().max().item()
-        rel = err / max(scale, 1e-12)
+        rel = err / max(scale, 1e-4 * gmax)
+        report.append((rel, k, err, scale))
         checked += 1
         if rel > worst[1]:
             worst = (k, rel)
+    for rel, k, err, scale in sorted(report, reverse=True)[:8]:
+        print("   %-55s rel %.2e abs %.2e ref-scale %.2e (gmax %.2e)" % (k, rel, err, scale, gmax))
     zrel = (z.grad.cpu() - z_ref.grad).abs().max().item() / max(z_ref.grad.abs().max().item(), 1e-12)
     return fwd_err, worst, zrel, checked
 

@@ -183,17 +183,11 @@ def test_stem_head_and_bn_stats():
 # ---------------------------------------------------------------------------------------------
 # backward kernels
 # ---------------------------------------------------------------------------------------------
-def _bf16_planes(t):
-    from deepsee_b200 import ops
-    planes, sums = ops.grad_prep(t)
-    return planes, sums
-
-
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 128, 128), (2, 16, 16, 128, 256),
                                             (1, 24, 40, 512, 512), (2, 12, 20, 64, 128)])
 @pytest.mark.parametrize("passes", [1, 3])
 def test_wgrad_and_dgrad_match_autograd(B, H, W, Cin, Cout, passes):
-    """conv3x3_wgrad (bf16 gradient planes x fp16 activation planes, MN-major tcgen05 operands) and
+    """conv3x3_wgrad (scaled fp16 gradient planes x fp16 activation planes, MN-major tcgen05 operands) and
     backward-data (the forward kernel on gradient planes with the transposed filter) against
     torch autograd of F.conv2d."""
     from deepsee_b200 import ops
