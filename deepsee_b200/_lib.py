@@ -25,6 +25,9 @@ SYMBOLS = [
     "dsee_stem_fwd", "dsee_head_fwd",
     "dsee_conv2d_direct_fwd", "dsee_instance_norm_fwd", "dsee_region_pool_chunks",
     "dsee_region_pool_fwd", "dsee_nchw_to_nhwc", "dsee_disc_input", "dsee_avgpool3s2_fwd",
+    "dsee_act_bwd", "dsee_conv2d_direct_dgrad", "dsee_conv2d_direct_wgrad_workspace_floats",
+    "dsee_conv2d_direct_wgrad", "dsee_channel_sum_chunks", "dsee_channel_sum",
+    "dsee_instance_norm_bwd", "dsee_region_pool_bwd", "dsee_avgpool3s2_bwd", "dsee_disc_input_bwd",
 ]
 
 
@@ -125,6 +128,15 @@ def load():
         "dsee_nchw_to_nhwc": [vp, vp, i, i, i, i, i, vp],
         "dsee_disc_input": [vp, vp, vp, vp, i, i, i, i, i, vp],
         "dsee_avgpool3s2_fwd": [vp, vp, i, i, i, i, vp],
+        "dsee_act_bwd": [vp, vp, vp, i64, i, vp],
+        "dsee_conv2d_direct_dgrad": [vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp],
+        "dsee_conv2d_direct_wgrad": [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp],
+        "dsee_channel_sum_chunks": [i64],
+        "dsee_channel_sum": [vp, i64, i, vp, vp, vp],
+        "dsee_instance_norm_bwd": [vp, vp, vp, vp, vp, vp, i, i, i, i, vp],
+        "dsee_region_pool_bwd": [vp, vp, vp, i, i, i, i, vp],
+        "dsee_avgpool3s2_bwd": [vp, vp, i, i, i, i, vp],
+        "dsee_disc_input_bwd": [vp, vp, i, i, i, i, i, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -132,6 +144,8 @@ def load():
         fn.restype = C.c_int
     lib.dsee_conv3x3_wgrad_workspace_floats.argtypes = [i, i, i, i, i]
     lib.dsee_conv3x3_wgrad_workspace_floats.restype = C.c_int64
+    lib.dsee_conv2d_direct_wgrad_workspace_floats.argtypes = [i, i, i, i, i, i, i]
+    lib.dsee_conv2d_direct_wgrad_workspace_floats.restype = C.c_int64
     if lib.dsee_version() != ABI_VERSION:
         raise RuntimeError("deepsee_b200: ABI version mismatch")
     _lib = lib

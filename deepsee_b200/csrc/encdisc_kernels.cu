@@ -406,3 +406,424 @@ extern "C" int dsee_avgpool3s2_fwd(const float* in, float* out, int B, int Hi, i
     avgpool3s2_kernel<<<cdiv2(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, Hi, Wi, C, Ho, Wo);
     LAUNCH_END();
 }
+
+// =================================================================================================
+// backward of the style-encoder / discriminator layers (fp32, NHWC; deterministic reductions)
+// =================================================================================================
+namespace dsee {
+
+// dx = dy * act'(.) from the layer OUTPUT: act 1 LeakyReLU (sign of out), 2 tanh (1 - out^2)
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ out,
+                               float* __restrict__ dx, int64_t n, int act, float slope) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float o = out[i];
+    dx[i] = dy[i] * (act == 1 ? (o > 0.f ? 1.f : slope) : (1.f - o * o));
+}
+
+// backward-data of direct_conv_kernel: thread = one (pre-upsample) input pixel x 4 input channels
+//   dx[b,yi,xi,ci] = sum over the 2^ups x 2^ups upsampled copies (yu,xu), taps (ky,kx) with
+//                    yo*stride - pad + ky == yu, and co:  dy[b,yo,xo,co] * w[ky][kx][ci][co]
+__global__ void __launch_bounds__(128)
+direct_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                    int B, int Hi, int Wi, int Cin, int Ho, int Wo, int Cout, int KH, int KW,
+                    int stride, int pad, int ups) {
+    const int cq = Cin >> 2;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * Hi * Wi * cq) return;
+    const int q = (int)(i % cq);
+    int64_t r = i / cq;
+    const int xi = (int)(r % Wi);
+    r /= Wi;
+    const int yi = (int)(r % Hi);
+    const int b = (int)(r / Hi);
+    const int f = 1 << ups;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sy = 0; sy < f; ++sy)
+        for (int sx = 0; sx < f; ++sx) {
+            const int yu = yi * f + sy, xu = xi * f + sx;
+            for (int ky = 0; ky < KH; ++ky) {
+                const int ty = yu + pad - ky;
+                if (ty < 0 || ty % stride != 0) continue;
+                const int yo = ty / stride;
+                if (yo >= Ho) continue;
+                for (int kx = 0; kx < KW; ++kx) {
+                    const int tx = xu + pad - kx;
+                    if (tx < 0 || tx % stride != 0) continue;
+                    const int xo = tx / stride;
+                    if (xo >= Wo) continue;
+                    const float* dp = dy + (((size_t)b * Ho + yo) * Wo + xo) * Cout;
+                    const float* wt = w + ((size_t)(ky * KW + kx) * Cin + q * 4) * Cout;
+                    int co = 0;
+                    if ((Cout & 3) == 0) {
+                        for (; co < Cout; co += 4) {
+                            const float4 d = __ldg(reinterpret_cast<const float4*>(dp + co));
+                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + co));
+                            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + Cout + co));
+                            const float4 w2 = __ldg(reinterpret_cast<const float4*>(wt + 2 * Cout + co));
+                            const float4 w3 = __ldg(reinterpret_cast<const float4*>(wt + 3 * Cout + co));
+                            acc.x += d.x * w0.x + d.y * w0.y + d.z * w0.z + d.w * w0.w;
+                            acc.y += d.x * w1.x + d.y * w1.y + d.z * w1.z + d.w * w1.w;
+                            acc.z += d.x * w2.x + d.y * w2.y + d.z * w2.z + d.w * w2.w;
+                            acc.w += d.x * w3.x + d.y * w3.y + d.z * w3.z + d.w * w3.w;
+                        }
+                    }
+                    for (; co < Cout; ++co) {
+                        const float d = __ldg(dp + co);
+                        acc.x += d * __ldg(wt + co);
+                        acc.y += d * __ldg(wt + Cout + co);
+                        acc.z += d * __ldg(wt + 2 * Cout + co);
+                        acc.w += d * __ldg(wt + 3 * Cout + co);
+                    }
+                }
+            }
+        }
+    *reinterpret_cast<float4*>(dx + (((size_t)b * Hi + yi) * Wi + xi) * Cin + q * 4) = acc;
+}
+
+// weight gradient of direct_conv_kernel as a pixel-reduction GEMM per filter tap:
+//   dw[tap][ci][co] = sum_p x[p @ tap][ci] * dy[p][co]
+// block = 256 threads -> a 64(ci) x 64(co) tile, 4x4 per thread, 16 pixels per smem stage; the
+// pixel range is split over `splits` blocks whose partial tiles a fixed-order kernel reduces.
+constexpr int DW_T = 64, DW_PK = 16;
+__global__ void __launch_bounds__(256)
+direct_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                    float* __restrict__ partial, int B, int Hi, int Wi, int Cin, int Ho, int Wo,
+                    int Cout, int KH, int KW, int stride, int pad, int ups, int splits, int ci_tiles,
+                    int co_tiles) {
+    __shared__ float xs[DW_PK][DW_T];
+    __shared__ float ds[DW_PK][DW_T];
+    int u = blockIdx.x;
+    const int cot = u % co_tiles;
+    u /= co_tiles;
+    const int cit = u % ci_tiles;
+    u /= ci_tiles;
+    const int tap = u % (KH * KW);
+    const int split = u / (KH * KW);
+    const int ky = tap / KW, kx = tap % KW;
+    const int ci0 = cit * DW_T, co0 = cot * DW_T;
+    const int64_t npix = (int64_t)B * Ho * Wo;
+    const int64_t pbeg = npix * split / splits, pend = npix * (split + 1) / splits;
+    const int Hu = Hi << ups, Wu = Wi << ups;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+    for (int64_t p0 = pbeg; p0 < pend; p0 += DW_PK) {
+        for (int e = threadIdx.x; e < DW_PK * DW_T; e += 256) {
+            const int pk = e / DW_T, c = e % DW_T;
+            const int64_t p = p0 + pk;
+            float xv = 0.f, dv = 0.f;
+            if (p < pend) {
+                const int xo = (int)(p % Wo);
+                const int yo = (int)((p / Wo) % Ho);
+                const int b = (int)(p / ((int64_t)Wo * Ho));
+                const int yu = yo * stride - pad + ky, xu = xo * stride - pad + kx;
+                if (yu >= 0 && yu < Hu && xu >= 0 && xu < Wu && ci0 + c < Cin)
+                    xv = __ldg(x + (((size_t)b * Hi + (yu >> ups)) * Wi + (xu >> ups)) * Cin + ci0 + c);
+                if (co0 + c < Cout) dv = __ldg(dy + (size_t)p * Cout + co0 + c);
+            }
+            xs[pk][c] = xv;
+            ds[pk][c] = dv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int pk = 0; pk < DW_PK; ++pk) {
+            const float4 a = *reinterpret_cast<const float4*>(&xs[pk][ty * 4]);
+            const float4 d = *reinterpret_cast<const float4*>(&ds[pk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, dv4[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] += av[r] * dv4[c];
+        }
+        __syncthreads();
+    }
+    float* out = partial + ((size_t)split * KH * KW + tap) * Cin * Cout;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int ci = ci0 + ty * 4 + r;
+        if (ci >= Cin) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int co = co0 + tx * 4 + c;
+            if (co < Cout) out[(size_t)ci * Cout + co] = acc[r][c];
+        }
+    }
+}
+
+// out[i] = sum_s partial[s][i]  (fixed order)
+__global__ void sum_splits_kernel(const float* __restrict__ partial, float* __restrict__ out, int splits,
+                                  int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a = 0.f;
+    for (int s = 0; s < splits; ++s) a += partial[(size_t)s * n + i];
+    out[i] = a;
+}
+
+// per-channel sums over pixels (bias gradient): grid (C/32, chunks); partial [chunks][C]
+constexpr int CS_PIX = 2048;
+__global__ void channel_sum_kernel(const float* __restrict__ x, int64_t npix, int C,
+                                   float* __restrict__ partial) {
+    __shared__ float sh[8][32];
+    const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    const int64_t p0 = (int64_t)blockIdx.y * CS_PIX;
+    const int64_t p1 = p0 + CS_PIX < npix ? p0 + CS_PIX : npix;
+    float a = 0.f;
+    if (c < C)
+        for (int64_t p = p0 + g; p < p1; p += 8) a += __ldg(x + (size_t)p * C + c);
+    sh[g][cl] = a;
+    __syncthreads();
+    if (g == 0 && c < C) {
+        float t = 0.f;
+        for (int j = 0; j < 8; ++j) t += sh[j][cl];
+        partial[(size_t)blockIdx.y * C + c] = t;
+    }
+}
+
+// instance-norm backward. y = (x - mean) * rstd, out = act(y):
+//   g = dout * act'(y);  dx = rstd * (g - mean_p(g) - y * mean_p(g * y))
+// stats kernel: grid (C/32, B), block 32 x 8 -> sums[b][c][2] = (sum g, sum g*y)
+__device__ __forceinline__ float act_grad(float y, int act, float slope) {
+    if (act == 1) return y > 0.f ? 1.f : slope;
+    if (act == 2) {
+        const float t = tanhf(y);
+        return 1.f - t * t;
+    }
+    return 1.f;
+}
+__global__ void instnorm_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ dout,
+                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                          int HW, int C, int act, float slope, float* __restrict__ sums) {
+    __shared__ double sh[8][32][2];
+    const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl, b = blockIdx.y;
+    double s0 = 0.0, s1 = 0.0;
+    if (c < C) {
+        const float m = mean[(size_t)b * C + c], r = rstd[(size_t)b * C + c];
+        const size_t base = (size_t)b * HW * C + c;
+        for (int i = g; i < HW; i += 8) {
+            const float y = (__ldg(x + base + (size_t)i * C) - m) * r;
+            const float gg = __ldg(dout + base + (size_t)i * C) * act_grad(y, act, slope);
+            s0 += gg;
+            s1 += (double)gg * y;
+        }
+    }
+    sh[g][cl][0] = s0;
+    sh[g][cl][1] = s1;
+    __syncthreads();
+    if (g == 0 && c < C) {
+        double a = 0, q = 0;
+        for (int k = 0; k < 8; ++k) {
+            a += sh[k][cl][0];
+            q += sh[k][cl][1];
+        }
+        sums[((size_t)b * C + c) * 2] = (float)(a / HW);
+        sums[((size_t)b * C + c) * 2 + 1] = (float)(q / HW);
+    }
+}
+__global__ void instnorm_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dout,
+                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                          const float* __restrict__ sums, float* __restrict__ dx,
+                                          int64_t n, int HW, int C, int act, float slope) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(i % C);
+    const int b = (int)(i / ((int64_t)C * HW));
+    const size_t bc = (size_t)b * C + c;
+    const float r = rstd[bc];
+    const float y = (x[i] - mean[bc]) * r;
+    const float g = dout[i] * act_grad(y, act, slope);
+    dx[i] = r * (g - sums[bc * 2] - y * sums[bc * 2 + 1]);
+}
+
+// backward of region_pool: dx[b,p,c] = dstyle[b, labels[b,p], c] / HW
+__global__ void region_pool_bwd_kernel(const float* __restrict__ dstyle, const uint8_t* __restrict__ labels,
+                                       float* __restrict__ dx, int64_t n4, int HW, int C, int L,
+                                       float inv_hw) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int cq = C >> 2;
+    const int q = (int)(i % cq);
+    const int64_t bp = i / cq;
+    const int b = (int)(bp / HW);
+    const int l = labels[bp];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (l < L) {
+        v = __ldg(reinterpret_cast<const float4*>(dstyle + ((size_t)b * L + l) * C) + q);
+        v.x *= inv_hw; v.y *= inv_hw; v.z *= inv_hw; v.w *= inv_hw;
+    }
+    reinterpret_cast<float4*>(dx)[i] = v;
+}
+
+// backward of avgpool3s2 (count_include_pad=False): din[yi,xi] = sum over outputs covering it of
+// dout / count(output)
+__global__ void avgpool3s2_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din, int B,
+                                      int Hi, int Wi, int C, int Ho, int Wo) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * Hi * Wi * C) return;
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int xi = (int)(r % Wi);
+    r /= Wi;
+    const int yi = (int)(r % Hi);
+    const int b = (int)(r / Hi);
+    float s = 0.f;
+    for (int yo = (yi) / 2; yo <= (yi + 1) / 2; ++yo) {
+        if (yo >= Ho) continue;
+        const int y0 = max(yo * 2 - 1, 0), y1 = min(yo * 2 + 1, Hi - 1);
+        for (int xo = (xi) / 2; xo <= (xi + 1) / 2; ++xo) {
+            if (xo >= Wo) continue;
+            const int x0 = max(xo * 2 - 1, 0), x1 = min(xo * 2 + 1, Wi - 1);
+            const int cnt = (y1 - y0 + 1) * (x1 - x0 + 1);
+            s += dout[(((size_t)b * Ho + yo) * Wo + xo) * C + c] / (float)cnt;
+        }
+    }
+    din[i] = s;
+}
+
+// backward of disc_input wrt the fake image: dfake[b,c,p] = dx[b,p,L+c] (first B images)
+__global__ void disc_input_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dfake, int B,
+                                      int L, int HW, int Cp) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * 3 * HW) return;
+    const int p = (int)(i % HW);
+    const int c = (int)((i / HW) % 3);
+    const int b = (int)(i / ((int64_t)3 * HW));
+    dfake[i] = dx[((size_t)b * HW + p) * Cp + L + c];
+}
+
+}  // namespace dsee
+
+extern "C" int dsee_act_bwd(const float* dy, const float* out, float* dx, int64_t n, int act,
+                            void* stream) {
+    DSEE_CHECK_ARG(dy && out && dx && n > 0 && (act == 1 || act == 2), "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    act_bwd_kernel<<<cdiv2(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, out, dx, n, act, 0.2f);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_conv2d_direct_dgrad(const float* dy, const float* w, float* dx, int B, int Hi,
+                                        int Wi, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                                        int ups, void* stream) {
+    DSEE_CHECK_ARG(dy && w && dx && B > 0 && Hi > 0 && Wi > 0 && Cin > 0 && Cin % 4 == 0 && Cout > 0,
+                   "bad argument (Cin must be a multiple of 4)");
+    DSEE_CHECK_ARG(stride >= 1 && (ups == 0 || ups == 1), "bad stride/ups");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int Hu = Hi << ups, Wu = Wi << ups;
+    const int Ho = (Hu + 2 * pad - KH) / stride + 1, Wo = (Wu + 2 * pad - KW) / stride + 1;
+    int64_t n = (int64_t)B * Hi * Wi * (Cin / 4);
+    direct_dgrad_kernel<<<cdiv2(n, 128), 128, 0, (cudaStream_t)stream>>>(
+        dy, w, dx, B, Hi, Wi, Cin, Ho, Wo, Cout, KH, KW, stride, pad, ups);
+    LAUNCH_END();
+}
+
+static int direct_wgrad_splits(int64_t npix, int tiles) {
+    int splits = (148 * 4 + tiles - 1) / tiles;
+    const int64_t maxs = (npix + 255) / 256;  // at least 256 pixels per split
+    if (splits > maxs) splits = (int)maxs;
+    if (splits < 1) splits = 1;
+    if (splits > 64) splits = 64;
+    return splits;
+}
+
+extern "C" int64_t dsee_conv2d_direct_wgrad_workspace_floats(int B, int Ho, int Wo, int Cin, int Cout,
+                                                             int KH, int KW) {
+    const int tiles = KH * KW * ((Cin + DW_T - 1) / DW_T) * ((Cout + DW_T - 1) / DW_T);
+    return (int64_t)direct_wgrad_splits((int64_t)B * Ho * Wo, tiles) * KH * KW * Cin * Cout;
+}
+
+extern "C" int dsee_conv2d_direct_wgrad(const float* x, const float* dy, float* dw, float* workspace,
+                                        int B, int Hi, int Wi, int Cin, int Cout, int KH, int KW,
+                                        int stride, int pad, int ups, void* stream) {
+    DSEE_CHECK_ARG(x && dy && dw && workspace && B > 0 && Hi > 0 && Wi > 0 && Cin > 0 && Cout > 0,
+                   "bad argument");
+    DSEE_CHECK_ARG(stride >= 1 && (ups == 0 || ups == 1), "bad stride/ups");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int Hu = Hi << ups, Wu = Wi << ups;
+    const int Ho = (Hu + 2 * pad - KH) / stride + 1, Wo = (Wu + 2 * pad - KW) / stride + 1;
+    const int ci_tiles = (Cin + DW_T - 1) / DW_T, co_tiles = (Cout + DW_T - 1) / DW_T;
+    const int tiles = KH * KW * ci_tiles * co_tiles;
+    const int splits = direct_wgrad_splits((int64_t)B * Ho * Wo, tiles);
+    cudaStream_t st = (cudaStream_t)stream;
+    direct_wgrad_kernel<<<tiles * splits, 256, 0, st>>>(x, dy, workspace, B, Hi, Wi, Cin, Ho, Wo, Cout,
+                                                        KH, KW, stride, pad, ups, splits, ci_tiles,
+                                                        co_tiles);
+    count_launch();
+    const int64_t n = (int64_t)KH * KW * Cin * Cout;
+    sum_splits_kernel<<<cdiv2(n, 256), 256, 0, st>>>(workspace, dw, splits, n);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_channel_sum_chunks(int64_t npix) { return cdiv2(npix, CS_PIX); }
+
+extern "C" int dsee_channel_sum(const float* x, int64_t npix, int C, float* workspace, float* out,
+                                void* stream) {
+    DSEE_CHECK_ARG(x && workspace && out && npix > 0 && C > 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = dsee_channel_sum_chunks(npix);
+    channel_sum_kernel<<<dim3(cdiv2(C, 32), chunks), 256, 0, st>>>(x, npix, C, workspace);
+    count_launch();
+    sum_splits_kernel<<<cdiv2(C, 256), 256, 0, st>>>(workspace, out, chunks, C);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_instance_norm_bwd(const float* x, const float* dout, const float* mean,
+                                      const float* rstd, float* dx, float* sums, int B, int HW, int C,
+                                      int act, void* stream) {
+    DSEE_CHECK_ARG(x && dout && mean && rstd && dx && sums && B > 0 && HW > 0 && C > 0, "bad argument");
+    DSEE_CHECK_ARG(act >= 0 && act <= 2, "act must be 0, 1 or 2");
+    int rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    instnorm_bwd_stats_kernel<<<dim3(cdiv2(C, 32), B), 256, 0, st>>>(x, dout, mean, rstd, HW, C, act,
+                                                                      0.2f, sums);
+    count_launch();
+    const int64_t n = (int64_t)B * HW * C;
+    instnorm_bwd_apply_kernel<<<cdiv2(n, 256), 256, 0, st>>>(x, dout, mean, rstd, sums, dx, n, HW, C,
+                                                             act, 0.2f);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_region_pool_bwd(const float* dstyle, const uint8_t* labels, float* dx, int B,
+                                    int HW, int C, int L, void* stream) {
+    DSEE_CHECK_ARG(dstyle && labels && dx && B > 0 && HW > 0 && C > 0 && C % 4 == 0 && L > 0,
+                   "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int64_t n4 = (int64_t)B * HW * (C / 4);
+    region_pool_bwd_kernel<<<cdiv2(n4, 256), 256, 0, (cudaStream_t)stream>>>(dstyle, labels, dx, n4, HW,
+                                                                             C, L, 1.0f / (float)HW);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_avgpool3s2_bwd(const float* dout, float* din, int B, int Hi, int Wi, int C,
+                                   void* stream) {
+    DSEE_CHECK_ARG(dout && din && B > 0 && Hi > 0 && Wi > 0 && C > 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int Ho = (Hi + 2 - 3) / 2 + 1, Wo = (Wi + 2 - 3) / 2 + 1;
+    const int64_t n = (int64_t)B * Hi * Wi * C;
+    avgpool3s2_bwd_kernel<<<cdiv2(n, 256), 256, 0, (cudaStream_t)stream>>>(dout, din, B, Hi, Wi, C, Ho,
+                                                                           Wo);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_disc_input_bwd(const float* dx, float* dfake, int B, int L, int H, int W, int Cp,
+                                   void* stream) {
+    DSEE_CHECK_ARG(dx && dfake && B > 0 && L > 0 && Cp >= L + 3, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int64_t n = (int64_t)B * 3 * H * W;
+    disc_input_bwd_kernel<<<cdiv2(n, 256), 256, 0, (cudaStream_t)stream>>>(dx, dfake, B, L, H * W, Cp);
+    LAUNCH_END();
+}

@@ -37,13 +37,16 @@ class MultiscaleDiscriminator(BaseNetwork):
 
     def downsample(self, x_nhwc):
         """discriminator.py:46-49: avg_pool2d(3, stride 2, pad 1, count_include_pad=False)."""
-        return ops.avgpool3s2(x_nhwc)
+        return ops.AvgPool3s2Fn.apply(x_nhwc)
 
-    def forward_nhwc(self, x_nhwc):
+    def forward_nhwc(self, x_nhwc, detach_params=False):
+        """``detach_params``: the generator step only needs the gradient wrt the input; detaching
+        the weights skips the discriminator's weight-gradient kernels there (the reference computes
+        and then discards those gradients: trainer_manager.py:48-49 zeroes them before use)."""
         result = []
         feats = not self.opt.no_ganFeat_loss
         for name, D in self.named_children():
-            out = D.forward_nhwc(x_nhwc)
+            out = D.forward_nhwc(x_nhwc, detach_params)
             result.append(out if feats else [out[-1]])
             x_nhwc = self.downsample(x_nhwc)
         return result
@@ -84,22 +87,23 @@ class NLayerDiscriminator(BaseNetwork):
     def compute_D_input_nc(self, opt):
         return opt.label_nc + opt.output_nc + (1 if opt.contain_dontcare_label else 0)
 
-    def forward_nhwc(self, x):
+    def forward_nhwc(self, x, detach_params=False):
         """x NHWC [B,H,W,Cp] (channels beyond input_nc are zero) -> list of NHWC feature maps."""
+        det = (lambda t: t.detach() if t is not None else None) if detach_params else (lambda t: t)
         outs = []
         conv0 = self.model0[0]
-        x = ops.conv2d_direct(x, _khwc(conv0.weight.detach(), x.shape[3]), conv0.bias, stride=2,
-                              pad=2, lrelu=True)
+        x = ops.Conv2dDirectFn.apply(x, det(_khwc(conv0.weight, x.shape[3])), det(conv0.bias), 2, 2, 0,
+                                     True)
         outs.append(x)
         for n in range(1, self.n_layers):
             seq = getattr(self, 'model%d' % n)[0]  # Sequential(spectral conv, InstanceNorm2d)
             conv = seq[0]
             stride = 1 if n == self.n_layers - 1 else 2
-            y = ops.conv2d_direct(x, _khwc(effective_weight(conv).detach()), None, stride=stride, pad=2)
-            x, _, _ = ops.instance_norm(y, 1)
+            y = ops.Conv2dDirectFn.apply(x, det(_khwc(effective_weight(conv))), None, stride, 2, 0, False)
+            x = ops.InstanceNormFn.apply(y, 1)
             outs.append(x)
         last = getattr(self, 'model%d' % self.n_layers)[0]
-        x = ops.conv2d_direct(x, _khwc(last.weight.detach()), last.bias, stride=1, pad=2)
+        x = ops.Conv2dDirectFn.apply(x, det(_khwc(last.weight)), det(last.bias), 1, 2, 0, False)
         outs.append(x)
         return outs
 

@@ -26,12 +26,13 @@ def _khwc(w, pad_cin=None):
 
 
 def _stage(x, seq, stride=1, ups=0, act=1, pad_cin=None):
-    """x NHWC -> act(instance_norm(conv(x))). ``seq`` = nn.Sequential(spectral conv, InstanceNorm)."""
+    """x NHWC -> act(instance_norm(conv(x))). ``seq`` = nn.Sequential(spectral conv, InstanceNorm).
+    The spectral-normalised weight stays an autograd tensor, so the weight gradient the conv node
+    returns flows on to ``weight_orig`` through torch's own spectral-norm graph."""
     conv = seq[0]
-    w = _khwc(effective_weight(conv).detach(), pad_cin)
-    y = ops.conv2d_direct(x, w, None, stride=stride, pad=1, ups=ups)
-    out, _, _ = ops.instance_norm(y, act)
-    return out
+    w = _khwc(effective_weight(conv), pad_cin)
+    y = ops.Conv2dDirectFn.apply(x, w, None, stride, 1, ups, False)
+    return ops.InstanceNormFn.apply(y, act)
 
 
 class AbtractStyleEncoder(BaseNetwork):
@@ -55,7 +56,7 @@ class AbtractStyleEncoder(BaseNetwork):
         """encoder.py:36-49 (divides by H*W of the feature map, not by the region area)."""
         B, H, W, _ = x_nhwc.shape
         labels = ops.resize_labels(labels_full, H, W)
-        return ops.region_pool(x_nhwc, labels, self.opt.label_nc)
+        return ops.RegionPoolFn.apply(x_nhwc, labels, self.opt.label_nc)
 
     def corrupt_style_matrix(self, style_matrix, max_range_noise, region_idx=None):
         """encoder.py:51-70 (all regions). Tiny [B,19,128] elementwise op; the uniform draw uses
@@ -64,12 +65,17 @@ class AbtractStyleEncoder(BaseNetwork):
             raise NotImplementedError('region_idx subsets are a demo-only feature')
         w = torch.sigmoid(self.noise_weights).view(1, -1, 1)
         if self.opt.noisy_style_dist == 'uniform':
-            noise = (torch.rand_like(style_matrix) * 2 - 1) * max_range_noise
+            noise = (self._unit_noise(style_matrix) * 2 - 1) * max_range_noise
         elif self.opt.noisy_style_dist == 'normal':
             noise = (torch.randn_like(style_matrix) * 2 - 1) * max_range_noise
         else:
             raise ValueError("Does not exist: {}".format(self.opt.noisy_style_dist))
         return (style_matrix + noise * w).clamp(-1, 1)
+
+    def _unit_noise(self, like):
+        """U[0,1) draw of corrupt_style_matrix (encoder.py:62); a method so tests can replay the
+        reference's draw."""
+        return torch.rand_like(like)
 
     def _final(self, x):
         return _stage(x, self.final[0], act=2)

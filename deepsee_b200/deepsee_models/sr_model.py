@@ -149,7 +149,8 @@ class SRModel(torch.nn.Module):
         fake_image, _, _ = self.generate_fake(
             input_semantics=input_semantics, image_downsized=image_downsized,
             full_image=style_image, guiding_image=guiding_image, guiding_label=guiding_label)
-        pred_fake, pred_real = self.discriminate(input_semantics, fake_image, image_full)
+        pred_fake, pred_real = self.discriminate(input_semantics, fake_image, image_full,
+                                                 for_generator=True)
         SR_losses['GAN'] = self.criterionGAN(pred_fake, True, for_discriminator=False)
         if not self.opt.no_ganFeat_loss:
             num_D = len(pred_fake)
@@ -172,7 +173,8 @@ class SRModel(torch.nn.Module):
                 input_semantics=input_semantics, image_downsized=image_downsized,
                 full_image=image_full, guiding_image=guiding_image, guiding_label=guiding_label)
             fake_image = fake_image.detach()
-        fake_image.requires_grad_()
+        # (the reference also calls fake_image.requires_grad_() here, sr_model.py:556; nothing
+        # reads that gradient, so the input-gradient kernels of the first layer are skipped)
         pred_fake, pred_real = self.discriminate(input_semantics, fake_image, image_full)
         D_losses['D_Fake'] = self.criterionGAN(pred_fake, False, for_discriminator=True)
         D_losses['D_Real'] = self.criterionGAN(pred_real, True, for_discriminator=True)
@@ -229,15 +231,15 @@ class SRModel(torch.nn.Module):
             self.last_encoded_style_is_noisy = not no_noise
         return self.netE(style_image, style_semantics, mode=mode, no_noise=no_noise)
 
-    def discriminate(self, input_semantics, fake_image, real_image):
+    def discriminate(self, input_semantics, fake_image, real_image, for_generator=False):
         """sr_model.py:655-668: D sees [seg | fake] and [seg | real] in one batch. The two cats and
         the NCHW->NHWC conversion are one kernel (ops.disc_input) on the uint8 label map."""
         labels, _ = ops.labels_from_onehot(input_semantics.contiguous().float())
         L = input_semantics.shape[1]
         cp = (L + 3 + 3) // 4 * 4
-        x = ops.disc_input(labels, fake_image.contiguous().float(), real_image.contiguous().float(),
-                           L, cp)
-        out = self.netD.forward_nhwc(x)
+        x = ops.DiscInputFn.apply(labels, fake_image.contiguous().float(),
+                                  real_image.contiguous().float(), L, cp)
+        out = self.netD.forward_nhwc(x, detach_params=for_generator)
         out = [[t.permute(0, 3, 1, 2) for t in scale] for scale in out]
         return self.divide_pred(out)
 

@@ -563,3 +563,150 @@ def avgpool3s2(x):
     out = torch.empty((B, Ho, Wo, Cc), dtype=torch.float32, device=x.device)
     _lib.check(_lib.load().dsee_avgpool3s2_fwd(_p(x), _p(out), B, Hi, Wi, Cc, _stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# style encoder / discriminator backward, and the autograd nodes that tie forward and backward
+# together (fp32 NHWC tensors, so PyTorch's autograd carries them between layers and into the
+# loss code unchanged)
+# ---------------------------------------------------------------------------------------------
+def act_bwd(dy, out, act):
+    _chk_cuda(dy, out)
+    dx = torch.empty_like(dy)
+    _lib.check(_lib.load().dsee_act_bwd(_p(dy), _p(out), _p(dx), dy.numel(), act, _stream()))
+    return dx
+
+
+def conv2d_direct_dgrad(dy, w_khwc, x_shape, stride, pad, ups):
+    _chk_cuda(dy, w_khwc)
+    B, Hi, Wi, Cin = x_shape
+    KH, KW, _, Cout = w_khwc.shape
+    dx = torch.empty(x_shape, dtype=torch.float32, device=dy.device)
+    _lib.check(_lib.load().dsee_conv2d_direct_dgrad(_p(dy), _p(w_khwc), _p(dx), B, Hi, Wi, Cin, Cout,
+                                                    KH, KW, stride, pad, ups, _stream()))
+    return dx
+
+
+def conv2d_direct_wgrad(x, dy, w_shape, stride, pad, ups):
+    _chk_cuda(x, dy)
+    B, Hi, Wi, Cin = x.shape
+    KH, KW, _, Cout = w_shape
+    _, Ho, Wo, _ = dy.shape
+    lib = _lib.load()
+    ws = torch.empty(lib.dsee_conv2d_direct_wgrad_workspace_floats(B, Ho, Wo, Cin, Cout, KH, KW),
+                     dtype=torch.float32, device=x.device)
+    dw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
+    _lib.check(lib.dsee_conv2d_direct_wgrad(_p(x), _p(dy), _p(dw), _p(ws), B, Hi, Wi, Cin, Cout, KH, KW,
+                                            stride, pad, ups, _stream()))
+    return dw
+
+
+def channel_sum(x):
+    """[..., C] -> [C] sums over all leading dims."""
+    _chk_cuda(x)
+    Cc = x.shape[-1]
+    npix = x.numel() // Cc
+    lib = _lib.load()
+    ws = torch.empty((lib.dsee_channel_sum_chunks(npix), Cc), dtype=torch.float32, device=x.device)
+    out = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    _lib.check(lib.dsee_channel_sum(_p(x), npix, Cc, _p(ws), _p(out), _stream()))
+    return out
+
+
+class Conv2dDirectFn(torch.autograd.Function):
+    """conv2d_direct (+ fused LeakyReLU) with its backward-data / weight-gradient kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w_khwc, bias, stride, pad, ups, lrelu):
+        w_khwc = w_khwc.contiguous()
+        out = conv2d_direct(x, w_khwc, bias, stride=stride, pad=pad, ups=ups, lrelu=lrelu)
+        ctx.cfg = (stride, pad, ups, lrelu, bias is not None)
+        ctx.save_for_backward(x, w_khwc, out if lrelu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, out = ctx.saved_tensors
+        stride, pad, ups, lrelu, has_bias = ctx.cfg
+        dy = dy.contiguous()
+        if lrelu:
+            dy = act_bwd(dy, out, 1)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = conv2d_direct_dgrad(dy, w, tuple(x.shape), stride, pad, ups)
+        if ctx.needs_input_grad[1]:
+            dw = conv2d_direct_wgrad(x, dy, tuple(w.shape), stride, pad, ups)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = channel_sum(dy)
+        return dx, dw, db, None, None, None, None
+
+
+class InstanceNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        out, mean, rstd = instance_norm(x, act)
+        ctx.act = act
+        ctx.save_for_backward(x, mean, rstd)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, mean, rstd = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, H, W, Cc = x.shape
+        dx = torch.empty_like(x)
+        sums = torch.empty((B, Cc, 2), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().dsee_instance_norm_bwd(_p(x), _p(dout), _p(mean), _p(rstd), _p(dx),
+                                                      _p(sums), B, H * W, Cc, ctx.act, _stream()))
+        return dx, None
+
+
+class RegionPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, labels, L):
+        ctx.save_for_backward(labels)
+        ctx.shape = tuple(x.shape)
+        ctx.L = L
+        return region_pool(x, labels, L)
+
+    @staticmethod
+    def backward(ctx, dstyle):
+        (labels,) = ctx.saved_tensors
+        B, H, W, Cc = ctx.shape
+        dstyle = dstyle.contiguous()
+        dx = torch.empty(ctx.shape, dtype=torch.float32, device=dstyle.device)
+        _lib.check(_lib.load().dsee_region_pool_bwd(_p(dstyle), _p(labels), _p(dx), B, H * W, Cc, ctx.L,
+                                                    _stream()))
+        return dx, None, None
+
+
+class AvgPool3s2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        return avgpool3s2(x)
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, Hi, Wi, Cc = ctx.shape
+        dout = dout.contiguous()
+        din = torch.empty(ctx.shape, dtype=torch.float32, device=dout.device)
+        _lib.check(_lib.load().dsee_avgpool3s2_bwd(_p(dout), _p(din), B, Hi, Wi, Cc, _stream()))
+        return din
+
+
+class DiscInputFn(torch.autograd.Function):
+    """SRModel.discriminate's input assembly; the gradient goes to the fake image only."""
+
+    @staticmethod
+    def forward(ctx, labels, fake, real, L, Cp):
+        ctx.meta = (tuple(fake.shape), L, Cp)
+        return disc_input(labels, fake, real, L, Cp)
+
+    @staticmethod
+    def backward(ctx, dx):
+        (B, _, H, W), L, Cp = ctx.meta
+        dx = dx.contiguous()
+        dfake = torch.empty((B, 3, H, W), dtype=torch.float32, device=dx.device)
+        _lib.check(_lib.load().dsee_disc_input_bwd(_p(dx), _p(dfake), B, L, H, W, Cp, _stream()))
+        return None, dfake, None, None, None

@@ -328,6 +328,39 @@ int dsee_disc_input(const uint8_t* labels, const float* fake, const float* real,
 /* Replaces MultiscaleDiscriminator.downsample (discriminator.py:46-49), NHWC. */
 int dsee_avgpool3s2_fwd(const float* in, float* out, int B, int Hi, int Wi, int C, void* stream);
 
+/* ---- style encoder / discriminator backward (fp32, NHWC) ------------------------------------- */
+/* dx = dy * act'(.) evaluated from the layer output: act 1 LeakyReLU(0.2), 2 tanh.  Used for the
+ * LeakyReLU fused into dsee_conv2d_direct_fwd (discriminator.py:84-85). */
+int dsee_act_bwd(const float* dy, const float* out, float* dx, int64_t n, int act, void* stream);
+/* Backward-data of dsee_conv2d_direct_fwd (autograd of the nn.Conv2d calls at encoder.py:84-98,
+ * 142-157 and discriminator.py:84-96): dx fp32 NHWC [B,Hi,Wi,Cin] at the pre-upsample resolution
+ * (the folded 2x upsample is transposed into a 2x2 sum). Cin % 4 == 0. */
+int dsee_conv2d_direct_dgrad(const float* dy, const float* w, float* dx, int B, int Hi, int Wi,
+                             int Cin, int Cout, int KH, int KW, int stride, int pad, int ups,
+                             void* stream);
+/* Weight gradient, dw fp32 [KH][KW][Cin][Cout]; deterministic split over pixels through
+ * workspace fp32 [dsee_conv2d_direct_wgrad_workspace_floats()]. */
+int64_t dsee_conv2d_direct_wgrad_workspace_floats(int B, int Ho, int Wo, int Cin, int Cout, int KH,
+                                                  int KW);
+int dsee_conv2d_direct_wgrad(const float* x, const float* dy, float* dw, float* workspace, int B,
+                             int Hi, int Wi, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                             int ups, void* stream);
+/* out[c] = sum_p x[p][c] (conv bias gradient). workspace fp32 [dsee_channel_sum_chunks()][C]. */
+int dsee_channel_sum_chunks(int64_t npix);
+int dsee_channel_sum(const float* x, int64_t npix, int C, float* workspace, float* out, void* stream);
+/* Backward of dsee_instance_norm_fwd: x = the forward INPUT, mean / rstd from the forward;
+ * sums scratch fp32 [B][C][2]. */
+int dsee_instance_norm_bwd(const float* x, const float* dout, const float* mean, const float* rstd,
+                           float* dx, float* sums, int B, int HW, int C, int act, void* stream);
+/* Backward of dsee_region_pool_fwd: dx[b,p,c] = dstyle[b, labels[b,p], c] / HW. */
+int dsee_region_pool_bwd(const float* dstyle, const uint8_t* labels, float* dx, int B, int HW, int C,
+                         int L, void* stream);
+/* Backward of dsee_avgpool3s2_fwd. din fp32 NHWC [B,Hi,Wi,C]. */
+int dsee_avgpool3s2_bwd(const float* dout, float* din, int B, int Hi, int Wi, int C, void* stream);
+/* Backward of dsee_disc_input wrt the fake image: dfake NCHW [B,3,H,W] from dx NHWC [2B,H,W,Cp]. */
+int dsee_disc_input_bwd(const float* dx, float* dfake, int B, int L, int H, int W, int Cp,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

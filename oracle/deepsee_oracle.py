@@ -433,7 +433,7 @@ def discriminator_losses(sdD, opt, seg, fake, real):
 
 # ---- model facade -------------------------------------------------------------------------------
 def encode_style(sdE, opt, rng, training, image_lr, seg, image_hr, guiding_image, guiding_label,
-                 no_noise=None, encode_full=False, unit_noise=None):
+                 no_noise=None, encode_full=False, unit_noise=None, unit_noise_fn=None):
     """SRModel.get_encoder_inputs / encode_style, sr_model.py:582-650.  ``rng`` is a
     ``random.Random`` standing in for the module-level ``random`` the reference draws from."""
     variant = "guided" if "full" in opt.netE else "independent"
@@ -456,7 +456,8 @@ def encode_style(sdE, opt, rng, training, image_lr, seg, image_hr, guiding_image
         if not no_noise:
             no_noise = rng.random() < 0.5
     if unit_noise is None and not no_noise and opt.noisy_style_scale > 0:
-        unit_noise = torch.rand(style_img.shape[0], opt.label_nc, opt.regional_style_size)
+        shape = (style_img.shape[0], opt.label_nc, opt.regional_style_size)
+        unit_noise = unit_noise_fn(shape) if unit_noise_fn is not None else torch.rand(shape)
     return encode_style_run(sdE, opt, style_img, style_sem, mode, no_noise, unit_noise, training), mode
 
 
@@ -664,11 +665,15 @@ class CpuTrainer:
     def _noise_fn(self, name, shape):
         return torch.randn(shape)
 
+    def _style_noise(self, shape):
+        return torch.rand(shape)
+
     def _fake(self, d):
         opt = self.opt
         style_img = d.get("guiding_image") if opt.guiding_style_image else d["image_hr"]
         z, _ = encode_style(self.sdE, opt, self.rng, True, d["image_lr"], d["input_semantics"],
-                            style_img, d.get("guiding_image"), d.get("guiding_label"))
+                            style_img, d.get("guiding_image"), d.get("guiding_label"),
+                            unit_noise_fn=self._style_noise)
         return generator_forward(self.sdG, opt, d["image_lr"], d["input_semantics"], z, True,
                                  self._noise_fn)
 

@@ -308,3 +308,92 @@ def test_shared_mlp_and_style_gather_backward():
         if not ups:
             ds = ops.style_gather_bwd(dsrc, nh, labels, L, d)
             torch.testing.assert_close(ds, style.grad, rtol=1e-4, atol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# style encoder / discriminator layer nodes: forward + backward against torch autograd
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Cin,Cout,K,stride,pad,ups,lrelu,bias", [
+    (4, 32, 3, 1, 1, 0, False, False),     # encoder initial (RGB padded to 4)
+    (32, 64, 3, 2, 1, 0, False, False),    # encoder down
+    (64, 128, 3, 1, 1, 1, False, False),   # encoder up_conv (folded upsample)
+    (24, 32, 4, 2, 2, 0, True, True),      # discriminator model0 (+ fused LeakyReLU)
+    (32, 64, 4, 2, 2, 0, False, False),    # discriminator inner
+    (64, 128, 4, 1, 2, 0, False, False),
+    (128, 1, 4, 1, 2, 0, False, True),     # discriminator prediction conv
+])
+def test_conv2d_direct_node(Cin, Cout, K, stride, pad, ups, lrelu, bias):
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(Cin * 3 + Cout + K)
+    B, H, W = 2, 13, 18
+    x = torch.randn(B, Cin, H, W, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, K, K, generator=g) / (K * Cin ** 0.5)).cuda().requires_grad_(True)
+    b = torch.randn(Cout, generator=g).cuda().requires_grad_(True) if bias else None
+    xin = F.interpolate(x, scale_factor=2, mode="nearest") if ups else x
+    ref = F.conv2d(xin, w, b, stride=stride, padding=pad)
+    if lrelu:
+        ref = F.leaky_relu(ref, 0.2)
+    dy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1)).cuda()
+    ref.backward(dy)
+    x2 = _nhwc(x.detach()).requires_grad_(True)
+    w2 = w.detach().permute(2, 3, 1, 0).contiguous().requires_grad_(True)
+    b2 = b.detach().clone().requires_grad_(True) if bias else None
+    out = ops.Conv2dDirectFn.apply(x2, w2, b2, stride, pad, ups, lrelu)
+    torch.testing.assert_close(_nchw(out), ref, rtol=1e-4, atol=1e-5)
+    out.backward(_nhwc(dy))
+    torch.testing.assert_close(_nchw(x2.grad), x.grad, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(w2.grad, w.grad.permute(2, 3, 1, 0), rtol=1e-4, atol=2e-4)
+    if bias:
+        torch.testing.assert_close(b2.grad, b.grad, rtol=1e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_instance_norm_node(act):
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(40 + act)
+    x = (torch.randn(2, 64, 9, 14, generator=g) * 1.7 + 0.3).cuda().requires_grad_(True)
+    y = F.instance_norm(x, eps=1e-5)
+    ref = [y, F.leaky_relu(y, 0.2), torch.tanh(y)][act]
+    dy = torch.randn(ref.shape, generator=g).cuda()
+    ref.backward(dy)
+    x2 = _nhwc(x.detach()).requires_grad_(True)
+    out = ops.InstanceNormFn.apply(x2, act)
+    torch.testing.assert_close(_nchw(out), ref, rtol=1e-4, atol=1e-5)
+    out.backward(_nhwc(dy))
+    torch.testing.assert_close(_nchw(x2.grad), x.grad, rtol=2e-4, atol=2e-5)
+
+
+def test_pool_and_input_nodes():
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(77)
+    B, H, W, C, L = 2, 11, 16, 128, 19
+    # region pool (encoder.py:36-49)
+    x = torch.randn(B, C, H, W, generator=g).cuda().requires_grad_(True)
+    labels = torch.randint(0, L, (B, H, W), generator=g, dtype=torch.uint8).cuda()
+    onehot = F.one_hot(labels.long(), L).permute(0, 3, 1, 2).float()
+    ref = torch.einsum("bchw,blhw->blc", x, onehot) / (H * W)
+    ds = torch.randn(B, L, C, generator=g).cuda()
+    ref.backward(ds)
+    x2 = _nhwc(x.detach()).requires_grad_(True)
+    out = ops.RegionPoolFn.apply(x2, labels, L)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-6)
+    out.backward(ds)
+    torch.testing.assert_close(_nchw(x2.grad), x.grad, rtol=1e-5, atol=1e-7)
+    # avg-pool pyramid (discriminator.py:46-49)
+    for (h, w) in ((11, 16), (8, 8), (9, 5)):
+        x = torch.randn(B, 8, h, w, generator=g).cuda().requires_grad_(True)
+        ref = F.avg_pool2d(x, 3, stride=2, padding=[1, 1], count_include_pad=False)
+        dy = torch.randn(ref.shape, generator=g).cuda()
+        ref.backward(dy)
+        x2 = _nhwc(x.detach()).requires_grad_(True)
+        out = ops.AvgPool3s2Fn.apply(x2)
+        torch.testing.assert_close(_nchw(out), ref, rtol=1e-5, atol=1e-6)
+        out.backward(_nhwc(dy))
+        torch.testing.assert_close(_nchw(x2.grad), x.grad, rtol=1e-5, atol=1e-6)
+    # discriminator input assembly (sr_model.py:655-664)
+    fake = torch.randn(B, 3, H, W, generator=g).cuda().requires_grad_(True)
+    real = torch.randn(B, 3, H, W, generator=g).cuda()
+    xin = ops.DiscInputFn.apply(labels, fake, real, L, 24)
+    dxin = torch.randn(xin.shape, generator=g).cuda()
+    xin.backward(dxin)
+    torch.testing.assert_close(fake.grad, dxin[:B, :, :, L:L + 3].permute(0, 3, 1, 2))
