@@ -2,13 +2,17 @@
 """Benchmark of the DeepSEE hot path on B200 (contract: see DESIGN.md "Measurement").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c4]
-                    [--passes 1|3]
+                    [--passes 1|3] [--mode train|infer]
 
-One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one per-GPU batch of
-synthetic input: BASELINE.json config c2 (8x SR, 256x256, independent model, batch 8 per GPU) by
-default; c4 = 32x SR 512x512 independent, batch 2 per GPU.  Inputs of the `value` measurement are
-resident in HBM; `e2e` goes through BaseManager.preprocess + SRModel.forward with pinned host
-buffers and the H2D / D2H copies inside the timed region.
+One JSON line on stdout (rank 0).  A "step" is ONE TRAINING ITERATION of the reference's loop
+(train.py:60-68: TrainerManager.run_generator_one_step + run_discriminator_one_step) over one
+per-GPU batch of synthetic input: style encoder + SPADE/SEAN generator forward and backward,
+multi-scale discriminator forward/backward, hinge + feature-matching losses, both Adam updates and,
+for N > 1, the NCCL all-reduce of the G+E and D gradients.  Default workload = BASELINE.json config
+c2 (8x SR, 256x256, independent model, batch 8 per GPU); c4 = 32x SR 512x512 independent, batch 2
+per GPU.  `value` is measured with the raw batch resident in HBM; `e2e` feeds pinned HOST buffers
+through the same TrainerManager calls (H2D copies inside the timed region) and reads the losses
+back to the host every step.
 """
 import argparse
 import json
@@ -21,19 +25,25 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# algorithmic (reference-equivalent dense conv) FLOPs per sample: SURVEY.md section 8d
 CONFIGS = {
-    "c2": dict(name="8x_independent_256x256", batch=8, flops_fwd_img=1725.1e9 + 5.0e9, d_pair=5.49e9),
-    "c4": dict(name="32x_independent_512x512", batch=2, flops_fwd_img=5397.4e9 + 1.3e9, d_pair=20.9e9),
+    "c2": dict(name="8x_independent_256x256", batch=8, train_flops=6.95e12, fwd_flops=1725.1e9 + 5.0e9 + 5.49e9),
+    "c3": dict(name="8x_guided_256x256", batch=8, train_flops=7.02e12, fwd_flops=1725.1e9 + 20.7e9 + 5.49e9),
+    "c4": dict(name="32x_independent_512x512", batch=2, train_flops=21.72e12, fwd_flops=5397.4e9 + 1.3e9 + 20.9e9),
+    "c5": dict(name="32x_guided_512x512", batch=4, train_flops=22.05e12, fwd_flops=5397.4e9 + 82.6e9 + 20.9e9),
 }
 METRIC = "generator+discriminator images/sec"
+WORKLOAD = ("%s, batch %d per GPU, one full training iteration per step (style encoder + SPADE/SEAN "
+            "generator fwd+bwd, multi-scale discriminator fwd+bwd on [fake|real], hinge + feature-"
+            "matching losses, Adam for G+E and D%s)")
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d["bf16_tflops_sustained"], d["bf16_tflops"], d["hbm_gbs"], "measured"
-    return 1400.0, 1590.0, 6650.0, "fallback"
+        return d["bf16_tflops_sustained"], d["bf16_tflops"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 1400.0, 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler(threading.Thread):
@@ -58,7 +68,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([s.strip() for s in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def result(self):
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
@@ -79,26 +89,31 @@ def build_opt(o):
     return opt
 
 
-def run_reference(args):
-    """The reference's CPU implementation of the path (oracle port: the reference is pure Python
-    over ATen, nothing to compile) on the host cores; each step = a bounded sample (1 image)."""
+def cpu_train_iteration_timer(cfg, threads):
+    """The reference's training iteration on the host cores: the oracle's restatement of
+    trainer_manager.py:32-61 (the reference is pure Python over ATen, so there is nothing to
+    compile; `kind` = "port").  Returns a closure running ONE iteration on a batch of 1."""
     import torch
     from oracle import deepsee_oracle as O
+    torch.set_num_threads(threads)
+    o = O.make_opt(cfg["name"], is_train=True)
+    tr = O.CpuTrainer(o, O.make_generator_state(o, 0), O.make_encoder_state(o, 1),
+                      O.make_discriminator_state(o, 2))
+    d = O.preprocess(o, O.synthetic_batch(o, 1, seed=1234))
+
+    def step():
+        tr.generator_step(d)
+        tr.discriminator_step(d)
+    return step
+
+
+def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = CONFIGS[args.config]
     cores = os.cpu_count()
-    torch.set_num_threads(cores)
-    o = O.make_opt(cfg["name"], is_train=True)
-    sdG, sdE, sdD = O.make_generator_state(o, 0), O.make_encoder_state(o, 1), O.make_discriminator_state(o, 2)
-    d = O.preprocess(o, O.synthetic_batch(o, 1, seed=1234))
-
-    def step():
-        with torch.no_grad():
-            fake, _ = O.inference(sdG, sdE, o, d["image_lr"], d["input_semantics"], d["image_hr"])
-            O.discriminate(sdD, o, d["input_semantics"], fake, d["image_hr"], training=False)
-
+    step = cpu_train_iteration_timer(cfg, cores)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -111,40 +126,40 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC % (cfg["name"], 1), "precision": "fp32 (ATen CPU)"},
+        "config": {"workload": WORKLOAD % (cfg["name"], 1, ""), "precision": "fp32 (ATen CPU)"},
         "cpu_baseline": {"value": v, "unit": "images/sec", "cores": cores, "kind": "port",
-                         "sample": "1 image per step (batch 1), oracle port of the reference forward"},
+                         "sample": "1 image per step (batch 1): one full G+D training iteration of the "
+                                   "oracle port of trainer_manager.py:32-61, torch CPU fp32"},
         "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
-
-
-WORKLOAD_DESC = ("%s, batch %d per GPU: style encoder + SPADE/SEAN generator forward + multi-scale "
-                 "discriminator forward on [fake|real] (inference path; backward not yet native)")
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--passes", type=int, default=None)
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist
     from oracle import deepsee_oracle as O      # synthetic inputs / seeded weights / CPU baseline only
     from deepsee_b200 import _lib, ops, parallel
     from deepsee_b200.config import config
-    from deepsee_b200.managers.base_manager import BaseManager
+    from deepsee_b200.managers.trainer_manager import TrainerManager
 
     if args.passes:
         config.passes = args.passes
+    config.check_onehot = False  # the bench feeds its own one-hot maps; skip the per-forward D2H flag read
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -153,49 +168,57 @@ def main():
     cfg = CONFIGS[args.config]
     b = cfg["batch"]
     o = O.make_opt(cfg["name"], is_train=True)
-    mgr = BaseManager(build_opt(o))
-    model = mgr.sr_model.eval()
+    mgr = TrainerManager(build_opt(o))
+    model = mgr.sr_model
     model.netSR.load_state_dict(O.make_generator_state(o, 0), strict=True)
     model.netE.load_state_dict(O.make_encoder_state(o, 1), strict=True)
     model.netD.load_state_dict(O.make_discriminator_state(o, 2), strict=True)
+    train = args.mode == "train"
+    model.train(train)
 
     raw = O.synthetic_batch(o, b, seed=1234 + rank)
-    host = {"label": raw["label"].float().pin_memory(), "image": raw["image"].pin_memory()}
-    dev = mgr.preprocess({k: v.clone() for k, v in host.items()}, from_dataloader=True)
+    host = {k: (v.float() if "label" in k else v).pin_memory() for k, v in raw.items()}
+    dev = {k: v.cuda() for k, v in host.items()}
     torch.cuda.synchronize()
 
-    def hot_step(data):
+    def iteration(data):
+        if train:
+            mgr.run_generator_one_step(dict(data))
+            mgr.run_discriminator_one_step(dict(data))
+            return mgr.get_latest_losses()
         with torch.no_grad():
-            out = model(dict(data), "inference")
-            pf, pr = model.discriminate(data["input_semantics"], out["fake_image"], data["image_hr"])
-        return out["fake_image"], pf
+            d = mgr.preprocess(dict(data), from_dataloader=True)
+            out = model(d, "inference")
+            pf, _ = model.discriminate(d["input_semantics"], out["fake_image"], d["image_hr"])
+        return {"pred": pf[0][-1].mean()}
 
-    def e2e_step():
-        data = mgr.preprocess({k: v for k, v in host.items()}, from_dataloader=True)
-        fake, pf = hot_step(data)
-        return fake.cpu(), float(pf[0][-1].mean().cpu())
+    def e2e_iteration():
+        losses = iteration(host)
+        return {k: float(v.detach().mean()) for k, v in losses.items()}  # D2H read of the step's result
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # inputs (b x 19 x S x S fp32 one-hot etc.) and every activation exceed L2 (126 MB) at these
-    # sizes, so no explicit flush is needed between iterations.
+    # The raw batch (b x 4 x S x S fp32) plus every activation of the step (several GB) exceed the
+    # 126 MB L2 many times over, so successive iterations cannot hit in L2; no explicit flush.
     for _ in range(args.warmup):
-        hot_step(dev)
+        iteration(dev)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()  # `ncu --profile-from-start off` captures exactly the timed region
     with ops.KernelTimer() as kt:
         e0.record()
         for _ in range(args.steps):
-            hot_step(dev)
+            iteration(dev)
         e1.record()
         barrier()
+    torch.cuda.profiler.stop()
     launches = _lib.launch_count() - n0
     ms = e0.elapsed_time(e1)
     ksum = kt.summary()
@@ -204,20 +227,25 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
 
-    # end to end through the public API with host buffers
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            e2e_iteration()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            last = e2e_iteration()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": b * world * args.steps / e2e_s, "unit": "images/sec",
+               "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())) * (2 if train else 1),
+               "d2h_bytes_per_step": 4 * len(last), "last_losses": last}
     sampler.stop_flag = True
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
     if rank != 0:
         return
 
@@ -225,53 +253,63 @@ def main():
     imgs = b * world * args.steps
     value = imgs / (ms / 1000.0)
     sust, burst, hbm, how = peaks()
-    # dominant kernel family = the tcgen05 implicit-GEMM kernel (K2 conv and K1 modulate share it)
+    # tensor-core launches by family (CUDA events on the launching stream around each launch)
+    fam = {}
+    for tag, (n, t_ms, fl) in ksum.items():
+        f = tag.rsplit("_", 1)[0]
+        a = fam.setdefault(f, [0, 0.0, 0.0])
+        a[0] += n
+        a[1] += t_ms
+        a[2] += fl
     tot_ms = sum(v[1] for v in ksum.values())
     tot_fl = sum(v[2] for v in ksum.values())
     top = max(ksum.items(), key=lambda kv: kv[1][1])
     top_tflops = top[1][2] / (top[1][1] / 1000.0) / 1e12
+    flops_per_img = cfg["train_flops"] if train else cfg["fwd_flops"]
     roofline = {
-        "bound": "tensor", "kernel": "conv3x3_tc_kernel (%s)" % top[0],
+        "bound": "tensor", "kernel": "tcgen05 implicit-GEMM family; dominant launch group: %s" % top[0],
         "achieved": top_tflops, "peak": sust, "unit": "TFLOP/s", "frac": top_tflops / sust,
-        "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json); fp16 operands, same pipe" % how,
+        "peak_source": "%s: bf16 dense sustained; kind::f16 operands run on the same pipe at the same rate" % how,
         "executed_passes": config.passes,
         "executed_frac": top_tflops * config.passes / sust,
-        "all_tc_launches": {"achieved": tot_fl / (tot_ms / 1000.0) / 1e12,
-                            "share_of_step": tot_ms / ms, "launches_per_step": sum(v[0] for v in ksum.values()) / args.steps},
+        "all_tc_launches": {"achieved": tot_fl / (tot_ms / 1000.0) / 1e12, "share_of_step": tot_ms / ms,
+                            "launches_per_step": sum(v[0] for v in ksum.values()) / args.steps},
+        "by_family": {f: {"launches_per_step": a[0] / args.steps, "ms_per_step": a[1] / args.steps,
+                          "tflops": a[2] / (a[1] / 1000.0) / 1e12} for f, a in sorted(fam.items())},
+        "whole_step": {"algorithmic_tflops_per_gpu": value / world * flops_per_img / 1e12,
+                       "frac_of_peak": value / world * flops_per_img / 1e12 / sust},
         "traffic": None,
     }
     line = {
         "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32-class (fp16 split x%d, fp32 accumulate)" % config.passes
-        if config.passes == 3 else "fp16 operands (TF32-class), fp32 accumulate",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": ("fp16 hi+lo split operands x3 passes, fp32 accumulate (fp32-class)" if config.passes == 3
+                  else "fp16 operands, fp32 accumulate (TF32-class: what stock PyTorch/cuDNN runs these convs in)"),
         "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC % (cfg["name"], b), "global_batch": b * world,
-                   "image": "%dx%d" % (S, S), "parallelism": "dp%d" % world,
-                   "l2": "inputs and activations larger than L2, no flush", "passes": config.passes},
+        "config": {"workload": WORKLOAD % (cfg["name"], b, ", NCCL all-reduce of G+E and D gradients" if world > 1 else "")
+                   if train else "%s, batch %d per GPU, inference forward (encoder + generator + discriminator)" % (cfg["name"], b),
+                   "global_batch": b * world, "image": "%dx%d" % (S, S), "parallelism": "dp%d" % world,
+                   "l2": "inputs and activations larger than L2, no flush", "passes": config.passes,
+                   "mode": args.mode},
         "gpu_launches": launches,
         "clocks": sampler.result(),
-        "e2e": {"value": imgs / e2e_s, "unit": "images/sec",
-                "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())),
-                "d2h_bytes_per_step": int(b * 3 * S * S * 4 + 4)},
+        "e2e": e2e,
         "roofline": roofline,
+        "peak_mem_gib": round(peak_mem, 2),
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and train:
         cores = os.cpu_count()
-        torch.set_num_threads(cores)
-        sdG, sdE, sdD = O.make_generator_state(o, 0), O.make_encoder_state(o, 1), O.make_discriminator_state(o, 2)
-        d1 = O.preprocess(o, O.synthetic_batch(o, 1, seed=1234))
-        n = 0
+        step = cpu_train_iteration_timer(cfg, cores)
         t0 = time.perf_counter()
-        while n < 2 or (time.perf_counter() - t0 < 12 and n < 6):
-            with torch.no_grad():
-                fk, _ = O.inference(sdG, sdE, o, d1["image_lr"], d1["input_semantics"], d1["image_hr"])
-                O.discriminate(sdD, o, d1["input_semantics"], fk, d1["image_hr"], training=False)
+        n = 0
+        while n < 1 or (time.perf_counter() - t0 < 12 and n < 4):
+            step()
             n += 1
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": n / dt, "unit": "images/sec", "cores": cores, "kind": "port",
-                                "sample": "%d images, batch 1, same workload (oracle port of the "
-                                          "reference forward, torch CPU fp32)" % n}
+                                "sample": "%d training iteration(s) at batch 1 of the same workload "
+                                          "(oracle port of trainer_manager.py:32-61, torch CPU fp32)" % n}
     print(json.dumps(line))
 
 

@@ -83,6 +83,18 @@ def test_generator_eval_full_width_vs_oracle():
     err = (out.cpu() - ref).abs().max().item()
     print("full width 3-pass max-abs vs oracle:", err, "ref std", ref.std().item())
     assert err < 2e-4
+    from deepsee_b200.config import config
+    old = config.passes
+    config.passes = 1
+    try:
+        with torch.no_grad():
+            out1 = G(d["image_lr"].cuda(), seg=d["input_semantics"].cuda(), z=z.cuda())
+    finally:
+        config.passes = old
+    e1 = (out1.cpu() - ref).abs()
+    print("full width 1-pass (fp16 operands, TF32-class) max-abs vs oracle: %.3e, mean-abs %.3e"
+          % (e1.max().item(), e1.mean().item()))
+    assert e1.max().item() < 1e-2
 
 
 def test_generator_rejects_non_onehot():
