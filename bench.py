@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--torch-profile", default=None,
+                    help="write a torch.profiler (CUPTI) kernel table of 2 extra steps to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -227,6 +229,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
 
+    if args.torch_profile and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            t0 = time.perf_counter()
+            for _ in range(2):
+                iteration(dev)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+        with open(args.torch_profile, "w") as f:
+            f.write("2 steps under the profiler: %.1f ms wall\n" % (wall * 1000))
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=70,
+                                              max_name_column_width=70))
     e2e = None
     if not args.no_e2e:
         for _ in range(2):

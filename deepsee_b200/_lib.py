@@ -15,7 +15,8 @@ SYMBOLS = [
     "dsee_version", "dsee_last_error", "dsee_launch_count",
     "dsee_onehot_from_labels", "dsee_labels_from_onehot", "dsee_resize_labels",
     "dsee_shared_mlp_fwd", "dsee_style_gather_fwd",
-    "dsee_prep_conv_weight", "dsee_split_f16",
+    "dsee_prep_conv_weight", "dsee_split_f16", "dsee_prep_conv_weight_ex", "dsee_split_f16_ups2",
+    "dsee_fold2x2", "dsee_conv2d_tc", "dsee_conv2d_tc_wgrad_workspace_floats", "dsee_conv2d_tc_wgrad",
     "dsee_conv3x3_fwd", "dsee_conv3x3_stats_tiles", "dsee_spade_modulate_fwd",
     "dsee_spade_modulate_bwd", "dsee_grad_prep_blocks", "dsee_grad_prep", "dsee_reduce_partials",
     "dsee_conv3x3_wgrad_workspace_floats", "dsee_conv3x3_wgrad", "dsee_bn_bwd_blocks", "dsee_bn_bwd",
@@ -46,7 +47,7 @@ class ConvEpilogue(C.Structure):
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("res_ups", C.c_int),
         ("noise", C.c_void_p * 2), ("noise_w", C.c_void_p * 2),
         ("out", C.c_void_p), ("stats_partial", C.c_void_p), ("act_mask", C.c_void_p),
-        ("amax_out", C.c_void_p),
+        ("amax_out", C.c_void_p), ("lrelu", C.c_int),
     ]
 
 
@@ -58,6 +59,17 @@ class ModulateArgs(C.Structure):
         ("gamma_bias", C.c_void_p), ("beta_bias", C.c_void_p),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
         ("C", C.c_int),
+    ]
+
+
+class Conv2dTCArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("Hi", C.c_int), ("Wi", C.c_int),
+        ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("Ci", C.c_int), ("a_inv_scale", C.c_void_p),
+        ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
+        ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("w_inv_scale", C.c_void_p),
+        ("n_total", C.c_int), ("passes", C.c_int), ("transposed", C.c_int),
+        ("Ho", C.c_int), ("Wo", C.c_int),
     ]
 
 
@@ -99,6 +111,11 @@ def load():
         "dsee_style_gather_fwd": [vp, vp, vp, vp, i, i, i, i, i, vp],
         "dsee_prep_conv_weight": [vp, vp, vp, vp, i, i, i, vp],
         "dsee_split_f16": [vp, vp, vp, i64, vp],
+        "dsee_prep_conv_weight_ex": [vp, vp, vp, vp, i, i, i, i, i, vp],
+        "dsee_split_f16_ups2": [vp, vp, vp, i, i, i, i, vp],
+        "dsee_fold2x2": [vp, vp, i, i, i, i, vp],
+        "dsee_conv2d_tc": [C.POINTER(Conv2dTCArgs), C.POINTER(ConvEpilogue), vp],
+        "dsee_conv2d_tc_wgrad": [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, i, i, vp, vp, vp],
         "dsee_conv3x3_fwd": [C.POINTER(ConvOperands), C.POINTER(ConvEpilogue), vp],
         "dsee_conv3x3_stats_tiles": [i, i, i],
         "dsee_spade_modulate_fwd": [C.POINTER(ConvOperands), C.POINTER(ModulateArgs), vp],
@@ -144,6 +161,8 @@ def load():
         fn.restype = C.c_int
     lib.dsee_conv3x3_wgrad_workspace_floats.argtypes = [i, i, i, i, i]
     lib.dsee_conv3x3_wgrad_workspace_floats.restype = C.c_int64
+    lib.dsee_conv2d_tc_wgrad_workspace_floats.argtypes = [i, i, i, i, i, i, i]
+    lib.dsee_conv2d_tc_wgrad_workspace_floats.restype = C.c_int64
     lib.dsee_conv2d_direct_wgrad_workspace_floats.argtypes = [i, i, i, i, i, i, i]
     lib.dsee_conv2d_direct_wgrad_workspace_floats.restype = C.c_int64
     if lib.dsee_version() != ABI_VERSION:

@@ -45,8 +45,11 @@ int require_sm100();
 
 // Encodes a tiled tensor map (rank <= 5) for a 16-bit element tensor with 128B swizzle.
 // dims/strides innermost-first; strides[0] is implied (= 2 bytes).
+// elem_strides (optional, per dimension): traversal stride; the box then lands
+// ceil(box[i] / elem_strides[i]) elements of dimension i in shared memory.
 int encode_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, bool bf16);
+                    const uint64_t* strides_bytes, const uint32_t* box, bool bf16,
+                    const uint32_t* elem_strides = nullptr);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------

@@ -41,13 +41,21 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
+constexpr int MAX_TAPS = 16;
 
 enum { EPI_CONV = 0, EPI_MODULATE = 1, EPI_MODULATE_BWD = 2 };
 
 struct alignas(64) ConvParams {
     CUtensorMap tmA[4];  // [source*2 + plane]
     CUtensorMap tmB[2];  // [plane]
-    int B, H, W;
+    int B, H, W;       // tile space: the output pixels this launch computes, per image
+    int Hm, Wm;        // output tensor dims in memory; pixel (y,x) of the tile space lives at
+    int o_step, o_offy, o_offx;  //   (y*o_step + o_offy, x*o_step + o_offx)
+    int ntaps, a_step; // filter taps; A box origin = tile origin * a_step + tap offset
+    int8_t tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
+    int tap_k[MAX_TAPS];  // K offset of the tap's weight block
+    int b_rows;        // weight rows per TMA box (= MMA N)
+    int lrelu;         // EPI_CONV: fuse LeakyReLU(0.2) after the bias
     int tiles_w, tiles_h, n_tiles, num_tiles;
     int cb0, cb_total;  // 64-channel blocks in source 0 / in total
     int passes;
@@ -174,8 +182,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int k_iters = p.passes * 9 * p.cb_total;
-    const int cin_total = p.cb_total * BLOCK_K;
+    const int k_iters = p.passes * p.ntaps * p.cb_total;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -188,21 +195,20 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                 for (int pass = 0; pass < p.passes; ++pass) {
                     const int pa = (pass == 1) ? 1 : 0;
                     const int pb = (pass == 2) ? 1 : 0;
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
                         for (int cb = 0; cb < p.cb_total; ++cb, ++it) {
                             const int s = it % STAGES;
                             const uint32_t ph = (it / STAGES) & 1;
                             mbar_wait(&empty_bar[s], ph ^ 1);
-                            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                            mbar_expect_tx(&full_bar[s], A_BYTES + p.b_rows * BLOCK_K * 2);
                             uint8_t* sa = smem + s * STAGE_BYTES;
                             uint8_t* sb = sa + A_BYTES;
                             const int src = (cb >= p.cb0) ? 1 : 0;
                             const int cl = src ? cb - p.cb0 : cb;
                             tma_load_4d(&p.tmA[src * 2 + pa], &full_bar[s], sa, cl * BLOCK_K,
-                                        w0 + dx, h0 + dy, b);
-                            tma_load_2d(&p.tmB[pb], &full_bar[s], sb, tap * cin_total + cb * BLOCK_K,
-                                        n0);
+                                        w0 * p.a_step + dx, h0 * p.a_step + dy, b);
+                            tma_load_2d(&p.tmB[pb], &full_bar[s], sb, p.tap_k[tap] + cb * BLOCK_K, n0);
                         }
                     }
                 }
@@ -258,7 +264,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
 
             if (EPI == EPI_CONV) {
                 const int n0 = nt * BLOCK_N;
-                const size_t pix = ((size_t)b * p.H + y) * p.W + x;
+                const size_t pix = ((size_t)b * p.Hm + (y * p.o_step + p.o_offy)) * p.Wm +
+                                   (x * p.o_step + p.o_offx);
                 float* orow = p.out + pix * p.n_total;
                 const float* rrow = nullptr;
                 if (p.residual) {
@@ -277,6 +284,10 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         o[j] = __uint_as_float(v[j]) * inv_scale + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+                    if (p.lrelu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[j] = o[j] > 0.f ? o[j] : 0.2f * o[j];
+                    }
                     if (valid && p.act_mask) {
                         const uint4* mrow = reinterpret_cast<const uint4*>(p.act_mask + pix * p.n_total + n);
 #pragma unroll
@@ -523,6 +534,17 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops) {
     p.B = ops->B;
     p.H = ops->H;
     p.W = ops->W;
+    p.Hm = ops->H;
+    p.Wm = ops->W;
+    p.o_step = 1;
+    p.a_step = 1;
+    p.ntaps = 9;
+    for (int t = 0; t < 9; ++t) {
+        p.tap_dy[t] = (int8_t)(t / 3 - 1);
+        p.tap_dx[t] = (int8_t)(t % 3 - 1);
+        p.tap_k[t] = t * (ops->a_channels[0] + ops->a_channels[1]);
+    }
+    p.b_rows = BLOCK_N;
     p.tiles_w = (ops->W + TILE_W - 1) / TILE_W;
     p.tiles_h = (ops->H + TILE_H - 1) / TILE_H;
     p.n_tiles = (ops->n_total + BLOCK_N - 1) / BLOCK_N;
@@ -624,9 +646,124 @@ extern "C" int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_e
     p.out = epi->out;
     p.stats_partial = epi->stats_partial;
     p.act_mask = (const __half*)epi->act_mask;
+    p.lrelu = epi->lrelu;
     p.amax_out = epi->amax_out;
     if (p.amax_out) DSEE_CUDA(cudaMemsetAsync(p.amax_out, 0, sizeof(float), (cudaStream_t)stream));
     return launch<EPI_CONV>(p, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// general KH x KW / strided convolution and its backward-data on the same kernel (EPI_CONV)
+// ------------------------------------------------------------------------------------------------
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+extern "C" int dsee_conv2d_tc(const dsee_conv2d_tc_args* a, const dsee_conv_epilogue* epi, void* stream) {
+    DSEE_CHECK_ARG(a && epi && epi->out, "NULL argument");
+    DSEE_CHECK_ARG(a->B > 0 && a->Hi > 0 && a->Wi > 0 && a->Ho > 0 && a->Wo > 0, "bad geometry");
+    DSEE_CHECK_ARG(a->Ci > 0 && a->Ci % 8 == 0, "A channels must be a multiple of 8 (got %d)", a->Ci);
+    DSEE_CHECK_ARG(a->KH > 0 && a->KW > 0 && a->KH * a->KW <= MAX_TAPS, "at most %d filter taps", MAX_TAPS);
+    DSEE_CHECK_ARG(a->stride == 1 || a->stride == 2, "stride must be 1 or 2");
+    DSEE_CHECK_ARG(a->passes == 1 || (a->passes == 3 && a->a_lo && a->w_lo), "passes must be 1, or 3 with lo planes");
+    DSEE_CHECK_ARG(a->a_hi && a->w_hi && a->w_inv_scale, "NULL operand pointer");
+    DSEE_CHECK_ARG(a->n_total > 0 && a->n_total % 32 == 0, "n_total must be a multiple of 32");
+    DSEE_CHECK_ARG(!epi->residual && !epi->noise[0] && !epi->noise[1] && !epi->stats_partial &&
+                       (!epi->act_mask || a->stride == 1),
+                   "epilogue option not supported by the general conv");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int T = a->KH * a->KW;
+    const int cpad = round_up(a->Ci, BLOCK_K);  // K block per tap in the prepared weight
+    ConvParams base;
+    memset(&base, 0, sizeof(base));
+    base.B = a->B;
+    base.Hm = a->Ho;
+    base.Wm = a->Wo;
+    base.cb0 = base.cb_total = cpad / BLOCK_K;
+    base.passes = a->passes;
+    base.n_total = a->n_total;
+    base.w_inv_scale = a->w_inv_scale;
+    base.a_inv_scale = a->a_inv_scale;
+    base.b_rows = round_up(a->n_total < BLOCK_N ? a->n_total : BLOCK_N, 16);
+    base.idesc = (1u << 4) | ((uint32_t)(base.b_rows >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    base.n_tiles = (a->n_total + BLOCK_N - 1) / BLOCK_N;
+    base.bias = epi->bias;
+    base.out = epi->out;
+    base.lrelu = epi->lrelu;
+    base.act_mask = (const __half*)epi->act_mask;
+    base.amax_out = epi->amax_out;
+    if (base.amax_out) DSEE_CUDA(cudaMemsetAsync(base.amax_out, 0, sizeof(float), (cudaStream_t)stream));
+    const int a_step = a->transposed ? 1 : a->stride;
+    for (int pl = 0; pl < 2; ++pl) {
+        const void* ab = pl ? a->a_lo : a->a_hi;
+        if (ab) {
+            uint64_t dims[4] = {(uint64_t)a->Ci, (uint64_t)a->Wi, (uint64_t)a->Hi, (uint64_t)a->B};
+            uint64_t strides[3] = {(uint64_t)a->Ci * 2, (uint64_t)a->Wi * a->Ci * 2,
+                                   (uint64_t)a->Hi * a->Wi * a->Ci * 2};
+            uint32_t box[4] = {BLOCK_K, (uint32_t)(TILE_W * a_step), (uint32_t)(TILE_H * a_step), 1};
+            uint32_t es[4] = {1, (uint32_t)a_step, (uint32_t)a_step, 1};
+            rc = encode_tmap_16b(&base.tmA[pl], ab, 4, dims, strides, box, false, es);
+            if (rc) return rc;
+        } else {
+            base.tmA[pl] = base.tmA[0];
+        }
+        base.tmA[2 + pl] = base.tmA[pl];
+        const void* wb = pl ? a->w_lo : a->w_hi;
+        if (wb) {
+            const uint64_t Ktot = (uint64_t)T * cpad;
+            uint64_t dims[2] = {Ktot, (uint64_t)a->n_total};
+            uint64_t strides[1] = {Ktot * 2};
+            uint32_t box[2] = {BLOCK_K, (uint32_t)base.b_rows};
+            rc = encode_tmap_16b(&base.tmB[pl], wb, 2, dims, strides, box, false);
+            if (rc) return rc;
+        } else {
+            base.tmB[pl] = base.tmB[0];
+        }
+    }
+    const int classes = a->transposed ? a->stride : 1;
+    for (int py = 0; py < classes; ++py)
+        for (int px = 0; px < classes; ++px) {
+            ConvParams p = base;
+            int nt = 0;
+            for (int ky = 0; ky < a->KH; ++ky)
+                for (int kx = 0; kx < a->KW; ++kx) {
+                    int dy, dx;
+                    if (!a->transposed) {
+                        dy = ky - a->pad;
+                        dx = kx - a->pad;
+                    } else {
+                        // dX[y] = sum_ky dY[(y + pad - ky) / stride] * w[ky] over exact divisions
+                        const int ty = py + a->pad - ky, tx = px + a->pad - kx;
+                        if (ty % a->stride != 0 || tx % a->stride != 0) continue;
+                        dy = ty / a->stride;
+                        dx = tx / a->stride;
+                    }
+                    p.tap_dy[nt] = (int8_t)dy;
+                    p.tap_dx[nt] = (int8_t)dx;
+                    p.tap_k[nt] = (ky * a->KW + kx) * cpad;
+                    ++nt;
+                }
+            p.ntaps = nt;
+            p.a_step = a_step;
+            if (a->transposed) {
+                p.H = (a->Ho - py + a->stride - 1) / a->stride;
+                p.W = (a->Wo - px + a->stride - 1) / a->stride;
+                p.o_step = a->stride;
+                p.o_offy = py;
+                p.o_offx = px;
+            } else {
+                p.H = a->Ho;
+                p.W = a->Wo;
+                p.o_step = 1;
+            }
+            if (p.H <= 0 || p.W <= 0) continue;
+            DSEE_CHECK_ARG(nt > 0, "a parity class of the transposed conv has no taps (kernel < stride)");
+            p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
+            p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
+            p.num_tiles = p.B * p.tiles_h * p.tiles_w * p.n_tiles;
+            rc = launch<EPI_CONV>(p, (cudaStream_t)stream);
+            if (rc) return rc;
+        }
+    return 0;
 }
 
 extern "C" int dsee_spade_modulate_fwd(const dsee_conv_operands* ops, const dsee_modulate_args* mod,

@@ -79,7 +79,8 @@ static EncodeTiledFn get_encode() {
 }
 
 int encode_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, bool bf16) {
+                    const uint64_t* strides_bytes, const uint32_t* box, bool bf16,
+                    const uint32_t* elem_strides) {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -94,7 +95,7 @@ int encode_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t
     for (int i = 0; i < rank; ++i) {
         d[i] = dims[i];
         b[i] = box[i];
-        es[i] = 1;
+        es[i] = elem_strides ? elem_strides[i] : 1;
     }
     for (int i = 0; i < rank - 1; ++i) {
         s[i] = strides_bytes[i];

@@ -172,6 +172,30 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, __half* __restri
     if (out_lo) out_lo[o] = l;
 }
 
+__global__ void prep_weight_ex_kernel(const float* __restrict__ w, __half* __restrict__ out_hi,
+                                      __half* __restrict__ out_lo, float* inv_scale, int N, int C,
+                                      int T, int transpose) {
+    // normal:    out[n][tap][c (padded to Cp)];   transpose: out[c][tap][n (padded to Np)]
+    const float scale = pow2_scale_for(inv_scale[1], 14);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) inv_scale[0] = 1.f / scale;
+    const int rows = transpose ? C : N, cols = transpose ? N : C;
+    const int cp = (cols + 63) / 64 * 64;
+    if (i >= (int64_t)rows * T * cp) return;
+    const int cc = (int)(i % cp);
+    const int tap = (int)((i / cp) % T);
+    const int r = (int)(i / ((int64_t)T * cp));
+    float v = 0.f;
+    if (cc < cols) {
+        const int n = transpose ? cc : r, c = transpose ? r : cc;
+        v = w[((size_t)n * C + c) * T + tap] * scale;
+    }
+    __half h, l;
+    split_f16(v, h, l);
+    out_hi[i] = h;
+    if (out_lo) out_lo[i] = l;
+}
+
 __global__ void split_kernel(const float* __restrict__ in, __half* __restrict__ hi,
                              __half* __restrict__ lo, int64_t n4) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,6 +207,56 @@ __global__ void split_kernel(const float* __restrict__ in, __half* __restrict__ 
     for (int e = 0; e < 4; ++e) split_f16(a[e], h[e], l[e]);
     reinterpret_cast<uint2*>(hi)[i] = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
     if (lo) reinterpret_cast<uint2*>(lo)[i] = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
+}
+
+// fp32 NHWC [B,H,W,C] -> fp16 planes [B,2H,2W,C] (nearest 2x upsample materialised for the
+// encoder's up_conv / conv2 input, encoder.py:94-95,153-154)
+__global__ void split_ups_kernel(const float* __restrict__ in, __half* __restrict__ hi,
+                                 __half* __restrict__ lo, int B, int H, int W, int C4) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * H * W * C4) return;
+    const int g = (int)(i % C4);
+    int64_t r = i / C4;
+    const int x = (int)(r % W);
+    r /= W;
+    const int y = (int)(r % H);
+    const int b = (int)(r / H);
+    float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    float a[4] = {v.x, v.y, v.z, v.w};
+    __half h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_f16(a[e], h[e], l[e]);
+    const uint2 ph = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+    const uint2 pl = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
+#pragma unroll
+    for (int s2 = 0; s2 < 4; ++s2) {
+        const size_t o = (((size_t)b * 2 * H + 2 * y + (s2 >> 1)) * 2 * W + 2 * x + (s2 & 1)) * C4 + g;
+        reinterpret_cast<uint2*>(hi)[o] = ph;
+        if (lo) reinterpret_cast<uint2*>(lo)[o] = pl;
+    }
+}
+
+// dY [B,2Ho,2Wo,C] -> [B,Ho,Wo,C] summing 2x2 (transpose of the nearest upsample)
+__global__ void fold2x2_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int Ho,
+                               int Wo, int C4) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * Ho * Wo * C4) return;
+    const int g = (int)(i % C4);
+    int64_t r = i / C4;
+    const int xo = (int)(r % Wo);
+    r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    const int W = Wo * 2, H = Ho * 2;
+    const float4* base = reinterpret_cast<const float4*>(in);
+    float4 a = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int s2 = 0; s2 < 4; ++s2) {
+        const size_t fp = ((size_t)b * H + yo * 2 + (s2 >> 1)) * W + xo * 2 + (s2 & 1);
+        const float4 v = __ldg(base + fp * C4 + g);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = a;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -487,12 +561,52 @@ extern "C" int dsee_prep_conv_weight(const float* w, void* out_hi, void* out_lo,
     LAUNCH_END();
 }
 
+extern "C" int dsee_prep_conv_weight_ex(const float* w, void* out_hi, void* out_lo, float* inv_scale,
+                                        int N, int C, int KH, int KW, int transpose, void* stream) {
+    DSEE_CHECK_ARG(w && out_hi && inv_scale && N > 0 && C > 0 && KH > 0 && KW > 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = KH * KW;
+    const int64_t n = (int64_t)N * C * T;
+    DSEE_CUDA(cudaMemsetAsync(inv_scale, 0, 2 * sizeof(float), st));
+    int blocks = cdiv(n, 256 * 8);
+    if (blocks > 1024) blocks = 1024;
+    amax_kernel<<<blocks, 256, 0, st>>>(w, n, inv_scale + 1);
+    count_launch();
+    const int rows = transpose ? C : N, cols = transpose ? N : C;
+    const int64_t total = (int64_t)rows * T * ((cols + 63) / 64 * 64);
+    prep_weight_ex_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, (__half*)out_hi, (__half*)out_lo,
+                                                            inv_scale, N, C, T, transpose);
+    LAUNCH_END();
+}
+
 extern "C" int dsee_split_f16(const float* in, void* out_hi, void* out_lo, int64_t n, void* stream) {
     DSEE_CHECK_ARG(in && out_hi && n > 0 && n % 4 == 0, "bad argument (n must be a multiple of 4)");
     int rc = require_sm100();
     if (rc) return rc;
     split_kernel<<<cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(in, (__half*)out_hi,
                                                                      (__half*)out_lo, n / 4);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_split_f16_ups2(const float* in, void* out_hi, void* out_lo, int B, int H, int W,
+                                   int C, void* stream) {
+    DSEE_CHECK_ARG(in && out_hi && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int64_t n = (int64_t)B * H * W * (C / 4);
+    split_ups_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(in, (__half*)out_hi, (__half*)out_lo,
+                                                                     B, H, W, C / 4);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_fold2x2(const float* in, float* out, int B, int Ho, int Wo, int C, void* stream) {
+    DSEE_CHECK_ARG(in && out && B > 0 && Ho > 0 && Wo > 0 && C % 4 == 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
+    fold2x2_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, Ho, Wo, C / 4);
     LAUNCH_END();
 }
 

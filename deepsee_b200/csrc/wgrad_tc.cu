@@ -40,6 +40,8 @@ struct alignas(64) WgradParams {
     int B, H, W;
     int tiles_w, tiles_h, ptiles;  // pixel tiles
     int n_total, c_total;
+    int ntaps, a_step;           // filter taps; A box origin = dY tile origin * a_step + tap offset
+    int8_t tap_dy[16], tap_dx[16];
     int n_tiles, c_tiles, splits, num_units;
     int n_cols;  // activation channels per unit (<= 256)
     int passes;
@@ -63,8 +65,8 @@ __device__ __forceinline__ void wg_decode(const WgradParams& p, int unit, int& n
                                           int& split) {
     ct = unit % p.c_tiles;
     unit /= p.c_tiles;
-    tap = unit % 9;
-    unit /= 9;
+    tap = unit % p.ntaps;
+    unit /= p.ntaps;
     nt = unit % p.n_tiles;
     split = unit / p.n_tiles;
 }
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
                 int nt, tap, ct, split;
                 wg_decode(p, unit, nt, tap, ct, split);
-                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
                 const int pt0 = (int)((int64_t)p.ptiles * split / p.splits);
                 const int pt1 = (int)((int64_t)p.ptiles * (split + 1) / p.splits);
                 for (int pt = pt0; pt < pt1; ++pt) {
@@ -134,7 +136,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                                         nt * WG_M + i * 64, w0, h0, b);
                         for (int i = 0; i < nboxA; ++i)
                             tma_load_4d(&p.tmA[pa], &full_bar[s], sa + i * WG_BOX_BYTES,
-                                        ct * WG_NMAX + i * 64, w0 + dx, h0 + dy, b);
+                                        ct * WG_NMAX + i * 64, w0 * p.a_step + dx, h0 * p.a_step + dy,
+                                        b);
                     }
                 }
             }
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * WG_NMAX;
             const int n = nt * WG_M + m;
-            float* orow = p.partial + (((size_t)split * p.n_total + n) * 9 + tap) * p.c_total +
+            float* orow = p.partial + (((size_t)split * p.n_total + n) * p.ntaps + tap) * p.c_total +
                           (size_t)ct * WG_NMAX;
 #pragma unroll 1
             for (int ch = 0; ch < p.n_cols / 32; ++ch) {
@@ -226,17 +229,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
 // out[i] = sum_s partial[s][i] (fixed order), optionally transposing [n][9][c] -> [n][c][9]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
-                                    int splits, int n_total, int c_total, int to_nc9) {
-    const int64_t total = (int64_t)n_total * 9 * c_total;
+                                    int splits, int n_total, int c_total, int to_nc9, int T) {
+    const int64_t total = (int64_t)n_total * T * c_total;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     float a = 0.f;
     for (int s = 0; s < splits; ++s) a += partial[(size_t)s * total + i];
     if (to_nc9) {
         const int c = (int)(i % c_total);
-        const int tap = (int)((i / c_total) % 9);
-        const int n = (int)(i / ((int64_t)9 * c_total));
-        out[((size_t)n * c_total + c) * 9 + tap] = a;
+        const int tap = (int)((i / c_total) % T);
+        const int n = (int)(i / ((int64_t)T * c_total));
+        out[((size_t)n * c_total + c) * T + tap] = a;
     } else {
         out[i] = a;
     }
@@ -246,11 +249,11 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 
 using namespace dsee;
 
-static int wgrad_plan(int B, int H, int W, int n_total, int c_total, int* splits_out) {
+static int wgrad_plan(int B, int H, int W, int n_total, int c_total, int* splits_out, int T = 9) {
     const int ptiles = B * ((H + WG_TH - 1) / WG_TH) * ((W + WG_TW - 1) / WG_TW);
     const int n_tiles = (n_total + WG_M - 1) / WG_M;
     const int c_tiles = (c_total + WG_NMAX - 1) / WG_NMAX;
-    const int base = n_tiles * 9 * c_tiles;
+    const int base = n_tiles * T * c_tiles;
     int splits = (2 * 148 + base - 1) / base;  // ~2 units per SM
     if (splits > ptiles) splits = ptiles;
     if (splits < 1) splits = 1;
@@ -265,18 +268,14 @@ extern "C" int64_t dsee_conv3x3_wgrad_workspace_floats(int B, int H, int W, int 
     return (int64_t)splits * n_total * 9 * c_total;
 }
 
-extern "C" int dsee_conv3x3_wgrad(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale,
-                                  const void* a_hi, const void* a_lo, const float* a_inv_scale,
-                                  int dtype, int B, int H, int W, int n_total, int c_total, int passes,
-                                  float* workspace, float* dw, int layout_nc9, void* stream) {
-    const int dy_dtype = dtype, a_dtype = dtype;
-    DSEE_CHECK_ARG(dy_hi && a_hi && workspace && dw, "NULL pointer");
-    DSEE_CHECK_ARG(B > 0 && H > 0 && W > 0, "bad geometry");
-    DSEE_CHECK_ARG(n_total % 128 == 0, "n_total must be a multiple of 128 (got %d)", n_total);
-    DSEE_CHECK_ARG(c_total == 64 || c_total == 128 || c_total % 256 == 0,
-                   "c_total must be 64, 128 or a multiple of 256 (got %d)", c_total);
-    DSEE_CHECK_ARG(passes == 1 || (passes == 3 && dy_lo && a_lo), "passes must be 1, or 3 with lo planes");
-    DSEE_CHECK_ARG(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale, const void* a_hi,
+                      const void* a_lo, const float* a_inv_scale, int dtype, int B, int H, int W,
+                      int Hi, int Wi, int n_total, int a_channels, int c_total, int KH, int KW,
+                      int stride, int pad, int passes, float* workspace, float* dw, int layout_nc9,
+                      void* stream) {
+    // H, W: dY (= forward output) size; Hi, Wi: activation (= forward input) size;
+    // a_channels: channels stored in the activation planes, c_total: dW columns (a multiple of 64)
+    const int T = KH * KW;
     int rc = require_sm100();
     if (rc) return rc;
     WgradParams p;
@@ -288,34 +287,43 @@ extern "C" int dsee_conv3x3_wgrad(const void* dy_hi, const void* dy_lo, const fl
     p.tiles_h = (H + WG_TH - 1) / WG_TH;
     p.n_total = n_total;
     p.c_total = c_total;
-    p.n_tiles = n_total / WG_M;
+    p.ntaps = T;
+    p.a_step = stride;
+    for (int t = 0; t < T; ++t) {
+        p.tap_dy[t] = (int8_t)(t / KW - pad);
+        p.tap_dx[t] = (int8_t)(t % KW - pad);
+    }
+    p.n_tiles = (n_total + WG_M - 1) / WG_M;
     p.c_tiles = (c_total + WG_NMAX - 1) / WG_NMAX;
     p.n_cols = c_total < WG_NMAX ? c_total : WG_NMAX;
-    p.ptiles = wgrad_plan(B, H, W, n_total, c_total, &p.splits);
-    p.num_units = p.n_tiles * 9 * p.c_tiles * p.splits;
+    p.ptiles = wgrad_plan(B, H, W, n_total, c_total, &p.splits, T);
+    p.num_units = p.n_tiles * T * p.c_tiles * p.splits;
     p.passes = passes;
     p.partial = workspace;
     p.inv_scale[0] = dy_inv_scale;
     p.inv_scale[1] = a_inv_scale;
     // kind::f16, fp32 accumulate, both operands MN-major, M = 128, N = n_cols
-    p.idesc = (1u << 4) | ((uint32_t)dy_dtype << 7) | ((uint32_t)a_dtype << 10) | (1u << 15) |
-              (1u << 16) | ((uint32_t)(p.n_cols >> 3) << 17) | ((uint32_t)(WG_M >> 4) << 24);
-    uint32_t box[4] = {64, WG_TW, WG_TH, 1};
+    p.idesc = (1u << 4) | ((uint32_t)dtype << 7) | ((uint32_t)dtype << 10) | (1u << 15) | (1u << 16) |
+              ((uint32_t)(p.n_cols >> 3) << 17) | ((uint32_t)(WG_M >> 4) << 24);
+    uint32_t boxd[4] = {64, WG_TW, WG_TH, 1};
+    uint32_t boxa[4] = {64, (uint32_t)(WG_TW * stride), (uint32_t)(WG_TH * stride), 1};
+    uint32_t esa[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     for (int pl = 0; pl < 2; ++pl) {
         const void* d = pl ? dy_lo : dy_hi;
         const void* a = pl ? a_lo : a_hi;
         if (d) {
             uint64_t dims[4] = {(uint64_t)n_total, (uint64_t)W, (uint64_t)H, (uint64_t)B};
             uint64_t st[3] = {(uint64_t)n_total * 2, (uint64_t)W * n_total * 2, (uint64_t)H * W * n_total * 2};
-            rc = encode_tmap_16b(&p.tmD[pl], d, 4, dims, st, box, dy_dtype == 1);
+            rc = encode_tmap_16b(&p.tmD[pl], d, 4, dims, st, boxd, dtype == 1);
             if (rc) return rc;
         } else {
             p.tmD[pl] = p.tmD[0];
         }
         if (a) {
-            uint64_t dims[4] = {(uint64_t)c_total, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-            uint64_t st[3] = {(uint64_t)c_total * 2, (uint64_t)W * c_total * 2, (uint64_t)H * W * c_total * 2};
-            rc = encode_tmap_16b(&p.tmA[pl], a, 4, dims, st, box, a_dtype == 1);
+            uint64_t dims[4] = {(uint64_t)a_channels, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
+            uint64_t st[3] = {(uint64_t)a_channels * 2, (uint64_t)Wi * a_channels * 2,
+                              (uint64_t)Hi * Wi * a_channels * 2};
+            rc = encode_tmap_16b(&p.tmA[pl], a, 4, dims, st, boxa, dtype == 1, esa);
             if (rc) return rc;
         } else {
             p.tmA[pl] = p.tmA[0];
@@ -336,10 +344,50 @@ extern "C" int dsee_conv3x3_wgrad(const void* dy_hi, const void* dy_lo, const fl
     wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM, st>>>(p);
     count_launch();
     DSEE_CUDA(cudaGetLastError());
-    const int64_t total = (int64_t)n_total * 9 * c_total;
+    const int64_t total = (int64_t)n_total * T * c_total;
     wgrad_reduce_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(workspace, dw, p.splits, n_total,
-                                                                    c_total, layout_nc9);
+                                                                    c_total, layout_nc9, T);
     count_launch();
     DSEE_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int dsee_conv3x3_wgrad(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale,
+                                  const void* a_hi, const void* a_lo, const float* a_inv_scale,
+                                  int dtype, int B, int H, int W, int n_total, int c_total, int passes,
+                                  float* workspace, float* dw, int layout_nc9, void* stream) {
+    DSEE_CHECK_ARG(dy_hi && a_hi && workspace && dw, "NULL pointer");
+    DSEE_CHECK_ARG(B > 0 && H > 0 && W > 0, "bad geometry");
+    DSEE_CHECK_ARG(n_total % 128 == 0, "n_total must be a multiple of 128 (got %d)", n_total);
+    DSEE_CHECK_ARG(c_total == 64 || c_total == 128 || c_total % 256 == 0,
+                   "c_total must be 64, 128 or a multiple of 256 (got %d)", c_total);
+    DSEE_CHECK_ARG(passes == 1 || (passes == 3 && dy_lo && a_lo), "passes must be 1, or 3 with lo planes");
+    DSEE_CHECK_ARG(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+    return wgrad_impl(dy_hi, dy_lo, dy_inv_scale, a_hi, a_lo, a_inv_scale, dtype, B, H, W, H, W, n_total,
+                      c_total, c_total, 3, 3, 1, 1, passes, workspace, dw, layout_nc9, stream);
+}
+
+extern "C" int64_t dsee_conv2d_tc_wgrad_workspace_floats(int B, int Ho, int Wo, int n_total, int Ci,
+                                                         int KH, int KW) {
+    int splits;
+    const int cpad = (Ci + 63) / 64 * 64;
+    wgrad_plan(B, Ho, Wo, n_total, cpad, &splits, KH * KW);
+    return (int64_t)splits * n_total * KH * KW * cpad;
+}
+
+extern "C" int dsee_conv2d_tc_wgrad(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale,
+                                    const void* a_hi, const void* a_lo, const float* a_inv_scale, int B,
+                                    int Ho, int Wo, int Hi, int Wi, int n_total, int Ci, int KH, int KW,
+                                    int stride, int pad, int passes, float* workspace, float* dw,
+                                    void* stream) {
+    DSEE_CHECK_ARG(dy_hi && a_hi && workspace && dw, "NULL pointer");
+    DSEE_CHECK_ARG(B > 0 && Ho > 0 && Wo > 0 && Hi > 0 && Wi > 0, "bad geometry");
+    DSEE_CHECK_ARG(n_total % 8 == 0 && Ci % 8 == 0, "channel counts must be multiples of 8");
+    DSEE_CHECK_ARG(KH * KW <= 16 && (stride == 1 || stride == 2), "at most 16 taps, stride 1 or 2");
+    DSEE_CHECK_ARG(passes == 1 || (passes == 3 && dy_lo && a_lo), "passes must be 1, or 3 with lo planes");
+    const int cpad = (Ci + 63) / 64 * 64;
+    DSEE_CHECK_ARG(cpad == 64 || cpad == 128 || cpad % 256 == 0,
+                   "input channels (padded to 64) must be 64, 128 or a multiple of 256");
+    return wgrad_impl(dy_hi, dy_lo, dy_inv_scale, a_hi, a_lo, a_inv_scale, 0, B, Ho, Wo, Hi, Wi, n_total,
+                      Ci, cpad, KH, KW, stride, pad, passes, workspace, dw, 1, stream);
 }

@@ -52,7 +52,7 @@ class MultiscaleDiscriminator(BaseNetwork):
         return result
 
     def forward(self, input):
-        cp = (input.shape[1] + 3) // 4 * 4
+        cp = (input.shape[1] + 31) // 32 * 32
         res = self.forward_nhwc(ops.nchw_to_nhwc(input.contiguous().float(), cp))
         return [[t.permute(0, 3, 1, 2) for t in scale] for scale in res]
 
@@ -92,23 +92,22 @@ class NLayerDiscriminator(BaseNetwork):
         det = (lambda t: t.detach() if t is not None else None) if detach_params else (lambda t: t)
         outs = []
         conv0 = self.model0[0]
-        x = ops.Conv2dDirectFn.apply(x, det(_khwc(conv0.weight, x.shape[3])), det(conv0.bias), 2, 2, 0,
-                                     True)
+        x = ops.conv_layer(x, det(conv0.weight), det(conv0.bias), 2, 2, lrelu=True)
         outs.append(x)
         for n in range(1, self.n_layers):
             seq = getattr(self, 'model%d' % n)[0]  # Sequential(spectral conv, InstanceNorm2d)
             conv = seq[0]
             stride = 1 if n == self.n_layers - 1 else 2
-            y = ops.Conv2dDirectFn.apply(x, det(_khwc(effective_weight(conv))), None, stride, 2, 0, False)
+            y = ops.conv_layer(x, det(effective_weight(conv)), None, stride, 2)
             x = ops.InstanceNormFn.apply(y, 1)
             outs.append(x)
         last = getattr(self, 'model%d' % self.n_layers)[0]
-        x = ops.Conv2dDirectFn.apply(x, det(_khwc(last.weight)), det(last.bias), 1, 2, 0, False)
+        x = ops.conv_layer(x, det(last.weight), det(last.bias), 1, 2)
         outs.append(x)
         return outs
 
     def forward(self, input):
-        cp = (input.shape[1] + 3) // 4 * 4
+        cp = (input.shape[1] + 31) // 32 * 32
         outs = self.forward_nhwc(ops.nchw_to_nhwc(input.contiguous().float(), cp))
         outs = [t.permute(0, 3, 1, 2) for t in outs]
         return outs if not self.opt.no_ganFeat_loss else outs[-1]

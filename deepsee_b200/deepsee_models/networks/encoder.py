@@ -30,8 +30,7 @@ def _stage(x, seq, stride=1, ups=0, act=1, pad_cin=None):
     The spectral-normalised weight stays an autograd tensor, so the weight gradient the conv node
     returns flows on to ``weight_orig`` through torch's own spectral-norm graph."""
     conv = seq[0]
-    w = _khwc(effective_weight(conv), pad_cin)
-    y = ops.Conv2dDirectFn.apply(x, w, None, stride, 1, ups, False)
+    y = ops.conv_layer(x, effective_weight(conv), None, stride, 1, ups=ups)
     return ops.InstanceNormFn.apply(y, act)
 
 

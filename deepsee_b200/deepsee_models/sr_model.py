@@ -236,7 +236,7 @@ class SRModel(torch.nn.Module):
         the NCHW->NHWC conversion are one kernel (ops.disc_input) on the uint8 label map."""
         labels, _ = ops.labels_from_onehot(input_semantics.contiguous().float())
         L = input_semantics.shape[1]
-        cp = (L + 3 + 3) // 4 * 4
+        cp = (L + 3 + 31) // 32 * 32  # zero channels up to a multiple of 32 (tcgen05 epilogue width)
         x = ops.DiscInputFn.apply(labels, fake_image.contiguous().float(),
                                   real_image.contiguous().float(), L, cp)
         out = self.netD.forward_nhwc(x, detach_params=for_generator)

@@ -613,6 +613,157 @@ def channel_sum(x):
     return out
 
 
+def split_f16_ups2(x, want_lo=True):
+    """fp32 NHWC [B,H,W,C] -> fp16 planes [B,2H,2W,C] (nearest 2x upsample materialised)."""
+    _chk_cuda(x)
+    B, H, W, Cc = x.shape
+    hi = torch.empty((B, 2 * H, 2 * W, Cc), dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    _lib.check(_lib.load().dsee_split_f16_ups2(_p(x), _p(hi), _p(lo), B, H, W, Cc, _stream()))
+    return SplitPlanes(hi, lo)
+
+
+def fold2x2(x):
+    _chk_cuda(x)
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, H // 2, W // 2, Cc), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().dsee_fold2x2(_p(x), _p(out), B, H // 2, W // 2, Cc, _stream()))
+    return out
+
+
+def prep_conv_weight_ex(w, want_lo=True, transpose=False, rows=None):
+    """fp32 [N,C,KH,KW] -> planes [N, KH*KW*Cp] (or [rows >= C, KH*KW*Np] transposed); K blocks
+    padded to 64 with zeros, extra rows zero."""
+    _chk_cuda(w)
+    N, Cin, KH, KW = w.shape
+    r, cols = (Cin, N) if transpose else (N, Cin)
+    rows = max(rows or r, r)
+    kp = (cols + 63) // 64 * 64
+    alloc = torch.zeros if rows > r else torch.empty
+    hi = alloc((rows, KH * KW * kp), dtype=torch.float16, device=w.device)
+    lo = alloc((rows, KH * KW * kp), dtype=torch.float16, device=w.device) if want_lo else None
+    inv = torch.empty(2, dtype=torch.float32, device=w.device)
+    _lib.check(_lib.load().dsee_prep_conv_weight_ex(_p(w), _p(hi), _p(lo), _p(inv), N, Cin, KH, KW,
+                                                    int(transpose), _stream()))
+    return PreparedWeight(hi, lo, inv, rows, cols)
+
+
+def conv2d_tc(a, pw, bias, KH, KW, stride, pad, out_hw, passes=3, lrelu=False, transposed=False,
+              tag="conv2d_tc"):
+    """General strided conv (or its backward-data when transposed) on the tcgen05 kernel.
+    a: SplitPlanes / GradPlanes NHWC; out_hw: output (Ho, Wo)."""
+    _chk_cuda(a.hi, a.lo, bias)
+    B, Hi, Wi, Ci = a.hi.shape
+    args = _lib.Conv2dTCArgs()
+    args.B, args.Hi, args.Wi = B, Hi, Wi
+    args.a_hi, args.a_lo, args.Ci = a.hi.data_ptr(), (a.lo.data_ptr() if a.lo is not None else 0), Ci
+    inv = getattr(a, "inv_scale", None)
+    args.a_inv_scale = inv.data_ptr() if inv is not None else 0
+    args.KH, args.KW, args.stride, args.pad = KH, KW, stride, pad
+    args.w_hi, args.w_lo = pw.hi.data_ptr(), (pw.lo.data_ptr() if pw.lo is not None else 0)
+    args.w_inv_scale = pw.inv_scale.data_ptr()
+    args.n_total, args.passes, args.transposed = pw.n_total, passes, int(transposed)
+    args.Ho, args.Wo = out_hw
+    out = torch.empty((B, out_hw[0], out_hw[1], pw.n_total), dtype=torch.float32, device=a.hi.device)
+    epi = _lib.ConvEpilogue()
+    epi.bias = bias.data_ptr() if bias is not None else 0
+    epi.out = out.data_ptr()
+    epi.lrelu = int(lrelu)
+    npix = B * (Hi * Wi if transposed else out_hw[0] * out_hw[1])
+    flops = 2.0 * KH * KW * pw.cin * pw.n_total * npix
+    _timed(tag, flops, lambda: _lib.check(_lib.load().dsee_conv2d_tc(C.byref(args), C.byref(epi),
+                                                                     _stream())))
+    return out
+
+
+def conv2d_tc_wgrad(dy, a, w_shape, stride, pad, passes=3):
+    """-> dW [N, Ci_w, KH, KW] for the forward conv with activation planes `a`."""
+    _chk_cuda(dy.hi, dy.lo, a.hi, a.lo)
+    N, Cw, KH, KW = w_shape
+    B, Ho, Wo, _ = dy.hi.shape
+    _, Hi, Wi, Ci = a.hi.shape
+    lib = _lib.load()
+    cpad = (Ci + 63) // 64 * 64
+    ws = torch.empty(lib.dsee_conv2d_tc_wgrad_workspace_floats(B, Ho, Wo, N, Ci, KH, KW),
+                     dtype=torch.float32, device=dy.hi.device)
+    dw = torch.empty((N, cpad, KH, KW), dtype=torch.float32, device=dy.hi.device)
+    flops = 2.0 * KH * KW * Cw * N * B * Ho * Wo
+    _timed("wgrad2d", flops, lambda: _lib.check(lib.dsee_conv2d_tc_wgrad(
+        _p(dy.hi), _p(dy.lo), _p(getattr(dy, "inv_scale", None)), _p(a.hi), _p(a.lo),
+        _p(getattr(a, "inv_scale", None)), B, Ho, Wo, Hi, Wi, N, Ci, KH, KW, stride, pad, passes,
+        _p(ws), _p(dw), _stream())))
+    return dw[:, :Cw].contiguous() if cpad != Cw else dw
+
+
+def tc_conv_eligible(cin_x, cout):
+    """Layers the tcgen05 path takes: enough channels for a K block to make sense and an output
+    width the epilogue stores in 32-column chunks (the RGB stem of the encoder and the
+    discriminator's 1-channel prediction conv stay on the direct fp32 kernels)."""
+    return cin_x % 8 == 0 and cin_x >= 16 and cout % 32 == 0 and cout in (32, 64, 128, 256, 512, 1024)
+
+
+class Conv2dTCFn(torch.autograd.Function):
+    """Encoder / discriminator conv layer (3x3 or 4x4, stride 1 / 2, optional folded 2x upsample of
+    the input, optional fused bias + LeakyReLU) on the tcgen05 implicit-GEMM kernels.
+    x fp32 NHWC [B,Hi,Wi,Cx]; w fp32 [N,Cw,KH,KW] (PyTorch layout, Cw <= Cx: x may carry zero
+    padding channels); out fp32 NHWC."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, pad, ups, lrelu):
+        from .config import config
+        passes = config.passes
+        want_lo = passes == 3
+        N, Cw, KH, KW = w.shape
+        planes = split_f16_ups2(x, want_lo) if ups else split_f16(x, want_lo)
+        B, Hu, Wu, Cx = planes.hi.shape
+        Ho, Wo = (Hu + 2 * pad - KH) // stride + 1, (Wu + 2 * pad - KW) // stride + 1
+        pw = prep_conv_weight_ex(w.contiguous(), want_lo)
+        out = conv2d_tc(planes, pw, bias, KH, KW, stride, pad, (Ho, Wo), passes=passes, lrelu=lrelu)
+        ctx.cfg = (stride, pad, ups, lrelu, bias is not None, passes, want_lo, tuple(x.shape))
+        ctx.planes = planes
+        ctx.save_for_backward(w, out if lrelu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        w, out = ctx.saved_tensors
+        stride, pad, ups, lrelu, has_bias, passes, want_lo, xshape = ctx.cfg
+        planes = ctx.planes
+        ctx.planes = None
+        N, Cw, KH, KW = w.shape
+        dy = dy.contiguous()
+        if lrelu:
+            dy = act_bwd(dy, out, 1)
+        g, sums = grad_prep(dy, want_lo=want_lo)
+        dx = dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw = conv2d_tc_wgrad(g, planes, tuple(w.shape), stride, pad, passes=passes)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = sums[0]
+        if ctx.needs_input_grad[0]:
+            B, Hu, Wu, Cx = planes.hi.shape
+            rows = (Cx + 31) // 32 * 32
+            pwT = prep_conv_weight_ex(w.contiguous(), want_lo, transpose=True, rows=rows)
+            dx = conv2d_tc(g, pwT, None, KH, KW, stride, pad, (Hu, Wu), passes=passes, transposed=True,
+                           tag="dgrad2d")
+            if rows != Cx:
+                dx = dx[..., :Cx].contiguous()
+            if ups:
+                dx = fold2x2(dx)
+        return dx, dw, db, None, None, None, None
+
+
+def conv_layer(x, w, bias, stride, pad, ups=0, lrelu=False):
+    """Dispatch of an encoder / discriminator conv: tcgen05 path when eligible, else the direct fp32
+    kernels. w in PyTorch layout [N,Cw,KH,KW] (autograd tensor)."""
+    if tc_conv_eligible(x.shape[3], w.shape[0]):
+        return Conv2dTCFn.apply(x, w, bias, stride, pad, ups, lrelu)
+    wk = w.permute(2, 3, 1, 0)
+    if x.shape[3] > wk.shape[2]:
+        wk = torch.nn.functional.pad(wk, (0, 0, 0, x.shape[3] - wk.shape[2]))
+    return Conv2dDirectFn.apply(x, wk.contiguous(), bias, stride, pad, ups, lrelu)
+
+
 class Conv2dDirectFn(torch.autograd.Function):
     """conv2d_direct (+ fused LeakyReLU) with its backward-data / weight-gradient kernels."""
 

@@ -85,6 +85,13 @@ int dsee_prep_conv_weight(const float* w, void* out_hi, void* out_lo, float* inv
 /* fp32 NHWC [rows][C] -> fp16 split planes (used for tensors not produced by a fused epilogue). */
 int dsee_split_f16(const float* in, void* out_hi, void* out_lo, int64_t n, void* stream);
 
+/* fp32 NHWC [B,H,W,C] -> fp16 split planes [B,2H,2W,C] with the nn.Upsample(scale_factor=2) in
+ * front of the encoder's up_conv / conv2 (encoder.py:94-95,153-154) materialised, and its
+ * transpose for the backward pass: out[b,y,x,c] = sum of the 2x2 block of in [B,2Ho,2Wo,C]. */
+int dsee_split_f16_ups2(const float* in, void* out_hi, void* out_lo, int B, int H, int W, int C,
+                        void* stream);
+int dsee_fold2x2(const float* in, float* out, int B, int Ho, int Wo, int C, void* stream);
+
 /* ---- the fused tensor-core kernels ---------------------------------------------------------- */
 typedef struct {
     /* geometry: stride-1 3x3 conv, zero padding 1, output size == input size */
@@ -136,9 +143,55 @@ typedef struct {
     /* optional device float: receives max |out| (what the next gradient-plane scale is chosen
      * from); zeroed by the call. */
     float* amax_out;
+    /* fuse LeakyReLU(0.2) after the bias (discriminator.py:84-85) */
+    int lrelu;
 } dsee_conv_epilogue;
 int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_epilogue* epi, void* stream);
 int dsee_conv3x3_stats_tiles(int B, int H, int W);
+
+/* General KH x KW (<= 16 taps), stride 1 / 2 convolution on the same tcgen05 kernel: the style
+ * encoder's 3x3 stride-1/2 layers (encoder.py:84-98,142-157) and the discriminator's 4x4
+ * stride-1/2 layers (discriminator.py:84-96).  A stride-2 tap is a TMA box with element stride 2.
+ *   transposed = 0:  out[b,yo,xo,n] = bias[n] + sum A[b, yo*stride - pad + ky, xo*stride - pad + kx, c]
+ *                                               * w[n,c,ky,kx]          (out [B,Ho,Wo,n_total])
+ *   transposed = 1:  backward-data of that conv: A = dY planes [B,Hi,Wi,Ci] (Hi, Wi = the forward
+ *                    output size, Ci = forward Cout), out = dX [B,Ho,Wo,n_total] (the forward input
+ *                    size / channels); stride 2 runs as 4 output-parity classes.
+ * A channels only need to be a multiple of 8: TMA zero-fills the 64-channel K block beyond Ci and
+ * dsee_prep_conv_weight_ex pads the weight K blocks with zeros.
+ * Epilogue: bias, lrelu, act_mask (stride 1 only), amax_out, out; no residual / noise / stats. */
+typedef struct {
+    int B, Hi, Wi;
+    const void* a_hi;
+    const void* a_lo;
+    int Ci;
+    const float* a_inv_scale;
+    int KH, KW, stride, pad;
+    const void* w_hi;
+    const void* w_lo;
+    const float* w_inv_scale;
+    int n_total;
+    int passes;
+    int transposed;
+    int Ho, Wo;
+} dsee_conv2d_tc_args;
+int dsee_conv2d_tc(const dsee_conv2d_tc_args* args, const dsee_conv_epilogue* epi, void* stream);
+/* Weights for dsee_conv2d_tc / dsee_conv2d_tc_wgrad: fp32 [N][C][KH][KW] -> scaled fp16 planes
+ *   transpose = 0: [N][KH*KW*Cp], k = (ky*KW+kx)*Cp + c, Cp = C rounded up to 64 (zeros beyond C)
+ *   transpose = 1: [C][KH*KW*Np], k = (ky*KW+kx)*Np + n, Np = N rounded up to 64 (not rotated:
+ *                  the tap offsets of the transposed conv carry the rotation). */
+int dsee_prep_conv_weight_ex(const float* w, void* out_hi, void* out_lo, float* inv_scale, int N,
+                             int C, int KH, int KW, int transpose, void* stream);
+
+/* Weight gradient of dsee_conv2d_tc: dY planes [B,Ho,Wo,n_total], activation planes
+ * [B,Hi,Wi,Ci] (the forward input) -> dw fp32 [n_total][Cp][KH][KW], Cp = Ci rounded up to 64
+ * (columns beyond Ci are zero).  workspace fp32 [dsee_conv2d_tc_wgrad_workspace_floats()]. */
+int64_t dsee_conv2d_tc_wgrad_workspace_floats(int B, int Ho, int Wo, int n_total, int Ci, int KH,
+                                              int KW);
+int dsee_conv2d_tc_wgrad(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale,
+                         const void* a_hi, const void* a_lo, const float* a_inv_scale, int B, int Ho,
+                         int Wo, int Hi, int Wi, int n_total, int Ci, int KH, int KW, int stride,
+                         int pad, int passes, float* workspace, float* dw, void* stream);
 
 /* K1.  Replaces SPADE.forward (normalization.py:105-120), SEAN_Block.forward (:167-213) and
  * PureSEAN_Block.forward (:254-286) together with the following actvn (architecture.py:96,114,147):

@@ -342,9 +342,10 @@ def test_conv2d_direct_node(Cin, Cout, K, stride, pad, ups, lrelu, bias):
     torch.testing.assert_close(_nchw(out), ref, rtol=1e-4, atol=5e-5)
     out.backward(_nhwc(dy))
     torch.testing.assert_close(_nchw(x2.grad), x.grad, rtol=1e-4, atol=5e-5)
-    torch.testing.assert_close(w2.grad, w.grad.permute(2, 3, 1, 0), rtol=1e-4, atol=2e-4)
+    wref = w.grad.permute(2, 3, 1, 0)
+    assert (w2.grad - wref).abs().max().item() <= 1e-4 * wref.abs().max().item()
     if bias:
-        torch.testing.assert_close(b2.grad, b.grad, rtol=1e-4, atol=2e-4)
+        assert (b2.grad - b.grad).abs().max().item() <= 1e-4 * b.grad.abs().max().item()
 
 
 @pytest.mark.parametrize("act", [0, 1, 2])
@@ -397,3 +398,61 @@ def test_pool_and_input_nodes():
     dxin = torch.randn(xin.shape, generator=g).cuda()
     xin.backward(dxin)
     torch.testing.assert_close(fake.grad, dxin[:B, :, :, L:L + 3].permute(0, 3, 1, 2))
+
+
+@pytest.mark.parametrize("Cx,Cw,Cout,K,stride,pad,ups,lrelu,bias", [
+    (32, 32, 64, 3, 2, 1, 0, False, False),     # encoder down0
+    (64, 64, 128, 3, 2, 1, 0, False, False),    # encoder down1
+    (128, 128, 256, 3, 1, 1, 1, False, False),  # encoder up_conv (upsample materialised)
+    (256, 256, 128, 3, 1, 1, 0, False, False),  # encoder final
+    (32, 22, 32, 4, 2, 2, 0, True, True),       # discriminator model0 (22 real + 10 zero channels)
+    (24, 22, 32, 4, 2, 2, 0, True, True),
+    (32, 32, 64, 4, 2, 2, 0, False, False),     # discriminator inner, stride 2
+    (128, 128, 256, 4, 1, 2, 0, False, False),  # discriminator inner, stride 1
+])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_conv2d_tc_node(Cx, Cw, Cout, K, stride, pad, ups, lrelu, bias, passes):
+    """The general strided tcgen05 conv (TMA element strides), its 4-parity-class backward-data
+    and the strided weight gradient against torch autograd."""
+    from deepsee_b200 import ops
+    from deepsee_b200.config import config
+    g = torch.Generator(device="cpu").manual_seed(Cx + Cout + K + stride)
+    B, H, W = 2, 13, 18
+    x = torch.randn(B, Cx, H, W, generator=g)
+    x[:, Cw:] = 0
+    x = x.cuda().requires_grad_(True)
+    w = (torch.randn(Cout, Cw, K, K, generator=g) / (K * Cw ** 0.5)).cuda().requires_grad_(True)
+    b = torch.randn(Cout, generator=g).cuda().requires_grad_(True) if bias else None
+    xin = F.interpolate(x, scale_factor=2, mode="nearest") if ups else x
+    ref = F.conv2d(xin[:, :Cw], w, b, stride=stride, padding=pad)
+    if lrelu:
+        ref = F.leaky_relu(ref, 0.2)
+    dy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1)).cuda()
+    ref.backward(dy)
+    x2 = _nhwc(x.detach()).requires_grad_(True)
+    w2 = w.detach().clone().requires_grad_(True)
+    b2 = b.detach().clone().requires_grad_(True) if bias else None
+    assert ops.tc_conv_eligible(Cx, Cout)
+    old = config.passes
+    config.passes = passes
+    try:
+        out = ops.conv_layer(x2, w2, b2, stride, pad, ups=ups, lrelu=lrelu)
+        out.backward(_nhwc(dy))
+    finally:
+        config.passes = old
+    tol = 5e-5 if passes == 3 else 2e-2
+
+    def chk(a, r, what):
+        if passes == 3:
+            err, s = (a - r).abs().max().item(), r.abs().max().item()
+            assert err <= tol * s, (what, err, s)
+        else:
+            # 1-pass forward differences (1e-3) flip a few fused-LeakyReLU masks; relative L2 is the
+            # meaningful measure there
+            rel = ((a - r).norm() / r.norm()).item()
+            assert rel <= 5e-3, (what, rel)
+    chk(_nchw(out), ref, "fwd")
+    chk(_nchw(x2.grad)[:, :Cw], x.grad[:, :Cw], "dgrad")
+    chk(w2.grad, w.grad, "wgrad")
+    if bias:
+        chk(b2.grad, b.grad, "dbias")
