@@ -20,11 +20,11 @@ SYMBOLS = [
     "dsee_conv3x3_fwd", "dsee_conv3x3_stats_tiles", "dsee_spade_modulate_fwd",
     "dsee_spade_modulate_bwd", "dsee_grad_prep_blocks", "dsee_grad_prep", "dsee_reduce_partials",
     "dsee_conv3x3_wgrad_workspace_floats", "dsee_conv3x3_wgrad", "dsee_bn_bwd_blocks", "dsee_bn_bwd",
-    "dsee_shared_mlp_bwd_blocks", "dsee_shared_mlp_bwd", "dsee_style_gather_bwd",
+    "dsee_actv_grad_prep", "dsee_onehot_planes", "dsee_shared_mlp_bwd_blocks", "dsee_shared_mlp_bwd", "dsee_style_gather_bwd",
     "dsee_stem_bwd_blocks", "dsee_stem_bwd", "dsee_head_bwd_blocks", "dsee_head_bwd",
     "dsee_bn_stats", "dsee_bn_finalize", "dsee_bn_eval_affine",
     "dsee_stem_fwd", "dsee_head_fwd",
-    "dsee_conv2d_direct_fwd", "dsee_instance_norm_fwd", "dsee_region_pool_chunks",
+    "dsee_conv2d_direct_fwd", "dsee_instance_norm_fwd", "dsee_instance_norm_workspace_bytes", "dsee_region_pool_chunks",
     "dsee_region_pool_fwd", "dsee_nchw_to_nhwc", "dsee_disc_input", "dsee_avgpool3s2_fwd",
     "dsee_act_bwd", "dsee_conv2d_direct_dgrad", "dsee_conv2d_direct_wgrad_workspace_floats",
     "dsee_conv2d_direct_wgrad", "dsee_channel_sum_chunks", "dsee_channel_sum",
@@ -126,20 +126,22 @@ def load():
         "dsee_conv3x3_wgrad": [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp, i, vp],
         "dsee_bn_bwd_blocks": [i, i, i],
         "dsee_bn_bwd": [vp, vp, i, vp, vp, vp, vp, vp, f, vp, i, i, i, i, vp, vp, vp],
+        "dsee_actv_grad_prep": [vp, i, i, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp],
+        "dsee_onehot_planes": [vp, vp, i64, i, vp],
         "dsee_shared_mlp_bwd_blocks": [i, i, i],
         "dsee_shared_mlp_bwd": [vp, i, i, vp, vp, i, i, i, i, i, i, vp, vp, vp],
         "dsee_style_gather_bwd": [vp, i, i, vp, vp, vp, i, i, i, i, vp],
         "dsee_stem_bwd_blocks": [i, i, i],
         "dsee_stem_bwd": [vp, vp, i, i, i, i, vp, vp, vp],
         "dsee_head_bwd_blocks": [i, i, i],
-        "dsee_head_bwd": [vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp],
+        "dsee_head_bwd": [vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp],
         "dsee_bn_stats": [vp, i, vp, vp, i, i, i, i, vp, C.POINTER(C.c_int), vp],
         "dsee_bn_finalize": [vp, i, i, d, d, f, f, vp, vp, vp, vp, vp, vp, vp],
         "dsee_bn_eval_affine": [vp, vp, f, i, vp, vp, vp],
         "dsee_stem_fwd": [vp, vp, vp, vp, i, i, i, i, vp],
         "dsee_head_fwd": [vp, vp, vp, vp, i, i, i, i, vp],
         "dsee_conv2d_direct_fwd": [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, i, vp],
-        "dsee_instance_norm_fwd": [vp, vp, vp, vp, i, i, i, f, i, vp],
+        "dsee_instance_norm_fwd": [vp, vp, vp, vp, vp, i, i, i, f, i, vp],
         "dsee_region_pool_chunks": [i],
         "dsee_region_pool_fwd": [vp, vp, vp, vp, i, i, i, i, vp],
         "dsee_nchw_to_nhwc": [vp, vp, i, i, i, i, i, vp],
@@ -150,7 +152,7 @@ def load():
         "dsee_conv2d_direct_wgrad": [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp],
         "dsee_channel_sum_chunks": [i64],
         "dsee_channel_sum": [vp, i64, i, vp, vp, vp],
-        "dsee_instance_norm_bwd": [vp, vp, vp, vp, vp, vp, i, i, i, i, vp],
+        "dsee_instance_norm_bwd": [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp],
         "dsee_region_pool_bwd": [vp, vp, vp, i, i, i, i, vp],
         "dsee_avgpool3s2_bwd": [vp, vp, i, i, i, i, vp],
         "dsee_disc_input_bwd": [vp, vp, i, i, i, i, i, vp],
@@ -161,6 +163,8 @@ def load():
         fn.restype = C.c_int
     lib.dsee_conv3x3_wgrad_workspace_floats.argtypes = [i, i, i, i, i]
     lib.dsee_conv3x3_wgrad_workspace_floats.restype = C.c_int64
+    lib.dsee_instance_norm_workspace_bytes.argtypes = [i, i, i]
+    lib.dsee_instance_norm_workspace_bytes.restype = C.c_int64
     lib.dsee_conv2d_tc_wgrad_workspace_floats.argtypes = [i, i, i, i, i, i, i]
     lib.dsee_conv2d_tc_wgrad_workspace_floats.restype = C.c_int64
     lib.dsee_conv2d_direct_wgrad_workspace_floats.argtypes = [i, i, i, i, i, i, i]

@@ -84,24 +84,23 @@ __global__ void grad_prep_kernel(const float* __restrict__ dy, __half* __restric
     }
 }
 
-// out[k][c] = sum_s partial[s][c][k] (double, fixed order). grid = C/32, block = 32 x 8.
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int n, int C, int nq,
-                                       float scale, float* __restrict__ out) {
-    __shared__ double sh[8][32];
+// out[k][c] = sum_s partial[s][c][k] (double, fixed order). grid = (C/32, nq), block = 32 x 32.
+__global__ void __launch_bounds__(1024)
+reduce_partials_kernel(const float* __restrict__ partial, int n, int C, int nq, float scale,
+                       float* __restrict__ out) {
+    __shared__ double sh[32][33];
     const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
-    for (int k = 0; k < nq; ++k) {
-        double a = 0.0;
-        if (c < C)
-            for (int s = g; s < n; s += 8) a += (double)partial[((size_t)s * C + c) * nq + k];
-        sh[g][cl] = a;
-        __syncthreads();
-        if (g == 0 && c < C) {
-            double t = 0.0;
-            for (int j = 0; j < 8; ++j) t += sh[j][cl];
-            out[(size_t)k * C + c] = (float)(t * scale);
-        }
-        __syncthreads();
+    const int k = blockIdx.y;
+    double a = 0.0;
+    if (c < C)
+        for (int s = g; s < n; s += 32) a += (double)__ldg(partial + ((size_t)s * C + c) * nq + k);
+    sh[g][cl] = a;
+    __syncthreads();
+    if (g == 0 && c < C) {
+        double t = 0.0;
+        for (int j = 0; j < 32; ++j) t += sh[j][cl];
+        out[(size_t)k * C + c] = (float)(t * scale);
     }
 }
 
@@ -180,6 +179,90 @@ __global__ void bn_bwd_kernel(const float* __restrict__ dxhat, const float* __re
             nw_partial[(size_t)blockIdx.x * C + c] = a;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mlp_shared backward on the tensor cores.  actv[p,o] = relu(bias[o] + sum_tap table[tap][label(p+tap)][o])
+// is a 3x3 conv over the one-hot map, so d table = wgrad(G, onehot) with
+//   G[p,o] = relu'(actv[p,o]) * (sum over the 2^ups x 2^ups upsampled copies of d actv)
+// This kernel builds G as scaled fp16 planes (+ block partials of sum G = the bias gradient);
+// onehot_planes_kernel builds the other operand; dsee_conv3x3_wgrad does the reduction.
+// ------------------------------------------------------------------------------------------------
+__global__ void actv_grad_prep_kernel(const float* __restrict__ dsrc, int ld, int coff,
+                                      const __half* __restrict__ actv_hi, const float* __restrict__ amax,
+                                      int B, int Hl, int Wl, int ups, int nh, __half* __restrict__ hi,
+                                      __half* __restrict__ lo, float* __restrict__ inv_scale,
+                                      float* __restrict__ partial) {
+    extern __shared__ float red[];  // [lanes][nh]
+    const int cg = nh >> 2;
+    const int lanes = blockDim.x / cg;
+    const int g = threadIdx.x % cg, pl = threadIdx.x / cg;
+    const int f = 1 << ups;
+    // |G| <= f*f * max|dsrc|
+    const float scale = pow2_scale_for(__ldg(amax) * (float)(f * f), 14);
+    if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[0] = 1.f / scale;
+    const int64_t npix = (int64_t)B * Hl * Wl;
+    const int64_t p0 = (int64_t)blockIdx.x * GP_PIX;
+    const int H = Hl << ups, W = Wl << ups;
+    float s[4] = {0, 0, 0, 0};
+    if (pl < lanes) {
+        for (int i = pl; i < GP_PIX; i += lanes) {
+            const int64_t pix = p0 + i;
+            if (pix >= npix) break;
+            const int xl = (int)(pix % Wl);
+            const int yl = (int)((pix / Wl) % Hl);
+            const int b = (int)(pix / ((int64_t)Wl * Hl));
+            const size_t fp0 = ((size_t)b * H + yl * f) * W + xl * f;
+            const uint2 av = __ldg(reinterpret_cast<const uint2*>(actv_hi + fp0 * nh) + g);
+            float a[4] = {0, 0, 0, 0};
+            for (int sy = 0; sy < f; ++sy)
+                for (int sx = 0; sx < f; ++sx) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(
+                        dsrc + (fp0 + (size_t)sy * W + sx) * ld + coff + g * 4));
+                    a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+                }
+            // ReLU gate: actv > 0  <=>  fp16 hi plane positive (sign clear, magnitude non-zero)
+            const uint32_t m[4] = {av.x & 0xffffu, av.x >> 16, av.y & 0xffffu, av.y >> 16};
+            uint32_t ph[2], plw[2];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (!(m[e] != 0 && m[e] < 0x8000u)) a[e] = 0.f;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float s0 = fminf(fmaxf(a[2 * e] * scale, -65504.f), 65504.f);
+                const float s1 = fminf(fmaxf(a[2 * e + 1] * scale, -65504.f), 65504.f);
+                const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
+                const __half l0 = __float2half_rn(s0 - __half2float(h0));
+                const __half l1 = __float2half_rn(s1 - __half2float(h1));
+                ph[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                plw[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            *reinterpret_cast<uint2*>(hi + (size_t)pix * nh + g * 4) = make_uint2(ph[0], ph[1]);
+            if (lo) *reinterpret_cast<uint2*>(lo + (size_t)pix * nh + g * 4) = make_uint2(plw[0], plw[1]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s[e] += a[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) red[(size_t)pl * nh + g * 4 + e] = s[e];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) {
+        float a = 0.f;
+        for (int l = 0; l < lanes; ++l) a += red[(size_t)l * nh + i];
+        partial[(size_t)blockIdx.x * nh + i] = a;
+    }
+}
+
+// one-hot of a uint8 label map as an fp16 NHWC plane with Lp channels (zeros beyond the label range)
+__global__ void onehot_planes_kernel(const uint8_t* __restrict__ labels, __half* __restrict__ out,
+                                     int64_t npix, int Lp8) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix * Lp8) return;
+    const int g = (int)(i % Lp8);
+    const int l = labels[i / Lp8] - g * 8;
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (l >= 0 && l < 8) w[l >> 1] = (l & 1) ? 0x3C000000u : 0x00003C00u;  // fp16 1.0
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -271,79 +354,75 @@ __global__ void stem_bwd_kernel(const float* __restrict__ x, const float* __rest
 // ------------------------------------------------------------------------------------------------
 // image-head backward.  out = tanh(conv(lrelu(x))):  dpre = dout * (1 - out^2)   [B,3,H,W] NCHW
 //   dX[p][c]       = lrelu'(x[p][c]) * sum_{tap,o} dpre[o][p - tap] * w[o][c][tap]
-//   dW[o][c][tap]  = sum_p dpre[o][p] * lrelu(x[p + tap][c]),   db[o] = sum_p dpre[o][p]
+//   dW[o][c][tap]  = sum_p dpre[o][p - tap] * lrelu(x[p][c]),   db[o] = sum_p dpre[o][p]
+// One pass over x: a persistent block walks 8x16 pixel tiles; the 27 values dpre[o][p - tap] of
+// every tile pixel are staged in shared memory (read as warp broadcasts), a thread owns 2 channels
+// with its 54 weights and 54 dW accumulators in registers.
 // ------------------------------------------------------------------------------------------------
-__global__ void head_dpre_kernel(const float* __restrict__ dout, const float* __restrict__ out,
-                                 float* __restrict__ dpre, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float o = out[i];
-    dpre[i] = dout[i] * (1.f - o * o);
-}
-
-// thread = (pixel, 4 channels); weights [3][C][9] read through L1
-__global__ void head_dx_kernel(const float* __restrict__ x, const float* __restrict__ dpre,
-                               const float* __restrict__ w, float* __restrict__ dx, int B, int H, int W,
-                               int C) {
-    const int cg = C >> 2;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)B * H * W * cg) return;
-    const int g = (int)(i % cg);
-    const int64_t pix = i / cg;
-    const int xx = (int)(pix % W), yy = (int)((pix / W) % H), b = (int)(pix / ((int64_t)W * H));
-    float acc[4] = {0, 0, 0, 0};
+constexpr int HB_TH = 8, HB_TW = 16, HB_PX = HB_TH * HB_TW;
+__global__ void __launch_bounds__(512)
+head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ out,
+                const float* __restrict__ dout, int B, int H, int W, int C, float* __restrict__ dx,
+                float* __restrict__ partial /*[grid][C][28]*/) {
+    __shared__ float patch[HB_PX][28];
+    const int c2 = threadIdx.x * 2;
+    float wr[2][27], acc[2][27];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-        // output pixel q = p - (tap offset) used x[p] with weight tap
-        const int yq = yy - (tap / 3 - 1), xq = xx - (tap % 3 - 1);
-        if (yq < 0 || yq >= H || xq < 0 || xq >= W) continue;
+    for (int e = 0; e < 2; ++e)
 #pragma unroll
-        for (int o = 0; o < 3; ++o) {
-            const float d = __ldg(dpre + (((size_t)b * 3 + o) * H + yq) * W + xq);
+        for (int k = 0; k < 27; ++k) {
+            wr[e][k] = __ldg(w + ((size_t)(k / 9) * C + c2 + e) * 9 + k % 9);
+            acc[e][k] = 0.f;
+        }
+    float bacc = 0.f;
+    const int tiles_w = (W + HB_TW - 1) / HB_TW, tiles_h = (H + HB_TH - 1) / HB_TH;
+    const int ntiles = B * tiles_h * tiles_w;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int w0 = (tile % tiles_w) * HB_TW;
+        const int h0 = ((tile / tiles_w) % tiles_h) * HB_TH;
+        const int b = tile / (tiles_w * tiles_h);
+        __syncthreads();
+        for (int i = threadIdx.x; i < HB_PX * 27; i += blockDim.x) {
+            const int pi = i / 27, k = i % 27;
+            const int o = k / 9, tap = k % 9;
+            const int yy = h0 + pi / HB_TW - (tap / 3 - 1), xx = w0 + pi % HB_TW - (tap % 3 - 1);
+            float v = 0.f;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                const size_t idx = (((size_t)b * 3 + o) * H + yy) * W + xx;
+                const float ov = __ldg(out + idx);
+                v = __ldg(dout + idx) * (1.f - ov * ov);
+            }
+            patch[pi][k] = v;
+        }
+        __syncthreads();
+        for (int pi = 0; pi < HB_PX; ++pi) {
+            const int yy = h0 + pi / HB_TW, xx = w0 + pi % HB_TW;
+            if (yy >= H || xx >= W) continue;  // block-uniform
+            const size_t pix = ((size_t)b * H + yy) * W + xx;
+            const float2 xv = __ldg(reinterpret_cast<const float2*>(x + pix * C + c2));
+            const float v0 = xv.x > 0.f ? xv.x : 0.2f * xv.x, v1 = xv.y > 0.f ? xv.y : 0.2f * xv.y;
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[e] += d * __ldg(w + ((size_t)o * C + g * 4 + e) * 9 + tap);
+            for (int k = 0; k < 27; ++k) {
+                const float d = patch[pi][k];
+                a0 += d * wr[0][k];
+                a1 += d * wr[1][k];
+                acc[0][k] += d * v0;
+                acc[1][k] += d * v1;
+            }
+            *reinterpret_cast<float2*>(dx + pix * C + c2) =
+                make_float2(a0 * (xv.x > 0.f ? 1.f : 0.2f), a1 * (xv.y > 0.f ? 1.f : 0.2f));
+            if (threadIdx.x < 3) bacc += patch[pi][threadIdx.x * 9 + 4];  // centre tap = dpre[o][p]
         }
     }
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)pix * C) + g);
-    float4 r;
-    r.x = acc[0] * (xv.x > 0.f ? 1.f : 0.2f);
-    r.y = acc[1] * (xv.y > 0.f ? 1.f : 0.2f);
-    r.z = acc[2] * (xv.z > 0.f ? 1.f : 0.2f);
-    r.w = acc[3] * (xv.w > 0.f ? 1.f : 0.2f);
-    reinterpret_cast<float4*>(dx + (size_t)pix * C)[g] = r;
-}
-
-// block = C threads over HD_PIX output pixels; partial [blocks][C][27 + (c < 3 ? bias : 0)]
-constexpr int HD_PIX = 128;
-__global__ void head_dw_kernel(const float* __restrict__ x, const float* __restrict__ dpre, int B, int H,
-                               int W, int C, float* __restrict__ partial /*[blocks][C][28]*/) {
-    const int c = threadIdx.x;
-    const int64_t npix = (int64_t)B * H * W;
-    const int64_t p0 = (int64_t)blockIdx.x * HD_PIX;
-    float acc[28];
+    float* o = partial + (size_t)blockIdx.x * C * 28;
 #pragma unroll
-    for (int k = 0; k < 28; ++k) acc[k] = 0.f;
-    for (int i = 0; i < HD_PIX; ++i) {
-        const int64_t pix = p0 + i;
-        if (pix >= npix) break;
-        const int xx = (int)(pix % W), yy = (int)((pix / W) % H), b = (int)(pix / ((int64_t)W * H));
-        float d[3];
+    for (int e = 0; e < 2; ++e) {
 #pragma unroll
-        for (int o = 0; o < 3; ++o) d[o] = __ldg(dpre + (((size_t)b * 3 + o) * H + yy) * W + xx);
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
-            if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
-            float v = __ldg(x + (((size_t)b * H + y2) * W + x2) * C + c);
-            v = v > 0.f ? v : 0.2f * v;
-#pragma unroll
-            for (int o = 0; o < 3; ++o) acc[o * 9 + tap] += d[o] * v;
-        }
-        if (c < 3) acc[27] += d[c];
+        for (int k = 0; k < 27; ++k) o[(size_t)(c2 + e) * 28 + k] = acc[e][k];
+        if (c2 + e >= 3) o[(size_t)(c2 + e) * 28 + 27] = 0.f;
     }
-    float* o = partial + ((size_t)blockIdx.x * C + c) * 28;
-#pragma unroll
-    for (int k = 0; k < 28; ++k) o[k] = acc[k];
+    if (threadIdx.x < 3) o[(size_t)threadIdx.x * 28 + 27] = bacc;
 }
 
 }  // namespace dsee
@@ -386,7 +465,8 @@ extern "C" int dsee_reduce_partials(const float* partial, int n, int C, int nq, 
     DSEE_CHECK_ARG(partial && out && n > 0 && C > 0 && nq > 0, "bad argument");
     int rc = require_sm100();
     if (rc) return rc;
-    reduce_partials_kernel<<<cdivb(C, 32), 256, 0, (cudaStream_t)stream>>>(partial, n, C, nq, scale, out);
+    reduce_partials_kernel<<<dim3(cdivb(C, 32), nq), 1024, 0, (cudaStream_t)stream>>>(partial, n, C, nq,
+                                                                                    scale, out);
     LAUNCH_END();
 }
 
@@ -407,6 +487,34 @@ extern "C" int dsee_bn_bwd(const float* dxhat, const float* x, int x_ups, const 
     bn_bwd_kernel<<<dsee_bn_bwd_blocks(B, Hx, Wx), 256, sm, (cudaStream_t)stream>>>(
         dxhat, x, x_ups, noise, noise_w, bn_scale, bn_shift, sums, inv_count, dskip, B, Hx, Wx, C, dx,
         nw_partial);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_actv_grad_prep(const float* dsrc, int ld, int coff, const void* actv_hi,
+                                   const float* dsrc_amax, int B, int Hl, int Wl, int ups, int nh,
+                                   void* out_hi, void* out_lo, float* inv_scale, float* partial,
+                                   void* stream) {
+    DSEE_CHECK_ARG(dsrc && actv_hi && dsrc_amax && out_hi && inv_scale && partial, "NULL pointer");
+    DSEE_CHECK_ARG(nh % 4 == 0 && nh / 4 <= 256 && 256 % (nh / 4) == 0 && (ups == 0 || ups == 1) &&
+                       ld % 4 == 0 && coff % 4 == 0,
+                   "bad shape");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int64_t npix = (int64_t)B * Hl * Wl;
+    const int lanes = 256 / (nh / 4);
+    actv_grad_prep_kernel<<<cdivb(npix, GP_PIX), 256, (size_t)lanes * nh * sizeof(float),
+                            (cudaStream_t)stream>>>(dsrc, ld, coff, (const __half*)actv_hi, dsrc_amax,
+                                                    B, Hl, Wl, ups, nh, (__half*)out_hi, (__half*)out_lo,
+                                                    inv_scale, partial);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_onehot_planes(const uint8_t* labels, void* out, int64_t npix, int Lp, void* stream) {
+    DSEE_CHECK_ARG(labels && out && npix > 0 && Lp > 0 && Lp % 8 == 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    onehot_planes_kernel<<<cdivb(npix * (Lp / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        labels, (__half*)out, npix, Lp / 8);
     LAUNCH_END();
 }
 
@@ -436,8 +544,8 @@ extern "C" int dsee_shared_mlp_bwd(const float* dsrc, int ld, int coff, const vo
         dsrc, ld, coff, (const __half*)actv_hi, labels, B, Hl, Wl, ups, L, nh, partial);
     count_launch();
     // [blocks][rows*nh][1] -> [rows*nh]
-    reduce_partials_kernel<<<cdivb(rows * nh, 32), 256, 0, st>>>(partial, blocks, rows * nh, 1, 1.f,
-                                                                  dtable_dbias);
+    reduce_partials_kernel<<<dim3(cdivb(rows * nh, 32), 1), 1024, 0, st>>>(partial, blocks, rows * nh, 1,
+                                                                            1.f, dtable_dbias);
     LAUNCH_END();
 }
 
@@ -453,29 +561,28 @@ extern "C" int dsee_stem_bwd(const float* x, const float* dy, int B, int H, int 
     stem_bwd_kernel<<<blocks, 128, 0, st>>>(x, dy, B, H, W, C, partial);
     count_launch();
     // partial [blocks][C*28] -> dw_db [C*28]  (per channel: 27 weight grads then the bias grad)
-    reduce_partials_kernel<<<cdivb(C * 28, 32), 256, 0, st>>>(partial, blocks, C * 28, 1, 1.f, dw_db);
+    reduce_partials_kernel<<<dim3(cdivb(C * 28, 32), 1), 1024, 0, st>>>(partial, blocks, C * 28, 1, 1.f,
+                                                                         dw_db);
     LAUNCH_END();
 }
 
-extern "C" int dsee_head_bwd_blocks(int B, int H, int W) { return cdivb((int64_t)B * H * W, HD_PIX); }
+extern "C" int dsee_head_bwd_blocks(int B, int H, int W) {
+    const int ntiles = B * ((H + HB_TH - 1) / HB_TH) * ((W + HB_TW - 1) / HB_TW);
+    return ntiles < 2 * 148 ? ntiles : 2 * 148;
+}
 
 extern "C" int dsee_head_bwd(const float* x, const float* w, const float* out, const float* dout,
-                             int B, int H, int W, int C, float* dpre, float* dx, float* partial,
-                             float* dw_db, void* stream) {
-    DSEE_CHECK_ARG(x && w && out && dout && dpre && dx && partial && dw_db, "NULL pointer");
-    DSEE_CHECK_ARG(C % 4 == 0 && C <= 1024, "C must be a multiple of 4 and <= 1024");
+                             int B, int H, int W, int C, float* dx, float* partial, float* dw_db,
+                             void* stream) {
+    DSEE_CHECK_ARG(x && w && out && dout && dx && partial && dw_db, "NULL pointer");
+    DSEE_CHECK_ARG(C % 2 == 0 && C >= 4 && C <= 1024, "C must be even, 4..1024");
     int rc = require_sm100();
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n = (int64_t)B * 3 * H * W;
-    head_dpre_kernel<<<cdivb(n, 256), 256, 0, st>>>(dout, out, dpre, n);
-    count_launch();
-    const int64_t nx = (int64_t)B * H * W * (C / 4);
-    head_dx_kernel<<<cdivb(nx, 256), 256, 0, st>>>(x, dpre, w, dx, B, H, W, C);
-    count_launch();
     const int blocks = dsee_head_bwd_blocks(B, H, W);
-    head_dw_kernel<<<blocks, C, 0, st>>>(x, dpre, B, H, W, C, partial);
+    head_bwd_kernel<<<blocks, C / 2, 0, st>>>(x, w, out, dout, B, H, W, C, dx, partial);
     count_launch();
-    reduce_partials_kernel<<<cdivb(C * 28, 32), 256, 0, st>>>(partial, blocks, C * 28, 1, 1.f, dw_db);
+    reduce_partials_kernel<<<dim3(cdivb(C * 28, 32), 1), 1024, 0, st>>>(partial, blocks, C * 28, 1, 1.f,
+                                                                         dw_db);
     LAUNCH_END();
 }

@@ -142,19 +142,23 @@ __global__ void direct_conv_small_kernel(const float* __restrict__ x, const floa
 // ------------------------------------------------------------------------------------------------
 // instance norm (affine=False, eps inside sqrt, biased variance) + activation
 // ------------------------------------------------------------------------------------------------
-// grid (C/32, B), block 256 = 32 channels x 8 pixel lanes; fixed-order reduction.
-__global__ void instnorm_stats_kernel(const float* __restrict__ x, int HW, int C, float eps,
-                                      float* __restrict__ mean, float* __restrict__ rstd) {
+// grid (C/32, B, chunks), block 256 = 32 channels x 8 pixel lanes: per-chunk double partials
+// (sum, sum of squares), then a fixed-order finalize -> deterministic, and enough blocks to fill the
+// GPU even for the 32-channel layers.
+constexpr int IN_CHUNK = 2048;  // pixels per chunk
+__global__ void instnorm_stats_kernel(const float* __restrict__ x, int HW, int C,
+                                      double* __restrict__ partial) {
     __shared__ double sh[8][32][2];
     const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl, b = blockIdx.y;
-    double a = 0.0, q = 0.0;
+    const int p0 = blockIdx.z * IN_CHUNK, p1 = min(p0 + IN_CHUNK, HW);
+    float a = 0.f, q = 0.f;
     if (c < C) {
         const float* p = x + (size_t)b * HW * C + c;
-        for (int i = g; i < HW; i += 8) {
-            float v = __ldg(p + (size_t)i * C);
+        for (int i = p0 + g; i < p1; i += 8) {
+            const float v = __ldg(p + (size_t)i * C);
             a += v;
-            q += (double)v * v;
+            q += v * v;
         }
     }
     sh[g][cl][0] = a;
@@ -166,12 +170,28 @@ __global__ void instnorm_stats_kernel(const float* __restrict__ x, int HW, int C
             A += sh[k][cl][0];
             Q += sh[k][cl][1];
         }
-        double m = A / HW;
-        double var = Q / HW - m * m;
-        if (var < 0) var = 0;
-        mean[(size_t)b * C + c] = (float)m;
-        rstd[(size_t)b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+        double* o = partial + (((size_t)b * gridDim.z + blockIdx.z) * C + c) * 2;
+        o[0] = A;
+        o[1] = Q;
     }
+}
+__global__ void instnorm_finalize_kernel(const double* __restrict__ partial, int chunks, int HW, int C,
+                                         int BC, float eps, float* __restrict__ mean,
+                                         float* __restrict__ rstd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BC) return;
+    const int b = i / C, c = i % C;
+    double A = 0, Q = 0;
+    for (int k = 0; k < chunks; ++k) {
+        const double* o = partial + (((size_t)b * chunks + k) * C + c) * 2;
+        A += o[0];
+        Q += o[1];
+    }
+    const double m = A / HW;
+    double var = Q / HW - m * m;
+    if (var < 0) var = 0;
+    mean[i] = (float)m;
+    rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 // act: 0 none, 1 leaky relu (slope), 2 tanh
@@ -199,7 +219,7 @@ __global__ void instnorm_apply_kernel(const float* __restrict__ x, const float* 
 // region-wise masked mean pooling (encoder.py:36-49): style[b,l,c] = sum_{p: label(p)=l} x[b,p,c] / HW
 // grid (chunks, B); block = C threads (thread owns a channel column -> no smem conflicts).
 // ------------------------------------------------------------------------------------------------
-constexpr int POOL_CHUNK = 1024;
+constexpr int POOL_CHUNK = 256;
 __global__ void region_pool_partial_kernel(const float* __restrict__ x, int ld, int coff,
                                            const uint8_t* __restrict__ labels, int HW, int C, int L,
                                            float* __restrict__ partial) {
@@ -210,7 +230,17 @@ __global__ void region_pool_partial_kernel(const float* __restrict__ x, int ld, 
     const int p1 = min(p0 + POOL_CHUNK, HW);
     const uint8_t* lb = labels + (size_t)b * HW;
     const float* xp = x + (size_t)b * HW * ld + coff + c;
-    for (int p = p0; p < p1; ++p) {
+    int p = p0;
+    for (; p + 4 <= p1; p += 4) {  // 4 independent loads in flight per thread
+        const float v0 = __ldg(xp + (size_t)p * ld), v1 = __ldg(xp + (size_t)(p + 1) * ld);
+        const float v2 = __ldg(xp + (size_t)(p + 2) * ld), v3 = __ldg(xp + (size_t)(p + 3) * ld);
+        const int l0 = lb[p], l1 = lb[p + 1], l2 = lb[p + 2], l3 = lb[p + 3];
+        if (l0 < L) acc[l0 * C + c] += v0;
+        if (l1 < L) acc[l1 * C + c] += v1;
+        if (l2 < L) acc[l2 * C + c] += v2;
+        if (l3 < L) acc[l3 * C + c] += v3;
+    }
+    for (; p < p1; ++p) {
         int l = lb[p];
         if (l < L) acc[l * C + c] += __ldg(xp + (size_t)p * ld);
     }
@@ -324,13 +354,23 @@ extern "C" int dsee_conv2d_direct_fwd(const float* x, const float* w, const floa
     LAUNCH_END();
 }
 
-extern "C" int dsee_instance_norm_fwd(const float* x, float* out, float* mean, float* rstd, int B,
-                                      int HW, int C, float eps, int act, void* stream) {
-    DSEE_CHECK_ARG(x && out && mean && rstd && B > 0 && HW > 0 && C > 0 && C % 4 == 0, "bad argument");
+extern "C" int64_t dsee_instance_norm_workspace_bytes(int B, int HW, int C) {
+    return (int64_t)B * cdiv2(HW, IN_CHUNK) * C * 2 * (int64_t)sizeof(double);
+}
+
+extern "C" int dsee_instance_norm_fwd(const float* x, float* out, float* mean, float* rstd,
+                                      void* workspace, int B, int HW, int C, float eps, int act,
+                                      void* stream) {
+    DSEE_CHECK_ARG(x && out && mean && rstd && workspace && B > 0 && HW > 0 && C > 0 && C % 4 == 0,
+                   "bad argument");
     int rc = require_sm100();
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    instnorm_stats_kernel<<<dim3(cdiv2(C, 32), B), 256, 0, st>>>(x, HW, C, eps, mean, rstd);
+    const int chunks = cdiv2(HW, IN_CHUNK);
+    instnorm_stats_kernel<<<dim3(cdiv2(C, 32), B, chunks), 256, 0, st>>>(x, HW, C, (double*)workspace);
+    count_launch();
+    instnorm_finalize_kernel<<<cdiv2(B * C, 128), 128, 0, st>>>((const double*)workspace, chunks, HW, C,
+                                                                B * C, eps, mean, rstd);
     count_launch();
     int64_t n4 = (int64_t)B * HW * C / 4;
     instnorm_apply_kernel<<<cdiv2(n4, 256), 256, 0, st>>>(x, mean, rstd, out, n4, HW, C, act, 0.2f);
@@ -598,19 +638,21 @@ __device__ __forceinline__ float act_grad(float y, int act, float slope) {
 }
 __global__ void instnorm_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ dout,
                                           const float* __restrict__ mean, const float* __restrict__ rstd,
-                                          int HW, int C, int act, float slope, float* __restrict__ sums) {
+                                          int HW, int C, int act, float slope,
+                                          double* __restrict__ partial) {
     __shared__ double sh[8][32][2];
     const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl, b = blockIdx.y;
-    double s0 = 0.0, s1 = 0.0;
+    const int p0 = blockIdx.z * IN_CHUNK, p1 = min(p0 + IN_CHUNK, HW);
+    float s0 = 0.f, s1 = 0.f;
     if (c < C) {
         const float m = mean[(size_t)b * C + c], r = rstd[(size_t)b * C + c];
         const size_t base = (size_t)b * HW * C + c;
-        for (int i = g; i < HW; i += 8) {
+        for (int i = p0 + g; i < p1; i += 8) {
             const float y = (__ldg(x + base + (size_t)i * C) - m) * r;
             const float gg = __ldg(dout + base + (size_t)i * C) * act_grad(y, act, slope);
             s0 += gg;
-            s1 += (double)gg * y;
+            s1 += gg * y;
         }
     }
     sh[g][cl][0] = s0;
@@ -622,9 +664,24 @@ __global__ void instnorm_bwd_stats_kernel(const float* __restrict__ x, const flo
             a += sh[k][cl][0];
             q += sh[k][cl][1];
         }
-        sums[((size_t)b * C + c) * 2] = (float)(a / HW);
-        sums[((size_t)b * C + c) * 2 + 1] = (float)(q / HW);
+        double* o = partial + (((size_t)b * gridDim.z + blockIdx.z) * C + c) * 2;
+        o[0] = a;
+        o[1] = q;
     }
+}
+__global__ void instnorm_bwd_finalize_kernel(const double* __restrict__ partial, int chunks, int HW,
+                                             int C, int BC, float* __restrict__ sums) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BC) return;
+    const int b = i / C, c = i % C;
+    double a = 0, q = 0;
+    for (int k = 0; k < chunks; ++k) {
+        const double* o = partial + (((size_t)b * chunks + k) * C + c) * 2;
+        a += o[0];
+        q += o[1];
+    }
+    sums[(size_t)i * 2] = (float)(a / HW);
+    sums[(size_t)i * 2 + 1] = (float)(q / HW);
 }
 __global__ void instnorm_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dout,
                                           const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -778,15 +835,20 @@ extern "C" int dsee_channel_sum(const float* x, int64_t npix, int C, float* work
 }
 
 extern "C" int dsee_instance_norm_bwd(const float* x, const float* dout, const float* mean,
-                                      const float* rstd, float* dx, float* sums, int B, int HW, int C,
-                                      int act, void* stream) {
-    DSEE_CHECK_ARG(x && dout && mean && rstd && dx && sums && B > 0 && HW > 0 && C > 0, "bad argument");
+                                      const float* rstd, float* dx, float* sums, void* workspace, int B,
+                                      int HW, int C, int act, void* stream) {
+    DSEE_CHECK_ARG(x && dout && mean && rstd && dx && sums && workspace && B > 0 && HW > 0 && C > 0,
+                   "bad argument");
     DSEE_CHECK_ARG(act >= 0 && act <= 2, "act must be 0, 1 or 2");
     int rc = require_sm100();
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    instnorm_bwd_stats_kernel<<<dim3(cdiv2(C, 32), B), 256, 0, st>>>(x, dout, mean, rstd, HW, C, act,
-                                                                      0.2f, sums);
+    const int chunks = cdiv2(HW, IN_CHUNK);
+    instnorm_bwd_stats_kernel<<<dim3(cdiv2(C, 32), B, chunks), 256, 0, st>>>(
+        x, dout, mean, rstd, HW, C, act, 0.2f, (double*)workspace);
+    count_launch();
+    instnorm_bwd_finalize_kernel<<<cdiv2(B * C, 128), 128, 0, st>>>((const double*)workspace, chunks, HW,
+                                                                    C, B * C, sums);
     count_launch();
     const int64_t n = (int64_t)B * HW * C;
     instnorm_bwd_apply_kernel<<<cdiv2(n, 256), 256, 0, st>>>(x, dout, mean, rstd, sums, dx, n, HW, C,

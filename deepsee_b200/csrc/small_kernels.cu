@@ -317,18 +317,18 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int x_ups, const fl
     }
 }
 
-// grid = C/32 blocks, block = 32 channels x 8 partial lanes; double accumulation, fixed order.
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int n_partials, int C,
+// grid = C/32 blocks, block = 32 channels x 32 partial lanes; double accumulation, fixed order.
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int n_partials, int C,
                                    double count, double ucount, float eps, float momentum,
                                    float* running_mean,
                                    float* running_var, float* bn_scale, float* bn_shift,
                                    float* mean_out, float* var_out) {
-    __shared__ double sh[8][32][2];
+    __shared__ double sh[32][32][2];
     const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
     double a = 0.0, q = 0.0;
     if (c < C) {
-        for (int s = g; s < n_partials; s += 8) {
+        for (int s = g; s < n_partials; s += 32) {
             float2 v = __ldg(reinterpret_cast<const float2*>(partial) + (size_t)s * C + c);
             a += (double)v.x;
             q += (double)v.y;
@@ -339,7 +339,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int n_part
     __syncthreads();
     if (g == 0 && c < C) {
         double A = 0.0, Q = 0.0;
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 32; ++k) {
             A += sh[k][cl][0];
             Q += sh[k][cl][1];
         }
@@ -639,7 +639,7 @@ extern "C" int dsee_bn_finalize(const float* stats_partial, int n_partials, int 
     DSEE_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "running stats mismatch");
     int rc = require_sm100();
     if (rc) return rc;
-    bn_finalize_kernel<<<cdiv(C, 32), 256, 0, (cudaStream_t)stream>>>(
+    bn_finalize_kernel<<<cdiv(C, 32), 1024, 0, (cudaStream_t)stream>>>(
         stats_partial, n_partials, C, count, unbias_count, eps, momentum, running_mean, running_var,
         bn_scale, bn_shift, mean_out, var_out);
     LAUNCH_END();

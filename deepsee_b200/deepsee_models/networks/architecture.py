@@ -71,7 +71,7 @@ def _norm_backward(norm, st, dt, dt_amax, x, x_ups, noise, noise_w, L, passes, w
     dWm = [ops.conv3x3_wgrad(dgb, src, passes=passes) for src in st.srcs]
     dWm = dWm[0] if len(dWm) == 1 else torch.cat(dWm, 1)
     pwT = ops.prep_conv_weight(Wm.contiguous(), want_lo=want_lo, transpose=True)
-    dsrc = ops.conv3x3([dgb], pwT, None, passes=passes, tag="dgrad_mod")
+    dsrc, dsrc_amax = ops.conv3x3([dgb], pwT, None, passes=passes, want_amax=True, tag="dgrad_mod")
     del dgb
     meta = st.meta
     dtab = dtb = dstyle = None
@@ -79,7 +79,9 @@ def _norm_backward(norm, st, dt, dt_amax, x, x_ups, noise, noise_w, L, passes, w
     for src, kind in zip(st.srcs, meta['kinds']):
         d = src.hi.shape[3]
         if kind == 'actv':
-            t, b = ops.shared_mlp_bwd(dsrc, coff, meta['actv'].hi, meta['labels'], meta['ups'], L)
+            onehot = meta['ctx'].onehot_at(*meta['fm'])
+            t, b = ops.shared_mlp_bwd_tc(dsrc, dsrc_amax, coff, meta['actv'].hi, meta['labels'], onehot,
+                                         meta['ups'], L, passes=passes)
             dtab = t if dtab is None else dtab + t
             dtb = b if dtb is None else dtb + b
         else:

@@ -79,6 +79,14 @@ class GenContext:
             self._cache[key] = ops.resize_labels(self.labels_full, h, w)
         return self._cache[key]
 
+    def onehot_at(self, h, w):
+        """fp16 one-hot plane of the label map at (h, w): the second operand of the tensor-core
+        weight gradient of mlp_shared (built on first use in the backward pass)."""
+        key = ('onehot', h, w)
+        if key not in self._cache:
+            self._cache[key] = ops.onehot_planes(self.labels_at(h, w))
+        return self._cache[key]
+
 
 def _interleave_gamma_beta(wg, wb):
     """[C,Cin,3,3] x2 -> [2C,Cin,3,3] with rows [g(0..127) | b(0..127) | g(128..255) | ...]."""
@@ -135,7 +143,7 @@ class _CondNormBase(nn.Module):
             if table is None:
                 table, bias = self.table_and_bias()
             actv = ops.shared_mlp(labels, table.detach(), bias.detach(), ups=ups, want_lo=want_lo)
-        meta = {'labels': labels, 'ups': ups, 'actv': actv}
+        meta = {'labels': labels, 'ups': ups, 'actv': actv, 'fm': (fh, fw), 'ctx': ctx}
         if self.kind == 'spade':
             meta['kinds'] = ['actv']
             return [actv], meta

@@ -384,6 +384,50 @@ def shared_mlp_bwd(dsrc, coff, actv_hi, labels, ups, L):
     return out[:9 * L].view(9, L, nh), out[9 * L]
 
 
+def onehot_planes(labels, Lp=64):
+    """uint8 [B,H,W] -> fp16 one-hot plane [B,H,W,Lp] (exact; the A operand of the table wgrad)."""
+    _chk_cuda(labels)
+    B, H, W = labels.shape
+    out = torch.empty((B, H, W, Lp), dtype=torch.float16, device=labels.device)
+    _lib.check(_lib.load().dsee_onehot_planes(_p(labels), _p(out), B * H * W, Lp, _stream()))
+    return SplitPlanes(out, None)
+
+
+def shared_mlp_bwd_tc(dsrc, dsrc_amax, coff, actv_hi, labels, onehot, ups, L, passes=3):
+    """mlp_shared backward as a tensor-core wgrad against the one-hot plane:
+    -> (dtable [9,L,nh], dbias [nh])."""
+    _chk_cuda(dsrc, dsrc_amax, actv_hi, labels, onehot.hi)
+    B, Hl, Wl = labels.shape
+    nh = actv_hi.shape[3]
+    lib = _lib.load()
+    want_lo = passes == 3
+    hi = torch.empty((B, Hl, Wl, nh), dtype=torch.float16, device=dsrc.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    inv = torch.empty(1, dtype=torch.float32, device=dsrc.device)
+    part = torch.empty((lib.dsee_grad_prep_blocks(B * Hl * Wl), nh, 1), dtype=torch.float32,
+                       device=dsrc.device)
+    _lib.check(lib.dsee_actv_grad_prep(_p(dsrc), dsrc.shape[3], coff, _p(actv_hi), _p(dsrc_amax), B, Hl,
+                                       Wl, ups, nh, _p(hi), _p(lo), _p(inv), _p(part), _stream()))
+    g = GradPlanes(hi, lo, inv)
+    oh = onehot if not want_lo else SplitPlanes(onehot.hi, _zeros_like_cached(onehot.hi))
+    dw = conv3x3_wgrad(g, oh, passes=passes)  # [nh, Lp, 3, 3]
+    dtable = dw[:, :L].permute(2, 3, 1, 0).reshape(9, L, nh)
+    return dtable, reduce_partials(part)[0]
+
+
+_ZERO_CACHE = {}
+
+
+def _zeros_like_cached(t):
+    """An all-zero lo plane for exact operands (the one-hot map), shared across calls."""
+    key = (tuple(t.shape), t.dtype, t.device)
+    z = _ZERO_CACHE.get(key)
+    if z is None:
+        z = torch.zeros_like(t)
+        _ZERO_CACHE[key] = z
+    return z
+
+
 def style_gather_bwd(dsrc, coff, labels, L, d):
     """dstyle[b,l,:] = sum over pixels with label l of dsrc[b,y,x,coff:coff+d]."""
     _chk_cuda(dsrc, labels)
@@ -414,13 +458,12 @@ def head_bwd(x_nhwc, w, out, dout):
     _chk_cuda(x_nhwc, w, out, dout)
     B, H, W, Cc = x_nhwc.shape
     lib = _lib.load()
-    dpre = torch.empty_like(out)
     dx = torch.empty_like(x_nhwc)
     part = torch.empty((lib.dsee_head_bwd_blocks(B, H, W), Cc, 28), dtype=torch.float32,
                        device=dout.device)
     res = torch.empty((Cc, 28), dtype=torch.float32, device=dout.device)
-    _lib.check(lib.dsee_head_bwd(_p(x_nhwc), _p(w), _p(out), _p(dout), B, H, W, Cc, _p(dpre), _p(dx),
-                                 _p(part), _p(res), _stream()))
+    _lib.check(lib.dsee_head_bwd(_p(x_nhwc), _p(w), _p(out), _p(dout), B, H, W, Cc, _p(dx), _p(part),
+                                 _p(res), _stream()))
     dw = res[:, :27].reshape(Cc, 3, 9).permute(1, 0, 2).reshape(3, Cc, 3, 3).contiguous()
     return dx, dw, res[:3, 27].contiguous()
 
@@ -519,8 +562,11 @@ def instance_norm(x, act, eps=1e-5):
     out = torch.empty_like(x)
     mean = torch.empty((B, Cc), dtype=torch.float32, device=x.device)
     rstd = torch.empty_like(mean)
-    _lib.check(_lib.load().dsee_instance_norm_fwd(_p(x), _p(out), _p(mean), _p(rstd), B, H * W, Cc,
-                                                  float(eps), act, _stream()))
+    lib = _lib.load()
+    ws = torch.empty(lib.dsee_instance_norm_workspace_bytes(B, H * W, Cc), dtype=torch.uint8,
+                     device=x.device)
+    _lib.check(lib.dsee_instance_norm_fwd(_p(x), _p(out), _p(mean), _p(rstd), _p(ws), B, H * W, Cc,
+                                          float(eps), act, _stream()))
     return out, mean, rstd
 
 
@@ -807,8 +853,11 @@ class InstanceNormFn(torch.autograd.Function):
         B, H, W, Cc = x.shape
         dx = torch.empty_like(x)
         sums = torch.empty((B, Cc, 2), dtype=torch.float32, device=x.device)
-        _lib.check(_lib.load().dsee_instance_norm_bwd(_p(x), _p(dout), _p(mean), _p(rstd), _p(dx),
-                                                      _p(sums), B, H * W, Cc, ctx.act, _stream()))
+        lib = _lib.load()
+        ws = torch.empty(lib.dsee_instance_norm_workspace_bytes(B, H * W, Cc), dtype=torch.uint8,
+                         device=x.device)
+        _lib.check(lib.dsee_instance_norm_bwd(_p(x), _p(dout), _p(mean), _p(rstd), _p(dx), _p(sums),
+                                              _p(ws), B, H * W, Cc, ctx.act, _stream()))
         return dx, None
 
 

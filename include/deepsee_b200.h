@@ -306,6 +306,17 @@ int dsee_shared_mlp_bwd_blocks(int B, int Hl, int Wl);
 int dsee_shared_mlp_bwd(const float* dsrc, int ld, int coff, const void* actv_hi,
                         const uint8_t* labels, int B, int Hl, int Wl, int ups, int L, int nh,
                         float* partial, float* dtable_dbias, void* stream);
+/* The same gradient on the tensor cores: mlp_shared is a 3x3 conv over the one-hot map, so
+ * d table = dsee_conv3x3_wgrad(G planes, one-hot planes) with
+ *   G[b,yl,xl,o] = relu'(actv) * (sum over the 2^ups x 2^ups copies of dsrc[..., coff+o]),
+ * emitted here as scaled fp16 split planes [B,Hl,Wl,nh] (scale from *dsrc_amax = max|dsrc|, e.g.
+ * dsee_conv_epilogue.amax_out of the kernel that produced dsrc; 2^-e -> inv_scale[0]) together with
+ * block partials fp32 [dsee_grad_prep_blocks(B*Hl*Wl)][nh] of sum G (the bias gradient).
+ * dsee_onehot_planes writes the other operand: fp16 [npix][Lp] (Lp % 8 == 0, zeros beyond L). */
+int dsee_actv_grad_prep(const float* dsrc, int ld, int coff, const void* actv_hi,
+                        const float* dsrc_amax, int B, int Hl, int Wl, int ups, int nh, void* out_hi,
+                        void* out_lo, float* inv_scale, float* partial, void* stream);
+int dsee_onehot_planes(const uint8_t* labels, void* out, int64_t npix, int Lp, void* stream);
 /* Backward of dsee_style_gather_fwd: dstyle[b,l,:] = sum_{p: labels[b,p]==l} dsrc[b,p,coff:coff+d].
  * workspace fp32 [B][dsee_region_pool_chunks(HW)][L][d]. */
 int dsee_style_gather_bwd(const float* dsrc, int ld, int coff, const uint8_t* labels, float* dstyle,
@@ -316,11 +327,11 @@ int dsee_stem_bwd_blocks(int B, int H, int W);
 int dsee_stem_bwd(const float* x, const float* dy, int B, int H, int W, int C, float* partial,
                   float* dw_db, void* stream);
 /* Backward of dsee_head_fwd.  out = the forward result, dout its gradient (NCHW [B,3,H,W]);
- * dpre scratch fp32 [B,3,H,W]; dx fp32 NHWC [B,H,W,C]; partial fp32 [dsee_head_bwd_blocks()][C][28];
+ * dx fp32 NHWC [B,H,W,C]; partial fp32 [dsee_head_bwd_blocks()][C][28];
  * dw_db fp32 [C][28]: [c][o*9+tap] = dW[o][c][tap], [c][27] = dbias[c] for c < 3. */
 int dsee_head_bwd_blocks(int B, int H, int W);
 int dsee_head_bwd(const float* x, const float* w, const float* out, const float* dout, int B, int H,
-                  int W, int C, float* dpre, float* dx, float* partial, float* dw_db, void* stream);
+                  int W, int C, float* dx, float* partial, float* dw_db, void* stream);
 
 /* ---- batch-norm statistics ------------------------------------------------------------------ */
 /* Per-channel sum / sum of squares of x (+ noise) at the post-upsample resolution, written as
@@ -363,9 +374,11 @@ int dsee_conv2d_direct_fwd(const float* x, const float* w, const float* bias, fl
                            int ups, int lrelu, void* stream);
 /* Replaces nn.InstanceNorm2d(affine=False) (normalization.py:48) + the following activation
  * (act: 0 none, 1 LeakyReLU(0.2), 2 tanh; encoder.py:25-26,86). x, out fp32 NHWC [B,HW,C];
- * mean, rstd fp32 [B,C] are kept for the backward pass. */
-int dsee_instance_norm_fwd(const float* x, float* out, float* mean, float* rstd, int B, int HW,
-                           int C, float eps, int act, void* stream);
+ * mean, rstd fp32 [B,C] are kept for the backward pass; workspace:
+ * dsee_instance_norm_workspace_bytes() bytes of per-chunk double partials (deterministic). */
+int64_t dsee_instance_norm_workspace_bytes(int B, int HW, int C);
+int dsee_instance_norm_fwd(const float* x, float* out, float* mean, float* rstd, void* workspace,
+                           int B, int HW, int C, float eps, int act, void* stream);
 /* Replaces AbtractStyleEncoder.extract_style_matrix (encoder.py:36-49):
  * style[b,l,c] = sum_{p : labels[b,p]==l} x[b,p,c] / HW.  workspace fp32
  * [B][dsee_region_pool_chunks(HW)][L][C]. */
@@ -402,9 +415,10 @@ int dsee_conv2d_direct_wgrad(const float* x, const float* dy, float* dw, float* 
 int dsee_channel_sum_chunks(int64_t npix);
 int dsee_channel_sum(const float* x, int64_t npix, int C, float* workspace, float* out, void* stream);
 /* Backward of dsee_instance_norm_fwd: x = the forward INPUT, mean / rstd from the forward;
- * sums scratch fp32 [B][C][2]. */
+ * sums scratch fp32 [B][C][2]; workspace as for the forward. */
 int dsee_instance_norm_bwd(const float* x, const float* dout, const float* mean, const float* rstd,
-                           float* dx, float* sums, int B, int HW, int C, int act, void* stream);
+                           float* dx, float* sums, void* workspace, int B, int HW, int C, int act,
+                           void* stream);
 /* Backward of dsee_region_pool_fwd: dx[b,p,c] = dstyle[b, labels[b,p], c] / HW. */
 int dsee_region_pool_bwd(const float* dstyle, const uint8_t* labels, float* dx, int B, int HW, int C,
                          int L, void* stream);

@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Launches each tensor-core kernel of the generator path ONCE at the shapes of bench.py's default
+workload (c2: 256x256, batch 8, 512 channels; the top block of the generator), for
+`ncu --set full` captures and for CUDA-event timing without the rest of the step around them.
+
+    python profiles/kernels_microbench.py [--passes 1|3] [--reps N] [--B 8] [--S 256]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from deepsee_b200 import ops  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--passes", type=int, default=1)
+    ap.add_argument("--reps", type=int, default=1)
+    ap.add_argument("--B", type=int, default=8)
+    ap.add_argument("--S", type=int, default=256)
+    ap.add_argument("--C", type=int, default=512)
+    a = ap.parse_args()
+    B, S, C, L, nh, d = a.B, a.S, a.C, 19, 128, 128
+    want_lo = a.passes == 3
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(0)
+    rn = lambda *s: torch.randn(*s, generator=g, device=dev)
+    x = rn(B, S, S, C)
+    act = ops.split_f16(rn(B, S, S, C), want_lo)
+    w = rn(C, C, 3, 3) / (3 * C ** 0.5)
+    pw = ops.prep_conv_weight(w, want_lo)
+    pwT = ops.prep_conv_weight(w, want_lo, transpose=True)
+    bias = rn(C)
+    labels = torch.randint(0, L, (B, S, S), generator=g, device=dev, dtype=torch.uint8)
+    table, tb = rn(9, L, nh), rn(nh)
+    actv = ops.shared_mlp(labels, table, tb, want_lo=want_lo)
+    smap = ops.style_gather(labels, rn(B, L, d), want_lo=want_lo)
+    wm = rn(2 * C, nh + d, 3, 3) / (3 * (nh + d) ** 0.5)
+    pwm = ops.prep_conv_weight(wm, want_lo)
+    pwmT = ops.prep_conv_weight(wm, want_lo, transpose=True)
+    wg = wm.view(C // 128, 2, 128, nh + d, 3, 3)[:, 0].reshape(C, nh + d, 3, 3).contiguous()
+    pwg = ops.prep_conv_weight(wg, want_lo)
+    sc, sh, gb, bb = torch.ones(C, device=dev), torch.zeros(C, device=dev), torch.ones(C, device=dev), torch.zeros(C, device=dev)
+    dy = rn(B, S, S, C) * 1e-3
+    gp, _ = ops.grad_prep(dy, want_lo=want_lo)
+    torch.cuda.synchronize()
+
+    def timed(name, fn, flops):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(a.reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.reps
+        print("%-22s %8.3f ms  %7.1f TFLOP/s (reference-equivalent), x%d executed" %
+              (name, ms, flops / ms / 1e9, a.passes))
+        return r
+
+    px = B * S * S
+    torch.cuda.profiler.start()
+    timed("K2 conv3x3 fwd", lambda: ops.conv3x3([act], pw, bias, residual=x, passes=a.passes, want_stats=True),
+          2 * 9 * C * C * px)
+    timed("K1 modulate fwd", lambda: ops.spade_modulate([actv, smap], pwm, x, 0, sc, sh, gb, bb, passes=a.passes,
+                                                        want_lo=want_lo), 2 * 9 * (nh + d) * 2 * C * px)
+    dt, amax = timed("dgrad (K2 bwd-data)", lambda: ops.conv3x3([gp], pwT, None, passes=a.passes, act_mask=act.hi,
+                                                                want_amax=True, tag="dgrad"), 2 * 9 * C * C * px)
+    timed("wgrad 512x512", lambda: ops.conv3x3_wgrad(gp, act, passes=a.passes), 2 * 9 * C * C * px)
+    dxhat, dgb, sums = timed("K1 backward", lambda: ops.spade_modulate_bwd([actv, smap], pwg, x, 0, sc, sh, gb, dt,
+                                                                           amax, passes=a.passes, want_lo=want_lo),
+                             2 * 9 * (nh + d) * C * px)
+    timed("dgrad_mod", lambda: ops.conv3x3([dgb], pwmT, None, passes=a.passes, tag="dgrad_mod"),
+          2 * 9 * (nh + d) * 2 * C * px)
+    timed("wgrad modulation", lambda: ops.conv3x3_wgrad(dgb, actv, passes=a.passes), 2 * 9 * nh * 2 * C * px)
+    torch.cuda.profiler.stop()
+
+
+if __name__ == "__main__":
+    main()

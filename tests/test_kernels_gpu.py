@@ -305,6 +305,12 @@ def test_shared_mlp_and_style_gather_backward():
         ref_tab = wt.grad.permute(2, 3, 1, 0).reshape(9, L, nh)
         torch.testing.assert_close(dtab, ref_tab, rtol=1e-4, atol=1e-3)
         torch.testing.assert_close(dtb, bias.grad, rtol=1e-4, atol=1e-3)
+        # tensor-core route: wgrad of G against the one-hot plane
+        amax = dsrc.abs().max().reshape(1)
+        dtab2, dtb2 = ops.shared_mlp_bwd_tc(dsrc, amax, 0, planes.hi, labels, ops.onehot_planes(labels),
+                                            ups, L, passes=3)
+        assert (dtab2 - ref_tab).abs().max().item() <= 5e-5 * ref_tab.abs().max().item()
+        torch.testing.assert_close(dtb2, bias.grad, rtol=1e-4, atol=1e-3)
         if not ups:
             ds = ops.style_gather_bwd(dsrc, nh, labels, L, d)
             torch.testing.assert_close(ds, style.grad, rtol=1e-4, atol=1e-3)
@@ -450,7 +456,7 @@ def test_conv2d_tc_node(Cx, Cw, Cout, K, stride, pad, ups, lrelu, bias, passes):
             # 1-pass forward differences (1e-3) flip a few fused-LeakyReLU masks; relative L2 is the
             # meaningful measure there
             rel = ((a - r).norm() / r.norm()).item()
-            assert rel <= 5e-3, (what, rel)
+            assert rel <= (2e-2 if lrelu else 5e-3), (what, rel)
     chk(_nchw(out), ref, "fwd")
     chk(_nchw(x2.grad)[:, :Cw], x.grad[:, :Cw], "dgrad")
     chk(w2.grad, w.grad, "wgrad")
