@@ -260,6 +260,9 @@ def main():
                "d2h_bytes_per_step": 4 * len(last), "last_losses": last}
     sampler.stop_flag = True
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
 
@@ -324,7 +327,7 @@ def main():
         line["cpu_baseline"] = {"value": n / dt, "unit": "images/sec", "cores": cores, "kind": "port",
                                 "sample": "%d training iteration(s) at batch 1 of the same workload "
                                           "(oracle port of trainer_manager.py:32-61, torch CPU fp32)" % n}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdeepsee_b200.so")
+LIB_PATH = os.environ.get("DSEE_LIB_PATH") or os.path.join(_HERE, "lib", "libdeepsee_b200.so")
 
 # every symbol include/deepsee_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [

@@ -26,11 +26,17 @@ namespace dsee {
 
 constexpr int WG_M = 128;        // dY channels per unit
 constexpr int WG_NMAX = 256;     // activation channels per unit
-constexpr int WG_KPIX = 128;     // pixels per K step (8 x 16 tile)
-constexpr int WG_TW = 16, WG_TH = 8;
-constexpr int WG_BOX_BYTES = WG_KPIX * 64 * 2;                 // 16 KB: 128 pixel rows x 64 ch
-constexpr int WG_STAGE_BYTES = (WG_M / 64 + WG_NMAX / 64) * WG_BOX_BYTES;  // 96 KB
-constexpr int WG_STAGES = 2;
+#ifndef DSEE_WG_TH
+#define DSEE_WG_TH 8
+#endif
+#ifndef DSEE_WG_STAGES
+#define DSEE_WG_STAGES 2
+#endif
+constexpr int WG_TW = 16, WG_TH = DSEE_WG_TH;
+constexpr int WG_KPIX = WG_TW * WG_TH;                         // pixels per K step
+constexpr int WG_BOX_BYTES = WG_KPIX * 64 * 2;                 // pixel rows x 64 ch
+constexpr int WG_STAGE_BYTES = (WG_M / 64 + WG_NMAX / 64) * WG_BOX_BYTES;
+constexpr int WG_STAGES = DSEE_WG_STAGES;
 constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
 constexpr int WG_THREADS = 192;
 

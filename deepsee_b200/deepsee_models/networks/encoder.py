@@ -108,8 +108,9 @@ class FullStyleEncoder(AbtractStyleEncoder):
             self.max_range_noise = self.opt.noisy_style_scale
 
     def forward_main(self, x_nchw):
-        x = ops.nchw_to_nhwc(x_nchw.contiguous().float(), 4)
-        x = _stage(x, self.initial[0], pad_cin=4)
+        # RGB zero-padded to 16 channels: the narrowest input the tensor-core conv takes
+        x = ops.nchw_to_nhwc(x_nchw.contiguous().float(), 16)
+        x = _stage(x, self.initial[0])
         x = _stage(x, self.down0[0], stride=2)
         x = _stage(x, self.down1[0], stride=2)
         x = _stage(x, self.up_conv[1], ups=1)
@@ -144,8 +145,8 @@ class MinistyleEncoder(AbtractStyleEncoder):
             self.add_module(name, module)
 
     def forward_main(self, x_nchw):
-        x = ops.nchw_to_nhwc(x_nchw.contiguous().float(), 4)
-        x = _stage(x, self.initial[0], pad_cin=4)
+        x = ops.nchw_to_nhwc(x_nchw.contiguous().float(), 16)
+        x = _stage(x, self.initial[0])
         x = _stage(x, self.conv0[0])
         x = _stage(x, self.conv1[0])
         x = _stage(x, self.conv2[1], ups=1)

@@ -804,6 +804,13 @@ def conv_layer(x, w, bias, stride, pad, ups=0, lrelu=False):
     kernels. w in PyTorch layout [N,Cw,KH,KW] (autograd tensor)."""
     if tc_conv_eligible(x.shape[3], w.shape[0]):
         return Conv2dTCFn.apply(x, w, bias, stride, pad, ups, lrelu)
+    if tc_conv_eligible(x.shape[3], 32) and w.shape[0] < 32:
+        # narrow outputs (the discriminator's 1-channel prediction conv): zero-pad the filter bank to
+        # the 32 columns the tensor-core epilogue stores and slice; autograd un-pads the gradients
+        n = w.shape[0]
+        wp = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, 32 - n))
+        bp = torch.nn.functional.pad(bias, (0, 32 - n)) if bias is not None else None
+        return Conv2dTCFn.apply(x, wp, bp, stride, pad, ups, lrelu)[..., :n].contiguous()
     wk = w.permute(2, 3, 1, 0)
     if x.shape[3] > wk.shape[2]:
         wk = torch.nn.functional.pad(wk, (0, 0, 0, x.shape[3] - wk.shape[2]))
