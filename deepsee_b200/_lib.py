@@ -18,8 +18,8 @@ SYMBOLS = [
     "dsee_prep_conv_weight", "dsee_split_f16", "dsee_prep_conv_weight_ex", "dsee_split_f16_ups2",
     "dsee_fold2x2", "dsee_conv2d_tc", "dsee_conv2d_tc_wgrad_workspace_floats", "dsee_conv2d_tc_wgrad",
     "dsee_conv3x3_fwd", "dsee_conv3x3_stats_tiles", "dsee_spade_modulate_fwd",
-    "dsee_spade_modulate_bwd", "dsee_grad_prep_blocks", "dsee_grad_prep", "dsee_reduce_partials",
-    "dsee_conv3x3_wgrad_workspace_floats", "dsee_conv3x3_wgrad", "dsee_bn_bwd_blocks", "dsee_bn_bwd",
+    "dsee_spade_modulate_bwd", "dsee_spade_modulate_bwd_saved", "dsee_grad_prep_blocks", "dsee_grad_prep", "dsee_reduce_partials",
+    "dsee_conv3x3_wgrad_workspace_floats", "dsee_conv3x3_wgrad", "dsee_conv3x3_wgrad2", "dsee_bn_bwd_blocks", "dsee_bn_bwd",
     "dsee_actv_grad_prep", "dsee_onehot_planes", "dsee_shared_mlp_bwd_blocks", "dsee_shared_mlp_bwd", "dsee_style_gather_bwd",
     "dsee_stem_bwd_blocks", "dsee_stem_bwd", "dsee_head_bwd_blocks", "dsee_head_bwd",
     "dsee_bn_stats", "dsee_bn_finalize", "dsee_bn_eval_affine",
@@ -58,7 +58,7 @@ class ModulateArgs(C.Structure):
         ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
         ("gamma_bias", C.c_void_p), ("beta_bias", C.c_void_p),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
-        ("C", C.c_int),
+        ("C", C.c_int), ("g_hi", C.c_void_p), ("g_lo", C.c_void_p),
     ]
 
 
@@ -120,10 +120,14 @@ def load():
         "dsee_conv3x3_stats_tiles": [i, i, i],
         "dsee_spade_modulate_fwd": [C.POINTER(ConvOperands), C.POINTER(ModulateArgs), vp],
         "dsee_spade_modulate_bwd": [C.POINTER(ConvOperands), C.POINTER(ModulateBwdArgs), vp],
+        "dsee_spade_modulate_bwd_saved": [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp,
+                                          vp, vp, vp],
         "dsee_grad_prep_blocks": [i64],
         "dsee_grad_prep": [vp, vp, vp, vp, vp, vp, i64, i, vp, vp],
         "dsee_reduce_partials": [vp, i, i, i, f, vp, vp],
         "dsee_conv3x3_wgrad": [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp, i, vp],
+        "dsee_conv3x3_wgrad2": [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i), i, i, i, i, i, i,
+                                vp, vp, i, vp],
         "dsee_bn_bwd_blocks": [i, i, i],
         "dsee_bn_bwd": [vp, vp, i, vp, vp, vp, vp, vp, f, vp, i, i, i, i, vp, vp, vp],
         "dsee_actv_grad_prep": [vp, i, i, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp],

@@ -7,6 +7,12 @@ class _Config:
     #   3 = hi*hi + lo*hi + hi*lo  (fp32-class accuracy; the parity default)
     #   1 = hi*hi                  (fp16 operands = TF32-class accuracy, 3x fewer MMAs)
     passes = int(os.environ.get("DSEE_PASSES", "3"))
+    # Training: K1 saves G = gamma + gamma_bias (fp16 planes, +1-2 B per activation element) so its
+    # backward is one streaming pass instead of re-running the gamma GEMM (0 = recompute).
+    save_gamma = os.environ.get("DSEE_SAVE_GAMMA", "1") != "0"
+    # Issue the weight-gradient GEMMs of the generator on a second stream (they are leaves of the
+    # backward graph) so the HBM-bound kernels of the chain overlap with them.
+    overlap_wgrad = os.environ.get("DSEE_OVERLAP_WGRAD", "1") != "0"
     # Verify (one device->host read per generator forward) that the semantic input is one-hot.
     check_onehot = os.environ.get("DSEE_CHECK_ONEHOT", "1") != "0"
 

@@ -84,6 +84,114 @@ __global__ void grad_prep_kernel(const float* __restrict__ dy, __half* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1 backward from saved G = gamma + gamma_bias (fp16 planes): with xhat = xin*sc + sh,
+//   dxhat = dt * G,  dG = dt * xhat,  dB = dt   (dG|dB as scaled fp16 planes, channels interleaved
+//   per 128 like the modulation weight rows) + block partials (sum dxhat, sum dxhat*xhat, sum dG,
+//   sum dB).  thread = (pixel lane, 4 channels); GP_PIX pixels per block.
+// ------------------------------------------------------------------------------------------------
+__global__ void modulate_bwd_saved_kernel(const float* __restrict__ x, int x_ups,
+                                          const float* __restrict__ noise, const float* __restrict__ noise_w,
+                                          const float* __restrict__ sc, const float* __restrict__ sh,
+                                          const __half* __restrict__ g_hi, const __half* __restrict__ g_lo,
+                                          const float* __restrict__ dt, const float* __restrict__ dt_amax,
+                                          int B, int H, int W, int C, float* __restrict__ dxhat,
+                                          __half* __restrict__ dgb_hi, __half* __restrict__ dgb_lo,
+                                          float* __restrict__ dgb_inv_scale, float* __restrict__ partial) {
+    extern __shared__ float red[];  // [lanes][C][4]
+    const int cg = C >> 2;
+    const int lanes = blockDim.x / cg;
+    const int g = threadIdx.x % cg, pl = threadIdx.x / cg;
+    const float gscale = pow2_scale_for(__ldg(dt_amax), 10);  // 2^6 headroom for |xhat|
+    if (blockIdx.x == 0 && threadIdx.x == 0) *dgb_inv_scale = 1.f / gscale;
+    const int64_t npix = (int64_t)B * H * W;
+    const int64_t p0 = (int64_t)blockIdx.x * GP_PIX;
+    const int Hx = H >> x_ups, Wx = W >> x_ups;
+    float s[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[k][e] = 0.f;
+    if (pl < lanes) {
+        const float4 scv = __ldg(reinterpret_cast<const float4*>(sc) + g);
+        const float4 shv = __ldg(reinterpret_cast<const float4*>(sh) + g);
+        float4 nw = make_float4(0, 0, 0, 0);
+        if (noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
+        const int c = g * 4;
+        const int ng = (c >> 7) * 256 + (c & 127);  // interleaved position of channel c
+        for (int i = pl; i < GP_PIX; i += lanes) {
+            const int64_t pix = p0 + i;
+            if (pix >= npix) break;
+            const int xx = (int)(pix % W);
+            const int yy = (int)((pix / W) % H);
+            const int b = (int)(pix / ((int64_t)W * H));
+            const size_t xp = ((size_t)b * Hx + (yy >> x_ups)) * Wx + (xx >> x_ups);
+            float4 xv = __ldg(reinterpret_cast<const float4*>(x + xp * C) + g);
+            if (noise) {
+                const float4 nv = __ldg(reinterpret_cast<const float4*>(noise + (size_t)pix * C) + g);
+                xv.x += nw.x * nv.x; xv.y += nw.y * nv.y; xv.z += nw.z * nv.z; xv.w += nw.w * nv.w;
+            }
+            const float xh[4] = {xv.x * scv.x + shv.x, xv.y * scv.y + shv.y, xv.z * scv.z + shv.z,
+                                 xv.w * scv.w + shv.w};
+            const float4 dv = __ldg(reinterpret_cast<const float4*>(dt + (size_t)pix * C) + g);
+            const float d[4] = {dv.x, dv.y, dv.z, dv.w};
+            const uint2 gh = __ldg(reinterpret_cast<const uint2*>(g_hi + (size_t)pix * C) + g);
+            float G[4];
+            G[0] = __half2float(__ushort_as_half((unsigned short)(gh.x & 0xffffu)));
+            G[1] = __half2float(__ushort_as_half((unsigned short)(gh.x >> 16)));
+            G[2] = __half2float(__ushort_as_half((unsigned short)(gh.y & 0xffffu)));
+            G[3] = __half2float(__ushort_as_half((unsigned short)(gh.y >> 16)));
+            if (g_lo) {
+                const uint2 gl = __ldg(reinterpret_cast<const uint2*>(g_lo + (size_t)pix * C) + g);
+                G[0] += __half2float(__ushort_as_half((unsigned short)(gl.x & 0xffffu)));
+                G[1] += __half2float(__ushort_as_half((unsigned short)(gl.x >> 16)));
+                G[2] += __half2float(__ushort_as_half((unsigned short)(gl.y & 0xffffu)));
+                G[3] += __half2float(__ushort_as_half((unsigned short)(gl.y >> 16)));
+            }
+            float dxh[4], dG[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                dxh[e] = d[e] * G[e];
+                dG[e] = d[e] * xh[e];
+                s[0][e] += dxh[e];
+                s[1][e] += dxh[e] * xh[e];
+                s[2][e] += dG[e];
+                s[3][e] += d[e];
+            }
+            reinterpret_cast<float4*>(dxhat + (size_t)pix * C)[g] = make_float4(dxh[0], dxh[1], dxh[2], dxh[3]);
+            __half* rowh = dgb_hi + (size_t)pix * 2 * C + ng;
+            __half* rowl = dgb_lo ? dgb_lo + (size_t)pix * 2 * C + ng : nullptr;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const float* src = half ? d : dG;
+                uint32_t ph[2], plw[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float s0 = fminf(fmaxf(src[2 * e] * gscale, -65504.f), 65504.f);
+                    const float s1 = fminf(fmaxf(src[2 * e + 1] * gscale, -65504.f), 65504.f);
+                    const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
+                    const __half l0 = __float2half_rn(s0 - __half2float(h0));
+                    const __half l1 = __float2half_rn(s1 - __half2float(h1));
+                    ph[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                    plw[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                }
+                *reinterpret_cast<uint2*>(rowh + half * 128) = make_uint2(ph[0], ph[1]);
+                if (rowl) *reinterpret_cast<uint2*>(rowl + half * 128) = make_uint2(plw[0], plw[1]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) red[((size_t)pl * C + g * 4 + e) * 4 + k] = s[k][e];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * 4; i += blockDim.x) {
+        float a = 0.f;
+        for (int l = 0; l < lanes; ++l) a += red[(size_t)l * C * 4 + i];
+        partial[(size_t)blockIdx.x * C * 4 + i] = a;
+    }
+}
+
 // out[k][c] = sum_s partial[s][c][k] (double, fixed order). grid = (C/32, nq), block = 32 x 32.
 __global__ void __launch_bounds__(1024)
 reduce_partials_kernel(const float* __restrict__ partial, int n, int C, int nq, float scale,
@@ -457,6 +565,28 @@ extern "C" int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, float
     grad_prep_kernel<<<cdivb(npix, GP_PIX), 256, sm, st>>>(dy, (__half*)out_hi, (__half*)out_lo,
                                                            inv_scale, noise0, noise1, npix, C, partial,
                                                            nq);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_spade_modulate_bwd_saved(const float* x, int x_ups, const float* noise,
+                                             const float* noise_w, const float* bn_scale,
+                                             const float* bn_shift, const void* g_hi, const void* g_lo,
+                                             const float* dt, const float* dt_amax, int B, int H, int W,
+                                             int C, float* dxhat, void* dgb_hi, void* dgb_lo,
+                                             float* dgb_inv_scale, float* partial, void* stream) {
+    DSEE_CHECK_ARG(x && bn_scale && bn_shift && g_hi && dt && dt_amax && dxhat && dgb_hi && dgb_inv_scale &&
+                       partial,
+                   "NULL pointer");
+    DSEE_CHECK_ARG(C % 128 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "C must be 128, 256, 512 or 1024");
+    DSEE_CHECK_ARG((x_ups == 0 || x_ups == 1) && (noise == nullptr) == (noise_w == nullptr), "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int64_t npix = (int64_t)B * H * W;
+    const int lanes = 256 / (C / 4);
+    const size_t sm = (size_t)lanes * C * 4 * sizeof(float);
+    modulate_bwd_saved_kernel<<<cdivb(npix, GP_PIX), 256, sm, (cudaStream_t)stream>>>(
+        x, x_ups, noise, noise_w, bn_scale, bn_shift, (const __half*)g_hi, (const __half*)g_lo, dt, dt_amax,
+        B, H, W, C, dxhat, (__half*)dgb_hi, (__half*)dgb_lo, dgb_inv_scale, partial);
     LAUNCH_END();
 }
 

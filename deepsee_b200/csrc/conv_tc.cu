@@ -84,6 +84,8 @@ struct alignas(64) ConvParams {
     const float* beta_bias;
     __half* out_hi;
     __half* out_lo;
+    __half* g_hi;  // optional: G = gamma + gamma_bias saved for the backward pass (fp16 planes)
+    __half* g_lo;
     int C;
     // EPI_MODULATE_BWD
     const float* dt;         // fp32 NHWC [B,H,W,C]: gradient wrt the pre-activation t
@@ -456,6 +458,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                 const float* nrow = p.noise ? p.noise + pix * p.C : nullptr;
                 __half* hrow = p.out_hi + pix * p.C;
                 __half* lrow = p.out_lo ? p.out_lo + pix * p.C : nullptr;
+                __half* ghrow = p.g_hi ? p.g_hi + pix * p.C : nullptr;
+                __half* glrow = p.g_lo ? p.g_lo + pix * p.C : nullptr;
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
                     const int c = c0 + ch * 32;
@@ -466,7 +470,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                     if (valid) {
 #pragma unroll
                         for (int j8 = 0; j8 < 4; ++j8) {
-                            float a[8];
+                            float a[8], gsave[8];
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
                                 const int j = j8 * 8 + h * 4;
@@ -489,9 +493,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                                                __ldg(p.beta_bias + cc);
                                     float t = xh * G + Bv;
                                     a[h * 4 + e] = t > 0.f ? t : 0.2f * t;
+                                    gsave[h * 4 + e] = G;
                                 }
                             }
                             store_split8(hrow + c + j8 * 8, lrow ? lrow + c + j8 * 8 : nullptr, a);
+                            if (ghrow)
+                                store_split8(ghrow + c + j8 * 8, glrow ? glrow + c + j8 * 8 : nullptr, gsave);
                         }
                     }
                 }
@@ -794,6 +801,8 @@ extern "C" int dsee_spade_modulate_fwd(const dsee_conv_operands* ops, const dsee
     p.beta_bias = mod->beta_bias;
     p.out_hi = (__half*)mod->out_hi;
     p.out_lo = (__half*)mod->out_lo;
+    p.g_hi = (__half*)mod->g_hi;
+    p.g_lo = (__half*)mod->g_lo;
     p.C = mod->C;
     return launch<EPI_MODULATE>(p, (cudaStream_t)stream);
 }

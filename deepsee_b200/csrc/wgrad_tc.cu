@@ -43,6 +43,8 @@ constexpr int WG_THREADS = 192;
 struct alignas(64) WgradParams {
     CUtensorMap tmD[2];  // dY planes (hi, lo)
     CUtensorMap tmA[2];  // activation planes (hi, lo)
+    CUtensorMap tmA2[2]; // optional second activation source (channels c_split .. c_total)
+    int c_split;         // channels taken from the first source (== c_total when there is one)
     int B, H, W;
     int tiles_w, tiles_h, ptiles;  // pixel tiles
     int n_total, c_total;
@@ -140,10 +142,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                         for (int i = 0; i < WG_M / 64; ++i)
                             tma_load_4d(&p.tmD[pd], &full_bar[s], sd + i * WG_BOX_BYTES,
                                         nt * WG_M + i * 64, w0, h0, b);
-                        for (int i = 0; i < nboxA; ++i)
-                            tma_load_4d(&p.tmA[pa], &full_bar[s], sa + i * WG_BOX_BYTES,
-                                        ct * WG_NMAX + i * 64, w0 * p.a_step + dx, h0 * p.a_step + dy,
-                                        b);
+                        for (int i = 0; i < nboxA; ++i) {
+                            const int c = ct * WG_NMAX + i * 64;
+                            const bool second = c >= p.c_split;
+                            tma_load_4d(second ? &p.tmA2[pa] : &p.tmA[pa], &full_bar[s],
+                                        sa + i * WG_BOX_BYTES, second ? c - p.c_split : c,
+                                        w0 * p.a_step + dx, h0 * p.a_step + dy, b);
+                        }
                     }
                 }
             }
@@ -278,7 +283,8 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
                       const void* a_lo, const float* a_inv_scale, int dtype, int B, int H, int W,
                       int Hi, int Wi, int n_total, int a_channels, int c_total, int KH, int KW,
                       int stride, int pad, int passes, float* workspace, float* dw, int layout_nc9,
-                      void* stream) {
+                      void* stream, const void* a2_hi = nullptr, const void* a2_lo = nullptr,
+                      int a2_channels = 0) {
     // H, W: dY (= forward output) size; Hi, Wi: activation (= forward input) size;
     // a_channels: channels stored in the activation planes, c_total: dW columns (a multiple of 64)
     const int T = KH * KW;
@@ -293,6 +299,7 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
     p.tiles_h = (H + WG_TH - 1) / WG_TH;
     p.n_total = n_total;
     p.c_total = c_total;
+    p.c_split = a2_channels > 0 ? a_channels : c_total;
     p.ntaps = T;
     p.a_step = stride;
     for (int t = 0; t < T; ++t) {
@@ -334,6 +341,16 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
         } else {
             p.tmA[pl] = p.tmA[0];
         }
+        const void* a2 = pl ? a2_lo : a2_hi;
+        if (a2 && a2_channels > 0) {
+            uint64_t dims[4] = {(uint64_t)a2_channels, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
+            uint64_t st[3] = {(uint64_t)a2_channels * 2, (uint64_t)Wi * a2_channels * 2,
+                              (uint64_t)Hi * Wi * a2_channels * 2};
+            rc = encode_tmap_16b(&p.tmA2[pl], a2, 4, dims, st, boxa, dtype == 1, esa);
+            if (rc) return rc;
+        } else {
+            p.tmA2[pl] = p.tmA[pl];
+        }
     }
     static bool configured[64] = {false};
     int dev = 0;
@@ -371,6 +388,27 @@ extern "C" int dsee_conv3x3_wgrad(const void* dy_hi, const void* dy_lo, const fl
     DSEE_CHECK_ARG(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
     return wgrad_impl(dy_hi, dy_lo, dy_inv_scale, a_hi, a_lo, a_inv_scale, dtype, B, H, W, H, W, n_total,
                       c_total, c_total, 3, 3, 1, 1, passes, workspace, dw, layout_nc9, stream);
+}
+
+extern "C" int dsee_conv3x3_wgrad2(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale,
+                                   const void* const* a_hi, const void* const* a_lo,
+                                   const int* a_channels, int dtype, int B, int H, int W, int n_total,
+                                   int passes, float* workspace, float* dw, int layout_nc9, void* stream) {
+    DSEE_CHECK_ARG(dy_hi && a_hi && a_channels && a_hi[0] && workspace && dw, "NULL pointer");
+    DSEE_CHECK_ARG(B > 0 && H > 0 && W > 0, "bad geometry");
+    DSEE_CHECK_ARG(n_total % 128 == 0, "n_total must be a multiple of 128 (got %d)", n_total);
+    DSEE_CHECK_ARG(a_channels[0] > 0 && a_channels[0] % 64 == 0 && a_channels[1] >= 0 &&
+                       a_channels[1] % 64 == 0 && (a_channels[1] == 0 || a_hi[1]),
+                   "source channel counts must be multiples of 64");
+    const int c_total = a_channels[0] + a_channels[1];
+    DSEE_CHECK_ARG(c_total == 64 || c_total == 128 || c_total % 256 == 0,
+                   "total channels must be 64, 128 or a multiple of 256 (got %d)", c_total);
+    DSEE_CHECK_ARG(passes == 1 || (passes == 3 && dy_lo && a_lo && a_lo[0] && (a_channels[1] == 0 || a_lo[1])),
+                   "passes must be 1, or 3 with lo planes");
+    DSEE_CHECK_ARG(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+    return wgrad_impl(dy_hi, dy_lo, dy_inv_scale, a_hi[0], a_lo ? a_lo[0] : nullptr, nullptr, dtype, B, H,
+                      W, H, W, n_total, a_channels[0], c_total, 3, 3, 1, 1, passes, workspace, dw,
+                      layout_nc9, stream, a_hi[1], a_lo ? a_lo[1] : nullptr, a_channels[1]);
 }
 
 extern "C" int64_t dsee_conv2d_tc_wgrad_workspace_floats(int B, int Ho, int Wo, int n_total, int Ci,

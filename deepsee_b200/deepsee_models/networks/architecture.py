@@ -32,13 +32,44 @@ from .normalization import (SPADE, SEAN_Block, PureSEAN_Block, NoiseInjection, e
 BN_MOMENTUM = 0.1
 
 
+_SIDE = {}
+
+
+class _SideStream:
+    """Weight-gradient GEMMs are leaves of the backward graph: nothing in the block's backward chain
+    reads them.  They are issued on a second CUDA stream so the HBM-bound kernels of the chain
+    (K1 backward, batch-norm backward, gradient splitting) run underneath them instead of between
+    tensor-core kernels.  Tensors the side stream reads are kept alive in ``keep`` until the main
+    stream has waited for it (`join`)."""
+
+    def __init__(self):
+        dev = torch.cuda.current_device()
+        if dev not in _SIDE:
+            _SIDE[dev] = torch.cuda.Stream(device=dev)
+        self.side = _SIDE[dev] if config.overlap_wgrad else None
+        self.keep = []
+
+    def run(self, fn, *tensors):
+        if self.side is None:
+            return fn()
+        self.keep.extend(tensors)
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            return fn()
+
+    def join(self):
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        self.keep.clear()
+
+
 class _NormState:
     """What K1's backward needs from one conditional-norm layer's forward."""
-    __slots__ = ("srcs", "meta", "Wm", "gb", "sc", "sh", "inv_count")
+    __slots__ = ("srcs", "meta", "Wm", "gb", "sc", "sh", "inv_count", "g")
 
 
 def _norm_forward(blk, norm, pre, Wm, gb, bb, tab, tb, gctx, style, x, x_ups, H, W, part, count,
-                  ucount, noise, noise_w, passes, want_lo):
+                  ucount, noise, noise_w, passes, want_lo, save_g):
     """BN affine + sources + K1 -> (activation planes, _NormState)."""
     st = _NormState()
     bn = norm.param_free_norm
@@ -53,23 +84,29 @@ def _norm_forward(blk, norm, pre, Wm, gb, bb, tab, tb, gctx, style, x, x_ups, H,
     pw = pre if pre is not None else ops.prep_conv_weight(Wm.contiguous(), want_lo=want_lo)
     st.srcs, st.meta = norm.build_sources(gctx, style, H, W, want_lo, table=tab, bias=tb)
     st.Wm, st.gb = Wm, gb
-    a = ops.spade_modulate(st.srcs, pw, x, x_ups, st.sc, st.sh, gb, bb, noise=noise, noise_w=noise_w,
-                           passes=passes, want_lo=want_lo)
+    r = ops.spade_modulate(st.srcs, pw, x, x_ups, st.sc, st.sh, gb, bb, noise=noise, noise_w=noise_w,
+                           passes=passes, want_lo=want_lo, save_g=save_g)
+    a, st.g = r if save_g else (r, None)
     return a, st
 
 
-def _norm_backward(norm, st, dt, dt_amax, x, x_ups, noise, noise_w, L, passes, want_lo):
+def _norm_backward(norm, st, dt, dt_amax, x, x_ups, noise, noise_w, L, passes, want_lo, ss):
     """K1 backward for one layer -> (dxhat, sums[4,C], dWm, dtab, dtb, dstyle)."""
     C = x.shape[3]
     Wm = st.Wm
     cin = Wm.shape[1]
-    w_gamma = Wm.view(C // 128, 2, 128, cin, 3, 3)[:, 0].reshape(C, cin, 3, 3).contiguous()
-    pwg = ops.prep_conv_weight(w_gamma, want_lo=want_lo)
-    dxhat, dgb, sums = ops.spade_modulate_bwd(st.srcs, pwg, x, x_ups, st.sc, st.sh, st.gb, dt, dt_amax,
-                                              noise=noise, noise_w=noise_w, passes=passes,
-                                              want_lo=want_lo)
-    dWm = [ops.conv3x3_wgrad(dgb, src, passes=passes) for src in st.srcs]
-    dWm = dWm[0] if len(dWm) == 1 else torch.cat(dWm, 1)
+    if st.g is not None:
+        # G = gamma + gamma_bias was saved by the forward kernel: one streaming pass, no GEMM
+        dxhat, dgb, sums = ops.spade_modulate_bwd_saved(st.g, x, x_ups, st.sc, st.sh, dt, dt_amax,
+                                                        noise=noise, noise_w=noise_w, want_lo=want_lo)
+        st.g = None
+    else:
+        w_gamma = Wm.view(C // 128, 2, 128, cin, 3, 3)[:, 0].reshape(C, cin, 3, 3).contiguous()
+        pwg = ops.prep_conv_weight(w_gamma, want_lo=want_lo)
+        dxhat, dgb, sums = ops.spade_modulate_bwd(st.srcs, pwg, x, x_ups, st.sc, st.sh, st.gb, dt,
+                                                  dt_amax, noise=noise, noise_w=noise_w, passes=passes,
+                                                  want_lo=want_lo)
+    dWm = ss.run(lambda: ops.conv3x3_wgrad_multi(dgb, st.srcs, passes=passes), dgb, *st.srcs)
     pwT = ops.prep_conv_weight(Wm.contiguous(), want_lo=want_lo, transpose=True)
     dsrc, dsrc_amax = ops.conv3x3([dgb], pwT, None, passes=passes, want_amax=True, tag="dgrad_mod")
     del dgb
@@ -81,8 +118,8 @@ def _norm_backward(norm, st, dt, dt_amax, x, x_ups, noise, noise_w, L, passes, w
         if kind == 'actv':
             onehot = meta['ctx'].onehot_at(*meta['fm'])
             t, b = ops.shared_mlp_bwd_tc(dsrc, dsrc_amax, coff, meta['actv'].hi, meta['labels'], onehot,
-                                         meta['ups'], L, passes=passes)
-            dtab = t if dtab is None else dtab + t
+                                         meta['ups'], L, passes=passes, side=ss)
+            dtab = t if dtab is None else ss.run(lambda: dtab + t)  # t lives on the side stream
             dtb = b if dtb is None else dtb + b
         else:
             g = ops.style_gather_bwd(dsrc, coff, meta['labels'], L, d)
@@ -105,6 +142,7 @@ class _ResBlockFn(torch.autograd.Function):
         n_in, n_skip, n_mid = noises if noises is not None else (None, None, None)
         noisy = noises is not None
         pre = pre or {}
+        save_g = any(ctx.needs_input_grad) and config.save_gamma
 
         # ---- norm_0 + actvn -------------------------------------------------------------------
         part = None
@@ -118,7 +156,7 @@ class _ResBlockFn(torch.autograd.Function):
                 count = ucount = B * H * W
         a0, st0 = _norm_forward(blk, blk.norm_0, pre.get('pwm0'), Wm0, gb0, bb0, tab0, tb0, gctx,
                                 style, x, ups, H, W, part, count, ucount, n_in,
-                                nw_in if noisy else None, passes, want_lo)
+                                nw_in if noisy else None, passes, want_lo, save_g)
         # ---- conv_0 (+ noise_middle) ----------------------------------------------------------
         pw0 = pre.get('pw0') or ops.prep_conv_weight(W0.contiguous(), want_lo=want_lo)
         r = ops.conv3x3([a0], pw0, b0, noises=[(n_mid, nw_mid)] if noisy else (), passes=passes,
@@ -127,7 +165,7 @@ class _ResBlockFn(torch.autograd.Function):
         # ---- norm_1 + actvn -------------------------------------------------------------------
         a1, st1 = _norm_forward(blk, blk.norm_1, pre.get('pwm1'), Wm1, gb1, bb1, tab1, tb1, gctx,
                                 style, dx1, 0, H, W, part1, B * H * W, B * H * W, None, None, passes,
-                                want_lo)
+                                want_lo, save_g)
         # ---- conv_1 + shortcut ------------------------------------------------------------------
         pw1 = pre.get('pw1') or ops.prep_conv_weight(W1.contiguous(), want_lo=want_lo)
         r = ops.conv3x3([a1], pw1, b1, residual=x, res_ups=ups,
@@ -158,14 +196,15 @@ class _ResBlockFn(torch.autograd.Function):
         db1 = sums[0]
         dnw_in = sums[1] if noisy else None
         dnw_skip = sums[2] if noisy else None
-        dW1 = ops.conv3x3_wgrad(g1, a1, passes=passes)
+        ss = _SideStream()
+        dW1 = ss.run(lambda: ops.conv3x3_wgrad(g1, a1, passes=passes), g1, a1)
         pwT = ops.prep_conv_weight(s['W1'].contiguous(), want_lo=want_lo, transpose=True)
         dt1, amax1 = ops.conv3x3([g1], pwT, None, passes=passes, act_mask=a1.hi, want_amax=True,
                                  tag="dgrad")
         del g1
         # ---- norm_1 ----------------------------------------------------------------------------
         dxhat, nsums, dWm1, dtab1, dtb1, dstyle1 = _norm_backward(
-            blk.norm_1, st1, dt1, amax1, dx1, 0, None, None, L, passes, want_lo)
+            blk.norm_1, st1, dt1, amax1, dx1, 0, None, None, L, passes, want_lo, ss)
         del dt1
         dgb1, dbb1 = nsums[2], nsums[3]
         ddx1, _ = ops.bn_bwd(dxhat, dx1, 0, st1.sc, st1.sh, nsums, st1.inv_count)
@@ -175,7 +214,7 @@ class _ResBlockFn(torch.autograd.Function):
         del ddx1
         db0 = sums[0]
         dnw_mid = sums[1] if noisy else None
-        dW0 = ops.conv3x3_wgrad(g0, a0, passes=passes)
+        dW0 = ss.run(lambda: ops.conv3x3_wgrad(g0, a0, passes=passes), g0, a0)
         pwT = ops.prep_conv_weight(s['W0'].contiguous(), want_lo=want_lo, transpose=True)
         dt0, amax0 = ops.conv3x3([g0], pwT, None, passes=passes, act_mask=a0.hi, want_amax=True,
                                  tag="dgrad")
@@ -183,7 +222,7 @@ class _ResBlockFn(torch.autograd.Function):
         # ---- norm_0 (reads x through the folded upsample, + noise_in) ---------------------------
         nw_in = s['nw_in'] if noisy else None
         dxhat, nsums, dWm0, dtab0, dtb0, dstyle0 = _norm_backward(
-            blk.norm_0, st0, dt0, amax0, x, ups, n_in, nw_in, L, passes, want_lo)
+            blk.norm_0, st0, dt0, amax0, x, ups, n_in, nw_in, L, passes, want_lo, ss)
         del dt0
         dgb0, dbb0 = nsums[2], nsums[3]
         dx, dnw_in_bn = ops.bn_bwd(dxhat, x, ups, st0.sc, st0.sh, nsums, st0.inv_count, noise=n_in,
@@ -193,6 +232,7 @@ class _ResBlockFn(torch.autograd.Function):
         dstyle = dstyle0
         if dstyle1 is not None:
             dstyle = dstyle1 if dstyle is None else dstyle + dstyle1
+        ss.join()
         ctx.s = None
         return (None, None, None, None, None, None, dx, dstyle, dW0, db0, dW1, db1, dWm0, dgb0, dbb0,
                 dtab0, dtb0, dWm1, dgb1, dbb1, dtab1, dtb1, dnw_in, dnw_skip, dnw_mid)

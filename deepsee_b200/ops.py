@@ -247,8 +247,9 @@ def conv3x3(sources, pw, bias, residual=None, res_ups=0, noises=(), passes=3, wa
 
 
 def spade_modulate(sources, pw, x, x_ups, bn_scale, bn_shift, gamma_bias, beta_bias, noise=None,
-                   noise_w=None, passes=3, want_lo=True):
-    """K1: gamma/beta conv + batch-norm apply + modulation + LeakyReLU -> fp16 split planes."""
+                   noise_w=None, passes=3, want_lo=True, save_g=False):
+    """K1: gamma/beta conv + batch-norm apply + modulation + LeakyReLU -> fp16 split planes.
+    save_g: also return G = gamma + gamma_bias as split planes (what K1's backward multiplies by)."""
     ops, (B, H, W) = _operands(sources, pw, passes)
     _chk_cuda(x, bn_scale, bn_shift, gamma_bias, beta_bias, noise, noise_w)
     Cc = x.shape[3]
@@ -265,10 +266,37 @@ def spade_modulate(sources, pw, x, x_ups, bn_scale, bn_shift, gamma_bias, beta_b
     m.out_hi = hi.data_ptr()
     m.out_lo = lo.data_ptr() if lo is not None else 0
     m.C = Cc
+    ghi = glo = None
+    if save_g:
+        ghi = torch.empty_like(hi)
+        glo = torch.empty_like(hi) if want_lo else None
+    m.g_hi = ghi.data_ptr() if ghi is not None else 0
+    m.g_lo = glo.data_ptr() if glo is not None else 0
     flops = 2.0 * 9 * pw.cin * pw.n_total * B * H * W
     _timed("modulate_%dx%d" % (H, W), flops,
            lambda: _lib.check(_lib.load().dsee_spade_modulate_fwd(C.byref(ops), C.byref(m), _stream())))
+    if save_g:
+        return SplitPlanes(hi, lo), SplitPlanes(ghi, glo)
     return SplitPlanes(hi, lo)
+
+
+def spade_modulate_bwd_saved(g_planes, x, x_ups, bn_scale, bn_shift, dt, dt_amax, noise=None,
+                             noise_w=None, want_lo=True):
+    """K1 backward from the saved G planes (one streaming pass) -> (dxhat, dgb GradPlanes, sums[4,C])."""
+    _chk_cuda(x, bn_scale, bn_shift, dt, dt_amax, noise, noise_w, g_planes.hi, g_planes.lo)
+    B, H, W, Cc = dt.shape
+    dev = x.device
+    lib = _lib.load()
+    dxhat = torch.empty((B, H, W, Cc), dtype=torch.float32, device=dev)
+    ghi = torch.empty((B, H, W, 2 * Cc), dtype=torch.float16, device=dev)
+    glo = torch.empty_like(ghi) if want_lo else None
+    ginv = torch.empty(1, dtype=torch.float32, device=dev)
+    part = torch.empty((lib.dsee_grad_prep_blocks(B * H * W), Cc, 4), dtype=torch.float32, device=dev)
+    _lib.check(lib.dsee_spade_modulate_bwd_saved(_p(x), x_ups, _p(noise), _p(noise_w), _p(bn_scale),
+                                                 _p(bn_shift), _p(g_planes.hi), _p(g_planes.lo), _p(dt),
+                                                 _p(dt_amax), B, H, W, Cc, _p(dxhat), _p(ghi), _p(glo),
+                                                 _p(ginv), _p(part), _stream()))
+    return dxhat, GradPlanes(ghi, glo, ginv), reduce_partials(part)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -317,6 +345,30 @@ def conv3x3_wgrad(dy, a, passes=3):
         _p(dy.hi), _p(dy.lo), _p(getattr(dy, "inv_scale", None)), _p(a.hi), _p(a.lo),
         _p(getattr(a, "inv_scale", None)), _DTYPE_CODE[dy.hi.dtype], B, H, W, N, Cc, passes, _p(ws),
         _p(dw), 1, _stream())))
+    return dw
+
+
+def conv3x3_wgrad_multi(dy, sources, passes=3):
+    """conv3x3_wgrad against up to two channel-concatenated activation sources in one launch:
+    -> dW [N, C0 + C1, 3, 3]."""
+    if len(sources) == 1:
+        return conv3x3_wgrad(dy, sources[0], passes=passes)
+    assert len(sources) == 2
+    _chk_cuda(dy.hi, dy.lo, *[t for s_ in sources for t in (s_.hi, s_.lo)])
+    B, H, W, N = dy.hi.shape
+    chans = [s_.hi.shape[3] for s_ in sources]
+    ctot = sum(chans)
+    lib = _lib.load()
+    ws = torch.empty(lib.dsee_conv3x3_wgrad_workspace_floats(B, H, W, N, ctot), dtype=torch.float32,
+                     device=dy.hi.device)
+    dw = torch.empty((N, ctot, 3, 3), dtype=torch.float32, device=dy.hi.device)
+    a_hi = (C.c_void_p * 2)(*[s_.hi.data_ptr() for s_ in sources])
+    a_lo = (C.c_void_p * 2)(*[(s_.lo.data_ptr() if s_.lo is not None else 0) for s_ in sources])
+    ach = (C.c_int * 2)(*chans)
+    flops = 2.0 * 9 * ctot * N * B * H * W
+    _timed("wgrad_%dx%d" % (H, W), flops, lambda: _lib.check(lib.dsee_conv3x3_wgrad2(
+        _p(dy.hi), _p(dy.lo), _p(getattr(dy, "inv_scale", None)), a_hi, a_lo, ach,
+        _DTYPE_CODE[dy.hi.dtype], B, H, W, N, passes, _p(ws), _p(dw), 1, _stream())))
     return dw
 
 
@@ -393,7 +445,7 @@ def onehot_planes(labels, Lp=64):
     return SplitPlanes(out, None)
 
 
-def shared_mlp_bwd_tc(dsrc, dsrc_amax, coff, actv_hi, labels, onehot, ups, L, passes=3):
+def shared_mlp_bwd_tc(dsrc, dsrc_amax, coff, actv_hi, labels, onehot, ups, L, passes=3, side=None):
     """mlp_shared backward as a tensor-core wgrad against the one-hot plane:
     -> (dtable [9,L,nh], dbias [nh])."""
     _chk_cuda(dsrc, dsrc_amax, actv_hi, labels, onehot.hi)
@@ -410,8 +462,10 @@ def shared_mlp_bwd_tc(dsrc, dsrc_amax, coff, actv_hi, labels, onehot, ups, L, pa
                                        Wl, ups, nh, _p(hi), _p(lo), _p(inv), _p(part), _stream()))
     g = GradPlanes(hi, lo, inv)
     oh = onehot if not want_lo else SplitPlanes(onehot.hi, _zeros_like_cached(onehot.hi))
-    dw = conv3x3_wgrad(g, oh, passes=passes)  # [nh, Lp, 3, 3]
-    dtable = dw[:, :L].permute(2, 3, 1, 0).reshape(9, L, nh)
+    def table_grad():
+        dw = conv3x3_wgrad(g, oh, passes=passes)  # [nh, Lp, 3, 3]
+        return dw[:, :L].permute(2, 3, 1, 0).reshape(9, L, nh)
+    dtable = side.run(table_grad, g, oh) if side is not None else table_grad()
     return dtable, reduce_partials(part)[0]
 
 

@@ -216,6 +216,10 @@ typedef struct {
     void* out_hi;        /* fp16 NHWC [B,H,W,C] */
     void* out_lo;        /* may be NULL */
     int C;               /* multiple of 128 */
+    /* optional (training): G = gamma + gamma_bias saved as fp16 split planes NHWC [B,H,W,C] so
+     * the backward pass (dsee_spade_modulate_bwd_saved) does not re-run the gamma GEMM */
+    void* g_hi;
+    void* g_lo;
 } dsee_modulate_args;
 int dsee_spade_modulate_fwd(const dsee_conv_operands* ops, const dsee_modulate_args* mod,
                             void* stream);
@@ -286,6 +290,13 @@ int dsee_conv3x3_wgrad(const void* dy_hi, const void* dy_lo, const float* dy_inv
                        const void* a_hi, const void* a_lo, const float* a_inv_scale, int dtype, int B,
                        int H, int W, int n_total, int c_total, int passes, float* workspace, float* dw,
                        int layout_nc9, void* stream);
+/* The same with the activation operand given as up to two channel-concatenated sources (the
+ * [actv | style_map] input of a SEAN modulation conv, normalization.py:198-201): one launch with a
+ * 256-wide MMA instead of two 128-wide ones.  a_channels[i] % 64 == 0, a_channels[1] may be 0. */
+int dsee_conv3x3_wgrad2(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale,
+                        const void* const* a_hi, const void* const* a_lo, const int* a_channels,
+                        int dtype, int B, int H, int W, int n_total, int passes, float* workspace,
+                        float* dw, int layout_nc9, void* stream);
 /* Batch-norm backward (differentiates batchnorm.py:78-93 / F.batch_norm in training mode) with the
  * folded 2x upsample transposed into a 2x2 sum and the identity shortcut's gradient added:
  *   xhat = (x[up] + noise_w*noise) * bn_scale + bn_shift
@@ -332,6 +343,15 @@ int dsee_stem_bwd(const float* x, const float* dy, int B, int H, int W, int C, f
 int dsee_head_bwd_blocks(int B, int H, int W);
 int dsee_head_bwd(const float* x, const float* w, const float* out, const float* dout, int B, int H,
                   int W, int C, float* dx, float* partial, float* dw_db, void* stream);
+
+/* K1 backward from the saved G planes (no GEMM; one streaming pass, HBM bound: reads x, dt, G,
+ * writes dxhat and the dgb planes).  Same outputs as dsee_spade_modulate_bwd; partial fp32
+ * [dsee_grad_prep_blocks(B*H*W)][C][4]. */
+int dsee_spade_modulate_bwd_saved(const float* x, int x_ups, const float* noise, const float* noise_w,
+                                  const float* bn_scale, const float* bn_shift, const void* g_hi,
+                                  const void* g_lo, const float* dt, const float* dt_amax, int B, int H,
+                                  int W, int C, float* dxhat, void* dgb_hi, void* dgb_lo,
+                                  float* dgb_inv_scale, float* partial, void* stream);
 
 /* ---- batch-norm statistics ------------------------------------------------------------------ */
 /* Per-channel sum / sum of squares of x (+ noise) at the post-upsample resolution, written as

@@ -49,7 +49,8 @@ def _run_case(name, over, passes, batch=2, train=True, seed=31):
 
     def rec_mod(*a, **k):
         r = orig_mod(*a, **k)
-        masks.append((r.hi > 0).permute(0, 3, 1, 2).cpu())
+        act = r if hasattr(r, "hi") else r[0]  # (activation planes, saved G planes) when training
+        masks.append((act.hi > 0).permute(0, 3, 1, 2).cpu())
         return r
 
     def rec_head(x, *a, **k):
