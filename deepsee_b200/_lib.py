@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("DSEE_LIB_PATH") or os.path.join(_HERE, "lib", "libdee
 # every symbol include/deepsee_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "dsee_version", "dsee_last_error", "dsee_launch_count",
-    "dsee_onehot_from_labels", "dsee_labels_from_onehot", "dsee_resize_labels",
+    "dsee_noise_fill", "dsee_onehot_from_labels", "dsee_labels_from_onehot", "dsee_resize_labels",
     "dsee_shared_mlp_fwd", "dsee_style_gather_fwd",
     "dsee_prep_conv_weight", "dsee_split_f16", "dsee_prep_conv_weight_ex", "dsee_split_f16_ups2",
     "dsee_fold2x2", "dsee_conv2d_tc", "dsee_conv2d_tc_wgrad_workspace_floats", "dsee_conv2d_tc_wgrad",
@@ -47,7 +47,7 @@ class ConvEpilogue(C.Structure):
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("res_ups", C.c_int),
         ("noise", C.c_void_p * 2), ("noise_w", C.c_void_p * 2),
         ("out", C.c_void_p), ("stats_partial", C.c_void_p), ("act_mask", C.c_void_p),
-        ("amax_out", C.c_void_p), ("lrelu", C.c_int),
+        ("amax_out", C.c_void_p), ("lrelu", C.c_int), ("noise_seed", C.c_uint64 * 2),
     ]
 
 
@@ -58,7 +58,7 @@ class ModulateArgs(C.Structure):
         ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
         ("gamma_bias", C.c_void_p), ("beta_bias", C.c_void_p),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
-        ("C", C.c_int), ("g_hi", C.c_void_p), ("g_lo", C.c_void_p),
+        ("C", C.c_int), ("g_hi", C.c_void_p), ("g_lo", C.c_void_p), ("noise_seed", C.c_uint64),
     ]
 
 
@@ -102,7 +102,7 @@ def load():
     lib.dsee_version.restype = C.c_int
     lib.dsee_last_error.restype = C.c_char_p
     lib.dsee_launch_count.restype = C.c_int64
-    vp, i, f, d, i64 = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_int64
+    vp, i, f, d, i64, u64 = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_int64, C.c_uint64
     sig = {
         "dsee_onehot_from_labels": [vp, vp, i, i, i, i, vp, vp],
         "dsee_labels_from_onehot": [vp, vp, i, i, i, i, vp, vp],
@@ -120,16 +120,17 @@ def load():
         "dsee_conv3x3_stats_tiles": [i, i, i],
         "dsee_spade_modulate_fwd": [C.POINTER(ConvOperands), C.POINTER(ModulateArgs), vp],
         "dsee_spade_modulate_bwd": [C.POINTER(ConvOperands), C.POINTER(ModulateBwdArgs), vp],
-        "dsee_spade_modulate_bwd_saved": [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp,
-                                          vp, vp, vp],
+        "dsee_spade_modulate_bwd_saved": [vp, i, vp, u64, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp,
+                                          vp, vp, vp, vp],
+        "dsee_noise_fill": [u64, vp, i64, vp],
         "dsee_grad_prep_blocks": [i64],
-        "dsee_grad_prep": [vp, vp, vp, vp, vp, vp, i64, i, vp, vp],
+        "dsee_grad_prep": [vp, vp, vp, vp, vp, vp, u64, u64, i64, i, vp, vp],
         "dsee_reduce_partials": [vp, i, i, i, f, vp, vp],
         "dsee_conv3x3_wgrad": [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp, i, vp],
         "dsee_conv3x3_wgrad2": [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i), i, i, i, i, i, i,
                                 vp, vp, i, vp],
         "dsee_bn_bwd_blocks": [i, i, i],
-        "dsee_bn_bwd": [vp, vp, i, vp, vp, vp, vp, vp, f, vp, i, i, i, i, vp, vp, vp],
+        "dsee_bn_bwd": [vp, vp, i, vp, u64, vp, vp, vp, vp, f, vp, i, i, i, i, vp, vp, vp],
         "dsee_actv_grad_prep": [vp, i, i, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp],
         "dsee_onehot_planes": [vp, vp, i64, i, vp],
         "dsee_shared_mlp_bwd_blocks": [i, i, i],
@@ -139,7 +140,7 @@ def load():
         "dsee_stem_bwd": [vp, vp, i, i, i, i, vp, vp, vp],
         "dsee_head_bwd_blocks": [i, i, i],
         "dsee_head_bwd": [vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp],
-        "dsee_bn_stats": [vp, i, vp, vp, i, i, i, i, vp, C.POINTER(C.c_int), vp],
+        "dsee_bn_stats": [vp, i, vp, u64, vp, i, i, i, i, vp, C.POINTER(C.c_int), vp],
         "dsee_bn_finalize": [vp, i, i, d, d, f, f, vp, vp, vp, vp, vp, vp, vp],
         "dsee_bn_eval_affine": [vp, vp, f, i, vp, vp, vp],
         "dsee_stem_fwd": [vp, vp, vp, vp, i, i, i, i, vp],

@@ -13,6 +13,8 @@ class _Config:
     # Issue the weight-gradient GEMMs of the generator on a second stream (they are leaves of the
     # backward graph) so the HBM-bound kernels of the chain overlap with them.
     overlap_wgrad = os.environ.get("DSEE_OVERLAP_WGRAD", "1") != "0"
+    # NoiseInjection: 0 = in-kernel counter-based noise (never in HBM), 1 = torch.randn tensors.
+    noise_tensors = os.environ.get("DSEE_NOISE_TENSORS", "0") == "1"
     # Verify (one device->host read per generator forward) that the semantic input is one-hot.
     check_onehot = os.environ.get("DSEE_CHECK_ONEHOT", "1") != "0"
 

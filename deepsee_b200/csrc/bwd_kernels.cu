@@ -33,7 +33,8 @@ __global__ void grad_amax_kernel(const float* __restrict__ x, int64_t n4, float*
 __global__ void grad_prep_kernel(const float* __restrict__ dy, __half* __restrict__ hi,
                                  __half* __restrict__ lo, float* __restrict__ inv_scale,
                                  const float* __restrict__ n0, const float* __restrict__ n1,
-                                 int64_t npix, int C, float* __restrict__ partial, int nq) {
+                                 unsigned long long seed0, unsigned long long seed1, int64_t npix, int C,
+                                 float* __restrict__ partial, int nq) {
     extern __shared__ float red[];  // [lanes][C][nq]
     const float scale = pow2_scale_for(inv_scale[1], 14);
     if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[0] = 1.f / scale;
@@ -63,12 +64,12 @@ __global__ void grad_prep_kernel(const float* __restrict__ dy, __half* __restric
             if (lo) *reinterpret_cast<uint2*>(lo + (size_t)pix * C + g * 4) = make_uint2(plw[0], plw[1]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) s[0][e] += a[e];
-            if (n0) {
-                const float4 nv = __ldg(reinterpret_cast<const float4*>(n0 + (size_t)pix * C) + g);
+            if (nq > 1) {
+                const float4 nv = load_noise4(n0, seed0, (size_t)pix * C + g * 4);
                 s[1][0] += a[0] * nv.x; s[1][1] += a[1] * nv.y; s[1][2] += a[2] * nv.z; s[1][3] += a[3] * nv.w;
             }
-            if (n1) {
-                const float4 nv = __ldg(reinterpret_cast<const float4*>(n1 + (size_t)pix * C) + g);
+            if (nq > 2) {
+                const float4 nv = load_noise4(n1, seed1, (size_t)pix * C + g * 4);
                 s[2][0] += a[0] * nv.x; s[2][1] += a[1] * nv.y; s[2][2] += a[2] * nv.z; s[2][3] += a[3] * nv.w;
             }
         }
@@ -91,7 +92,8 @@ __global__ void grad_prep_kernel(const float* __restrict__ dy, __half* __restric
 //   sum dB).  thread = (pixel lane, 4 channels); GP_PIX pixels per block.
 // ------------------------------------------------------------------------------------------------
 __global__ void modulate_bwd_saved_kernel(const float* __restrict__ x, int x_ups,
-                                          const float* __restrict__ noise, const float* __restrict__ noise_w,
+                                          const float* __restrict__ noise, unsigned long long noise_seed,
+                                          const float* __restrict__ noise_w,
                                           const float* __restrict__ sc, const float* __restrict__ sh,
                                           const __half* __restrict__ g_hi, const __half* __restrict__ g_lo,
                                           const float* __restrict__ dt, const float* __restrict__ dt_amax,
@@ -116,7 +118,8 @@ __global__ void modulate_bwd_saved_kernel(const float* __restrict__ x, int x_ups
         const float4 scv = __ldg(reinterpret_cast<const float4*>(sc) + g);
         const float4 shv = __ldg(reinterpret_cast<const float4*>(sh) + g);
         float4 nw = make_float4(0, 0, 0, 0);
-        if (noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
+        const bool has_noise = noise_w != nullptr;
+        if (has_noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
         const int c = g * 4;
         const int ng = (c >> 7) * 256 + (c & 127);  // interleaved position of channel c
         for (int i = pl; i < GP_PIX; i += lanes) {
@@ -127,8 +130,8 @@ __global__ void modulate_bwd_saved_kernel(const float* __restrict__ x, int x_ups
             const int b = (int)(pix / ((int64_t)W * H));
             const size_t xp = ((size_t)b * Hx + (yy >> x_ups)) * Wx + (xx >> x_ups);
             float4 xv = __ldg(reinterpret_cast<const float4*>(x + xp * C) + g);
-            if (noise) {
-                const float4 nv = __ldg(reinterpret_cast<const float4*>(noise + (size_t)pix * C) + g);
+            if (has_noise) {
+                const float4 nv = load_noise4(noise, noise_seed, (size_t)pix * C + g * 4);
                 xv.x += nw.x * nv.x; xv.y += nw.y * nv.y; xv.z += nw.z * nv.z; xv.w += nw.w * nv.w;
             }
             const float xh[4] = {xv.x * scv.x + shv.x, xv.y * scv.y + shv.y, xv.z * scv.z + shv.z,
@@ -220,7 +223,8 @@ reduce_partials_kernel(const float* __restrict__ partial, int n, int C, int nq, 
 // ------------------------------------------------------------------------------------------------
 constexpr int BB_PIX = 64;  // low-res pixels per block
 __global__ void bn_bwd_kernel(const float* __restrict__ dxhat, const float* __restrict__ x, int ups,
-                              const float* __restrict__ noise, const float* __restrict__ noise_w,
+                              const float* __restrict__ noise, unsigned long long noise_seed,
+                              const float* __restrict__ noise_w,
                               const float* __restrict__ sc, const float* __restrict__ sh,
                               const float* __restrict__ sums /*[2][C]: sum dxhat, sum dxhat*xhat*/,
                               float inv_count, const float* __restrict__ dskip, int B, int Hx,
@@ -243,7 +247,8 @@ __global__ void bn_bwd_kernel(const float* __restrict__ dxhat, const float* __re
         m1.x *= inv_count; m1.y *= inv_count; m1.z *= inv_count; m1.w *= inv_count;
         m2.x *= inv_count; m2.y *= inv_count; m2.z *= inv_count; m2.w *= inv_count;
         float4 nw = make_float4(0, 0, 0, 0);
-        if (noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
+        const bool has_noise = noise_w != nullptr;
+        if (has_noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
         for (int i = pl; i < BB_PIX; i += lanes) {
             const int64_t pix = p0 + i;
             if (pix >= npix) break;
@@ -257,8 +262,8 @@ __global__ void bn_bwd_kernel(const float* __restrict__ dxhat, const float* __re
                     const size_t fp = ((size_t)b * H + (yy * f + sy)) * W + (xx * f + sx);
                     const float4 d = __ldg(reinterpret_cast<const float4*>(dxhat + fp * C) + g);
                     float4 xi = xv, nv = make_float4(0, 0, 0, 0);
-                    if (noise) {
-                        nv = __ldg(reinterpret_cast<const float4*>(noise + fp * C) + g);
+                    if (has_noise) {
+                        nv = load_noise4(noise, noise_seed, fp * C + g * 4);
                         xi.x += nw.x * nv.x; xi.y += nw.y * nv.y; xi.z += nw.z * nv.z; xi.w += nw.w * nv.w;
                     }
                     float4 r;
@@ -545,14 +550,16 @@ using namespace dsee;
 extern "C" int dsee_grad_prep_blocks(int64_t npix) { return cdivb(npix, GP_PIX); }
 
 extern "C" int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, float* inv_scale,
-                              const float* noise0, const float* noise1, int64_t npix, int C,
-                              float* partial, void* stream) {
+                              const float* noise0, const float* noise1, unsigned long long seed0,
+                              unsigned long long seed1, int64_t npix, int C, float* partial,
+                              void* stream) {
     DSEE_CHECK_ARG(dy && out_hi && inv_scale && partial && npix > 0, "bad argument");
     DSEE_CHECK_ARG(C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "C must divide 1024 (got %d)", C);
-    DSEE_CHECK_ARG(!(noise1 && !noise0), "noise1 without noise0");
+    const bool has0 = noise0 || seed0, has1 = noise1 || seed1;
+    DSEE_CHECK_ARG(!(has1 && !has0), "noise1 without noise0");
     int rc = require_sm100();
     if (rc) return rc;
-    const int nq = 1 + (noise0 ? 1 : 0) + (noise1 ? 1 : 0);
+    const int nq = 1 + (has0 ? 1 : 0) + (has1 ? 1 : 0);
     const int lanes = 256 / (C / 4);
     size_t sm = (size_t)lanes * C * nq * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
@@ -563,13 +570,14 @@ extern "C" int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, float
     grad_amax_kernel<<<ablocks, 256, 0, st>>>(dy, n4, inv_scale + 1);
     count_launch();
     grad_prep_kernel<<<cdivb(npix, GP_PIX), 256, sm, st>>>(dy, (__half*)out_hi, (__half*)out_lo,
-                                                           inv_scale, noise0, noise1, npix, C, partial,
-                                                           nq);
+                                                           inv_scale, noise0, noise1, seed0, seed1, npix,
+                                                           C, partial, nq);
     LAUNCH_END();
 }
 
 extern "C" int dsee_spade_modulate_bwd_saved(const float* x, int x_ups, const float* noise,
-                                             const float* noise_w, const float* bn_scale,
+                                             unsigned long long noise_seed, const float* noise_w,
+                                             const float* bn_scale,
                                              const float* bn_shift, const void* g_hi, const void* g_lo,
                                              const float* dt, const float* dt_amax, int B, int H, int W,
                                              int C, float* dxhat, void* dgb_hi, void* dgb_lo,
@@ -578,14 +586,17 @@ extern "C" int dsee_spade_modulate_bwd_saved(const float* x, int x_ups, const fl
                        partial,
                    "NULL pointer");
     DSEE_CHECK_ARG(C % 128 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "C must be 128, 256, 512 or 1024");
-    DSEE_CHECK_ARG((x_ups == 0 || x_ups == 1) && (noise == nullptr) == (noise_w == nullptr), "bad argument");
+    DSEE_CHECK_ARG((x_ups == 0 || x_ups == 1) &&
+                       (noise != nullptr || noise_seed != 0) == (noise_w != nullptr),
+                   "bad argument");
     int rc = require_sm100();
     if (rc) return rc;
     const int64_t npix = (int64_t)B * H * W;
     const int lanes = 256 / (C / 4);
     const size_t sm = (size_t)lanes * C * 4 * sizeof(float);
     modulate_bwd_saved_kernel<<<cdivb(npix, GP_PIX), 256, sm, (cudaStream_t)stream>>>(
-        x, x_ups, noise, noise_w, bn_scale, bn_shift, (const __half*)g_hi, (const __half*)g_lo, dt, dt_amax,
+        x, x_ups, noise, noise_seed, noise_w, bn_scale, bn_shift, (const __half*)g_hi, (const __half*)g_lo, dt,
+        dt_amax,
         B, H, W, C, dxhat, (__half*)dgb_hi, (__half*)dgb_lo, dgb_inv_scale, partial);
     LAUNCH_END();
 }
@@ -603,20 +614,21 @@ extern "C" int dsee_reduce_partials(const float* partial, int n, int C, int nq, 
 extern "C" int dsee_bn_bwd_blocks(int B, int Hx, int Wx) { return cdivb((int64_t)B * Hx * Wx, BB_PIX); }
 
 extern "C" int dsee_bn_bwd(const float* dxhat, const float* x, int x_ups, const float* noise,
-                           const float* noise_w, const float* bn_scale, const float* bn_shift,
+                           unsigned long long noise_seed, const float* noise_w, const float* bn_scale,
+                           const float* bn_shift,
                            const float* sums, float inv_count, const float* dskip, int B, int Hx,
                            int Wx, int C, float* dx, float* nw_partial, void* stream) {
     DSEE_CHECK_ARG(dxhat && x && bn_scale && bn_shift && sums && dx, "NULL pointer");
     DSEE_CHECK_ARG(C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "C must divide 1024 (got %d)", C);
-    DSEE_CHECK_ARG((noise == nullptr) == (noise_w == nullptr), "noise/noise_w mismatch");
-    DSEE_CHECK_ARG(!nw_partial || noise, "nw_partial needs noise");
+    DSEE_CHECK_ARG((noise != nullptr || noise_seed != 0) == (noise_w != nullptr), "noise/noise_w mismatch");
+    DSEE_CHECK_ARG(!nw_partial || noise_w, "nw_partial needs noise");
     int rc = require_sm100();
     if (rc) return rc;
     const int lanes = 256 / (C / 4);
     size_t sm = nw_partial ? (size_t)lanes * C * sizeof(float) : 0;
     bn_bwd_kernel<<<dsee_bn_bwd_blocks(B, Hx, Wx), 256, sm, (cudaStream_t)stream>>>(
-        dxhat, x, x_ups, noise, noise_w, bn_scale, bn_shift, sums, inv_count, dskip, B, Hx, Wx, C, dx,
-        nw_partial);
+        dxhat, x, x_ups, noise, noise_seed, noise_w, bn_scale, bn_shift, sums, inv_count, dskip, B, Hx, Wx,
+        C, dx, nw_partial);
     LAUNCH_END();
 }
 

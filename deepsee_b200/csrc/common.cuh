@@ -203,6 +203,43 @@ __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
     atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+// ----------------------------------------------------------------------------------------------
+// Counter-based N(0,1) noise for NoiseInjection (normalization.py:299-304).  The value of element
+// e (linear NHWC index) of a noise tensor is a pure function of (seed, e): Philox4x32-10 on the
+// counter e/4 gives the 4 values of channels e..e+3 through two Box-Muller pairs.  Every kernel
+// that needs the tensor (statistics, K1, K2's epilogue, the backward passes) regenerates it, so it
+// is never written to or read from HBM.  dsee_noise_fill materialises the same stream for tests.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 noise_normal4(unsigned long long seed, unsigned long long idx4) {
+    uint32_t c0 = (uint32_t)idx4, c1 = (uint32_t)(idx4 >> 32), c2 = 0u, c3 = 0u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    const float k = 2.3283064365386963e-10f;  // 2^-32
+    const float u0 = ((float)c0 + 0.5f) * k, u1 = (float)c1 * k;
+    const float u2 = ((float)c2 + 0.5f) * k, u3 = (float)c3 * k;
+    const float r0 = sqrtf(-2.f * __logf(fminf(u0, 1.f))), r1 = sqrtf(-2.f * __logf(fminf(u2, 1.f)));
+    float s0, q0, s1, q1;
+    __sincosf(6.2831853071795865f * u1 - 3.1415926535897932f, &s0, &q0);
+    __sincosf(6.2831853071795865f * u3 - 3.1415926535897932f, &s1, &q1);
+    return make_float4(r0 * q0, r0 * s0, r1 * q1, r1 * s1);
+}
+// 4 consecutive channels of a noise tensor starting at element e (a multiple of 4): from HBM when an
+// explicit tensor is given, regenerated from the seed otherwise.
+__device__ __forceinline__ float4 load_noise4(const float* noise, unsigned long long seed, size_t e) {
+    if (noise) return __ldg(reinterpret_cast<const float4*>(noise + e));
+    return noise_normal4(seed, (unsigned long long)(e >> 2));
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

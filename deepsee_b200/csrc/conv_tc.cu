@@ -11,7 +11,8 @@
 // * fp32 accumulators live in TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i
 //   overlaps the main loop of tile i+1. Persistent CTAs, one per SM, static round-robin tiles.
 // * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM
-//   allocator, warps 2..5 = epilogue (one TMEM lane quarter each; thread == output pixel).
+//   allocator, warps 2..9 = epilogue (two per TMEM lane quarter, alternating 32-column chunks;
+//   thread == output pixel).
 //
 // Two epilogues share the main loop:
 //   EPI_CONV      K2: + bias (+ residual, optionally read through a folded 2x nearest upsample)
@@ -39,7 +40,8 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;              // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_TAPS = 16;
 
@@ -69,6 +71,7 @@ struct alignas(64) ConvParams {
     int res_ups;
     const float* rnoise[2];
     const float* rnoise_w[2];
+    unsigned long long rnoise_seed[2];
     float* out;
     float* stats_partial;
     const __half* act_mask;  // dgrad: multiply by LeakyReLU'(t) read off the saved activation's sign
@@ -78,6 +81,7 @@ struct alignas(64) ConvParams {
     int x_ups;
     const float* noise;
     const float* noise_w;
+    unsigned long long noise_seed;
     const float* bn_scale;
     const float* bn_shift;
     const float* gamma_bias;
@@ -171,7 +175,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -249,6 +253,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;  // TMEM lane quarter this warp may touch
+        const int eh = (warp - 2) >> 2;  // which of the quarter's two warps (chunk parity)
+        constexpr int ESTEP = EPI_WARPS / 4;
         const int m = q * 32 + lane;
         const int ly = m / TILE_W, lx = m % TILE_W;
         const float inv_scale = __ldg(p.w_inv_scale) * (p.a_inv_scale ? __ldg(p.a_inv_scale) : 1.f);
@@ -276,7 +282,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                     rrow = p.residual + rp * p.n_total;
                 }
 #pragma unroll 1
-                for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+                for (int ch = eh; ch < BLOCK_N / 32; ch += ESTEP) {
                     const int n = n0 + ch * 32;
                     if (n >= p.n_total) break;  // warp-uniform
                     uint32_t v[32];
@@ -318,12 +324,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         }
 #pragma unroll
                         for (int i2 = 0; i2 < 2; ++i2) {
-                            if (p.rnoise[i2]) {
-                                const float* nr = p.rnoise[i2] + pix * p.n_total + n;
+                            if (p.rnoise_w[i2]) {
+                                const size_t ne = pix * p.n_total + n;
                                 const float* nw = p.rnoise_w[i2] + n;
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
-                                    float4 r = __ldg(reinterpret_cast<const float4*>(nr) + j);
+                                    float4 r = load_noise4(p.rnoise[i2], p.rnoise_seed[i2], ne + 4 * j);
                                     float4 wv = __ldg(reinterpret_cast<const float4*>(nw) + j);
                                     o[4 * j] += wv.x * r.x;
                                     o[4 * j + 1] += wv.y * r.y;
@@ -384,7 +390,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                 const float gscale = pow2_scale_for(__ldg(p.dt_amax), 10);
                 if (tile == 0 && threadIdx.x == 64) *p.dgb_inv_scale = 1.f / gscale;
 #pragma unroll 1
-                for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+                for (int ch = eh; ch < BLOCK_N / 32; ch += ESTEP) {
                     const int c = c0 + ch * 32;
                     if (c >= p.C) break;
                     uint32_t g[32];
@@ -455,13 +461,13 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                 const int Hx = p.H >> p.x_ups, Wx = p.W >> p.x_ups;
                 const size_t xp = ((size_t)b * Hx + (y >> p.x_ups)) * Wx + (x >> p.x_ups);
                 const float* xrow = p.x + xp * p.C;
-                const float* nrow = p.noise ? p.noise + pix * p.C : nullptr;
+                const bool has_noise = p.noise_w != nullptr;
                 __half* hrow = p.out_hi + pix * p.C;
                 __half* lrow = p.out_lo ? p.out_lo + pix * p.C : nullptr;
                 __half* ghrow = p.g_hi ? p.g_hi + pix * p.C : nullptr;
                 __half* glrow = p.g_lo ? p.g_lo + pix * p.C : nullptr;
 #pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
+                for (int ch = eh; ch < 4; ch += ESTEP) {
                     const int c = c0 + ch * 32;
                     uint32_t g[32], bt[32];
                     tmem_ld32(taddr + ch * 32, g);
@@ -476,8 +482,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                                 const int j = j8 * 8 + h * 4;
                                 float4 xv = __ldg(reinterpret_cast<const float4*>(xrow + c + j));
                                 float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-                                if (nrow) {
-                                    float4 nv = __ldg(reinterpret_cast<const float4*>(nrow + c + j));
+                                if (has_noise) {
+                                    float4 nv = load_noise4(p.noise, p.noise_seed, pix * p.C + c + j);
                                     float ns[4] = {nv.x, nv.y, nv.z, nv.w};
 #pragma unroll
                                     for (int e = 0; e < 4; ++e)
@@ -642,10 +648,11 @@ extern "C" int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_e
     DSEE_CHECK_ARG(!epi->residual || epi->res_ups == 0 || (ops->H % 2 == 0 && ops->W % 2 == 0),
                    "folded upsample needs even H, W");
     for (int i = 0; i < 2; ++i) {
-        DSEE_CHECK_ARG((epi->noise[i] == nullptr) == (epi->noise_w[i] == nullptr),
-                       "noise[%d] and noise_w[%d] must be given together", i, i);
+        DSEE_CHECK_ARG((epi->noise[i] != nullptr || epi->noise_seed[i] != 0) == (epi->noise_w[i] != nullptr),
+                       "noise[%d] (tensor or seed) and noise_w[%d] must be given together", i, i);
         p.rnoise[i] = epi->noise[i];
         p.rnoise_w[i] = epi->noise_w[i];
+        p.rnoise_seed[i] = epi->noise_seed[i];
     }
     p.bias = epi->bias;
     p.residual = epi->residual;
@@ -673,7 +680,7 @@ extern "C" int dsee_conv2d_tc(const dsee_conv2d_tc_args* a, const dsee_conv_epil
     DSEE_CHECK_ARG(a->passes == 1 || (a->passes == 3 && a->a_lo && a->w_lo), "passes must be 1, or 3 with lo planes");
     DSEE_CHECK_ARG(a->a_hi && a->w_hi && a->w_inv_scale, "NULL operand pointer");
     DSEE_CHECK_ARG(a->n_total > 0 && a->n_total % 32 == 0, "n_total must be a multiple of 32");
-    DSEE_CHECK_ARG(!epi->residual && !epi->noise[0] && !epi->noise[1] && !epi->stats_partial &&
+    DSEE_CHECK_ARG(!epi->residual && !epi->noise_w[0] && !epi->noise_w[1] && !epi->stats_partial &&
                        (!epi->act_mask || a->stride == 1),
                    "epilogue option not supported by the general conv");
     int rc = require_sm100();
@@ -789,12 +796,13 @@ extern "C" int dsee_spade_modulate_fwd(const dsee_conv_operands* ops, const dsee
     DSEE_CHECK_ARG(mod->x_ups == 0 || mod->x_ups == 1, "x_ups must be 0 or 1");
     DSEE_CHECK_ARG(mod->x_ups == 0 || (ops->H % 2 == 0 && ops->W % 2 == 0),
                    "folded upsample needs even H, W");
-    DSEE_CHECK_ARG((mod->noise == nullptr) == (mod->noise_w == nullptr),
-                   "noise and noise_w must be given together");
+    DSEE_CHECK_ARG((mod->noise != nullptr || mod->noise_seed != 0) == (mod->noise_w != nullptr),
+                   "noise (tensor or seed) and noise_w must be given together");
     p.x = mod->x;
     p.x_ups = mod->x_ups;
     p.noise = mod->noise;
     p.noise_w = mod->noise_w;
+    p.noise_seed = mod->noise_seed;
     p.bn_scale = mod->bn_scale;
     p.bn_shift = mod->bn_shift;
     p.gamma_bias = mod->gamma_bias;

@@ -265,9 +265,15 @@ __global__ void fold2x2_kernel(const float* __restrict__ in, float* __restrict__
 constexpr int STAT_PIX = 256;  // pixels per partial
 
 // block = 256 threads: thread t owns channels 4*(t % (C/4)) .. +3 and every (256/(C/4))-th pixel.
+__global__ void noise_fill_kernel(unsigned long long seed, float* __restrict__ out, int64_t n4) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    reinterpret_cast<float4*>(out)[i] = noise_normal4(seed, (unsigned long long)i);
+}
+
 __global__ void bn_stats_kernel(const float* __restrict__ x, int x_ups, const float* __restrict__ noise,
-                                const float* __restrict__ noise_w, int B, int H, int W, int C,
-                                float* __restrict__ partial) {
+                                unsigned long long noise_seed, const float* __restrict__ noise_w, int B,
+                                int H, int W, int C, float* __restrict__ partial) {
     extern __shared__ float red[];  // [pix_lanes][C][2]
     const int cg = C >> 2;
     const int pix_lanes = blockDim.x / cg;
@@ -277,7 +283,8 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int x_ups, const fl
     const int Hx = H >> x_ups, Wx = W >> x_ups;
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     float4 nw = make_float4(0, 0, 0, 0);
-    if (noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
+    const bool has_noise = noise_w != nullptr;
+    if (has_noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
     if (pl < pix_lanes) {
         for (int i = pl; i < STAT_PIX; i += pix_lanes) {
             int64_t pix = p0 + i;
@@ -287,8 +294,8 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int x_ups, const fl
             int b = (int)(pix / ((int64_t)W * H));
             size_t xp = ((size_t)b * Hx + (yy >> x_ups)) * Wx + (xx >> x_ups);
             float4 v = __ldg(reinterpret_cast<const float4*>(x + xp * C) + g);
-            if (noise) {
-                float4 nv = __ldg(reinterpret_cast<const float4*>(noise + (size_t)pix * C) + g);
+            if (has_noise) {
+                float4 nv = load_noise4(noise, noise_seed, (size_t)pix * C + g * 4);
                 v.x += nw.x * nv.x;
                 v.y += nw.y * nv.y;
                 v.z += nw.z * nv.z;
@@ -610,22 +617,30 @@ extern "C" int dsee_fold2x2(const float* in, float* out, int B, int Ho, int Wo, 
     LAUNCH_END();
 }
 
-extern "C" int dsee_bn_stats(const float* x, int x_ups, const float* noise, const float* noise_w,
-                             int B, int H, int W, int C, float* stats_partial, int* n_partials,
-                             void* stream) {
+extern "C" int dsee_noise_fill(unsigned long long seed, float* out, int64_t n, void* stream) {
+    DSEE_CHECK_ARG(out && n > 0 && n % 4 == 0, "bad argument (n must be a multiple of 4)");
+    int rc = require_sm100();
+    if (rc) return rc;
+    noise_fill_kernel<<<cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(seed, out, n / 4);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_bn_stats(const float* x, int x_ups, const float* noise, unsigned long long noise_seed,
+                             const float* noise_w, int B, int H, int W, int C, float* stats_partial,
+                             int* n_partials, void* stream) {
     DSEE_CHECK_ARG(n_partials != nullptr, "n_partials is NULL");
     int64_t npix = (int64_t)B * H * W;
     *n_partials = cdiv(npix, STAT_PIX);
     if (!stats_partial) return 0;  // size query
     DSEE_CHECK_ARG(x && C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0,
                    "C must divide 1024 (got %d)", C);
-    DSEE_CHECK_ARG((noise == nullptr) == (noise_w == nullptr), "noise/noise_w mismatch");
+    DSEE_CHECK_ARG((noise != nullptr || noise_seed != 0) == (noise_w != nullptr), "noise/noise_w mismatch");
     int rc = require_sm100();
     if (rc) return rc;
     int pix_lanes = 256 / (C / 4);
     size_t sm = (size_t)pix_lanes * C * 2 * sizeof(float);
-    bn_stats_kernel<<<*n_partials, 256, sm, (cudaStream_t)stream>>>(x, x_ups, noise, noise_w, B, H, W,
-                                                                    C, stats_partial);
+    bn_stats_kernel<<<*n_partials, 256, sm, (cudaStream_t)stream>>>(x, x_ups, noise, noise_seed, noise_w,
+                                                                    B, H, W, C, stats_partial);
     LAUNCH_END();
 }
 

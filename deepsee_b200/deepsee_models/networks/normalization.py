@@ -272,7 +272,16 @@ class NoiseInjection(nn.Module):
         self.weight = nn.Parameter(torch.zeros(self.n_channels), requires_grad=True)
 
     def sample(self, B, H, W):
-        return torch.randn((B, H, W, self.n_channels), dtype=torch.float32, device=self.weight.device)
+        """One draw of the [B,H,W,C] N(0,1) tensor of normalization.py:301, as a seed: the kernels
+        regenerate its elements (counter-based Philox) instead of reading a materialised tensor.
+        The seed comes from torch's CPU generator, so `torch.manual_seed` controls it and ranks
+        seeded differently draw different noise.  DSEE_NOISE_TENSORS=1 materialises torch.randn
+        tensors instead (what the parity tests replace with the oracle's noise)."""
+        from ...config import config
+        if config.noise_tensors:
+            return torch.randn((B, H, W, self.n_channels), dtype=torch.float32,
+                               device=self.weight.device)
+        return ops.NoiseSeed(int(torch.randint(1, 2 ** 62, (1,)).item()))
 
     def forward(self, tensor, noise=None):
         raise RuntimeError('NoiseInjection is fused into the conv epilogues on the B200 path')

@@ -62,9 +62,30 @@ def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+class NoiseSeed(int):
+    """A NoiseInjection tensor that is never materialised: the kernels regenerate its elements from
+    this 64-bit seed (counter-based Philox + Box-Muller, see dsee_noise_fill)."""
+
+
+def _noise(n):
+    """noise argument (None | fp32 NHWC tensor | NoiseSeed) -> (pointer, seed) for the C ABI."""
+    if n is None:
+        return C.c_void_p(0), 0
+    if isinstance(n, NoiseSeed):
+        return C.c_void_p(0), int(n)
+    return _p(n), 0
+
+
+def noise_fill(seed, shape, device="cuda"):
+    """Materialises the noise tensor a NoiseSeed stands for (tests)."""
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    _lib.check(_lib.load().dsee_noise_fill(int(seed), _p(out), out.numel(), _stream()))
+    return out
+
+
 def _chk_cuda(*ts):
     for t in ts:
-        if t is not None:
+        if t is not None and not isinstance(t, NoiseSeed):
             if not t.is_cuda:
                 raise RuntimeError("deepsee_b200 ops need CUDA tensors (no CPU fallback exists)")
             if not t.is_contiguous():
@@ -224,15 +245,18 @@ def conv3x3(sources, pw, bias, residual=None, res_ups=0, noises=(), passes=3, wa
     epi.act_mask = act_mask.data_ptr() if act_mask is not None else 0
     epi.residual = residual.data_ptr() if residual is not None else 0
     epi.res_ups = res_ups
-    noises = [n for n in noises if n is not None]
+    noises = [n for n in noises if n is not None and n[0] is not None]
     assert len(noises) <= 2
     for i in range(2):
         if i < len(noises):
             _chk_cuda(noises[i][0], noises[i][1])
-            epi.noise[i] = noises[i][0].data_ptr()
+            ptr, seed = _noise(noises[i][0])
+            epi.noise[i] = ptr.value or 0
+            epi.noise_seed[i] = seed
             epi.noise_w[i] = noises[i][1].data_ptr()
         else:
             epi.noise[i] = 0
+            epi.noise_seed[i] = 0
             epi.noise_w[i] = 0
     epi.out = out.data_ptr()
     epi.stats_partial = stats.data_ptr() if stats is not None else 0
@@ -259,7 +283,8 @@ def spade_modulate(sources, pw, x, x_ups, bn_scale, bn_shift, gamma_bias, beta_b
     lo = torch.empty_like(hi) if want_lo else None
     m = _lib.ModulateArgs()
     m.x, m.x_ups = x.data_ptr(), x_ups
-    m.noise = noise.data_ptr() if noise is not None else 0
+    nptr, nseed = _noise(noise)
+    m.noise, m.noise_seed = nptr.value or 0, nseed
     m.noise_w = noise_w.data_ptr() if noise_w is not None else 0
     m.bn_scale, m.bn_shift = bn_scale.data_ptr(), bn_shift.data_ptr()
     m.gamma_bias, m.beta_bias = gamma_bias.data_ptr(), beta_bias.data_ptr()
@@ -292,7 +317,8 @@ def spade_modulate_bwd_saved(g_planes, x, x_ups, bn_scale, bn_shift, dt, dt_amax
     glo = torch.empty_like(ghi) if want_lo else None
     ginv = torch.empty(1, dtype=torch.float32, device=dev)
     part = torch.empty((lib.dsee_grad_prep_blocks(B * H * W), Cc, 4), dtype=torch.float32, device=dev)
-    _lib.check(lib.dsee_spade_modulate_bwd_saved(_p(x), x_ups, _p(noise), _p(noise_w), _p(bn_scale),
+    nptr, nseed = _noise(noise)
+    _lib.check(lib.dsee_spade_modulate_bwd_saved(_p(x), x_ups, nptr, nseed, _p(noise_w), _p(bn_scale),
                                                  _p(bn_shift), _p(g_planes.hi), _p(g_planes.lo), _p(dt),
                                                  _p(dt_amax), B, H, W, Cc, _p(dxhat), _p(ghi), _p(glo),
                                                  _p(ginv), _p(part), _stream()))
@@ -315,8 +341,9 @@ def grad_prep(dy, noise0=None, noise1=None, want_lo=True):
     nq = 1 + (noise0 is not None) + (noise1 is not None)
     nb = lib.dsee_grad_prep_blocks(npix)
     part = torch.empty((nb, Cc, nq), dtype=torch.float32, device=dy.device)
-    _lib.check(lib.dsee_grad_prep(_p(dy), _p(hi), _p(lo), _p(inv), _p(noise0), _p(noise1), npix, Cc,
-                                  _p(part), _stream()))
+    (p0, s0), (p1, s1) = _noise(noise0), _noise(noise1)
+    _lib.check(lib.dsee_grad_prep(_p(dy), _p(hi), _p(lo), _p(inv), p0, p1, s0, s1, npix, Cc, _p(part),
+                                  _stream()))
     return GradPlanes(hi, lo, inv), reduce_partials(part)
 
 
@@ -389,6 +416,9 @@ def spade_modulate_bwd(sources, pw_gamma, x, x_ups, bn_scale, bn_shift, gamma_bi
     part = torch.empty((lib.dsee_conv3x3_stats_tiles(B, H, W), Cc, 4), dtype=torch.float32, device=dev)
     m = _lib.ModulateBwdArgs()
     m.x, m.x_ups = x.data_ptr(), x_ups
+    if isinstance(noise, NoiseSeed):
+        raise RuntimeError("the GEMM-recompute K1 backward takes explicit noise tensors only; "
+                           "keep DSEE_SAVE_GAMMA=1 (default) with in-kernel noise")
     m.noise = noise.data_ptr() if noise is not None else 0
     m.noise_w = noise_w.data_ptr() if noise_w is not None else 0
     m.bn_scale, m.bn_shift = bn_scale.data_ptr(), bn_shift.data_ptr()
@@ -414,7 +444,8 @@ def bn_bwd(dxhat, x, x_ups, bn_scale, bn_shift, sums, inv_count, noise=None, noi
     if noise is not None:
         nwp = torch.empty((lib.dsee_bn_bwd_blocks(B, Hx, Wx), Cc, 1), dtype=torch.float32,
                           device=x.device)
-    _lib.check(lib.dsee_bn_bwd(_p(dxhat), _p(x), x_ups, _p(noise), _p(noise_w), _p(bn_scale),
+    nptr, nseed = _noise(noise)
+    _lib.check(lib.dsee_bn_bwd(_p(dxhat), _p(x), x_ups, nptr, nseed, _p(noise_w), _p(bn_scale),
                                _p(bn_shift), _p(sums), float(inv_count), _p(dskip), B, Hx, Wx, Cc,
                                _p(dx), _p(nwp), _stream()))
     return dx, (reduce_partials(nwp)[0] if nwp is not None else None)
@@ -532,10 +563,11 @@ def bn_stats(x, x_ups=0, noise=None, noise_w=None):
     H, W = Hx << x_ups, Wx << x_ups
     n = C.c_int(0)
     lib = _lib.load()
-    _lib.check(lib.dsee_bn_stats(C.c_void_p(0), x_ups, C.c_void_p(0), C.c_void_p(0), B, H, W, Cc,
+    _lib.check(lib.dsee_bn_stats(C.c_void_p(0), x_ups, C.c_void_p(0), 0, C.c_void_p(0), B, H, W, Cc,
                                  C.c_void_p(0), C.byref(n), _stream()))
     part = torch.empty((n.value, Cc, 2), dtype=torch.float32, device=x.device)
-    _lib.check(lib.dsee_bn_stats(_p(x), x_ups, _p(noise), _p(noise_w), B, H, W, Cc, _p(part),
+    nptr, nseed = _noise(noise)
+    _lib.check(lib.dsee_bn_stats(_p(x), x_ups, nptr, nseed, _p(noise_w), B, H, W, Cc, _p(part),
                                  C.byref(n), _stream()))
     return part
 

@@ -54,6 +54,14 @@ int dsee_labels_from_onehot(const float* onehot, uint8_t* labels, int B, int L, 
 int dsee_resize_labels(const uint8_t* in, uint8_t* out, int B, int Hin, int Win, int Hout,
                        int Wout, void* stream);
 
+/* ---- noise injection ---------------------------------------------------------------------------- */
+/* NoiseInjection (normalization.py:299-304) draws a fresh N(0,1) tensor per forward.  Every entry
+ * point that takes a `noise` tensor also takes a `noise_seed`: with noise == NULL and a non-zero
+ * seed the tensor's elements are regenerated on the fly (Philox4x32-10 keyed by the seed, counter =
+ * NHWC element index / 4, Box-Muller), identically in every kernel, and never touch HBM.
+ * dsee_noise_fill materialises exactly that tensor (tests; n % 4 == 0). */
+int dsee_noise_fill(unsigned long long seed, float* out, int64_t n, void* stream);
+
 /* ---- conditional-norm operand builders ------------------------------------------------------ */
 /* Replaces mlp_shared = Conv2d(L, nh, 3, pad 1) + ReLU over the one-hot map
  * (normalization.py:98-101,114 / 149-152,175 / 239-242,262) as a 9-tap table gather:
@@ -145,6 +153,9 @@ typedef struct {
     float* amax_out;
     /* fuse LeakyReLU(0.2) after the bias (discriminator.py:84-85) */
     int lrelu;
+    /* when noise[i] is NULL and noise_seed[i] != 0 the noise tensor is regenerated in the kernel
+     * from the counter-based generator (see dsee_noise_fill) instead of being read from HBM */
+    unsigned long long noise_seed[2];
 } dsee_conv_epilogue;
 int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_epilogue* epi, void* stream);
 int dsee_conv3x3_stats_tiles(int B, int H, int W);
@@ -220,6 +231,7 @@ typedef struct {
      * the backward pass (dsee_spade_modulate_bwd_saved) does not re-run the gamma GEMM */
     void* g_hi;
     void* g_lo;
+    unsigned long long noise_seed; /* used when noise == NULL and noise_w != NULL */
 } dsee_modulate_args;
 int dsee_spade_modulate_fwd(const dsee_conv_operands* ops, const dsee_modulate_args* mod,
                             void* stream);
@@ -270,11 +282,11 @@ int dsee_spade_modulate_bwd(const dsee_conv_operands* ops, const dsee_modulate_b
  * 2^-e, [1] is scratch), plus per-channel block partials of
  * (sum dY, sum dY*noise0, sum dY*noise1) = gradients of a conv bias (architecture.py:98,122) and of
  * NoiseInjection.weight (normalization.py:299-304).  partial fp32 [dsee_grad_prep_blocks()][C][nq],
- * nq = 1 + (noise0 != NULL) + (noise1 != NULL); reduce with dsee_reduce_partials. */
+ * nq = 1 + (noise0 or seed0 given) + (noise1 or seed1 given); reduce with dsee_reduce_partials. */
 int dsee_grad_prep_blocks(int64_t npix);
 int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, float* inv_scale,
-                   const float* noise0, const float* noise1, int64_t npix, int C, float* partial,
-                   void* stream);
+                   const float* noise0, const float* noise1, unsigned long long seed0,
+                   unsigned long long seed1, int64_t npix, int C, float* partial, void* stream);
 /* out[k][c] = scale * sum_s partial[s][c][k]  (double accumulation, fixed order). */
 int dsee_reduce_partials(const float* partial, int n, int C, int nq, float scale, float* out,
                          void* stream);
@@ -307,7 +319,7 @@ int dsee_conv3x3_wgrad2(const void* dy_hi, const void* dy_lo, const float* dy_in
  * [dsee_bn_bwd_blocks()][C] = block partials of sum(dxin*noise) (gradient of noise_in.weight). */
 int dsee_bn_bwd_blocks(int B, int Hx, int Wx);
 int dsee_bn_bwd(const float* dxhat, const float* x, int x_ups, const float* noise,
-                const float* noise_w, const float* bn_scale, const float* bn_shift,
+                unsigned long long noise_seed, const float* noise_w, const float* bn_scale, const float* bn_shift,
                 const float* sums, float inv_count, const float* dskip, int B, int Hx, int Wx, int C,
                 float* dx, float* nw_partial, void* stream);
 /* Backward of dsee_shared_mlp_fwd: gradient of the 9-tap table and bias.  dsrc fp32 NHWC with row
@@ -347,7 +359,8 @@ int dsee_head_bwd(const float* x, const float* w, const float* out, const float*
 /* K1 backward from the saved G planes (no GEMM; one streaming pass, HBM bound: reads x, dt, G,
  * writes dxhat and the dgb planes).  Same outputs as dsee_spade_modulate_bwd; partial fp32
  * [dsee_grad_prep_blocks(B*H*W)][C][4]. */
-int dsee_spade_modulate_bwd_saved(const float* x, int x_ups, const float* noise, const float* noise_w,
+int dsee_spade_modulate_bwd_saved(const float* x, int x_ups, const float* noise,
+                                  unsigned long long noise_seed, const float* noise_w,
                                   const float* bn_scale, const float* bn_shift, const void* g_hi,
                                   const void* g_lo, const float* dt, const float* dt_amax, int B, int H,
                                   int W, int C, float* dxhat, void* dgb_hi, void* dgb_lo,
@@ -357,8 +370,9 @@ int dsee_spade_modulate_bwd_saved(const float* x, int x_ups, const float* noise,
 /* Per-channel sum / sum of squares of x (+ noise) at the post-upsample resolution, written as
  * tile partials like the K2 epilogue does.  Replaces the statistics half of
  * SynchronizedBatchNorm2d.forward (batchnorm.py:72-76) for tensors K2 did not produce. */
-int dsee_bn_stats(const float* x, int x_ups, const float* noise, const float* noise_w, int B, int H,
-                  int W, int C, float* stats_partial, int* n_partials, void* stream);
+int dsee_bn_stats(const float* x, int x_ups, const float* noise, unsigned long long noise_seed,
+                  const float* noise_w, int B, int H, int W, int C, float* stats_partial,
+                  int* n_partials, void* stream);
 /* Reduces partials [n_partials][C][2] in a fixed order (double accumulation) and produces
  * bn_scale = 1/sqrt(var+eps), bn_shift = -mean*bn_scale; when running_mean/var are non-NULL also
  * updates them with momentum and the unbiased variance (batchnorm.py:84-93). count = number of

@@ -66,17 +66,18 @@ def main():
     torch.cuda.profiler.start()
     timed("K2 conv3x3 fwd", lambda: ops.conv3x3([act], pw, bias, residual=x, passes=a.passes, want_stats=True),
           2 * 9 * C * C * px)
-    timed("K1 modulate fwd", lambda: ops.spade_modulate([actv, smap], pwm, x, 0, sc, sh, gb, bb, passes=a.passes,
-                                                        want_lo=want_lo), 2 * 9 * (nh + d) * 2 * C * px)
+    _, gsaved = timed("K1 modulate fwd", lambda: ops.spade_modulate([actv, smap], pwm, x, 0, sc, sh, gb, bb,
+                                                                    passes=a.passes, want_lo=want_lo, save_g=True),
+                      2 * 9 * (nh + d) * 2 * C * px)
     dt, amax = timed("dgrad (K2 bwd-data)", lambda: ops.conv3x3([gp], pwT, None, passes=a.passes, act_mask=act.hi,
                                                                 want_amax=True, tag="dgrad"), 2 * 9 * C * C * px)
     timed("wgrad 512x512", lambda: ops.conv3x3_wgrad(gp, act, passes=a.passes), 2 * 9 * C * C * px)
-    dxhat, dgb, sums = timed("K1 backward", lambda: ops.spade_modulate_bwd([actv, smap], pwg, x, 0, sc, sh, gb, dt,
-                                                                           amax, passes=a.passes, want_lo=want_lo),
-                             2 * 9 * (nh + d) * C * px)
+    dxhat, dgb, sums = timed("K1 backward (saved G)", lambda: ops.spade_modulate_bwd_saved(
+        gsaved, x, 0, sc, sh, dt, amax, want_lo=want_lo), 0.0)
     timed("dgrad_mod", lambda: ops.conv3x3([dgb], pwmT, None, passes=a.passes, tag="dgrad_mod"),
           2 * 9 * (nh + d) * 2 * C * px)
-    timed("wgrad modulation", lambda: ops.conv3x3_wgrad(dgb, actv, passes=a.passes), 2 * 9 * nh * 2 * C * px)
+    timed("wgrad modulation", lambda: ops.conv3x3_wgrad_multi(dgb, [actv, smap], passes=a.passes),
+          2 * 9 * (nh + d) * 2 * C * px)
     torch.cuda.profiler.stop()
 
 

@@ -152,3 +152,51 @@ def test_generator_backward_eval_mode():
     fwd_err, worst, zrel, _ = _run_case(name, over, 3, train=False)
     print("eval-mode: fwd %.3e worst %.3e (%s) dz %.3e" % (fwd_err, worst[1], worst[0], zrel))
     assert worst[1] < 2e-3 and zrel < 2e-3
+
+
+def test_in_kernel_noise_matches_materialised_stream():
+    """NoiseInjection in production is a seed: every kernel regenerates the tensor's elements
+    (Philox4x32-10 + Box-Muller).  (a) the stream is N(0,1); (b) a training forward+backward run on
+    seeds equals, bit for bit, the same run fed the tensors dsee_noise_fill materialises from those
+    seeds - i.e. statistics pass, K1, K2 epilogues and the backward kernels all see identical noise."""
+    from deepsee_b200 import ops
+    z = ops.noise_fill(12345, (4, 32, 32, 128))
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.var()) - 1.0) < 1e-2
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.1          # kurtosis of a normal
+    flat = z.flatten()
+    assert abs(float((flat[:-1] * flat[1:]).mean())) < 5e-3  # neighbours uncorrelated
+    assert not torch.equal(z, ops.noise_fill(12346, (4, 32, 32, 128)))
+
+    name, over = CASES["8x"]
+    o = O.make_opt(name, is_train=True, **over)
+    sd = O.make_generator_state(o, 0)
+    d = O.preprocess(o, O.synthetic_batch(o, 2, seed=3))
+    zst = (torch.rand(2, 19, 128, generator=torch.Generator().manual_seed(4)) * 2 - 1).cuda()
+    proj = torch.randn(2, 3, o.crop_size, o.crop_size, generator=torch.Generator().manual_seed(5)).cuda()
+
+    def run(materialise):
+        G = _build_G(o, sd).train()
+        seeds = {}
+        for pfx, _, _ in O.generator_layout(o):
+            blk = G.get_submodule(pfx[:-1])
+            for k, nm in enumerate(("noise_in", "noise_skip", "noise_middle")):
+                seed = 1000 + 7 * len(seeds)
+                seeds[pfx + nm] = seed
+                C = getattr(blk, nm).n_channels
+                if materialise:
+                    getattr(blk, nm).sample = (lambda s, C: (lambda B, H, W: ops.noise_fill(s, (B, H, W, C))))(seed, C)
+                else:
+                    getattr(blk, nm).sample = (lambda s: (lambda B, H, W: ops.NoiseSeed(s)))(seed)
+        zz = zst.clone().requires_grad_(True)
+        out = G(d["image_lr"].cuda(), seg=d["input_semantics"].cuda(), z=zz)
+        (out * proj).sum().backward()
+        torch.cuda.synchronize()
+        return out.detach(), zz.grad, {k: p.grad for k, p in G.named_parameters() if p.grad is not None}
+
+    out_s, dz_s, g_s = run(False)
+    out_t, dz_t, g_t = run(True)
+    assert torch.equal(out_s, out_t)
+    assert torch.equal(dz_s, dz_t)
+    for k in g_t:
+        assert torch.equal(g_s[k], g_t[k]), k
+    assert any("noise_in.weight" in k for k in g_s)
