@@ -238,21 +238,29 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// out[i] = sum_s partial[s][i] (fixed order), optionally transposing [n][9][c] -> [n][c][9]
+// out = sum_s partial[s] (fixed order), optionally transposing [n][T][c] -> [n][c][T].
+// block = (n, 32-channel slab): coalesced reads of T x 32 partial rows, smem transpose, coalesced
+// write of the 32*T contiguous outputs.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                     int splits, int n_total, int c_total, int to_nc9, int T) {
+    __shared__ float tile[16][33];
+    const int cblocks = c_total / 32;
+    const int n = blockIdx.x / cblocks, c0 = (blockIdx.x % cblocks) * 32;
     const int64_t total = (int64_t)n_total * T * c_total;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
+    const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;  // 32 x 16 threads
     float a = 0.f;
-    for (int s = 0; s < splits; ++s) a += partial[(size_t)s * total + i];
-    if (to_nc9) {
-        const int c = (int)(i % c_total);
-        const int tap = (int)((i / c_total) % T);
-        const int n = (int)(i / ((int64_t)T * c_total));
-        out[((size_t)n * c_total + c) * T + tap] = a;
-    } else {
-        out[i] = a;
+    if (row < T) {
+        const size_t i = ((size_t)n * T + row) * c_total + c0 + lane;
+        for (int s = 0; s < splits; ++s) a += __ldg(partial + (size_t)s * total + i);
+        if (!to_nc9) out[i] = a;
+        tile[row][lane] = a;
+    }
+    if (!to_nc9) return;
+    __syncthreads();
+    // out[(n*c_total + c0 + cl) * T + tap], contiguous over (cl, tap)
+    for (int e = threadIdx.x; e < 32 * T; e += blockDim.x) {
+        const int cl = e / T, tap = e % T;
+        out[((size_t)n * c_total + c0) * T + e] = tile[tap][cl];
     }
 }
 
@@ -368,8 +376,9 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
     count_launch();
     DSEE_CUDA(cudaGetLastError());
     const int64_t total = (int64_t)n_total * T * c_total;
-    wgrad_reduce_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(workspace, dw, p.splits, n_total,
-                                                                    c_total, layout_nc9, T);
+    (void)total;
+    wgrad_reduce_kernel<<<n_total * (c_total / 32), 512, 0, st>>>(workspace, dw, p.splits, n_total, c_total,
+                                                                  layout_nc9, T);
     count_launch();
     DSEE_CUDA(cudaGetLastError());
     return 0;
