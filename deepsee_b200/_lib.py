@@ -26,6 +26,8 @@ SYMBOLS = [
     "dsee_stem_fwd", "dsee_head_fwd",
     "dsee_conv2d_direct_fwd", "dsee_instance_norm_fwd", "dsee_instance_norm_workspace_bytes", "dsee_region_pool_chunks",
     "dsee_region_pool_fwd", "dsee_nchw_to_nhwc", "dsee_disc_input", "dsee_avgpool3s2_fwd",
+    "dsee_spectral_workspace_floats", "dsee_spectral_weight_fwd", "dsee_spectral_weight_bwd",
+    "dsee_modweight_fwd", "dsee_modweight_bwd_workspace_bytes", "dsee_modweight_bwd",
     "dsee_act_bwd", "dsee_conv2d_direct_dgrad", "dsee_conv2d_direct_wgrad_workspace_floats",
     "dsee_conv2d_direct_wgrad", "dsee_channel_sum_chunks", "dsee_channel_sum",
     "dsee_instance_norm_bwd", "dsee_region_pool_bwd", "dsee_avgpool3s2_bwd", "dsee_disc_input_bwd",
@@ -82,6 +84,21 @@ class ModulateBwdArgs(C.Structure):
         ("dxhat", C.c_void_p), ("dgb_hi", C.c_void_p), ("dgb_lo", C.c_void_p),
         ("partial", C.c_void_p), ("C", C.c_int),
         ("dt_amax", C.c_void_p), ("dgb_inv_scale", C.c_void_p),
+    ]
+
+
+class ModWeightArgs(C.Structure):
+    _fields_ = [
+        ("w_seg", C.c_void_p * 2), ("w_sty", C.c_void_p * 2), ("b_seg", C.c_void_p * 2),
+        ("b_sty", C.c_void_p * 2), ("alpha", C.c_void_p * 2),
+        ("C", C.c_int), ("c1", C.c_int), ("c2", C.c_int), ("plus_one", C.c_int),
+    ]
+
+
+class ModWeightGrads(C.Structure):
+    _fields_ = [
+        ("dw_seg", C.c_void_p * 2), ("dw_sty", C.c_void_p * 2), ("db_seg", C.c_void_p * 2),
+        ("db_sty", C.c_void_p * 2), ("dalpha", C.c_void_p * 2),
     ]
 
 
@@ -152,6 +169,10 @@ def load():
         "dsee_nchw_to_nhwc": [vp, vp, i, i, i, i, i, vp],
         "dsee_disc_input": [vp, vp, vp, vp, i, i, i, i, i, vp],
         "dsee_avgpool3s2_fwd": [vp, vp, i, i, i, i, vp],
+        "dsee_spectral_weight_fwd": [vp, vp, vp, i, i, i, f, vp, vp, vp, vp],
+        "dsee_spectral_weight_bwd": [vp, vp, vp, vp, vp, i, i, vp, vp, vp],
+        "dsee_modweight_fwd": [C.POINTER(ModWeightArgs), vp, vp, vp, vp],
+        "dsee_modweight_bwd": [C.POINTER(ModWeightArgs), vp, vp, vp, C.POINTER(ModWeightGrads), vp, vp],
         "dsee_act_bwd": [vp, vp, vp, i64, i, vp],
         "dsee_conv2d_direct_dgrad": [vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp],
         "dsee_conv2d_direct_wgrad": [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp],
@@ -168,6 +189,10 @@ def load():
         fn.restype = C.c_int
     lib.dsee_conv3x3_wgrad_workspace_floats.argtypes = [i, i, i, i, i]
     lib.dsee_conv3x3_wgrad_workspace_floats.restype = C.c_int64
+    lib.dsee_spectral_workspace_floats.argtypes = [i, i]
+    lib.dsee_spectral_workspace_floats.restype = C.c_int64
+    lib.dsee_modweight_bwd_workspace_bytes.argtypes = [i, i, i]
+    lib.dsee_modweight_bwd_workspace_bytes.restype = C.c_int64
     lib.dsee_instance_norm_workspace_bytes.argtypes = [i, i, i]
     lib.dsee_instance_norm_workspace_bytes.restype = C.c_int64
     lib.dsee_conv2d_tc_wgrad_workspace_floats.argtypes = [i, i, i, i, i, i, i]

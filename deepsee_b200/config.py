@@ -15,6 +15,10 @@ class _Config:
     overlap_wgrad = os.environ.get("DSEE_OVERLAP_WGRAD", "1") != "0"
     # NoiseInjection: 0 = in-kernel counter-based noise (never in HBM), 1 = torch.randn tensors.
     noise_tensors = os.environ.get("DSEE_NOISE_TENSORS", "0") == "1"
+    # Debug switches: run torch's own spectral-norm hook / build the modulation weight from torch ops
+    # instead of the fused kernels (ops.SpectralWeightFn / ops.ModWeightFn).
+    torch_spectral = os.environ.get("DSEE_TORCH_SPECTRAL", "0") == "1"
+    torch_modweight = os.environ.get("DSEE_TORCH_MODWEIGHT", "0") == "1"
     # Verify (one device->host read per generator forward) that the semantic input is one-hot.
     check_onehot = os.environ.get("DSEE_CHECK_ONEHOT", "1") != "0"
 

@@ -27,12 +27,22 @@ BN_EPS = 1e-5
 
 
 def effective_weight(conv):
-    """Weight a (possibly spectral-normalised) conv would use in its forward: runs torch's
-    spectral-norm pre-forward hook (one power iteration in training mode, W_orig / sigma) without
-    running the conv (architecture.py:40-44; torch/nn/utils/spectral_norm.py)."""
+    """Weight a (possibly spectral-normalised) conv uses in its forward (architecture.py:40-44;
+    torch/nn/utils/spectral_norm.py:92-113): one power iteration in training mode (u / v buffers
+    updated in place), W_orig / sigma, u and v constants for autograd.  The module keeps torch's
+    parametrisation (weight_orig / weight_u / weight_v in the state_dict); the arithmetic runs in
+    ops.SpectralWeightFn.  DSEE_TORCH_SPECTRAL=1 runs torch's own hook instead."""
+    from ...config import config
+    if not hasattr(conv, 'weight_orig'):
+        return conv.weight
+    if config.torch_spectral or not conv.weight_orig.is_cuda:
+        for hook in conv._forward_pre_hooks.values():
+            hook(conv, None)
+        return conv.weight
+    eps = 1e-12
     for hook in conv._forward_pre_hooks.values():
-        hook(conv, None)
-    return conv.weight
+        eps = getattr(hook, 'eps', eps)
+    return ops.SpectralWeightFn.apply(conv.weight_orig, conv.weight_u, conv.weight_v, conv.training, eps)
 
 
 def get_nonspade_norm_layer(opt, norm_type='instance', oneD=False):
@@ -161,8 +171,26 @@ class _CondNormBase(nn.Module):
         return [style_map], meta
 
     def combined_weight(self):
-        """-> (W [2C, Cin_total, 3, 3] rows interleaved, gamma_bias [C], beta_bias [C]); plain
-        torch ops so autograd carries gradients back to the individual parameters."""
+        """-> (W [2C, Cin_total, 3, 3] rows interleaved, gamma_bias [C], beta_bias [C]) as one fused
+        autograd node (ops.ModWeightFn); DSEE_TORCH_MODWEIGHT=1 builds it from torch ops."""
+        from ...config import config
+        if config.torch_modweight:
+            return self.combined_weight_torch()
+        g, b = getattr(self, 'mlp_gamma', None), getattr(self, 'mlp_beta', None)
+        sg, sb = getattr(self, 'mlp_style_gamma', None), getattr(self, 'mlp_style_beta', None)
+        if self.kind == 'spade':
+            sg = sb = None
+        elif self.kind == 'puresean':
+            g = b = None
+        w = lambda m: m.weight if m is not None else None
+        bi = lambda m: m.bias if m is not None else None
+        two = g is not None and sg is not None
+        return ops.ModWeightFn.apply(self.kind != 'puresean', w(g), w(b), w(sg), w(sb), bi(g), bi(b),
+                                     bi(sg), bi(sb), self.alpha_gamma if two else None,
+                                     self.alpha_beta if two else None)
+
+    def combined_weight_torch(self):
+        """The same tensors from plain torch ops (reference for the fused node's tests)."""
         if self.kind == 'spade':
             wg, wb = self.mlp_gamma.weight, self.mlp_beta.weight
             gb, bb = self.mlp_gamma.bias + 1.0, self.mlp_beta.bias

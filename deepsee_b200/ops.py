@@ -1003,3 +1003,98 @@ class DiscInputFn(torch.autograd.Function):
         dfake = torch.empty((B, 3, H, W), dtype=torch.float32, device=dx.device)
         _lib.check(_lib.load().dsee_disc_input_bwd(_p(dx), _p(dfake), B, L, H, W, Cp, _stream()))
         return None, dfake, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter-side fusions: spectral normalisation and the modulation-weight assembly
+# ---------------------------------------------------------------------------------------------
+class SpectralWeightFn(torch.autograd.Function):
+    """W_eff = W_orig / sigma with torch.nn.utils.spectral_norm's semantics (one power iteration in
+    training mode, updating the u / v buffers in place; stored u, v in eval mode; u, v are constants
+    for autograd) in 3-5 kernels instead of ~12 ATen launches."""
+
+    @staticmethod
+    def forward(ctx, w_orig, u, v, training, eps):
+        _chk_cuda(w_orig, u, v)
+        N = w_orig.shape[0]
+        K = w_orig.numel() // N
+        lib = _lib.load()
+        ws = torch.empty(lib.dsee_spectral_workspace_floats(N, K), dtype=torch.float32, device=w_orig.device)
+        sig = torch.empty(2, dtype=torch.float32, device=w_orig.device)
+        w_eff = torch.empty_like(w_orig)
+        _lib.check(lib.dsee_spectral_weight_fwd(_p(w_orig), _p(u), _p(v), N, K, int(training), float(eps),
+                                                _p(ws), _p(sig), _p(w_eff), _stream()))
+        # u / v are overwritten by the next forward; the backward needs this forward's values
+        ctx.save_for_backward(w_eff, u.clone(), v.clone(), sig)
+        return w_eff
+
+    @staticmethod
+    def backward(ctx, dw_eff):
+        w_eff, u, v, sig = ctx.saved_tensors
+        dw_eff = dw_eff.contiguous()
+        N = w_eff.shape[0]
+        K = w_eff.numel() // N
+        ws = torch.empty(128, dtype=torch.float64, device=w_eff.device)
+        dw = torch.empty_like(w_eff)
+        _lib.check(_lib.load().dsee_spectral_weight_bwd(_p(dw_eff), _p(w_eff), _p(u), _p(v), _p(sig), N, K,
+                                                        _p(ws), _p(dw), _stream()))
+        return dw, None, None, None, None
+
+
+class ModWeightFn(torch.autograd.Function):
+    """K1's fused modulation weight (interleaved gamma|beta rows over [seg | style] columns, alpha
+    blend folded in) and its two bias vectors from the reference's separate parameters: one kernel
+    forward, two backward.  Inputs that do not exist for a layer kind are None."""
+
+    @staticmethod
+    def forward(ctx, plus_one, wg, wb, wsg, wsb, bg, bb, bsg, bsb, ag, ab):
+        ref = wg if wg is not None else wsg
+        Cc = ref.shape[0]
+        c1 = wg.shape[1] if wg is not None else 0
+        c2 = wsg.shape[1] if wsg is not None else 0
+        tensors = [wg, wb, wsg, wsb, bg, bb, bsg, bsb, ag, ab]
+        tensors = [t.contiguous() if t is not None else None for t in tensors]
+        _chk_cuda(*tensors)
+        args = _modweight_args(tensors, Cc, c1, c2, plus_one)
+        wm = torch.empty((2 * Cc, c1 + c2, 3, 3), dtype=torch.float32, device=ref.device)
+        gbias = torch.empty(Cc, dtype=torch.float32, device=ref.device)
+        bbias = torch.empty(Cc, dtype=torch.float32, device=ref.device)
+        _lib.check(_lib.load().dsee_modweight_fwd(C.byref(args), _p(wm), _p(gbias), _p(bbias), _stream()))
+        ctx.meta = (Cc, c1, c2, plus_one)
+        ctx.save_for_backward(*[t for t in tensors if t is not None])
+        ctx.present = [t is not None for t in tensors]
+        return wm, gbias, bbias
+
+    @staticmethod
+    def backward(ctx, dwm, dgb, dbb):
+        Cc, c1, c2, plus_one = ctx.meta
+        it = iter(ctx.saved_tensors)
+        tensors = [next(it) if p else None for p in ctx.present]
+        args = _modweight_args(tensors, Cc, c1, c2, plus_one)
+        dev = dwm.device
+        grads = [torch.empty_like(t) if t is not None else None for t in tensors]
+        g = _lib.ModWeightGrads()
+        for i in range(2):
+            g.dw_seg[i] = grads[0 + i].data_ptr() if grads[0 + i] is not None else 0
+            g.dw_sty[i] = grads[2 + i].data_ptr() if grads[2 + i] is not None else 0
+            g.db_seg[i] = grads[4 + i].data_ptr() if grads[4 + i] is not None else 0
+            g.db_sty[i] = grads[6 + i].data_ptr() if grads[6 + i] is not None else 0
+            g.dalpha[i] = grads[8 + i].data_ptr() if grads[8 + i] is not None else 0
+        lib = _lib.load()
+        ws = torch.empty(lib.dsee_modweight_bwd_workspace_bytes(Cc, c1, c2), dtype=torch.uint8, device=dev)
+        _lib.check(lib.dsee_modweight_bwd(C.byref(args), _p(dwm.contiguous()), _p(dgb.contiguous()),
+                                          _p(dbb.contiguous()), C.byref(g), _p(ws), _stream()))
+        return (None, *grads)
+
+
+def _modweight_args(tensors, Cc, c1, c2, plus_one):
+    wg, wb, wsg, wsb, bg, bb, bsg, bsb, ag, ab = tensors
+    a = _lib.ModWeightArgs()
+    ptr = lambda t: t.data_ptr() if t is not None else 0
+    a.w_seg[0], a.w_seg[1] = ptr(wg), ptr(wb)
+    a.w_sty[0], a.w_sty[1] = ptr(wsg), ptr(wsb)
+    a.b_seg[0], a.b_seg[1] = ptr(bg), ptr(bb)
+    a.b_sty[0], a.b_sty[1] = ptr(bsg), ptr(bsb)
+    a.alpha[0], a.alpha[1] = ptr(ag), ptr(ab)
+    a.C, a.c1, a.c2, a.plus_one = Cc, c1, c2, int(plus_one)
+    return a

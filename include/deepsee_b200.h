@@ -462,6 +462,49 @@ int dsee_avgpool3s2_bwd(const float* dout, float* din, int B, int Hi, int Wi, in
 int dsee_disc_input_bwd(const float* dx, float* dfake, int B, int L, int H, int W, int Cp,
                         void* stream);
 
+/* ---- parameter-side fusions ---------------------------------------------------------------------- */
+/* Replaces torch.nn.utils.spectral_norm's compute_weight (torch/nn/utils/spectral_norm.py:92-113,
+ * applied at architecture.py:40-44 and normalization.py:29-31) for a weight viewed as [N][K]:
+ *   power_iteration (training): v <- normalize(W^T u), u <- normalize(W v)   (in place, eps inside max)
+ *   sigma = u . (W v);  w_eff = W / sigma;  sigma2 = {sigma, 1/sigma} (device float[2])
+ * workspace fp32 [dsee_spectral_workspace_floats(N,K)].  The backward treats u, v as constants like
+ * torch does:  dW = (dW_eff - <dW_eff, W_eff> u v^T) / sigma   (workspace: 128 doubles). */
+int64_t dsee_spectral_workspace_floats(int N, int K);
+int dsee_spectral_weight_fwd(const float* w_orig, float* u, float* v, int N, int K, int power_iteration,
+                             float eps, float* workspace, float* sigma2, float* w_eff, void* stream);
+int dsee_spectral_weight_bwd(const float* dw_eff, const float* w_eff, const float* u, const float* v,
+                             const float* sigma2, int N, int K, void* workspace, float* dw_orig,
+                             void* stream);
+/* Assembly of K1's fused modulation weight from the reference's separate convs
+ * (normalization.py:116-119 SPADE, :198-213 SEAN with the sigmoid(alpha) blend, :283-286 PureSEAN):
+ * rows interleaved per 128 channels [gamma | beta], columns [seg source (c1) | style source (c2)],
+ *   Wm[gamma c] = [(1-a_g) Wg[c] | a_g Wsg[c]],  gamma_bias = (1-a_g) bg + a_g bsg (+1 if plus_one)
+ * with a = sigmoid(alpha) for two sources, 0 for the seg source only, 1 for the style source only.
+ * index 0 = gamma, 1 = beta.  The backward scatters dWm / d gamma_bias / d beta_bias to the sources
+ * and reduces d alpha deterministically. */
+typedef struct {
+    const float* w_seg[2];   /* mlp_gamma / mlp_beta weights [C][c1][3][3] or NULL */
+    const float* w_sty[2];   /* mlp_style_gamma / mlp_style_beta weights [C][c2][3][3] or NULL */
+    const float* b_seg[2];
+    const float* b_sty[2];
+    const float* alpha[2];   /* alpha_gamma / alpha_beta device scalars (two sources only) */
+    int C, c1, c2;
+    int plus_one;
+} dsee_modweight_args;
+typedef struct {
+    float* dw_seg[2];
+    float* dw_sty[2];
+    float* db_seg[2];
+    float* db_sty[2];
+    float* dalpha[2];
+} dsee_modweight_grads;
+int dsee_modweight_fwd(const dsee_modweight_args* args, float* wm, float* gamma_bias, float* beta_bias,
+                       void* stream);
+int64_t dsee_modweight_bwd_workspace_bytes(int C, int c1, int c2);
+int dsee_modweight_bwd(const dsee_modweight_args* args, const float* dwm, const float* dgamma_bias,
+                       const float* dbeta_bias, const dsee_modweight_grads* grads, void* workspace,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

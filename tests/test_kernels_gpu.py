@@ -462,3 +462,59 @@ def test_conv2d_tc_node(Cx, Cw, Cout, K, stride, pad, ups, lrelu, bias, passes):
     chk(w2.grad, w.grad, "wgrad")
     if bias:
         chk(b2.grad, b.grad, "dbias")
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter-side fusions
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(128, 128, 3, 3), (512, 512, 3, 3), (64, 32, 4, 4), (128, 256, 3, 3)])
+@pytest.mark.parametrize("training", [True, False])
+def test_spectral_weight_node_vs_torch(shape, training):
+    """ops.SpectralWeightFn against torch.nn.utils.spectral_norm's own hook: effective weight, the
+    in-place u / v power-iteration update and the gradient wrt weight_orig."""
+    import torch.nn as nn
+    from deepsee_b200 import ops
+    torch.manual_seed(shape[0] + shape[1])
+    conv = nn.utils.spectral_norm(nn.Conv2d(shape[1], shape[0], shape[2], padding=1)).cuda()
+    conv.train(training)
+    w0, u0, v0 = conv.weight_orig.detach().clone(), conv.weight_u.clone(), conv.weight_v.clone()
+    for hook in conv._forward_pre_hooks.values():
+        hook(conv, None)
+    ref = conv.weight
+    dy = torch.randn_like(ref)
+    ref.backward(dy)
+    w1 = w0.clone().requires_grad_(True)
+    u1, v1 = u0.clone(), v0.clone()
+    out = ops.SpectralWeightFn.apply(w1, u1, v1, training, 1e-12)
+    out.backward(dy)
+    torch.testing.assert_close(out, ref, rtol=2e-5, atol=1e-6)
+    torch.testing.assert_close(u1, conv.weight_u, rtol=2e-5, atol=1e-6)
+    torch.testing.assert_close(v1, conv.weight_v, rtol=2e-5, atol=1e-6)
+    g = conv.weight_orig.grad
+    assert (w1.grad - g).abs().max().item() <= 2e-5 * g.abs().max().item()
+
+
+@pytest.mark.parametrize("kind", ["spade", "sean", "puresean"])
+def test_modweight_node_vs_torch_ops(kind):
+    from deepsee_b200.deepsee_models.networks import normalization as Nz
+    from deepsee_b200.options.configurations import make_opt
+    opt = make_opt(None)
+    cls = {"spade": Nz.SPADE, "sean": Nz.SEAN_Block, "puresean": Nz.PureSEAN_Block}[kind]
+    torch.manual_seed(3)
+    m = cls("spadesyncbatch3x3" if kind == "spade" else "seansyncbatch3x3", 256, 19, opt).cuda()
+    for p in m.parameters():
+        torch.nn.init.normal_(p, 0.0, 0.3)
+    w_ref, gb_ref, bb_ref = m.combined_weight_torch()
+    dw, dg, db = torch.randn_like(w_ref), torch.randn_like(gb_ref), torch.randn_like(bb_ref)
+    ((w_ref * dw).sum() + (gb_ref * dg).sum() + (bb_ref * db).sum()).backward()
+    ref_grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad()
+    w, gb, bb = m.combined_weight()
+    torch.testing.assert_close(w, w_ref, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(gb, gb_ref, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(bb, bb_ref, rtol=1e-6, atol=1e-7)
+    ((w * dw).sum() + (gb * dg).sum() + (bb * db).sum()).backward()
+    got = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    assert set(got) == set(ref_grads), (sorted(got), sorted(ref_grads))
+    for k, r in ref_grads.items():
+        assert (got[k] - r).abs().max().item() <= 1e-4 * max(r.abs().max().item(), 1e-6), k
