@@ -20,6 +20,11 @@ class _Config:
     # instead of the fused kernels (ops.SpectralWeightFn / ops.ModWeightFn).
     torch_spectral = os.environ.get("DSEE_TORCH_SPECTRAL", "0") == "1"
     torch_modweight = os.environ.get("DSEE_TORCH_MODWEIGHT", "0") == "1"
+    # Multi-GPU batch-norm statistics: 0 = per-rank statistics (north_star: NCCL all-reduce "for G/D
+    # gradients only"), 1 = global-batch statistics like the reference's DataParallel mode
+    # (sync_batchnorm/batchnorm.py:63-93): one [2,C] all-reduce per norm layer forward and one
+    # [2,C] all-reduce per norm layer backward.
+    sync_bn = os.environ.get("DSEE_SYNC_BN", "0") == "1"
     # Verify (one device->host read per generator forward) that the semantic input is one-hot.
     check_onehot = os.environ.get("DSEE_CHECK_ONEHOT", "1") != "0"
 

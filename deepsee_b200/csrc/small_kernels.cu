@@ -118,6 +118,51 @@ __global__ void shared_mlp_kernel(const uint8_t* __restrict__ labels, const floa
         *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack2(l4[0], l4[1]), pack2(l4[2], l4[3]));
 }
 
+// Same computation with the whole 9 x L x nh table staged in shared memory (87.5 KB for L = 19,
+// nh = 128): persistent blocks, thread = (pixel lane, 4 hidden channels); the 9 gathers per output
+// become LDS.128 instead of L1/L2 round trips.  Summation order identical to shared_mlp_kernel.
+__global__ void __launch_bounds__(256)
+shared_mlp_smem_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ table,
+                       const float* __restrict__ bias, __half* __restrict__ out_hi,
+                       __half* __restrict__ out_lo, int B, int Hl, int Wl, int ups, int L, int nh) {
+    extern __shared__ float4 tab_sm[];  // [9][L][nh/4]
+    const int groups = nh >> 2;
+    const int n4 = 9 * L * groups;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) tab_sm[i] = __ldg(reinterpret_cast<const float4*>(table) + i);
+    __syncthreads();
+    const int g = threadIdx.x % groups, pl = threadIdx.x / groups, lanes = blockDim.x / groups;
+    const int H = Hl << ups, W = Wl << ups;
+    const int64_t npix = (int64_t)B * H * W;
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + g);
+    for (int64_t pix = (int64_t)blockIdx.x * lanes + pl; pix < npix; pix += (int64_t)gridDim.x * lanes) {
+        const int x = (int)(pix % W);
+        const int y = (int)((pix / W) % H);
+        const int b = (int)(pix / ((int64_t)W * H));
+        const int yl = y >> ups, xl = x >> ups;
+        const uint8_t* lb = labels + (size_t)b * Hl * Wl;
+        float4 acc = bv;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yy = yl + tap / 3 - 1, xx = xl + tap % 3 - 1;
+            if (yy < 0 || yy >= Hl || xx < 0 || xx >= Wl) continue;  // zero padding
+            const int l = lb[yy * Wl + xx];
+            const float4 t = tab_sm[((size_t)tap * L + l) * groups + g];
+            acc.x += t.x;
+            acc.y += t.y;
+            acc.z += t.z;
+            acc.w += t.w;
+        }
+        const float a[4] = {fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f)};
+        __half h[4], l4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_f16(a[e], h[e], l4[e]);
+        const size_t o = (size_t)pix * nh + (size_t)g * 4;
+        *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+        if (out_lo)
+            *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack2(l4[0], l4[1]), pack2(l4[2], l4[3]));
+    }
+}
+
 __global__ void style_gather_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ style,
                                     __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B,
                                     int HW, int L, int d) {
@@ -402,10 +447,15 @@ __global__ void stem_kernel(const float* __restrict__ x, const float* __restrict
     }
 }
 
-// warp per HEAD_PX horizontally adjacent pixels; lanes split the channels (float4 x 4 = 16 ch per
-// 128-channel slab); weights staged in smem as [tap][c][4] (3 outputs + pad).
+// Image head.  A warp owns a strip of HEAD_PX horizontally adjacent pixels x HEAD_ROWS output rows
+// and slides down it: every input row is loaded ONCE (6 columns x 16 channels per lane and 128-channel
+// slab, LeakyReLU applied on load) and feeds the three output rows it touches (ky = 2, 1, 0), so HBM/L2
+// read amplification is (HEAD_ROWS + 2) / HEAD_ROWS instead of 3.  Lanes split the channels; weights
+// are staged in smem as [tap][c][4] (3 outputs + pad).  Adjacent warps of a block take adjacent
+// column groups of the same strip, so the column halo is an L1 hit.
 constexpr int HEAD_PX = 4;
-__global__ void __launch_bounds__(256)
+constexpr int HEAD_ROWS = 16;
+__global__ void __launch_bounds__(256, 2)
 head_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
             float* __restrict__ out, int B, int H, int W, int C) {
     extern __shared__ float4 wsm[];  // [9][C]
@@ -417,67 +467,89 @@ head_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wgroups = (W + HEAD_PX - 1) / HEAD_PX;
-    const int64_t ngroups = (int64_t)B * H * wgroups;
-    for (int64_t grp = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; grp < ngroups;
-         grp += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-        const int xg = (int)(grp % wgroups);
-        const int yy = (int)((grp / wgroups) % H);
-        const int b = (int)(grp / ((int64_t)wgroups * H));
+    const int strips = (H + HEAD_ROWS - 1) / HEAD_ROWS;
+    const int64_t nunits = (int64_t)B * strips * wgroups;
+    const float b0 = bias[0], b1 = bias[1], b2 = bias[2];
+    for (int64_t unit = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; unit < nunits;
+         unit += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const int xg = (int)(unit % wgroups);
+        const int st = (int)((unit / wgroups) % strips);
+        const int b = (int)(unit / ((int64_t)wgroups * strips));
         const int x0 = xg * HEAD_PX;
-        float acc[HEAD_PX][3];
+        const int y0 = st * HEAD_ROWS;
+        const int y1 = min(y0 + HEAD_ROWS, H);
+        // acc[k]: partial output row (r - 1 + k) while input row r is being consumed
+        float acc[3][HEAD_PX][3];
 #pragma unroll
-        for (int px = 0; px < HEAD_PX; ++px) acc[px][0] = acc[px][1] = acc[px][2] = 0.f;
-        for (int cs = lane * 4; cs < C; cs += 128) {
+        for (int k = 0; k < 3; ++k)
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int y2 = yy + ky - 1;
-                if (y2 < 0 || y2 >= H) continue;
-                // columns x0-1 .. x0+HEAD_PX of the activated input, 4 channels each
-                float4 col[HEAD_PX + 2];
+            for (int px = 0; px < HEAD_PX; ++px) acc[k][px][0] = acc[k][px][1] = acc[k][px][2] = 0.f;
+        for (int r = y0 - 1; r <= y1; ++r) {
+            if (r >= 0 && r < H) {
+                const float* xrow = x + ((size_t)b * H + r) * W * C;
+                for (int cs = lane * 4; cs < C; cs += 128) {
+                    float4 col[HEAD_PX + 2];
 #pragma unroll
-                for (int j = 0; j < HEAD_PX + 2; ++j) {
-                    const int x2 = x0 + j - 1;
-                    float4 v = make_float4(0, 0, 0, 0);
-                    if (x2 >= 0 && x2 < W)
-                        v = __ldg(reinterpret_cast<const float4*>(
-                            x + (((size_t)b * H + y2) * W + x2) * C + cs));
-                    v.x = v.x > 0.f ? v.x : 0.2f * v.x;
-                    v.y = v.y > 0.f ? v.y : 0.2f * v.y;
-                    v.z = v.z > 0.f ? v.z : 0.2f * v.z;
-                    v.w = v.w > 0.f ? v.w : 0.2f * v.w;
-                    col[j] = v;
-                }
+                    for (int j = 0; j < HEAD_PX + 2; ++j) {
+                        const int x2 = x0 + j - 1;
+                        float4 v = make_float4(0, 0, 0, 0);
+                        if (x2 >= 0 && x2 < W) v = __ldg(reinterpret_cast<const float4*>(xrow + (size_t)x2 * C + cs));
+                        v.x = v.x > 0.f ? v.x : 0.2f * v.x;
+                        v.y = v.y > 0.f ? v.y : 0.2f * v.y;
+                        v.z = v.z > 0.f ? v.z : 0.2f * v.z;
+                        v.w = v.w > 0.f ? v.w : 0.2f * v.w;
+                        col[j] = v;
+                    }
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const float4* wt = wsm + (size_t)(ky * 3 + kx) * C + cs;
-                    const float4 w0 = wt[0], w1 = wt[1], w2 = wt[2], w3 = wt[3];
+                    for (int k = 0; k < 3; ++k) {
+                        // output row r - 1 + k sees input row r through filter row ky = 2 - k
+                        const int ky = 2 - k;
 #pragma unroll
-                    for (int px = 0; px < HEAD_PX; ++px) {
-                        const float4 v = col[px + kx];
-                        acc[px][0] += v.x * w0.x + v.y * w1.x + v.z * w2.x + v.w * w3.x;
-                        acc[px][1] += v.x * w0.y + v.y * w1.y + v.z * w2.y + v.w * w3.y;
-                        acc[px][2] += v.x * w0.z + v.y * w1.z + v.z * w2.z + v.w * w3.z;
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const float4* wt = wsm + (size_t)(ky * 3 + kx) * C + cs;
+                            const float4 w0 = wt[0], w1 = wt[1], w2 = wt[2], w3 = wt[3];
+#pragma unroll
+                            for (int px = 0; px < HEAD_PX; ++px) {
+                                const float4 v = col[px + kx];
+                                acc[k][px][0] += v.x * w0.x + v.y * w1.x + v.z * w2.x + v.w * w3.x;
+                                acc[k][px][1] += v.x * w0.y + v.y * w1.y + v.z * w2.y + v.w * w3.y;
+                                acc[k][px][2] += v.x * w0.z + v.y * w1.z + v.z * w2.z + v.w * w3.z;
+                            }
+                        }
                     }
                 }
             }
-        }
+            // output row r - 1 is complete
+            const int yo = r - 1;
+            if (yo >= y0 && yo < y1) {
 #pragma unroll
-        for (int px = 0; px < HEAD_PX; ++px)
+                for (int px = 0; px < HEAD_PX; ++px)
 #pragma unroll
-            for (int o = 0; o < 3; ++o)
+                    for (int o = 0; o < 3; ++o)
 #pragma unroll
-                for (int s = 16; s >= 1; s >>= 1)
-                    acc[px][o] += __shfl_xor_sync(0xffffffffu, acc[px][o], s);
-        if (lane < HEAD_PX * 3) {
-            const int px = lane / 3, o = lane % 3;
-            float v = 0.f;
+                        for (int sft = 16; sft >= 1; sft >>= 1)
+                            acc[0][px][o] += __shfl_xor_sync(0xffffffffu, acc[0][px][o], sft);
+                if (lane < HEAD_PX * 3) {
+                    const int px = lane / 3, o = lane % 3;
+                    float v = 0.f;
 #pragma unroll
-            for (int a = 0; a < HEAD_PX; ++a)
+                    for (int a = 0; a < HEAD_PX; ++a)
 #pragma unroll
-                for (int c2 = 0; c2 < 3; ++c2)
-                    if (a == px && c2 == o) v = acc[a][c2];
-            const int xo = x0 + px;
-            if (xo < W) out[(((size_t)b * 3 + o) * H + yy) * W + xo] = tanhf(v + bias[o]);
+                        for (int c2 = 0; c2 < 3; ++c2)
+                            if (a == px && c2 == o) v = acc[0][a][c2];
+                    const int xo = x0 + px;
+                    const float bo = o == 0 ? b0 : (o == 1 ? b1 : b2);
+                    if (xo < W) out[(((size_t)b * 3 + o) * H + yo) * W + xo] = tanhf(v + bo);
+                }
+            }
+#pragma unroll
+            for (int px = 0; px < HEAD_PX; ++px)
+#pragma unroll
+                for (int o = 0; o < 3; ++o) {
+                    acc[0][px][o] = acc[1][px][o];
+                    acc[1][px][o] = acc[2][px][o];
+                    acc[2][px][o] = 0.f;
+                }
         }
     }
 }
@@ -534,6 +606,27 @@ extern "C" int dsee_shared_mlp_fwd(const uint8_t* labels, const float* table, co
     int rc = require_sm100();
     if (rc) return rc;
     int64_t n = (int64_t)B * (Hl << ups) * (Wl << ups) * (nh / 4);
+    const size_t tab_bytes = (size_t)9 * L * nh * sizeof(float);
+    const int64_t npix = (int64_t)B * (Hl << ups) * (Wl << ups);
+    if (tab_bytes <= 100 * 1024 && nh <= 1024 && 256 % (nh / 4) == 0 && npix >= 4096) {
+        // table resident in shared memory, two persistent blocks per SM
+        static bool configured[64] = {false};
+        int dev = 0;
+        DSEE_CUDA(cudaGetDevice(&dev));
+        if (dev < 64 && !configured[dev]) {
+            DSEE_CUDA(cudaFuncSetAttribute(shared_mlp_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           100 * 1024));
+            configured[dev] = true;
+        }
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int lanes = 256 / (nh / 4);
+        int blocks = cdiv(npix, (int64_t)lanes * 16);  // >= 16 pixels per thread lane to amortise the table load
+        if (blocks > 2 * sms) blocks = 2 * sms;
+        shared_mlp_smem_kernel<<<blocks, 256, tab_bytes, (cudaStream_t)stream>>>(
+            labels, table, bias, (__half*)out_hi, (__half*)out_lo, B, Hl, Wl, ups, L, nh);
+        LAUNCH_END();
+    }
     shared_mlp_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
         labels, table, bias, (__half*)out_hi, (__half*)out_lo, B, Hl, Wl, ups, L, nh);
     LAUNCH_END();
@@ -694,11 +787,12 @@ extern "C" int dsee_head_fwd(const float* x, const float* w, const float* bias, 
                                        200 * 1024));
         configured[dev] = true;
     }
-    int64_t ngroups = (int64_t)B * H * ((W + HEAD_PX - 1) / HEAD_PX);
-    int blocks = cdiv(ngroups, 8);
+    int64_t nunits = (int64_t)B * ((H + HEAD_ROWS - 1) / HEAD_ROWS) * ((W + HEAD_PX - 1) / HEAD_PX);
+    int blocks = cdiv(nunits, 8);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (blocks > sms * 2) blocks = sms * 2;
+    const int per_sm = sm <= 110 * 1024 ? 2 : 1;  // __launch_bounds__(256, 2)
+    if (blocks > sms * per_sm) blocks = sms * per_sm;
     head_kernel<<<blocks, 256, sm, (cudaStream_t)stream>>>(x, w, bias, out, B, H, W, C);
     LAUNCH_END();
 }

@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 import torch.nn.utils.spectral_norm as spectral_norm
 
-from ... import ops
+from ... import ops, parallel
 from ...config import config
 from .normalization import (SPADE, SEAN_Block, PureSEAN_Block, NoiseInjection, effective_weight,
                             BN_EPS)
@@ -74,6 +74,11 @@ def _norm_forward(blk, norm, pre, Wm, gb, bb, tab, tb, gctx, style, x, x_ups, H,
     st = _NormState()
     bn = norm.param_free_norm
     if blk.training:
+        if config.sync_bn and parallel.is_dist():
+            # global-batch statistics (the reference's Sync-BN, batchnorm.py:80-93): all-reduce the
+            # per-channel (sum, sum of squares) before they become mean / variance
+            part = parallel.allreduce_sum_(ops.reduce_partials(part)).t().contiguous().unsqueeze(0)
+            count, ucount = count * parallel.world_size(), ucount * parallel.world_size()
         st.sc, st.sh, _, _ = ops.bn_finalize(part, count, BN_EPS, BN_MOMENTUM, bn.running_mean,
                                              bn.running_var, unbias_count=ucount)
         bn.num_batches_tracked.add_(1)
@@ -126,6 +131,17 @@ def _norm_backward(norm, st, dt, dt_amax, x, x_ups, noise, noise_w, L, passes, w
             dstyle = g if dstyle is None else dstyle + g
         coff += d
     return dxhat, sums, dWm, dtab, dtb, dstyle
+
+
+def _sync_bwd_sums(nsums, st):
+    """Sync-BN backward: batch-norm's two reductions (sum dxhat, sum dxhat*xhat) run over the global
+    batch.  Every rank differentiates its OWN mean loss and the gradient buckets are averaged
+    afterwards, so the unscaled local sums are the right summands.  Rows 2-3 (parameter gradients)
+    stay local."""
+    if not (config.sync_bn and parallel.is_dist()) or st.inv_count == 0.0:
+        return nsums
+    head = parallel.allreduce_sum_(nsums[:2].clone())
+    return torch.cat([head, nsums[2:]], 0)
 
 
 class _ResBlockFn(torch.autograd.Function):
@@ -207,6 +223,7 @@ class _ResBlockFn(torch.autograd.Function):
             blk.norm_1, st1, dt1, amax1, dx1, 0, None, None, L, passes, want_lo, ss)
         del dt1
         dgb1, dbb1 = nsums[2], nsums[3]
+        nsums = _sync_bwd_sums(nsums, st1)
         ddx1, _ = ops.bn_bwd(dxhat, dx1, 0, st1.sc, st1.sh, nsums, st1.inv_count)
         del dxhat
         # ---- conv_0: dx1 = conv(a0, W0) + b0 + w_mid*n_mid --------------------------------------
@@ -225,6 +242,7 @@ class _ResBlockFn(torch.autograd.Function):
             blk.norm_0, st0, dt0, amax0, x, ups, n_in, nw_in, L, passes, want_lo, ss)
         del dt0
         dgb0, dbb0 = nsums[2], nsums[3]
+        nsums = _sync_bwd_sums(nsums, st0)
         dx, dnw_in_bn = ops.bn_bwd(dxhat, x, ups, st0.sc, st0.sh, nsums, st0.inv_count, noise=n_in,
                                    noise_w=nw_in, dskip=dout)
         if noisy:

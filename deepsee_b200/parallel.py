@@ -42,6 +42,13 @@ def init_from_env(backend=None):
     dist.init_process_group(backend=backend, init_method="env://")
 
 
+def allreduce_sum_(t):
+    """In-place sum over ranks of a small statistics tensor (Sync-BN mode); identity for one rank."""
+    if is_dist():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
 def seed_python_random(seed):
     """Python's `random` drives SRModel's encoder coin flips (sr_model.py:616,643); all ranks must
     draw the same sequence or their gradient buckets would disagree on which encoder ran."""
@@ -75,18 +82,21 @@ class GradBucket:
 
     @torch.no_grad()
     def allreduce_mean(self):
-        """Gathers .grad into the bucket (zeros where absent), all-reduces, writes the mean back."""
+        """Gathers .grad into the bucket (zeros where absent), all-reduces, and leaves every
+        parameter's .grad as a view of the averaged bucket (no copy back).  The gather is one
+        multi-tensor copy, not one launch per parameter."""
         if not is_dist():
             return
+        src, dst = [], []
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 v.zero_()
-            else:
-                v.copy_(p.grad)
+            elif p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad)
+                dst.append(v)
+        if dst:
+            torch._foreach_copy_(dst, src)
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         self.flat.mul_(1.0 / dist.get_world_size())
         for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                p.grad = v.clone()
-            else:
-                p.grad.copy_(v)
+            p.grad = v

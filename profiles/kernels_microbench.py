@@ -78,6 +78,46 @@ def main():
           2 * 9 * (nh + d) * 2 * C * px)
     timed("wgrad modulation", lambda: ops.conv3x3_wgrad_multi(dgb, [actv, smap], passes=a.passes),
           2 * 9 * (nh + d) * 2 * C * px)
+
+    # ---- HBM-bound kernels of the same block (algorithmic bytes = one read of each input + one write
+    # of each output; in-kernel noise costs no bytes) -------------------------------------------
+    def hbm(name, fn, nbytes):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(a.reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.reps
+        print("%-34s %8.3f ms  %7.1f GB/s (algorithmic)" % (name, ms, nbytes / ms / 1e6))
+        return r
+
+    n = px * C
+    hb = 4 if want_lo else 2                  # bytes per element of a split-plane operand
+    nw = torch.full((C,), 0.1, device=dev)
+    seed = ops.NoiseSeed(1234567)
+    x_lo = rn(B, S // 2, S // 2, C)
+    hbm("grad_prep (no noise)", lambda: ops.grad_prep(dy, want_lo=want_lo), n * (4 + 4 + hb))
+    hbm("grad_prep (+2 noise sums)", lambda: ops.grad_prep(dy, seed, ops.NoiseSeed(77), want_lo=want_lo),
+        n * (4 + 4 + hb))
+    hbm("K1 backward (saved G)", lambda: ops.spade_modulate_bwd_saved(gsaved, x, 0, sc, sh, dt, amax,
+                                                                      want_lo=want_lo), n * (hb + 4 + 4 + 4 + 2 * hb))
+    hbm("K1 backward (saved G, ups+noise)", lambda: ops.spade_modulate_bwd_saved(
+        gsaved, x_lo, 1, sc, sh, dt, amax, noise=seed, noise_w=nw, want_lo=want_lo), n * (hb + 1 + 4 + 4 + 2 * hb))
+    hbm("bn_bwd", lambda: ops.bn_bwd(dxhat, x, 0, sc, sh, sums, 1.0 / px), n * 12)
+    hbm("bn_bwd (ups+noise+dskip)", lambda: ops.bn_bwd(dxhat, x_lo, 1, sc, sh, sums, 1.0 / px, noise=seed,
+                                                       noise_w=nw, dskip=dy), n * (4 + 4 + 1 + 1))
+    hbm("bn_stats (ups+noise)", lambda: ops.bn_stats(x_lo, 1, seed, nw), n * 1)
+    hbm("bn_stats", lambda: ops.bn_stats(x, 0), n * 4)
+    wh, bh = rn(3, C, 3, 3) / (3 * C ** 0.5), rn(3)
+    out = hbm("head fwd", lambda: ops.head(x, wh, bh), n * 4 + px * 12)
+    dout = rn(B, 3, S, S)
+    hbm("head bwd", lambda: ops.head_bwd(x, wh, out, dout), n * 8 + px * 24)
+    hbm("shared_mlp (table gather)", lambda: ops.shared_mlp(labels, table, tb, want_lo=want_lo),
+        px * (1 + nh * hb))
+    hbm("style_gather", lambda: ops.style_gather(labels, rn(B, L, d), want_lo=want_lo), px * (1 + d * hb))
     torch.cuda.profiler.stop()
 
 

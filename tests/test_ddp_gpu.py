@@ -1,0 +1,54 @@
+"""GPU, two devices: the data-parallel path on real NCCL.  A global batch of 4 is trained for one
+iteration (G step + D step) as 2 ranks x 2 samples with Sync-BN statistics (DSEE_SYNC_BN=1: the
+reference's DataParallel semantics, sync_batchnorm/batchnorm.py:63-93) and as one process x 4
+samples; averaged losses, all-reduced gradients and BN running statistics must agree.  Skipped on
+boxes with fewer than two GPUs (the world_size-2 host logic is covered on CPU by
+tests/test_parallel_cpu.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _run(tmp_path, nproc, sync_bn, tag):
+    out = str(tmp_path / ("%s.pt" % tag))
+    env = dict(os.environ, DSEE_SYNC_BN="1" if sync_bn else "0", DSEE_PASSES="3")
+    worker = os.path.join(HERE, "ddp_worker.py")
+    if nproc == 1:
+        cmd = [sys.executable, worker, "--out", out]
+        env.pop("WORLD_SIZE", None)
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+               "--master-addr", "127.0.0.1", "--master-port", "29571", worker, "--out", out]
+    subprocess.run(cmd, env=env, check=True, timeout=600)
+    return torch.load(out)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_sync_bn_matches_single_process(tmp_path):
+    one = _run(tmp_path, 1, False, "one")
+    two = _run(tmp_path, 2, True, "two")
+    assert set(one) == set(two)
+    assert any(k.startswith("grad_") for k in one)
+    for k in sorted(one):
+        a, b = one[k], two[k]
+        scale = float(a.abs().max()) + 1e-12
+        err = float((a - b).abs().max()) / scale
+        print("%-55s max|diff|/max|ref| = %.2e" % (k, err))
+        # both runs execute the same kernels; differences come from the summation order of the
+        # batch statistics / all-reduce and LeakyReLU kink flips they trigger
+        assert err < (2e-3 if k.startswith("loss") or k == "running_mean" else 3e-2), k
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_local_bn_runs(tmp_path):
+    """Default mode (per-rank BN statistics, gradient all-reduce only): runs and produces finite,
+    rank-averaged results."""
+    two = _run(tmp_path, 2, False, "two_local")
+    for k, v in two.items():
+        assert torch.isfinite(v).all(), k
