@@ -299,6 +299,8 @@ def main():
                             "launches_per_step": sum(v[0] for v in ksum.values()) / args.steps},
         "by_family": {f: {"launches_per_step": a[0] / args.steps, "ms_per_step": a[1] / args.steps,
                           "tflops": a[2] / (a[1] / 1000.0) / 1e12} for f, a in sorted(fam.items())},
+        "by_launch_group": {t: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,
+                                "tflops": v[2] / (v[1] / 1000.0) / 1e12} for t, v in sorted(ksum.items())},
         "whole_step": {"algorithmic_tflops_per_gpu": value / world * flops_per_img / 1e12,
                        "frac_of_peak": value / world * flops_per_img / 1e12 / sust},
         "traffic": None,

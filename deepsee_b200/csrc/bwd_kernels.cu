@@ -222,7 +222,8 @@ reduce_partials_kernel(const float* __restrict__ partial, int n, int C, int nq, 
 // thread = (low-res pixel, 4 channels); block writes sum(dxin * noise) partials.
 // ------------------------------------------------------------------------------------------------
 constexpr int BB_PIX = 64;  // low-res pixels per block
-__global__ void bn_bwd_kernel(const float* __restrict__ dxhat, const float* __restrict__ x, int ups,
+template <bool HAS_NOISE>
+__global__ void __launch_bounds__(256, HAS_NOISE ? 3 : 4) bn_bwd_kernel(const float* __restrict__ dxhat, const float* __restrict__ x, int ups,
                               const float* __restrict__ noise, unsigned long long noise_seed,
                               const float* __restrict__ noise_w,
                               const float* __restrict__ sc, const float* __restrict__ sh,
@@ -247,11 +248,12 @@ __global__ void bn_bwd_kernel(const float* __restrict__ dxhat, const float* __re
         m1.x *= inv_count; m1.y *= inv_count; m1.z *= inv_count; m1.w *= inv_count;
         m2.x *= inv_count; m2.y *= inv_count; m2.z *= inv_count; m2.w *= inv_count;
         float4 nw = make_float4(0, 0, 0, 0);
-        const bool has_noise = noise_w != nullptr;
+        constexpr bool has_noise = HAS_NOISE;
         if (has_noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
-        for (int i = pl; i < BB_PIX; i += lanes) {
+        const int iend = (int)(npix - p0 < BB_PIX ? npix - p0 : BB_PIX);
+#pragma unroll 2
+        for (int i = pl; i < iend; i += lanes) {
             const int64_t pix = p0 + i;
-            if (pix >= npix) break;
             const int xx = (int)(pix % Wx);
             const int yy = (int)((pix / Wx) % Hx);
             const int b = (int)(pix / ((int64_t)Wx * Hx));
@@ -626,7 +628,8 @@ extern "C" int dsee_bn_bwd(const float* dxhat, const float* x, int x_ups, const 
     if (rc) return rc;
     const int lanes = 256 / (C / 4);
     size_t sm = nw_partial ? (size_t)lanes * C * sizeof(float) : 0;
-    bn_bwd_kernel<<<dsee_bn_bwd_blocks(B, Hx, Wx), 256, sm, (cudaStream_t)stream>>>(
+    auto kern = noise_w ? bn_bwd_kernel<true> : bn_bwd_kernel<false>;
+    kern<<<dsee_bn_bwd_blocks(B, Hx, Wx), 256, sm, (cudaStream_t)stream>>>(
         dxhat, x, x_ups, noise, noise_seed, noise_w, bn_scale, bn_shift, sums, inv_count, dskip, B, Hx, Wx,
         C, dx, nw_partial);
     LAUNCH_END();

@@ -148,31 +148,35 @@ __global__ void direct_conv_small_kernel(const float* __restrict__ x, const floa
 constexpr int IN_CHUNK = 2048;  // pixels per chunk
 __global__ void instnorm_stats_kernel(const float* __restrict__ x, int HW, int C,
                                       double* __restrict__ partial) {
-    __shared__ double sh[8][32][2];
-    const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl, b = blockIdx.y;
+    // block 256 = 8 channel quads (one 32-channel slab, float4 loads) x 32 pixel lanes
+    __shared__ float sh[32][8][8];
+    const int q = threadIdx.x & 7, g = threadIdx.x >> 3;
+    const int c = blockIdx.x * 32 + q * 4, b = blockIdx.y;
     const int p0 = blockIdx.z * IN_CHUNK, p1 = min(p0 + IN_CHUNK, HW);
-    float a = 0.f, q = 0.f;
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < C) {
         const float* p = x + (size_t)b * HW * C + c;
-        for (int i = p0 + g; i < p1; i += 8) {
-            const float v = __ldg(p + (size_t)i * C);
-            a += v;
-            q += v * v;
+#pragma unroll 4
+        for (int i = p0 + g; i < p1; i += 32) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)i * C));
+            a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+            s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
         }
     }
-    sh[g][cl][0] = a;
-    sh[g][cl][1] = q;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        sh[g][q][e] = a[e];
+        sh[g][q][4 + e] = s2[e];
+    }
     __syncthreads();
-    if (g == 0 && c < C) {
-        double A = 0, Q = 0;
-        for (int k = 0; k < 8; ++k) {
-            A += sh[k][cl][0];
-            Q += sh[k][cl][1];
+    if (threadIdx.x < 64) {
+        // thread = (channel of the slab, sum | sum of squares); fixed-order double accumulation
+        const int cl = threadIdx.x & 31, k = threadIdx.x >> 5;
+        if (blockIdx.x * 32 + cl < C) {
+            double A = 0;
+            for (int l = 0; l < 32; ++l) A += (double)sh[l][cl >> 2][k * 4 + (cl & 3)];
+            partial[(((size_t)b * gridDim.z + blockIdx.z) * C + blockIdx.x * 32 + cl) * 2 + k] = A;
         }
-        double* o = partial + (((size_t)b * gridDim.z + blockIdx.z) * C + c) * 2;
-        o[0] = A;
-        o[1] = Q;
     }
 }
 __global__ void instnorm_finalize_kernel(const double* __restrict__ partial, int chunks, int HW, int C,
@@ -640,33 +644,44 @@ __global__ void instnorm_bwd_stats_kernel(const float* __restrict__ x, const flo
                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                           int HW, int C, int act, float slope,
                                           double* __restrict__ partial) {
-    __shared__ double sh[8][32][2];
-    const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl, b = blockIdx.y;
+    // same thread layout as instnorm_stats_kernel
+    __shared__ float sh[32][8][8];
+    const int q = threadIdx.x & 7, g = threadIdx.x >> 3;
+    const int c = blockIdx.x * 32 + q * 4, b = blockIdx.y;
     const int p0 = blockIdx.z * IN_CHUNK, p1 = min(p0 + IN_CHUNK, HW);
-    float s0 = 0.f, s1 = 0.f;
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < C) {
-        const float m = mean[(size_t)b * C + c], r = rstd[(size_t)b * C + c];
+        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean + (size_t)b * C + c));
+        const float4 r4 = __ldg(reinterpret_cast<const float4*>(rstd + (size_t)b * C + c));
+        const float m[4] = {m4.x, m4.y, m4.z, m4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w};
         const size_t base = (size_t)b * HW * C + c;
-        for (int i = p0 + g; i < p1; i += 8) {
-            const float y = (__ldg(x + base + (size_t)i * C) - m) * r;
-            const float gg = __ldg(dout + base + (size_t)i * C) * act_grad(y, act, slope);
-            s0 += gg;
-            s1 += gg * y;
+#pragma unroll 2
+        for (int i = p0 + g; i < p1; i += 32) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(x + base + (size_t)i * C));
+            const float4 dv = __ldg(reinterpret_cast<const float4*>(dout + base + (size_t)i * C));
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float y = (xs[e] - m[e]) * r[e];
+                const float gg = ds[e] * act_grad(y, act, slope);
+                s0[e] += gg;
+                s1[e] += gg * y;
+            }
         }
     }
-    sh[g][cl][0] = s0;
-    sh[g][cl][1] = s1;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        sh[g][q][e] = s0[e];
+        sh[g][q][4 + e] = s1[e];
+    }
     __syncthreads();
-    if (g == 0 && c < C) {
-        double a = 0, q = 0;
-        for (int k = 0; k < 8; ++k) {
-            a += sh[k][cl][0];
-            q += sh[k][cl][1];
+    if (threadIdx.x < 64) {
+        const int cl = threadIdx.x & 31, k = threadIdx.x >> 5;
+        if (blockIdx.x * 32 + cl < C) {
+            double A = 0;
+            for (int l = 0; l < 32; ++l) A += (double)sh[l][cl >> 2][k * 4 + (cl & 3)];
+            partial[(((size_t)b * gridDim.z + blockIdx.z) * C + blockIdx.x * 32 + cl) * 2 + k] = A;
         }
-        double* o = partial + (((size_t)b * gridDim.z + blockIdx.z) * C + c) * 2;
-        o[0] = a;
-        o[1] = q;
     }
 }
 __global__ void instnorm_bwd_finalize_kernel(const double* __restrict__ partial, int chunks, int HW,
@@ -837,7 +852,8 @@ extern "C" int dsee_channel_sum(const float* x, int64_t npix, int C, float* work
 extern "C" int dsee_instance_norm_bwd(const float* x, const float* dout, const float* mean,
                                       const float* rstd, float* dx, float* sums, void* workspace, int B,
                                       int HW, int C, int act, void* stream) {
-    DSEE_CHECK_ARG(x && dout && mean && rstd && dx && sums && workspace && B > 0 && HW > 0 && C > 0,
+    DSEE_CHECK_ARG(x && dout && mean && rstd && dx && sums && workspace && B > 0 && HW > 0 && C > 0 &&
+                       C % 4 == 0,
                    "bad argument");
     DSEE_CHECK_ARG(act >= 0 && act <= 2, "act must be 0, 1 or 2");
     int rc = require_sm100();

@@ -121,7 +121,7 @@ __global__ void shared_mlp_kernel(const uint8_t* __restrict__ labels, const floa
 // Same computation with the whole 9 x L x nh table staged in shared memory (87.5 KB for L = 19,
 // nh = 128): persistent blocks, thread = (pixel lane, 4 hidden channels); the 9 gathers per output
 // become LDS.128 instead of L1/L2 round trips.  Summation order identical to shared_mlp_kernel.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 shared_mlp_smem_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ table,
                        const float* __restrict__ bias, __half* __restrict__ out_hi,
                        __half* __restrict__ out_lo, int B, int Hl, int Wl, int ups, int L, int nh) {
@@ -316,6 +316,7 @@ __global__ void noise_fill_kernel(unsigned long long seed, float* __restrict__ o
     reinterpret_cast<float4*>(out)[i] = noise_normal4(seed, (unsigned long long)i);
 }
 
+template <bool HAS_NOISE>
 __global__ void bn_stats_kernel(const float* __restrict__ x, int x_ups, const float* __restrict__ noise,
                                 unsigned long long noise_seed, const float* __restrict__ noise_w, int B,
                                 int H, int W, int C, float* __restrict__ partial) {
@@ -328,12 +329,13 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int x_ups, const fl
     const int Hx = H >> x_ups, Wx = W >> x_ups;
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     float4 nw = make_float4(0, 0, 0, 0);
-    const bool has_noise = noise_w != nullptr;
+    constexpr bool has_noise = HAS_NOISE;
     if (has_noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
     if (pl < pix_lanes) {
-        for (int i = pl; i < STAT_PIX; i += pix_lanes) {
+        const int iend = (int)(npix - p0 < STAT_PIX ? npix - p0 : STAT_PIX);
+#pragma unroll 4
+        for (int i = pl; i < iend; i += pix_lanes) {
             int64_t pix = p0 + i;
-            if (pix >= npix) break;
             int xx = (int)(pix % W);
             int yy = (int)((pix / W) % H);
             int b = (int)(pix / ((int64_t)W * H));
@@ -608,7 +610,7 @@ extern "C" int dsee_shared_mlp_fwd(const uint8_t* labels, const float* table, co
     int64_t n = (int64_t)B * (Hl << ups) * (Wl << ups) * (nh / 4);
     const size_t tab_bytes = (size_t)9 * L * nh * sizeof(float);
     const int64_t npix = (int64_t)B * (Hl << ups) * (Wl << ups);
-    if (tab_bytes <= 100 * 1024 && nh <= 1024 && 256 % (nh / 4) == 0 && npix >= 4096) {
+    if (tab_bytes <= 100 * 1024 && nh <= 1024 && 512 % (nh / 4) == 0 && npix >= 4096) {
         // table resident in shared memory, two persistent blocks per SM
         static bool configured[64] = {false};
         int dev = 0;
@@ -620,10 +622,10 @@ extern "C" int dsee_shared_mlp_fwd(const uint8_t* labels, const float* table, co
         }
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int lanes = 256 / (nh / 4);
+        const int lanes = 512 / (nh / 4);
         int blocks = cdiv(npix, (int64_t)lanes * 16);  // >= 16 pixels per thread lane to amortise the table load
         if (blocks > 2 * sms) blocks = 2 * sms;
-        shared_mlp_smem_kernel<<<blocks, 256, tab_bytes, (cudaStream_t)stream>>>(
+        shared_mlp_smem_kernel<<<blocks, 512, tab_bytes, (cudaStream_t)stream>>>(
             labels, table, bias, (__half*)out_hi, (__half*)out_lo, B, Hl, Wl, ups, L, nh);
         LAUNCH_END();
     }
@@ -732,7 +734,8 @@ extern "C" int dsee_bn_stats(const float* x, int x_ups, const float* noise, unsi
     if (rc) return rc;
     int pix_lanes = 256 / (C / 4);
     size_t sm = (size_t)pix_lanes * C * 2 * sizeof(float);
-    bn_stats_kernel<<<*n_partials, 256, sm, (cudaStream_t)stream>>>(x, x_ups, noise, noise_seed, noise_w,
+    auto kern = noise_w ? bn_stats_kernel<true> : bn_stats_kernel<false>;
+    kern<<<*n_partials, 256, sm, (cudaStream_t)stream>>>(x, x_ups, noise, noise_seed, noise_w,
                                                                     B, H, W, C, stats_partial);
     LAUNCH_END();
 }

@@ -273,10 +273,23 @@ static int wgrad_plan(int B, int H, int W, int n_total, int c_total, int* splits
     const int n_tiles = (n_total + WG_M - 1) / WG_M;
     const int c_tiles = (c_total + WG_NMAX - 1) / WG_NMAX;
     const int base = n_tiles * T * c_tiles;
-    int splits = (2 * 148 + base - 1) / base;  // ~2 units per SM
-    if (splits > ptiles) splits = ptiles;
-    if (splits < 1) splits = 1;
-    if (splits > 16) splits = 16;
+    // Pixel splits: units = base * splits run as ceil(units / 148) waves of ceil(ptiles / splits)
+    // K steps each.  Pick the split count with the shortest makespan (a wave that is only partly
+    // full costs as much as a full one: base = 72 with 5 splits is 3 waves of 820 steps, with 2 or
+    // 4 splits it is 2048 steps in total); ties go to fewer splits (less partial-buffer traffic).
+    // Each unit also pays a fixed cost (accumulator drain + pipeline fill) of about 8 K steps.
+    const int sms = 148;
+    int splits = 1;
+    long best = -1;
+    for (int s = 1; s <= 16 && s <= ptiles; ++s) {
+        const long waves = ((long)base * s + sms - 1) / sms;
+        const long steps = (ptiles + s - 1) / s;
+        const long cost = waves * (steps + 8);
+        if (best < 0 || cost < best) {
+            best = cost;
+            splits = s;
+        }
+    }
     *splits_out = splits;
     return ptiles;
 }

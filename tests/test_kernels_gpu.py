@@ -121,11 +121,12 @@ def test_label_ops_bit_exact():
     assert bad3.item() == 1
 
 
+@pytest.mark.parametrize("S", [32, 72])   # 72: the shared-memory-table kernel also at ups = 0
 @pytest.mark.parametrize("ups", [0, 1])
-def test_shared_mlp_and_style_gather(ups):
+def test_shared_mlp_and_style_gather(ups, S):
     from deepsee_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(5)
-    B, L, S, nh, d = 2, 19, 32, 128, 128
+    B, L, nh, d = 2, 19, 128, 128
     lab = torch.randint(0, L, (B, 1, S, S), generator=g).cuda()
     oh = torch.zeros(B, L, S, S, device="cuda").scatter_(1, lab, 1.0)
     w = torch.randn(nh, L, 3, 3, generator=g).cuda() * 0.2
