@@ -18,7 +18,7 @@ SYMBOLS = [
     "dsee_prep_conv_weight", "dsee_split_f16", "dsee_prep_conv_weight_ex", "dsee_split_f16_ups2",
     "dsee_fold2x2", "dsee_conv2d_tc", "dsee_conv2d_tc_wgrad_workspace_floats", "dsee_conv2d_tc_wgrad",
     "dsee_conv3x3_fwd", "dsee_conv3x3_stats_tiles", "dsee_spade_modulate_fwd",
-    "dsee_spade_modulate_bwd", "dsee_spade_modulate_bwd_saved", "dsee_grad_prep_blocks", "dsee_grad_prep", "dsee_reduce_partials",
+    "dsee_spade_modulate_bwd", "dsee_spade_modulate_bwd_saved", "dsee_dgrad_modulate_bwd", "dsee_grad_prep_blocks", "dsee_grad_prep", "dsee_reduce_partials",
     "dsee_conv3x3_wgrad_workspace_floats", "dsee_conv3x3_wgrad", "dsee_conv3x3_wgrad2", "dsee_bn_bwd_blocks", "dsee_bn_bwd",
     "dsee_actv_grad_prep", "dsee_onehot_planes", "dsee_shared_mlp_bwd_blocks", "dsee_shared_mlp_bwd", "dsee_style_gather_bwd",
     "dsee_stem_bwd_blocks", "dsee_stem_bwd", "dsee_head_bwd_blocks", "dsee_head_bwd",
@@ -87,6 +87,18 @@ class ModulateBwdArgs(C.Structure):
     ]
 
 
+class DgradModBwdArgs(C.Structure):
+    _fields_ = [
+        ("act_mask", C.c_void_p), ("g_hi", C.c_void_p), ("g_lo", C.c_void_p),
+        ("x", C.c_void_p), ("x_ups", C.c_int),
+        ("noise", C.c_void_p), ("noise_seed", C.c_uint64), ("noise_w", C.c_void_p),
+        ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
+        ("dy_amax", C.c_void_p), ("w_l1", C.c_void_p),
+        ("dxhat", C.c_void_p), ("dgb_hi", C.c_void_p), ("dgb_lo", C.c_void_p),
+        ("dgb_inv_scale", C.c_void_p), ("partial", C.c_void_p), ("C", C.c_int),
+    ]
+
+
 class ModWeightArgs(C.Structure):
     _fields_ = [
         ("w_seg", C.c_void_p * 2), ("w_sty", C.c_void_p * 2), ("b_seg", C.c_void_p * 2),
@@ -137,6 +149,7 @@ def load():
         "dsee_conv3x3_stats_tiles": [i, i, i],
         "dsee_spade_modulate_fwd": [C.POINTER(ConvOperands), C.POINTER(ModulateArgs), vp],
         "dsee_spade_modulate_bwd": [C.POINTER(ConvOperands), C.POINTER(ModulateBwdArgs), vp],
+        "dsee_dgrad_modulate_bwd": [C.POINTER(ConvOperands), C.POINTER(DgradModBwdArgs), vp],
         "dsee_spade_modulate_bwd_saved": [vp, i, vp, u64, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp,
                                           vp, vp, vp, vp],
         "dsee_noise_fill": [u64, vp, i64, vp],

@@ -10,6 +10,9 @@ class _Config:
     # Training: K1 saves G = gamma + gamma_bias (fp16 planes, +1-2 B per activation element) so its
     # backward is one streaming pass instead of re-running the gamma GEMM (0 = recompute).
     save_gamma = os.environ.get("DSEE_SAVE_GAMMA", "1") != "0"
+    # Backward: run the backward-data GEMM of a main conv and K1's backward of the norm layer in front
+    # of it as one kernel (needs save_gamma); 0 = dgrad -> dt in HBM -> streaming K1 backward.
+    fuse_dgrad_modbwd = os.environ.get("DSEE_FUSE_DGRAD_MODBWD", "1") != "0"
     # Issue the weight-gradient GEMMs of the generator on a second stream (they are leaves of the
     # backward graph) so the HBM-bound kernels of the chain overlap with them.
     # (measured gain on B200: ~1 %; off by default so per-kernel CUDA-event timings stay clean)

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256, HAS_NOISE ? 3 : 4) bn_bwd_kernel(const fl
         constexpr bool has_noise = HAS_NOISE;
         if (has_noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
         const int iend = (int)(npix - p0 < BB_PIX ? npix - p0 : BB_PIX);
-#pragma unroll 2
+#pragma unroll(HAS_NOISE ? 1 : 2)
         for (int i = pl; i < iend; i += lanes) {
             const int64_t pix = p0 + i;
             const int xx = (int)(pix % Wx);

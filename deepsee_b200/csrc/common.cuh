@@ -205,16 +205,20 @@ __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
 
 // ----------------------------------------------------------------------------------------------
 // Counter-based N(0,1) noise for NoiseInjection (normalization.py:299-304).  The value of element
-// e (linear NHWC index) of a noise tensor is a pure function of (seed, e): Philox4x32-10 on the
+// e (linear NHWC index) of a noise tensor is a pure function of (seed, e): Philox4x32-7 on the
 // counter e/4 gives the 4 values of channels e..e+3 through two Box-Muller pairs.  Every kernel
 // that needs the tensor (statistics, K1, K2's epilogue, the backward passes) regenerates it, so it
 // is never written to or read from HBM.  dsee_noise_fill materialises the same stream for tests.
 // ----------------------------------------------------------------------------------------------
+// Rounds: 7 is the smallest round count of Philox4x32 that is Crush-resistant (Salmon et al.,
+// "Parallel random numbers: as easy as 1, 2, 3", SC'11, table 2); cuRAND's default of 10 adds safety
+// margin the noise injection does not need, and the generator sits in compute-bound epilogues.
+constexpr int NOISE_PHILOX_ROUNDS = 7;
 __device__ __forceinline__ float4 noise_normal4(unsigned long long seed, unsigned long long idx4) {
     uint32_t c0 = (uint32_t)idx4, c1 = (uint32_t)(idx4 >> 32), c2 = 0u, c3 = 0u;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < NOISE_PHILOX_ROUNDS; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         c0 = hi1 ^ c1 ^ k0;

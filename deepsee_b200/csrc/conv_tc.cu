@@ -14,13 +14,25 @@
 //   allocator, warps 2..9 = epilogue (two per TMEM lane quarter, alternating 32-column chunks;
 //   thread == output pixel).
 //
-// Two epilogues share the main loop:
+// Epilogue data layout: tcgen05.ld hands a thread one pixel row (32 channels) of the accumulator.
+// Global memory wants the opposite (a warp instruction covering consecutive channels of few pixels),
+// so EPI_CONV and EPI_DGRAD_MODBWD pass every 32 x 32 chunk through a per-warp padded shared-memory
+// tile and continue with lane = (pixel sub-row r = lane/8, channel quad cq = lane%8): 8 steps of
+// 4 pixels x 32 channels, every global access a float4 / 8-byte access of a fully used 128-byte
+// (64-byte for fp16 planes) segment, per-channel sums accumulated in registers (lane owns 4 channels).
+//
+// Epilogues sharing the main loop:
 //   EPI_CONV      K2: + bias (+ residual, optionally read through a folded 2x nearest upsample)
 //                 -> fp32 NHWC, optional per-channel sum / sum-of-squares tile partials.
 //   EPI_MODULATE  K1: the accumulator columns are [gamma(128) | beta(128)]; the epilogue applies
 //                 batch-norm scale/shift, x_hat*(gamma)+beta, LeakyReLU(0.2) and emits the fp16
 //                 split planes that the next conv consumes.
 //
+//   EPI_DGRAD_MODBWD  backward-data of a main conv fused with K1's backward: the accumulator is
+//                 dt (gradient wrt the conditional norm's output, LeakyReLU' applied from the saved
+//                 activation's sign); the epilogue multiplies by the saved G / x_hat and emits
+//                 dx_hat (fp32), the [dG | dB] gradient planes and the per-channel sums batch-norm's
+//                 backward needs - dt itself never reaches HBM.
 // Reference semantics: architecture.py:75-130, normalization.py:105-120,167-213,254-286.
 #include "common.cuh"
 #include "../../include/deepsee_b200.h"
@@ -39,13 +51,16 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int EPI_WARPS = 8;              // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int EPI_TILE_FLOATS = 32 * 33;  // per-warp 32 pixel x 32 channel transpose tile (padded rows)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                           EPI_WARPS * EPI_TILE_FLOATS * 4;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_TAPS = 16;
 
-enum { EPI_CONV = 0, EPI_MODULATE = 1, EPI_MODULATE_BWD = 2 };
+enum { EPI_CONV = 0, EPI_MODULATE = 1, EPI_MODULATE_BWD = 2, EPI_DGRAD_MODBWD = 3 };
 
 struct alignas(64) ConvParams {
     CUtensorMap tmA[4];  // [source*2 + plane]
@@ -99,6 +114,11 @@ struct alignas(64) ConvParams {
     const float* dt_amax;    // device scalar: max |dt| (sets the dgb plane scale)
     float* dgb_inv_scale;    // out: 2^-e of the dgb planes
     float* bwd_partial;      // [m_tiles*4][C][4] = sum dxhat, sum dxhat*xhat, sum dG, sum dB
+    // EPI_DGRAD_MODBWD (backward-data GEMM whose epilogue is K1's backward)
+    const __half* gs_hi;     // saved G = gamma + gamma_bias planes (fp16 NHWC [B,H,W,C])
+    const __half* gs_lo;
+    const float* dy_amax;    // device scalar: max |dY| of the gradient operand
+    const float* w_l1;       // device scalar: max over input channels of sum |W| (bounds |dt|)
 };
 
 __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& b, int& h0, int& w0,
@@ -270,106 +290,99 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
 
+            float* T = reinterpret_cast<float*>(bars + 32) + (warp - 2) * EPI_TILE_FLOATS;
+            const int er = lane >> 3, ecq = lane & 7;  // transposed layout: pixel sub-row, channel quad
             if (EPI == EPI_CONV) {
                 const int n0 = nt * BLOCK_N;
-                const size_t pix = ((size_t)b * p.Hm + (y * p.o_step + p.o_offy)) * p.Wm +
-                                   (x * p.o_step + p.o_offx);
-                float* orow = p.out + pix * p.n_total;
-                const float* rrow = nullptr;
-                if (p.residual) {
-                    const int Hr = p.H >> p.res_ups, Wr = p.W >> p.res_ups;
-                    const size_t rp = ((size_t)b * Hr + (y >> p.res_ups)) * Wr + (x >> p.res_ups);
-                    rrow = p.residual + rp * p.n_total;
-                }
+                const int Hr = p.H >> p.res_ups, Wr = p.W >> p.res_ups;
+                float tmax = 0.f;
 #pragma unroll 1
                 for (int ch = eh; ch < BLOCK_N / 32; ch += ESTEP) {
                     const int n = n0 + ch * 32;
                     if (n >= p.n_total) break;  // warp-uniform
-                    uint32_t v[32];
-                    tmem_ld32(taddr + ch * 32, v);
-                    tmem_ld_wait();
-                    float o[32];
+                    {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + ch * 32, v);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        o[j] = __uint_as_float(v[j]) * inv_scale + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-                    if (p.lrelu) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) o[j] = o[j] > 0.f ? o[j] : 0.2f * o[j];
+                        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
                     }
-                    if (valid && p.act_mask) {
-                        const uint4* mrow = reinterpret_cast<const uint4*>(p.act_mask + pix * p.n_total + n);
+                    __syncwarp();
+                    const int nc = n + ecq * 4;  // this lane's 4 channels
+                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc));
+                    float4 nw0 = make_float4(0.f, 0.f, 0.f, 0.f), nw1 = nw0;
+                    if (p.rnoise_w[0]) nw0 = __ldg(reinterpret_cast<const float4*>(p.rnoise_w[0] + nc));
+                    if (p.rnoise_w[1]) nw1 = __ldg(reinterpret_cast<const float4*>(p.rnoise_w[1] + nc));
+                    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+                    for (int st = 0; st < 8; ++st) {
+                        const int pi = st * 4 + er;
+                        const int mm = q * 32 + pi;
+                        const int yy = h0 + mm / TILE_W, xx = w0 + mm % TILE_W;
+                        if (yy >= p.H || xx >= p.W) continue;
+                        const float* tp = T + pi * 33 + ecq * 4;
+                        float o[4] = {tp[0] * inv_scale + bias4.x, tp[1] * inv_scale + bias4.y,
+                                      tp[2] * inv_scale + bias4.z, tp[3] * inv_scale + bias4.w};
+                        if (p.lrelu) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint4 mv = __ldg(mrow + j);
-                            const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                // fp16 > 0  <=>  sign bit clear and magnitude bits non-zero
-                                const uint32_t lo16 = mw[e] & 0xffffu, hi16 = mw[e] >> 16;
-                                if (!(lo16 != 0 && lo16 < 0x8000u)) o[j * 8 + e * 2] *= 0.2f;
-                                if (!(hi16 != 0 && hi16 < 0x8000u)) o[j * 8 + e * 2 + 1] *= 0.2f;
-                            }
+                            for (int e = 0; e < 4; ++e) o[e] = o[e] > 0.f ? o[e] : 0.2f * o[e];
                         }
-                    }
-                    if (valid) {
-                        if (rrow) {
+                        const size_t pix = ((size_t)b * p.Hm + (yy * p.o_step + p.o_offy)) * p.Wm +
+                                           (xx * p.o_step + p.o_offx);
+                        const size_t oe = pix * p.n_total + nc;
+                        if (p.act_mask) {
+                            const uint2 mv = __ldg(reinterpret_cast<const uint2*>(p.act_mask + oe));
+                            const uint32_t m16[4] = {mv.x & 0xffffu, mv.x >> 16, mv.y & 0xffffu, mv.y >> 16};
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float4 r = __ldg(reinterpret_cast<const float4*>(rrow + n) + j);
-                                o[4 * j] += r.x;
-                                o[4 * j + 1] += r.y;
-                                o[4 * j + 2] += r.z;
-                                o[4 * j + 3] += r.w;
-                            }
+                            for (int e = 0; e < 4; ++e)  // fp16 > 0 <=> sign clear and magnitude non-zero
+                                if (!(m16[e] != 0 && m16[e] < 0x8000u)) o[e] *= 0.2f;
                         }
-#pragma unroll
-                        for (int i2 = 0; i2 < 2; ++i2) {
-                            if (p.rnoise_w[i2]) {
-                                const size_t ne = pix * p.n_total + n;
-                                const float* nw = p.rnoise_w[i2] + n;
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    float4 r = load_noise4(p.rnoise[i2], p.rnoise_seed[i2], ne + 4 * j);
-                                    float4 wv = __ldg(reinterpret_cast<const float4*>(nw) + j);
-                                    o[4 * j] += wv.x * r.x;
-                                    o[4 * j + 1] += wv.y * r.y;
-                                    o[4 * j + 2] += wv.z * r.z;
-                                    o[4 * j + 3] += wv.w * r.w;
-                                }
-                            }
+                        if (p.residual) {
+                            const size_t rp = ((size_t)b * Hr + (yy >> p.res_ups)) * Wr + (xx >> p.res_ups);
+                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + rp * p.n_total + nc));
+                            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
                         }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            reinterpret_cast<float4*>(orow + n)[j] =
-                                make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                    }
-                    if (p.amax_out) {
-                        float m = 0.f;
-                        if (valid) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) m = fmaxf(m, fabsf(o[j]));
+                        if (p.rnoise_w[0]) {
+                            const float4 r4 = load_noise4(p.rnoise[0], p.rnoise_seed[0], oe);
+                            o[0] += nw0.x * r4.x; o[1] += nw0.y * r4.y; o[2] += nw0.z * r4.z; o[3] += nw0.w * r4.w;
                         }
+                        if (p.rnoise_w[1]) {
+                            const float4 r4 = load_noise4(p.rnoise[1], p.rnoise_seed[1], oe);
+                            o[0] += nw1.x * r4.x; o[1] += nw1.y * r4.y; o[2] += nw1.z * r4.z; o[3] += nw1.w * r4.w;
+                        }
+                        *reinterpret_cast<float4*>(p.out + oe) = make_float4(o[0], o[1], o[2], o[3]);
 #pragma unroll
-                        for (int sft = 16; sft >= 1; sft >>= 1)
-                            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sft));
-                        if (lane == 0 && m > 0.f && !isinf(m) && !isnan(m)) atomic_max_nonneg(p.amax_out, m);
+                        for (int e = 0; e < 4; ++e) {
+                            tmax = fmaxf(tmax, fabsf(o[e]));
+                            s1[e] += o[e];
+                            s2[e] += o[e] * o[e];
+                        }
                     }
                     if (p.stats_partial) {
-                        // tile partial of sum / sum^2 per channel, one slot per (m-tile, quarter)
-                        float s1[32], s2[32];
+                        // tile partial of sum / sum^2 per channel, one slot per (m-tile, quarter):
+                        // fold the 4 pixel sub-rows (lane bits 3, 4), lanes 0..7 write 4 channels each
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float t = valid ? o[j] : 0.f;
-                            s1[j] = t;
-                            s2[j] = t * t;
+                        for (int e = 0; e < 4; ++e) {
+                            s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8);
+                            s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 8);
+                            s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
+                            s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
                         }
-                        float r1 = warp_transpose_reduce(s1, lane);
-                        float r2 = warp_transpose_reduce(s2, lane);
-                        const size_t slot = (size_t)(tile / p.n_tiles) * 4 + q;
-                        float* sp = p.stats_partial + (slot * p.n_total + n + lane) * 2;
-                        sp[0] = r1;
-                        sp[1] = r2;
+                        if (lane < 8) {
+                            const size_t slot = (size_t)(tile / p.n_tiles) * 4 + q;
+                            float4* sp = reinterpret_cast<float4*>(p.stats_partial + (slot * p.n_total + nc) * 2);
+                            sp[0] = make_float4(s1[0], s2[0], s1[1], s2[1]);
+                            sp[1] = make_float4(s1[2], s2[2], s1[3], s2[3]);
+                        }
                     }
+                    __syncwarp();  // T is rewritten by the next chunk
+                }
+                if (p.amax_out) {
+#pragma unroll
+                    for (int sft = 16; sft >= 1; sft >>= 1)
+                        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, sft));
+                    if (lane == 0 && tmax > 0.f && !isinf(tmax) && !isnan(tmax)) atomic_max_nonneg(p.amax_out, tmax);
                 }
             } else if (EPI == EPI_MODULATE_BWD) {
                 // gamma-only GEMM (n_total == C): recompute G = gamma + gamma_bias, then
@@ -454,59 +467,198 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                     *reinterpret_cast<float4*>(p.bwd_partial + (slot * p.C + c + lane) * 4) =
                         make_float4(r0, r1, r2, r3);
                 }
-            } else {
-                // EPI_MODULATE: columns [0,128) gamma, [128,256) beta for channels nt*128 + j
-                const int c0 = nt * 128;
-                const size_t pix = ((size_t)b * p.H + y) * p.W + x;
+            } else if (EPI == EPI_DGRAD_MODBWD) {
+                // accumulator = conv_transpose(dY, W) for channels c0..c0+255 of the tile's pixels:
+                //   dt = acc * lrelu'(t)   (sign of the saved activation),
+                //   dxhat = dt * G, dG = dt * xhat, dB = dt  (+ the 4 per-channel tile sums)
+                const int c0 = nt * BLOCK_N;
                 const int Hx = p.H >> p.x_ups, Wx = p.W >> p.x_ups;
-                const size_t xp = ((size_t)b * Hx + (y >> p.x_ups)) * Wx + (x >> p.x_ups);
-                const float* xrow = p.x + xp * p.C;
                 const bool has_noise = p.noise_w != nullptr;
-                __half* hrow = p.out_hi + pix * p.C;
-                __half* lrow = p.out_lo ? p.out_lo + pix * p.C : nullptr;
-                __half* ghrow = p.g_hi ? p.g_hi + pix * p.C : nullptr;
-                __half* glrow = p.g_lo ? p.g_lo + pix * p.C : nullptr;
+                // |dt| <= max|dY| * max_c sum_{n,tap} |W[n,c,tap]|: a bound known before the GEMM runs,
+                // so the planes can be scaled here (2^6 of headroom for |xhat|, the split clamps)
+                const float gscale = pow2_scale_for(__ldg(p.dy_amax) * __ldg(p.w_l1), 10);
+                if (tile == 0 && threadIdx.x == 64) *p.dgb_inv_scale = 1.f / gscale;
+#pragma unroll 1
+                for (int ch = eh; ch < BLOCK_N / 32; ch += ESTEP) {
+                    const int c = c0 + ch * 32;
+                    if (c >= p.C) break;
+                    {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + ch * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
+                    }
+                    __syncwarp();
+                    const int cc = c + ecq * 4;  // this lane's 4 channels
+                    const float4 sc4 = __ldg(reinterpret_cast<const float4*>(p.bn_scale + cc));
+                    const float4 sh4 = __ldg(reinterpret_cast<const float4*>(p.bn_shift + cc));
+                    float4 nw4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_noise) nw4 = __ldg(reinterpret_cast<const float4*>(p.noise_w + cc));
+                    const int ng = (cc >> 7) * 256 + (cc & 127);  // interleaved [dG(128) | dB(128)] position
+                    float sm[4][4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) sm[k][e] = 0.f;
+#pragma unroll 2
+                    for (int st = 0; st < 8; ++st) {
+                        const int pi = st * 4 + er;
+                        const int mm = q * 32 + pi;
+                        const int yy = h0 + mm / TILE_W, xx = w0 + mm % TILE_W;
+                        if (yy >= p.H || xx >= p.W) continue;
+                        const size_t pix = ((size_t)b * p.H + yy) * p.W + xx;
+                        const size_t pe = pix * p.C + cc;
+                        const size_t xp = ((size_t)b * Hx + (yy >> p.x_ups)) * Wx + (xx >> p.x_ups);
+                        float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + xp * p.C + cc));
+                        const uint2 mv = __ldg(reinterpret_cast<const uint2*>(p.act_mask + pe));
+                        const uint2 gv = __ldg(reinterpret_cast<const uint2*>(p.gs_hi + pe));
+                        uint2 lv = make_uint2(0u, 0u);
+                        if (p.gs_lo) lv = __ldg(reinterpret_cast<const uint2*>(p.gs_lo + pe));
+                        if (has_noise) {
+                            const float4 nv = load_noise4(p.noise, p.noise_seed, pe);
+                            xv.x += nw4.x * nv.x; xv.y += nw4.y * nv.y; xv.z += nw4.z * nv.z; xv.w += nw4.w * nv.w;
+                        }
+                        const float xh[4] = {xv.x * sc4.x + sh4.x, xv.y * sc4.y + sh4.y, xv.z * sc4.z + sh4.z,
+                                             xv.w * sc4.w + sh4.w};
+                        const uint32_t m16[4] = {mv.x & 0xffffu, mv.x >> 16, mv.y & 0xffffu, mv.y >> 16};
+                        const uint32_t g16[4] = {gv.x & 0xffffu, gv.x >> 16, gv.y & 0xffffu, gv.y >> 16};
+                        const uint32_t l16[4] = {lv.x & 0xffffu, lv.x >> 16, lv.y & 0xffffu, lv.y >> 16};
+                        const float* tp = T + pi * 33 + ecq * 4;
+                        float d[4], dxh[4], dG[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float mk = (m16[e] != 0 && m16[e] < 0x8000u) ? 1.f : 0.2f;  // fp16 > 0
+                            const float G = __half2float(__ushort_as_half((unsigned short)g16[e])) +
+                                            __half2float(__ushort_as_half((unsigned short)l16[e]));
+                            d[e] = tp[e] * inv_scale * mk;
+                            dxh[e] = d[e] * G;
+                            dG[e] = d[e] * xh[e];
+                            sm[0][e] += dxh[e];
+                            sm[1][e] += dxh[e] * xh[e];
+                            sm[2][e] += dG[e];
+                            sm[3][e] += d[e];
+                        }
+                        *reinterpret_cast<float4*>(p.dxhat + pe) = make_float4(dxh[0], dxh[1], dxh[2], dxh[3]);
+                        __half* rowh = p.dgb_hi + pix * (size_t)(2 * p.C) + ng;
+                        __half* rowl = p.dgb_lo ? p.dgb_lo + pix * (size_t)(2 * p.C) + ng : nullptr;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const float* src = half ? d : dG;
+                            uint32_t ph[2], plw[2];
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const float v0 = fminf(fmaxf(src[2 * e] * gscale, -65504.f), 65504.f);
+                                const float v1 = fminf(fmaxf(src[2 * e + 1] * gscale, -65504.f), 65504.f);
+                                const __half hh0 = __float2half_rn(v0), hh1 = __float2half_rn(v1);
+                                const __half ll0 = __float2half_rn(v0 - __half2float(hh0));
+                                const __half ll1 = __float2half_rn(v1 - __half2float(hh1));
+                                ph[e] = (uint32_t)__half_as_ushort(hh0) | ((uint32_t)__half_as_ushort(hh1) << 16);
+                                plw[e] = (uint32_t)__half_as_ushort(ll0) | ((uint32_t)__half_as_ushort(ll1) << 16);
+                            }
+                            *reinterpret_cast<uint2*>(rowh + half * 128) = make_uint2(ph[0], ph[1]);
+                            if (rowl) *reinterpret_cast<uint2*>(rowl + half * 128) = make_uint2(plw[0], plw[1]);
+                        }
+                    }
+                    // fold the 4 pixel sub-rows; lanes 0..7 write their 4 channels x 4 sums
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            sm[k][e] += __shfl_xor_sync(0xffffffffu, sm[k][e], 8);
+                            sm[k][e] += __shfl_xor_sync(0xffffffffu, sm[k][e], 16);
+                        }
+                    if (lane < 8) {
+                        const size_t slot = (size_t)(tile / p.n_tiles) * 4 + q;
+                        float4* bp = reinterpret_cast<float4*>(p.bwd_partial + (slot * p.C + cc) * 4);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) bp[e] = make_float4(sm[0][e], sm[1][e], sm[2][e], sm[3][e]);
+                    }
+                    __syncwarp();  // T is rewritten by the next chunk
+                }
+            } else {
+                // EPI_MODULATE: columns [0,128) gamma, [128,256) beta for channels nt*128 + j.
+                // Both 32 x 32 chunks go through the transpose tile (gamma first, kept in registers).
+                const int c0 = nt * 128;
+                const int Hx = p.H >> p.x_ups, Wx = p.W >> p.x_ups;
+                const bool has_noise = p.noise_w != nullptr;
 #pragma unroll 1
                 for (int ch = eh; ch < 4; ch += ESTEP) {
                     const int c = c0 + ch * 32;
-                    uint32_t g[32], bt[32];
-                    tmem_ld32(taddr + ch * 32, g);
-                    tmem_ld32(taddr + 128 + ch * 32, bt);
-                    tmem_ld_wait();
-                    if (valid) {
+                    float gt[8][4];
+                    {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + ch * 32, v);
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8) {
-                            float a[8], gsave[8];
+                        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
+                        __syncwarp();
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const int j = j8 * 8 + h * 4;
-                                float4 xv = __ldg(reinterpret_cast<const float4*>(xrow + c + j));
-                                float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-                                if (has_noise) {
-                                    float4 nv = load_noise4(p.noise, p.noise_seed, pix * p.C + c + j);
-                                    float ns[4] = {nv.x, nv.y, nv.z, nv.w};
+                        for (int st = 0; st < 8; ++st)
 #pragma unroll
-                                    for (int e = 0; e < 4; ++e)
-                                        xs[e] += __ldg(p.noise_w + c + j + e) * ns[e];
-                                }
+                            for (int e = 0; e < 4; ++e) gt[st][e] = T[(st * 4 + er) * 33 + ecq * 4 + e];
+                        __syncwarp();
+                        tmem_ld32(taddr + 128 + ch * 32, v);
+                        tmem_ld_wait();
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int cc = c + j + e;
-                                    float xh = xs[e] * __ldg(p.bn_scale + cc) + __ldg(p.bn_shift + cc);
-                                    float G = __uint_as_float(g[j + e]) * inv_scale +
-                                              __ldg(p.gamma_bias + cc);
-                                    float Bv = __uint_as_float(bt[j + e]) * inv_scale +
-                                               __ldg(p.beta_bias + cc);
-                                    float t = xh * G + Bv;
-                                    a[h * 4 + e] = t > 0.f ? t : 0.2f * t;
-                                    gsave[h * 4 + e] = G;
-                                }
-                            }
-                            store_split8(hrow + c + j8 * 8, lrow ? lrow + c + j8 * 8 : nullptr, a);
-                            if (ghrow)
-                                store_split8(ghrow + c + j8 * 8, glrow ? glrow + c + j8 * 8 : nullptr, gsave);
-                        }
+                        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
+                        __syncwarp();
                     }
+                    const int cc = c + ecq * 4;  // this lane's 4 channels
+                    const float4 sc4 = __ldg(reinterpret_cast<const float4*>(p.bn_scale + cc));
+                    const float4 sh4 = __ldg(reinterpret_cast<const float4*>(p.bn_shift + cc));
+                    const float4 gb4 = __ldg(reinterpret_cast<const float4*>(p.gamma_bias + cc));
+                    const float4 bb4 = __ldg(reinterpret_cast<const float4*>(p.beta_bias + cc));
+                    float4 nw4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_noise) nw4 = __ldg(reinterpret_cast<const float4*>(p.noise_w + cc));
+                    const float scv[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, shv[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+                    const float gbv[4] = {gb4.x, gb4.y, gb4.z, gb4.w}, bbv[4] = {bb4.x, bb4.y, bb4.z, bb4.w};
+#pragma unroll
+                    for (int st = 0; st < 8; ++st) {
+                        const int pi = st * 4 + er;
+                        const int mm = q * 32 + pi;
+                        const int yy = h0 + mm / TILE_W, xx = w0 + mm % TILE_W;
+                        if (yy >= p.H || xx >= p.W) continue;
+                        const size_t pix = ((size_t)b * p.H + yy) * p.W + xx;
+                        const size_t pe = pix * p.C + cc;
+                        const size_t xp = ((size_t)b * Hx + (yy >> p.x_ups)) * Wx + (xx >> p.x_ups);
+                        float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + xp * p.C + cc));
+                        if (has_noise) {
+                            const float4 nv = load_noise4(p.noise, p.noise_seed, pe);
+                            xv.x += nw4.x * nv.x; xv.y += nw4.y * nv.y; xv.z += nw4.z * nv.z; xv.w += nw4.w * nv.w;
+                        }
+                        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                        const float* tp = T + pi * 33 + ecq * 4;
+                        uint32_t ah[2], al[2], gh[2], gl[2];
+#pragma unroll
+                        for (int e2 = 0; e2 < 2; ++e2) {
+                            __half hh[2], ll[2], ghh[2], gll[2];
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const int e = e2 * 2 + k;
+                                const float xh = xs[e] * scv[e] + shv[e];
+                                const float G = gt[st][e] * inv_scale + gbv[e];
+                                const float Bv = tp[e] * inv_scale + bbv[e];
+                                float t = xh * G + Bv;
+                                t = t > 0.f ? t : 0.2f * t;
+                                t = fminf(fmaxf(t, -65504.f), 65504.f);
+                                const float Gc = fminf(fmaxf(G, -65504.f), 65504.f);
+                                hh[k] = __float2half_rn(t);
+                                ll[k] = __float2half_rn(t - __half2float(hh[k]));
+                                ghh[k] = __float2half_rn(Gc);
+                                gll[k] = __float2half_rn(Gc - __half2float(ghh[k]));
+                            }
+                            ah[e2] = (uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16);
+                            al[e2] = (uint32_t)__half_as_ushort(ll[0]) | ((uint32_t)__half_as_ushort(ll[1]) << 16);
+                            gh[e2] = (uint32_t)__half_as_ushort(ghh[0]) | ((uint32_t)__half_as_ushort(ghh[1]) << 16);
+                            gl[e2] = (uint32_t)__half_as_ushort(gll[0]) | ((uint32_t)__half_as_ushort(gll[1]) << 16);
+                        }
+                        *reinterpret_cast<uint2*>(p.out_hi + pe) = make_uint2(ah[0], ah[1]);
+                        if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + pe) = make_uint2(al[0], al[1]);
+                        if (p.g_hi) *reinterpret_cast<uint2*>(p.g_hi + pe) = make_uint2(gh[0], gh[1]);
+                        if (p.g_lo) *reinterpret_cast<uint2*>(p.g_lo + pe) = make_uint2(gl[0], gl[1]);
+                    }
+                    __syncwarp();  // T is rewritten by the next chunk
                 }
             }
             // all TMEM reads of this accumulator stage are complete (wait::ld above)
@@ -845,4 +997,41 @@ extern "C" int dsee_spade_modulate_bwd(const dsee_conv_operands* ops, const dsee
     p.dgb_inv_scale = a->dgb_inv_scale;
     p.bwd_partial = a->partial;
     return launch<EPI_MODULATE_BWD>(p, (cudaStream_t)stream);
+}
+
+extern "C" int dsee_dgrad_modulate_bwd(const dsee_conv_operands* ops, const dsee_dgrad_modbwd_args* a,
+                                       void* stream) {
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = fill_common(p, ops);
+    if (rc) return rc;
+    DSEE_CHECK_ARG(a != nullptr, "dgrad+modulate bwd args are NULL");
+    DSEE_CHECK_ARG(a->C > 0 && a->C % 128 == 0 && ops->n_total == a->C,
+                   "transposed weights expected: n_total (%d) must equal C (%d)", ops->n_total, a->C);
+    DSEE_CHECK_ARG(a->act_mask && a->g_hi && a->x && a->bn_scale && a->bn_shift && a->dy_amax && a->w_l1 &&
+                       a->dxhat && a->dgb_hi && a->dgb_inv_scale && a->partial,
+                   "NULL dgrad+modulate bwd pointer");
+    DSEE_CHECK_ARG(a->x_ups == 0 || a->x_ups == 1, "x_ups must be 0 or 1");
+    DSEE_CHECK_ARG(a->x_ups == 0 || (ops->H % 2 == 0 && ops->W % 2 == 0), "folded upsample needs even H, W");
+    DSEE_CHECK_ARG((a->noise != nullptr || a->noise_seed != 0) == (a->noise_w != nullptr),
+                   "noise (tensor or seed) and noise_w must be given together");
+    p.act_mask = (const __half*)a->act_mask;
+    p.gs_hi = (const __half*)a->g_hi;
+    p.gs_lo = (const __half*)a->g_lo;
+    p.x = a->x;
+    p.x_ups = a->x_ups;
+    p.noise = a->noise;
+    p.noise_seed = a->noise_seed;
+    p.noise_w = a->noise_w;
+    p.bn_scale = a->bn_scale;
+    p.bn_shift = a->bn_shift;
+    p.dy_amax = a->dy_amax;
+    p.w_l1 = a->w_l1;
+    p.C = a->C;
+    p.dxhat = a->dxhat;
+    p.dgb_hi = (__half*)a->dgb_hi;
+    p.dgb_lo = (__half*)a->dgb_lo;
+    p.dgb_inv_scale = a->dgb_inv_scale;
+    p.bwd_partial = a->partial;
+    return launch<EPI_DGRAD_MODBWD>(p, (cudaStream_t)stream);
 }

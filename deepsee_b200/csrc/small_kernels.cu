@@ -118,51 +118,6 @@ __global__ void shared_mlp_kernel(const uint8_t* __restrict__ labels, const floa
         *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack2(l4[0], l4[1]), pack2(l4[2], l4[3]));
 }
 
-// Same computation with the whole 9 x L x nh table staged in shared memory (87.5 KB for L = 19,
-// nh = 128): persistent blocks, thread = (pixel lane, 4 hidden channels); the 9 gathers per output
-// become LDS.128 instead of L1/L2 round trips.  Summation order identical to shared_mlp_kernel.
-__global__ void __launch_bounds__(512)
-shared_mlp_smem_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ table,
-                       const float* __restrict__ bias, __half* __restrict__ out_hi,
-                       __half* __restrict__ out_lo, int B, int Hl, int Wl, int ups, int L, int nh) {
-    extern __shared__ float4 tab_sm[];  // [9][L][nh/4]
-    const int groups = nh >> 2;
-    const int n4 = 9 * L * groups;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) tab_sm[i] = __ldg(reinterpret_cast<const float4*>(table) + i);
-    __syncthreads();
-    const int g = threadIdx.x % groups, pl = threadIdx.x / groups, lanes = blockDim.x / groups;
-    const int H = Hl << ups, W = Wl << ups;
-    const int64_t npix = (int64_t)B * H * W;
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + g);
-    for (int64_t pix = (int64_t)blockIdx.x * lanes + pl; pix < npix; pix += (int64_t)gridDim.x * lanes) {
-        const int x = (int)(pix % W);
-        const int y = (int)((pix / W) % H);
-        const int b = (int)(pix / ((int64_t)W * H));
-        const int yl = y >> ups, xl = x >> ups;
-        const uint8_t* lb = labels + (size_t)b * Hl * Wl;
-        float4 acc = bv;
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int yy = yl + tap / 3 - 1, xx = xl + tap % 3 - 1;
-            if (yy < 0 || yy >= Hl || xx < 0 || xx >= Wl) continue;  // zero padding
-            const int l = lb[yy * Wl + xx];
-            const float4 t = tab_sm[((size_t)tap * L + l) * groups + g];
-            acc.x += t.x;
-            acc.y += t.y;
-            acc.z += t.z;
-            acc.w += t.w;
-        }
-        const float a[4] = {fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f)};
-        __half h[4], l4[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) split_f16(a[e], h[e], l4[e]);
-        const size_t o = (size_t)pix * nh + (size_t)g * 4;
-        *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
-        if (out_lo)
-            *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack2(l4[0], l4[1]), pack2(l4[2], l4[3]));
-    }
-}
-
 __global__ void style_gather_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ style,
                                     __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B,
                                     int HW, int L, int d) {
@@ -215,6 +170,25 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, __half* __restri
     const size_t o = transpose ? ((size_t)c * 9 + (8 - tap)) * N + n : (size_t)i;
     out_hi[o] = h;
     if (out_lo) out_lo[o] = l;
+}
+
+// max over rows of sum_k |hi[row][k]| * inv_scale: one block per row of the prepared (scaled fp16)
+// planes; bounds |sum_k a[k] * w[row][k]| <= max|a| * result.
+__global__ void row_l1max_kernel(const __half* __restrict__ hi, int rowlen, float* inv_scale) {
+    __shared__ float red[8];
+    const __half* r = hi + (size_t)blockIdx.x * rowlen;
+    float a = 0.f;
+    for (int i = threadIdx.x; i < rowlen; i += blockDim.x) a += fabsf(__half2float(r[i]));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+        // 1 + 2^-9: the hi plane is w * scale rounded to 11 bits
+        atomic_max_nonneg(inv_scale + 2, t * inv_scale[0] * 1.002f);
+    }
 }
 
 __global__ void prep_weight_ex_kernel(const float* __restrict__ w, __half* __restrict__ out_hi,
@@ -333,7 +307,7 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int x_ups, const fl
     if (has_noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
     if (pl < pix_lanes) {
         const int iend = (int)(npix - p0 < STAT_PIX ? npix - p0 : STAT_PIX);
-#pragma unroll 4
+#pragma unroll(HAS_NOISE ? 1 : 4)
         for (int i = pl; i < iend; i += pix_lanes) {
             int64_t pix = p0 + i;
             int xx = (int)(pix % W);
@@ -449,109 +423,132 @@ __global__ void stem_kernel(const float* __restrict__ x, const float* __restrict
     }
 }
 
-// Image head.  A warp owns a strip of HEAD_PX horizontally adjacent pixels x HEAD_ROWS output rows
-// and slides down it: every input row is loaded ONCE (6 columns x 16 channels per lane and 128-channel
-// slab, LeakyReLU applied on load) and feeds the three output rows it touches (ky = 2, 1, 0), so HBM/L2
-// read amplification is (HEAD_ROWS + 2) / HEAD_ROWS instead of 3.  Lanes split the channels; weights
-// are staged in smem as [tap][c][4] (3 outputs + pad).  Adjacent warps of a block take adjacent
-// column groups of the same strip, so the column halo is an L1 hit.
-constexpr int HEAD_PX = 4;
-constexpr int HEAD_ROWS = 16;
+// Image head: tanh(conv3x3(leaky_relu(x), 512 -> 3) + bias), NHWC fp32 in, NCHW fp32 out.
+// HBM-bound by design (x is read once, 4 B per element): a block owns a 16 x 64 pixel tile and walks
+// the channels in slabs of 8.  Each slab's halo tile (18 x 66 pixels, LeakyReLU applied) is staged in
+// shared memory channel-major ([c][row][col]) through registers, double-buffered so the next slab's
+// global loads are in flight while the current one is consumed.  A thread owns 4 horizontally
+// adjacent pixels x 3 outputs; per channel and filter row it reads 6 consecutive inputs
+// (LDS.128 + LDS.64, conflict-free) and the 27 weights of that channel as broadcast LDS.128.
+constexpr int HT_H = 16, HT_W = 64, HT_CS = 8, HT_WP = 68;
+constexpr int HT_NPIX = (HT_H + 2) * (HT_W + 2);
+constexpr int HT_NLD = (2 * HT_NPIX + 255) / 256;
+constexpr int HT_XS = HT_CS * (HT_H + 2) * HT_WP;  // floats per x buffer
+constexpr int HT_SMEM = (2 * HT_XS + 2 * HT_CS * 28) * (int)sizeof(float);
 __global__ void __launch_bounds__(256, 2)
 head_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
             float* __restrict__ out, int B, int H, int W, int C) {
-    extern __shared__ float4 wsm[];  // [9][C]
-    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
-        int tap = i / C, c = i % C;
-        wsm[i] = make_float4(w[((size_t)0 * C + c) * 9 + tap], w[((size_t)1 * C + c) * 9 + tap],
-                             w[((size_t)2 * C + c) * 9 + tap], 0.f);
+    extern __shared__ __align__(16) float hsm[];
+    float* xs = hsm;                 // [2][HT_CS][HT_H + 2][HT_WP]
+    float* ws = hsm + 2 * HT_XS;     // [2][HT_CS][28]: index (ky*3 + kx)*3 + o
+    const int tiles_w = (W + HT_W - 1) / HT_W, tiles_h = (H + HT_H - 1) / HT_H;
+    const int tile = blockIdx.x;
+    const int w0 = (tile % tiles_w) * HT_W;
+    const int h0 = ((tile / tiles_w) % tiles_h) * HT_H;
+    const int b = tile / (tiles_w * tiles_h);
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int nslab = C / HT_CS;
+    float4 stage[HT_NLD];
+
+    // staging slots of this thread, decoded once: (row, col, channel half) of the halo tile packed in
+    // one register each (the slab index is the only thing that changes between iterations)
+    uint32_t slot[HT_NLD];
+#pragma unroll
+    for (int k = 0; k < HT_NLD; ++k) {
+        const int e = t + k * 256;
+        slot[k] = 0xffffffffu;
+        if (e < 2 * HT_NPIX) {
+            const int half = e / HT_NPIX, pix = e % HT_NPIX;
+            const int r = pix / (HT_W + 2), cidx = pix % (HT_W + 2);
+            const int y = h0 - 1 + r, xg = w0 - 1 + cidx;
+            const uint32_t inside = (y >= 0 && y < H && xg >= 0 && xg < W) ? 1u : 0u;
+            slot[k] = (uint32_t)r | ((uint32_t)cidx << 5) | ((uint32_t)half << 12) | (inside << 13);
+        }
     }
+    const float* xbase = x + (((size_t)b * H + (h0 - 1)) * W + (w0 - 1)) * C;  // halo origin (may be out of range)
+    auto gload = [&](int slab) {
+#pragma unroll
+        for (int k = 0; k < HT_NLD; ++k) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t sl = slot[k];
+            if (sl != 0xffffffffu && (sl >> 13)) {
+                const int r = sl & 31, cidx = (sl >> 5) & 127, half = (sl >> 12) & 1;
+                v = __ldg(reinterpret_cast<const float4*>(xbase + ((ptrdiff_t)r * W + cidx) * C + slab * HT_CS +
+                                                          half * 4));
+                v.x = v.x > 0.f ? v.x : 0.2f * v.x;
+                v.y = v.y > 0.f ? v.y : 0.2f * v.y;
+                v.z = v.z > 0.f ? v.z : 0.2f * v.z;
+                v.w = v.w > 0.f ? v.w : 0.2f * v.w;
+            }
+            stage[k] = v;
+        }
+    };
+    auto sstore = [&](int buf, int slab) {
+#pragma unroll
+        for (int k = 0; k < HT_NLD; ++k) {
+            const uint32_t sl = slot[k];
+            if (sl != 0xffffffffu) {
+                const int r = sl & 31, cidx = (sl >> 5) & 127, half = (sl >> 12) & 1;
+                float* d = xs + buf * HT_XS + (half * 4) * (HT_H + 2) * HT_WP + r * HT_WP + cidx;
+                d[0] = stage[k].x;
+                d[(HT_H + 2) * HT_WP] = stage[k].y;
+                d[2 * (HT_H + 2) * HT_WP] = stage[k].z;
+                d[3 * (HT_H + 2) * HT_WP] = stage[k].w;
+            }
+        }
+        if (t < HT_CS * 27) {
+            const int c = t / 27, k = t % 27, tap = k / 3, o = k % 3;
+            ws[(buf * HT_CS + c) * 28 + k] = __ldg(w + ((size_t)o * C + slab * HT_CS + c) * 9 + tap);
+        }
+    };
+
+    float acc[4][3];
+#pragma unroll
+    for (int px = 0; px < 4; ++px) acc[px][0] = acc[px][1] = acc[px][2] = 0.f;
+
+    gload(0);
+    sstore(0, 0);
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wgroups = (W + HEAD_PX - 1) / HEAD_PX;
-    const int strips = (H + HEAD_ROWS - 1) / HEAD_ROWS;
-    const int64_t nunits = (int64_t)B * strips * wgroups;
-    const float b0 = bias[0], b1 = bias[1], b2 = bias[2];
-    for (int64_t unit = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; unit < nunits;
-         unit += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-        const int xg = (int)(unit % wgroups);
-        const int st = (int)((unit / wgroups) % strips);
-        const int b = (int)(unit / ((int64_t)wgroups * strips));
-        const int x0 = xg * HEAD_PX;
-        const int y0 = st * HEAD_ROWS;
-        const int y1 = min(y0 + HEAD_ROWS, H);
-        // acc[k]: partial output row (r - 1 + k) while input row r is being consumed
-        float acc[3][HEAD_PX][3];
+    for (int slab = 0; slab < nslab; ++slab) {
+        const int cur = slab & 1;
+        if (slab + 1 < nslab) gload(slab + 1);
+#pragma unroll 2
+        for (int c = 0; c < HT_CS; ++c) {
+            float wv[28];
+            const float4* wp = reinterpret_cast<const float4*>(ws + (cur * HT_CS + c) * 28);
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int px = 0; px < HEAD_PX; ++px) acc[k][px][0] = acc[k][px][1] = acc[k][px][2] = 0.f;
-        for (int r = y0 - 1; r <= y1; ++r) {
-            if (r >= 0 && r < H) {
-                const float* xrow = x + ((size_t)b * H + r) * W * C;
-                for (int cs = lane * 4; cs < C; cs += 128) {
-                    float4 col[HEAD_PX + 2];
-#pragma unroll
-                    for (int j = 0; j < HEAD_PX + 2; ++j) {
-                        const int x2 = x0 + j - 1;
-                        float4 v = make_float4(0, 0, 0, 0);
-                        if (x2 >= 0 && x2 < W) v = __ldg(reinterpret_cast<const float4*>(xrow + (size_t)x2 * C + cs));
-                        v.x = v.x > 0.f ? v.x : 0.2f * v.x;
-                        v.y = v.y > 0.f ? v.y : 0.2f * v.y;
-                        v.z = v.z > 0.f ? v.z : 0.2f * v.z;
-                        v.w = v.w > 0.f ? v.w : 0.2f * v.w;
-                        col[j] = v;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        // output row r - 1 + k sees input row r through filter row ky = 2 - k
-                        const int ky = 2 - k;
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const float4* wt = wsm + (size_t)(ky * 3 + kx) * C + cs;
-                            const float4 w0 = wt[0], w1 = wt[1], w2 = wt[2], w3 = wt[3];
-#pragma unroll
-                            for (int px = 0; px < HEAD_PX; ++px) {
-                                const float4 v = col[px + kx];
-                                acc[k][px][0] += v.x * w0.x + v.y * w1.x + v.z * w2.x + v.w * w3.x;
-                                acc[k][px][1] += v.x * w0.y + v.y * w1.y + v.z * w2.y + v.w * w3.y;
-                                acc[k][px][2] += v.x * w0.z + v.y * w1.z + v.z * w2.z + v.w * w3.z;
-                            }
-                        }
-                    }
-                }
-            }
-            // output row r - 1 is complete
-            const int yo = r - 1;
-            if (yo >= y0 && yo < y1) {
-#pragma unroll
-                for (int px = 0; px < HEAD_PX; ++px)
-#pragma unroll
-                    for (int o = 0; o < 3; ++o)
-#pragma unroll
-                        for (int sft = 16; sft >= 1; sft >>= 1)
-                            acc[0][px][o] += __shfl_xor_sync(0xffffffffu, acc[0][px][o], sft);
-                if (lane < HEAD_PX * 3) {
-                    const int px = lane / 3, o = lane % 3;
-                    float v = 0.f;
-#pragma unroll
-                    for (int a = 0; a < HEAD_PX; ++a)
-#pragma unroll
-                        for (int c2 = 0; c2 < 3; ++c2)
-                            if (a == px && c2 == o) v = acc[0][a][c2];
-                    const int xo = x0 + px;
-                    const float bo = o == 0 ? b0 : (o == 1 ? b1 : b2);
-                    if (xo < W) out[(((size_t)b * 3 + o) * H + yo) * W + xo] = tanhf(v + bo);
-                }
+            for (int j = 0; j < 7; ++j) {
+                const float4 q = wp[j];
+                wv[4 * j] = q.x; wv[4 * j + 1] = q.y; wv[4 * j + 2] = q.z; wv[4 * j + 3] = q.w;
             }
 #pragma unroll
-            for (int px = 0; px < HEAD_PX; ++px)
+            for (int ky = 0; ky < 3; ++ky) {
+                const float* row = xs + cur * HT_XS + (c * (HT_H + 2) + ty + ky) * HT_WP + 4 * tx;
+                const float4 a4 = *reinterpret_cast<const float4*>(row);
+                const float2 b2 = *reinterpret_cast<const float2*>(row + 4);
+                const float v[6] = {a4.x, a4.y, a4.z, a4.w, b2.x, b2.y};
 #pragma unroll
-                for (int o = 0; o < 3; ++o) {
-                    acc[0][px][o] = acc[1][px][o];
-                    acc[1][px][o] = acc[2][px][o];
-                    acc[2][px][o] = 0.f;
-                }
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int px = 0; px < 4; ++px)
+#pragma unroll
+                        for (int o = 0; o < 3; ++o) acc[px][o] += v[px + kx] * wv[(ky * 3 + kx) * 3 + o];
+            }
+        }
+        if (slab + 1 < nslab) sstore(cur ^ 1, slab + 1);
+        __syncthreads();
+    }
+    const int y = h0 + ty;
+    if (y < H) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            const float bo = __ldg(bias + o);
+            float* orow = out + (((size_t)b * 3 + o) * H + y) * W;
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+                const int xg = w0 + 4 * tx + px;
+                if (xg < W) orow[xg] = tanhf(acc[px][o] + bo);
+            }
         }
     }
 }
@@ -608,27 +605,6 @@ extern "C" int dsee_shared_mlp_fwd(const uint8_t* labels, const float* table, co
     int rc = require_sm100();
     if (rc) return rc;
     int64_t n = (int64_t)B * (Hl << ups) * (Wl << ups) * (nh / 4);
-    const size_t tab_bytes = (size_t)9 * L * nh * sizeof(float);
-    const int64_t npix = (int64_t)B * (Hl << ups) * (Wl << ups);
-    if (tab_bytes <= 100 * 1024 && nh <= 1024 && 512 % (nh / 4) == 0 && npix >= 4096) {
-        // table resident in shared memory, two persistent blocks per SM
-        static bool configured[64] = {false};
-        int dev = 0;
-        DSEE_CUDA(cudaGetDevice(&dev));
-        if (dev < 64 && !configured[dev]) {
-            DSEE_CUDA(cudaFuncSetAttribute(shared_mlp_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           100 * 1024));
-            configured[dev] = true;
-        }
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int lanes = 512 / (nh / 4);
-        int blocks = cdiv(npix, (int64_t)lanes * 16);  // >= 16 pixels per thread lane to amortise the table load
-        if (blocks > 2 * sms) blocks = 2 * sms;
-        shared_mlp_smem_kernel<<<blocks, 512, tab_bytes, (cudaStream_t)stream>>>(
-            labels, table, bias, (__half*)out_hi, (__half*)out_lo, B, Hl, Wl, ups, L, nh);
-        LAUNCH_END();
-    }
     shared_mlp_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
         labels, table, bias, (__half*)out_hi, (__half*)out_lo, B, Hl, Wl, ups, L, nh);
     LAUNCH_END();
@@ -653,13 +629,18 @@ extern "C" int dsee_prep_conv_weight(const float* w, void* out_hi, void* out_lo,
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     int64_t n = (int64_t)N * C * 9;
-    DSEE_CUDA(cudaMemsetAsync(inv_scale, 0, 2 * sizeof(float), st));
+    DSEE_CUDA(cudaMemsetAsync(inv_scale, 0, 3 * sizeof(float), st));
     int blocks = cdiv(n, 256 * 8);
     if (blocks > 1024) blocks = 1024;
     amax_kernel<<<blocks, 256, 0, st>>>(w, n, inv_scale + 1);
     count_launch();
     prep_weight_kernel<<<cdiv(n, 256), 256, 0, st>>>(w, (__half*)out_hi, (__half*)out_lo, inv_scale,
                                                      N, C, transpose);
+    if (transpose) {
+        count_launch();
+        DSEE_CUDA(cudaGetLastError());
+        row_l1max_kernel<<<C, 256, 0, st>>>((const __half*)out_hi, 9 * N, inv_scale);
+    }
     LAUNCH_END();
 }
 
@@ -778,24 +759,17 @@ extern "C" int dsee_stem_fwd(const float* x, const float* w, const float* bias, 
 extern "C" int dsee_head_fwd(const float* x, const float* w, const float* bias, float* out, int B,
                              int H, int W, int C, void* stream) {
     DSEE_CHECK_ARG(x && w && bias && out && B > 0 && H > 0 && W > 0, "bad argument");
-    DSEE_CHECK_ARG(C % 128 == 0 && (size_t)9 * C * 16 <= 200 * 1024, "C must be a multiple of 128 and <= 1408");
+    DSEE_CHECK_ARG(C > 0 && C % HT_CS == 0, "C must be a multiple of %d (got %d)", HT_CS, C);
     int rc = require_sm100();
     if (rc) return rc;
     static bool configured[64] = {false};
     int dev = 0;
     DSEE_CUDA(cudaGetDevice(&dev));
-    size_t sm = (size_t)9 * C * sizeof(float4);
     if (dev < 64 && !configured[dev]) {
-        DSEE_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       200 * 1024));
+        DSEE_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
         configured[dev] = true;
     }
-    int64_t nunits = (int64_t)B * ((H + HEAD_ROWS - 1) / HEAD_ROWS) * ((W + HEAD_PX - 1) / HEAD_PX);
-    int blocks = cdiv(nunits, 8);
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int per_sm = sm <= 110 * 1024 ? 2 : 1;  // __launch_bounds__(256, 2)
-    if (blocks > sms * per_sm) blocks = sms * per_sm;
-    head_kernel<<<blocks, 256, sm, (cudaStream_t)stream>>>(x, w, bias, out, B, H, W, C);
+    const int64_t tiles = (int64_t)B * ((H + HT_H - 1) / HT_H) * ((W + HT_W - 1) / HT_W);
+    head_kernel<<<(unsigned)tiles, 256, HT_SMEM, (cudaStream_t)stream>>>(x, w, bias, out, B, H, W, C);
     LAUNCH_END();
 }

@@ -111,6 +111,28 @@ def _norm_backward(norm, st, dt, dt_amax, x, x_ups, noise, noise_w, L, passes, w
         dxhat, dgb, sums = ops.spade_modulate_bwd(st.srcs, pwg, x, x_ups, st.sc, st.sh, st.gb, dt,
                                                   dt_amax, noise=noise, noise_w=noise_w, passes=passes,
                                                   want_lo=want_lo)
+    return (dxhat, sums) + _norm_backward_tail(st, dgb, L, passes, want_lo, ss)
+
+
+def _conv_and_norm_backward(st, g, W, a, x, x_ups, noise, noise_w, L, passes, want_lo, ss):
+    """Backward-data of a main conv (gradient planes ``g`` of its output, weight ``W``, input
+    activation planes ``a``) followed by K1's backward of the norm layer that produced ``a``
+    -> (dxhat, sums[4,C], dWm, dtab, dtb, dstyle).  With the saved G planes both run as ONE kernel
+    (ops.dgrad_modulate_bwd: dt stays in TMEM / registers); otherwise dgrad -> dt -> K1 backward."""
+    pwT = ops.prep_conv_weight(W.contiguous(), want_lo=want_lo, transpose=True)
+    if st.g is not None and config.fuse_dgrad_modbwd:
+        dxhat, dgb, sums = ops.dgrad_modulate_bwd(g, pwT, a.hi, st.g, x, x_ups, st.sc, st.sh, noise=noise,
+                                                  noise_w=noise_w, passes=passes, want_lo=want_lo)
+        st.g = None
+        return (dxhat, sums) + _norm_backward_tail(st, dgb, L, passes, want_lo, ss)
+    dt, amax = ops.conv3x3([g], pwT, None, passes=passes, act_mask=a.hi, want_amax=True, tag="dgrad")
+    return _norm_backward(None, st, dt, amax, x, x_ups, noise, noise_w, L, passes, want_lo, ss)
+
+
+def _norm_backward_tail(st, dgb, L, passes, want_lo, ss):
+    """From the [dG | dB] gradient planes: modulation-weight gradient, gradient of the sources
+    (mlp_shared table / bias, style matrix) -> (dWm, dtab, dtb, dstyle)."""
+    Wm = st.Wm
     dWm = ss.run(lambda: ops.conv3x3_wgrad_multi(dgb, st.srcs, passes=passes), dgb, *st.srcs)
     pwT = ops.prep_conv_weight(Wm.contiguous(), want_lo=want_lo, transpose=True)
     dsrc, dsrc_amax = ops.conv3x3([dgb], pwT, None, passes=passes, want_amax=True, tag="dgrad_mod")
@@ -130,7 +152,7 @@ def _norm_backward(norm, st, dt, dt_amax, x, x_ups, noise, noise_w, L, passes, w
             g = ops.style_gather_bwd(dsrc, coff, meta['labels'], L, d)
             dstyle = g if dstyle is None else dstyle + g
         coff += d
-    return dxhat, sums, dWm, dtab, dtb, dstyle
+    return dWm, dtab, dtb, dstyle
 
 
 def _sync_bwd_sums(nsums, st):
@@ -214,14 +236,10 @@ class _ResBlockFn(torch.autograd.Function):
         dnw_skip = sums[2] if noisy else None
         ss = _SideStream()
         dW1 = ss.run(lambda: ops.conv3x3_wgrad(g1, a1, passes=passes), g1, a1)
-        pwT = ops.prep_conv_weight(s['W1'].contiguous(), want_lo=want_lo, transpose=True)
-        dt1, amax1 = ops.conv3x3([g1], pwT, None, passes=passes, act_mask=a1.hi, want_amax=True,
-                                 tag="dgrad")
+        # ---- backward-data of conv_1 + norm_1 --------------------------------------------------
+        dxhat, nsums, dWm1, dtab1, dtb1, dstyle1 = _conv_and_norm_backward(
+            st1, g1, s['W1'], a1, dx1, 0, None, None, L, passes, want_lo, ss)
         del g1
-        # ---- norm_1 ----------------------------------------------------------------------------
-        dxhat, nsums, dWm1, dtab1, dtb1, dstyle1 = _norm_backward(
-            blk.norm_1, st1, dt1, amax1, dx1, 0, None, None, L, passes, want_lo, ss)
-        del dt1
         dgb1, dbb1 = nsums[2], nsums[3]
         nsums = _sync_bwd_sums(nsums, st1)
         ddx1, _ = ops.bn_bwd(dxhat, dx1, 0, st1.sc, st1.sh, nsums, st1.inv_count)
@@ -232,15 +250,11 @@ class _ResBlockFn(torch.autograd.Function):
         db0 = sums[0]
         dnw_mid = sums[1] if noisy else None
         dW0 = ss.run(lambda: ops.conv3x3_wgrad(g0, a0, passes=passes), g0, a0)
-        pwT = ops.prep_conv_weight(s['W0'].contiguous(), want_lo=want_lo, transpose=True)
-        dt0, amax0 = ops.conv3x3([g0], pwT, None, passes=passes, act_mask=a0.hi, want_amax=True,
-                                 tag="dgrad")
-        del g0
-        # ---- norm_0 (reads x through the folded upsample, + noise_in) ---------------------------
+        # ---- backward-data of conv_0 + norm_0 (reads x through the folded upsample, + noise_in) -
         nw_in = s['nw_in'] if noisy else None
-        dxhat, nsums, dWm0, dtab0, dtb0, dstyle0 = _norm_backward(
-            blk.norm_0, st0, dt0, amax0, x, ups, n_in, nw_in, L, passes, want_lo, ss)
-        del dt0
+        dxhat, nsums, dWm0, dtab0, dtb0, dstyle0 = _conv_and_norm_backward(
+            st0, g0, s['W0'], a0, x, ups, n_in, nw_in, L, passes, want_lo, ss)
+        del g0
         dgb0, dbb0 = nsums[2], nsums[3]
         nsums = _sync_bwd_sums(nsums, st0)
         dx, dnw_in_bn = ops.bn_bwd(dxhat, x, ups, st0.sc, st0.sh, nsums, st0.inv_count, noise=n_in,

@@ -168,7 +168,7 @@ def prep_conv_weight(w, want_lo=True, transpose=False):
     rows, cols = (Cin, N) if transpose else (N, Cin)
     hi = torch.empty((rows, 9 * cols), dtype=torch.float16, device=w.device)
     lo = torch.empty_like(hi) if want_lo else None
-    inv = torch.empty(2, dtype=torch.float32, device=w.device)
+    inv = torch.empty(3, dtype=torch.float32, device=w.device)  # [2^-e, max|w|, row-L1 bound (transpose)]
     _lib.check(_lib.load().dsee_prep_conv_weight(_p(w), _p(hi), _p(lo), _p(inv), N, Cin,
                                                  int(transpose), _stream()))
     return PreparedWeight(hi, lo, inv, rows, cols)
@@ -322,6 +322,44 @@ def spade_modulate_bwd_saved(g_planes, x, x_ups, bn_scale, bn_shift, dt, dt_amax
                                                  _p(bn_shift), _p(g_planes.hi), _p(g_planes.lo), _p(dt),
                                                  _p(dt_amax), B, H, W, Cc, _p(dxhat), _p(ghi), _p(glo),
                                                  _p(ginv), _p(part), _stream()))
+    return dxhat, GradPlanes(ghi, glo, ginv), reduce_partials(part)
+
+
+def dgrad_modulate_bwd(dy, pwT, act_mask, g_planes, x, x_ups, bn_scale, bn_shift, noise=None, noise_w=None,
+                       passes=3, want_lo=True, tag="dgrad_modbwd"):
+    """Backward-data of a main conv fused with K1's backward (dt never reaches HBM):
+    dy GradPlanes of the conv output, pwT = prep_conv_weight(W, transpose=True), act_mask = fp16 hi
+    plane of the conv's input activation, g_planes = G saved by K1's forward.
+    -> (dxhat fp32 NHWC, dgb GradPlanes [B,H,W,2C] interleaved, sums fp32 [4,C])."""
+    ops, (B, H, W) = _operands([dy], pwT, passes)
+    _chk_cuda(act_mask, g_planes.hi, g_planes.lo, x, bn_scale, bn_shift, noise, noise_w)
+    Cc = x.shape[3]
+    assert pwT.n_total == Cc and tuple(act_mask.shape) == (B, H, W, Cc)
+    assert tuple(x.shape[:3]) == (B, H >> x_ups, W >> x_ups)
+    dev = x.device
+    lib = _lib.load()
+    dxhat = torch.empty((B, H, W, Cc), dtype=torch.float32, device=dev)
+    ghi = torch.empty((B, H, W, 2 * Cc), dtype=torch.float16, device=dev)
+    glo = torch.empty_like(ghi) if want_lo else None
+    ginv = torch.empty(1, dtype=torch.float32, device=dev)
+    part = torch.empty((lib.dsee_conv3x3_stats_tiles(B, H, W), Cc, 4), dtype=torch.float32, device=dev)
+    a = _lib.DgradModBwdArgs()
+    a.act_mask = act_mask.data_ptr()
+    a.g_hi = g_planes.hi.data_ptr()
+    a.g_lo = g_planes.lo.data_ptr() if g_planes.lo is not None else 0
+    a.x, a.x_ups = x.data_ptr(), x_ups
+    nptr, nseed = _noise(noise)
+    a.noise, a.noise_seed = nptr.value or 0, nseed
+    a.noise_w = noise_w.data_ptr() if noise_w is not None else 0
+    a.bn_scale, a.bn_shift = bn_scale.data_ptr(), bn_shift.data_ptr()
+    a.dy_amax = dy.inv_scale.data_ptr() + 4        # grad_prep: inv_scale[1] = max|dY|
+    a.w_l1 = pwT.inv_scale.data_ptr() + 8          # prep_conv_weight(transpose): inv_scale[2]
+    a.dxhat, a.dgb_hi = dxhat.data_ptr(), ghi.data_ptr()
+    a.dgb_lo = glo.data_ptr() if glo is not None else 0
+    a.dgb_inv_scale, a.partial, a.C = ginv.data_ptr(), part.data_ptr(), Cc
+    flops = 2.0 * 9 * pwT.cin * pwT.n_total * B * H * W
+    _timed("%s_%dx%d" % (tag, H, W), flops,
+           lambda: _lib.check(lib.dsee_dgrad_modulate_bwd(C.byref(ops), C.byref(a), _stream())))
     return dxhat, GradPlanes(ghi, glo, ginv), reduce_partials(part)
 
 

@@ -57,7 +57,7 @@ int dsee_resize_labels(const uint8_t* in, uint8_t* out, int B, int Hin, int Win,
 /* ---- noise injection ---------------------------------------------------------------------------- */
 /* NoiseInjection (normalization.py:299-304) draws a fresh N(0,1) tensor per forward.  Every entry
  * point that takes a `noise` tensor also takes a `noise_seed`: with noise == NULL and a non-zero
- * seed the tensor's elements are regenerated on the fly (Philox4x32-10 keyed by the seed, counter =
+ * seed the tensor's elements are regenerated on the fly (Philox4x32-7 keyed by the seed, counter =
  * NHWC element index / 4, Box-Muller), identically in every kernel, and never touch HBM.
  * dsee_noise_fill materialises exactly that tensor (tests; n % 4 == 0). */
 int dsee_noise_fill(unsigned long long seed, float* out, int64_t n, void* stream);
@@ -83,8 +83,9 @@ int dsee_style_gather_fwd(const uint8_t* labels, const float* style, void* out_h
 /* Conv weight fp32 [N][C][3][3] (PyTorch layout; spectral normalisation already applied,
  * architecture.py:40-44) -> GEMM B-operand planes fp16 [N][9*C] with k = (ky*3+kx)*C + c,
  * multiplied by a power of two 2^e chosen so max|w|*2^e is in [2^13, 2^14) (keeps the lo plane
- * out of the fp16 subnormal range). inv_scale is a device float[2]: [0] receives 2^-e (what the
- * conv kernels read), [1] is scratch (max|w|).
+ * out of the fp16 subnormal range). inv_scale is a device float[3]: [0] receives 2^-e (what the
+ * conv kernels read), [1] max|w|, [2] (transpose=1 only) max over rows of sum |w| along the row =
+ * the factor that bounds the backward-data result (dsee_dgrad_modulate_bwd.w_l1).
  * transpose=1 builds the backward-data operand instead (autograd of F.conv2d wrt its input =
  * convolution of the output gradient with the transposed, 180-degree-rotated filter):
  * planes [C][9*N] with k = (8-tap)*N + n. */
@@ -267,6 +268,40 @@ typedef struct {
     float* dgb_inv_scale;
 } dsee_modulate_bwd_args;
 int dsee_spade_modulate_bwd(const dsee_conv_operands* ops, const dsee_modulate_bwd_args* args,
+                            void* stream);
+
+/* Backward-data of a main conv (architecture.py:98,122) FUSED with K1's backward (autograd of
+ * normalization.py:105-120,167-213,254-286 + architecture.py:147's LeakyReLU): `ops` are the gradient
+ * planes of the conv output and the weight from dsee_prep_conv_weight(transpose=1); the accumulator
+ * dt = conv_transpose(dY, W) * LeakyReLU'(t) never reaches HBM.  The epilogue reads the saved
+ * activation's sign (act_mask), the saved G = gamma + gamma_bias planes and x, and writes
+ *   dxhat fp32 NHWC = dt * G,   dgb planes [B,H,W,2C] = [dt * xhat | dt] (scaled fp16, channels
+ *   interleaved per 128 like the modulation weight rows), partial [dsee_conv3x3_stats_tiles()][C][4]
+ *   = tile sums of (dxhat, dxhat*xhat, dG, dB).
+ * The plane scale comes from a bound available before the GEMM runs: |dt| <= dy_amax * w_l1 with
+ * dy_amax = max|dY| (inv_scale[1] of dsee_grad_prep) and w_l1 = max over input channels of
+ * sum_{n,tap} |W| (inv_scale[2] of dsee_prep_conv_weight(transpose=1)). */
+typedef struct {
+    const void* act_mask;       /* fp16 hi plane of the forward activation a = LeakyReLU(t) */
+    const void* g_hi;           /* saved G planes (dsee_modulate_args.g_hi / g_lo) */
+    const void* g_lo;           /* NULL for 1-pass */
+    const float* x;             /* K1's x input (fp32 NHWC, at H >> x_ups) */
+    int x_ups;
+    const float* noise;         /* NoiseInjection on x: tensor, or NULL with noise_seed != 0 */
+    unsigned long long noise_seed;
+    const float* noise_w;
+    const float* bn_scale;
+    const float* bn_shift;
+    const float* dy_amax;       /* device scalar */
+    const float* w_l1;          /* device scalar */
+    float* dxhat;
+    void* dgb_hi;
+    void* dgb_lo;
+    float* dgb_inv_scale;       /* out: 2^-e of the dgb planes */
+    float* partial;
+    int C;
+} dsee_dgrad_modbwd_args;
+int dsee_dgrad_modulate_bwd(const dsee_conv_operands* ops, const dsee_dgrad_modbwd_args* args,
                             void* stream);
 
 /* ---- generator backward (autograd of the fused kernels above) -------------------------------- */

@@ -61,7 +61,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.reps
-        print("%-22s %8.3f ms  %7.1f TFLOP/s (reference-equivalent), x%d executed" %
+        print("%-28s %8.3f ms  %7.1f TFLOP/s (reference-equivalent), x%d executed" %
               (name, ms, flops / ms / 1e9, a.passes))
         return r
 
@@ -77,6 +77,8 @@ def main():
     timed("wgrad 512x512", lambda: ops.conv3x3_wgrad(gp, act, passes=a.passes), 2 * 9 * C * C * px)
     dxhat, dgb, sums = timed("K1 backward (saved G)", lambda: ops.spade_modulate_bwd_saved(
         gsaved, x, 0, sc, sh, dt, amax, want_lo=want_lo), 0.0)
+    timed("dgrad + K1 backward (fused)", lambda: ops.dgrad_modulate_bwd(
+        gp, pwT, act.hi, gsaved, x, 0, sc, sh, passes=a.passes, want_lo=want_lo), 2 * 9 * C * C * px)
     timed("dgrad_mod", lambda: ops.conv3x3([dgb], pwmT, None, passes=a.passes, tag="dgrad_mod"),
           2 * 9 * (nh + d) * 2 * C * px)
     timed("wgrad modulation", lambda: ops.conv3x3_wgrad_multi(dgb, [actv, smap], passes=a.passes),

@@ -161,7 +161,7 @@ def test_generator_backward_eval_mode():
 
 def test_in_kernel_noise_matches_materialised_stream():
     """NoiseInjection in production is a seed: every kernel regenerates the tensor's elements
-    (Philox4x32-10 + Box-Muller).  (a) the stream is N(0,1); (b) a training forward+backward run on
+    (Philox4x32-7 + Box-Muller).  (a) the stream is N(0,1); (b) a training forward+backward run on
     seeds equals, bit for bit, the same run fed the tensors dsee_noise_fill materialises from those
     seeds - i.e. statistics pass, K1, K2 epilogues and the backward kernels all see identical noise."""
     from deepsee_b200 import ops

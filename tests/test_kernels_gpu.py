@@ -228,6 +228,47 @@ def test_dgrad_leaky_relu_mask():
     assert (dt - t.grad).abs().max().item() <= 3e-5 * t.grad.abs().max().item()
 
 
+@pytest.mark.parametrize("passes", [1, 3])
+@pytest.mark.parametrize("ups,noisy", [(0, False), (1, True)])
+def test_fused_dgrad_modulate_bwd_matches_two_kernel_path(ups, noisy, passes):
+    """dsee_dgrad_modulate_bwd (backward-data GEMM with K1's backward as its epilogue, plane scale from
+    the a-priori bound max|dY| * row-L1(W)) against dgrad -> dt in HBM -> dsee_spade_modulate_bwd_saved
+    (plane scale from the measured max|dt|): dxhat identical, [dG|dB] planes equal after un-scaling to
+    fp16 rounding, per-channel sums equal to summation order."""
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(21 + ups)
+    B, H, W, C = 2, 24, 32, 256
+    want_lo = passes == 3
+    Hx, Wx = H >> ups, W >> ups
+    x = torch.randn(B, Hx, Wx, C, generator=g).cuda()
+    act = ops.split_f16(torch.randn(B, H, W, C, generator=g).cuda(), want_lo)
+    G = ops.split_f16((torch.randn(B, H, W, C, generator=g) * 0.5 + 1).cuda(), want_lo)
+    w = (torch.randn(C, C, 3, 3, generator=g) / (3 * C ** 0.5)).cuda()
+    dy = (torch.randn(B, H, W, C, generator=g) * 1e-3).cuda()
+    sc = (torch.rand(C, generator=g) + 0.5).cuda()
+    sh = (torch.randn(C, generator=g) * 0.1).cuda()
+    noise = torch.randn(B, H, W, C, generator=g).cuda() if noisy else None
+    nw = (torch.randn(C, generator=g) * 0.3).cuda() if noisy else None
+    gp, _ = ops.grad_prep(dy, want_lo=want_lo)
+    pwT = ops.prep_conv_weight(w, want_lo, transpose=True)
+    # the a-priori bound really bounds dt
+    dt, amax = ops.conv3x3([gp], pwT, None, passes=passes, act_mask=act.hi, want_amax=True)
+    bound = float(gp.inv_scale[1]) * float(pwT.inv_scale[2])
+    l1 = float(w.abs().sum(dim=(0, 2, 3)).max())
+    assert abs(float(pwT.inv_scale[2]) - l1) <= 5e-3 * l1
+    assert float(amax) <= bound
+    dxh0, dgb0, s0 = ops.spade_modulate_bwd_saved(G, x, ups, sc, sh, dt, amax, noise=noise, noise_w=nw,
+                                                  want_lo=want_lo)
+    dxh1, dgb1, s1 = ops.dgrad_modulate_bwd(gp, pwT, act.hi, G, x, ups, sc, sh, noise=noise, noise_w=nw,
+                                            passes=passes, want_lo=want_lo)
+    assert torch.equal(dxh0, dxh1)
+    val = lambda p: (p.hi.float() + (p.lo.float() if p.lo is not None else 0)) * p.inv_scale
+    v0, v1 = val(dgb0), val(dgb1)
+    tol = (2e-6 if want_lo else 1.2e-3) * v0.abs().max().item()
+    assert (v0 - v1).abs().max().item() <= tol
+    torch.testing.assert_close(s1, s0, rtol=1e-4, atol=1e-5 * s0.abs().max().item())
+
+
 @pytest.mark.parametrize("ups,noisy", [(0, False), (1, True), (1, False)])
 def test_bn_bwd_matches_autograd(ups, noisy):
     from deepsee_b200 import ops
