@@ -315,12 +315,35 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                     if (p.rnoise_w[0]) nw0 = __ldg(reinterpret_cast<const float4*>(p.rnoise_w[0] + nc));
                     if (p.rnoise_w[1]) nw1 = __ldg(reinterpret_cast<const float4*>(p.rnoise_w[1] + nc));
                     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
+                    // residual / mask loads of all 8 steps are issued before the first use
+                    float4 rq[8];
+                    uint2 mq[8];
+                    bool ok[8];
+#pragma unroll
                     for (int st = 0; st < 8; ++st) {
+                        const int mm = q * 32 + st * 4 + er;
+                        const int yy = h0 + mm / TILE_W, xx = w0 + mm % TILE_W;
+                        ok[st] = (yy < p.H) && (xx < p.W);
+                        rq[st] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        mq[st] = make_uint2(0u, 0u);
+                        if (ok[st]) {
+                            if (p.residual) {
+                                const size_t rp = ((size_t)b * Hr + (yy >> p.res_ups)) * Wr + (xx >> p.res_ups);
+                                rq[st] = __ldg(reinterpret_cast<const float4*>(p.residual + rp * p.n_total + nc));
+                            }
+                            if (p.act_mask) {
+                                const size_t pix = ((size_t)b * p.Hm + (yy * p.o_step + p.o_offy)) * p.Wm +
+                                                   (xx * p.o_step + p.o_offx);
+                                mq[st] = __ldg(reinterpret_cast<const uint2*>(p.act_mask + pix * p.n_total + nc));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int st = 0; st < 8; ++st) {
+                        if (!ok[st]) continue;
                         const int pi = st * 4 + er;
                         const int mm = q * 32 + pi;
                         const int yy = h0 + mm / TILE_W, xx = w0 + mm % TILE_W;
-                        if (yy >= p.H || xx >= p.W) continue;
                         const float* tp = T + pi * 33 + ecq * 4;
                         float o[4] = {tp[0] * inv_scale + bias4.x, tp[1] * inv_scale + bias4.y,
                                       tp[2] * inv_scale + bias4.z, tp[3] * inv_scale + bias4.w};
@@ -332,17 +355,13 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                                            (xx * p.o_step + p.o_offx);
                         const size_t oe = pix * p.n_total + nc;
                         if (p.act_mask) {
-                            const uint2 mv = __ldg(reinterpret_cast<const uint2*>(p.act_mask + oe));
+                            const uint2 mv = mq[st];
                             const uint32_t m16[4] = {mv.x & 0xffffu, mv.x >> 16, mv.y & 0xffffu, mv.y >> 16};
 #pragma unroll
                             for (int e = 0; e < 4; ++e)  // fp16 > 0 <=> sign clear and magnitude non-zero
                                 if (!(m16[e] != 0 && m16[e] < 0x8000u)) o[e] *= 0.2f;
                         }
-                        if (p.residual) {
-                            const size_t rp = ((size_t)b * Hr + (yy >> p.res_ups)) * Wr + (xx >> p.res_ups);
-                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + rp * p.n_total + nc));
-                            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-                        }
+                        o[0] += rq[st].x; o[1] += rq[st].y; o[2] += rq[st].z; o[3] += rq[st].w;
                         if (p.rnoise_w[0]) {
                             const float4 r4 = load_noise4(p.rnoise[0], p.rnoise_seed[0], oe);
                             o[0] += nw0.x * r4.x; o[1] += nw0.y * r4.y; o[2] += nw0.z * r4.z; o[3] += nw0.w * r4.w;
@@ -501,20 +520,37 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                     for (int k = 0; k < 4; ++k)
 #pragma unroll
                         for (int e = 0; e < 4; ++e) sm[k][e] = 0.f;
-#pragma unroll 2
+                    // all global loads of the chunk's 8 steps are issued before the first use (one
+                    // memory round trip per chunk instead of eight)
+                    float4 xq[8];
+                    uint2 mq[8], gq[8], lq[8];
+                    bool ok[8];
+#pragma unroll
                     for (int st = 0; st < 8; ++st) {
+                        const int mm = q * 32 + st * 4 + er;
+                        const int yy = h0 + mm / TILE_W, xx = w0 + mm % TILE_W;
+                        ok[st] = (yy < p.H) && (xx < p.W);
+                        xq[st] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        mq[st] = gq[st] = lq[st] = make_uint2(0u, 0u);
+                        if (ok[st]) {
+                            const size_t pe = (((size_t)b * p.H + yy) * p.W + xx) * p.C + cc;
+                            const size_t xp = ((size_t)b * Hx + (yy >> p.x_ups)) * Wx + (xx >> p.x_ups);
+                            xq[st] = __ldg(reinterpret_cast<const float4*>(p.x + xp * p.C + cc));
+                            mq[st] = __ldg(reinterpret_cast<const uint2*>(p.act_mask + pe));
+                            gq[st] = __ldg(reinterpret_cast<const uint2*>(p.gs_hi + pe));
+                            if (p.gs_lo) lq[st] = __ldg(reinterpret_cast<const uint2*>(p.gs_lo + pe));
+                        }
+                    }
+#pragma unroll
+                    for (int st = 0; st < 8; ++st) {
+                        if (!ok[st]) continue;
                         const int pi = st * 4 + er;
                         const int mm = q * 32 + pi;
                         const int yy = h0 + mm / TILE_W, xx = w0 + mm % TILE_W;
-                        if (yy >= p.H || xx >= p.W) continue;
                         const size_t pix = ((size_t)b * p.H + yy) * p.W + xx;
                         const size_t pe = pix * p.C + cc;
-                        const size_t xp = ((size_t)b * Hx + (yy >> p.x_ups)) * Wx + (xx >> p.x_ups);
-                        float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + xp * p.C + cc));
-                        const uint2 mv = __ldg(reinterpret_cast<const uint2*>(p.act_mask + pe));
-                        const uint2 gv = __ldg(reinterpret_cast<const uint2*>(p.gs_hi + pe));
-                        uint2 lv = make_uint2(0u, 0u);
-                        if (p.gs_lo) lv = __ldg(reinterpret_cast<const uint2*>(p.gs_lo + pe));
+                        float4 xv = xq[st];
+                        const uint2 mv = mq[st], gv = gq[st], lv = lq[st];
                         if (has_noise) {
                             const float4 nv = load_noise4(p.noise, p.noise_seed, pe);
                             xv.x += nw4.x * nv.x; xv.y += nw4.y * nv.y; xv.z += nw4.z * nv.z; xv.w += nw4.w * nv.w;
@@ -613,6 +649,17 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                     if (has_noise) nw4 = __ldg(reinterpret_cast<const float4*>(p.noise_w + cc));
                     const float scv[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, shv[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
                     const float gbv[4] = {gb4.x, gb4.y, gb4.z, gb4.w}, bbv[4] = {bb4.x, bb4.y, bb4.z, bb4.w};
+                    float4 xq[8];
+#pragma unroll
+                    for (int st = 0; st < 8; ++st) {  // x loads of all 8 steps issued up front
+                        const int mm = q * 32 + st * 4 + er;
+                        const int yy = h0 + mm / TILE_W, xx = w0 + mm % TILE_W;
+                        xq[st] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (yy < p.H && xx < p.W) {
+                            const size_t xp = ((size_t)b * Hx + (yy >> p.x_ups)) * Wx + (xx >> p.x_ups);
+                            xq[st] = __ldg(reinterpret_cast<const float4*>(p.x + xp * p.C + cc));
+                        }
+                    }
 #pragma unroll
                     for (int st = 0; st < 8; ++st) {
                         const int pi = st * 4 + er;
@@ -621,8 +668,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         if (yy >= p.H || xx >= p.W) continue;
                         const size_t pix = ((size_t)b * p.H + yy) * p.W + xx;
                         const size_t pe = pix * p.C + cc;
-                        const size_t xp = ((size_t)b * Hx + (yy >> p.x_ups)) * Wx + (xx >> p.x_ups);
-                        float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + xp * p.C + cc));
+                        float4 xv = xq[st];
                         if (has_noise) {
                             const float4 nv = load_noise4(p.noise, p.noise_seed, pe);
                             xv.x += nw4.x * nv.x; xv.y += nw4.y * nv.y; xv.z += nw4.z * nv.z; xv.w += nw4.w * nv.w;
