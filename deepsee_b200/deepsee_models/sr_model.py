@@ -7,8 +7,10 @@ networks underneath run on the deepsee_b200 CUDA kernels.  Differences, all deli
     DataParallel are gone (data parallelism = one SRModel per rank + NCCL gradient all-reduce,
     see managers/base_manager.py);
   * the [seg | image] / fake | real concatenations of `discriminate` are one fused kernel;
-  * the demo-only style-manipulation modes (sr_model.py:116-444) are not part of the hot path;
-    'inference_noise' is kept, the others raise NotImplementedError.
+  * the demo-time style-manipulation modes (sr_model.py:116-444) batch all their variants into one
+    generator call instead of one batch-1 call per variant (`_style_sweep`);
+    'inference_replace_semantics' is broken in the reference (calls a method that does not exist)
+    and raises NotImplementedError here.
 """
 import random
 from collections import OrderedDict
@@ -20,6 +22,11 @@ from . import networks
 from .. import ops
 from ..config import config
 from ..util import util
+
+
+_SWEEP_MODES = ("inference_multi_modal", "inference_reference_semantics", "inference_interpolation",
+                "inference_interpolation_style", "inference_reference", "inference_reference_interpolation")
+_CONSISTENT_REGIONS = [4, 6, 8, 11]   # left/right pairs kept consistent (sr_model.py:134,314)
 
 
 class SRModel(torch.nn.Module):
@@ -104,12 +111,161 @@ class SRModel(torch.nn.Module):
                 fake_image = torch.stack([fake_image[i * n:i * n + n] for i in range(n)], dim=0)
                 return OrderedDict([("input_label", input_semantics), ("image_downsized", image_lr),
                                     ("fake_image", fake_image), ("image_full", image_hr)])
-        elif mode.startswith("inference_"):
+        elif mode in _SWEEP_MODES:
+            with torch.no_grad():
+                return self._style_sweep(mode, data)
+        elif mode == "inference_particular_combined":
+            # sr_model.py:298-345: LR-only ("mini") style, optionally perturbed in opt.region_idx
+            with torch.no_grad():
+                style, _ = self.encode_style(input_semantics=input_semantics, downscaled_image=image_lr,
+                                             no_noise=True, encode_full=False)
+                if self.opt.noise_delta > 0:
+                    ridx = self._region_idx(input_semantics)
+                    style[:, ridx] = (style[:, ridx] + self.get_noise(style[:, ridx].shape,
+                                                                      self.opt.noise_delta)).clamp(-1, 1)
+                    style[:, _CONSISTENT_REGIONS] = style[:, [r + 1 for r in _CONSISTENT_REGIONS]]
+                fake, _, _ = self.generate_fake(input_semantics=input_semantics, image_downsized=image_lr,
+                                                encoded_style=style)
+                out = OrderedDict([("input_label", input_semantics), ("image_downsized", image_lr),
+                                   ("fake_image_original", fake), ("image_full", image_hr)])
+                return self._with_guiding(out, data)
+        elif mode == "inference_particular_full":
+            # sr_model.py:347-380: style of the HR image itself, and (guided models) of the guiding image
+            with torch.no_grad():
+                style, _ = self.encode_style(no_noise=True, encode_full=True, guiding_image=image_hr,
+                                             guiding_label=input_semantics)
+                fake, _, _ = self.generate_fake(input_semantics=input_semantics, image_downsized=image_lr,
+                                                encoded_style=style)
+                out = OrderedDict([("input_label", input_semantics), ("image_downsized", image_lr),
+                                   ("fake_image_original", fake), ("image_full", image_hr)])
+                if self.opt.guiding_style_image:
+                    gstyle, _ = self.encode_style(no_noise=True, encode_full=True, guiding_image=guiding_image,
+                                                  guiding_label=guiding_label)
+                    out["fake_image_guiding"], _, _ = self.generate_fake(
+                        input_semantics=input_semantics, image_downsized=image_lr, encoded_style=gstyle)
+                return self._with_guiding(out, data)
+        elif mode == "inference_replace_semantics":
             raise NotImplementedError(
-                "mode %r is a demo-only style manipulation of the reference (sr_model.py:116-444) "
-                "and is not part of the B200 hot path" % mode)
+                "mode 'inference_replace_semantics' calls SRModel.preprocess_input, which does not exist "
+                "in the reference either (sr_model.py:185); edit the label map before preprocessing and "
+                "use mode 'inference'")
         else:
             raise ValueError("|mode| is invalid")
+
+    # ---- demo-time style manipulation (sr_model.py:130-444) ------------------------------------------
+    def _region_idx(self, input_semantics):
+        r = getattr(self.opt, "region_idx", None)
+        return list(r) if r else list(range(input_semantics.size(1)))
+
+    def _with_guiding(self, out, data):
+        if self.opt.guiding_style_image:
+            for k_out, k_in in (("guiding_image_id", "guiding_image_id"), ("guiding_image", "guiding_image"),
+                                ("guiding_input_label", "guiding_label")):
+                if k_in in data:
+                    out[k_out] = data[k_in]
+        return out
+
+    def get_noise(self, shape, delta):
+        """sr_model.py:448-457."""
+        dist = getattr(self.opt, "noise_dist", "normal")
+        if dist == "normal":
+            noise = torch.randn(shape).clamp(-1, 1) * delta
+        elif dist == "uniform":
+            noise = torch.rand(shape).clamp(-1, 1) * delta
+        else:
+            raise ValueError("Invalid noise distribution: {}".format(dist))
+        return noise.cuda()
+
+    def _style_sweep(self, mode, data):
+        """The reference's style-manipulation modes (sr_model.py:130-166,198-296,381-444) all do the
+        same thing: build, per sample b, a list of variant style matrices, generate one image per
+        variant and lay the variants out side by side (or stacked with --dont_merge_fake).  The
+        reference runs one batch-1 generator call per variant; here all variants of all samples go
+        through ONE generator call (batch = B x variants), which is what the B200 kernels want."""
+        import numpy as np
+        opt = self.opt
+        sem, lr, hr = data["input_semantics"], data["image_lr"], data.get("image_hr")
+        gi, gl = data.get("guiding_image"), data.get("guiding_label")
+        B = sem.size(0)
+        ridx = self._region_idx(sem)
+        n = getattr(opt, "n_interpolation", 5)
+        delta = getattr(opt, "noise_delta", 0.0)
+        sem_of = list(range(B))           # which sample's semantics / LR image each row uses
+        variants = [[] for _ in range(B)]
+        if mode == "inference_reference_semantics":
+            # sr_model.py:198-218: every sample rendered with every sample's label map, own style
+            style = None
+        elif mode == "inference_interpolation_style":
+            s_from, s_to = data["style_from"].to(sem.device), data["style_to"].to(sem.device)
+            assert n % 2 == 1, "Please use an odd n such that the middle image has delta=0"
+            for b in range(B):
+                for t in np.linspace(0, 1, num=n):
+                    variants[b].append((1 - t) * s_from[b] + t * s_to[b])
+        else:
+            if mode == "inference_interpolation" and "style_matrix" in data:
+                style = data["style_matrix"]
+            elif mode in ("inference_reference", "inference_reference_interpolation"):
+                style, _ = self.encode_style(input_semantics=sem, full_image=hr, no_noise=True, encode_full=True,
+                                             guiding_image=gi if mode == "inference_reference" else None,
+                                             guiding_label=gl if mode == "inference_reference" else None)
+            else:
+                style, _ = self.encode_style(downscaled_image=lr, input_semantics=sem, full_image=hr,
+                                             no_noise=True, guiding_image=gi, guiding_label=gl)
+            for b in range(B):
+                if mode == "inference_multi_modal":        # :130-166 random perturbations
+                    for _ in range(n):
+                        v = style[b].clone()
+                        v[ridx] = (v[ridx] + self.get_noise(v[ridx].shape, delta)).clamp(-1, 1)
+                        v[_CONSISTENT_REGIONS] = v[[r + 1 for r in _CONSISTENT_REGIONS]]
+                        variants[b].append(v)
+                elif mode == "inference_interpolation":    # :219-261 shift the style by -delta..delta
+                    assert n % 2 == 1, "Please use an odd n such that the middle image has delta=0"
+                    for step in np.linspace(-delta, delta, num=n):
+                        v = style[b].clone()
+                        v[ridx] = (v[ridx] + float(step)).clamp(-1, 1)
+                        variants[b].append(v)
+                elif mode == "inference_reference":        # :381-410 regions of every other sample
+                    for other in range(B):
+                        v = style[b].clone()
+                        v[ridx] = style[other, ridx].clamp(-1, 1)
+                        variants[b].append(v)
+                elif mode == "inference_reference_interpolation":   # :411-444 towards the next sample
+                    a = style[b].clone()
+                    tgt = style[(b + 1) % B].clone() * getattr(opt, "manipulate_scale", 1.0)
+                    for t in np.linspace(0, 1, num=n):
+                        # (the reference updates style_a in place, so each step starts from the last)
+                        a[ridx] = ((1 - float(t)) * a[ridx] + float(t) * tgt[ridx]).clamp(-1, 1)
+                        variants[b].append(a.clone())
+        if mode == "inference_reference_semantics":
+            # NOTE reference quirk (:205-207): the inner loop overwrites current_semantics[b] with every
+            # sample's map in turn, so what is rendered is sample b <- the LAST sample's semantics
+            rows_sem, rows_lr = [], []
+            for b in range(B):
+                cur = sem.clone()
+                cur[b] = sem[B - 1]
+                rows_sem.append(cur)
+                rows_lr.append(lr)
+            fake, _, _ = self.generate_fake(input_semantics=torch.cat(rows_sem, 0),
+                                            image_downsized=torch.cat(rows_lr, 0))
+            fake_out = torch.cat(list(fake.split(B, 0)), -1)
+            applied = []
+        else:
+            per = len(variants[0])
+            z = torch.stack([v for b in range(B) for v in variants[b]], 0)
+            rep = torch.tensor([sem_of[b] for b in range(B) for _ in range(per)], device=sem.device)
+            fake, _, _ = self.generate_fake(input_semantics=sem[rep], image_downsized=lr[rep], encoded_style=z)
+            fake = fake.view(B, per, *fake.shape[1:])
+            if getattr(opt, "dont_merge_fake", False):
+                fake_out = fake                                              # [B, variants, 3, H, W]
+                applied = [torch.stack(variants[b]) for b in range(B)]
+            else:
+                fake_out = torch.cat([fake[:, i] for i in range(per)], -1)  # variants side by side
+                applied = []
+        out = OrderedDict([("input_label", sem), ("image_downsized", lr), ("fake_image", fake_out),
+                           ("image_full", hr)])
+        if mode in ("inference_interpolation", "inference_interpolation_style", "inference_multi_modal"):
+            out["style"] = applied
+        return self._with_guiding(out, data)
 
     def create_optimizers(self, opt):
         """sr_model.py:469-495: Adam; TTUR lr/2 for G (+E), 2*lr for D; "mini" params at lr_G/4."""

@@ -17,7 +17,7 @@ DEFAULTS = dict(
     gan_mode='hinge', lambda_feat=10.0, lambda_vgg=10.0, no_ganFeat_loss=False, no_vgg_loss=True,
     lr=0.0002, beta1=0.0, beta2=0.9, no_TTUR=False, gradient_clip=-1.0, niter=50, niter_decay=25,
     dataset='celebamaskhq', noise_dist='normal', noise_delta=0.0, n_interpolation=5,
-    region_idx=None, dont_merge_fake=False,
+    region_idx=None, dont_merge_fake=False, manipulate_scale=1.0,
 )
 
 

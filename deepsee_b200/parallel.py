@@ -39,7 +39,11 @@ def init_from_env(backend=None):
     if torch.cuda.is_available():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
-    dist.init_process_group(backend=backend, init_method="env://")
+    kw = {}
+    if backend == "nccl":
+        # bind the communicator to this rank's GPU up front (eager NCCL init, no device guessing in barrier())
+        kw["device_id"] = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group(backend=backend, init_method="env://", **kw)
 
 
 def allreduce_sum_(t):

@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--B", type=int, default=8)
     ap.add_argument("--S", type=int, default=256)
     ap.add_argument("--C", type=int, default=512)
+    ap.add_argument("--no-warm", action="store_true",
+                    help="launch every kernel exactly once (for `ncu --set full`, which replays each launch ~40 times)")
     a = ap.parse_args()
     B, S, C, L, nh, d = a.B, a.S, a.C, 19, 128, 128
     want_lo = a.passes == 3
@@ -52,8 +54,9 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         # two warm-up calls with the first result still alive: the timed loop then recycles two
         # cached output sets and never reaches cudaMalloc
-        r = fn()
-        r = fn()
+        if not a.no_warm:
+            r = fn()
+            r = fn()
         torch.cuda.synchronize()
         e0.record()
         for _ in range(a.reps):
@@ -88,8 +91,9 @@ def main():
     # of each output; in-kernel noise costs no bytes) -------------------------------------------
     def hbm(name, fn, nbytes):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r = fn()
-        r = fn()
+        if not a.no_warm:
+            r = fn()
+            r = fn()
         torch.cuda.synchronize()
         e0.record()
         for _ in range(a.reps):

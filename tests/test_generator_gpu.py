@@ -3,8 +3,9 @@ reference-shaped modules (which go through the C ABI), against
   (a) golden outputs of the unmodified reference (tests/golden, reduced width), and
   (b) the CPU oracle on the same seeded inputs at full width (512 channels).
 Tolerance: north_star states 1e-3 max-abs on the generator output (tanh range); the default
-3-pass split-fp16 tensor-core path is asserted at 2e-4, the 1-pass (TF32-class) mode is
-asserted at 1e-2 and its measured error printed."""
+3-pass split-fp16 tensor-core path is asserted at 2e-4; the 1-pass (TF32-class) mode, which is what
+bench.py measures, is asserted at 1e-3 on the full-width (512-channel) generator and at 1e-2 on the
+reduced-width golden cases (their pre-tanh scale is larger), measured errors printed."""
 import os
 
 import numpy as np
@@ -94,7 +95,8 @@ def test_generator_eval_full_width_vs_oracle():
     e1 = (out1.cpu() - ref).abs()
     print("full width 1-pass (fp16 operands, TF32-class) max-abs vs oracle: %.3e, mean-abs %.3e"
           % (e1.max().item(), e1.mean().item()))
-    assert e1.max().item() < 1e-2
+    # north_star: "outputs within 1e-3 max-abs of reference" - the precision bench.py measures
+    assert e1.max().item() < 1e-3
 
 
 def test_generator_rejects_non_onehot():
@@ -209,3 +211,65 @@ def test_srmodel_inference_mode_vs_oracle(tmp_path):
     err = (out["fake_image"].cpu() - ref_fake).abs().max().item()
     print("SRModel inference max-abs vs oracle:", err)
     assert err < 3e-4
+
+
+def test_srmodel_style_sweep_modes_match_demo_mode(tmp_path):
+    """The demo-time style-manipulation modes (sr_model.py:219-296,381-410) batch all variants into
+    one generator call; every variant must equal what mode 'demo' renders for that style matrix."""
+    import numpy as np
+    from deepsee_b200.managers.base_manager import BaseManager
+    o = O.make_opt("8x_independent_256x256", ngf=8, start_size=8, crop_size=64, load_size=64)
+    ck = tmp_path / o.name
+    ck.mkdir()
+    torch.save({"model": O.make_generator_state(o, 0)}, str(ck / "latest_net_SR.pth"))
+    torch.save({"model": O.make_encoder_state(o, 1)}, str(ck / "latest_net_E.pth"))
+    opt = _mk_opt(o, checkpoints_dir=str(tmp_path), n_interpolation=3, noise_delta=0.25, region_idx=[1, 2, 5],
+                  dont_merge_fake=False, manipulate_scale=1.0, batchSize=2)
+    mgr = BaseManager(opt)
+    model = mgr.sr_model.eval()
+    raw = O.synthetic_batch(o, 2, seed=41)
+    data = mgr.preprocess({"label": raw["label"].clone().float(), "image": raw["image"].clone()},
+                          from_dataloader=True)
+    S = o.crop_size
+    style = model(dict(data), "encode_only")
+    assert tuple(style.shape) == (2, 19, 128)
+
+    def demo(b, z):
+        d = {"input_semantics": data["input_semantics"][b:b + 1], "image_lr": data["image_lr"][b:b + 1],
+             "encoded_style": z[None]}
+        return model(d, "demo")["fake_image"][0]
+
+    out = model(dict(data), "inference_interpolation")
+    assert tuple(out["fake_image"].shape) == (2, 3, S, 3 * S)
+    for b in range(2):
+        for i, step in enumerate(np.linspace(-0.25, 0.25, num=3)):
+            z = style[b].clone()
+            z[[1, 2, 5]] = (z[[1, 2, 5]] + float(step)).clamp(-1, 1)
+            got = out["fake_image"][b, :, :, i * S:(i + 1) * S]
+            assert (got - demo(b, z)).abs().max().item() < 2e-5
+    # the middle variant (delta = 0) is the plain inference result
+    plain = model(dict(data), "inference")["fake_image"]
+    assert (out["fake_image"][:, :, :, S:2 * S] - plain).abs().max().item() < 2e-5
+
+    d2 = dict(data)
+    d2["style_from"], d2["style_to"] = style, style.flip(0)
+    out = model(d2, "inference_interpolation_style")
+    for b in range(2):
+        z = 0.5 * style[b] + 0.5 * style[1 - b]
+        assert (out["fake_image"][b, :, :, S:2 * S] - demo(b, z)).abs().max().item() < 2e-5
+
+    out = model(dict(data), "inference_reference")
+    assert tuple(out["fake_image"].shape) == (2, 3, S, 2 * S)
+    with torch.no_grad():  # this mode encodes the HR image (encoder_full), sr_model.py:386-388
+        full, _ = model.encode_style(input_semantics=data["input_semantics"], full_image=data["image_hr"],
+                                     no_noise=True, encode_full=True)
+    z = full[0].clone()
+    z[[1, 2, 5]] = full[1, [1, 2, 5]]
+    assert (out["fake_image"][0, :, :, S:] - demo(0, z)).abs().max().item() < 2e-5
+
+    opt.dont_merge_fake = True
+    out = model(dict(data), "inference_multi_modal")
+    assert tuple(out["fake_image"].shape) == (2, 3, 3, S, S) and len(out["style"]) == 2
+    assert (out["fake_image"][1, 2] - demo(1, out["style"][1][2])).abs().max().item() < 2e-5
+    with pytest.raises(NotImplementedError):
+        model(dict(data), "inference_replace_semantics")
