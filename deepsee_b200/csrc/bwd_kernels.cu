@@ -125,10 +125,13 @@ __global__ void modulate_bwd_saved_kernel(const float* __restrict__ x, int x_ups
         for (int i = pl; i < GP_PIX; i += lanes) {
             const int64_t pix = p0 + i;
             if (pix >= npix) break;
-            const int xx = (int)(pix % W);
-            const int yy = (int)((pix / W) % H);
-            const int b = (int)(pix / ((int64_t)W * H));
-            const size_t xp = ((size_t)b * Hx + (yy >> x_ups)) * Wx + (xx >> x_ups);
+            size_t xp = (size_t)pix;
+            if (x_ups) {  // 32-bit coordinates (npix < 2^31 is checked by the host wrapper)
+                const uint32_t pu = (uint32_t)pix;
+                const uint32_t xx = pu % (uint32_t)W, t2 = pu / (uint32_t)W;
+                const uint32_t yy = t2 % (uint32_t)H, b = t2 / (uint32_t)H;
+                xp = ((size_t)b * Hx + (yy >> 1)) * Wx + (xx >> 1);
+            }
             float4 xv = __ldg(reinterpret_cast<const float4*>(x + xp * C) + g);
             if (has_noise) {
                 const float4 nv = load_noise4(noise, noise_seed, (size_t)pix * C + g * 4);
@@ -251,12 +254,24 @@ __global__ void __launch_bounds__(256, HAS_NOISE ? 3 : 4) bn_bwd_kernel(const fl
         constexpr bool has_noise = HAS_NOISE;
         if (has_noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
         const int iend = (int)(npix - p0 < BB_PIX ? npix - p0 : BB_PIX);
+        // (b, yy, xx) of this lane's first pixel by 32-bit division, then advanced incrementally:
+        // 64-bit div/mod per pixel cost more issue slots than the memory traffic they index
+        const uint32_t pix0 = (uint32_t)(p0 + pl);
+        int xx = (int)(pix0 % (uint32_t)Wx);
+        int yy = (int)((pix0 / (uint32_t)Wx) % (uint32_t)Hx);
+        int b = (int)(pix0 / ((uint32_t)Wx * (uint32_t)Hx));
+        xx -= lanes;
 #pragma unroll(HAS_NOISE ? 1 : 2)
         for (int i = pl; i < iend; i += lanes) {
             const int64_t pix = p0 + i;
-            const int xx = (int)(pix % Wx);
-            const int yy = (int)((pix / Wx) % Hx);
-            const int b = (int)(pix / ((int64_t)Wx * Hx));
+            xx += lanes;
+            while (xx >= Wx) {
+                xx -= Wx;
+                if (++yy == Hx) {
+                    yy = 0;
+                    ++b;
+                }
+            }
             const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)pix * C) + g);
             float4 acc = make_float4(0, 0, 0, 0);
             for (int sy = 0; sy < f; ++sy)
@@ -324,9 +339,11 @@ __global__ void actv_grad_prep_kernel(const float* __restrict__ dsrc, int ld, in
         for (int i = pl; i < GP_PIX; i += lanes) {
             const int64_t pix = p0 + i;
             if (pix >= npix) break;
-            const int xl = (int)(pix % Wl);
-            const int yl = (int)((pix / Wl) % Hl);
-            const int b = (int)(pix / ((int64_t)Wl * Hl));
+            const uint32_t pu = (uint32_t)pix;  // 32-bit coordinates (host wrapper checks npix < 2^31)
+            const int xl = (int)(pu % (uint32_t)Wl);
+            const uint32_t t2 = pu / (uint32_t)Wl;
+            const int yl = (int)(t2 % (uint32_t)Hl);
+            const int b = (int)(t2 / (uint32_t)Hl);
             const size_t fp0 = ((size_t)b * H + yl * f) * W + xl * f;
             const uint2 av = __ldg(reinterpret_cast<const uint2*>(actv_hi + fp0 * nh) + g);
             float a[4] = {0, 0, 0, 0};
@@ -594,6 +611,7 @@ extern "C" int dsee_spade_modulate_bwd_saved(const float* x, int x_ups, const fl
     int rc = require_sm100();
     if (rc) return rc;
     const int64_t npix = (int64_t)B * H * W;
+    DSEE_CHECK_ARG(npix < ((int64_t)1 << 31), "more than 2^31 pixels");
     const int lanes = 256 / (C / 4);
     const size_t sm = (size_t)lanes * C * 4 * sizeof(float);
     modulate_bwd_saved_kernel<<<cdivb(npix, GP_PIX), 256, sm, (cudaStream_t)stream>>>(
@@ -624,6 +642,7 @@ extern "C" int dsee_bn_bwd(const float* dxhat, const float* x, int x_ups, const 
     DSEE_CHECK_ARG(C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "C must divide 1024 (got %d)", C);
     DSEE_CHECK_ARG((noise != nullptr || noise_seed != 0) == (noise_w != nullptr), "noise/noise_w mismatch");
     DSEE_CHECK_ARG(!nw_partial || noise_w, "nw_partial needs noise");
+    DSEE_CHECK_ARG((int64_t)B * Hx * Wx < ((int64_t)1 << 31), "more than 2^31 pixels");
     int rc = require_sm100();
     if (rc) return rc;
     const int lanes = 256 / (C / 4);
@@ -646,6 +665,7 @@ extern "C" int dsee_actv_grad_prep(const float* dsrc, int ld, int coff, const vo
     int rc = require_sm100();
     if (rc) return rc;
     const int64_t npix = (int64_t)B * Hl * Wl;
+    DSEE_CHECK_ARG(npix < ((int64_t)1 << 31), "more than 2^31 pixels");
     const int lanes = 256 / (nh / 4);
     actv_grad_prep_kernel<<<cdivb(npix, GP_PIX), 256, (size_t)lanes * nh * sizeof(float),
                             (cudaStream_t)stream>>>(dsrc, ld, coff, (const __half*)actv_hi, dsrc_amax,

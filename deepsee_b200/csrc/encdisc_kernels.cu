@@ -204,9 +204,9 @@ __global__ void instnorm_apply_kernel(const float* __restrict__ x, const float* 
                                       int64_t n4, int HW, int C, int act, float slope) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
-    const int cq = C >> 2;
-    const int q = (int)(i % cq);
-    const int b = (int)(i / ((int64_t)cq * HW));
+    const uint32_t cq = (uint32_t)C >> 2;
+    const int q = (int)((uint32_t)i % cq);  // n4 < 2^31 (host wrapper)
+    const int b = (int)((uint32_t)i / (cq * (uint32_t)HW));
     float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
     const float4 m = __ldg(reinterpret_cast<const float4*>(mean + (size_t)b * C) + q);
     const float4 r = __ldg(reinterpret_cast<const float4*>(rstd + (size_t)b * C) + q);
@@ -367,6 +367,7 @@ extern "C" int dsee_instance_norm_fwd(const float* x, float* out, float* mean, f
                                       void* stream) {
     DSEE_CHECK_ARG(x && out && mean && rstd && workspace && B > 0 && HW > 0 && C > 0 && C % 4 == 0,
                    "bad argument");
+    DSEE_CHECK_ARG((int64_t)B * HW * C < ((int64_t)1 << 31), "more than 2^31 elements");
     int rc = require_sm100();
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -704,8 +705,8 @@ __global__ void instnorm_bwd_apply_kernel(const float* __restrict__ x, const flo
                                           int64_t n, int HW, int C, int act, float slope) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int c = (int)(i % C);
-    const int b = (int)(i / ((int64_t)C * HW));
+    const int c = (int)((uint32_t)i % (uint32_t)C);  // n < 2^31 (host wrapper)
+    const int b = (int)((uint32_t)i / ((uint32_t)C * (uint32_t)HW));
     const size_t bc = (size_t)b * C + c;
     const float r = rstd[bc];
     const float y = (x[i] - mean[bc]) * r;
@@ -856,6 +857,7 @@ extern "C" int dsee_instance_norm_bwd(const float* x, const float* dout, const f
                        C % 4 == 0,
                    "bad argument");
     DSEE_CHECK_ARG(act >= 0 && act <= 2, "act must be 0, 1 or 2");
+    DSEE_CHECK_ARG((int64_t)B * HW * C < ((int64_t)1 << 31), "more than 2^31 elements");
     int rc = require_sm100();
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;

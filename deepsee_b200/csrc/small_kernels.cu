@@ -85,15 +85,18 @@ __global__ void shared_mlp_kernel(const uint8_t* __restrict__ labels, const floa
                                   const float* __restrict__ bias, __half* __restrict__ out_hi,
                                   __half* __restrict__ out_lo, int B, int Hl, int Wl, int ups, int L,
                                   int nh) {
-    const int groups = nh >> 2;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // 32-bit index arithmetic (the host wrapper checks the element count): five 64-bit div/mod per
+    // thread cost more than the 8 bytes the thread produces
+    const uint32_t groups = (uint32_t)nh >> 2;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int H = Hl << ups, W = Wl << ups;
-    if (i >= (int64_t)B * H * W * groups) return;
-    int g = (int)(i % groups);
-    int64_t pix = i / groups;
-    int x = (int)(pix % W);
-    int y = (int)((pix / W) % H);
-    int b = (int)(pix / ((int64_t)W * H));
+    if (i >= (uint32_t)B * H * W * groups) return;
+    const int g = (int)(i % groups);
+    const uint32_t pix = i / groups;
+    const int x = (int)(pix % (uint32_t)W);
+    const uint32_t t2 = pix / (uint32_t)W;
+    const int y = (int)(t2 % (uint32_t)H);
+    const int b = (int)(t2 / (uint32_t)H);
     const int yl = y >> ups, xl = x >> ups;
     const uint8_t* lb = labels + (size_t)b * Hl * Wl;
     float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + g);
@@ -121,12 +124,12 @@ __global__ void shared_mlp_kernel(const uint8_t* __restrict__ labels, const floa
 __global__ void style_gather_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ style,
                                     __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B,
                                     int HW, int L, int d) {
-    const int groups = d >> 2;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)B * HW * groups) return;
-    int g = (int)(i % groups);
-    int64_t pix = i / groups;
-    int b = (int)(pix / HW);
+    const uint32_t groups = (uint32_t)d >> 2;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit: checked by the host wrapper
+    if (i >= (uint32_t)B * HW * groups) return;
+    const int g = (int)(i % groups);
+    const uint32_t pix = i / groups;
+    const int b = (int)(pix / (uint32_t)HW);
     int l = labels[pix];
     if (l >= L) l = L - 1;
     float4 s = __ldg(reinterpret_cast<const float4*>(style + ((size_t)b * L + l) * d) + g);
@@ -310,10 +313,13 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int x_ups, const fl
 #pragma unroll(HAS_NOISE ? 1 : 4)
         for (int i = pl; i < iend; i += pix_lanes) {
             int64_t pix = p0 + i;
-            int xx = (int)(pix % W);
-            int yy = (int)((pix / W) % H);
-            int b = (int)(pix / ((int64_t)W * H));
-            size_t xp = ((size_t)b * Hx + (yy >> x_ups)) * Wx + (xx >> x_ups);
+            size_t xp = (size_t)pix;
+            if (x_ups) {  // 32-bit coordinates: 64-bit div/mod per pixel would dominate the issue slots
+                const uint32_t pu = (uint32_t)pix;
+                const uint32_t xx = pu % (uint32_t)W, t2 = pu / (uint32_t)W;
+                const uint32_t yy = t2 % (uint32_t)H, b = t2 / (uint32_t)H;
+                xp = ((size_t)b * Hx + (yy >> 1)) * Wx + (xx >> 1);
+            }
             float4 v = __ldg(reinterpret_cast<const float4*>(x + xp * C) + g);
             if (has_noise) {
                 float4 nv = load_noise4(noise, noise_seed, (size_t)pix * C + g * 4);
@@ -605,6 +611,7 @@ extern "C" int dsee_shared_mlp_fwd(const uint8_t* labels, const float* table, co
     int rc = require_sm100();
     if (rc) return rc;
     int64_t n = (int64_t)B * (Hl << ups) * (Wl << ups) * (nh / 4);
+    DSEE_CHECK_ARG(n < ((int64_t)1 << 31), "more than 2^31 output quads");
     shared_mlp_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
         labels, table, bias, (__half*)out_hi, (__half*)out_lo, B, Hl, Wl, ups, L, nh);
     LAUNCH_END();
@@ -617,6 +624,7 @@ extern "C" int dsee_style_gather_fwd(const uint8_t* labels, const float* style, 
     int rc = require_sm100();
     if (rc) return rc;
     int64_t n = (int64_t)B * H * W * (d / 4);
+    DSEE_CHECK_ARG(n < ((int64_t)1 << 31), "more than 2^31 output quads");
     style_gather_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
         labels, style, (__half*)out_hi, (__half*)out_lo, B, H * W, L, d);
     LAUNCH_END();
@@ -711,6 +719,7 @@ extern "C" int dsee_bn_stats(const float* x, int x_ups, const float* noise, unsi
     DSEE_CHECK_ARG(x && C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0,
                    "C must divide 1024 (got %d)", C);
     DSEE_CHECK_ARG((noise != nullptr || noise_seed != 0) == (noise_w != nullptr), "noise/noise_w mismatch");
+    DSEE_CHECK_ARG(npix < ((int64_t)1 << 31), "more than 2^31 pixels");
     int rc = require_sm100();
     if (rc) return rc;
     int pix_lanes = 256 / (C / 4);
