@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cprofile", default=None,
+                    help="write a cProfile table (main thread: forward passes, optimizers) of 3 extra steps to this file")
     ap.add_argument("--torch-profile", default=None,
                     help="write a torch.profiler (CUPTI) kernel table of 2 extra steps to this file")
     args = ap.parse_args()
@@ -247,6 +249,20 @@ def main():
             f.write("2 steps under the profiler: %.1f ms wall\n" % (wall * 1000))
             f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=70,
                                               max_name_column_width=70))
+    if args.cprofile and rank == 0:
+        import cProfile
+        import io
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(3):
+            iteration(dev)
+        torch.cuda.synchronize()
+        pr.disable()
+        buf = io.StringIO()
+        pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(70)
+        pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(45)
+        open(args.cprofile, "w").write(buf.getvalue())
     e2e = None
     if not args.no_e2e:
         for _ in range(2):
