@@ -46,47 +46,44 @@ def peaks():
     return 1400.0, 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
-        self.stop_flag = False
-
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+class ClockSampler:
+    """SM clocks / throttle reasons during the timed region (B200_PROFILING.md's clocks line): ONE
+    `nvidia-smi -lms 200` process running in the background - no per-sample process spawn next to
+    the launching thread."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.stop_flag = False
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def result(self):
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        samples = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+                samples = [[f.strip() for f in line.split(",")] for line in out.splitlines() if line.strip()]
+            except Exception:
+                pass
+        sm = sorted(int(s_[0]) for s_ in samples if s_[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names)
-                   if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
-        mx = max([int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()] or [0])
+                   if any(len(s_) > 2 + i and s_[2 + i].lower().startswith("active") for s_ in samples)]
+        mx = max([int(s_[1]) for s_ in samples if len(s_) > 1 and s_[1].isdigit()] or [0])
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
                 "reasons": reasons, "samples": len(sm)}
-
-
-def build_opt(o):
-    from deepsee_b200.options.configurations import make_opt
-    d = dict(o)
-    name = d.pop("name")
-    opt = make_opt(None, **d)
-    opt.name = name
-    return opt
 
 
 def cpu_train_iteration_timer(cfg, threads):
@@ -159,10 +156,12 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from oracle import deepsee_oracle as O      # synthetic inputs / seeded weights / CPU baseline only
+    # this arm touches the product only; oracle/ is imported by the cpu_baseline leg alone (below)
     from deepsee_b200 import _lib, ops, parallel
     from deepsee_b200.config import config
     from deepsee_b200.managers.trainer_manager import TrainerManager
+    from deepsee_b200.options.configurations import make_opt
+    from deepsee_b200.util.synthetic import synthetic_batch, settle_spectral_norm
 
     # Default precision of the measured step: 1 pass = fp16 operands with fp32 accumulation, the
     # TF32 class (10-bit mantissa) that stock PyTorch/cuDNN runs the reference's convs in on this GPU;
@@ -177,16 +176,22 @@ def main():
     parallel.init_from_env()
     cfg = CONFIGS[args.config]
     b = cfg["batch"]
-    o = O.make_opt(cfg["name"], is_train=True)
-    mgr = TrainerManager(build_opt(o))
+    torch.manual_seed(0)                         # same random-init weights on every rank
+    o = make_opt(cfg["name"], isTrain=True, gpu_ids=[local], batchSize=b)
+    mgr = TrainerManager(o)                      # random-init weights of the named architecture
     model = mgr.sr_model
-    model.netSR.load_state_dict(O.make_generator_state(o, 0), strict=True)
-    model.netE.load_state_dict(O.make_encoder_state(o, 1), strict=True)
-    model.netD.load_state_dict(O.make_discriminator_state(o, 2), strict=True)
+    for net in (model.netSR, model.netE, model.netD):
+        settle_spectral_norm(net)
+    with torch.no_grad():                        # NoiseInjection.weight is zero-initialised (normalization.py:297)
+        for n_, p_ in model.netSR.named_parameters():
+            if ".noise_" in n_:
+                p_.fill_(0.1)
+    parallel.broadcast_module(model)
     train = args.mode == "train"
     model.train(train)
+    torch.manual_seed(1234 + rank)               # NoiseInjection seeds differ per rank
 
-    raw = O.synthetic_batch(o, b, seed=1234 + rank)
+    raw = synthetic_batch(o, b, seed=1234 + rank)
     host = {k: (v.float() if "label" in k else v).pin_memory() for k, v in raw.items()}
     dev = {k: v.cuda() for k, v in host.items()}
     torch.cuda.synchronize()
@@ -319,7 +324,11 @@ def main():
                                 "tflops": v[2] / (v[1] / 1000.0) / 1e12} for t, v in sorted(ksum.items())},
         "whole_step": {"algorithmic_tflops_per_gpu": value / world * flops_per_img / 1e12,
                        "frac_of_peak": value / world * flops_per_img / 1e12 / sust},
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (K2, 512->512
+        # at 256x256, batch 8) from the committed `ncu --set full` capture; algorithmic = fp16 activation
+        # planes + fp32 shortcut + fp32 output + weights = 2.42 GB
+        "traffic": 2.73e9 if (args.config in ("c2", "c3") and train) else None,
+        "traffic_source": "profiles/r1_kernels_ncu_full_selected.csv (conv3x3_tc_kernel<0>, first row)",
     }
     line = {
         "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
