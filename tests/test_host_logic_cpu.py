@@ -1,0 +1,92 @@
+"""CPU: host-side logic that needs no GPU - the synthetic workload helpers, the rule that the product
+(and bench.py's own arm) never touches oracle/, option presets, and the SRModel mode table."""
+import ast
+import os
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_synthetic_batch_shapes_and_determinism():
+    from deepsee_b200.options.configurations import make_opt
+    from deepsee_b200.util.synthetic import synthetic_batch
+    o = make_opt("8x_independent_256x256")
+    a, b = synthetic_batch(o, 3, seed=7), synthetic_batch(o, 3, seed=7)
+    assert set(a) == {"image", "label"}
+    assert tuple(a["image"].shape) == (3, 3, 256, 256) and a["image"].dtype == torch.float32
+    assert tuple(a["label"].shape) == (3, 1, 256, 256) and a["label"].dtype == torch.int64
+    assert torch.equal(a["image"], b["image"]) and torch.equal(a["label"], b["label"])
+    assert float(a["image"].min()) >= -1 and float(a["image"].max()) <= 1
+    assert int(a["label"].min()) >= 0 and int(a["label"].max()) < o.label_nc
+    # blocky maps are constant on the 16 x 16 grid cells
+    cell = a["label"][:, :, :16, :16]
+    assert (cell == cell[:, :, :1, :1]).all()
+    iid = synthetic_batch(o, 1, seed=7, blocky=False)["label"]
+    assert iid[0, 0, :16, :16].unique().numel() > 4
+    g = synthetic_batch(make_opt("32x_guided_512x512"), 1)
+    assert set(g) == {"image", "label", "guiding_image", "guiding_label"}
+    assert tuple(g["guiding_label"].shape) == (1, 1, 512, 512)
+
+
+def test_settle_spectral_norm_converges_to_the_largest_singular_value():
+    from deepsee_b200.util.synthetic import settle_spectral_norm
+    torch.manual_seed(3)
+    conv = torch.nn.utils.spectral_norm(torch.nn.Conv2d(6, 10, 3))
+    net = torch.nn.Sequential(conv, torch.nn.Conv2d(10, 4, 1))
+    assert settle_spectral_norm(net, iters=200) == 1
+    w = conv.weight_orig.detach().flatten(1)
+    sigma = torch.dot(conv.weight_u, torch.mv(w, conv.weight_v))
+    assert abs(float(sigma) - float(torch.linalg.matrix_norm(w, 2))) < 1e-4 * float(sigma)
+
+
+def _oracle_imports(path):
+    """(lineno, enclosing function or None) of every import of the oracle package in a source file."""
+    tree = ast.parse(open(path).read())
+    found = []
+
+    def visit(node, fn):
+        for ch in ast.iter_child_nodes(node):
+            f = ch.name if isinstance(ch, (ast.FunctionDef, ast.AsyncFunctionDef)) else fn
+            if isinstance(ch, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in ch.names):
+                found.append((ch.lineno, fn))
+            if isinstance(ch, ast.ImportFrom) and (ch.module or "").split(".")[0] == "oracle":
+                found.append((ch.lineno, fn))
+            visit(ch, f)
+    visit(tree, None)
+    return found
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "deepsee_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                assert _oracle_imports(os.path.join(dirpath, f)) == [], f
+    # bench.py: only the CPU-baseline leg (which also serves --impl reference) may use it
+    where = _oracle_imports(os.path.join(ROOT, "bench.py"))
+    assert where and all(fn == "cpu_train_iteration_timer" for _, fn in where), where
+
+
+def test_option_presets_match_the_reference_names():
+    from deepsee_b200.options.configurations import make_opt
+    o = make_opt("8x_independent_256x256")
+    assert (o.start_size, o.crop_size, o.add_noise, o.netE, o.guiding_style_image) == (32, 256, True, "combinedstyle", False)
+    o = make_opt("32x_guided_512x512")
+    assert (o.start_size, o.crop_size, o.add_noise, o.netE, o.guiding_style_image) == (16, 512, False, "fullstyle", True)
+    o = make_opt("8x_guided_128x128", ngf=8)
+    assert (o.start_size, o.crop_size, o.dataset, o.ngf) == (16, 128, "celeba", 8)
+    with pytest.raises(ValueError):
+        make_opt("4x_something")
+
+
+def test_srmodel_mode_table_covers_the_reference_modes():
+    """Every mode string of the reference's SRModel.forward (sr_model.py:76-444) is dispatched."""
+    src = open(os.path.join(ROOT, "deepsee_b200", "deepsee_models", "sr_model.py")).read()
+    for mode in ("generator", "discriminator", "inference", "encode_only", "demo", "baseline",
+                 "inference_noise", "inference_multi_modal", "inference_replace_semantics",
+                 "inference_reference_semantics", "inference_interpolation", "inference_interpolation_style",
+                 "inference_particular_combined", "inference_particular_full", "inference_reference",
+                 "inference_reference_interpolation"):
+        assert repr(mode) in src or '"%s"' % mode in src, mode
