@@ -271,7 +271,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int q = warp & 3;  // TMEM lane quarter this warp may touch
         const int eh = (warp - 2) >> 2;  // which of the quarter's two warps (chunk parity)
         constexpr int ESTEP = EPI_WARPS / 4;

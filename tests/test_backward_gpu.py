@@ -151,6 +151,25 @@ def test_generator_backward_vs_oracle(case, passes):
     assert checked > 50
 
 
+@pytest.mark.parametrize("save_gamma,fuse", [(True, False), (False, False)])
+def test_generator_backward_alternate_kernel_paths(save_gamma, fuse):
+    """The default backward runs backward-data and K1's backward as one kernel (saved G planes).  The
+    two other routes stay selectable and must agree with the oracle just as well: streaming K1
+    backward on the saved G planes (DSEE_FUSE_DGRAD_MODBWD=0) and the gamma-GEMM-recompute kernel
+    (DSEE_SAVE_GAMMA=0; explicit noise tensors, which is what this harness injects)."""
+    from deepsee_b200.config import config
+    old = (config.save_gamma, config.fuse_dgrad_modbwd)
+    config.save_gamma, config.fuse_dgrad_modbwd = save_gamma, fuse
+    try:
+        name, over = CASES["8x"]
+        fwd_err, worst, zrel, checked = _run_case(name, over, 3)
+    finally:
+        config.save_gamma, config.fuse_dgrad_modbwd = old
+    print("save_gamma=%s fuse=%s: worst param-grad rel err %.3e (%s); dz rel err %.3e" %
+          (save_gamma, fuse, worst[1], worst[0], zrel))
+    assert worst[1] < 2e-3 and zrel < 2e-3 and checked > 50
+
+
 def test_generator_backward_eval_mode():
     """Gradients with running statistics (eval-mode batch norm, no noise)."""
     name, over = CASES["8x"]
