@@ -154,13 +154,13 @@ def load():
                                           vp, vp, vp, vp],
         "dsee_noise_fill": [u64, vp, i64, vp],
         "dsee_grad_prep_blocks": [i64],
-        "dsee_grad_prep": [vp, vp, vp, vp, vp, vp, u64, u64, i64, i, vp, vp],
+        "dsee_grad_prep": [vp, vp, vp, vp, vp, vp, u64, u64, i64, i, vp, vp, vp],
         "dsee_reduce_partials": [vp, i, i, i, f, vp, vp],
         "dsee_conv3x3_wgrad": [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp, i, vp],
         "dsee_conv3x3_wgrad2": [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i), i, i, i, i, i, i,
                                 vp, vp, i, vp],
         "dsee_bn_bwd_blocks": [i, i, i],
-        "dsee_bn_bwd": [vp, vp, i, vp, u64, vp, vp, vp, vp, f, vp, i, i, i, i, vp, vp, vp],
+        "dsee_bn_bwd": [vp, vp, i, vp, u64, vp, vp, vp, vp, f, vp, i, i, i, i, vp, vp, i, vp, vp],
         "dsee_actv_grad_prep": [vp, i, i, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp],
         "dsee_onehot_planes": [vp, vp, i64, i, vp],
         "dsee_shared_mlp_bwd_blocks": [i, i, i],

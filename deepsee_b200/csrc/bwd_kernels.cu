@@ -34,10 +34,16 @@ __global__ void grad_prep_kernel(const float* __restrict__ dy, __half* __restric
                                  __half* __restrict__ lo, float* __restrict__ inv_scale,
                                  const float* __restrict__ n0, const float* __restrict__ n1,
                                  unsigned long long seed0, unsigned long long seed1, int64_t npix, int C,
-                                 float* __restrict__ partial, int nq) {
+                                 float* __restrict__ partial, int nq, const float* __restrict__ amax_in) {
     extern __shared__ float red[];  // [lanes][C][nq]
-    const float scale = pow2_scale_for(inv_scale[1], 14);
-    if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[0] = 1.f / scale;
+    // max|dY|: from the producer (amax_in) or from grad_amax_kernel (inv_scale[1]); inv_scale[1] is
+    // only read by kernels launched after this one when it is written here
+    const float amax = amax_in ? __ldg(amax_in) : inv_scale[1];
+    const float scale = pow2_scale_for(amax, 14);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        inv_scale[0] = 1.f / scale;
+        if (amax_in) inv_scale[1] = amax;
+    }
     const int cg = C >> 2;
     const int lanes = blockDim.x / cg;
     const int g = threadIdx.x % cg, pl = threadIdx.x / cg;
@@ -233,7 +239,8 @@ __global__ void __launch_bounds__(256, HAS_NOISE ? 3 : 4) bn_bwd_kernel(const fl
                               const float* __restrict__ sums /*[2][C]: sum dxhat, sum dxhat*xhat*/,
                               float inv_count, const float* __restrict__ dskip, int B, int Hx,
                               int Wx, int C, float* __restrict__ dx,
-                              float* __restrict__ nw_partial) {
+                              float* __restrict__ nw_partial, int nw_with_skip,
+                              float* __restrict__ amax_out) {
     extern __shared__ float red[];  // [lanes][C]
     const int cg = C >> 2;
     const int lanes = blockDim.x / cg;
@@ -243,6 +250,7 @@ __global__ void __launch_bounds__(256, HAS_NOISE ? 3 : 4) bn_bwd_kernel(const fl
     const int H = Hx << ups, W = Wx << ups;
     const int f = 1 << ups;
     float nacc[4] = {0, 0, 0, 0};
+    float tmax = 0.f;
     if (pl < lanes) {
         const float4 scv = __ldg(reinterpret_cast<const float4*>(sc) + g);
         const float4 shv = __ldg(reinterpret_cast<const float4*>(sh) + g);
@@ -292,10 +300,12 @@ __global__ void __launch_bounds__(256, HAS_NOISE ? 3 : 4) bn_bwd_kernel(const fl
                     if (dskip) {
                         const float4 k = __ldg(reinterpret_cast<const float4*>(dskip + fp * C) + g);
                         acc.x += k.x; acc.y += k.y; acc.z += k.z; acc.w += k.w;
+                        if (nw_with_skip) { r.x += k.x; r.y += k.y; r.z += k.z; r.w += k.w; }
                     }
                     nacc[0] += r.x * nv.x; nacc[1] += r.y * nv.y; nacc[2] += r.z * nv.z; nacc[3] += r.w * nv.w;
                 }
             reinterpret_cast<float4*>(dx + (size_t)pix * C)[g] = acc;
+            tmax = fmaxf(tmax, fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w))));
         }
         if (nw_partial)
 #pragma unroll
@@ -308,6 +318,11 @@ __global__ void __launch_bounds__(256, HAS_NOISE ? 3 : 4) bn_bwd_kernel(const fl
             for (int l = 0; l < lanes; ++l) a += red[(size_t)l * C + c];
             nw_partial[(size_t)blockIdx.x * C + c] = a;
         }
+    }
+    if (amax_out) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        if ((threadIdx.x & 31) == 0 && tmax > 0.f && !isinf(tmax) && !isnan(tmax)) atomic_max_nonneg(amax_out, tmax);
     }
 }
 
@@ -571,7 +586,7 @@ extern "C" int dsee_grad_prep_blocks(int64_t npix) { return cdivb(npix, GP_PIX);
 extern "C" int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, float* inv_scale,
                               const float* noise0, const float* noise1, unsigned long long seed0,
                               unsigned long long seed1, int64_t npix, int C, float* partial,
-                              void* stream) {
+                              const float* amax_in, void* stream) {
     DSEE_CHECK_ARG(dy && out_hi && inv_scale && partial && npix > 0, "bad argument");
     DSEE_CHECK_ARG(C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "C must divide 1024 (got %d)", C);
     const bool has0 = noise0 || seed0, has1 = noise1 || seed1;
@@ -582,15 +597,17 @@ extern "C" int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, float
     const int lanes = 256 / (C / 4);
     size_t sm = (size_t)lanes * C * nq * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-    DSEE_CUDA(cudaMemsetAsync(inv_scale, 0, 2 * sizeof(float), st));
-    const int64_t n4 = npix * C / 4;
-    int ablocks = cdivb(n4, 256 * 8);
-    if (ablocks > 148 * 8) ablocks = 148 * 8;
-    grad_amax_kernel<<<ablocks, 256, 0, st>>>(dy, n4, inv_scale + 1);
-    count_launch();
+    if (!amax_in) {
+        DSEE_CUDA(cudaMemsetAsync(inv_scale, 0, 2 * sizeof(float), st));
+        const int64_t n4 = npix * C / 4;
+        int ablocks = cdivb(n4, 256 * 8);
+        if (ablocks > 148 * 8) ablocks = 148 * 8;
+        grad_amax_kernel<<<ablocks, 256, 0, st>>>(dy, n4, inv_scale + 1);
+        count_launch();
+    }
     grad_prep_kernel<<<cdivb(npix, GP_PIX), 256, sm, st>>>(dy, (__half*)out_hi, (__half*)out_lo,
                                                            inv_scale, noise0, noise1, seed0, seed1, npix,
-                                                           C, partial, nq);
+                                                           C, partial, nq, amax_in);
     LAUNCH_END();
 }
 
@@ -637,7 +654,8 @@ extern "C" int dsee_bn_bwd(const float* dxhat, const float* x, int x_ups, const 
                            unsigned long long noise_seed, const float* noise_w, const float* bn_scale,
                            const float* bn_shift,
                            const float* sums, float inv_count, const float* dskip, int B, int Hx,
-                           int Wx, int C, float* dx, float* nw_partial, void* stream) {
+                           int Wx, int C, float* dx, float* nw_partial, int noise_grad_with_skip,
+                           float* amax_out, void* stream) {
     DSEE_CHECK_ARG(dxhat && x && bn_scale && bn_shift && sums && dx, "NULL pointer");
     DSEE_CHECK_ARG(C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "C must divide 1024 (got %d)", C);
     DSEE_CHECK_ARG((noise != nullptr || noise_seed != 0) == (noise_w != nullptr), "noise/noise_w mismatch");
@@ -647,10 +665,12 @@ extern "C" int dsee_bn_bwd(const float* dxhat, const float* x, int x_ups, const 
     if (rc) return rc;
     const int lanes = 256 / (C / 4);
     size_t sm = nw_partial ? (size_t)lanes * C * sizeof(float) : 0;
+    DSEE_CHECK_ARG(!noise_grad_with_skip || (dskip && nw_partial), "noise_grad_with_skip needs dskip and nw_partial");
+    if (amax_out) DSEE_CUDA(cudaMemsetAsync(amax_out, 0, sizeof(float), (cudaStream_t)stream));
     auto kern = noise_w ? bn_bwd_kernel<true> : bn_bwd_kernel<false>;
     kern<<<dsee_bn_bwd_blocks(B, Hx, Wx), 256, sm, (cudaStream_t)stream>>>(
         dxhat, x, x_ups, noise, noise_seed, noise_w, bn_scale, bn_shift, sums, inv_count, dskip, B, Hx, Wx,
-        C, dx, nw_partial);
+        C, dx, nw_partial, noise_grad_with_skip, amax_out);
     LAUNCH_END();
 }
 

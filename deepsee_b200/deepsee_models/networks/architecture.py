@@ -230,10 +230,11 @@ class _ResBlockFn(torch.autograd.Function):
         x, dx1, a0, a1, st0, st1 = s['x'], s['dx1'], s['a0'], s['a1'], s['st0'], s['st1']
 
         # ---- conv_1 + shortcut: out = conv(a1, W1) + b1 + x_up + w_in*n_in + w_skip*n_skip ------
-        g1, sums = ops.grad_prep(dout, n_in, n_skip, want_lo=want_lo)
+        # (d noise_in.weight of the shortcut rides along in norm_0's bn_bwd below, which regenerates
+        # n_in anyway; max|dout| comes with the tensor when the next block's bn_bwd produced it)
+        g1, sums = ops.grad_prep(dout, n_skip, None, want_lo=want_lo, amax=getattr(dout, "_dsee_amax", None))
         db1 = sums[0]
-        dnw_in = sums[1] if noisy else None
-        dnw_skip = sums[2] if noisy else None
+        dnw_skip = sums[1] if noisy else None
         ss = _SideStream()
         dW1 = ss.run(lambda: ops.conv3x3_wgrad(g1, a1, passes=passes), g1, a1)
         # ---- backward-data of conv_1 + norm_1 --------------------------------------------------
@@ -242,10 +243,10 @@ class _ResBlockFn(torch.autograd.Function):
         del g1
         dgb1, dbb1 = nsums[2], nsums[3]
         nsums = _sync_bwd_sums(nsums, st1)
-        ddx1, _ = ops.bn_bwd(dxhat, dx1, 0, st1.sc, st1.sh, nsums, st1.inv_count)
+        ddx1, _, amax1 = ops.bn_bwd(dxhat, dx1, 0, st1.sc, st1.sh, nsums, st1.inv_count, want_amax=True)
         del dxhat
         # ---- conv_0: dx1 = conv(a0, W0) + b0 + w_mid*n_mid --------------------------------------
-        g0, sums = ops.grad_prep(ddx1, n_mid, None, want_lo=want_lo)
+        g0, sums = ops.grad_prep(ddx1, n_mid, None, want_lo=want_lo, amax=amax1)
         del ddx1
         db0 = sums[0]
         dnw_mid = sums[1] if noisy else None
@@ -257,10 +258,12 @@ class _ResBlockFn(torch.autograd.Function):
         del g0
         dgb0, dbb0 = nsums[2], nsums[3]
         nsums = _sync_bwd_sums(nsums, st0)
-        dx, dnw_in_bn = ops.bn_bwd(dxhat, x, ups, st0.sc, st0.sh, nsums, st0.inv_count, noise=n_in,
-                                   noise_w=nw_in, dskip=dout)
-        if noisy:
-            dnw_in = dnw_in + dnw_in_bn
+        dx, dnw_in, dx_amax = ops.bn_bwd(dxhat, x, ups, st0.sc, st0.sh, nsums, st0.inv_count, noise=n_in,
+                                         noise_w=nw_in, dskip=dout, noise_grad_with_skip=noisy,
+                                         want_amax=True)
+        # the previous block's backward receives this very tensor as its `dout` (a block output has one
+        # consumer); if autograd hands over a different tensor the attribute is simply absent
+        dx._dsee_amax = dx_amax
         dstyle = dstyle0
         if dstyle1 is not None:
             dstyle = dstyle1 if dstyle is None else dstyle + dstyle1

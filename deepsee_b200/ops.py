@@ -376,9 +376,11 @@ def dgrad_modulate_bwd(dy, pwT, act_mask, g_planes, x, x_ups, bn_scale, bn_shift
 # ---------------------------------------------------------------------------------------------
 # generator backward
 # ---------------------------------------------------------------------------------------------
-def grad_prep(dy, noise0=None, noise1=None, want_lo=True):
+def grad_prep(dy, noise0=None, noise1=None, want_lo=True, amax=None):
     """dY fp32 NHWC -> (scaled fp16 GradPlanes, sums fp32 [nq,C]): sums[0] = sum dY (bias
-    gradient), sums[1+i] = sum dY*noise_i (NoiseInjection.weight gradients)."""
+    gradient), sums[1+i] = sum dY*noise_i (NoiseInjection.weight gradients).
+    amax: device scalar max|dY| when the producer already knows it (bn_bwd(want_amax=True));
+    otherwise it is computed here with one extra pass over dY."""
     _chk_cuda(dy, noise0, noise1)
     Cc = dy.shape[-1]
     npix = dy.numel() // Cc
@@ -391,7 +393,7 @@ def grad_prep(dy, noise0=None, noise1=None, want_lo=True):
     part = torch.empty((nb, Cc, nq), dtype=torch.float32, device=dy.device)
     (p0, s0), (p1, s1) = _noise(noise0), _noise(noise1)
     _lib.check(lib.dsee_grad_prep(_p(dy), _p(hi), _p(lo), _p(inv), p0, p1, s0, s1, npix, Cc, _p(part),
-                                  _stream()))
+                                  _p(amax), _stream()))
     return GradPlanes(hi, lo, inv), reduce_partials(part)
 
 
@@ -482,8 +484,10 @@ def spade_modulate_bwd(sources, pw_gamma, x, x_ups, bn_scale, bn_shift, gamma_bi
     return dxhat, GradPlanes(ghi, glo, ginv), reduce_partials(part)
 
 
-def bn_bwd(dxhat, x, x_ups, bn_scale, bn_shift, sums, inv_count, noise=None, noise_w=None, dskip=None):
-    """-> (dx fp32 NHWC at x's resolution, d noise_w [C] or None)."""
+def bn_bwd(dxhat, x, x_ups, bn_scale, bn_shift, sums, inv_count, noise=None, noise_w=None, dskip=None,
+           noise_grad_with_skip=False, want_amax=False):
+    """-> (dx fp32 NHWC at x's resolution, d noise_w [C] or None[, device scalar max|dx|]).
+    noise_grad_with_skip: d noise_w also collects sum(dskip * noise) (the shortcut's noise term)."""
     _chk_cuda(dxhat, x, bn_scale, bn_shift, sums, noise, noise_w, dskip)
     B, Hx, Wx, Cc = x.shape
     lib = _lib.load()
@@ -493,10 +497,12 @@ def bn_bwd(dxhat, x, x_ups, bn_scale, bn_shift, sums, inv_count, noise=None, noi
         nwp = torch.empty((lib.dsee_bn_bwd_blocks(B, Hx, Wx), Cc, 1), dtype=torch.float32,
                           device=x.device)
     nptr, nseed = _noise(noise)
+    amax = torch.empty(1, dtype=torch.float32, device=x.device) if want_amax else None
     _lib.check(lib.dsee_bn_bwd(_p(dxhat), _p(x), x_ups, nptr, nseed, _p(noise_w), _p(bn_scale),
                                _p(bn_shift), _p(sums), float(inv_count), _p(dskip), B, Hx, Wx, Cc,
-                               _p(dx), _p(nwp), _stream()))
-    return dx, (reduce_partials(nwp)[0] if nwp is not None else None)
+                               _p(dx), _p(nwp), int(bool(noise_grad_with_skip)), _p(amax), _stream()))
+    dnw = reduce_partials(nwp)[0] if nwp is not None else None
+    return (dx, dnw, amax) if want_amax else (dx, dnw)
 
 
 def shared_mlp_bwd(dsrc, coff, actv_hi, labels, ups, L):

@@ -317,11 +317,14 @@ int dsee_dgrad_modulate_bwd(const dsee_conv_operands* ops, const dsee_dgrad_modb
  * 2^-e, [1] is scratch), plus per-channel block partials of
  * (sum dY, sum dY*noise0, sum dY*noise1) = gradients of a conv bias (architecture.py:98,122) and of
  * NoiseInjection.weight (normalization.py:299-304).  partial fp32 [dsee_grad_prep_blocks()][C][nq],
- * nq = 1 + (noise0 or seed0 given) + (noise1 or seed1 given); reduce with dsee_reduce_partials. */
+ * nq = 1 + (noise0 or seed0 given) + (noise1 or seed1 given); reduce with dsee_reduce_partials.
+ * amax_in: NULL (max|dY| is computed here, one extra read of dY), or a device scalar holding it
+ * (dsee_bn_bwd.amax_out); either way inv_scale[1] holds max|dY| afterwards. */
 int dsee_grad_prep_blocks(int64_t npix);
 int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, float* inv_scale,
                    const float* noise0, const float* noise1, unsigned long long seed0,
-                   unsigned long long seed1, int64_t npix, int C, float* partial, void* stream);
+                   unsigned long long seed1, int64_t npix, int C, float* partial, const float* amax_in,
+                   void* stream);
 /* out[k][c] = scale * sum_s partial[s][c][k]  (double accumulation, fixed order). */
 int dsee_reduce_partials(const float* partial, int n, int C, int nq, float scale, float* out,
                          void* stream);
@@ -351,12 +354,16 @@ int dsee_conv3x3_wgrad2(const void* dy_hi, const void* dy_lo, const float* dy_in
  *   dx[b,y',x',c] = sum over the 2^ups x 2^ups block of (dxin + dskip)
  * sums fp32 [2][C] = (sum dxhat, sum dxhat*xhat) (pass inv_count = 0 for eval-mode statistics);
  * dskip fp32 NHWC [B,Hx<<ups,Wx<<ups,C] or NULL; nw_partial NULL or fp32
- * [dsee_bn_bwd_blocks()][C] = block partials of sum(dxin*noise) (gradient of noise_in.weight). */
+ * [dsee_bn_bwd_blocks()][C] = block partials of sum(dxin*noise) (gradient of noise_in.weight), or of
+ * sum((dxin+dskip)*noise) when noise_grad_with_skip != 0 (the shortcut of architecture.py:76-79 adds
+ * the same noise term, so its weight gradient can ride along instead of regenerating the noise in
+ * dsee_grad_prep).  amax_out: NULL, or a device scalar that receives max|dx| (what dsee_grad_prep
+ * would otherwise compute with a pass of its own over dx). */
 int dsee_bn_bwd_blocks(int B, int Hx, int Wx);
 int dsee_bn_bwd(const float* dxhat, const float* x, int x_ups, const float* noise,
                 unsigned long long noise_seed, const float* noise_w, const float* bn_scale, const float* bn_shift,
                 const float* sums, float inv_count, const float* dskip, int B, int Hx, int Wx, int C,
-                float* dx, float* nw_partial, void* stream);
+                float* dx, float* nw_partial, int noise_grad_with_skip, float* amax_out, void* stream);
 /* Backward of dsee_shared_mlp_fwd: gradient of the 9-tap table and bias.  dsrc fp32 NHWC with row
  * stride ld, the actv gradient in columns [coff, coff+nh).  partial fp32
  * [dsee_shared_mlp_bwd_blocks()][9*L+1][nh]; dtable_dbias fp32 [9*L+1][nh] (last row = bias). */

@@ -295,6 +295,19 @@ def test_bn_bwd_matches_autograd(ups, noisy):
     torch.testing.assert_close(_nchw(dx), x.grad, rtol=1e-3, atol=2e-4)
     if noisy:
         torch.testing.assert_close(dnw, nw.grad, rtol=1e-3, atol=2e-3)
+    # optional outputs: max|dx| for the gradient split that follows, and the shortcut's share of
+    # d noise_w (sum dskip * noise) folded into the same reduction
+    dx2, dnw2, amax = ops.bn_bwd(dxh, _nhwc(x.detach()), ups, sc, sh, sums, 1.0 / (B * H * W), noise=n_,
+                                 noise_w=nw.detach() if noisy else None, dskip=_nhwc(dskip),
+                                 noise_grad_with_skip=noisy, want_amax=True)
+    assert torch.equal(dx2, dx) and float(amax) == float(dx.abs().max())
+    if noisy:
+        extra = (dskip * noise).sum(dim=(0, 2, 3))
+        torch.testing.assert_close(dnw2, nw.grad + extra, rtol=1e-3, atol=4e-3)
+    gp_a, s_a = ops.grad_prep(dx)
+    gp_b, s_b = ops.grad_prep(dx, amax=amax)
+    assert torch.equal(gp_a.hi, gp_b.hi) and torch.equal(gp_a.lo, gp_b.lo)
+    assert torch.equal(gp_a.inv_scale, gp_b.inv_scale) and torch.equal(s_a, s_b)
 
 
 def test_stem_and_head_backward():
