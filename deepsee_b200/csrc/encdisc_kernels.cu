@@ -285,10 +285,11 @@ __global__ void disc_input_kernel(const uint8_t* __restrict__ labels, const floa
                                   int L, int HW, int Cp) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)2 * B * HW * Cp) return;
-    const int c = (int)(i % Cp);
-    const int64_t bp = i / Cp;
-    const int p = (int)(bp % HW);
-    const int b2 = (int)(bp / HW);
+    const uint32_t iu = (uint32_t)i;  // < 2^31 elements (host wrapper): 32-bit div/mod
+    const int c = (int)(iu % (uint32_t)Cp);
+    const uint32_t bp = iu / (uint32_t)Cp;
+    const int p = (int)(bp % (uint32_t)HW);
+    const int b2 = (int)(bp / (uint32_t)HW);
     const int b = b2 % B;
     float v = 0.f;
     if (c < L) {
@@ -305,12 +306,13 @@ __global__ void avgpool3s2_kernel(const float* __restrict__ in, float* __restric
                                   int Wi, int C, int Ho, int Wo) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * Ho * Wo * C) return;
-    const int c = (int)(i % C);
-    int64_t r = i / C;
-    const int xo = (int)(r % Wo);
-    r /= Wo;
-    const int yo = (int)(r % Ho);
-    const int b = (int)(r / Ho);
+    const uint32_t iu = (uint32_t)i;  // < 2^31 elements (host wrapper): 32-bit div/mod
+    const int c = (int)(iu % (uint32_t)C);
+    uint32_t r = iu / (uint32_t)C;
+    const int xo = (int)(r % (uint32_t)Wo);
+    r /= (uint32_t)Wo;
+    const int yo = (int)(r % (uint32_t)Ho);
+    const int b = (int)(r / (uint32_t)Ho);
     float s = 0.f;
     int cnt = 0;
     for (int ky = 0; ky < 3; ++ky) {
@@ -433,6 +435,7 @@ extern "C" int dsee_nchw_to_nhwc(const float* in, float* out, int B, int C, int 
 extern "C" int dsee_disc_input(const uint8_t* labels, const float* fake, const float* real,
                                float* out, int B, int L, int H, int W, int Cp, void* stream) {
     DSEE_CHECK_ARG(labels && fake && real && out && B > 0 && L > 0 && Cp >= L + 3, "bad argument");
+    DSEE_CHECK_ARG((int64_t)2 * B * H * W * Cp < ((int64_t)1 << 31), "more than 2^31 elements");
     int rc = require_sm100();
     if (rc) return rc;
     int64_t n = (int64_t)2 * B * H * W * Cp;
@@ -444,6 +447,7 @@ extern "C" int dsee_disc_input(const uint8_t* labels, const float* fake, const f
 extern "C" int dsee_avgpool3s2_fwd(const float* in, float* out, int B, int Hi, int Wi, int C,
                                    void* stream) {
     DSEE_CHECK_ARG(in && out && B > 0 && Hi > 0 && Wi > 0 && C > 0, "bad argument");
+    DSEE_CHECK_ARG((int64_t)B * Hi * Wi * C < ((int64_t)1 << 31), "more than 2^31 elements");
     int rc = require_sm100();
     if (rc) return rc;
     const int Ho = (Hi + 2 - 3) / 2 + 1, Wo = (Wi + 2 - 3) / 2 + 1;

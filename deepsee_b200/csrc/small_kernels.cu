@@ -164,9 +164,10 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, __half* __restri
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) inv_scale[0] = 1.f / scale;
     if (i >= (int64_t)N * 9 * C) return;
-    int c = (int)(i % C);
-    int tap = (int)((i / C) % 9);
-    int n = (int)(i / ((int64_t)9 * C));
+    const uint32_t iu = (uint32_t)i;  // < 2^31 elements (host wrapper): 32-bit div/mod
+    int c = (int)(iu % (uint32_t)C);
+    int tap = (int)((iu / (uint32_t)C) % 9u);
+    int n = (int)(iu / (9u * (uint32_t)C));
     float v = w[((size_t)n * C + c) * 9 + tap] * scale;
     __half h, l;
     split_f16(v, h, l);
@@ -204,9 +205,10 @@ __global__ void prep_weight_ex_kernel(const float* __restrict__ w, __half* __res
     const int rows = transpose ? C : N, cols = transpose ? N : C;
     const int cp = (cols + 63) / 64 * 64;
     if (i >= (int64_t)rows * T * cp) return;
-    const int cc = (int)(i % cp);
-    const int tap = (int)((i / cp) % T);
-    const int r = (int)(i / ((int64_t)T * cp));
+    const uint32_t iu = (uint32_t)i;  // < 2^31 elements (host wrapper): 32-bit div/mod
+    const int cc = (int)(iu % (uint32_t)cp);
+    const int tap = (int)((iu / (uint32_t)cp) % (uint32_t)T);
+    const int r = (int)(iu / ((uint32_t)T * (uint32_t)cp));
     float v = 0.f;
     if (cc < cols) {
         const int n = transpose ? cc : r, c = transpose ? r : cc;
@@ -637,6 +639,7 @@ extern "C" int dsee_prep_conv_weight(const float* w, void* out_hi, void* out_lo,
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     int64_t n = (int64_t)N * C * 9;
+    DSEE_CHECK_ARG(n < ((int64_t)1 << 31), "weight tensor too large");
     DSEE_CUDA(cudaMemsetAsync(inv_scale, 0, 3 * sizeof(float), st));
     int blocks = cdiv(n, 256 * 8);
     if (blocks > 1024) blocks = 1024;
@@ -667,6 +670,7 @@ extern "C" int dsee_prep_conv_weight_ex(const float* w, void* out_hi, void* out_
     count_launch();
     const int rows = transpose ? C : N, cols = transpose ? N : C;
     const int64_t total = (int64_t)rows * T * ((cols + 63) / 64 * 64);
+    DSEE_CHECK_ARG(total < ((int64_t)1 << 31), "weight tensor too large");
     prep_weight_ex_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, (__half*)out_hi, (__half*)out_lo,
                                                             inv_scale, N, C, T, transpose);
     LAUNCH_END();

@@ -152,9 +152,10 @@ __global__ void combine_fwd_kernel(CombineArgs p, float* __restrict__ wm, float*
     const int64_t total = (int64_t)2 * p.C * ct * 9;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < total) {
-        const int tap = (int)(i % 9);
-        const int col = (int)((i / 9) % ct);
-        const int row = (int)(i / ((int64_t)9 * ct));
+        const uint32_t iu = (uint32_t)i;  // total < 2^31 (host wrapper): 32-bit div/mod
+        const int tap = (int)(iu % 9u);
+        const int col = (int)((iu / 9u) % (uint32_t)ct);
+        const int row = (int)(iu / (9u * (uint32_t)ct));
         const int which = (row >> 7) & 1;                 // 0 gamma, 1 beta
         const int c = ((row >> 8) << 7) + (row & 127);    // channel
         const float a = blend_a(p, which);
@@ -190,9 +191,10 @@ __global__ void combine_bwd_kernel(CombineArgs p, const float* __restrict__ dwm,
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double da[2] = {0.0, 0.0};
     if (i < total) {
-        const int tap = (int)(i % 9);
-        const int col = (int)((i / 9) % ct);
-        const int row = (int)(i / ((int64_t)9 * ct));
+        const uint32_t iu = (uint32_t)i;  // total < 2^31 (host wrapper): 32-bit div/mod
+        const int tap = (int)(iu % 9u);
+        const int col = (int)((iu / 9u) % (uint32_t)ct);
+        const int row = (int)(iu / (9u * (uint32_t)ct));
         const int which = (row >> 7) & 1;
         const int c = ((row >> 8) << 7) + (row & 127);
         const float a = blend_a(p, which);
@@ -323,6 +325,7 @@ extern "C" int dsee_modweight_fwd(const dsee_modweight_args* a, float* wm, float
     rc = require_sm100();
     if (rc) return rc;
     const int64_t total = (int64_t)2 * p.C * (p.c1 + p.c2) * 9;
+    DSEE_CHECK_ARG(total < ((int64_t)1 << 31), "modulation weight too large");
     combine_fwd_kernel<<<cdivw(total, 256), 256, 0, (cudaStream_t)stream>>>(p, wm, gamma_bias, beta_bias);
     LAUNCH_END();
 }
@@ -352,6 +355,7 @@ extern "C" int dsee_modweight_bwd(const dsee_modweight_args* a, const float* dwm
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = (int64_t)2 * p.C * (p.c1 + p.c2) * 9;
+    DSEE_CHECK_ARG(total < ((int64_t)1 << 31), "modulation weight too large");
     const int blocks = cdivw(total, 256);
     combine_bwd_kernel<<<blocks, 256, 0, st>>>(p, dwm, dgb, dbb, o, (double*)workspace);
     count_launch();
