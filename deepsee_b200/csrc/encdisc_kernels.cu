@@ -743,12 +743,13 @@ __global__ void avgpool3s2_bwd_kernel(const float* __restrict__ dout, float* __r
                                       int Hi, int Wi, int C, int Ho, int Wo) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * Hi * Wi * C) return;
-    const int c = (int)(i % C);
-    int64_t r = i / C;
-    const int xi = (int)(r % Wi);
-    r /= Wi;
-    const int yi = (int)(r % Hi);
-    const int b = (int)(r / Hi);
+    const uint32_t iu = (uint32_t)i;  // < 2^31 elements (host wrapper): 32-bit div/mod
+    const int c = (int)(iu % (uint32_t)C);
+    uint32_t r = iu / (uint32_t)C;
+    const int xi = (int)(r % (uint32_t)Wi);
+    r /= (uint32_t)Wi;
+    const int yi = (int)(r % (uint32_t)Hi);
+    const int b = (int)(r / (uint32_t)Hi);
     float s = 0.f;
     for (int yo = (yi) / 2; yo <= (yi + 1) / 2; ++yo) {
         if (yo >= Ho) continue;
@@ -893,6 +894,7 @@ extern "C" int dsee_region_pool_bwd(const float* dstyle, const uint8_t* labels, 
 extern "C" int dsee_avgpool3s2_bwd(const float* dout, float* din, int B, int Hi, int Wi, int C,
                                    void* stream) {
     DSEE_CHECK_ARG(dout && din && B > 0 && Hi > 0 && Wi > 0 && C > 0, "bad argument");
+    DSEE_CHECK_ARG((int64_t)B * Hi * Wi * C < ((int64_t)1 << 31), "more than 2^31 elements");
     int rc = require_sm100();
     if (rc) return rc;
     const int Ho = (Hi + 2 - 3) / 2 + 1, Wo = (Wi + 2 - 3) / 2 + 1;

@@ -312,16 +312,26 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int x_ups, const fl
     if (has_noise) nw = __ldg(reinterpret_cast<const float4*>(noise_w) + g);
     if (pl < pix_lanes) {
         const int iend = (int)(npix - p0 < STAT_PIX ? npix - p0 : STAT_PIX);
+        // (b, yy, xx) of this lane's first pixel by one 32-bit division, then advanced incrementally
+        // (per-pixel div/mod would cost more issue slots than the noise generator)
+        const uint32_t pix0 = (uint32_t)(p0 + pl);
+        int xx = (int)(pix0 % (uint32_t)W);
+        int yy = (int)((pix0 / (uint32_t)W) % (uint32_t)H);
+        int b = (int)(pix0 / ((uint32_t)W * (uint32_t)H));
+        xx -= pix_lanes;
 #pragma unroll(HAS_NOISE ? 1 : 4)
         for (int i = pl; i < iend; i += pix_lanes) {
             int64_t pix = p0 + i;
-            size_t xp = (size_t)pix;
-            if (x_ups) {  // 32-bit coordinates: 64-bit div/mod per pixel would dominate the issue slots
-                const uint32_t pu = (uint32_t)pix;
-                const uint32_t xx = pu % (uint32_t)W, t2 = pu / (uint32_t)W;
-                const uint32_t yy = t2 % (uint32_t)H, b = t2 / (uint32_t)H;
-                xp = ((size_t)b * Hx + (yy >> 1)) * Wx + (xx >> 1);
+            xx += pix_lanes;
+            while (xx >= W) {
+                xx -= W;
+                if (++yy == H) {
+                    yy = 0;
+                    ++b;
+                }
             }
+            size_t xp = (size_t)pix;
+            if (x_ups) xp = ((size_t)b * Hx + (yy >> 1)) * Wx + (xx >> 1);
             float4 v = __ldg(reinterpret_cast<const float4*>(x + xp * C) + g);
             if (has_noise) {
                 float4 nv = load_noise4(noise, noise_seed, (size_t)pix * C + g * 4);
