@@ -170,8 +170,8 @@ class _ResBlockFn(torch.autograd.Function):
     """forward / backward of one SPADEResnetBlock (architecture.py:75-147) on the C-ABI kernels."""
 
     @staticmethod
-    def forward(ctx, blk, gctx, ups, stats_in, noises, pre, x, style, W0, b0, W1, b1, Wm0, gb0, bb0,
-                tab0, tb0, Wm1, gb1, bb1, tab1, tb1, nw_in, nw_skip, nw_mid):
+    def forward(ctx, blk, gctx, ups, stats_in, noises, pre, grad_on, x, style, W0, b0, W1, b1, Wm0, gb0,
+                bb0, tab0, tb0, Wm1, gb1, bb1, tab1, tb1, nw_in, nw_skip, nw_mid):
         B, Hx, Wx, C = x.shape
         H, W = Hx << ups, Wx << ups
         passes = config.passes
@@ -180,7 +180,11 @@ class _ResBlockFn(torch.autograd.Function):
         n_in, n_skip, n_mid = noises if noises is not None else (None, None, None)
         noisy = noises is not None
         pre = pre or {}
-        save_g = any(ctx.needs_input_grad) and config.save_gamma
+        # grad mode is invisible inside Function.forward (always off) and needs_input_grad ignores
+        # torch.no_grad(), so the caller passes it: under no_grad (the discriminator step's generator
+        # forward) nothing is kept for a backward pass and K1 does not write its G planes
+        need_bwd = grad_on and any(ctx.needs_input_grad)
+        save_g = need_bwd and config.save_gamma
 
         # ---- norm_0 + actvn -------------------------------------------------------------------
         part = None
@@ -211,7 +215,7 @@ class _ResBlockFn(torch.autograd.Function):
                         want_stats=training)
         out, stats = r if training else (r, None)
 
-        if any(ctx.needs_input_grad):
+        if need_bwd:
             ctx.s = dict(blk=blk, ups=ups, noises=noises, x=x, W0=W0, W1=W1, a0=a0, a1=a1, dx1=dx1,
                          st0=st0, st1=st1, nw_in=nw_in, passes=passes, want_lo=want_lo)
         if stats is None:
@@ -269,7 +273,7 @@ class _ResBlockFn(torch.autograd.Function):
             dstyle = dstyle1 if dstyle is None else dstyle + dstyle1
         ss.join()
         ctx.s = None
-        return (None, None, None, None, None, None, dx, dstyle, dW0, db0, dW1, db1, dWm0, dgb0, dbb0,
+        return (None, None, None, None, None, None, None, dx, dstyle, dW0, db0, dW1, db1, dWm0, dgb0, dbb0,
                 dtab0, dtb0, dWm1, dgb1, dbb1, dtab1, dtb1, dnw_in, dnw_skip, dnw_mid)
 
 
@@ -351,7 +355,8 @@ class SPADEResnetBlock(nn.Module):
             Wm1, gb1, bb1 = self.norm_1.combined_weight()
         tab0, tb0 = self.norm_0.table_and_bias()
         tab1, tb1 = self.norm_1.table_and_bias()
-        out, stats = _ResBlockFn.apply(self, ctx, ups, stats_in, noises, pre, x, ctx.style, W0,
+        out, stats = _ResBlockFn.apply(self, ctx, ups, stats_in, noises, pre, torch.is_grad_enabled(), x,
+                                       ctx.style, W0,
                                        self.conv_0.bias, W1, self.conv_1.bias, Wm0, gb0, bb0, tab0,
                                        tb0, Wm1, gb1, bb1, tab1, tb1, *nw)
         return out, (stats if self.training else None)

@@ -42,7 +42,8 @@ def effective_weight(conv):
     eps = 1e-12
     for hook in conv._forward_pre_hooks.values():
         eps = getattr(hook, 'eps', eps)
-    return ops.SpectralWeightFn.apply(conv.weight_orig, conv.weight_u, conv.weight_v, conv.training, eps)
+    return ops.SpectralWeightFn.apply(conv.weight_orig, conv.weight_u, conv.weight_v, conv.training, eps,
+                                      torch.is_grad_enabled())
 
 
 def get_nonspade_norm_layer(opt, norm_type='instance', oneD=False):

@@ -1068,7 +1068,7 @@ class SpectralWeightFn(torch.autograd.Function):
     for autograd) in 3-5 kernels instead of ~12 ATen launches."""
 
     @staticmethod
-    def forward(ctx, w_orig, u, v, training, eps):
+    def forward(ctx, w_orig, u, v, training, eps, keep_for_backward=True):
         _chk_cuda(w_orig, u, v)
         N = w_orig.shape[0]
         K = w_orig.numel() // N
@@ -1078,8 +1078,10 @@ class SpectralWeightFn(torch.autograd.Function):
         w_eff = torch.empty_like(w_orig)
         _lib.check(lib.dsee_spectral_weight_fwd(_p(w_orig), _p(u), _p(v), N, K, int(training), float(eps),
                                                 _p(ws), _p(sig), _p(w_eff), _stream()))
-        # u / v are overwritten by the next forward; the backward needs this forward's values
-        ctx.save_for_backward(w_eff, u.clone(), v.clone(), sig)
+        if keep_for_backward and ctx.needs_input_grad[0]:
+            # u / v are overwritten by the next forward; the backward needs this forward's values
+            # (callers pass keep_for_backward=False under no_grad: grad mode is invisible in here)
+            ctx.save_for_backward(w_eff, u.clone(), v.clone(), sig)
         return w_eff
 
     @staticmethod
@@ -1092,7 +1094,7 @@ class SpectralWeightFn(torch.autograd.Function):
         dw = torch.empty_like(w_eff)
         _lib.check(_lib.load().dsee_spectral_weight_bwd(_p(dw_eff), _p(w_eff), _p(u), _p(v), _p(sig), N, K,
                                                         _p(ws), _p(dw), _stream()))
-        return dw, None, None, None, None
+        return dw, None, None, None, None, None
 
 
 class ModWeightFn(torch.autograd.Function):
