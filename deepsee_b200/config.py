@@ -28,9 +28,6 @@ class _Config:
     # (sync_batchnorm/batchnorm.py:63-93): one [2,C] all-reduce per norm layer forward and one
     # [2,C] all-reduce per norm layer backward.
     sync_bn = os.environ.get("DSEE_SYNC_BN", "0") == "1"
-    # Generator step: build the discriminator graph with frozen discriminator parameters so the
-    # weight gradients the reference computes and discards are never computed (sr_model.py).
-    freeze_d_in_g_step = os.environ.get("DSEE_FREEZE_D_IN_G_STEP", "1") != "0"
     # Verify (one device->host read per generator forward) that the semantic input is one-hot.
     check_onehot = os.environ.get("DSEE_CHECK_ONEHOT", "1") != "0"
 

@@ -306,19 +306,11 @@ class SRModel(torch.nn.Module):
         fake_image, _, _ = self.generate_fake(
             input_semantics=input_semantics, image_downsized=image_downsized,
             full_image=style_image, guiding_image=guiding_image, guiding_label=guiding_label)
-        # The generator step only needs the discriminator's INPUT gradient.  The reference lets
-        # autograd compute the discriminator's weight gradients here too and throws them away
-        # (optimizer_D.zero_grad() runs before they are ever read, trainer_manager.py:49); building
-        # this graph with the discriminator's parameters frozen skips those weight-gradient kernels.
-        d_params = [p for p in self.netD.parameters() if p.requires_grad] if config.freeze_d_in_g_step else []
-        for p in d_params:
-            p.requires_grad_(False)
-        try:
-            pred_fake, pred_real = self.discriminate(input_semantics, fake_image, image_full,
-                                                     for_generator=True)
-        finally:
-            for p in d_params:
-                p.requires_grad_(True)
+        # (for_generator=True: the discriminator runs with detached parameters - the generator step only
+        # needs its INPUT gradient; the reference computes the weight gradients too and discards them,
+        # trainer_manager.py:49)
+        pred_fake, pred_real = self.discriminate(input_semantics, fake_image, image_full,
+                                                 for_generator=True)
         SR_losses['GAN'] = self.criterionGAN(pred_fake, True, for_discriminator=False)
         if not self.opt.no_ganFeat_loss:
             num_D = len(pred_fake)
