@@ -20,7 +20,6 @@ import torch.nn.functional as F
 
 from . import networks
 from .. import ops
-from ..config import config
 from ..util import util
 
 
