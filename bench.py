@@ -168,7 +168,6 @@ def main():
     # tests/test_generator_gpu.py pins it inside north_star's 1e-3 max-abs bound.  --passes 3 measures
     # the fp32-class split-operand mode (the library default, DSEE_PASSES).
     config.passes = args.passes or 1
-    config.check_onehot = False  # the bench feeds its own one-hot maps; skip the per-forward D2H flag read
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

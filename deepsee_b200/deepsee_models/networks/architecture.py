@@ -236,7 +236,11 @@ class _ResBlockFn(torch.autograd.Function):
         # ---- conv_1 + shortcut: out = conv(a1, W1) + b1 + x_up + w_in*n_in + w_skip*n_skip ------
         # (d noise_in.weight of the shortcut rides along in norm_0's bn_bwd below, which regenerates
         # n_in anyway; max|dout| comes with the tensor when the next block's bn_bwd produced it)
-        g1, sums = ops.grad_prep(dout, n_skip, None, want_lo=want_lo, amax=getattr(dout, "_dsee_amax", None))
+        tag = getattr(dout, "_dsee_amax", None)
+        # valid only for the very tensor bn_bwd wrote: an in-place accumulation by the autograd engine
+        # (a block output with a second consumer) bumps the version counter and voids it
+        amax_in = tag[0] if tag is not None and tag[1] == dout._version else None
+        g1, sums = ops.grad_prep(dout, n_skip, None, want_lo=want_lo, amax=amax_in)
         db1 = sums[0]
         dnw_skip = sums[1] if noisy else None
         ss = _SideStream()
@@ -267,7 +271,7 @@ class _ResBlockFn(torch.autograd.Function):
                                          want_amax=True)
         # the previous block's backward receives this very tensor as its `dout` (a block output has one
         # consumer); if autograd hands over a different tensor the attribute is simply absent
-        dx._dsee_amax = dx_amax
+        dx._dsee_amax = (dx_amax, dx._version)
         dstyle = dstyle0
         if dstyle1 is not None:
             dstyle = dstyle1 if dstyle is None else dstyle + dstyle1

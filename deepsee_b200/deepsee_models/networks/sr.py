@@ -100,7 +100,32 @@ class DeepSEESR(BaseNetwork):
         for i in range(self.n_blocks - 1):
             x, st = self.up_list[i].forward_nhwc(x, ctx, ups=1, stats_in=st)
         out = _HeadFn.apply(x, self.conv_img.weight, self.conv_img.bias)
-        if config.check_onehot and int(bad.item()) != 0:
-            raise ValueError('DeepSEESR: `seg` must be a one-hot map (exactly one 1.0 per pixel); '
-                             'the B200 path consumes it as an integer label map')
+        if config.check_onehot:
+            self._check_onehot(bad)
         return out
+
+    _ONEHOT_MSG = ('DeepSEESR: `seg` must be a one-hot map (exactly one 1.0 per pixel); '
+                   'the B200 path consumes it as an integer label map')
+
+    def _check_onehot(self, bad):
+        """`bad` is a device flag set by labels_from_onehot.  Reading it with .item() would stall the
+        launch pipeline once per forward, so in training mode the flag travels to pinned host memory
+        asynchronously and is examined at the NEXT forward (by then the copy finished long ago): a bad
+        batch raises one call late, a training loop keeps running ahead of the GPU.  In eval mode
+        (demo / inference, one call at a time) the check is immediate."""
+        pend = getattr(self, '_onehot_pending', None)
+        if pend is not None:
+            host, ev = pend
+            ev.synchronize()
+            self._onehot_pending = None
+            if int(host[0]) != 0:
+                raise ValueError(self._ONEHOT_MSG + ' (detected in the previous forward)')
+        if not self.training:
+            if int(bad.item()) != 0:
+                raise ValueError(self._ONEHOT_MSG)
+            return
+        host = torch.empty(1, dtype=bad.dtype, pin_memory=True)
+        host.copy_(bad, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._onehot_pending = (host, ev)

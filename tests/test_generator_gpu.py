@@ -108,6 +108,13 @@ def test_generator_rejects_non_onehot():
     with pytest.raises(ValueError, match="one-hot"):
         with torch.no_grad():
             G(d["image_lr"].cuda(), seg=seg.cuda(), z=torch.zeros(1, 19, 128).cuda())
+    # training mode: the flag is read without stalling the launch pipeline, one forward late
+    G.train()
+    with torch.no_grad():
+        G(d["image_lr"].cuda(), seg=seg.cuda(), z=torch.zeros(1, 19, 128).cuda())
+        with pytest.raises(ValueError, match="previous forward"):
+            G(d["image_lr"].cuda(), seg=d["input_semantics"].cuda(), z=torch.zeros(1, 19, 128).cuda())
+        G(d["image_lr"].cuda(), seg=d["input_semantics"].cuda(), z=torch.zeros(1, 19, 128).cuda())
 
 
 def test_generator_train_forward_vs_oracle():
