@@ -27,6 +27,7 @@ SYMBOLS = [
     "dsee_conv2d_direct_fwd", "dsee_instance_norm_fwd", "dsee_instance_norm_workspace_bytes", "dsee_region_pool_chunks",
     "dsee_region_pool_fwd", "dsee_nchw_to_nhwc", "dsee_disc_input", "dsee_avgpool3s2_fwd",
     "dsee_spectral_workspace_floats", "dsee_spectral_weight_fwd", "dsee_spectral_weight_bwd",
+    "dsee_spectral_weight_fwd_batched",
     "dsee_modweight_fwd", "dsee_modweight_bwd_workspace_bytes", "dsee_modweight_bwd",
     "dsee_act_bwd", "dsee_conv2d_direct_dgrad", "dsee_conv2d_direct_wgrad_workspace_floats",
     "dsee_conv2d_direct_wgrad", "dsee_channel_sum_chunks", "dsee_channel_sum",
@@ -96,6 +97,14 @@ class DgradModBwdArgs(C.Structure):
         ("dy_amax", C.c_void_p), ("w_l1", C.c_void_p),
         ("dxhat", C.c_void_p), ("dgb_hi", C.c_void_p), ("dgb_lo", C.c_void_p),
         ("dgb_inv_scale", C.c_void_p), ("partial", C.c_void_p), ("C", C.c_int),
+    ]
+
+
+class SnItem(C.Structure):
+    _fields_ = [
+        ("w_orig", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("w_eff", C.c_void_p),
+        ("sigma2", C.c_void_p), ("workspace", C.c_void_p), ("u_saved", C.c_void_p), ("v_saved", C.c_void_p),
+        ("N", C.c_int), ("K", C.c_int),
     ]
 
 
@@ -183,6 +192,7 @@ def load():
         "dsee_disc_input": [vp, vp, vp, vp, i, i, i, i, i, vp],
         "dsee_avgpool3s2_fwd": [vp, vp, i, i, i, i, vp],
         "dsee_spectral_weight_fwd": [vp, vp, vp, i, i, i, f, vp, vp, vp, vp],
+        "dsee_spectral_weight_fwd_batched": [C.POINTER(SnItem), i, i, f, vp],
         "dsee_spectral_weight_bwd": [vp, vp, vp, vp, vp, i, i, vp, vp, vp],
         "dsee_modweight_fwd": [C.POINTER(ModWeightArgs), vp, vp, vp, vp],
         "dsee_modweight_bwd": [C.POINTER(ModWeightArgs), vp, vp, vp, C.POINTER(ModWeightGrads), vp, vp],

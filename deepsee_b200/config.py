@@ -28,6 +28,9 @@ class _Config:
     # (sync_batchnorm/batchnorm.py:63-93): one [2,C] all-reduce per norm layer forward and one
     # [2,C] all-reduce per norm layer backward.
     sync_bn = os.environ.get("DSEE_SYNC_BN", "0") == "1"
+    # Spectral normalisation of a network's layers in one batched launch sequence per forward
+    # (ops.spectral_prepass) instead of five launches per layer; 0 = per-layer kernels.
+    batched_spectral = os.environ.get("DSEE_BATCHED_SPECTRAL", "1") != "0"
     # Verify (one device->host read per generator forward) that the semantic input is one-hot.
     check_onehot = os.environ.get("DSEE_CHECK_ONEHOT", "1") != "0"
 

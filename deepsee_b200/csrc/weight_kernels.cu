@@ -7,6 +7,7 @@
 // normalization.py:29-31); normalization.py:116-119, 198-213, 283-286 (gamma/beta convs and the
 // sigmoid(alpha) blend).
 #include "common.cuh"
+#include <string.h>
 #include "launch_count.h"
 #include "../../include/deepsee_b200.h"
 
@@ -94,6 +95,82 @@ __global__ void scale_by_kernel(const float* __restrict__ in, const float* __res
                                 float* __restrict__ out, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] * __ldg(scale);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same five steps for up to SN_MAX_BATCH layers per launch (blockIdx.z / .y / .x = layer): a
+// network's spectral-norm layers are independent, and one launch per step per NETWORK instead of per
+// LAYER removes ~250 launches of microsecond kernels from every training iteration.
+// ------------------------------------------------------------------------------------------------
+struct SnBatch {
+    dsee_sn_item it[DSEE_SN_MAX_BATCH];
+    int count;
+};
+__global__ void sn_wt_u_batched_kernel(const __grid_constant__ SnBatch b) {
+    const dsee_sn_item& t = b.it[blockIdx.z];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= t.K) return;
+    const int s = blockIdx.y;
+    const int n0 = (int)((int64_t)t.N * s / SN_SLICES), n1 = (int)((int64_t)t.N * (s + 1) / SN_SLICES);
+    float a = 0.f;
+    for (int n = n0; n < n1; ++n) a += __ldg(t.w_orig + (size_t)n * t.K + k) * __ldg(t.u + n);
+    t.workspace[(size_t)s * t.K + k] = a;
+}
+__global__ void sn_finish_v_batched_kernel(const __grid_constant__ SnBatch b, float eps) {
+    const dsee_sn_item& t = b.it[blockIdx.x];
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < t.K; k += blockDim.x) {
+        float x = 0.f;
+        for (int s = 0; s < SN_SLICES; ++s) x += t.workspace[(size_t)s * t.K + k];
+        t.v[k] = x;
+        acc += (double)x * x;
+    }
+    const double nrm = sqrt(block_sum_double(acc, sh));
+    const float inv = 1.f / fmaxf((float)nrm, eps);
+    for (int k = threadIdx.x; k < t.K; k += blockDim.x) t.v[k] *= inv;
+}
+__global__ void sn_w_v_batched_kernel(const __grid_constant__ SnBatch b) {
+    const dsee_sn_item& t = b.it[blockIdx.y];
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (n >= t.N) return;
+    float a = 0.f;
+    for (int k = lane; k < t.K; k += 32) a += __ldg(t.w_orig + (size_t)n * t.K + k) * __ldg(t.v + k);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) t.workspace[(size_t)SN_SLICES * t.K + n] = a;
+}
+__global__ void sn_finish_u_batched_kernel(const __grid_constant__ SnBatch b, float eps, int update_u) {
+    const dsee_sn_item& t = b.it[blockIdx.x];
+    const float* s = t.workspace + (size_t)SN_SLICES * t.K;
+    __shared__ double sh[32];
+    double acc = 0.0;
+    if (update_u) {
+        for (int n = threadIdx.x; n < t.N; n += blockDim.x) acc += (double)s[n] * s[n];
+        const double nrm = sqrt(block_sum_double(acc, sh));
+        const float inv = 1.f / fmaxf((float)nrm, eps);
+        for (int n = threadIdx.x; n < t.N; n += blockDim.x) t.u[n] = s[n] * inv;
+        __syncthreads();
+    }
+    acc = 0.0;
+    for (int n = threadIdx.x; n < t.N; n += blockDim.x) acc += (double)t.u[n] * s[n];
+    const double sigma = block_sum_double(acc, sh);
+    if (threadIdx.x == 0) {
+        t.sigma2[0] = (float)sigma;
+        t.sigma2[1] = (float)(1.0 / sigma);
+    }
+    // this forward's u / v for the backward pass (the buffers are overwritten by the next forward)
+    if (t.u_saved)
+        for (int n = threadIdx.x; n < t.N; n += blockDim.x) t.u_saved[n] = t.u[n];
+    if (t.v_saved)
+        for (int k = threadIdx.x; k < t.K; k += blockDim.x) t.v_saved[k] = t.v[k];
+}
+__global__ void scale_by_batched_kernel(const __grid_constant__ SnBatch b) {
+    const dsee_sn_item& t = b.it[blockIdx.y];
+    const int64_t n = (int64_t)t.N * t.K;
+    const float sc = __ldg(t.sigma2 + 1);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        t.w_eff[i] = t.w_orig[i] * sc;
 }
 
 // backward of W_eff = W / sigma(W), sigma = u^T W v with u, v constants:
@@ -277,6 +354,46 @@ extern "C" int dsee_spectral_weight_fwd(const float* w_orig, float* u, float* v,
     const int64_t n = (int64_t)N * K;
     scale_by_kernel<<<cdivw(n, 256), 256, 0, st>>>(w_orig, sigma2 + 1, w_eff, n);
     LAUNCH_END();
+}
+
+extern "C" int dsee_spectral_weight_fwd_batched(const dsee_sn_item* items, int count, int power_iteration,
+                                                float eps, void* stream) {
+    DSEE_CHECK_ARG(items && count > 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int base = 0; base < count; base += DSEE_SN_MAX_BATCH) {
+        SnBatch b;
+        memset(&b, 0, sizeof(b));
+        b.count = count - base < DSEE_SN_MAX_BATCH ? count - base : DSEE_SN_MAX_BATCH;
+        int maxN = 0, maxK = 0;
+        int64_t maxNK = 0;
+        for (int i = 0; i < b.count; ++i) {
+            const dsee_sn_item& t = items[base + i];
+            DSEE_CHECK_ARG(t.w_orig && t.u && t.v && t.w_eff && t.sigma2 && t.workspace && t.N > 0 && t.K > 0,
+                           "bad spectral-norm item %d", base + i);
+            b.it[i] = t;
+            maxN = t.N > maxN ? t.N : maxN;
+            maxK = t.K > maxK ? t.K : maxK;
+            maxNK = (int64_t)t.N * t.K > maxNK ? (int64_t)t.N * t.K : maxNK;
+        }
+        if (power_iteration) {
+            sn_wt_u_batched_kernel<<<dim3(cdivw(maxK, 256), SN_SLICES, b.count), 256, 0, st>>>(b);
+            count_launch();
+            sn_finish_v_batched_kernel<<<b.count, 1024, 0, st>>>(b, eps);
+            count_launch();
+        }
+        sn_w_v_batched_kernel<<<dim3(cdivw((int64_t)maxN * 32, 256), b.count), 256, 0, st>>>(b);
+        count_launch();
+        sn_finish_u_batched_kernel<<<b.count, 1024, 0, st>>>(b, eps, power_iteration);
+        count_launch();
+        int blocks = cdivw(maxNK, 256 * 4);
+        if (blocks > 2048) blocks = 2048;
+        scale_by_batched_kernel<<<dim3(blocks, b.count), 256, 0, st>>>(b);
+        count_launch();
+        DSEE_CUDA(cudaGetLastError());
+    }
+    return 0;
 }
 
 extern "C" int dsee_spectral_weight_bwd(const float* dw_eff, const float* w_eff, const float* u,

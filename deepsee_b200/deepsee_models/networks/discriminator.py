@@ -13,7 +13,7 @@ import torch.nn as nn
 from ... import ops
 from .base_network import BaseNetwork
 from .encoder import _khwc
-from .normalization import get_nonspade_norm_layer, effective_weight
+from .normalization import get_nonspade_norm_layer, effective_weight, spectral_prepass
 
 
 class MultiscaleDiscriminator(BaseNetwork):
@@ -45,10 +45,12 @@ class MultiscaleDiscriminator(BaseNetwork):
         and then discards those gradients: trainer_manager.py:48-49 zeroes them before use)."""
         result = []
         feats = not self.opt.no_ganFeat_loss
-        for name, D in self.named_children():
-            out = D.forward_nhwc(x_nhwc, detach_params)
-            result.append(out if feats else [out[-1]])
-            x_nhwc = self.downsample(x_nhwc)
+        convs = [c for _, D in self.named_children() for c in D.sn_convs()]
+        with spectral_prepass(convs):
+            for name, D in self.named_children():
+                out = D.forward_nhwc(x_nhwc, detach_params)
+                result.append(out if feats else [out[-1]])
+                x_nhwc = self.downsample(x_nhwc)
         return result
 
     def forward(self, input):
@@ -86,6 +88,9 @@ class NLayerDiscriminator(BaseNetwork):
 
     def compute_D_input_nc(self, opt):
         return opt.label_nc + opt.output_nc + (1 if opt.contain_dontcare_label else 0)
+
+    def sn_convs(self):
+        return [getattr(self, 'model%d' % n)[0][0] for n in range(1, self.n_layers)]
 
     def forward_nhwc(self, x, detach_params=False):
         """x NHWC [B,H,W,Cp] (channels beyond input_nc are zero) -> list of NHWC feature maps."""

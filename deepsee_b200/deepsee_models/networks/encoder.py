@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from ... import ops
 from .base_network import BaseNetwork
-from .normalization import get_nonspade_norm_layer, effective_weight
+from .normalization import get_nonspade_norm_layer, effective_weight, spectral_prepass
 
 
 def _khwc(w, pad_cin=None):
@@ -116,9 +116,13 @@ class FullStyleEncoder(AbtractStyleEncoder):
         x = _stage(x, self.up_conv[1], ups=1)
         return x, None
 
+    def main_convs(self):
+        return [self.initial[0][0], self.down0[0][0], self.down1[0][0], self.up_conv[1][0]]
+
     def forward(self, x=None, seg=None, mode="full", no_noise=False):
-        x, activations = self.forward_main(x)
-        x = self._final(x)
+        with spectral_prepass(self.main_convs() + [self.final[0][0]]):
+            x, activations = self.forward_main(x)
+            x = self._final(x)
         style_matrix = self.extract_style_matrix(x, self._labels(seg))
         if self.noisy_style and not no_noise:
             style_matrix = self.corrupt_style_matrix(style_matrix, self.max_range_noise)
@@ -152,9 +156,13 @@ class MinistyleEncoder(AbtractStyleEncoder):
         x = _stage(x, self.conv2[1], ups=1)
         return x, None
 
+    def main_convs(self):
+        return [self.initial[0][0], self.conv0[0][0], self.conv1[0][0], self.conv2[1][0]]
+
     def forward(self, x=None, seg=None, mode="mini"):
-        x, activations = self.forward_main(x)
-        x = self._final(x)
+        with spectral_prepass(self.main_convs() + [self.final[0][0]]):
+            x, activations = self.forward_main(x)
+            x = self._final(x)
         return self.extract_style_matrix(x, self._labels(seg)), activations
 
 
@@ -176,12 +184,15 @@ class CombinedstyleEncoder(AbtractStyleEncoder):
 
     def forward(self, x=None, seg=None, mode=None, no_noise=False):
         if mode == "full":
-            x, activations = self.encoder_full.forward_main(x)
+            enc = self.encoder_full
         elif mode == "mini":
-            x, activations = self.encoder_mini.forward_main(x)
+            enc = self.encoder_mini
         else:
             raise NotImplementedError()
-        x = self._final(x)
+        # only the branch that runs is normalised (its u / v advance like the reference's hooks)
+        with spectral_prepass(enc.main_convs() + [self.final[0][0]]):
+            x, activations = enc.forward_main(x)
+            x = self._final(x)
         style_matrix = self.extract_style_matrix(x, self._labels(seg))
         if self.noisy_style and not no_noise:
             style_matrix = self.corrupt_style_matrix(style_matrix, self.max_range_noise)

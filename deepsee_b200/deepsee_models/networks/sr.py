@@ -14,7 +14,7 @@ from ... import ops
 from ...config import config
 from .architecture import SPADEResnetBlock
 from .base_network import BaseNetwork
-from .normalization import GenContext
+from .normalization import GenContext, spectral_prepass
 
 
 class _StemFn(torch.autograd.Function):
@@ -93,12 +93,14 @@ class DeepSEESR(BaseNetwork):
         labels, bad = ops.labels_from_onehot(seg)
         ctx = GenContext(labels, z.contiguous().float() if z is not None else None)
 
+        blocks = [self.head_0, self.G_middle_0, self.G_middle_1] + [self.up_list[i] for i in range(self.n_blocks - 1)]
         x = _StemFn.apply(x_downsized, self.initial.weight, self.initial.bias)
-        x, st = self.head_0.forward_nhwc(x, ctx, ups=0)
-        x, st = self.G_middle_0.forward_nhwc(x, ctx, ups=1, stats_in=st)
-        x, st = self.G_middle_1.forward_nhwc(x, ctx, ups=0, stats_in=st)
-        for i in range(self.n_blocks - 1):
-            x, st = self.up_list[i].forward_nhwc(x, ctx, ups=1, stats_in=st)
+        with spectral_prepass([c for blk in blocks for c in (blk.conv_0, blk.conv_1)]):
+            x, st = self.head_0.forward_nhwc(x, ctx, ups=0)
+            x, st = self.G_middle_0.forward_nhwc(x, ctx, ups=1, stats_in=st)
+            x, st = self.G_middle_1.forward_nhwc(x, ctx, ups=0, stats_in=st)
+            for i in range(self.n_blocks - 1):
+                x, st = self.up_list[i].forward_nhwc(x, ctx, ups=1, stats_in=st)
         out = _HeadFn.apply(x, self.conv_img.weight, self.conv_img.bias)
         if config.check_onehot:
             self._check_onehot(bad)

@@ -1068,7 +1068,14 @@ class SpectralWeightFn(torch.autograd.Function):
     for autograd) in 3-5 kernels instead of ~12 ATen launches."""
 
     @staticmethod
-    def forward(ctx, w_orig, u, v, training, eps, keep_for_backward=True):
+    def forward(ctx, w_orig, u, v, training, eps, keep_for_backward=True, pre=None):
+        """pre: (w_eff, sigma2, u_saved, v_saved) already computed for this layer by
+        spectral_prepass (one batched launch sequence per network); then only the graph is wired."""
+        if pre is not None:
+            w_eff, sig, u_s, v_s = pre
+            if keep_for_backward and ctx.needs_input_grad[0]:
+                ctx.save_for_backward(w_eff, u_s, v_s, sig)
+            return w_eff
         _chk_cuda(w_orig, u, v)
         N = w_orig.shape[0]
         K = w_orig.numel() // N
@@ -1094,7 +1101,48 @@ class SpectralWeightFn(torch.autograd.Function):
         dw = torch.empty_like(w_eff)
         _lib.check(_lib.load().dsee_spectral_weight_bwd(_p(dw_eff), _p(w_eff), _p(u), _p(v), _p(sig), N, K,
                                                         _p(ws), _p(dw), _stream()))
-        return dw, None, None, None, None, None
+        return dw, None, None, None, None, None, None
+
+
+def spectral_prepass(convs, training, eps, keep_for_backward):
+    """SpectralWeightFn's forward arithmetic for a list of spectral-normalised layers in ONE batched
+    launch sequence (dsee_spectral_weight_fwd_batched): power iteration (training), sigma, W / sigma.
+    -> list of (w_eff shaped like weight_orig, sigma2 [2], u_saved | None, v_saved | None), all views
+    of a few flat buffers."""
+    lib = _lib.load()
+    n = len(convs)
+    shapes = [tuple(c.weight_orig.shape) for c in convs]
+    NK = [(sh[0], int(torch.Size(sh).numel() // sh[0])) for sh in shapes]
+    dev = convs[0].weight_orig.device
+    tot_w = sum(N * K for N, K in NK)
+    tot_ws = sum(lib.dsee_spectral_workspace_floats(N, K) for N, K in NK)
+    tot_uv = sum(N + K for N, K in NK) if keep_for_backward else 0
+    flat = torch.empty(tot_w + tot_ws + 2 * n + tot_uv, dtype=torch.float32, device=dev)
+    items = (_lib.SnItem * n)()
+    base = flat.data_ptr()
+    o_w, o_ws, o_sig, o_uv = 0, tot_w, tot_w + tot_ws, tot_w + tot_ws + 2 * n
+    out = []
+    for i, (c, (N, K)) in enumerate(zip(convs, NK)):
+        _chk_cuda(c.weight_orig, c.weight_u, c.weight_v)
+        it = items[i]
+        it.w_orig, it.u, it.v = c.weight_orig.data_ptr(), c.weight_u.data_ptr(), c.weight_v.data_ptr()
+        it.w_eff, it.sigma2, it.workspace = base + 4 * o_w, base + 4 * o_sig, base + 4 * o_ws
+        it.N, it.K = N, K
+        w_eff = flat[o_w:o_w + N * K].view(shapes[i])
+        sig = flat[o_sig:o_sig + 2]
+        u_s = v_s = None
+        if keep_for_backward:
+            it.u_saved, it.v_saved = base + 4 * o_uv, base + 4 * (o_uv + N)
+            u_s, v_s = flat[o_uv:o_uv + N], flat[o_uv + N:o_uv + N + K]
+            o_uv += N + K
+        else:
+            it.u_saved, it.v_saved = 0, 0
+        out.append((w_eff, sig, u_s, v_s))
+        o_w += N * K
+        o_ws += lib.dsee_spectral_workspace_floats(N, K)
+        o_sig += 2
+    _lib.check(lib.dsee_spectral_weight_fwd_batched(items, n, int(training), float(eps), _stream()))
+    return out
 
 
 class ModWeightFn(torch.autograd.Function):

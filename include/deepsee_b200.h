@@ -517,6 +517,26 @@ int dsee_spectral_weight_fwd(const float* w_orig, float* u, float* v, int N, int
 int dsee_spectral_weight_bwd(const float* dw_eff, const float* w_eff, const float* u, const float* v,
                              const float* sigma2, int N, int K, void* workspace, float* dw_orig,
                              void* stream);
+
+/* The forward of dsee_spectral_weight_fwd for many layers at once (one launch per step for up to
+ * DSEE_SN_MAX_BATCH layers instead of five launches per layer; more layers run in chunks).  items is
+ * a HOST array; every pointer in it is a device pointer.  workspace: dsee_spectral_workspace_floats(N, K)
+ * floats per item; u_saved / v_saved (optional, may be NULL): copies of this forward's u / v for
+ * dsee_spectral_weight_bwd.  Arithmetic identical to the per-layer entry point. */
+#define DSEE_SN_MAX_BATCH 24
+typedef struct {
+    const float* w_orig;
+    float* u;
+    float* v;
+    float* w_eff;
+    float* sigma2;
+    float* workspace;
+    float* u_saved;
+    float* v_saved;
+    int N, K;
+} dsee_sn_item;
+int dsee_spectral_weight_fwd_batched(const dsee_sn_item* items, int count, int power_iteration, float eps,
+                                     void* stream);
 /* Assembly of K1's fused modulation weight from the reference's separate convs
  * (normalization.py:116-119 SPADE, :198-213 SEAN with the sigmoid(alpha) blend, :283-286 PureSEAN):
  * rows interleaved per 128 channels [gamma | beta], columns [seg source (c1) | style source (c2)],

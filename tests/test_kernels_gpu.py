@@ -549,6 +549,42 @@ def test_spectral_weight_node_vs_torch(shape, training):
     assert (w1.grad - g).abs().max().item() <= 2e-5 * g.abs().max().item()
 
 
+@pytest.mark.parametrize("training", [True, False])
+def test_batched_spectral_prepass_equals_per_layer_node(training):
+    """spectral_prepass (one batched launch sequence for a list of layers of different shapes) against
+    the per-layer SpectralWeightFn: effective weights, updated u / v and weight_orig gradients are
+    bit-identical; an unlisted layer still takes the per-layer path."""
+    import copy
+    import torch.nn as nn
+    from deepsee_b200.config import config
+    from deepsee_b200.deepsee_models.networks.normalization import effective_weight, spectral_prepass
+    torch.manual_seed(3)
+    shapes = [(64, 27, 3), (128, 64, 3), (32, 48, 4), (512, 512, 3)]
+    a = [nn.utils.spectral_norm(nn.Conv2d(ci, co, k)).cuda().train(training) for co, ci, k in shapes]
+    b = copy.deepcopy(a)
+    extra_a = nn.utils.spectral_norm(nn.Conv2d(8, 16, 3)).cuda().train(training)
+    extra_b = copy.deepcopy(extra_a)
+    dys = [torch.randn_like(c.weight_orig) for c in a + [extra_a]]
+    old = config.batched_spectral
+    try:
+        config.batched_spectral = False
+        wa = [effective_weight(c) for c in a + [extra_a]]
+        config.batched_spectral = True
+        with spectral_prepass(b):
+            assert all(c._sn_pre is not None for c in b)
+            wb = [effective_weight(c) for c in b + [extra_b]]
+        assert all(c._sn_pre is None for c in b)
+    finally:
+        config.batched_spectral = old
+    for x, y, dy in zip(wa, wb, dys):
+        assert torch.equal(x, y)
+        x.backward(dy)
+        y.backward(dy)
+    for ca, cb in zip(a + [extra_a], b + [extra_b]):
+        assert torch.equal(ca.weight_u, cb.weight_u) and torch.equal(ca.weight_v, cb.weight_v)
+        assert torch.equal(ca.weight_orig.grad, cb.weight_orig.grad)
+
+
 @pytest.mark.parametrize("kind", ["spade", "sean", "puresean"])
 def test_modweight_node_vs_torch_ops(kind):
     from deepsee_b200.deepsee_models.networks import normalization as Nz
