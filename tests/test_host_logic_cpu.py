@@ -90,3 +90,54 @@ def test_srmodel_mode_table_covers_the_reference_modes():
                  "inference_particular_combined", "inference_particular_full", "inference_reference",
                  "inference_reference_interpolation"):
         assert repr(mode) in src or '"%s"' % mode in src, mode
+
+
+def test_style_sweep_layout_with_stub_networks():
+    """SRModel._style_sweep's host logic (which style matrix goes with which sample, how variants are
+    laid out) on CPU, with stub networks: the 'generator' paints every pixel with the mean of the
+    style rows it was given plus 10 x the sample's LR mean, so the output identifies (sample, variant)."""
+    import numpy as np
+    from deepsee_b200.deepsee_models.sr_model import SRModel
+    from deepsee_b200.options.configurations import make_opt
+
+    B, S = 2, 8
+    opt = make_opt("8x_independent_256x256", n_interpolation=3, noise_delta=0.5, region_idx=[1, 2],
+                   dont_merge_fake=False, batchSize=B)
+    m = SRModel.__new__(SRModel)
+    torch.nn.Module.__init__(m)
+    m.opt = opt
+    m.model_variant = "independent"
+    style = torch.linspace(-0.4, 0.4, B * 19 * 4).view(B, 19, 4)
+
+    def encode_style(**kw):
+        return style.clone(), None
+
+    def generate_fake(input_semantics, image_downsized, encoded_style=None, **kw):
+        n = image_downsized.shape[0]
+        val = encoded_style[:, [1, 2]].mean(dim=(1, 2)) + 10 * image_downsized.mean(dim=(1, 2, 3))
+        return val.view(n, 1, 1, 1).expand(n, 3, S, S).clone(), None, encoded_style
+
+    m.encode_style, m.generate_fake = encode_style, generate_fake
+    data = {"input_semantics": torch.zeros(B, 19, S, S), "image_hr": torch.zeros(B, 3, S, S),
+            "image_lr": torch.stack([torch.full((3, 2, 2), float(b + 1)) for b in range(B)])}
+
+    out = m._style_sweep("inference_interpolation", data)
+    assert tuple(out["fake_image"].shape) == (B, 3, S, 3 * S)
+    for b in range(B):
+        for i, step in enumerate(np.linspace(-0.5, 0.5, num=3)):
+            want = (style[b, [1, 2]] + float(step)).clamp(-1, 1).mean() + 10 * (b + 1)
+            got = out["fake_image"][b, 0, 0, i * S]
+            assert abs(float(got) - float(want)) < 1e-5, (b, i)
+
+    opt.dont_merge_fake = True
+    out = m._style_sweep("inference_reference", data)
+    assert tuple(out["fake_image"].shape) == (B, B, 3, S, S)
+    # sample 0 rendered with sample 1's regions 1, 2
+    want = style[1, [1, 2]].mean() + 10 * 1
+    assert abs(float(out["fake_image"][0, 1, 0, 0, 0]) - float(want)) < 1e-5
+
+    d2 = dict(data, style_from=style, style_to=style.flip(0))
+    out = m._style_sweep("inference_interpolation_style", d2)
+    mid = 0.5 * style[0, [1, 2]].mean() + 0.5 * style[1, [1, 2]].mean() + 10 * 1
+    assert abs(float(out["fake_image"][0, 1, 0, 0, 0]) - float(mid)) < 1e-5
+    assert len(out["style"]) == B and tuple(out["style"][0].shape) == (3, 19, 4)
