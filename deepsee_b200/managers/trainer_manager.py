@@ -6,6 +6,7 @@ Same public surface as the reference (`run_generator_one_step`, `run_discriminat
   * one process per GPU; after each backward the G(+E) or D gradients are averaged across ranks
     with ONE flat NCCL all-reduce (..parallel.GradBucket) - the only data-path collective;
   * checkpoints are written by rank 0 only.
+Both optimizer steps share one code path (`_optimize`).
 """
 from torch.nn.utils import clip_grad_value_
 
@@ -17,51 +18,45 @@ class TrainerManager(BaseManager):
     def __init__(self, opt):
         super().__init__(opt, create_model=True)
         assert opt.isTrain
-        self.optimizer_G, self.optimizer_D = self.sr_model_on_one_gpu.create_optimizers(opt)
+        model = self.sr_model_on_one_gpu
+        self.optimizer_G, self.optimizer_D = model.create_optimizers(opt)
         self.old_lr = opt.lr
         self.generated = None
         self.logs = {}
-        self.g_losses = {}
-        self.d_losses = {}
-        m = self.sr_model_on_one_gpu
-        g_params = list(m.netSR.parameters()) + (list(m.netE.parameters()) if m.use_E else [])
-        self._bucket_G = parallel.GradBucket(g_params) if parallel.is_dist() else None
-        self._bucket_D = parallel.GradBucket(list(m.netD.parameters())) if parallel.is_dist() else None
+        self.g_losses, self.d_losses = {}, {}
+        self._bucket_G = self._bucket_D = None
+        if parallel.is_dist():
+            g_params = list(model.netSR.parameters()) + (list(model.netE.parameters()) if model.use_E else [])
+            self._bucket_G = parallel.GradBucket(g_params)
+            self._bucket_D = parallel.GradBucket(list(model.netD.parameters()))
 
-    def get_logs(self):
-        return {**self.logs, **self.sr_model_on_one_gpu.get_logs()}
+    # ---- one optimizer step (trainer_manager.py:32-61) ------------------------------------------------
+    def _optimize(self, data, mode, optimizer, bucket):
+        """zero_grad -> forward(mode) -> mean of the summed losses -> backward -> gradient all-reduce
+        (multi-GPU) -> optional value clipping -> optimizer step.  Returns SRModel.forward's result."""
+        optimizer.zero_grad()
+        result = self.sr_model(self.preprocess_input(data), mode=mode)
+        losses = result[0] if mode == 'generator' else result
+        sum(losses.values()).mean().backward()
+        if bucket is not None:
+            bucket.allreduce_mean()
+        if self.opt.gradient_clip > 0:
+            clip_grad_value_(self.sr_model.parameters(), self.opt.gradient_clip)
+        optimizer.step()
+        return result
 
+    def run_generator_one_step(self, data):
+        self.g_losses, self.generated = self._optimize(data, 'generator', self.optimizer_G, self._bucket_G)
+
+    def run_discriminator_one_step(self, data):
+        self.d_losses = self._optimize(data, 'discriminator', self.optimizer_D, self._bucket_D)
+
+    # ---- accessors train.py uses ----------------------------------------------------------------------
     def preprocess_input(self, data):
         return super().preprocess(data, from_dataloader=True)
 
-    def run_generator_one_step(self, data):
-        """trainer_manager.py:32-46."""
-        self.optimizer_G.zero_grad()
-        data_preprocessed = self.preprocess_input(data)
-        g_losses, generated = self.sr_model(data_preprocessed, mode='generator')
-        g_loss = sum(g_losses.values()).mean()
-        g_loss.backward()
-        if self._bucket_G is not None:
-            self._bucket_G.allreduce_mean()
-        if self.opt.gradient_clip > 0:
-            clip_grad_value_(self.sr_model.parameters(), self.opt.gradient_clip)
-        self.optimizer_G.step()
-        self.g_losses = g_losses
-        self.generated = generated
-
-    def run_discriminator_one_step(self, data):
-        """trainer_manager.py:48-61."""
-        self.optimizer_D.zero_grad()
-        data_preprocessed = self.preprocess_input(data)
-        d_losses = self.sr_model(data_preprocessed, mode='discriminator')
-        d_loss = sum(d_losses.values()).mean()
-        d_loss.backward()
-        if self._bucket_D is not None:
-            self._bucket_D.allreduce_mean()
-        if self.opt.gradient_clip > 0:
-            clip_grad_value_(self.sr_model.parameters(), self.opt.gradient_clip)
-        self.optimizer_D.step()
-        self.d_losses = d_losses
+    def get_logs(self):
+        return {**self.logs, **self.sr_model_on_one_gpu.get_logs()}
 
     def get_latest_losses(self):
         return {**self.g_losses, **self.d_losses}
@@ -74,20 +69,16 @@ class TrainerManager(BaseManager):
             self.sr_model_on_one_gpu.save(epoch)
 
     def update_learning_rate(self, epoch):
-        """trainer_manager.py:76-99."""
-        if epoch > self.opt.niter:
-            lrd = self.opt.lr / self.opt.niter_decay
-            new_lr = self.old_lr - lrd
-        else:
-            new_lr = self.old_lr
-        if new_lr != self.old_lr:
-            if self.opt.no_TTUR:
-                new_lr_G, new_lr_D = new_lr, new_lr
-            else:
-                new_lr_G, new_lr_D = new_lr / 2, new_lr * 2
-            for param_group in self.optimizer_D.param_groups:
-                param_group['lr'] = new_lr_D
-            for param_group in self.optimizer_G.param_groups:
-                param_group['lr'] = new_lr_G
-            print('update learning rate: %f -> %f' % (self.old_lr, new_lr))
-            self.old_lr = new_lr
+        """trainer_manager.py:76-99: constant for `niter` epochs, then a linear decay by
+        lr / niter_decay per epoch; with TTUR the generator runs at half and the discriminator at
+        twice the base rate."""
+        decay = self.opt.lr / self.opt.niter_decay if epoch > self.opt.niter else 0.0
+        new_lr = self.old_lr - decay
+        if new_lr == self.old_lr:
+            return
+        g_scale, d_scale = (1.0, 1.0) if self.opt.no_TTUR else (0.5, 2.0)
+        for optimizer, scale in ((self.optimizer_G, g_scale), (self.optimizer_D, d_scale)):
+            for group in optimizer.param_groups:
+                group['lr'] = new_lr * scale
+        print('update learning rate: %f -> %f' % (self.old_lr, new_lr))
+        self.old_lr = new_lr

@@ -21,46 +21,45 @@ DEFAULTS = dict(
 )
 
 
-def get_config_independent(opt):
-    opt.netE = "combinedstyle"
-    opt.noisy_style_scale = 0.2
+# Presets keyed by what the model name contains (same rules as the reference's if/elif chain,
+# options/configurations.py:16-43).  A name needs one resolution preset and one variant preset.
+_RESOLUTION_PRESETS = (
+    (lambda n: "8x_" in n and "128x128" in n,
+     dict(start_size=16, crop_size=128, load_size=128, dataset="celeba", add_noise=True)),
+    (lambda n: "8x_" in n and "256x256" in n,
+     dict(start_size=32, crop_size=256, load_size=256, dataset="celebamaskhq", add_noise=True,
+          max_fm_size=256)),
+    (lambda n: "32x_" in n,
+     dict(start_size=16, crop_size=512, load_size=512, dataset="celebamaskhq", add_noise=False,
+          max_fm_size=256)),
+)
+_VARIANT_PRESETS = (
+    ("independent", dict(netE="combinedstyle", noisy_style_scale=0.2)),
+    ("guided", dict(netE="fullstyle", noisy_style_scale=0.05, guiding_style_image=True)),
+)
+
+
+def _apply(opt, fields):
+    for key, value in fields.items():
+        setattr(opt, key, value)
     return opt
+
+
+def get_config_independent(opt):
+    return _apply(opt, dict(_VARIANT_PRESETS)["independent"])
 
 
 def get_config_guided(opt):
-    opt.netE = "fullstyle"
-    opt.noisy_style_scale = 0.05
-    opt.guiding_style_image = True
-    return opt
+    return _apply(opt, dict(_VARIANT_PRESETS)["guided"])
 
 
 def get_opt_config(opt, name):
-    if "128x128" in name and "8x_" in name:
-        opt.start_size = 16
-        opt.crop_size, opt.load_size = 128, 128
-        opt.dataset = "celeba"
-        opt.add_noise = True
-    elif "256x256" in name and "8x_" in name:
-        opt.start_size = 32
-        opt.crop_size, opt.load_size = 256, 256
-        opt.dataset = "celebamaskhq"
-        opt.add_noise = True
-        opt.max_fm_size = 256
-    elif "32x_" in name:
-        opt.start_size = 16
-        opt.crop_size, opt.load_size = 512, 512
-        opt.dataset = "celebamaskhq"
-        opt.add_noise = False
-        opt.max_fm_size = 256
-    else:
+    """Fills `opt` from the presets a model name such as "8x_independent_256x256" selects."""
+    resolution = next((fields for matches, fields in _RESOLUTION_PRESETS if matches(name)), None)
+    variant = next((fields for key, fields in _VARIANT_PRESETS if key in name), None)
+    if resolution is None or variant is None:
         raise ValueError("Invalid name: '{}'. Please specify your options yourself.".format(name))
-    if "independent" in name:
-        opt = get_config_independent(opt)
-    elif "guided" in name:
-        opt = get_config_guided(opt)
-    else:
-        raise ValueError("Invalid name: '{}'. Please specify your options yourself.".format(name))
-    return opt
+    return _apply(_apply(opt, resolution), variant)
 
 
 def make_opt(name=None, **overrides):
