@@ -219,6 +219,63 @@ def enc_disc_case():
     np.savez_compressed(os.path.join(GOLD, "enc_disc_losses.npz"), **out)
 
 
+def trainer_case():
+    """One full training iteration (G step + D step, both Adam updates) through the reference's own
+    TrainerManager on CPU (managers/trainer_manager.py:32-61), against the oracle's CpuTrainer."""
+    from managers.trainer_manager import TrainerManager  # reference
+    o = O.make_opt("8x_independent_256x256", is_train=True, ngf=8, nef=8, ndf=8, start_size=8,
+                   crop_size=64, load_size=64, add_noise=False, noisy_style_scale=0.0)
+    ro = ref_opt(o)
+    sdG, sdE, sdD = O.make_generator_state(o, 0), O.make_encoder_state(o, 1), \
+        O.make_discriminator_state(o, 2)
+    clone = lambda sd: {k: v.clone() for k, v in sd.items()}
+    mgr = TrainerManager(ro)
+    model = mgr.sr_model_on_one_gpu
+    model.netSR.load_state_dict(clone(sdG), strict=True)
+    model.netE.load_state_dict(clone(sdE), strict=True)
+    model.netD.load_state_dict(clone(sdD), strict=True)
+    model.train()
+    raw = O.synthetic_batch(o, 2, seed=5)
+    batch = lambda: {"label": raw["label"].clone().float(), "image": raw["image"].clone()}
+    random.seed(0)
+    torch.manual_seed(0)
+    mgr.run_generator_one_step(batch())
+    mgr.run_discriminator_one_step(batch())
+    ref_losses = {k: float(v.detach().mean()) for k, v in mgr.get_latest_losses().items()}
+
+    tr = O.CpuTrainer(o, clone(sdG), clone(sdE), clone(sdD))
+    d = O.preprocess(o, raw)
+    torch.manual_seed(0)
+    g_l, _ = tr.generator_step(d)
+    d_l = tr.discriminator_step(d)
+    mine = {k: float(v.detach().mean()) for k, v in {**g_l, **d_l}.items()}
+    print("trainer losses reference", ref_losses, "oracle", mine)
+    for k in ref_losses:
+        assert abs(ref_losses[k] - mine[k]) < 2e-5 * max(1.0, abs(ref_losses[k])), k
+    out = {"weights_checksum": np.float64(checksum(sdG) + checksum(sdE) + checksum(sdD))}
+    for k, v in ref_losses.items():
+        out["loss_" + k] = np.float64(v)
+    # parameters after both Adam steps (Adam's first step moves every touched weight by ~lr, so
+    # these pin the sign pattern of the gradients as well as the optimizer settings)
+    probes = {"G": (model.netSR.state_dict(), tr.sdG, ["conv_img.bias", "head_0.conv_1.weight_orig",
+                                                        "up_list.1.norm_1.mlp_gamma.bias",
+                                                        "G_middle_0.norm_0.alpha_gamma"]),
+              "E": (model.netE.state_dict(), tr.sdE, ["final.0.0.bias", "encoder_mini.conv0.0.0.weight_orig"]),
+              "D": (model.netD.state_dict(), tr.sdD, ["discriminator_0.model0.0.bias",
+                                                        "discriminator_1.model2.0.0.weight_orig"])}
+    for net, (ref_sd, my_sd, keys) in probes.items():
+        for k in keys:
+            if k not in ref_sd:
+                continue
+            a, b = ref_sd[k].detach().flatten()[:64], my_sd[k].detach().flatten()[:64]
+            err = (a - b).abs().max().item()
+            print("  %s.%s max-abs after the iteration %.2e" % (net, k, err))
+            assert err < 2e-6
+            out["param_%s.%s" % (net, k)] = t2n(a)
+    np.savez_compressed(os.path.join(GOLD, "train_iteration.npz"), **out)
+    print("training-iteration golden ok")
+
+
 def label_case():
     o = O.make_opt("8x_independent_256x256")
     ro = ref_opt(o)
@@ -244,9 +301,13 @@ def label_case():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "trainer":   # add this one golden without touching the others
+        trainer_case()
+        sys.exit(0)
     label_case()
     gen_case("g8x_eval", CASES["g8x_eval"])
     gen_case("g32x_eval", CASES["g32x_eval"])
     gen_case("g8x_train", CASES["g8x_train"], train=True)
     enc_disc_case()
+    trainer_case()
     print("goldens written to", GOLD)

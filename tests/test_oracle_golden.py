@@ -128,3 +128,30 @@ def test_generator_layouts():
     lay = O.generator_layout(o)
     assert [b[1] for b in lay] == ["spade", "sean", "sean", "sean", "sean", "sean", "puresean"]
     assert [b[2] for b in lay] == [False, True, False, True, True, True, True]
+
+
+def test_cpu_trainer_vs_reference_training_iteration():
+    """The oracle's CpuTrainer (restatement of trainer_manager.py:32-61 + sr_model.py:469-564) against
+    a golden written by the reference's own TrainerManager on CPU: the four losses of one G step + one D
+    step and a probe of parameters of all three networks after both Adam updates."""
+    g = np.load(os.path.join(GOLD, "train_iteration.npz"))
+    o = O.make_opt("8x_independent_256x256", is_train=True, ngf=8, nef=8, ndf=8, start_size=8,
+                   crop_size=64, load_size=64, add_noise=False, noisy_style_scale=0.0)
+    sdG, sdE, sdD = O.make_generator_state(o, 0), O.make_encoder_state(o, 1), O.make_discriminator_state(o, 2)
+    cs = sum(float(v.double().abs().sum()) for sd in (sdG, sdE, sdD) for v in sd.values())
+    assert abs(cs - float(g["weights_checksum"])) < 1e-6 * cs, "seeded weights drifted (torch RNG changed?)"
+    tr = O.CpuTrainer(o, sdG, sdE, sdD)
+    d = O.preprocess(o, O.synthetic_batch(o, 2, seed=5))
+    torch.manual_seed(0)
+    g_l, _ = tr.generator_step(d)
+    d_l = tr.discriminator_step(d)
+    for k, v in {**g_l, **d_l}.items():
+        ref = float(g["loss_" + k])
+        assert abs(float(v.detach().mean()) - ref) < 2e-5 * max(1.0, abs(ref)), (k, float(v.detach().mean()), ref)
+    probes = [k for k in g.files if k.startswith("param_")]
+    assert len(probes) >= 6
+    for k in probes:
+        net, key = k[len("param_"):].split(".", 1)
+        sd = {"G": tr.sdG, "E": tr.sdE, "D": tr.sdD}[net]
+        got = sd[key].detach().flatten()[:64].numpy()
+        assert np.abs(got - g[k]).max() < 2e-6, k
