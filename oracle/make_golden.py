@@ -219,12 +219,21 @@ def enc_disc_case():
     np.savez_compressed(os.path.join(GOLD, "enc_disc_losses.npz"), **out)
 
 
-def trainer_case():
+TRAINER_CASES = {
+    "train_iteration": ("8x_independent_256x256", dict(ngf=8, nef=8, ndf=8, start_size=8, crop_size=64,
+                                                       load_size=64)),
+    # guided model (style encoder on the HR guiding image), PureSEAN tail + max_fm_size quirk
+    "train_iteration_guided": ("32x_guided_512x512", dict(ngf=8, nef=8, ndf=8, start_size=4, crop_size=128,
+                                                          load_size=512, max_fm_size=64)),
+}
+
+
+def trainer_case(tag="train_iteration"):
     """One full training iteration (G step + D step, both Adam updates) through the reference's own
     TrainerManager on CPU (managers/trainer_manager.py:32-61), against the oracle's CpuTrainer."""
     from managers.trainer_manager import TrainerManager  # reference
-    o = O.make_opt("8x_independent_256x256", is_train=True, ngf=8, nef=8, ndf=8, start_size=8,
-                   crop_size=64, load_size=64, add_noise=False, noisy_style_scale=0.0)
+    name, over = TRAINER_CASES[tag]
+    o = O.make_opt(name, is_train=True, add_noise=False, noisy_style_scale=0.0, **over)
     ro = ref_opt(o)
     sdG, sdE, sdD = O.make_generator_state(o, 0), O.make_encoder_state(o, 1), \
         O.make_discriminator_state(o, 2)
@@ -236,7 +245,7 @@ def trainer_case():
     model.netD.load_state_dict(clone(sdD), strict=True)
     model.train()
     raw = O.synthetic_batch(o, 2, seed=5)
-    batch = lambda: {"label": raw["label"].clone().float(), "image": raw["image"].clone()}
+    batch = lambda: {k: (v.clone().float() if "label" in k else v.clone()) for k, v in raw.items()}
     random.seed(0)
     torch.manual_seed(0)
     mgr.run_generator_one_step(batch())
@@ -260,7 +269,8 @@ def trainer_case():
     probes = {"G": (model.netSR.state_dict(), tr.sdG, ["conv_img.bias", "head_0.conv_1.weight_orig",
                                                         "up_list.1.norm_1.mlp_gamma.bias",
                                                         "G_middle_0.norm_0.alpha_gamma"]),
-              "E": (model.netE.state_dict(), tr.sdE, ["final.0.0.bias", "encoder_mini.conv0.0.0.weight_orig"]),
+              "E": (model.netE.state_dict(), tr.sdE, ["encoder_mini.conv0.0.0.weight_orig", "down0.0.0.weight_orig",
+                                                        "final.0.0.weight_orig"]),
               "D": (model.netD.state_dict(), tr.sdD, ["discriminator_0.model0.0.bias",
                                                         "discriminator_1.model2.0.0.weight_orig"])}
     for net, (ref_sd, my_sd, keys) in probes.items():
@@ -272,8 +282,8 @@ def trainer_case():
             print("  %s.%s max-abs after the iteration %.2e" % (net, k, err))
             assert err < 2e-6
             out["param_%s.%s" % (net, k)] = t2n(a)
-    np.savez_compressed(os.path.join(GOLD, "train_iteration.npz"), **out)
-    print("training-iteration golden ok")
+    np.savez_compressed(os.path.join(GOLD, tag + ".npz"), **out)
+    print("training-iteration golden ok:", tag)
 
 
 def label_case():
@@ -301,13 +311,15 @@ def label_case():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    if len(sys.argv) > 1 and sys.argv[1] == "trainer":   # add this one golden without touching the others
-        trainer_case()
+    if len(sys.argv) > 1 and sys.argv[1] == "trainer":   # add these goldens without touching the others
+        for tag in TRAINER_CASES:
+            trainer_case(tag)
         sys.exit(0)
     label_case()
     gen_case("g8x_eval", CASES["g8x_eval"])
     gen_case("g32x_eval", CASES["g32x_eval"])
     gen_case("g8x_train", CASES["g8x_train"], train=True)
     enc_disc_case()
-    trainer_case()
+    for tag in TRAINER_CASES:
+        trainer_case(tag)
     print("goldens written to", GOLD)

@@ -130,13 +130,23 @@ def test_generator_layouts():
     assert [b[2] for b in lay] == [False, True, False, True, True, True, True]
 
 
-def test_cpu_trainer_vs_reference_training_iteration():
+TRAINER_CASES = {
+    "train_iteration": ("8x_independent_256x256", dict(ngf=8, nef=8, ndf=8, start_size=8, crop_size=64,
+                                                       load_size=64)),
+    "train_iteration_guided": ("32x_guided_512x512", dict(ngf=8, nef=8, ndf=8, start_size=4, crop_size=128,
+                                                          load_size=512, max_fm_size=64)),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(TRAINER_CASES))
+def test_cpu_trainer_vs_reference_training_iteration(tag):
     """The oracle's CpuTrainer (restatement of trainer_manager.py:32-61 + sr_model.py:469-564) against
-    a golden written by the reference's own TrainerManager on CPU: the four losses of one G step + one D
-    step and a probe of parameters of all three networks after both Adam updates."""
-    g = np.load(os.path.join(GOLD, "train_iteration.npz"))
-    o = O.make_opt("8x_independent_256x256", is_train=True, ngf=8, nef=8, ndf=8, start_size=8,
-                   crop_size=64, load_size=64, add_noise=False, noisy_style_scale=0.0)
+    goldens written by the reference's own TrainerManager on CPU: the four losses of one G step + one D
+    step and probes of parameters of all three networks after both Adam updates, for the independent
+    8x preset and for the guided 32x preset (PureSEAN tail, style encoder on the guiding image)."""
+    g = np.load(os.path.join(GOLD, tag + ".npz"))
+    name, over = TRAINER_CASES[tag]
+    o = O.make_opt(name, is_train=True, add_noise=False, noisy_style_scale=0.0, **over)
     sdG, sdE, sdD = O.make_generator_state(o, 0), O.make_encoder_state(o, 1), O.make_discriminator_state(o, 2)
     cs = sum(float(v.double().abs().sum()) for sd in (sdG, sdE, sdD) for v in sd.values())
     assert abs(cs - float(g["weights_checksum"])) < 1e-6 * cs, "seeded weights drifted (torch RNG changed?)"
