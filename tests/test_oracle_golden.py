@@ -165,3 +165,37 @@ def test_cpu_trainer_vs_reference_training_iteration(tag):
         sd = {"G": tr.sdG, "E": tr.sdE, "D": tr.sdD}[net]
         got = sd[key].detach().flatten()[:64].numpy()
         assert np.abs(got - g[k]).max() < 2e-6, k
+
+
+def test_param_free_bn_known_answers_of_the_reference_sync_bn_tests():
+    """The only numerics the reference's own tests pin on this path are the vendored Sync-BN unit tests
+    (Synchronized-BatchNorm-PyTorch/tests/test_numeric_batchnorm.py:30-52, test_sync_batchnorm.py:79-107):
+    batch norm in the sum / sum-of-squares formulation equals nn.BatchNorm - output, input gradient,
+    running mean and UNBIASED running variance - on rand(16, 10[, 16, 16]).  Same check for the oracle's
+    param_free_bn (affine=False, eps 1e-5, momentum 0.1), with torch.allclose defaults like the
+    reference's assertTensorClose."""
+    torch.manual_seed(0)
+    x = torch.rand(16, 10, 16, 16)
+    sd = {"bn.running_mean": torch.zeros(10), "bn.running_var": torch.ones(10),
+          "bn.num_batches_tracked": torch.zeros((), dtype=torch.long)}
+    a = x.clone().requires_grad_(True)
+    y = O.param_free_bn(a, sd, "bn.", True)
+    y.sum().backward()
+
+    b = x.clone().requires_grad_(True)
+    n = b.numel() // b.shape[1]
+    s1 = b.sum(dim=(0, 2, 3))
+    s2 = (b * b).sum(dim=(0, 2, 3))
+    mean = s1 / n
+    sumvar = s2 - s1 * mean                       # handy_var of the reference tests
+    std = torch.sqrt((sumvar / n).clamp(min=1e-5) + 0)  # bias var; eps enters as in batchnorm.py:87-93
+    y2 = (b - mean.view(1, -1, 1, 1)) / torch.sqrt(sumvar.view(1, -1, 1, 1) / n + 1e-5)
+    y2.sum().backward()
+    assert torch.allclose(y, y2, atol=1e-5) and torch.allclose(a.grad, b.grad, atol=1e-5)
+    assert torch.allclose(sd["bn.running_mean"], 0.1 * mean.detach())
+    assert torch.allclose(sd["bn.running_var"], 0.9 * torch.ones(10) + 0.1 * (sumvar / (n - 1)).detach())
+    assert int(sd["bn.num_batches_tracked"]) == 1 and std.min() > 0
+    # eval mode uses the running statistics
+    z = O.param_free_bn(x, sd, "bn.", False)
+    ref = (x - sd["bn.running_mean"].view(1, -1, 1, 1)) / torch.sqrt(sd["bn.running_var"].view(1, -1, 1, 1) + 1e-5)
+    assert torch.allclose(z, ref, atol=1e-6)
