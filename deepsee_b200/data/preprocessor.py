@@ -1,5 +1,4 @@
 """Input preprocessing (reference: data/preprocessor.py:5-41)."""
-import torch
 import torch.nn.functional as F
 
 from .. import ops

@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from ... import ops
 from .base_network import BaseNetwork
-from .encoder import _khwc
+
 from .normalization import get_nonspade_norm_layer, effective_weight, spectral_prepass
 
 

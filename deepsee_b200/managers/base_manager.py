@@ -6,7 +6,6 @@ WORLD_SIZE); the model is a plain SRModel on the local device and the managers a
 G and D gradients over NCCL (see ..parallel).  `sr_model` and `sr_model_on_one_gpu` are the same
 object, which is what the reference exposes when it does not wrap.
 """
-import torch
 
 from ..data.preprocessor import Preprocessor
 from ..deepsee_models.sr_model import SRModel
