@@ -36,10 +36,32 @@ def _worker(rank, world, port, q):
             p.grad = torch.full_like(p, 4.0)
     bucket = parallel.GradBucket(list(net.parameters()))
     bucket.allreduce_mean()
+    # after the reduction every .grad IS a view of the flat bucket (no copy back)
+    views_ok = all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+    # Sync-BN mode: batch-norm backward's two reductions are summed over ranks, the parameter-gradient
+    # rows stay local (deepsee_models/networks/architecture.py:_sync_bwd_sums)
+    from deepsee_b200.config import config
+    from deepsee_b200.deepsee_models.networks import architecture as arch
+    nsums = torch.arange(12, dtype=torch.float32).view(4, 3) + 100 * rank
+
+    class _St:
+        inv_count = 0.25
+    config.sync_bn = False
+    local = arch._sync_bwd_sums(nsums, _St)
+    config.sync_bn = True
+    synced = arch._sync_bwd_sums(nsums, _St)
+    _St.inv_count = 0.0                                # eval-mode statistics: nothing to synchronise
+    evalmode = arch._sync_bwd_sums(nsums, _St)
+    config.sync_bn = False
+    sync_ok = (local is nsums and evalmode is nsums and
+               torch.equal(synced[:2], 2 * torch.arange(6, dtype=torch.float32).view(2, 3) + 100) and
+               torch.equal(synced[2:], nsums[2:]))
+    stat = parallel.allreduce_sum_(torch.full((2, 4), float(rank + 1)))
+    sync_ok = sync_ok and torch.equal(stat, torch.full((2, 4), 3.0))
     parallel.seed_python_random(0)
     flips = [random.random() for _ in range(3)]
     q.put((rank, w0, net[0].weight.grad.clone(), net[1].weight.grad.clone(), net.running.clone(), flips,
-           bucket.nbytes()))
+           bucket.nbytes(), views_ok, sync_ok))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -56,7 +78,9 @@ def test_grad_bucket_allreduce_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (_, w_a, g0_a, g1_a, run_a, flips_a, nb), (_, w_b, g0_b, g1_b, run_b, flips_b, _) = res
+    (_, w_a, g0_a, g1_a, run_a, flips_a, nb, va, sa), (_, w_b, g0_b, g1_b, run_b, flips_b, _, vb, sb) = res
+    assert va and vb, "gradients are not views of the reduced bucket"
+    assert sa and sb, "Sync-BN statistics all-reduce"
     assert torch.equal(w_a, w_b)                        # broadcast from rank 0
     assert torch.equal(run_a, run_b) and float(run_a[0]) == 0.0   # buffers too
     assert torch.allclose(g0_a, torch.full_like(g0_a, 1.5)) and torch.equal(g0_a, g0_b)   # mean(1, 2)
