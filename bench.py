@@ -130,6 +130,66 @@ def run_reference(args):
     }))
 
 
+def kernel_traffic(tag, cfg_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of a kernel group inside the timed
+    step, from the committed `ncu --set full` capture (profiles/r2_kernel_traffic.csv: tag, config,
+    read bytes, written bytes, source).  None when that launch group has not been captured."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r2_kernel_traffic.csv")
+    if not os.path.exists(p):
+        return None, None
+    for row in csv.DictReader(open(p)):
+        if row["tag"] == tag and row["config"] == cfg_key:
+            return float(row["dram_read_bytes"]) + float(row["dram_write_bytes"]), row["source"]
+    return None, None
+
+
+def parity_leg(cfg):
+    """One batch-1 generator forward of THIS configuration's full-size generator in THIS run's
+    precision mode, train mode (batch statistics, noise injection), against the CPU oracle on the
+    same conditioned weights / inputs / noise tensors -> max-abs on the tanh output.  Checker only:
+    runs after the timed regions, on rank 0, next to the cpu_baseline leg."""
+    import torch
+    from oracle import deepsee_oracle as O
+    from deepsee_b200.options.configurations import make_opt
+    from deepsee_b200.deepsee_models.networks.sr import DeepSEESR
+    o = O.make_opt(cfg["name"], is_train=True)
+    sd = O.make_generator_state(o, 0)
+    d = O.preprocess(o, O.synthetic_batch(o, 1, seed=70))
+    z = torch.rand(1, 19, 128, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    noises = {}
+
+    def noise_fn(nm, shape):
+        noises[nm] = torch.randn(shape, generator=torch.Generator().manual_seed(len(noises)))
+        return noises[nm]
+
+    with torch.no_grad():
+        ref = O.generator_forward({k: v.clone() for k, v in sd.items()}, o, d["image_lr"],
+                                  d["input_semantics"], z, True, noise_fn)
+    od = dict(o)
+    name = od.pop("name")
+    opt = make_opt(None, **od)
+    opt.name = name
+    G = DeepSEESR(opt).cuda()
+    G.load_state_dict(sd, strict=True)
+    G.train()
+    if o.add_noise:
+        for pfx, _, _ in O.generator_layout(o):
+            blk = G.get_submodule(pfx[:-1])
+            for nm in ("noise_in", "noise_skip", "noise_middle"):
+                n = noises[pfx + nm].permute(0, 2, 3, 1).contiguous().cuda()
+                getattr(blk, nm).sample = (lambda t: (lambda B, H, W: t))(n)
+    with torch.no_grad():
+        out = G(d["image_lr"].cuda(), seg=d["input_semantics"].cuda(), z=z.cuda())
+    e = (out.cpu() - ref).abs()
+    return {"max_abs": e.max().item(), "mean_abs": e.mean().item(), "ref_std": ref.std().item(),
+            "max_abs_over_std": e.max().item() / ref.std().item(), "tolerance": 1e-3,
+            "within_tolerance": bool(e.max().item() < 1e-3),
+            "what": "full-size %s generator, batch 1, train mode (batch statistics, noise injection), this "
+                    "run's precision mode vs the CPU oracle on conditioned weights; asserted at this shape "
+                    "by tests/test_full_size_parity_gpu.py" % cfg["name"]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -137,10 +197,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch of the headline config")
     ap.add_argument("--passes", type=int, default=None)
+    ap.add_argument("--passes3-upto", default=None,
+                    help="main convs up to this feature-map height run 3 passes (default 'auto' = output/4; 0 = off)")
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the `configs` block (c4 weak + strong, c5) measured after the headline config")
+    ap.add_argument("--extra-steps", type=int, default=5)
     ap.add_argument("--cprofile", default=None,
                     help="write a cProfile table (main thread: forward passes, optimizers) of 3 extra steps to this file")
     ap.add_argument("--torch-profile", default=None,
@@ -153,148 +219,191 @@ def main():
     # builds the model (e.g. SRModel.create_optimizers' "lr G: ..." line, sr_model.py:486) goes to stderr
     real_stdout, sys.stdout = sys.stdout, sys.stderr
 
+    import gc
     import torch
     import torch.distributed as dist
-    # this arm touches the product only; oracle/ is imported by the cpu_baseline leg alone (below)
+    # this arm touches the product only; oracle/ is imported by the cpu_baseline / parity legs alone
     from deepsee_b200 import _lib, ops, parallel
     from deepsee_b200.config import config
     from deepsee_b200.managers.trainer_manager import TrainerManager
     from deepsee_b200.options.configurations import make_opt
     from deepsee_b200.util.synthetic import synthetic_batch, settle_spectral_norm
 
-    # Default precision of the measured step: 1 pass = fp16 operands with fp32 accumulation, the
-    # TF32 class (10-bit mantissa) that stock PyTorch/cuDNN runs the reference's convs in on this GPU;
-    # tests/test_generator_gpu.py pins it inside north_star's 1e-3 max-abs bound.  --passes 3 measures
-    # the fp32-class split-operand mode (the library default, DSEE_PASSES).
+    # Precision of the measured step: 1 pass = fp16 operands with fp32 accumulation (the TF32 class,
+    # 10-bit mantissa, that stock PyTorch/cuDNN runs the reference's convs in on this GPU), with the
+    # main convs of the low-resolution stages (<= output/4, ~5 % of the FLOPs) at 3 passes: the cheapest
+    # mode that keeps the full-size generators inside north_star's 1e-3 max-abs bound
+    # (tests/test_full_size_parity_gpu.py; `parity` below is measured by this very run).
+    # --passes 3 measures the fp32-class split-operand mode (the library default, DSEE_PASSES).
     config.passes = args.passes or 1
+    if args.passes3_upto is not None:
+        config.passes3_upto = args.passes3_upto if args.passes3_upto == "auto" else int(args.passes3_upto)
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     parallel.init_from_env()
-    cfg = CONFIGS[args.config]
-    b = cfg["batch"]
-    torch.manual_seed(0)                         # same random-init weights on every rank
-    o = make_opt(cfg["name"], isTrain=True, gpu_ids=[local], batchSize=b)
-    mgr = TrainerManager(o)                      # random-init weights of the named architecture
-    model = mgr.sr_model
-    for net in (model.netSR, model.netE, model.netD):
-        settle_spectral_norm(net)
-    with torch.no_grad():                        # NoiseInjection.weight is zero-initialised (normalization.py:297)
-        for n_, p_ in model.netSR.named_parameters():
-            if ".noise_" in n_:
-                p_.fill_(0.1)
-    parallel.broadcast_module(model)
     train = args.mode == "train"
-    model.train(train)
-    torch.manual_seed(1234 + rank)               # NoiseInjection seeds differ per rank
-
-    raw = synthetic_batch(o, b, seed=1234 + rank)
-    host = {k: (v.float() if "label" in k else v).pin_memory() for k, v in raw.items()}
-    dev = {k: v.cuda() for k, v in host.items()}
-    torch.cuda.synchronize()
-
-    def iteration(data):
-        if train:
-            mgr.run_generator_one_step(dict(data))
-            mgr.run_discriminator_one_step(dict(data))
-            return mgr.get_latest_losses()
-        with torch.no_grad():
-            d = mgr.preprocess(dict(data), from_dataloader=True)
-            out = model(d, "inference")
-            pf, _ = model.discriminate(d["input_semantics"], out["fake_image"], d["image_hr"])
-        return {"pred": pf[0][-1].mean()}
-
-    def e2e_iteration():
-        losses = iteration(host)
-        return {k: float(v.detach().mean()) for k, v in losses.items()}  # D2H read of the step's result
+    sust, burst, hbm, how = peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # The raw batch (b x 4 x S x S fp32) plus every activation of the step (several GB) exceed the
-    # 126 MB L2 many times over, so successive iterations cannot hit in L2; no explicit flush.
-    for _ in range(args.warmup):
-        iteration(dev)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    n0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.profiler.start()  # `ncu --profile-from-start off` captures exactly the timed region
-    with ops.KernelTimer() as kt:
-        e0.record()
-        for _ in range(args.steps):
-            iteration(dev)
-        e1.record()
-        barrier()
-    torch.cuda.profiler.stop()
-    launches = _lib.launch_count() - n0
-    ms = e0.elapsed_time(e1)
-    ksum = kt.summary()
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    def max_over_ranks(v):
+        if world > 1:
+            t = torch.tensor([v], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return v
 
-    if args.torch_profile and rank == 0:
-        from torch.profiler import profile, ProfilerActivity
-        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-            t0 = time.perf_counter()
-            for _ in range(2):
+    def measure(cfg_key, b, steps, warmup, headline):
+        """Builds the named model, runs `warmup` + `steps` training iterations on a per-GPU batch of
+        b device-resident samples (CUDA events, max over ranks), then the same through pinned HOST
+        buffers (e2e).  Returns the result dict."""
+        cfg = CONFIGS[cfg_key]
+        torch.manual_seed(0)                         # same random-init weights on every rank
+        o = make_opt(cfg["name"], isTrain=True, gpu_ids=[local], batchSize=b)
+        mgr = TrainerManager(o)                      # random-init weights of the named architecture
+        model = mgr.sr_model
+        for net in (model.netSR, model.netE, model.netD):
+            settle_spectral_norm(net)
+        with torch.no_grad():                        # NoiseInjection.weight is zero-initialised (normalization.py:297)
+            for n_, p_ in model.netSR.named_parameters():
+                if ".noise_" in n_:
+                    p_.fill_(0.1)
+        parallel.broadcast_module(model)
+        model.train(train)
+        torch.manual_seed(1234 + rank)               # NoiseInjection seeds differ per rank
+        raw = synthetic_batch(o, b, seed=1234 + rank)
+        host = {k: (v.float() if "label" in k else v).pin_memory() for k, v in raw.items()}
+        dev = {k: v.cuda() for k, v in host.items()}
+        torch.cuda.synchronize()
+
+        def iteration(data):
+            if train:
+                mgr.run_generator_one_step(dict(data))
+                mgr.run_discriminator_one_step(dict(data))
+                return mgr.get_latest_losses()
+            with torch.no_grad():
+                d = mgr.preprocess(dict(data), from_dataloader=True)
+                out = model(d, "inference")
+                pf, _ = model.discriminate(d["input_semantics"], out["fake_image"], d["image_hr"])
+            return {"pred": pf[0][-1].mean()}
+
+        def e2e_iteration():
+            losses = iteration(host)
+            return {k: float(v.detach().mean()) for k, v in losses.items()}  # D2H read of the step's result
+
+        # The raw batch (b x 4 x S x S fp32) plus every activation of the step (several GB) exceed the
+        # 126 MB L2 many times over, so successive iterations cannot hit in L2; no explicit flush.
+        for _ in range(warmup):
+            iteration(dev)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0 and headline:
+            sampler.start()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if headline:
+            torch.cuda.profiler.start()  # `ncu --profile-from-start off` captures exactly the timed region
+        with ops.KernelTimer() as kt:
+            e0.record()
+            for _ in range(steps):
+                iteration(dev)
+            e1.record()
+            barrier()
+        if headline:
+            torch.cuda.profiler.stop()
+        launches = _lib.launch_count() - n0
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        ksum = kt.summary()
+        clocks = sampler.result() if (rank == 0 and headline) else None
+
+        if headline and args.torch_profile and rank == 0:
+            from torch.profiler import profile, ProfilerActivity
+            with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    iteration(dev)
+                torch.cuda.synchronize()
+                wall = time.perf_counter() - t0
+            with open(args.torch_profile, "w") as f:
+                f.write("2 steps under the profiler: %.1f ms wall\n" % (wall * 1000))
+                f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=90,
+                                                  max_name_column_width=70))
+        if headline and args.cprofile and rank == 0:
+            import cProfile
+            import io
+            import pstats
+            pr = cProfile.Profile()
+            pr.enable()
+            for _ in range(3):
                 iteration(dev)
             torch.cuda.synchronize()
-            wall = time.perf_counter() - t0
-        with open(args.torch_profile, "w") as f:
-            f.write("2 steps under the profiler: %.1f ms wall\n" % (wall * 1000))
-            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=70,
-                                              max_name_column_width=70))
-    if args.cprofile and rank == 0:
-        import cProfile
-        import io
-        import pstats
-        pr = cProfile.Profile()
-        pr.enable()
-        for _ in range(3):
-            iteration(dev)
-        torch.cuda.synchronize()
-        pr.disable()
-        buf = io.StringIO()
-        pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(70)
-        pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(45)
-        open(args.cprofile, "w").write(buf.getvalue())
-    e2e = None
-    if not args.no_e2e:
-        for _ in range(2):
-            e2e_iteration()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            last = e2e_iteration()
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([e2e_s], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        e2e = {"value": b * world * args.steps / e2e_s, "unit": "images/sec",
-               "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())) * (2 if train else 1),
-               "d2h_bytes_per_step": 4 * len(last), "last_losses": last}
-    sampler.stop_flag = True
-    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+            pr.disable()
+            buf = io.StringIO()
+            pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(70)
+            pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(45)
+            open(args.cprofile, "w").write(buf.getvalue())
+        e2e = None
+        if not args.no_e2e:
+            for _ in range(2):
+                e2e_iteration()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                last = e2e_iteration()
+            torch.cuda.synchronize()
+            e2e_s = max_over_ranks(time.perf_counter() - t0)
+            e2e = {"value": b * world * steps / e2e_s, "unit": "images/sec",
+                   "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())) * (2 if train else 1),
+                   "d2h_bytes_per_step": 4 * len(last), "last_losses": last}
+        peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+        S = o.crop_size
+        sync_bn = bool(world > 1 and config.sync_bn_for(o.norm_G))
+        del mgr, model, dev, host, raw
+        gc.collect()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        value = b * world * steps / (ms / 1000.0)
+        flops_per_img = cfg["train_flops"] if train else cfg["fwd_flops"]
+        return dict(cfg=cfg, b=b, S=S, steps=steps, ms=ms, value=value, ksum=ksum, launches=launches,
+                    clocks=clocks, e2e=e2e, peak_mem=peak_mem, sync_bn=sync_bn,
+                    whole_step={"algorithmic_tflops_per_gpu": value / world * flops_per_img / 1e12,
+                                "frac_of_peak": value / world * flops_per_img / 1e12 / sust})
+
+    b0 = args.batch or CONFIGS[args.config]["batch"]
+    R = measure(args.config, b0, args.steps, args.warmup, True)
+
+    # ---- the other BASELINE.json configurations, each with img/s, ms/step, whole-step fraction, e2e
+    extras = []
+    if train and not args.no_extra and args.config == "c2" and args.batch is None:
+        plan = [("c4", 2, "weak", "BASELINE config 4 (32x 512x512 independent, 2 images per GPU: batch 8 on 4 GPUs)"),
+                ("c5", 4, "weak", "BASELINE config 5 (32x 512x512 guided, 4 images per GPU: batch 32 on 8 GPUs)")]
+        if 8 % world == 0:
+            plan.insert(1, ("c4", 8 // world, "strong",
+                            "32x 512x512 independent, GLOBAL batch 8 split over the GPUs (north_star's >= 6x at 8 GPUs "
+                            "target, strong-scaling reading)"))
+        for key, b, scaling, what in plan:
+            r = measure(key, b, args.extra_steps, 3, False)
+            extras.append({
+                "config": key, "name": r["cfg"]["name"], "what": what, "scaling": scaling,
+                "per_gpu_batch": b, "global_batch": b * world, "n_gpus": world, "image": "%dx%d" % (r["S"], r["S"]),
+                "value": r["value"], "unit": "images/sec", "ms_per_step": r["ms"] / r["steps"], "steps": r["steps"],
+                "warmup": 3, "whole_step": r["whole_step"],
+                "e2e": {k: v for k, v in r["e2e"].items() if k != "last_losses"} if r["e2e"] else None,
+                "tc_share_of_step": sum(v[1] for v in r["ksum"].values()) / r["ms"],
+                "sync_bn": r["sync_bn"], "peak_mem_gib": round(r["peak_mem"], 2),
+            })
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
 
-    S = o.crop_size
-    imgs = b * world * args.steps
-    value = imgs / (ms / 1000.0)
-    sust, burst, hbm, how = peaks()
+    cfg, b, S, ms, value, ksum = R["cfg"], R["b"], R["S"], R["ms"], R["value"], R["ksum"]
     # tensor-core launches by family (CUDA events on the launching stream around each launch)
     fam = {}
     for tag, (n, t_ms, fl) in ksum.items():
@@ -307,46 +416,43 @@ def main():
     tot_fl = sum(v[2] for v in ksum.values())
     top = max(ksum.items(), key=lambda kv: kv[1][1])
     top_tflops = top[1][2] / (top[1][1] / 1000.0) / 1e12
-    flops_per_img = cfg["train_flops"] if train else cfg["fwd_flops"]
+    traffic, traffic_src = kernel_traffic(top[0], args.config)
     roofline = {
         "bound": "tensor", "kernel": "tcgen05 implicit-GEMM family; dominant launch group: %s" % top[0],
         "achieved": top_tflops, "peak": sust, "unit": "TFLOP/s", "frac": top_tflops / sust,
         "peak_source": "%s: bf16 dense sustained; kind::f16 operands run on the same pipe at the same rate" % how,
         "executed_passes": config.passes,
-        "executed_frac": top_tflops * config.passes / sust,
         "all_tc_launches": {"achieved": tot_fl / (tot_ms / 1000.0) / 1e12, "share_of_step": tot_ms / ms,
                             "launches_per_step": sum(v[0] for v in ksum.values()) / args.steps},
         "by_family": {f: {"launches_per_step": a[0] / args.steps, "ms_per_step": a[1] / args.steps,
                           "tflops": a[2] / (a[1] / 1000.0) / 1e12} for f, a in sorted(fam.items())},
         "by_launch_group": {t: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,
                                 "tflops": v[2] / (v[1] / 1000.0) / 1e12} for t, v in sorted(ksum.items())},
-        "whole_step": {"algorithmic_tflops_per_gpu": value / world * flops_per_img / 1e12,
-                       "frac_of_peak": value / world * flops_per_img / 1e12 / sust},
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (K2, 512->512
-        # at 256x256, batch 8) from the committed `ncu --set full` capture; algorithmic = fp16 activation
-        # planes + fp32 shortcut + fp32 output + weights = 2.42 GB
-        "traffic": 2.73e9 if (args.config in ("c2", "c3") and train) else None,
-        "traffic_source": "profiles/r1_kernels_ncu_full_selected.csv (conv3x3_tc_kernel<0>, first row)",
+        "whole_step": R["whole_step"],
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE in-step launch of the dominant launch group,
+        # looked up in the committed ncu --set full summary (null if that group was not captured)
+        "traffic": traffic, "traffic_source": traffic_src,
     }
     line = {
         "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": ("fp16 hi+lo split operands x3 passes, fp32 accumulate (fp32-class)" if config.passes == 3
-                  else "fp16 operands, fp32 accumulate (TF32-class: what stock PyTorch/cuDNN runs these convs in)"),
+        "dtype": config.precision_name(),
         "data": "synthetic",
         "config": {"workload": WORKLOAD % (cfg["name"], b, ", NCCL all-reduce of G+E and D gradients" if world > 1 else "")
                    if train else "%s, batch %d per GPU, inference forward (encoder + generator + discriminator)" % (cfg["name"], b),
                    "global_batch": b * world, "image": "%dx%d" % (S, S), "parallelism": "dp%d" % world,
                    "l2": "inputs and activations larger than L2, no flush", "passes": config.passes,
-                   "mode": args.mode},
-        "gpu_launches": launches,
-        "clocks": sampler.result(),
-        "e2e": e2e,
+                   "passes3_upto": config.passes3_upto, "sync_bn": R["sync_bn"], "mode": args.mode},
+        "gpu_launches": R["launches"],
+        "clocks": R["clocks"],
+        "e2e": R["e2e"],
         "roofline": roofline,
-        "peak_mem_gib": round(peak_mem, 2),
+        "peak_mem_gib": round(R["peak_mem"], 2),
     }
-    if not args.no_cpu_baseline and train:
+    if extras:
+        line["configs"] = extras
+    if not args.no_cpu_baseline and train and world == 1:
         cores = os.cpu_count()
         step = cpu_train_iteration_timer(cfg, cores)
         t0 = time.perf_counter()
@@ -358,6 +464,7 @@ def main():
         line["cpu_baseline"] = {"value": n / dt, "unit": "images/sec", "cores": cores, "kind": "port",
                                 "sample": "%d training iteration(s) at batch 1 of the same workload "
                                           "(oracle port of trainer_manager.py:32-61, torch CPU fp32)" % n}
+        line["parity"] = parity_leg(cfg)
     print(json.dumps(line), file=real_stdout, flush=True)
 
 

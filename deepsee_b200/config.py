@@ -7,6 +7,44 @@ class _Config:
     #   3 = hi*hi + lo*hi + hi*lo  (fp32-class accuracy; the parity default)
     #   1 = hi*hi                  (fp16 operands = TF32-class accuracy, 3x fewer MMAs)
     passes = int(os.environ.get("DSEE_PASSES", "3"))
+    # Mixed precision by resolution (only matters when passes == 1): the MAIN convs (K2) of generator
+    # blocks whose feature map is at most `passes3_upto` pixels high run 3 passes anyway.  Measured on
+    # the full-size generators (profiles/r2_precision_probe.json): the 1-pass error of the output comes
+    # almost entirely from the main convs (the gamma/beta GEMMs contribute nothing measurable), and
+    # about half of its variance from the blocks below the two highest resolutions - their rounding
+    # errors are upsampled into spatially coherent patches that every later block and the 3x3 image
+    # head sum up - while those blocks hold ~5 % of the FLOPs (each 2x upsample quadruples the work).
+    # "auto" = a quarter of the output size: everything except the two highest-resolution stages.
+    # 0 = off (pure 1-pass).
+    passes3_upto = os.environ.get("DSEE_PASSES3_UPTO", "auto")
+    # test / probe hook: {("k1" | "k2", H): passes} overrides of the rule above
+    pass_overrides = {}
+
+    def passes_for(self, kind, H, S=None):
+        """Tensor-core operand passes of one generator kernel: kind "k1" = the gamma/beta GEMM of a
+        conditional norm layer, "k2" = a main 3x3 conv (and, in the backward pass, the GEMMs that
+        share its operands), at feature-map height H of a generator whose output is S pixels high."""
+        o = self.pass_overrides.get((kind, H))
+        if o is not None:
+            return o
+        if self.passes == 3:
+            return 3
+        upto = self.passes3_upto
+        if upto == "auto":
+            upto = (S // 4) if S else 0
+        if kind == "k2" and H <= int(upto):
+            return 3
+        return self.passes
+
+    def precision_name(self):
+        if self.passes == 3:
+            return "fp16 hi+lo split operands x3 passes, fp32 accumulate (fp32-class)"
+        if self.passes3_upto in (0, "0"):
+            return "fp16 operands, fp32 accumulate (TF32-class)"
+        return ("fp16 operands, fp32 accumulate (TF32-class); main convs at <= %s of the output "
+                "resolution with hi+lo split operands x3 passes" %
+                ("1/4" if self.passes3_upto == "auto" else "%s px" % self.passes3_upto))
+
     # Training: K1 saves G = gamma + gamma_bias (fp16 planes, +1-2 B per activation element) so its
     # backward is one streaming pass instead of re-running the gamma GEMM (0 = recompute).
     save_gamma = os.environ.get("DSEE_SAVE_GAMMA", "1") != "0"
@@ -23,11 +61,21 @@ class _Config:
     # instead of the fused kernels (ops.SpectralWeightFn / ops.ModWeightFn).
     torch_spectral = os.environ.get("DSEE_TORCH_SPECTRAL", "0") == "1"
     torch_modweight = os.environ.get("DSEE_TORCH_MODWEIGHT", "0") == "1"
-    # Multi-GPU batch-norm statistics: 0 = per-rank statistics (north_star: NCCL all-reduce "for G/D
-    # gradients only"), 1 = global-batch statistics like the reference's DataParallel mode
-    # (sync_batchnorm/batchnorm.py:63-93): one [2,C] all-reduce per norm layer forward and one
-    # [2,C] all-reduce per norm layer backward.
-    sync_bn = os.environ.get("DSEE_SYNC_BN", "0") == "1"
+    # Multi-GPU batch-norm statistics.  "auto" (default): global-batch statistics whenever the
+    # generator's norm type says so (`norm_G` contains "syncbatch", the reference default) and more
+    # than one rank runs - the reference's multi-GPU semantics (sync_batchnorm/batchnorm.py:63-93):
+    # one [2,C] all-reduce per norm layer forward and one per norm layer backward; running
+    # statistics are then identical on every rank.  DSEE_SYNC_BN=0: per-rank statistics (gradient
+    # all-reduce is the only collective; running stats diverge across ranks, rank 0's are saved);
+    # DSEE_SYNC_BN=1: always synchronise.
+    sync_bn = {"0": False, "1": True}.get(os.environ.get("DSEE_SYNC_BN", "auto"), "auto")
+
+    def sync_bn_for(self, norm_G):
+        """Whether the conditional-norm layers of a generator with this norm_G string exchange their
+        batch statistics across ranks (the caller still checks that a process group exists)."""
+        if self.sync_bn == "auto":
+            return "syncbatch" in (norm_G or "")
+        return bool(self.sync_bn)
     # Spectral normalisation of a network's layers in one batched launch sequence per forward
     # (ops.spectral_prepass) instead of five launches per layer; 0 = per-layer kernels.
     batched_spectral = os.environ.get("DSEE_BATCHED_SPECTRAL", "1") != "0"

@@ -65,16 +65,21 @@ class _SideStream:
 
 class _NormState:
     """What K1's backward needs from one conditional-norm layer's forward."""
-    __slots__ = ("srcs", "meta", "Wm", "gb", "sc", "sh", "inv_count", "g")
+    __slots__ = ("srcs", "meta", "Wm", "gb", "sc", "sh", "inv_count", "g", "sync")
 
 
 def _norm_forward(blk, norm, pre, Wm, gb, bb, tab, tb, gctx, style, x, x_ups, H, W, part, count,
-                  ucount, noise, noise_w, passes, want_lo, save_g):
-    """BN affine + sources + K1 -> (activation planes, _NormState)."""
+                  ucount, noise, noise_w, passes, want_lo, save_g, out_lo=None):
+    """BN affine + sources + K1 -> (activation planes, _NormState).  ``passes`` / ``want_lo`` are
+    K1's own (its GEMM operands); ``out_lo``: whether the consumer of the activation planes (the
+    main conv) runs 3 passes and needs their lo plane (default: same as want_lo)."""
+    if out_lo is None:
+        out_lo = want_lo
     st = _NormState()
     bn = norm.param_free_norm
+    st.sync = parallel.is_dist() and config.sync_bn_for(blk.opt.norm_G)
     if blk.training:
-        if config.sync_bn and parallel.is_dist():
+        if st.sync:
             # global-batch statistics (the reference's Sync-BN, batchnorm.py:80-93): all-reduce the
             # per-channel (sum, sum of squares) before they become mean / variance
             part = parallel.allreduce_sum_(ops.reduce_partials(part)).t().contiguous().unsqueeze(0)
@@ -90,7 +95,7 @@ def _norm_forward(blk, norm, pre, Wm, gb, bb, tab, tb, gctx, style, x, x_ups, H,
     st.srcs, st.meta = norm.build_sources(gctx, style, H, W, want_lo, table=tab, bias=tb)
     st.Wm, st.gb = Wm, gb
     r = ops.spade_modulate(st.srcs, pw, x, x_ups, st.sc, st.sh, gb, bb, noise=noise, noise_w=noise_w,
-                           passes=passes, want_lo=want_lo, save_g=save_g)
+                           passes=passes, want_lo=out_lo, save_g=save_g)
     a, st.g = r if save_g else (r, None)
     return a, st
 
@@ -114,19 +119,20 @@ def _norm_backward(norm, st, dt, dt_amax, x, x_ups, noise, noise_w, L, passes, w
     return (dxhat, sums) + _norm_backward_tail(st, dgb, L, passes, want_lo, ss)
 
 
-def _conv_and_norm_backward(st, g, W, a, x, x_ups, noise, noise_w, L, passes, want_lo, ss):
+def _conv_and_norm_backward(st, g, W, a, x, x_ups, noise, noise_w, L, p1, p2, ss):
     """Backward-data of a main conv (gradient planes ``g`` of its output, weight ``W``, input
-    activation planes ``a``) followed by K1's backward of the norm layer that produced ``a``
-    -> (dxhat, sums[4,C], dWm, dtab, dtb, dstyle).  With the saved G planes both run as ONE kernel
-    (ops.dgrad_modulate_bwd: dt stays in TMEM / registers); otherwise dgrad -> dt -> K1 backward."""
-    pwT = ops.prep_conv_weight(W.contiguous(), want_lo=want_lo, transpose=True)
+    activation planes ``a``; ``p2`` passes) followed by K1's backward of the norm layer that produced
+    ``a`` (``p1`` passes for its GEMMs) -> (dxhat, sums[4,C], dWm, dtab, dtb, dstyle).  With the saved G
+    planes both run as ONE kernel (ops.dgrad_modulate_bwd: dt stays in TMEM / registers); otherwise
+    dgrad -> dt -> K1 backward."""
+    pwT = ops.prep_conv_weight(W.contiguous(), want_lo=p2 == 3, transpose=True)
     if st.g is not None and config.fuse_dgrad_modbwd:
         dxhat, dgb, sums = ops.dgrad_modulate_bwd(g, pwT, a.hi, st.g, x, x_ups, st.sc, st.sh, noise=noise,
-                                                  noise_w=noise_w, passes=passes, want_lo=want_lo)
+                                                  noise_w=noise_w, passes=p2, want_lo=p1 == 3)
         st.g = None
-        return (dxhat, sums) + _norm_backward_tail(st, dgb, L, passes, want_lo, ss)
-    dt, amax = ops.conv3x3([g], pwT, None, passes=passes, act_mask=a.hi, want_amax=True, tag="dgrad")
-    return _norm_backward(None, st, dt, amax, x, x_ups, noise, noise_w, L, passes, want_lo, ss)
+        return (dxhat, sums) + _norm_backward_tail(st, dgb, L, p1, p1 == 3, ss)
+    dt, amax = ops.conv3x3([g], pwT, None, passes=p2, act_mask=a.hi, want_amax=True, tag="dgrad")
+    return _norm_backward(None, st, dt, amax, x, x_ups, noise, noise_w, L, p1, p1 == 3, ss)
 
 
 def _norm_backward_tail(st, dgb, L, passes, want_lo, ss):
@@ -160,7 +166,10 @@ def _sync_bwd_sums(nsums, st):
     batch.  Every rank differentiates its OWN mean loss and the gradient buckets are averaged
     afterwards, so the unscaled local sums are the right summands.  Rows 2-3 (parameter gradients)
     stay local."""
-    if not (config.sync_bn and parallel.is_dist()) or st.inv_count == 0.0:
+    sync = getattr(st, 'sync', None)
+    if sync is None:
+        sync = parallel.is_dist() and config.sync_bn is True
+    if not sync or st.inv_count == 0.0:
         return nsums
     head = parallel.allreduce_sum_(nsums[:2].clone())
     return torch.cat([head, nsums[2:]], 0)
@@ -174,8 +183,9 @@ class _ResBlockFn(torch.autograd.Function):
                 bb0, tab0, tb0, Wm1, gb1, bb1, tab1, tb1, nw_in, nw_skip, nw_mid):
         B, Hx, Wx, C = x.shape
         H, W = Hx << ups, Wx << ups
-        passes = config.passes
-        want_lo = passes == 3
+        # operand passes of this block's gamma/beta GEMMs (p1) and main convs (p2): config.passes_for
+        S = gctx.labels_full.shape[1]
+        p1, p2 = config.passes_for('k1', H, S), config.passes_for('k2', H, S)
         training = blk.training
         n_in, n_skip, n_mid = noises if noises is not None else (None, None, None)
         noisy = noises is not None
@@ -198,26 +208,26 @@ class _ResBlockFn(torch.autograd.Function):
                 count = ucount = B * H * W
         a0, st0 = _norm_forward(blk, blk.norm_0, pre.get('pwm0'), Wm0, gb0, bb0, tab0, tb0, gctx,
                                 style, x, ups, H, W, part, count, ucount, n_in,
-                                nw_in if noisy else None, passes, want_lo, save_g)
+                                nw_in if noisy else None, p1, p1 == 3, save_g, out_lo=p2 == 3)
         # ---- conv_0 (+ noise_middle) ----------------------------------------------------------
-        pw0 = pre.get('pw0') or ops.prep_conv_weight(W0.contiguous(), want_lo=want_lo)
-        r = ops.conv3x3([a0], pw0, b0, noises=[(n_mid, nw_mid)] if noisy else (), passes=passes,
+        pw0 = pre.get('pw0') or ops.prep_conv_weight(W0.contiguous(), want_lo=p2 == 3)
+        r = ops.conv3x3([a0], pw0, b0, noises=[(n_mid, nw_mid)] if noisy else (), passes=p2,
                         want_stats=training)
         dx1, part1 = r if training else (r, None)
         # ---- norm_1 + actvn -------------------------------------------------------------------
         a1, st1 = _norm_forward(blk, blk.norm_1, pre.get('pwm1'), Wm1, gb1, bb1, tab1, tb1, gctx,
-                                style, dx1, 0, H, W, part1, B * H * W, B * H * W, None, None, passes,
-                                want_lo, save_g)
+                                style, dx1, 0, H, W, part1, B * H * W, B * H * W, None, None, p1,
+                                p1 == 3, save_g, out_lo=p2 == 3)
         # ---- conv_1 + shortcut ------------------------------------------------------------------
-        pw1 = pre.get('pw1') or ops.prep_conv_weight(W1.contiguous(), want_lo=want_lo)
+        pw1 = pre.get('pw1') or ops.prep_conv_weight(W1.contiguous(), want_lo=p2 == 3)
         r = ops.conv3x3([a1], pw1, b1, residual=x, res_ups=ups,
-                        noises=[(n_in, nw_in), (n_skip, nw_skip)] if noisy else (), passes=passes,
+                        noises=[(n_in, nw_in), (n_skip, nw_skip)] if noisy else (), passes=p2,
                         want_stats=training)
         out, stats = r if training else (r, None)
 
         if need_bwd:
             ctx.s = dict(blk=blk, ups=ups, noises=noises, x=x, W0=W0, W1=W1, a0=a0, a1=a1, dx1=dx1,
-                         st0=st0, st1=st1, nw_in=nw_in, passes=passes, want_lo=want_lo)
+                         st0=st0, st1=st1, nw_in=nw_in, p1=p1, p2=p2)
         if stats is None:
             stats = x.new_zeros(1)
         ctx.mark_non_differentiable(stats)
@@ -226,7 +236,8 @@ class _ResBlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, _dstats):
         s = ctx.s
-        blk, ups, passes, want_lo = s['blk'], s['ups'], s['passes'], s['want_lo']
+        blk, ups, p1, p2 = s['blk'], s['ups'], s['p1'], s['p2']
+        want_lo = p2 == 3
         n_in, n_skip, n_mid = s['noises'] if s['noises'] is not None else (None, None, None)
         noisy = s['noises'] is not None
         L = blk.opt.semantic_nc
@@ -244,10 +255,10 @@ class _ResBlockFn(torch.autograd.Function):
         db1 = sums[0]
         dnw_skip = sums[1] if noisy else None
         ss = _SideStream()
-        dW1 = ss.run(lambda: ops.conv3x3_wgrad(g1, a1, passes=passes), g1, a1)
+        dW1 = ss.run(lambda: ops.conv3x3_wgrad(g1, a1, passes=p2), g1, a1)
         # ---- backward-data of conv_1 + norm_1 --------------------------------------------------
         dxhat, nsums, dWm1, dtab1, dtb1, dstyle1 = _conv_and_norm_backward(
-            st1, g1, s['W1'], a1, dx1, 0, None, None, L, passes, want_lo, ss)
+            st1, g1, s['W1'], a1, dx1, 0, None, None, L, p1, p2, ss)
         del g1
         dgb1, dbb1 = nsums[2], nsums[3]
         nsums = _sync_bwd_sums(nsums, st1)
@@ -258,11 +269,11 @@ class _ResBlockFn(torch.autograd.Function):
         del ddx1
         db0 = sums[0]
         dnw_mid = sums[1] if noisy else None
-        dW0 = ss.run(lambda: ops.conv3x3_wgrad(g0, a0, passes=passes), g0, a0)
+        dW0 = ss.run(lambda: ops.conv3x3_wgrad(g0, a0, passes=p2), g0, a0)
         # ---- backward-data of conv_0 + norm_0 (reads x through the folded upsample, + noise_in) -
         nw_in = s['nw_in'] if noisy else None
         dxhat, nsums, dWm0, dtab0, dtb0, dstyle0 = _conv_and_norm_backward(
-            st0, g0, s['W0'], a0, x, ups, n_in, nw_in, L, passes, want_lo, ss)
+            st0, g0, s['W0'], a0, x, ups, n_in, nw_in, L, p1, p2, ss)
         del g0
         dgb0, dbb0 = nsums[2], nsums[3]
         nsums = _sync_bwd_sums(nsums, st0)
@@ -336,7 +347,8 @@ class SPADEResnetBlock(nn.Module):
         None). ``stats_in``: BN partial sums of x from the producing kernel (training only)."""
         B, Hx, Wx, C = x.shape
         H, W = Hx << ups, Wx << ups
-        want_lo = config.passes == 3
+        S = ctx.labels_full.shape[1]
+        lo1, lo2 = config.passes_for('k1', H, S) == 3, config.passes_for('k2', H, S) == 3
         noises = None
         nw = (None, None, None)
         if self.add_noise:
@@ -347,11 +359,11 @@ class SPADEResnetBlock(nn.Module):
         W0, W1 = effective_weight(self.conv_0), effective_weight(self.conv_1)
         cached = not self.training and not torch.is_grad_enabled()
         if cached:
-            pwm0, gb0, bb0 = self.norm_0.prepared(want_lo)
-            pwm1, gb1, bb1 = self.norm_1.prepared(want_lo)
+            pwm0, gb0, bb0 = self.norm_0.prepared(lo1)
+            pwm1, gb1, bb1 = self.norm_1.prepared(lo1)
             pre = {'pwm0': pwm0, 'pwm1': pwm1,
-                   'pw0': self._prepared_conv(self.conv_0, W0, 'conv_0', want_lo),
-                   'pw1': self._prepared_conv(self.conv_1, W1, 'conv_1', want_lo)}
+                   'pw0': self._prepared_conv(self.conv_0, W0, 'conv_0', lo2),
+                   'pw1': self._prepared_conv(self.conv_1, W1, 'conv_1', lo2)}
             Wm0 = Wm1 = None
         else:
             pre = None

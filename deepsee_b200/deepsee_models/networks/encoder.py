@@ -51,11 +51,13 @@ class AbtractStyleEncoder(BaseNetwork):
         labels, _ = ops.labels_from_onehot(seg.contiguous().float())
         return labels
 
-    def extract_style_matrix(self, x_nhwc, labels_full):
-        """encoder.py:36-49 (divides by H*W of the feature map, not by the region area)."""
+    def extract_style_matrix(self, x_nhwc, labels_full, n_regions=None):
+        """encoder.py:36-49 (divides by H*W of the feature map, not by the region area).  One row per
+        channel of the segmentation input (seg.size(1) = semantic_nc: with contain_dontcare_label
+        that is label_nc + 1)."""
         B, H, W, _ = x_nhwc.shape
         labels = ops.resize_labels(labels_full, H, W)
-        return ops.RegionPoolFn.apply(x_nhwc, labels, self.opt.label_nc)
+        return ops.RegionPoolFn.apply(x_nhwc, labels, n_regions or self.opt.semantic_nc)
 
     def corrupt_style_matrix(self, style_matrix, max_range_noise, region_idx=None):
         """encoder.py:51-70 (all regions). Tiny [B,19,128] elementwise op; the uniform draw uses
@@ -123,7 +125,7 @@ class FullStyleEncoder(AbtractStyleEncoder):
         with spectral_prepass(self.main_convs() + [self.final[0][0]]):
             x, activations = self.forward_main(x)
             x = self._final(x)
-        style_matrix = self.extract_style_matrix(x, self._labels(seg))
+        style_matrix = self.extract_style_matrix(x, self._labels(seg), seg.size(1))
         if self.noisy_style and not no_noise:
             style_matrix = self.corrupt_style_matrix(style_matrix, self.max_range_noise)
         return style_matrix, activations
@@ -163,7 +165,7 @@ class MinistyleEncoder(AbtractStyleEncoder):
         with spectral_prepass(self.main_convs() + [self.final[0][0]]):
             x, activations = self.forward_main(x)
             x = self._final(x)
-        return self.extract_style_matrix(x, self._labels(seg)), activations
+        return self.extract_style_matrix(x, self._labels(seg), seg.size(1)), activations
 
 
 class CombinedstyleEncoder(AbtractStyleEncoder):
@@ -193,7 +195,7 @@ class CombinedstyleEncoder(AbtractStyleEncoder):
         with spectral_prepass(enc.main_convs() + [self.final[0][0]]):
             x, activations = enc.forward_main(x)
             x = self._final(x)
-        style_matrix = self.extract_style_matrix(x, self._labels(seg))
+        style_matrix = self.extract_style_matrix(x, self._labels(seg), seg.size(1))
         if self.noisy_style and not no_noise:
             style_matrix = self.corrupt_style_matrix(style_matrix, self.max_range_noise)
         return style_matrix, activations

@@ -21,7 +21,10 @@ class BaseManager:
 
     def create_model(self, opt):
         parallel.init_from_env()           # no-op when launched as a single process
-        parallel.seed_python_random(0)     # encoder coin flips must agree across ranks
+        if parallel.is_dist():
+            # the encoder coin flips (Python's global `random`, like the reference) must agree across
+            # ranks; a single process keeps whatever seeding the caller did
+            parallel.seed_python_random(0)
         self.sr_model = SRModel(opt)
         parallel.broadcast_module(self.sr_model)  # identical initial weights on every rank
         self.sr_model_on_one_gpu = self.sr_model

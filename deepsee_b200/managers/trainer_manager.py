@@ -3,8 +3,9 @@
 Same public surface as the reference (`run_generator_one_step`, `run_discriminator_one_step`,
 `get_latest_losses`, `get_latest_generated`, `get_logs`, `save`, `update_learning_rate`,
 `sr_model`, `sr_model_on_one_gpu`), so train.py drives it unchanged.  Differences:
-  * one process per GPU; after each backward the G(+E) or D gradients are averaged across ranks
-    with ONE flat NCCL all-reduce (..parallel.GradBucket) - the only data-path collective;
+  * one process per GPU; the G(+E) or D gradients are averaged across ranks through a flat
+    bucket whose chunks are all-reduced over NCCL while the backward pass is still running
+    (..parallel.GradBucket);
   * checkpoints are written by rank 0 only.
 Both optimizer steps share one code path (`_optimize`).
 """
@@ -35,11 +36,13 @@ class TrainerManager(BaseManager):
         """zero_grad -> forward(mode) -> mean of the summed losses -> backward -> gradient all-reduce
         (multi-GPU) -> optional value clipping -> optimizer step.  Returns SRModel.forward's result."""
         optimizer.zero_grad()
+        if bucket is not None:
+            bucket.begin()        # .grad = views of the flat bucket; chunks all-reduce during backward
         result = self.sr_model(self.preprocess_input(data), mode=mode)
         losses = result[0] if mode == 'generator' else result
         sum(losses.values()).mean().backward()
         if bucket is not None:
-            bucket.allreduce_mean()
+            bucket.finish()
         if self.opt.gradient_clip > 0:
             clip_grad_value_(self.sr_model.parameters(), self.opt.gradient_clip)
         optimizer.step()

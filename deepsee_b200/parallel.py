@@ -7,7 +7,8 @@ loads / synthesises its own samples); the only data-path collective is one all-r
 flat fp32 gradient bucket per optimizer step (G+E after the generator backward, D after the
 discriminator backward), scaled by 1/world (the reference averages replica losses:
 trainer_manager.py:36,53).  Parameters without a gradient (never-used `style_conv.*`, the encoder
-branch the coin flip skipped) contribute zeros so every rank reduces the same layout.
+branch the coin flip skipped) contribute zeros so every rank reduces the same layout, and get
+`.grad = None` back afterwards so the optimizer skips them like a single-process run does.
 Works unchanged with the `gloo` backend on CPU tensors (used by the world_size-2 tests).
 """
 import os
@@ -68,29 +69,124 @@ def broadcast_module(module, src=0):
 
 
 class GradBucket:
-    """Flat fp32 gradient buffer over a fixed parameter list; one all-reduce per step."""
+    """Flat fp32 gradient buffer over a fixed parameter list, all-reduced in a few contiguous chunks
+    that are launched from inside the backward pass.
 
-    def __init__(self, params):
+    * `begin()` replaces `optimizer.zero_grad()`: one memset of the flat buffer and every
+      parameter's `.grad` becomes its view of it, so autograd accumulates straight into the bucket
+      (no gather copy afterwards).
+    * A post-accumulate-grad hook per parameter counts down its chunk; when the last gradient of a
+      chunk has landed, that chunk's all-reduce is issued asynchronously (NCCL's own stream) while
+      the backward pass continues.  Chunks are contiguous in parameter order, so the chunk holding
+      the LAST layers completes first.  The launch order is a function of the autograd graph, hence
+      the same on every rank.
+    * `finish()` issues whatever chunks are still open (parameters that got no gradient this step:
+      never-used `style_conv.*`, the encoder branch the coin flip skipped), waits, scales by
+      1/world, and restores `.grad = None` on the parameters that received no gradient, so Adam
+      skips them exactly like the single-process run and the reference do (the coin flips are
+      rank-synchronised, so the local "no gradient" set is the global one).
+    """
+
+    def __init__(self, params, n_chunks=4):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.views = []
         off = 0
+        offs = []
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            offs.append(off)
             off += p.numel()
+        # contiguous chunks of roughly equal size
+        n_chunks = max(1, min(n_chunks, len(self.params)))
+        target = (n + n_chunks - 1) // n_chunks if n else 1
+        self.chunk_of, self.chunk_range, self.chunk_params = [], [], []
+        lo = 0
+        cnt = 0
+        for i, p in enumerate(self.params):
+            self.chunk_of.append(len(self.chunk_range))
+            cnt += 1
+            end = offs[i] + p.numel()
+            if end - lo >= target or i == len(self.params) - 1:
+                self.chunk_range.append((lo, end))
+                self.chunk_params.append(cnt)
+                lo, cnt = end, 0
+        self._active = False
+        self._pending, self._touched, self._works, self._launched = [], [], [], []
+        for i, p in enumerate(self.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
 
     def nbytes(self):
         return self.flat.numel() * 4
 
+    def _make_hook(self, i):
+        def hook(param):
+            if not self._active:
+                return
+            if not self._touched[i]:
+                self._touched[i] = True
+                c = self.chunk_of[i]
+                self._pending[c] -= 1
+                if self._pending[c] == 0:
+                    self._launch(c)
+        return hook
+
+    def _launch(self, c):
+        lo, hi = self.chunk_range[c]
+        self._launched[c] = True
+        if hi > lo:
+            self._works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+
     @torch.no_grad()
-    def allreduce_mean(self):
-        """Gathers .grad into the bucket (zeros where absent), all-reduces, and leaves every
-        parameter's .grad as a view of the averaged bucket (no copy back).  The gather is one
-        multi-tensor copy, not one launch per parameter."""
+    def begin(self):
+        """Call instead of optimizer.zero_grad() before the forward pass of a step."""
+        if not is_dist():
+            for p in self.params:
+                p.grad = None
+            return
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+        self._pending = list(self.chunk_params)
+        self._touched = [False] * len(self.params)
+        self._launched = [False] * len(self.chunk_range)
+        self._works = []
+        self._active = True
+
+    @torch.no_grad()
+    def finish(self):
+        """Call after backward(): completes the reduction; .grad = averaged gradient (a bucket view)
+        for parameters that received one on this step, None for the others."""
         if not is_dist():
             return
+        if not self._active:
+            # begin() was not called (gradients live in their own tensors): gather them first
+            self._gather_loose_grads()
+        else:
+            for i, (p, v) in enumerate(zip(self.params, self.views)):
+                g = p.grad
+                if g is not None and g.data_ptr() != v.data_ptr():
+                    # something replaced .grad (e.g. a hook-free manual assignment): fold it in
+                    v.copy_(g)
+                    p.grad = v
+                    self._touched[i] = True
+        self._active = False
+        for c in range(len(self.chunk_range)):
+            if not self._launched[c]:
+                self._launch(c)
+        for w in self._works:
+            w.wait()
+        self._works = []
+        self.flat.mul_(1.0 / dist.get_world_size())
+        for p, v, t in zip(self.params, self.views, self._touched):
+            p.grad = v if t else None
+
+    def _gather_loose_grads(self):
+        self._touched = [p.grad is not None for p in self.params]
+        self._launched = [False] * len(self.chunk_range)
+        self._works = []
         src, dst = [], []
         for p, v in zip(self.params, self.views):
             if p.grad is None:
@@ -100,7 +196,7 @@ class GradBucket:
                 dst.append(v)
         if dst:
             torch._foreach_copy_(dst, src)
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        self.flat.mul_(1.0 / dist.get_world_size())
-        for p, v in zip(self.params, self.views):
-            p.grad = v
+
+    def allreduce_mean(self):
+        """One-shot form (no begin()): gathers .grad into the bucket, all-reduces, averages."""
+        self.finish()

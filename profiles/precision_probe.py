@@ -1,0 +1,113 @@
+"""Where does the 1-pass (fp16-operand) error of the generator come from?  (round 2)
+
+Runs the FULL-SIZE generators of the benched configurations (c2: 8x 256x256, 512 channels, 5 blocks;
+c4: 32x 512x512, 7 blocks incl. the PureSEAN tail) on the GPU under several operand-pass policies
+and compares each with the CPU oracle on the same conditioned weights and inputs.  The oracle is the
+checker only.  Output: one JSON object per (case, policy) in gpurun_out/precision_probe.json.
+
+    python profiles/precision_probe.py [c2] [c4] [c2train]
+"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import deepsee_oracle as O  # noqa: E402
+from deepsee_b200.config import config  # noqa: E402
+from deepsee_b200.options.configurations import make_opt  # noqa: E402
+from deepsee_b200.deepsee_models.networks.sr import DeepSEESR  # noqa: E402
+
+CASES = {
+    "c2": ("8x_independent_256x256", {}, False),
+    "c2train": ("8x_independent_256x256", {}, True),
+    "c4": ("32x_independent_512x512", {}, False),
+    "c4train": ("32x_independent_512x512", {}, True),
+}
+
+
+def mk_opt(o):
+    d = dict(o)
+    name = d.pop("name")
+    opt = make_opt(None, **d)
+    opt.name = name
+    return opt
+
+
+def policies(res):
+    """name -> pass_overrides dict (base passes = 1, config.passes3_upto = 0).  Round-2 finding of the
+    first version of this probe (profiles/r2_precision_probe_v1.json): K1's passes do not matter, so
+    the policies below only vary the main convs (k2)."""
+    P = {"all3": {(k, h): 3 for k in ("k1", "k2") for h in res}, "all1": {}}
+    for upto in res[-4:-1]:
+        P["k2 x3 upto %d" % upto] = {("k2", h): 3 for h in res if h <= upto}
+    return P
+
+
+def main():
+    which = [a for a in sys.argv[1:] if not a.startswith("seed=")] or ["c2", "c2train", "c4", "c4train"]
+    seeds = [int(a[5:]) for a in sys.argv[1:] if a.startswith("seed=")] or [77]
+    results = []
+    torch.set_num_threads(os.cpu_count())
+    for case, seed in [(c, sd_) for c in which for sd_ in seeds]:
+        name, over, train = CASES[case]
+        o = O.make_opt(name, is_train=train, **over)
+        S, s0 = o.crop_size, o.start_size
+        res = []
+        h = s0
+        while h <= S:
+            res.append(h)
+            h *= 2
+        sd = O.make_generator_state(o, seed - 77)
+        d = O.preprocess(o, O.synthetic_batch(o, 1, seed=seed))
+        z = torch.rand(1, 19, 128, generator=torch.Generator().manual_seed(seed + 5)) * 2 - 1
+        noises = {}
+
+        def noise_fn(nm, shape):
+            noises[nm] = torch.randn(shape, generator=torch.Generator().manual_seed(len(noises)))
+            return noises[nm]
+
+        t0 = time.time()
+        with torch.no_grad():
+            ref = O.generator_forward({k: v.clone() for k, v in sd.items()}, o, d["image_lr"],
+                                      d["input_semantics"], z, train, noise_fn if train else None)
+        t_cpu = time.time() - t0
+        x, seg, zz = d["image_lr"].cuda(), d["input_semantics"].cuda(), z.cuda()
+        for pname, ov in policies(res).items():
+            G = DeepSEESR(mk_opt(o)).cuda()
+            G.load_state_dict(sd, strict=True)
+            G.train(train)
+            if train and o.add_noise:
+                for pfx, _, _ in O.generator_layout(o):
+                    blk = G.get_submodule(pfx[:-1])
+                    for nm in ("noise_in", "noise_skip", "noise_middle"):
+                        n = noises[pfx + nm].permute(0, 2, 3, 1).contiguous().cuda()
+                        getattr(blk, nm).sample = (lambda t: (lambda B, H, W: t))(n)
+            config.passes = 1
+            config.passes3_upto = 0
+            config.pass_overrides = dict(ov)
+            with torch.no_grad():
+                out = G(x, seg=seg, z=zz)
+            torch.cuda.synchronize()
+            e = (out.cpu() - ref).abs()
+            r = {"case": case, "seed": seed, "policy": pname, "max_abs": e.max().item(), "mean_abs": e.mean().item(),
+                 "p9999": e.flatten().kthvalue(int(e.numel() * 0.9999)).values.item(),
+                 "ref_std": ref.std().item(), "max_abs_over_std": e.max().item() / ref.std().item(),
+                 "oracle_s": round(t_cpu, 1)}
+            print(json.dumps(r), flush=True)
+            results.append(r)
+            del G
+            torch.cuda.empty_cache()
+    config.pass_overrides = {}
+    config.passes3_upto = "auto"
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "precision_probe.json"), "w") as f:
+        json.dump(results, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,9 +64,10 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith(".py"):
                 assert _oracle_imports(os.path.join(dirpath, f)) == [], f
-    # bench.py: only the CPU-baseline leg (which also serves --impl reference) may use it
+    # bench.py: only the CPU-baseline leg (which also serves --impl reference) and the parity check that
+    # runs next to it (the oracle as the checker of the benched precision mode) may use it
     where = _oracle_imports(os.path.join(ROOT, "bench.py"))
-    assert where and all(fn == "cpu_train_iteration_timer" for _, fn in where), where
+    assert where and all(fn in ("cpu_train_iteration_timer", "parity_leg") for _, fn in where), where
 
 
 def test_option_presets_match_the_reference_names():

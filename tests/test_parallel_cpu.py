@@ -28,16 +28,38 @@ def _worker(rank, world, port, q):
     net.register_buffer("running", torch.full((4,), float(rank)))
     parallel.broadcast_module(net)                     # ... and end up with rank 0's
     w0 = net[0].weight.detach().clone()
-    # gradients: rank r contributes (r + 1) on layer 0; layer 1 has a gradient on rank 0 only
+    # one-shot form: rank r contributes (r + 1) on layer 0 and 4 * (1 - r) on layer 1
     for p in net[0].parameters():
         p.grad = torch.full_like(p, float(rank + 1))
-    if rank == 0:
-        for p in net[1].parameters():
-            p.grad = torch.full_like(p, 4.0)
-    bucket = parallel.GradBucket(list(net.parameters()))
+    for p in net[1].parameters():
+        p.grad = torch.full_like(p, 4.0 * (1 - rank))
+    bucket = parallel.GradBucket(list(net.parameters()), n_chunks=2)
     bucket.allreduce_mean()
     # after the reduction every .grad IS a view of the flat bucket (no copy back)
     views_ok = all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+    g0_oneshot, g1_oneshot = net[0].weight.grad.clone(), net[1].weight.grad.clone()
+    # hook form (what TrainerManager does): begin() -> backward accumulates straight into the bucket
+    # views and chunks are all-reduced as they complete -> finish().  `extra` takes no part in the
+    # loss (like the encoder branch the coin flip skipped): its .grad must come back None so Adam
+    # skips it as in a single-process run.
+    extra = torch.nn.Parameter(torch.zeros(7))
+    bucket2 = parallel.GradBucket(list(net.parameters()) + [extra], n_chunks=3)
+    bucket2.begin()
+    xin = torch.full((2, 6), float(rank + 1))
+    net(xin).sum().backward()
+    bucket2.finish()
+    with torch.no_grad():
+        # d/dW1 of sum(W1 (W0 x + b0) + b1) = 1 (x) h summed over the batch; compare with the mean
+        # of both ranks' analytic gradients
+        want = []
+        for r in range(world):
+            xr = torch.full((2, 6), float(r + 1))
+            h = torch.nn.functional.linear(xr, net[0].weight, net[0].bias)
+            want.append(torch.ones(2, 3).t() @ h)
+        want = sum(want) / world
+    views_ok = views_ok and extra.grad is None and torch.allclose(net[1].weight.grad, want, atol=1e-5) \
+        and net[1].weight.grad.data_ptr() == bucket2.views[2].data_ptr() \
+        and all(lo < hi for lo, hi in bucket2.chunk_range) and len(bucket2.chunk_range) == 3
     # Sync-BN mode: batch-norm backward's two reductions are summed over ranks, the parameter-gradient
     # rows stay local (deepsee_models/networks/architecture.py:_sync_bwd_sums)
     from deepsee_b200.config import config
@@ -60,7 +82,7 @@ def _worker(rank, world, port, q):
     sync_ok = sync_ok and torch.equal(stat, torch.full((2, 4), 3.0))
     parallel.seed_python_random(0)
     flips = [random.random() for _ in range(3)]
-    q.put((rank, w0, net[0].weight.grad.clone(), net[1].weight.grad.clone(), net.running.clone(), flips,
+    q.put((rank, w0, g0_oneshot, g1_oneshot, net.running.clone(), flips,
            bucket.nbytes(), views_ok, sync_ok))
     dist.barrier()
     dist.destroy_process_group()
@@ -79,12 +101,12 @@ def test_grad_bucket_allreduce_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     (_, w_a, g0_a, g1_a, run_a, flips_a, nb, va, sa), (_, w_b, g0_b, g1_b, run_b, flips_b, _, vb, sb) = res
-    assert va and vb, "gradients are not views of the reduced bucket"
+    assert va and vb, "bucket views / hook-driven chunked all-reduce / None-gradient restoration"
     assert sa and sb, "Sync-BN statistics all-reduce"
     assert torch.equal(w_a, w_b)                        # broadcast from rank 0
     assert torch.equal(run_a, run_b) and float(run_a[0]) == 0.0   # buffers too
     assert torch.allclose(g0_a, torch.full_like(g0_a, 1.5)) and torch.equal(g0_a, g0_b)   # mean(1, 2)
-    assert torch.allclose(g1_a, torch.full_like(g1_a, 2.0)) and torch.equal(g1_a, g1_b)   # mean(4, absent=0)
+    assert torch.allclose(g1_a, torch.full_like(g1_a, 2.0)) and torch.equal(g1_a, g1_b)   # mean(4, 0)
     assert flips_a == flips_b
     assert nb == 4 * (6 * 5 + 5 + 5 * 3 + 3)
 

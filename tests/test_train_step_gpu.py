@@ -62,12 +62,26 @@ def _rel_l2(ours, ref):
     return (num / max(den, 1e-30)) ** 0.5
 
 
+@pytest.mark.parametrize("mode", ["passes3", "bench"])
 @pytest.mark.parametrize("name,over", [
     ("8x_independent_256x256", dict(ngf=8, nef=8, ndf=8, start_size=8, crop_size=64, load_size=64)),
     ("32x_guided_512x512", dict(ngf=8, nef=8, ndf=8, start_size=4, crop_size=128, load_size=512,
                                 max_fm_size=64)),
 ])
-def test_train_iteration_vs_oracle(name, over):
+def test_train_iteration_vs_oracle(name, over, mode):
+    """mode "passes3": the library default (fp32-class).  mode "bench": the precision bench.py
+    measures (1 pass, main convs of the low-resolution stages 3 passes) - forward values within
+    north_star's 1e-3, losses to 5e-3 relative, gradients by the same loose rel-L2 bound."""
+    from deepsee_b200.config import config
+    from test_full_size_parity_gpu import bench_precision
+    import contextlib
+    with (bench_precision() if mode == "bench" else contextlib.nullcontext()):
+        _train_iteration(name, over, 5e-3 if mode == "bench" else 2e-4, 1e-3 if mode == "bench" else 3e-4,
+                         1e-2 if mode == "bench" else 2e-3)
+    assert config.passes == 3
+
+
+def _train_iteration(name, over, tol_g, tol_img, tol_d):
     from deepsee_b200.managers.trainer_manager import TrainerManager
     o = O.make_opt(name, is_train=True, **over)
     sdG, sdE, sdD = O.make_generator_state(o, 0), O.make_encoder_state(o, 1), O.make_discriminator_state(o, 2)
@@ -114,8 +128,10 @@ def test_train_iteration_vs_oracle(name, over):
     for k in g_ref:
         a, b = float(ours[k].mean()), float(g_ref[k].mean())
         print("G loss %-9s ours %.6f oracle %.6f" % (k, a, b))
-        assert abs(a - b) < 2e-4 * max(1.0, abs(b))
-    assert (mgr.get_latest_generated().detach().cpu() - fake_ref).abs().max().item() < 3e-4
+        assert abs(a - b) < tol_g * max(1.0, abs(b))
+    img_err = (mgr.get_latest_generated().detach().cpu() - fake_ref).abs().max().item()
+    print("generated image max-abs vs oracle %.3e" % img_err)
+    assert img_err < tol_img
     eG = _rel_l2(_grads(m.netSR.named_parameters()), ref_gG)
     eE = _rel_l2(_grads(m.netE.named_parameters()), ref_gE)
     print("G-step gradient rel-L2: generator %.3e encoder %.3e" % (eG, eE))
@@ -133,7 +149,7 @@ def test_train_iteration_vs_oracle(name, over):
     for k in d_ref:
         a, b = float(ours[k].mean()), float(d_ref[k].mean())
         print("D loss %-9s ours %.6f oracle %.6f" % (k, a, b))
-        assert abs(a - b) < 2e-3 * max(1.0, abs(b))   # G weights already moved by one Adam step
+        assert abs(a - b) < tol_d * max(1.0, abs(b))   # G weights already moved by one Adam step
     eD = _rel_l2(_grads(m.netD.named_parameters()), ref_gD)
     print("D-step gradient rel-L2: discriminator %.3e" % eD)
     assert eD < 5e-2
