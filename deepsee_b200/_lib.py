@@ -15,7 +15,7 @@ SYMBOLS = [
     "dsee_version", "dsee_last_error", "dsee_launch_count",
     "dsee_noise_fill", "dsee_onehot_from_labels", "dsee_labels_from_onehot", "dsee_resize_labels",
     "dsee_shared_mlp_fwd", "dsee_style_gather_fwd",
-    "dsee_prep_conv_weight", "dsee_split_f16", "dsee_prep_conv_weight_ex", "dsee_split_f16_ups2",
+    "dsee_prep_conv_weight", "dsee_prep_conv_weight_f8", "dsee_split_f16", "dsee_prep_conv_weight_ex", "dsee_split_f16_ups2",
     "dsee_fold2x2", "dsee_conv2d_tc", "dsee_conv2d_tc_wgrad_workspace_floats", "dsee_conv2d_tc_wgrad",
     "dsee_conv3x3_fwd", "dsee_conv3x3_stats_tiles", "dsee_spade_modulate_fwd",
     "dsee_spade_modulate_bwd", "dsee_spade_modulate_bwd_saved", "dsee_dgrad_modulate_bwd", "dsee_grad_prep_blocks", "dsee_grad_prep", "dsee_reduce_partials",
@@ -42,6 +42,7 @@ class ConvOperands(C.Structure):
         ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("w_inv_scale", C.c_void_p),
         ("n_total", C.c_int), ("passes", C.c_int), ("a_dtype", C.c_int), ("w_dtype", C.c_int),
         ("a_inv_scale", C.c_void_p),
+        ("a8_lo", C.c_void_p), ("a8_hi", C.c_void_p), ("w8", C.c_void_p),
     ]
 
 
@@ -62,6 +63,7 @@ class ModulateArgs(C.Structure):
         ("gamma_bias", C.c_void_p), ("beta_bias", C.c_void_p),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
         ("C", C.c_int), ("g_hi", C.c_void_p), ("g_lo", C.c_void_p), ("noise_seed", C.c_uint64),
+        ("out8_lo", C.c_void_p), ("out8_hi", C.c_void_p),
     ]
 
 
@@ -123,7 +125,7 @@ class ModWeightGrads(C.Structure):
     ]
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 
@@ -148,6 +150,7 @@ def load():
         "dsee_shared_mlp_fwd": [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp],
         "dsee_style_gather_fwd": [vp, vp, vp, vp, i, i, i, i, i, vp],
         "dsee_prep_conv_weight": [vp, vp, vp, vp, i, i, i, vp],
+        "dsee_prep_conv_weight_f8": [vp, vp, vp, i, i, vp],
         "dsee_split_f16": [vp, vp, vp, i64, vp],
         "dsee_prep_conv_weight_ex": [vp, vp, vp, vp, i, i, i, i, i, vp],
         "dsee_split_f16_ups2": [vp, vp, vp, i, i, i, i, vp],

@@ -7,43 +7,50 @@ class _Config:
     #   3 = hi*hi + lo*hi + hi*lo  (fp32-class accuracy; the parity default)
     #   1 = hi*hi                  (fp16 operands = TF32-class accuracy, 3x fewer MMAs)
     passes = int(os.environ.get("DSEE_PASSES", "3"))
-    # Mixed precision by resolution (only matters when passes == 1): the MAIN convs (K2) of generator
-    # blocks whose feature map is at most `passes3_upto` pixels high run 3 passes anyway.  Measured on
-    # the full-size generators (profiles/r2_precision_probe.json): the 1-pass error of the output comes
-    # almost entirely from the main convs (the gamma/beta GEMMs contribute nothing measurable), and
-    # about half of its variance from the blocks below the two highest resolutions - their rounding
-    # errors are upsampled into spatially coherent patches that every later block and the 3x3 image
-    # head sum up - while those blocks hold ~5 % of the FLOPs (each 2x upsample quadruples the work).
-    # "auto" = a quarter of the output size: everything except the two highest-resolution stages.
-    # 0 = off (pure 1-pass).
+    # Mixed precision (only matters when passes == 1).  Measured on the full-size generators
+    # (profiles/r2_precision_probe_v{1,2}.json, train mode, vs the CPU oracle): pure 1-pass (fp16
+    # operands = TF32-class) lands at 1.6e-3 ... 2.4e-3 max-abs on the tanh output - over north_star's
+    # 1e-3 - and the error comes overwhelmingly from the MAIN convs of the FORWARD pass (K2); the
+    # gamma/beta GEMMs (K1) matter only in the low-resolution stages, whose rounding errors are
+    # upsampled into spatially coherent patches that every later block and the 3x3 image head sum up.
+    # So in 1-pass mode:
+    #   * forward main convs run `k2_fwd_passes` (2 = one fp16 pass + an fp8 correction GEMM for both
+    #     rounding terms, at the cost of two fp16 passes; 3 = the full hi/lo split);
+    #   * K1 runs 3 passes in stages up to `passes3_upto` pixels high ("auto" = a quarter of the output
+    #     size: ~5 % of the FLOPs), 1 pass above;
+    #   * every backward GEMM (dgrad, wgrad) runs 1 pass: gradients carry no 1e-3 forward bound.
+    k2_fwd_passes = int(os.environ.get("DSEE_K2_FWD_PASSES", "2"))
     passes3_upto = os.environ.get("DSEE_PASSES3_UPTO", "auto")
-    # test / probe hook: {("k1" | "k2", H): passes} overrides of the rule above
+    # test / probe hook: {("k1" | "k2" | "k2b", H): passes} overrides of the rule above
     pass_overrides = {}
 
     def passes_for(self, kind, H, S=None):
-        """Tensor-core operand passes of one generator kernel: kind "k1" = the gamma/beta GEMM of a
-        conditional norm layer, "k2" = a main 3x3 conv (and, in the backward pass, the GEMMs that
-        share its operands), at feature-map height H of a generator whose output is S pixels high."""
+        """Tensor-core operand passes of one generator kernel at feature-map height H of a generator
+        whose output is S pixels high.  kind: "k1" = the gamma/beta GEMM of a conditional norm layer
+        and the backward GEMMs that share its operands; "k2" = a main 3x3 conv, forward; "k2b" = the
+        backward GEMMs of a main conv (backward-data, weight gradient)."""
         o = self.pass_overrides.get((kind, H))
         if o is not None:
             return o
         if self.passes == 3:
             return 3
-        upto = self.passes3_upto
-        if upto == "auto":
-            upto = (S // 4) if S else 0
-        if kind == "k2" and H <= int(upto):
-            return 3
+        if kind == "k2":
+            return self.k2_fwd_passes
+        if kind == "k1":
+            upto = self.passes3_upto
+            if upto == "auto":
+                upto = (S // 4) if S else 0
+            return 3 if H <= int(upto) else self.passes
         return self.passes
 
     def precision_name(self):
         if self.passes == 3:
             return "fp16 hi+lo split operands x3 passes, fp32 accumulate (fp32-class)"
-        if self.passes3_upto in (0, "0"):
-            return "fp16 operands, fp32 accumulate (TF32-class)"
-        return ("fp16 operands, fp32 accumulate (TF32-class); main convs at <= %s of the output "
-                "resolution with hi+lo split operands x3 passes" %
-                ("1/4" if self.passes3_upto == "auto" else "%s px" % self.passes3_upto))
+        k2 = {1: "1 pass", 2: "1 fp16 pass + fp8 correction of both operand-rounding terms",
+              3: "hi+lo split operands x3 passes"}[self.k2_fwd_passes]
+        return ("fp16 operands, fp32 accumulate (TF32-class) for the gamma/beta GEMMs and all backward GEMMs; "
+                "forward main convs: %s; gamma/beta GEMMs of stages <= %s: x3 passes" %
+                (k2, "1/4 of the output size" if self.passes3_upto == "auto" else "%s px" % self.passes3_upto))
 
     # Training: K1 saves G = gamma + gamma_bias (fp16 planes, +1-2 B per activation element) so its
     # backward is one streaming pass instead of re-running the gamma GEMM (0 = recompute).

@@ -50,6 +50,9 @@ int require_sm100();
 int encode_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, bool bf16,
                     const uint32_t* elem_strides = nullptr);
+// Same for an 8-bit element tensor (fp8 operands of tcgen05 kind::f8f6f4 are plain bytes to TMA).
+int encode_tmap_8b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------
@@ -149,6 +152,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Same with 8-bit float operands (e4m3 / e5m2 chosen per operand in idesc): K = 32 per instruction,
+// i.e. the same 32 bytes of a 128B-swizzled K-major row as a kind::f16 step, at twice the FLOP rate.
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                        uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");

@@ -39,6 +39,7 @@
 #include "launch_count.h"
 #include <string.h>
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 
 namespace dsee {
 
@@ -65,6 +66,12 @@ enum { EPI_CONV = 0, EPI_MODULATE = 1, EPI_MODULATE_BWD = 2, EPI_DGRAD_MODBWD = 
 struct alignas(64) ConvParams {
     CUtensorMap tmA[4];  // [source*2 + plane]
     CUtensorMap tmB[2];  // [plane]
+    // fp8 correction phase (passes == 2): A planes [0] = (a - a_hi) * 2^8, [1] = a (e5m2, bytes), and
+    // the e4m3 weight [n][tap][2][C]; K blocks of 128 bytes
+    CUtensorMap tmA8[2];
+    CUtensorMap tmB8;
+    int cb8;           // 128-channel blocks per fp8 plane (0 = no fp8 phase)
+    uint32_t idesc8;
     int B, H, W;       // tile space: the output pixels this launch computes, per image
     int Hm, Wm;        // output tensor dims in memory; pixel (y,x) of the tile space lives at
     int o_step, o_offy, o_offx;  //   (y*o_step + o_offy, x*o_step + o_offx)
@@ -105,6 +112,8 @@ struct alignas(64) ConvParams {
     __half* out_lo;
     __half* g_hi;  // optional: G = gamma + gamma_bias saved for the backward pass (fp16 planes)
     __half* g_lo;
+    uint8_t* out8_lo;  // optional: e5m2 planes of the activation for a passes == 2 consumer
+    uint8_t* out8_hi;
     int C;
     // EPI_MODULATE_BWD
     const float* dt;         // fp32 NHWC [B,H,W,C]: gradient wrt the pre-activation t
@@ -189,6 +198,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmA[i]);
         tma_prefetch_desc(&p.tmB[0]);
         tma_prefetch_desc(&p.tmB[1]);
+        if (p.cb8) {
+            tma_prefetch_desc(&p.tmA8[0]);
+            tma_prefetch_desc(&p.tmA8[1]);
+            tma_prefetch_desc(&p.tmB8);
+        }
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -208,7 +222,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int k_iters = p.passes * p.ntaps * p.cb_total;
+    // fp16 K iterations, then (passes == 2) the fp8 correction: per tap 2 planes x cb8 blocks of 128 B
+    const int k16 = p.passes * p.ntaps * p.cb_total;
+    const int k_iters = k16 + p.ntaps * 2 * p.cb8;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -238,6 +254,24 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         }
                     }
                 }
+                if (p.cb8) {
+                    // fp8 correction: [a_lo * 2^8 | a] x [w * 2^-8 ; w_lo], same stage geometry in bytes
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
+                        for (int cb = 0; cb < 2 * p.cb8; ++cb, ++it) {
+                            const int s = it % STAGES;
+                            const uint32_t ph = (it / STAGES) & 1;
+                            mbar_wait(&empty_bar[s], ph ^ 1);
+                            mbar_expect_tx(&full_bar[s], A_BYTES + p.b_rows * 128);
+                            uint8_t* sa = smem + s * STAGE_BYTES;
+                            uint8_t* sb = sa + A_BYTES;
+                            const int pl = cb >= p.cb8 ? 1 : 0;
+                            tma_load_4d(&p.tmA8[pl], &full_bar[s], sa, (cb - pl * p.cb8) * 128,
+                                        w0 * p.a_step + dx, h0 * p.a_step + dy, b);
+                            tma_load_2d(&p.tmB8, &full_bar[s], sb, (tap * 2 * p.cb8 + cb) * 128, n0);
+                        }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -260,10 +294,16 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                     const uint32_t sb = sa + A_BYTES;
                     const uint64_t da = umma_desc_sw128(sa, 1024);
                     const uint64_t db = umma_desc_sw128(sb, 1024);
+                    if (kit < k16) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k) {
-                        // advance 16 elements (32 B) along K inside the swizzle atom: +2 (16 B units)
-                        umma_f16(tmem_d, da + 2 * k, db + 2 * k, p.idesc, (kit | k) != 0);
+                        for (int k = 0; k < BLOCK_K / 16; ++k) {
+                            // advance 16 elements (32 B) along K inside the swizzle atom: +2 (16 B units)
+                            umma_f16(tmem_d, da + 2 * k, db + 2 * k, p.idesc, (kit | k) != 0);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)  // 32 fp8 elements = the same 32 B per step
+                            umma_f8(tmem_d, da + 2 * k, db + 2 * k, p.idesc8, 1u);
                     }
                     umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
                 }
@@ -676,6 +716,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
                         const float* tp = T + pi * 33 + ecq * 4;
                         uint32_t ah[2], al[2], gh[2], gl[2];
+                        uint32_t q_lo = 0u, q_hi = 0u;
 #pragma unroll
                         for (int e2 = 0; e2 < 2; ++e2) {
                             __half hh[2], ll[2], ghh[2], gll[2];
@@ -691,6 +732,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                                 const float Gc = fminf(fmaxf(G, -65504.f), 65504.f);
                                 hh[k] = __float2half_rn(t);
                                 ll[k] = __float2half_rn(t - __half2float(hh[k]));
+                                if (p.out8_hi) {
+                                    q_lo |= (uint32_t)__nv_cvt_float_to_fp8((t - __half2float(hh[k])) * 256.f,
+                                                                            __NV_SATFINITE, __NV_E5M2) << (8 * e);
+                                    q_hi |= (uint32_t)__nv_cvt_float_to_fp8(t, __NV_SATFINITE, __NV_E5M2) << (8 * e);
+                                }
                                 ghh[k] = __float2half_rn(Gc);
                                 gll[k] = __float2half_rn(Gc - __half2float(ghh[k]));
                             }
@@ -703,6 +749,10 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + pe) = make_uint2(al[0], al[1]);
                         if (p.g_hi) *reinterpret_cast<uint2*>(p.g_hi + pe) = make_uint2(gh[0], gh[1]);
                         if (p.g_lo) *reinterpret_cast<uint2*>(p.g_lo + pe) = make_uint2(gl[0], gl[1]);
+                        if (p.out8_hi) {
+                            *reinterpret_cast<uint32_t*>(p.out8_lo + pe) = q_lo;
+                            *reinterpret_cast<uint32_t*>(p.out8_hi + pe) = q_hi;
+                        }
                     }
                     __syncwarp();  // T is rewritten by the next chunk
                 }
@@ -722,12 +772,18 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int fill_common(ConvParams& p, const dsee_conv_operands* ops) {
+static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_f8 = false) {
     DSEE_CHECK_ARG(ops != nullptr, "conv operands are NULL");
     DSEE_CHECK_ARG(ops->B > 0 && ops->H > 0 && ops->W > 0, "bad geometry B=%d H=%d W=%d", ops->B,
                    ops->H, ops->W);
-    DSEE_CHECK_ARG(ops->passes == 1 || ops->passes == 3, "passes must be 1 or 3 (got %d)",
+    DSEE_CHECK_ARG(ops->passes >= 1 && ops->passes <= 3, "passes must be 1, 2 or 3 (got %d)",
                    ops->passes);
+    if (ops->passes == 2) {
+        DSEE_CHECK_ARG(allow_f8, "passes == 2 (fp8 correction) is implemented for dsee_conv3x3_fwd only");
+        DSEE_CHECK_ARG(ops->a8_lo && ops->a8_hi && ops->w8, "passes == 2 needs a8_lo, a8_hi and w8");
+        DSEE_CHECK_ARG(ops->a_channels[1] == 0 && ops->a_channels[0] % 128 == 0 && ops->a_dtype == 0,
+                       "passes == 2 needs one fp16 A source with a multiple of 128 channels");
+    }
     DSEE_CHECK_ARG(ops->a_channels[0] > 0 && ops->a_channels[0] % BLOCK_K == 0 &&
                        ops->a_channels[1] >= 0 && ops->a_channels[1] % BLOCK_K == 0,
                    "A channel counts must be multiples of %d (got %d, %d)", BLOCK_K,
@@ -762,7 +818,7 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops) {
     p.num_tiles = p.B * p.tiles_h * p.tiles_w * p.n_tiles;
     p.cb0 = ops->a_channels[0] / BLOCK_K;
     p.cb_total = (ops->a_channels[0] + ops->a_channels[1]) / BLOCK_K;
-    p.passes = ops->passes;
+    p.passes = ops->passes == 2 ? 1 : ops->passes;  // fp16 passes; passes == 2 adds the fp8 phase
     p.n_total = ops->n_total;
     p.w_inv_scale = ops->w_inv_scale;
     p.a_inv_scale = ops->a_inv_scale;
@@ -789,6 +845,25 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops) {
             rc = encode_tmap_16b(&p.tmA[src * 2 + pl], base, 4, dims, strides, box, ops->a_dtype == 1);
             if (rc) return rc;
         }
+    }
+    if (ops->passes == 2) {
+        const int C = ops->a_channels[0];
+        p.cb8 = C / 128;
+        // kind::f8f6f4: fp32 accumulate, A = e5m2, B = e4m3, K-major both
+        p.idesc8 = (1u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                   ((uint32_t)(BLOCK_M >> 4) << 24);
+        for (int pl = 0; pl < 2; ++pl) {
+            uint64_t dims[4] = {(uint64_t)C, (uint64_t)ops->W, (uint64_t)ops->H, (uint64_t)ops->B};
+            uint64_t strides[3] = {(uint64_t)C, (uint64_t)ops->W * C, (uint64_t)ops->H * ops->W * C};
+            uint32_t box[4] = {128, TILE_W, TILE_H, 1};
+            rc = encode_tmap_8b(&p.tmA8[pl], pl ? ops->a8_hi : ops->a8_lo, 4, dims, strides, box);
+            if (rc) return rc;
+        }
+        uint64_t dims[2] = {(uint64_t)18 * C, (uint64_t)ops->n_total};
+        uint64_t strides[1] = {(uint64_t)18 * C};
+        uint32_t box[2] = {128, BLOCK_N};
+        rc = encode_tmap_8b(&p.tmB8, ops->w8, 2, dims, strides, box);
+        if (rc) return rc;
     }
     const uint64_t Ktot = (uint64_t)9 * (ops->a_channels[0] + ops->a_channels[1]);
     // the weight matrix is padded by the caller to a multiple of BLOCK_N rows? No: TMA zero-fills
@@ -839,7 +914,7 @@ extern "C" int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_e
                                 void* stream) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
-    int rc = fill_common(p, ops);
+    int rc = fill_common(p, ops, true);
     if (rc) return rc;
     DSEE_CHECK_ARG(epi && epi->out, "epilogue/out is NULL");
     DSEE_CHECK_ARG(epi->res_ups == 0 || epi->res_ups == 1, "res_ups must be 0 or 1");
@@ -1009,6 +1084,9 @@ extern "C" int dsee_spade_modulate_fwd(const dsee_conv_operands* ops, const dsee
     p.out_lo = (__half*)mod->out_lo;
     p.g_hi = (__half*)mod->g_hi;
     p.g_lo = (__half*)mod->g_lo;
+    DSEE_CHECK_ARG((mod->out8_lo == nullptr) == (mod->out8_hi == nullptr), "out8_lo / out8_hi go together");
+    p.out8_lo = (uint8_t*)mod->out8_lo;
+    p.out8_hi = (uint8_t*)mod->out8_hi;
     p.C = mod->C;
     return launch<EPI_MODULATE>(p, (cudaStream_t)stream);
 }

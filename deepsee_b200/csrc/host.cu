@@ -78,9 +78,26 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+static int encode_tmap_any(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank,
+                           const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                           const uint32_t* elem_strides);
+
 int encode_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, bool bf16,
                     const uint32_t* elem_strides) {
+    return encode_tmap_any(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                           base, rank, dims, strides_bytes, box, elem_strides);
+}
+
+int encode_tmap_8b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box) {
+    return encode_tmap_any(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, base, rank, dims, strides_bytes, box,
+                           nullptr);
+}
+
+static int encode_tmap_any(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank,
+                           const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                           const uint32_t* elem_strides) {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -104,7 +121,7 @@ int encode_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t
             return -1;
         }
     }
-    CUresult r = enc(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+    CUresult r = enc(out, dtype,
                      (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -7,6 +7,7 @@
 #include "../../include/deepsee_b200.h"
 
 #include <math.h>
+#include <cuda_fp8.h>
 
 namespace dsee {
 
@@ -174,6 +175,23 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, __half* __restri
     const size_t o = transpose ? ((size_t)c * 9 + (8 - tap)) * N + n : (size_t)i;
     out_hi[o] = h;
     if (out_lo) out_lo[o] = l;
+}
+
+// fp8 companion planes of a prepared weight (dsee_conv_operands.passes == 2):
+// out8[n][tap][0][c] = e4m3(ws * 2^-8), out8[n][tap][1][c] = e4m3(ws - fp16(ws)), ws = w * 2^e
+__global__ void prep_weight_f8_kernel(const float* __restrict__ w, const float* __restrict__ inv_scale,
+                                      uint8_t* __restrict__ out8, int N, int C) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint32_t)N * 9u * (uint32_t)C) return;
+    const float scale = 1.f / __ldg(inv_scale);
+    const int c = (int)(i % (uint32_t)C);
+    const int tap = (int)((i / (uint32_t)C) % 9u);
+    const int n = (int)(i / (9u * (uint32_t)C));
+    const float v = fminf(fmaxf(w[((size_t)n * C + c) * 9 + tap] * scale, -65504.f), 65504.f);
+    const float lo = v - __half2float(__float2half_rn(v));
+    uint8_t* o = out8 + ((size_t)n * 9 + tap) * 2 * C + c;
+    o[0] = __nv_cvt_float_to_fp8(v * (1.f / 256.f), __NV_SATFINITE, __NV_E4M3);
+    o[C] = __nv_cvt_float_to_fp8(lo, __NV_SATFINITE, __NV_E4M3);
 }
 
 // max over rows of sum_k |hi[row][k]| * inv_scale: one block per row of the prepared (scaled fp16)
@@ -662,6 +680,18 @@ extern "C" int dsee_prep_conv_weight(const float* w, void* out_hi, void* out_lo,
         DSEE_CUDA(cudaGetLastError());
         row_l1max_kernel<<<C, 256, 0, st>>>((const __half*)out_hi, 9 * N, inv_scale);
     }
+    LAUNCH_END();
+}
+
+extern "C" int dsee_prep_conv_weight_f8(const float* w, const float* inv_scale, void* out8, int N, int C,
+                                        void* stream) {
+    DSEE_CHECK_ARG(w && inv_scale && out8 && N > 0 && C > 0 && C % 128 == 0,
+                   "bad argument (C must be a multiple of 128)");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int64_t n = (int64_t)N * C * 9;
+    DSEE_CHECK_ARG(n < ((int64_t)1 << 31), "weight tensor too large");
+    prep_weight_f8_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, inv_scale, (uint8_t*)out8, N, C);
     LAUNCH_END();
 }
 

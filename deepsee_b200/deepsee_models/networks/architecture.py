@@ -69,10 +69,11 @@ class _NormState:
 
 
 def _norm_forward(blk, norm, pre, Wm, gb, bb, tab, tb, gctx, style, x, x_ups, H, W, part, count,
-                  ucount, noise, noise_w, passes, want_lo, save_g, out_lo=None):
+                  ucount, noise, noise_w, passes, want_lo, save_g, out_lo=None, out_f8=False):
     """BN affine + sources + K1 -> (activation planes, _NormState).  ``passes`` / ``want_lo`` are
-    K1's own (its GEMM operands); ``out_lo``: whether the consumer of the activation planes (the
-    main conv) runs 3 passes and needs their lo plane (default: same as want_lo)."""
+    K1's own (its GEMM operands); ``out_lo`` / ``out_f8``: whether the consumer of the activation
+    planes (the main conv) runs 3 passes and needs their lo plane (default: same as want_lo) / runs
+    the fp8 correction (passes == 2) and needs their e5m2 planes."""
     if out_lo is None:
         out_lo = want_lo
     st = _NormState()
@@ -95,7 +96,7 @@ def _norm_forward(blk, norm, pre, Wm, gb, bb, tab, tb, gctx, style, x, x_ups, H,
     st.srcs, st.meta = norm.build_sources(gctx, style, H, W, want_lo, table=tab, bias=tb)
     st.Wm, st.gb = Wm, gb
     r = ops.spade_modulate(st.srcs, pw, x, x_ups, st.sc, st.sh, gb, bb, noise=noise, noise_w=noise_w,
-                           passes=passes, want_lo=out_lo, save_g=save_g)
+                           passes=passes, want_lo=out_lo, save_g=save_g, want_f8=out_f8)
     a, st.g = r if save_g else (r, None)
     return a, st
 
@@ -183,9 +184,13 @@ class _ResBlockFn(torch.autograd.Function):
                 bb0, tab0, tb0, Wm1, gb1, bb1, tab1, tb1, nw_in, nw_skip, nw_mid):
         B, Hx, Wx, C = x.shape
         H, W = Hx << ups, Wx << ups
-        # operand passes of this block's gamma/beta GEMMs (p1) and main convs (p2): config.passes_for
+        # operand passes of this block's gamma/beta GEMMs (p1), main convs forward (p2) and the main
+        # convs' backward GEMMs (p2b): config.passes_for
         S = gctx.labels_full.shape[1]
         p1, p2 = config.passes_for('k1', H, S), config.passes_for('k2', H, S)
+        p2b = config.passes_for('k2b', H, S)
+        if p2b == 3 and p2 != 3:
+            p2b = 1  # the activation planes were produced without their lo half
         training = blk.training
         n_in, n_skip, n_mid = noises if noises is not None else (None, None, None)
         noisy = noises is not None
@@ -208,26 +213,28 @@ class _ResBlockFn(torch.autograd.Function):
                 count = ucount = B * H * W
         a0, st0 = _norm_forward(blk, blk.norm_0, pre.get('pwm0'), Wm0, gb0, bb0, tab0, tb0, gctx,
                                 style, x, ups, H, W, part, count, ucount, n_in,
-                                nw_in if noisy else None, p1, p1 == 3, save_g, out_lo=p2 == 3)
+                                nw_in if noisy else None, p1, p1 == 3, save_g, out_lo=p2 == 3, out_f8=p2 == 2)
         # ---- conv_0 (+ noise_middle) ----------------------------------------------------------
-        pw0 = pre.get('pw0') or ops.prep_conv_weight(W0.contiguous(), want_lo=p2 == 3)
+        pw0 = pre.get('pw0') or ops.prep_conv_weight(W0.contiguous(), want_lo=p2 == 3, want_f8=p2 == 2)
         r = ops.conv3x3([a0], pw0, b0, noises=[(n_mid, nw_mid)] if noisy else (), passes=p2,
                         want_stats=training)
         dx1, part1 = r if training else (r, None)
         # ---- norm_1 + actvn -------------------------------------------------------------------
         a1, st1 = _norm_forward(blk, blk.norm_1, pre.get('pwm1'), Wm1, gb1, bb1, tab1, tb1, gctx,
                                 style, dx1, 0, H, W, part1, B * H * W, B * H * W, None, None, p1,
-                                p1 == 3, save_g, out_lo=p2 == 3)
+                                p1 == 3, save_g, out_lo=p2 == 3, out_f8=p2 == 2)
         # ---- conv_1 + shortcut ------------------------------------------------------------------
-        pw1 = pre.get('pw1') or ops.prep_conv_weight(W1.contiguous(), want_lo=p2 == 3)
+        pw1 = pre.get('pw1') or ops.prep_conv_weight(W1.contiguous(), want_lo=p2 == 3, want_f8=p2 == 2)
         r = ops.conv3x3([a1], pw1, b1, residual=x, res_ups=ups,
                         noises=[(n_in, nw_in), (n_skip, nw_skip)] if noisy else (), passes=p2,
                         want_stats=training)
         out, stats = r if training else (r, None)
 
         if need_bwd:
+            # (the e5m2 planes of a passes == 2 forward are not needed again)
+            a0, a1 = ops.SplitPlanes(a0.hi, a0.lo), ops.SplitPlanes(a1.hi, a1.lo)
             ctx.s = dict(blk=blk, ups=ups, noises=noises, x=x, W0=W0, W1=W1, a0=a0, a1=a1, dx1=dx1,
-                         st0=st0, st1=st1, nw_in=nw_in, p1=p1, p2=p2)
+                         st0=st0, st1=st1, nw_in=nw_in, p1=p1, p2=p2b)
         if stats is None:
             stats = x.new_zeros(1)
         ctx.mark_non_differentiable(stats)
@@ -330,15 +337,15 @@ class SPADEResnetBlock(nn.Module):
         return SPADE
 
     # -- prepared main-conv weights (inference cache) -----------------------------------------------
-    def _prepared_conv(self, conv, w, name, want_lo):
+    def _prepared_conv(self, conv, w, name, want_lo, want_f8=False):
         src = [getattr(conv, n) for n in ('weight_orig', 'weight_u', 'weight_v') if hasattr(conv, n)]
         if not src:
             src = [conv.weight]
-        key = tuple((t.data_ptr(), t._version) for t in src) + (want_lo,)
+        key = tuple((t.data_ptr(), t._version) for t in src) + (want_lo, want_f8)
         hit = self._wcache.get(name)
         if hit is not None and hit[0] == key:
             return hit[1]
-        pw = ops.prep_conv_weight(w.detach().contiguous(), want_lo=want_lo)
+        pw = ops.prep_conv_weight(w.detach().contiguous(), want_lo=want_lo, want_f8=want_f8)
         self._wcache[name] = (key, pw)
         return pw
 
@@ -349,6 +356,7 @@ class SPADEResnetBlock(nn.Module):
         H, W = Hx << ups, Wx << ups
         S = ctx.labels_full.shape[1]
         lo1, lo2 = config.passes_for('k1', H, S) == 3, config.passes_for('k2', H, S) == 3
+        f82 = config.passes_for('k2', H, S) == 2
         noises = None
         nw = (None, None, None)
         if self.add_noise:
@@ -362,8 +370,8 @@ class SPADEResnetBlock(nn.Module):
             pwm0, gb0, bb0 = self.norm_0.prepared(lo1)
             pwm1, gb1, bb1 = self.norm_1.prepared(lo1)
             pre = {'pwm0': pwm0, 'pwm1': pwm1,
-                   'pw0': self._prepared_conv(self.conv_0, W0, 'conv_0', lo2),
-                   'pw1': self._prepared_conv(self.conv_1, W1, 'conv_1', lo2)}
+                   'pw0': self._prepared_conv(self.conv_0, W0, 'conv_0', lo2, f82),
+                   'pw1': self._prepared_conv(self.conv_1, W1, 'conv_1', lo2, f82)}
             Wm0 = Wm1 = None
         else:
             pre = None

@@ -11,10 +11,14 @@ import torch
 
 from . import _lib
 
-SplitPlanes = namedtuple("SplitPlanes", ["hi", "lo"])  # fp16 NHWC [B,H,W,C]; value = hi + lo
+# fp16 NHWC [B,H,W,C]; value = hi + lo.  f8: None, or the (lo * 2^8, value) e5m2 byte planes a
+# passes == 2 consumer (fp8 correction GEMM) reads next to hi
+SplitPlanes = namedtuple("SplitPlanes", ["hi", "lo", "f8"], defaults=[None])
 # gradient operand: fp16 NHWC planes of g * 2^e plus the device scalar 2^-e
 GradPlanes = namedtuple("GradPlanes", ["hi", "lo", "inv_scale"])
-PreparedWeight = namedtuple("PreparedWeight", ["hi", "lo", "inv_scale", "n_total", "cin"])
+# f8: None, or the e4m3 companion [N][9][2][C] of the planes (dsee_prep_conv_weight_f8)
+PreparedWeight = namedtuple("PreparedWeight", ["hi", "lo", "inv_scale", "n_total", "cin", "f8"],
+                            defaults=[None])
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -169,9 +173,10 @@ def style_gather(labels, style, want_lo=True):
     return SplitPlanes(hi, lo)
 
 
-def prep_conv_weight(w, want_lo=True, transpose=False):
+def prep_conv_weight(w, want_lo=True, transpose=False, want_f8=False):
     """fp32 [N,C,3,3] -> scaled fp16 split planes [N, 9*C] in (tap, c) order.
-    transpose=True: the backward-data operand [C, 9*N] (transposed, 180-degree rotated)."""
+    transpose=True: the backward-data operand [C, 9*N] (transposed, 180-degree rotated).
+    want_f8: also the e4m3 companion for the fp8 correction GEMM (passes == 2)."""
     _chk_cuda(w)
     assert w.dtype == torch.float32 and w.dim() == 4 and w.shape[2:] == (3, 3)
     N, Cin = w.shape[:2]
@@ -181,7 +186,12 @@ def prep_conv_weight(w, want_lo=True, transpose=False):
     inv = torch.empty(3, dtype=torch.float32, device=w.device)  # [2^-e, max|w|, row-L1 bound (transpose)]
     _lib.check(_lib.load().dsee_prep_conv_weight(_p(w), _p(hi), _p(lo), _p(inv), N, Cin,
                                                  int(transpose), _stream()))
-    return PreparedWeight(hi, lo, inv, rows, cols)
+    f8 = None
+    if want_f8:
+        assert not transpose
+        f8 = torch.empty((N, 9, 2, Cin), dtype=torch.uint8, device=w.device)
+        _lib.check(_lib.load().dsee_prep_conv_weight_f8(_p(w), _p(inv), _p(f8), N, Cin, _stream()))
+    return PreparedWeight(hi, lo, inv, rows, cols, f8)
 
 
 def split_f16(x, want_lo=True):
@@ -226,6 +236,12 @@ def _operands(sources, pw, passes):
     ops.w_inv_scale = pw.inv_scale.data_ptr()
     ops.n_total = pw.n_total
     ops.passes = passes
+    ops.a8_lo = ops.a8_hi = ops.w8 = 0
+    if passes == 2:
+        if a0.f8 is None or pw.f8 is None or len(sources) != 1:
+            raise RuntimeError("passes == 2 (fp8 correction) needs one A source with fp8 planes "
+                               "(spade_modulate(want_f8=True)) and a weight prepared with want_f8=True")
+        ops.a8_lo, ops.a8_hi, ops.w8 = a0.f8[0].data_ptr(), a0.f8[1].data_ptr(), pw.f8.data_ptr()
     ops.a_dtype = _DTYPE_CODE[a0.hi.dtype]
     ops.w_dtype = _DTYPE_CODE[pw.hi.dtype]
     inv = getattr(a0, "inv_scale", None)
@@ -281,9 +297,10 @@ def conv3x3(sources, pw, bias, residual=None, res_ups=0, noises=(), passes=3, wa
 
 
 def spade_modulate(sources, pw, x, x_ups, bn_scale, bn_shift, gamma_bias, beta_bias, noise=None,
-                   noise_w=None, passes=3, want_lo=True, save_g=False):
+                   noise_w=None, passes=3, want_lo=True, save_g=False, want_f8=False):
     """K1: gamma/beta conv + batch-norm apply + modulation + LeakyReLU -> fp16 split planes.
-    save_g: also return G = gamma + gamma_bias as split planes (what K1's backward multiplies by)."""
+    save_g: also return G = gamma + gamma_bias as split planes (what K1's backward multiplies by).
+    want_f8: also the e5m2 planes a passes == 2 main conv reads (fp8 correction GEMM)."""
     ops, (B, H, W) = _operands(sources, pw, passes)
     _chk_cuda(x, bn_scale, bn_shift, gamma_bias, beta_bias, noise, noise_w)
     Cc = x.shape[3]
@@ -307,12 +324,18 @@ def spade_modulate(sources, pw, x, x_ups, bn_scale, bn_shift, gamma_bias, beta_b
         glo = torch.empty_like(hi) if want_lo else None
     m.g_hi = ghi.data_ptr() if ghi is not None else 0
     m.g_lo = glo.data_ptr() if glo is not None else 0
+    f8 = None
+    if want_f8:
+        f8 = (torch.empty((B, H, W, Cc), dtype=torch.uint8, device=dev),
+              torch.empty((B, H, W, Cc), dtype=torch.uint8, device=dev))
+    m.out8_lo = f8[0].data_ptr() if f8 is not None else 0
+    m.out8_hi = f8[1].data_ptr() if f8 is not None else 0
     flops = 2.0 * 9 * pw.cin * pw.n_total * B * H * W
     _timed("modulate_%dx%d" % (H, W), flops,
            lambda: _lib.check(_lib.load().dsee_spade_modulate_fwd(C.byref(ops), C.byref(m), _stream())))
     if save_g:
-        return SplitPlanes(hi, lo), SplitPlanes(ghi, glo)
-    return SplitPlanes(hi, lo)
+        return SplitPlanes(hi, lo, f8), SplitPlanes(ghi, glo)
+    return SplitPlanes(hi, lo, f8)
 
 
 def spade_modulate_bwd_saved(g_planes, x, x_ups, bn_scale, bn_shift, dt, dt_amax, noise=None,

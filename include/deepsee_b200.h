@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DSEE_ABI_VERSION 2
+#define DSEE_ABI_VERSION 3
 
 /* ---- library ------------------------------------------------------------------------------ */
 int dsee_version(void);
@@ -91,6 +91,14 @@ int dsee_style_gather_fwd(const uint8_t* labels, const float* style, void* out_h
  * planes [C][9*N] with k = (8-tap)*N + n. */
 int dsee_prep_conv_weight(const float* w, void* out_hi, void* out_lo, float* inv_scale, int N,
                           int C, int transpose, void* stream);
+/* fp8 companion of the planes above for dsee_conv_operands.passes == 2 (same reference weight,
+ * architecture.py:40-44): with ws = w * 2^e (inv_scale[0] = 2^-e must already hold the value
+ * dsee_prep_conv_weight wrote for this weight) and hi = fp16(ws):
+ *   out8[n][tap][0][c] = e4m3(ws * 2^-8)    (pairs with the activation's lo plane * 2^8)
+ *   out8[n][tap][1][c] = e4m3(ws - hi)      (pairs with the activation itself)
+ * out8: [N][9][2][C] bytes, C a multiple of 128. */
+int dsee_prep_conv_weight_f8(const float* w, const float* inv_scale, void* out8, int N, int C,
+                             void* stream);
 /* fp32 NHWC [rows][C] -> fp16 split planes (used for tensors not produced by a fused epilogue). */
 int dsee_split_f16(const float* in, void* out_hi, void* out_lo, int64_t n, void* stream);
 
@@ -115,12 +123,22 @@ typedef struct {
     const void* w_lo;
     const float* w_inv_scale; /* device scalar */
     int n_total;
-    int passes; /* 1: hi*hi (TF32-class accuracy)   3: hi*hi + lo*hi + hi*lo (fp32-class) */
+    int passes; /* 1: hi*hi (TF32-class accuracy)   3: hi*hi + lo*hi + hi*lo (fp32-class)
+                   2: hi*hi + an fp8 correction GEMM for both operand-rounding terms (a8_lo * w8[0] +
+                      a8_hi * w8[1], tcgen05 kind::f8f6f4 at twice the fp16 rate, accumulated into the
+                      same TMEM accumulator): the cost of two fp16 passes, ~5 % of the 1-pass error.
+                      dsee_conv3x3_fwd only; one A source. */
     int a_dtype; /* element type of the A planes: 0 fp16, 1 bf16 */
     int w_dtype; /* element type of the weight planes; must equal a_dtype (tcgen05 kind::f16
                     rejects mixed A/B formats) */
     const float* a_inv_scale; /* NULL, or device scalar 2^-e of pre-scaled A planes (gradient
                                  operands from dsee_grad_prep / dsee_spade_modulate_bwd) */
+    /* passes == 2 only: e5m2 NHWC [B,H,W,C] planes written by dsee_spade_modulate_fwd
+     * (a8_lo = (a - a_hi) * 2^8, a8_hi = a) and the e4m3 weight from dsee_prep_conv_weight_f8
+     * ([n_total][9][2][C]: per tap the hi weights * 2^-8, then the lo residual of the fp16 plane). */
+    const void* a8_lo;
+    const void* a8_hi;
+    const void* w8;
 } dsee_conv_operands;
 
 /* K2.  Replaces conv_0 / conv_1 of SPADEResnetBlock (architecture.py:34-35,98,122) plus what the
@@ -233,6 +251,10 @@ typedef struct {
     void* g_hi;
     void* g_lo;
     unsigned long long noise_seed; /* used when noise == NULL and noise_w != NULL */
+    /* optional: e5m2 NHWC [B,H,W,C] planes of the activation for a consumer that runs the fp8
+     * correction (dsee_conv_operands.passes == 2): out8_lo = (t - fp16(t)) * 2^8, out8_hi = t */
+    void* out8_lo;
+    void* out8_hi;
 } dsee_modulate_args;
 int dsee_spade_modulate_fwd(const dsee_conv_operands* ops, const dsee_modulate_args* mod,
                             void* stream);

@@ -39,12 +39,23 @@ def mk_opt(o):
 
 
 def policies(res):
-    """name -> pass_overrides dict (base passes = 1, config.passes3_upto = 0).  Round-2 finding of the
-    first version of this probe (profiles/r2_precision_probe_v1.json): K1's passes do not matter, so
-    the policies below only vary the main convs (k2)."""
-    P = {"all3": {(k, h): 3 for k in ("k1", "k2") for h in res}, "all1": {}}
-    for upto in res[-4:-1]:
-        P["k2 x3 upto %d" % upto] = {("k2", h): 3 for h in res if h <= upto}
+    """name -> pass_overrides dict (base passes = 1; every kernel listed explicitly).
+    v1 / v2 of this probe (profiles/r2_precision_probe_v{1,2}.json) showed the forward main convs (k2)
+    to be the dominant error source and K1 to matter in the low-resolution stages only; v3 compares
+    the candidates for the benched mode: k2 with the fp8 correction GEMM (passes 2) or 3 passes."""
+    S = res[-1]
+    low = [h for h in res if h <= S // 4]
+    P = {"all3": {(k, h): 3 for k in ("k1", "k2") for h in res}, "all1": {(k, h): 1 for k in ("k1", "k2") for h in res}}
+
+    def mk(k2, k1_low, k1_all=False):
+        d = {("k2", h): k2 for h in res}
+        d.update({("k1", h): (3 if (k1_all or (k1_low and h in low)) else 1) for h in res})
+        return d
+    P["k2=3, k1=1"] = mk(3, False)
+    P["k2=3, k1 x3 <= S/4"] = mk(3, True)
+    P["k2=2 (fp8 corr), k1=1"] = mk(2, False)
+    P["k2=2 (fp8 corr), k1 x3 <= S/4"] = mk(2, True)
+    P["k2=2 (fp8 corr), k1=3"] = mk(2, False, True)
     return P
 
 

@@ -42,6 +42,59 @@ def test_conv3x3_matches_torch(B, H, W, Cin, Cout, passes):
     assert err <= tol, (err, scale)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 128, 256), (2, 24, 40, 256, 512), (1, 32, 32, 512, 512)])
+def test_conv3x3_fp8_correction_matches_torch(B, H, W, Cin, Cout):
+    """passes == 2: one fp16 pass + the fp8 correction GEMM (kind::f8f6f4) for both operand-rounding
+    terms.  The fp8 planes are built here with torch's float8 casts (the kernels that produce them in
+    the model are checked against the same casts in test_spade_modulate_fp8_planes)."""
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + H + Cin + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda()
+    bias = torch.randn(Cout, generator=g).cuda()
+    ref = F.conv2d(x, w, bias, padding=1)
+    a = ops.split_f16(_nhwc(x))
+    xn = _nhwc(x)
+    lo = xn - a.hi.float()
+    f8 = ((lo * 256).to(torch.float8_e5m2).view(torch.uint8), xn.to(torch.float8_e5m2).view(torch.uint8))
+    a = ops.SplitPlanes(a.hi, None, f8)
+    pw = ops.prep_conv_weight(w, want_lo=False, want_f8=True)
+    # the weight's fp8 companion against torch's casts
+    scale = 1.0 / pw.inv_scale[0].item()
+    ws = (w * scale).permute(0, 2, 3, 1).reshape(Cout, 9, Cin)
+    want_hi = (ws / 256).to(torch.float8_e4m3fn).view(torch.uint8)
+    want_lo = (ws - ws.half().float()).to(torch.float8_e4m3fn).view(torch.uint8)
+    assert torch.equal(pw.f8[:, :, 0], want_hi) and torch.equal(pw.f8[:, :, 1], want_lo)
+    out1 = _nchw(ops.conv3x3([ops.SplitPlanes(a.hi, None)], pw, bias, passes=1))
+    out2 = _nchw(ops.conv3x3([a], pw, bias, passes=2))
+    s = ref.abs().max().item()
+    e1, e2 = (out1 - ref).abs().max().item() / s, (out2 - ref).abs().max().item() / s
+    print("1-pass rel err %.3e, fp16 + fp8 correction rel err %.3e" % (e1, e2))
+    # the correction removes >= 85 % of the 1-pass error (the fp8 operands carry ~3-6 % relative error)
+    assert e2 <= 0.15 * e1 + 2e-6 and e2 <= 6e-5
+
+
+def test_spade_modulate_fp8_planes():
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, H, W, C, nh = 1, 16, 16, 128, 128
+    actv = ops.split_f16(torch.randn(B, H, W, nh, generator=g).relu().cuda())
+    wm = (torch.randn(2 * C, nh, 3, 3, generator=g) / (3 * nh ** 0.5)).cuda()
+    pw = ops.prep_conv_weight(wm)
+    x = torch.randn(B, H, W, C, generator=g).cuda()
+    one, zero = torch.ones(C).cuda(), torch.zeros(C).cuda()
+    a = ops.spade_modulate([actv], pw, x, 0, one, zero, one, zero, passes=3, want_lo=True, want_f8=True)
+    t = a.hi.float() + a.lo.float()          # the fp32 activation to ~2^-22
+    assert a.f8 is not None and a.f8[0].dtype == torch.uint8
+    got_hi = a.f8[1].view(torch.float8_e5m2).float()
+    got_lo = a.f8[0].view(torch.float8_e5m2).float() / 256
+    # e5m2: 2 mantissa bits -> relative error <= 2^-3 (a half-ulp); below 2^-14 the format is
+    # subnormal with an absolute step of 2^-16
+    assert ((got_hi - t).abs() <= 0.126 * t.abs() + 2.0 ** -16).all()
+    lo = t - a.hi.float()
+    assert ((got_lo - lo).abs() <= 0.126 * lo.abs() + 2.0 ** -24).all()
+
+
 def test_conv3x3_residual_upsample_and_stats():
     from deepsee_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(7)
