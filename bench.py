@@ -190,6 +190,89 @@ def parity_leg(cfg):
                     "by tests/test_full_size_parity_gpu.py" % cfg["name"]}
 
 
+def ddp_parity_leg(world, rank, local):
+    """Data-parallel parity on the real NCCL ranks of this launch (N > 1): ONE training iteration of
+    a small model (16x16 -> 64x64, 128 channels) on a fixed global batch, (a) sharded over the ranks
+    with the gradient buckets / Sync-BN exchange of the product, (b) on the whole batch inside this
+    process with the process group ignored (parallel.local_mode).  Returns the largest relative
+    differences of the rank-averaged losses, the all-reduced gradients and the BN running statistics
+    - what tests/test_ddp_gpu.py asserts on a 2-GPU box, recorded by every multi-GPU bench run."""
+    import random
+    import torch
+    import torch.distributed as dist
+    from deepsee_b200 import parallel
+    from deepsee_b200.config import config
+    from deepsee_b200.managers.trainer_manager import TrainerManager
+    from deepsee_b200.options.configurations import make_opt
+    from deepsee_b200.util.synthetic import synthetic_batch, settle_spectral_norm
+    saved = config.passes
+    config.passes = 3
+    per = 2
+    kw = dict(isTrain=True, gpu_ids=[local], ngf=8, nef=8, ndf=8, start_size=16, crop_size=64, load_size=64,
+              add_noise=False, noisy_style_scale=0.0)
+
+    def build(batch):
+        torch.manual_seed(7)
+        mgr = TrainerManager(make_opt("8x_independent_256x256", batchSize=batch, **kw))
+        for net in (mgr.sr_model.netSR, mgr.sr_model.netE, mgr.sr_model.netD):
+            settle_spectral_norm(net)
+        parallel.broadcast_module(mgr.sr_model)
+        mgr.sr_model.train()
+        return mgr
+
+    def grads(mgr):
+        m = mgr.sr_model
+        named = list(m.netSR.named_parameters()) + [("E." + n, p) for n, p in m.netE.named_parameters()]
+        return {n: p.grad.detach().clone() for n, p in named if p.grad is not None}
+
+    try:
+        raw = synthetic_batch(make_opt("8x_independent_256x256", **kw), per * world, seed=4242)
+        raw["label"] = raw["label"].float()
+        # (a) sharded
+        mgr = build(per)
+        random.seed(0)
+        shard = {k: v[rank * per:(rank + 1) * per].clone() for k, v in raw.items()}
+        mgr.run_generator_one_step(dict(shard))
+        g_ddp = grads(mgr)
+        loss_ddp = {}
+        for k, v in mgr.get_latest_losses().items():
+            t = v.detach().mean().reshape(1).clone()
+            dist.all_reduce(t)
+            loss_ddp[k] = float(t) / world
+        rs_ddp = mgr.sr_model.netSR.state_dict()["G_middle_1.norm_1.param_free_norm.running_var"].clone()
+        # (b) whole batch, single-process semantics
+        with parallel.local_mode():
+            ref = build(per * world)
+            random.seed(0)
+            ref.run_generator_one_step({k: v.clone() for k, v in raw.items()})
+            g_ref = grads(ref)
+            loss_ref = {k: float(v.detach().mean()) for k, v in ref.get_latest_losses().items()}
+            rs_ref = ref.sr_model.netSR.state_dict()["G_middle_1.norm_1.param_free_norm.running_var"]
+        worst, worst_name = 0.0, None
+        for n, gr in g_ref.items():
+            if n not in g_ddp:
+                worst, worst_name = float("inf"), n + " (missing)"
+                break
+            e = float((g_ddp[n] - gr).abs().max()) / (float(gr.abs().max()) + 1e-12)
+            if e > worst:
+                worst, worst_name = e, n
+        res = {"ranks": world, "per_rank_batch": per, "sync_bn": bool(config.sync_bn_for("syncbatch")),
+               "loss_rel_diff": max(abs(loss_ddp[k] - loss_ref[k]) / max(1.0, abs(loss_ref[k])) for k in loss_ref),
+               "grad_max_rel_diff": worst, "grad_worst": worst_name, "grad_tensors": len(g_ref),
+               "grads_only_where_single_process_has_them": set(g_ddp) == set(g_ref),
+               "bn_running_var_rel_diff": float((rs_ddp - rs_ref).abs().max() / rs_ref.abs().max()),
+               "what": "1 training iteration, %d ranks x %d samples (NCCL gradient buckets%s) vs 1 process x %d "
+                       "samples, passes=3" % (world, per, " + Sync-BN" if config.sync_bn_for("syncbatch") else "",
+                                              per * world)}
+        t = torch.tensor([res["loss_rel_diff"], res["grad_max_rel_diff"], res["bn_running_var_rel_diff"]],
+                         device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res["loss_rel_diff"], res["grad_max_rel_diff"], res["bn_running_var_rel_diff"] = [float(x) for x in t]
+        return res
+    finally:
+        config.passes = saved
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -397,6 +480,12 @@ def main():
                 "tc_share_of_step": sum(v[1] for v in r["ksum"].values()) / r["ms"],
                 "sync_bn": r["sync_bn"], "peak_mem_gib": round(r["peak_mem"], 2),
             })
+    ddp_parity = None
+    if world > 1 and train and not args.no_extra:
+        try:
+            ddp_parity = ddp_parity_leg(world, rank, local)
+        except Exception as e:  # recorded, never fatal for the measurement
+            ddp_parity = {"error": repr(e)[:300]}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -452,6 +541,8 @@ def main():
     }
     if extras:
         line["configs"] = extras
+    if ddp_parity is not None:
+        line["ddp_parity"] = ddp_parity
     if not args.no_cpu_baseline and train and world == 1:
         cores = os.cpu_count()
         step = cpu_train_iteration_timer(cfg, cores)

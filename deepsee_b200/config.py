@@ -19,16 +19,18 @@ class _Config:
     #   * K1 runs 3 passes in stages up to `passes3_upto` pixels high ("auto" = a quarter of the output
     #     size: ~5 % of the FLOPs), 1 pass above;
     #   * every backward GEMM (dgrad, wgrad) runs 1 pass: gradients carry no 1e-3 forward bound.
+    #   * style encoder / discriminator convs: forward `ed_fwd_passes` (3), backward 1 pass.
     k2_fwd_passes = int(os.environ.get("DSEE_K2_FWD_PASSES", "2"))
+    ed_fwd_passes = int(os.environ.get("DSEE_ED_FWD_PASSES", "3"))
     passes3_upto = os.environ.get("DSEE_PASSES3_UPTO", "auto")
     # test / probe hook: {("k1" | "k2" | "k2b", H): passes} overrides of the rule above
     pass_overrides = {}
 
     def passes_for(self, kind, H, S=None):
         """Tensor-core operand passes of one generator kernel at feature-map height H of a generator
-        whose output is S pixels high.  kind: "k1" = the gamma/beta GEMM of a conditional norm layer
-        and the backward GEMMs that share its operands; "k2" = a main 3x3 conv, forward; "k2b" = the
-        backward GEMMs of a main conv (backward-data, weight gradient)."""
+        whose output is S pixels high.  kind: "k1" = the gamma/beta GEMM of a conditional norm layer,
+        forward; "k1b" = the backward GEMMs that share its operands; "k2" = a main 3x3 conv, forward;
+        "k2b" = the backward GEMMs of a main conv (backward-data, weight gradient)."""
         o = self.pass_overrides.get((kind, H))
         if o is not None:
             return o
@@ -36,7 +38,7 @@ class _Config:
             return 3
         if kind == "k2":
             return self.k2_fwd_passes
-        if kind == "k1":
+        if kind == "k1":  # forward only; "k1b" (its backward GEMMs) falls through to self.passes
             upto = self.passes3_upto
             if upto == "auto":
                 upto = (S // 4) if S else 0
@@ -49,9 +51,16 @@ class _Config:
         k2 = {1: "1 pass", 2: "1 fp16 pass + fp8 correction of both operand-rounding terms",
               3: "hi+lo split operands x3 passes"}[self.k2_fwd_passes]
         return ("fp16 operands, fp32 accumulate (TF32-class) for the gamma/beta GEMMs and all backward GEMMs; "
-                "forward main convs: %s; gamma/beta GEMMs of stages <= %s: x3 passes" %
+                "forward main convs: %s; forward gamma/beta GEMMs of stages <= %s and forward encoder / "
+                "discriminator convs: x3 passes" %
                 (k2, "1/4 of the output size" if self.passes3_upto == "auto" else "%s px" % self.passes3_upto))
 
+    # SEAN layers: fold the style branch into per-image modulation weights over the exact one-hot
+    # label planes (normalization.py:182-185,198-201: conv(style_map, W) = conv(onehot, W x style_b)),
+    # so K1's K per tap drops from 256 to 192 channels, the backward-data GEMM of the modulation
+    # halves (no gradient flows into a one-hot plane) and the gathered style_map is never built.
+    # Needs save_gamma.  0 = the gathered 128-channel style_map.
+    fold_style = os.environ.get("DSEE_FOLD_STYLE", "1") != "0"
     # Training: K1 saves G = gamma + gamma_bias (fp16 planes, +1-2 B per activation element) so its
     # backward is one streaming pass instead of re-running the gamma GEMM (0 = recompute).
     save_gamma = os.environ.get("DSEE_SAVE_GAMMA", "1") != "0"

@@ -71,6 +71,7 @@ struct alignas(64) ConvParams {
     CUtensorMap tmA8[2];
     CUtensorMap tmB8;
     int cb8;           // 128-channel blocks per fp8 plane (0 = no fp8 phase)
+    int w_brows;       // per-image weights: row offset of image b is b * w_brows (0 = shared)
     uint32_t idesc8;
     int B, H, W;       // tile space: the output pixels this launch computes, per image
     int Hm, Wm;        // output tensor dims in memory; pixel (y,x) of the tile space lives at
@@ -250,7 +251,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                             const int cl = src ? cb - p.cb0 : cb;
                             tma_load_4d(&p.tmA[src * 2 + pa], &full_bar[s], sa, cl * BLOCK_K,
                                         w0 * p.a_step + dx, h0 * p.a_step + dy, b);
-                            tma_load_2d(&p.tmB[pb], &full_bar[s], sb, p.tap_k[tap] + cb * BLOCK_K, n0);
+                            tma_load_2d(&p.tmB[pb], &full_bar[s], sb, p.tap_k[tap] + cb * BLOCK_K,
+                                        n0 + b * p.w_brows);
                         }
                     }
                 }
@@ -811,7 +813,13 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
         p.tap_dx[t] = (int8_t)(t % 3 - 1);
         p.tap_k[t] = t * (ops->a_channels[0] + ops->a_channels[1]);
     }
-    p.b_rows = BLOCK_N;
+    // MMA N = weight rows per TMA box: all of BLOCK_N, or the (16-aligned) n_total when it is smaller
+    p.b_rows = ops->n_total < BLOCK_N ? (ops->n_total + 15) / 16 * 16 : BLOCK_N;
+    DSEE_CHECK_ARG(ops->w_batch_rows == 0 || ops->w_batch_rows == ops->n_total,
+                   "w_batch_rows must be 0 or n_total");
+    DSEE_CHECK_ARG(ops->w_batch_rows == 0 || ops->n_total % BLOCK_N == 0,
+                   "per-image weights need n_total to be a multiple of %d", BLOCK_N);
+    p.w_brows = ops->w_batch_rows;
     p.tiles_w = (ops->W + TILE_W - 1) / TILE_W;
     p.tiles_h = (ops->H + TILE_H - 1) / TILE_H;
     p.n_tiles = (ops->n_total + BLOCK_N - 1) / BLOCK_N;
@@ -827,7 +835,7 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
                    "operand dtypes must both be 0 (fp16) or both 1 (bf16): tcgen05 kind::f16 rejects "
                    "mixed A/B formats");
     p.idesc = (1u << 4) | ((uint32_t)ops->a_dtype << 7) | ((uint32_t)ops->w_dtype << 10) |
-              ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+              ((uint32_t)(p.b_rows >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 
     for (int src = 0; src < 2; ++src) {
         const int C = ops->a_channels[src];
@@ -850,7 +858,7 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
         const int C = ops->a_channels[0];
         p.cb8 = C / 128;
         // kind::f8f6f4: fp32 accumulate, A = e5m2, B = e4m3, K-major both
-        p.idesc8 = (1u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+        p.idesc8 = (1u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(p.b_rows >> 3) << 17) |
                    ((uint32_t)(BLOCK_M >> 4) << 24);
         for (int pl = 0; pl < 2; ++pl) {
             uint64_t dims[4] = {(uint64_t)C, (uint64_t)ops->W, (uint64_t)ops->H, (uint64_t)ops->B};
@@ -861,7 +869,7 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
         }
         uint64_t dims[2] = {(uint64_t)18 * C, (uint64_t)ops->n_total};
         uint64_t strides[1] = {(uint64_t)18 * C};
-        uint32_t box[2] = {128, BLOCK_N};
+        uint32_t box[2] = {128, (uint32_t)p.b_rows};
         rc = encode_tmap_8b(&p.tmB8, ops->w8, 2, dims, strides, box);
         if (rc) return rc;
     }
@@ -874,9 +882,9 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
             p.tmB[pl] = p.tmB[0];
             continue;
         }
-        uint64_t dims[2] = {Ktot, (uint64_t)ops->n_total};
+        uint64_t dims[2] = {Ktot, (uint64_t)ops->n_total * (ops->w_batch_rows ? ops->B : 1)};
         uint64_t strides[1] = {Ktot * 2};
-        uint32_t box[2] = {BLOCK_K, BLOCK_N};
+        uint32_t box[2] = {BLOCK_K, (uint32_t)p.b_rows};
         rc = encode_tmap_16b(&p.tmB[pl], base, 2, dims, strides, box, ops->w_dtype == 1);
         if (rc) return rc;
     }

@@ -194,6 +194,31 @@ __global__ void prep_weight_f8_kernel(const float* __restrict__ w, const float* 
     o[C] = __nv_cvt_float_to_fp8(lo, __NV_SATFINITE, __NV_E4M3);
 }
 
+// Batched modulation weight (see dsee_prep_mod_weight_batched): out[b*N + n][tap][c],
+// c < Ca: wa[n][c][tap];  Ca <= c < Ca+Ls: ws[b][n][c-Ca][tap];  else 0.
+__global__ void prep_mod_weight_batched_kernel(const float* __restrict__ wa, const float* __restrict__ ws,
+                                               __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                               float* inv_scale, int B, int N, int Ca, int Ls, int Lp) {
+    const float scale = pow2_scale_for(inv_scale[1], 14);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) inv_scale[0] = 1.f / scale;
+    const uint32_t Ct = (uint32_t)(Ca + Lp);
+    if (i >= (uint32_t)B * N * 9u * Ct) return;
+    const int c = (int)(i % Ct);
+    const int tap = (int)((i / Ct) % 9u);
+    const uint32_t row = i / (9u * Ct);
+    const int n = (int)(row % (uint32_t)N), b = (int)(row / (uint32_t)N);
+    float v = 0.f;
+    if (c < Ca)
+        v = wa[((size_t)n * Ca + c) * 9 + tap];
+    else if (c - Ca < Ls)
+        v = ws[(((size_t)b * N + n) * Ls + (c - Ca)) * 9 + tap];
+    __half h, l;
+    split_f16(v * scale, h, l);
+    out_hi[i] = h;
+    if (out_lo) out_lo[i] = l;
+}
+
 // max over rows of sum_k |hi[row][k]| * inv_scale: one block per row of the prepared (scaled fp16)
 // planes; bounds |sum_k a[k] * w[row][k]| <= max|a| * result.
 __global__ void row_l1max_kernel(const __half* __restrict__ hi, int rowlen, float* inv_scale) {
@@ -692,6 +717,30 @@ extern "C" int dsee_prep_conv_weight_f8(const float* w, const float* inv_scale, 
     const int64_t n = (int64_t)N * C * 9;
     DSEE_CHECK_ARG(n < ((int64_t)1 << 31), "weight tensor too large");
     prep_weight_f8_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, inv_scale, (uint8_t*)out8, N, C);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_prep_mod_weight_batched(const float* wa, const float* ws, void* out_hi, void* out_lo,
+                                            float* inv_scale, int B, int N, int Ca, int Ls, int Lp,
+                                            void* stream) {
+    DSEE_CHECK_ARG(wa && ws && out_hi && inv_scale, "NULL pointer");
+    DSEE_CHECK_ARG(B > 0 && N > 0 && Ca > 0 && Ca % 64 == 0 && Ls > 0 && Ls <= Lp && Lp % 64 == 0,
+                   "bad shape (Ca, Lp multiples of 64; Ls <= Lp)");
+    int rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = (int64_t)B * N * 9 * (Ca + Lp);
+    DSEE_CHECK_ARG(total < ((int64_t)1 << 31), "weight tensor too large");
+    DSEE_CUDA(cudaMemsetAsync(inv_scale, 0, 2 * sizeof(float), st));
+    const int64_t na = (int64_t)N * Ca * 9, ns = (int64_t)B * N * Ls * 9;
+    int blocks = cdiv(na, 256 * 8);
+    amax_kernel<<<blocks > 1024 ? 1024 : blocks, 256, 0, st>>>(wa, na, inv_scale + 1);
+    count_launch();
+    blocks = cdiv(ns, 256 * 8);
+    amax_kernel<<<blocks > 1024 ? 1024 : blocks, 256, 0, st>>>(ws, ns, inv_scale + 1);
+    count_launch();
+    prep_mod_weight_batched_kernel<<<cdiv(total, 256), 256, 0, st>>>(wa, ws, (__half*)out_hi, (__half*)out_lo,
+                                                                     inv_scale, B, N, Ca, Ls, Lp);
     LAUNCH_END();
 }
 

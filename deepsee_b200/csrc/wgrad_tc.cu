@@ -241,12 +241,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 // out = sum_s partial[s] (fixed order), optionally transposing [n][T][c] -> [n][c][T].
 // block = (n, 32-channel slab): coalesced reads of T x 32 partial rows, smem transpose, coalesced
 // write of the 32*T contiguous outputs.
+// blockIdx.y = output group (per-image results: group g sums splits [g*splits, (g+1)*splits)).
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                     int splits, int n_total, int c_total, int to_nc9, int T) {
     __shared__ float tile[16][33];
     const int cblocks = c_total / 32;
     const int n = blockIdx.x / cblocks, c0 = (blockIdx.x % cblocks) * 32;
     const int64_t total = (int64_t)n_total * T * c_total;
+    partial += (size_t)blockIdx.y * splits * total;
+    out += (size_t)blockIdx.y * total;
     const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;  // 32 x 16 threads
     float a = 0.f;
     if (row < T) {
@@ -268,7 +271,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 
 using namespace dsee;
 
-static int wgrad_plan(int B, int H, int W, int n_total, int c_total, int* splits_out, int T = 9) {
+static int wgrad_plan(int B, int H, int W, int n_total, int c_total, int* splits_out, int T = 9,
+                      bool per_image = false) {
     const int ptiles = B * ((H + WG_TH - 1) / WG_TH) * ((W + WG_TW - 1) / WG_TW);
     const int n_tiles = (n_total + WG_M - 1) / WG_M;
     const int c_tiles = (c_total + WG_NMAX - 1) / WG_NMAX;
@@ -281,7 +285,10 @@ static int wgrad_plan(int B, int H, int W, int n_total, int c_total, int* splits
     const int sms = 148;
     int splits = 1;
     long best = -1;
-    for (int s = 1; s <= 16 && s <= ptiles; ++s) {
+    // per_image: split boundaries must coincide with image boundaries (ptiles = B * tiles per image,
+    // image-major), so the split count is a multiple of B
+    const int step = per_image ? B : 1, smax = per_image ? (B > 16 ? B : 16 / B * B) : 16;
+    for (int s = step; s <= smax && s <= ptiles; s += step) {
         const long waves = ((long)base * s + sms - 1) / sms;
         const long steps = (ptiles + s - 1) / s;
         const long cost = waves * (steps + 8);
@@ -305,7 +312,7 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
                       int Hi, int Wi, int n_total, int a_channels, int c_total, int KH, int KW,
                       int stride, int pad, int passes, float* workspace, float* dw, int layout_nc9,
                       void* stream, const void* a2_hi = nullptr, const void* a2_lo = nullptr,
-                      int a2_channels = 0) {
+                      int a2_channels = 0, bool per_image = false) {
     // H, W: dY (= forward output) size; Hi, Wi: activation (= forward input) size;
     // a_channels: channels stored in the activation planes, c_total: dW columns (a multiple of 64)
     const int T = KH * KW;
@@ -330,7 +337,7 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
     p.n_tiles = (n_total + WG_M - 1) / WG_M;
     p.c_tiles = (c_total + WG_NMAX - 1) / WG_NMAX;
     p.n_cols = c_total < WG_NMAX ? c_total : WG_NMAX;
-    p.ptiles = wgrad_plan(B, H, W, n_total, c_total, &p.splits, T);
+    p.ptiles = wgrad_plan(B, H, W, n_total, c_total, &p.splits, T, per_image);
     p.num_units = p.n_tiles * T * p.c_tiles * p.splits;
     p.passes = passes;
     p.partial = workspace;
@@ -390,8 +397,9 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
     DSEE_CUDA(cudaGetLastError());
     const int64_t total = (int64_t)n_total * T * c_total;
     (void)total;
-    wgrad_reduce_kernel<<<n_total * (c_total / 32), 512, 0, st>>>(workspace, dw, p.splits, n_total, c_total,
-                                                                  layout_nc9, T);
+    const int groups = per_image ? B : 1;
+    wgrad_reduce_kernel<<<dim3(n_total * (c_total / 32), groups), 512, 0, st>>>(
+        workspace, dw, p.splits / groups, n_total, c_total, layout_nc9, T);
     count_launch();
     DSEE_CUDA(cudaGetLastError());
     return 0;
@@ -431,6 +439,35 @@ extern "C" int dsee_conv3x3_wgrad2(const void* dy_hi, const void* dy_lo, const f
     return wgrad_impl(dy_hi, dy_lo, dy_inv_scale, a_hi[0], a_lo ? a_lo[0] : nullptr, nullptr, dtype, B, H,
                       W, H, W, n_total, a_channels[0], c_total, 3, 3, 1, 1, passes, workspace, dw,
                       layout_nc9, stream, a_hi[1], a_lo ? a_lo[1] : nullptr, a_channels[1]);
+}
+
+extern "C" int64_t dsee_conv3x3_wgrad_per_image_workspace_floats(int B, int H, int W, int n_total,
+                                                                 int c_total) {
+    int splits;
+    wgrad_plan(B, H, W, n_total, c_total, &splits, 9, true);
+    return (int64_t)splits * n_total * 9 * c_total;
+}
+
+extern "C" int dsee_conv3x3_wgrad2_per_image(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale,
+                                             const void* const* a_hi, const void* const* a_lo,
+                                             const int* a_channels, int dtype, int B, int H, int W,
+                                             int n_total, int passes, float* workspace, float* dw,
+                                             void* stream) {
+    DSEE_CHECK_ARG(dy_hi && a_hi && a_channels && a_hi[0] && workspace && dw, "NULL pointer");
+    DSEE_CHECK_ARG(B > 0 && H > 0 && W > 0, "bad geometry");
+    DSEE_CHECK_ARG(n_total % 128 == 0, "n_total must be a multiple of 128 (got %d)", n_total);
+    DSEE_CHECK_ARG(a_channels[0] > 0 && a_channels[0] % 64 == 0 && a_channels[1] >= 0 &&
+                       a_channels[1] % 64 == 0 && (a_channels[1] == 0 || a_hi[1]),
+                   "source channel counts must be multiples of 64");
+    const int c_total = a_channels[0] + a_channels[1];
+    DSEE_CHECK_ARG(c_total <= 256 || c_total % 256 == 0,
+                   "total channels must be at most 256 or a multiple of 256 (got %d)", c_total);
+    DSEE_CHECK_ARG(passes == 1 || (passes == 3 && dy_lo && a_lo && a_lo[0] && (a_channels[1] == 0 || a_lo[1])),
+                   "passes must be 1, or 3 with lo planes");
+    DSEE_CHECK_ARG(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+    return wgrad_impl(dy_hi, dy_lo, dy_inv_scale, a_hi[0], a_lo ? a_lo[0] : nullptr, nullptr, dtype, B, H,
+                      W, H, W, n_total, a_channels[0], c_total, 3, 3, 1, 1, passes, workspace, dw, 1, stream,
+                      a_hi[1], a_lo ? a_lo[1] : nullptr, a_channels[1], true);
 }
 
 extern "C" int64_t dsee_conv2d_tc_wgrad_workspace_floats(int B, int Ho, int Wo, int n_total, int Ci,

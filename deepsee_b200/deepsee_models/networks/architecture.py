@@ -27,7 +27,7 @@ import torch.nn.utils.spectral_norm as spectral_norm
 from ... import ops, parallel
 from ...config import config
 from .normalization import (SPADE, SEAN_Block, PureSEAN_Block, NoiseInjection, effective_weight,
-                            BN_EPS)
+                            fold_style_weight, BN_EPS)
 
 BN_MOMENTUM = 0.1
 
@@ -65,10 +65,10 @@ class _SideStream:
 
 class _NormState:
     """What K1's backward needs from one conditional-norm layer's forward."""
-    __slots__ = ("srcs", "meta", "Wm", "gb", "sc", "sh", "inv_count", "g", "sync")
+    __slots__ = ("srcs", "meta", "Wm", "Ws", "gb", "sc", "sh", "inv_count", "g", "sync")
 
 
-def _norm_forward(blk, norm, pre, Wm, gb, bb, tab, tb, gctx, style, x, x_ups, H, W, part, count,
+def _norm_forward(blk, norm, pre, Wm, Ws, gb, bb, tab, tb, gctx, style, x, x_ups, H, W, part, count,
                   ucount, noise, noise_w, passes, want_lo, save_g, out_lo=None, out_f8=False):
     """BN affine + sources + K1 -> (activation planes, _NormState).  ``passes`` / ``want_lo`` are
     K1's own (its GEMM operands); ``out_lo`` / ``out_f8``: whether the consumer of the activation
@@ -92,9 +92,15 @@ def _norm_forward(blk, norm, pre, Wm, gb, bb, tab, tb, gctx, style, x, x_ups, H,
     else:
         st.sc, st.sh = norm.eval_affine()
         st.inv_count = 0.0
-    pw = pre if pre is not None else ops.prep_conv_weight(Wm.contiguous(), want_lo=want_lo)
-    st.srcs, st.meta = norm.build_sources(gctx, style, H, W, want_lo, table=tab, bias=tb)
-    st.Wm, st.gb = Wm, gb
+    if pre is not None:
+        pw = pre
+    elif Ws is not None:  # folded style: shared actv columns + per-image one-hot columns
+        pw = ops.prep_mod_weight_batched(Wm.contiguous(), Ws.contiguous(), want_lo=want_lo)
+    else:
+        pw = ops.prep_conv_weight(Wm.contiguous(), want_lo=want_lo)
+    st.srcs, st.meta = norm.build_sources(gctx, style, H, W, want_lo, table=tab, bias=tb,
+                                          folded=Ws is not None)
+    st.Wm, st.Ws, st.gb = Wm, Ws, gb
     r = ops.spade_modulate(st.srcs, pw, x, x_ups, st.sc, st.sh, gb, bb, noise=noise, noise_w=noise_w,
                            passes=passes, want_lo=out_lo, save_g=save_g, want_f8=out_f8)
     a, st.g = r if save_g else (r, None)
@@ -102,7 +108,7 @@ def _norm_forward(blk, norm, pre, Wm, gb, bb, tab, tb, gctx, style, x, x_ups, H,
 
 
 def _norm_backward(norm, st, dt, dt_amax, x, x_ups, noise, noise_w, L, passes, want_lo, ss):
-    """K1 backward for one layer -> (dxhat, sums[4,C], dWm, dtab, dtb, dstyle)."""
+    """K1 backward for one layer -> (dxhat, sums[4,C], dWm, dtab, dtb, dstyle, dWs)."""
     C = x.shape[3]
     Wm = st.Wm
     cin = Wm.shape[1]
@@ -123,7 +129,7 @@ def _norm_backward(norm, st, dt, dt_amax, x, x_ups, noise, noise_w, L, passes, w
 def _conv_and_norm_backward(st, g, W, a, x, x_ups, noise, noise_w, L, p1, p2, ss):
     """Backward-data of a main conv (gradient planes ``g`` of its output, weight ``W``, input
     activation planes ``a``; ``p2`` passes) followed by K1's backward of the norm layer that produced
-    ``a`` (``p1`` passes for its GEMMs) -> (dxhat, sums[4,C], dWm, dtab, dtb, dstyle).  With the saved G
+    ``a`` (``p1`` passes for its GEMMs) -> (dxhat, sums[4,C], dWm, dtab, dtb, dstyle, dWs).  With the saved G
     planes both run as ONE kernel (ops.dgrad_modulate_bwd: dt stays in TMEM / registers); otherwise
     dgrad -> dt -> K1 backward."""
     pwT = ops.prep_conv_weight(W.contiguous(), want_lo=p2 == 3, transpose=True)
@@ -138,9 +144,19 @@ def _conv_and_norm_backward(st, g, W, a, x, x_ups, noise, noise_w, L, p1, p2, ss
 
 def _norm_backward_tail(st, dgb, L, passes, want_lo, ss):
     """From the [dG | dB] gradient planes: modulation-weight gradient, gradient of the sources
-    (mlp_shared table / bias, style matrix) -> (dWm, dtab, dtb, dstyle)."""
+    (mlp_shared table / bias, style matrix) -> (dWm, dtab, dtb, dstyle, dWs)."""
     Wm = st.Wm
-    dWm = ss.run(lambda: ops.conv3x3_wgrad_multi(dgb, st.srcs, passes=passes), dgb, *st.srcs)
+    dWs = None
+    if st.Ws is not None:
+        # folded style: one weight gradient per image; the actv columns are shared (sum over images),
+        # the label columns are the gradient of Ws.  Wm holds the actv columns only, so the
+        # backward-data GEMM below produces d(actv) and nothing for the (constant) one-hot planes.
+        nh = Wm.shape[1]
+        dfull = ss.run(lambda: ops.conv3x3_wgrad_per_image(dgb, st.srcs, passes=passes), dgb, *st.srcs)
+        dWm = ss.run(lambda: dfull[:, :, :nh].sum(0))
+        dWs = ss.run(lambda: dfull[:, :, nh:nh + st.Ws.shape[2]].contiguous())
+    else:
+        dWm = ss.run(lambda: ops.conv3x3_wgrad_multi(dgb, st.srcs, passes=passes), dgb, *st.srcs)
     pwT = ops.prep_conv_weight(Wm.contiguous(), want_lo=want_lo, transpose=True)
     dsrc, dsrc_amax = ops.conv3x3([dgb], pwT, None, passes=passes, want_amax=True, tag="dgrad_mod")
     del dgb
@@ -149,6 +165,8 @@ def _norm_backward_tail(st, dgb, L, passes, want_lo, ss):
     coff = 0
     for src, kind in zip(st.srcs, meta['kinds']):
         d = src.hi.shape[3]
+        if kind == 'onehot':
+            continue
         if kind == 'actv':
             onehot = meta['ctx'].onehot_at(*meta['fm'])
             t, b = ops.shared_mlp_bwd_tc(dsrc, dsrc_amax, coff, meta['actv'].hi, meta['labels'], onehot,
@@ -159,7 +177,7 @@ def _norm_backward_tail(st, dgb, L, passes, want_lo, ss):
             g = ops.style_gather_bwd(dsrc, coff, meta['labels'], L, d)
             dstyle = g if dstyle is None else dstyle + g
         coff += d
-    return dWm, dtab, dtb, dstyle
+    return dWm, dtab, dtb, dstyle, dWs
 
 
 def _sync_bwd_sums(nsums, st):
@@ -181,7 +199,7 @@ class _ResBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, blk, gctx, ups, stats_in, noises, pre, grad_on, x, style, W0, b0, W1, b1, Wm0, gb0,
-                bb0, tab0, tb0, Wm1, gb1, bb1, tab1, tb1, nw_in, nw_skip, nw_mid):
+                bb0, tab0, tb0, Wm1, gb1, bb1, tab1, tb1, nw_in, nw_skip, nw_mid, Ws0=None, Ws1=None):
         B, Hx, Wx, C = x.shape
         H, W = Hx << ups, Wx << ups
         # operand passes of this block's gamma/beta GEMMs (p1), main convs forward (p2) and the main
@@ -191,6 +209,9 @@ class _ResBlockFn(torch.autograd.Function):
         p2b = config.passes_for('k2b', H, S)
         if p2b == 3 and p2 != 3:
             p2b = 1  # the activation planes were produced without their lo half
+        p1b = config.passes_for('k1b', H, S)
+        if p1b == 3 and p1 != 3:
+            p1b = 1  # same for K1's sources
         training = blk.training
         n_in, n_skip, n_mid = noises if noises is not None else (None, None, None)
         noisy = noises is not None
@@ -211,7 +232,7 @@ class _ResBlockFn(torch.autograd.Function):
             else:
                 part = ops.bn_stats(x, ups, n_in, nw_in if noisy else None)
                 count = ucount = B * H * W
-        a0, st0 = _norm_forward(blk, blk.norm_0, pre.get('pwm0'), Wm0, gb0, bb0, tab0, tb0, gctx,
+        a0, st0 = _norm_forward(blk, blk.norm_0, pre.get('pwm0'), Wm0, Ws0, gb0, bb0, tab0, tb0, gctx,
                                 style, x, ups, H, W, part, count, ucount, n_in,
                                 nw_in if noisy else None, p1, p1 == 3, save_g, out_lo=p2 == 3, out_f8=p2 == 2)
         # ---- conv_0 (+ noise_middle) ----------------------------------------------------------
@@ -220,7 +241,7 @@ class _ResBlockFn(torch.autograd.Function):
                         want_stats=training)
         dx1, part1 = r if training else (r, None)
         # ---- norm_1 + actvn -------------------------------------------------------------------
-        a1, st1 = _norm_forward(blk, blk.norm_1, pre.get('pwm1'), Wm1, gb1, bb1, tab1, tb1, gctx,
+        a1, st1 = _norm_forward(blk, blk.norm_1, pre.get('pwm1'), Wm1, Ws1, gb1, bb1, tab1, tb1, gctx,
                                 style, dx1, 0, H, W, part1, B * H * W, B * H * W, None, None, p1,
                                 p1 == 3, save_g, out_lo=p2 == 3, out_f8=p2 == 2)
         # ---- conv_1 + shortcut ------------------------------------------------------------------
@@ -234,7 +255,7 @@ class _ResBlockFn(torch.autograd.Function):
             # (the e5m2 planes of a passes == 2 forward are not needed again)
             a0, a1 = ops.SplitPlanes(a0.hi, a0.lo), ops.SplitPlanes(a1.hi, a1.lo)
             ctx.s = dict(blk=blk, ups=ups, noises=noises, x=x, W0=W0, W1=W1, a0=a0, a1=a1, dx1=dx1,
-                         st0=st0, st1=st1, nw_in=nw_in, p1=p1, p2=p2b)
+                         st0=st0, st1=st1, nw_in=nw_in, p1=p1b, p2=p2b)
         if stats is None:
             stats = x.new_zeros(1)
         ctx.mark_non_differentiable(stats)
@@ -264,7 +285,7 @@ class _ResBlockFn(torch.autograd.Function):
         ss = _SideStream()
         dW1 = ss.run(lambda: ops.conv3x3_wgrad(g1, a1, passes=p2), g1, a1)
         # ---- backward-data of conv_1 + norm_1 --------------------------------------------------
-        dxhat, nsums, dWm1, dtab1, dtb1, dstyle1 = _conv_and_norm_backward(
+        dxhat, nsums, dWm1, dtab1, dtb1, dstyle1, dWs1 = _conv_and_norm_backward(
             st1, g1, s['W1'], a1, dx1, 0, None, None, L, p1, p2, ss)
         del g1
         dgb1, dbb1 = nsums[2], nsums[3]
@@ -279,7 +300,7 @@ class _ResBlockFn(torch.autograd.Function):
         dW0 = ss.run(lambda: ops.conv3x3_wgrad(g0, a0, passes=p2), g0, a0)
         # ---- backward-data of conv_0 + norm_0 (reads x through the folded upsample, + noise_in) -
         nw_in = s['nw_in'] if noisy else None
-        dxhat, nsums, dWm0, dtab0, dtb0, dstyle0 = _conv_and_norm_backward(
+        dxhat, nsums, dWm0, dtab0, dtb0, dstyle0, dWs0 = _conv_and_norm_backward(
             st0, g0, s['W0'], a0, x, ups, n_in, nw_in, L, p1, p2, ss)
         del g0
         dgb0, dbb0 = nsums[2], nsums[3]
@@ -296,7 +317,7 @@ class _ResBlockFn(torch.autograd.Function):
         ss.join()
         ctx.s = None
         return (None, None, None, None, None, None, None, dx, dstyle, dW0, db0, dW1, db1, dWm0, dgb0, dbb0,
-                dtab0, dtb0, dWm1, dgb1, dbb1, dtab1, dtb1, dnw_in, dnw_skip, dnw_mid)
+                dtab0, dtb0, dWm1, dgb1, dbb1, dtab1, dtb1, dnw_in, dnw_skip, dnw_mid, dWs0, dWs1)
 
 
 class SPADEResnetBlock(nn.Module):
@@ -366,23 +387,33 @@ class SPADEResnetBlock(nn.Module):
         # spectral norm: W_orig / sigma (one power iteration when training), an autograd tensor
         W0, W1 = effective_weight(self.conv_0), effective_weight(self.conv_1)
         cached = not self.training and not torch.is_grad_enabled()
+        # SEAN layers at or below max_fm_size: the style branch runs as per-image weights over the
+        # one-hot label planes (config.fold_style), rebuilt from the style matrix on every call
+        fold = [n.folds_style(H, W) and ctx.style is not None for n in (self.norm_0, self.norm_1)]
+        Wm, gbs, bbs, pwm = [None, None], [None, None], [None, None], [None, None]
+        for i, n in enumerate((self.norm_0, self.norm_1)):
+            if cached and not fold[i]:
+                pwm[i], gbs[i], bbs[i] = n.prepared(lo1)
+            elif cached:
+                Wm[i], gbs[i], bbs[i] = n.combined_cached()
+            else:
+                Wm[i], gbs[i], bbs[i] = n.combined_weight()
+        Ws = [None, None]
+        for i in range(2):
+            if fold[i]:
+                Wm[i], Ws[i] = fold_style_weight(Wm[i], ctx.style)
+        (Wm0, Wm1), (gb0, gb1), (bb0, bb1) = Wm, gbs, bbs
+        pre = None
         if cached:
-            pwm0, gb0, bb0 = self.norm_0.prepared(lo1)
-            pwm1, gb1, bb1 = self.norm_1.prepared(lo1)
-            pre = {'pwm0': pwm0, 'pwm1': pwm1,
+            pre = {'pwm0': pwm[0], 'pwm1': pwm[1],
                    'pw0': self._prepared_conv(self.conv_0, W0, 'conv_0', lo2, f82),
                    'pw1': self._prepared_conv(self.conv_1, W1, 'conv_1', lo2, f82)}
-            Wm0 = Wm1 = None
-        else:
-            pre = None
-            Wm0, gb0, bb0 = self.norm_0.combined_weight()
-            Wm1, gb1, bb1 = self.norm_1.combined_weight()
         tab0, tb0 = self.norm_0.table_and_bias()
         tab1, tb1 = self.norm_1.table_and_bias()
         out, stats = _ResBlockFn.apply(self, ctx, ups, stats_in, noises, pre, torch.is_grad_enabled(), x,
                                        ctx.style, W0,
                                        self.conv_0.bias, W1, self.conv_1.bias, Wm0, gb0, bb0, tab0,
-                                       tb0, Wm1, gb1, bb1, tab1, tb1, *nw)
+                                       tb0, Wm1, gb1, bb1, tab1, tb1, *nw, Ws[0], Ws[1])
         return out, (stats if self.training else None)
 
     def forward(self, x, seg, style=None, split_location=-1):

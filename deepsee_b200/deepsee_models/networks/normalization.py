@@ -135,6 +135,18 @@ class GenContext:
         return self._cache[key]
 
 
+def fold_style_weight(Wm, style, nh=NHIDDEN):
+    """Splits a SEAN layer's combined modulation weight [2C, nh + d, 3, 3] into the shared
+    mlp_shared-activation part Wa [2C, nh, 3, 3] and the per-image style part
+        Ws[b, o, l, ky, kx] = sum_s Wm[o, nh + s, ky, kx] * style[b, l, s]      ([B, 2C, L, 3, 3]),
+    i.e. conv(style_map, W_sty) with style_map[b,:,y,x] = style[b, label(y,x), :]
+    (normalization.py:182-185,198-201) rewritten as a conv over the one-hot label map.  Plain torch
+    ops: autograd carries the gradient of Ws back into the style matrix and the weights."""
+    Wa = Wm[:, :nh].contiguous()
+    Ws = torch.einsum('osyx,bls->bolyx', Wm[:, nh:], style).contiguous()
+    return Wa, Ws
+
+
 def _interleave_gamma_beta(wg, wb):
     """[C,Cin,3,3] x2 -> [2C,Cin,3,3] with rows [g(0..127) | b(0..127) | g(128..255) | ...]."""
     C = wg.shape[0]
@@ -171,7 +183,14 @@ class _CondNormBase(nn.Module):
         mx = getattr(self.opt, 'max_fm_size', 1 << 30) if self.kind != 'spade' else 1 << 30
         return min(H, mx), min(W, mx)
 
-    def build_sources(self, ctx, style, H, W, want_lo, table=None, bias=None):
+    def folds_style(self, H, W):
+        """True when this layer's style branch runs as per-image weights over the one-hot label planes
+        (config.fold_style): a SEAN layer at or below max_fm_size."""
+        from ...config import config
+        return (self.kind == 'sean' and config.fold_style and config.save_gamma and
+                self.fm_size(H, W) == (H, W))
+
+    def build_sources(self, ctx, style, H, W, want_lo, table=None, bias=None, folded=False):
         """-> (list of SplitPlanes feeding K1's A operand at resolution (H, W), meta). ``meta``
         records what each source is ('actv' = mlp_shared output, 'style' = gathered style matrix),
         the label map and the folded-upsample flag - what the backward pass needs."""
@@ -197,6 +216,12 @@ class _CondNormBase(nn.Module):
         if ups == 1:
             # normalization.py:188-190 / 275-277: style_map := upsampled actv (style is dropped)
             style_map, skind = actv, 'actv'
+        elif folded:
+            # the style branch lives in the per-image weights (fold_style_weight): K1 reads the exact
+            # one-hot planes instead of a gathered style_map
+            oh = ctx.onehot_at(fh, fw)
+            style_map = ops.SplitPlanes(oh.hi, ops._zeros_like_cached(oh.hi) if want_lo else None)
+            skind = 'onehot'
         else:
             if style is None:
                 raise RuntimeError('%s needs a style matrix z' % type(self).__name__)
@@ -242,6 +267,18 @@ class _CondNormBase(nn.Module):
             wg, wb = self.mlp_style_gamma.weight, self.mlp_style_beta.weight
             gb, bb = self.mlp_style_gamma.bias, self.mlp_style_beta.bias
         return _interleave_gamma_beta(wg, wb), gb.contiguous(), bb.contiguous()
+
+    def combined_cached(self):
+        """combined_weight() as plain fp32 tensors, cached while the parameters are unchanged
+        (inference with folded style: the per-image weights are rebuilt from it every call)."""
+        key = self._cache_key('raw')
+        cached = getattr(self, '_raw_cache', None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        with torch.no_grad():
+            val = tuple(t.detach() for t in self.combined_weight())
+        self._raw_cache = (key, val)
+        return val
 
     def _cache_key(self, want_lo):
         return tuple((p.data_ptr(), p._version) for p in self.parameters()) + (want_lo,)

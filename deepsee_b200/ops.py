@@ -17,8 +17,9 @@ SplitPlanes = namedtuple("SplitPlanes", ["hi", "lo", "f8"], defaults=[None])
 # gradient operand: fp16 NHWC planes of g * 2^e plus the device scalar 2^-e
 GradPlanes = namedtuple("GradPlanes", ["hi", "lo", "inv_scale"])
 # f8: None, or the e4m3 companion [N][9][2][C] of the planes (dsee_prep_conv_weight_f8)
-PreparedWeight = namedtuple("PreparedWeight", ["hi", "lo", "inv_scale", "n_total", "cin", "f8"],
-                            defaults=[None])
+# batched: the planes hold one [n_total, K] matrix per image (prep_mod_weight_batched)
+PreparedWeight = namedtuple("PreparedWeight", ["hi", "lo", "inv_scale", "n_total", "cin", "f8", "batched"],
+                            defaults=[None, False])
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -194,6 +195,21 @@ def prep_conv_weight(w, want_lo=True, transpose=False, want_f8=False):
     return PreparedWeight(hi, lo, inv, rows, cols, f8)
 
 
+def prep_mod_weight_batched(wa, ws, Lp=64, want_lo=True):
+    """SEAN modulation weight with the style branch folded into per-image weights over the one-hot
+    label planes: wa fp32 [N,Ca,3,3] (shared), ws fp32 [B,N,Ls,3,3] -> planes [B*N, 9*(Ca+Lp)]."""
+    _chk_cuda(wa, ws)
+    N, Ca = wa.shape[:2]
+    B, N2, Ls = ws.shape[:3]
+    assert N2 == N and tuple(wa.shape[2:]) == (3, 3) and tuple(ws.shape[3:]) == (3, 3)
+    hi = torch.empty((B * N, 9 * (Ca + Lp)), dtype=torch.float16, device=wa.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    inv = torch.empty(2, dtype=torch.float32, device=wa.device)
+    _lib.check(_lib.load().dsee_prep_mod_weight_batched(_p(wa), _p(ws), _p(hi), _p(lo), _p(inv), B, N, Ca,
+                                                        Ls, Lp, _stream()))
+    return PreparedWeight(hi, lo, inv, N, Ca + Lp, None, True)
+
+
 def split_f16(x, want_lo=True):
     _chk_cuda(x)
     assert x.dtype == torch.float32
@@ -236,6 +252,9 @@ def _operands(sources, pw, passes):
     ops.w_inv_scale = pw.inv_scale.data_ptr()
     ops.n_total = pw.n_total
     ops.passes = passes
+    ops.w_batch_rows = pw.n_total if pw.batched else 0
+    if pw.batched:
+        assert pw.hi.shape[0] == B * pw.n_total, "batched weight prepared for a different batch size"
     ops.a8_lo = ops.a8_hi = ops.w8 = 0
     if passes == 2:
         if a0.f8 is None or pw.f8 is None or len(sources) != 1:
@@ -469,6 +488,27 @@ def conv3x3_wgrad_multi(dy, sources, passes=3):
     _timed("wgrad_%dx%d" % (H, W), flops, lambda: _lib.check(lib.dsee_conv3x3_wgrad2(
         _p(dy.hi), _p(dy.lo), _p(getattr(dy, "inv_scale", None)), a_hi, a_lo, ach,
         _DTYPE_CODE[dy.hi.dtype], B, H, W, N, passes, _p(ws), _p(dw), 1, _stream())))
+    return dw
+
+
+def conv3x3_wgrad_per_image(dy, sources, passes=3):
+    """conv3x3_wgrad_multi with one result per image -> dW [B, N, C0 + C1, 3, 3]."""
+    srcs = list(sources) + [None] * (2 - len(sources))
+    _chk_cuda(dy.hi, dy.lo, *[t for s_ in sources for t in (s_.hi, s_.lo)])
+    B, H, W, N = dy.hi.shape
+    chans = [s_.hi.shape[3] if s_ is not None else 0 for s_ in srcs]
+    ctot = sum(chans)
+    lib = _lib.load()
+    ws = torch.empty(lib.dsee_conv3x3_wgrad_per_image_workspace_floats(B, H, W, N, ctot),
+                     dtype=torch.float32, device=dy.hi.device)
+    dw = torch.empty((B, N, ctot, 3, 3), dtype=torch.float32, device=dy.hi.device)
+    a_hi = (C.c_void_p * 2)(*[(s_.hi.data_ptr() if s_ is not None else 0) for s_ in srcs])
+    a_lo = (C.c_void_p * 2)(*[(s_.lo.data_ptr() if s_ is not None and s_.lo is not None else 0) for s_ in srcs])
+    ach = (C.c_int * 2)(*chans)
+    flops = 2.0 * 9 * ctot * N * B * H * W
+    _timed("wgrad_%dx%d" % (H, W), flops, lambda: _lib.check(lib.dsee_conv3x3_wgrad2_per_image(
+        _p(dy.hi), _p(dy.lo), _p(getattr(dy, "inv_scale", None)), a_hi, a_lo, ach,
+        _DTYPE_CODE[dy.hi.dtype], B, H, W, N, passes, _p(ws), _p(dw), _stream())))
     return dw
 
 
@@ -920,14 +960,18 @@ class Conv2dTCFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, stride, pad, ups, lrelu):
         from .config import config
+        # forward at config.ed_fwd_passes (3 by default: predictions, features and hinge / LeakyReLU
+        # kink decisions are fp32-class, 0.4 % of the step's FLOPs); backward GEMMs at config.passes
+        passes_f = 3 if config.passes == 3 else config.ed_fwd_passes
         passes = config.passes
-        want_lo = passes == 3
+        want_lo = passes_f == 3
         N, Cw, KH, KW = w.shape
         planes = split_f16_ups2(x, want_lo) if ups else split_f16(x, want_lo)
         B, Hu, Wu, Cx = planes.hi.shape
         Ho, Wo = (Hu + 2 * pad - KH) // stride + 1, (Wu + 2 * pad - KW) // stride + 1
         pw = prep_conv_weight_ex(w.contiguous(), want_lo)
-        out = conv2d_tc(planes, pw, bias, KH, KW, stride, pad, (Ho, Wo), passes=passes, lrelu=lrelu)
+        out = conv2d_tc(planes, pw, bias, KH, KW, stride, pad, (Ho, Wo), passes=passes_f, lrelu=lrelu)
+        want_lo = passes == 3
         ctx.cfg = (stride, pad, ups, lrelu, bias is not None, passes, want_lo, tuple(x.shape))
         ctx.planes = planes
         ctx.save_for_backward(w, out if lrelu else None)

@@ -18,8 +18,25 @@ import torch
 import torch.distributed as dist
 
 
+_LOCAL = [False]
+
+
+class local_mode:
+    """`with local_mode():` this process behaves like a single-process run (no gradient buckets, no
+    Sync-BN exchange, no broadcasts) although a process group exists - the single-process reference
+    of the data-parallel parity check that bench.py runs at N > 1."""
+
+    def __enter__(self):
+        self.saved = _LOCAL[0]
+        _LOCAL[0] = True
+
+    def __exit__(self, *exc):
+        _LOCAL[0] = self.saved
+        return False
+
+
 def is_dist():
-    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    return (not _LOCAL[0]) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
 def world_size():

@@ -99,6 +99,18 @@ int dsee_prep_conv_weight(const float* w, void* out_hi, void* out_lo, float* inv
  * out8: [N][9][2][C] bytes, C a multiple of 128. */
 int dsee_prep_conv_weight_f8(const float* w, const float* inv_scale, void* out8, int N, int C,
                              void* stream);
+/* Modulation weight of a SEAN layer with the style branch folded into per-image weights
+ * (normalization.py:182-185,198-213): style_map[b,:,y,x] = style[b, label(y,x), :] makes
+ *   conv(style_map, W_sty)[b,o,y,x] = sum_{tap,l} onehot[b,l,(y,x)+tap] * Ws[b,o,l,tap],
+ *   Ws[b,o,l,tap] = sum_s W_sty[o,s,tap] * style[b,l,s]
+ * so K1 reads the exact one-hot planes (Lp channels, Lp = 64) instead of a gathered 128-channel
+ * style map: K per tap 256 -> 192.  wa fp32 [N][Ca][3][3] (the mlp_shared-activation columns, shared
+ * by all images), ws fp32 [B][N][Ls][3][3] (Ls <= Lp label columns) -> planes [B*N][9*(Ca+Lp)],
+ * k = tap*(Ca+Lp) + c (zeros for Ls <= c - Ca < Lp), one power-of-two scale for everything;
+ * inv_scale: device float[2] = (2^-e, max|w|). */
+int dsee_prep_mod_weight_batched(const float* wa, const float* ws, void* out_hi, void* out_lo,
+                                 float* inv_scale, int B, int N, int Ca, int Ls, int Lp, void* stream);
+
 /* fp32 NHWC [rows][C] -> fp16 split planes (used for tensors not produced by a fused epilogue). */
 int dsee_split_f16(const float* in, void* out_hi, void* out_lo, int64_t n, void* stream);
 
@@ -139,6 +151,10 @@ typedef struct {
     const void* a8_lo;
     const void* a8_hi;
     const void* w8;
+    /* 0: one weight matrix for all images.  > 0 (= n_total): per-image weights, the planes hold
+     * [B * n_total][K] and image b reads rows b * w_batch_rows ... (the SEAN style branch folded into
+     * per-image weights over the one-hot label planes, dsee_prep_mod_weight_batched) */
+    int w_batch_rows;
 } dsee_conv_operands;
 
 /* K2.  Replaces conv_0 / conv_1 of SPADEResnetBlock (architecture.py:34-35,98,122) plus what the
@@ -212,6 +228,14 @@ int dsee_conv2d_tc(const dsee_conv2d_tc_args* args, const dsee_conv_epilogue* ep
  *                  the tap offsets of the transposed conv carry the rotation). */
 int dsee_prep_conv_weight_ex(const float* w, void* out_hi, void* out_lo, float* inv_scale, int N,
                              int C, int KH, int KW, int transpose, void* stream);
+
+/* dsee_conv3x3_wgrad2 with one result per image (the per-image weights above):
+ * dw fp32 [B][n_total][c_total][3][3]; the pixel splits never straddle an image. */
+int64_t dsee_conv3x3_wgrad_per_image_workspace_floats(int B, int H, int W, int n_total, int c_total);
+int dsee_conv3x3_wgrad2_per_image(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale,
+                                  const void* const* a_hi, const void* const* a_lo, const int* a_channels,
+                                  int dtype, int B, int H, int W, int n_total, int passes,
+                                  float* workspace, float* dw, void* stream);
 
 /* Weight gradient of dsee_conv2d_tc: dY planes [B,Ho,Wo,n_total], activation planes
  * [B,Hi,Wi,Ci] (the forward input) -> dw fp32 [n_total][Cp][KH][KW], Cp = Ci rounded up to 64

@@ -265,6 +265,54 @@ def test_wgrad_and_dgrad_match_autograd(B, H, W, Cin, Cout, passes):
     assert err <= tol * s, ("dgrad", err, s)
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 16, 16), (2, 24, 40), (8, 8, 16)])
+def test_per_image_weights_and_wgrad(B, H, W):
+    """The folded-style form of a SEAN layer (config.fold_style): K1 with one weight matrix per image
+    over [actv | one-hot] sources equals the gathered style_map form, and the per-image weight gradient
+    equals autograd of a per-image conv."""
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B + H)
+    C, nh, L, d = 128, 128, 19, 128
+    labels = torch.randint(0, L, (B, H, W), generator=g, dtype=torch.uint8).cuda()
+    actv = torch.randn(B, H, W, nh, generator=g).relu().cuda()
+    style = (torch.rand(B, L, d, generator=g) * 2 - 1).cuda()
+    wm = (torch.randn(2 * C, nh + d, 3, 3, generator=g) / (3 * (nh + d) ** 0.5)).cuda()
+    x = torch.randn(B, H, W, C, generator=g).cuda()
+    one, zero = torch.ones(C).cuda(), torch.zeros(C).cuda()
+    a_pl = ops.split_f16(actv)
+    # gathered form
+    smap = ops.style_gather(labels, style)
+    ref = ops.spade_modulate([a_pl, smap], ops.prep_conv_weight(wm), x, 0, one, zero, one, zero, passes=3)
+    # folded form
+    from deepsee_b200.deepsee_models.networks.normalization import fold_style_weight
+    Wa, Ws = fold_style_weight(wm, style)
+    oh = ops.onehot_planes(labels)
+    oh = ops.SplitPlanes(oh.hi, torch.zeros_like(oh.hi))
+    got = ops.spade_modulate([a_pl, oh], ops.prep_mod_weight_batched(Wa, Ws), x, 0, one, zero, one, zero,
+                             passes=3)
+    rv = ref.hi.float() + ref.lo.float()
+    e = ((got.hi.float() + got.lo.float()) - rv).abs().max().item() / rv.abs().max().item()
+    print("folded vs gathered K1 (3-pass) max-abs / max|ref| %.3e" % e)
+    assert e < 2e-5   # both fp32-class; the two forms round different intermediate tensors
+    # per-image weight gradient vs autograd of per-image convs over [actv | one-hot]
+    dy = torch.randn(B, H, W, 2 * C, generator=g).cuda() * 1e-2
+    gp, _ = ops.grad_prep(dy)
+    dw = ops.conv3x3_wgrad_per_image(gp, [a_pl, oh], passes=3)
+    src = torch.cat([actv, oh.hi.float()], 3).permute(0, 3, 1, 2)
+    for b in range(B):
+        w = torch.zeros(2 * C, nh + 64, 3, 3, device="cuda", requires_grad=True)
+        F.conv2d(src[b:b + 1], w, padding=1).backward(dy[b:b + 1].permute(0, 3, 1, 2))
+        err = (dw[b] - w.grad).abs().max().item() / w.grad.abs().max().item()
+        assert err < 2e-4, (b, err)
+    # backward-data with a 128-row transposed weight (N = 128 < BLOCK_N)
+    pwT = ops.prep_conv_weight(Wa, transpose=True)
+    dsrc = ops.conv3x3([gp], pwT, None, passes=3)
+    a_ref = actv.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    F.conv2d(a_ref, Wa, padding=1).backward(dy.permute(0, 3, 1, 2))
+    err = (dsrc.permute(0, 3, 1, 2) - a_ref.grad).abs().max().item() / a_ref.grad.abs().max().item()
+    assert err < 1e-4, err
+
+
 def test_dgrad_leaky_relu_mask():
     from deepsee_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(5)
