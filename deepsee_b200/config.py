@@ -55,6 +55,12 @@ class _Config:
                 "discriminator convs: x3 passes" %
                 (k2, "1/4 of the output size" if self.passes3_upto == "auto" else "%s px" % self.passes3_upto))
 
+    # Training: capture each optimizer sub-step (forward, backward, gradient all-reduce, Adam) of
+    # TrainerManager as a CUDA graph per encoder coin-flip variant and replay it (managers/
+    # trainer_manager.py).  Removes the host from the step: the small-kernel phases (style encoder,
+    # discriminator, parameter-side kernels) are launch-bound otherwise.  Off in the library (eager
+    # semantics, `.grad` readable after a step); bench.py turns it on.
+    cuda_graphs = os.environ.get("DSEE_CUDA_GRAPHS", "0") == "1"
     # SEAN layers: fold the style branch into per-image modulation weights over the exact one-hot
     # label planes (normalization.py:182-185,198-201: conv(style_map, W) = conv(onehot, W x style_b)),
     # so K1's K per tap drops from 256 to 192 channels, the backward-data GEMM of the modulation

@@ -34,8 +34,11 @@ __global__ void grad_prep_kernel(const float* __restrict__ dy, __half* __restric
                                  __half* __restrict__ lo, float* __restrict__ inv_scale,
                                  const float* __restrict__ n0, const float* __restrict__ n1,
                                  unsigned long long seed0, unsigned long long seed1, int64_t npix, int C,
-                                 float* __restrict__ partial, int nq, const float* __restrict__ amax_in) {
+                                 float* __restrict__ partial, int nq, const float* __restrict__ amax_in,
+                                 const unsigned long long* epoch) {
     extern __shared__ float red[];  // [lanes][C][nq]
+    seed0 = eff_noise_seed(seed0, epoch);
+    seed1 = eff_noise_seed(seed1, epoch);
     // max|dY|: from the producer (amax_in) or from grad_amax_kernel (inv_scale[1]); inv_scale[1] is
     // only read by kernels launched after this one when it is written here
     const float amax = amax_in ? __ldg(amax_in) : inv_scale[1];
@@ -105,8 +108,10 @@ __global__ void modulate_bwd_saved_kernel(const float* __restrict__ x, int x_ups
                                           const float* __restrict__ dt, const float* __restrict__ dt_amax,
                                           int B, int H, int W, int C, float* __restrict__ dxhat,
                                           __half* __restrict__ dgb_hi, __half* __restrict__ dgb_lo,
-                                          float* __restrict__ dgb_inv_scale, float* __restrict__ partial) {
+                                          float* __restrict__ dgb_inv_scale, float* __restrict__ partial,
+                                          const unsigned long long* epoch) {
     extern __shared__ float red[];  // [lanes][C][4]
+    noise_seed = eff_noise_seed(noise_seed, epoch);
     const int cg = C >> 2;
     const int lanes = blockDim.x / cg;
     const int g = threadIdx.x % cg, pl = threadIdx.x / cg;
@@ -240,8 +245,9 @@ __global__ void __launch_bounds__(256, HAS_NOISE ? 3 : 4) bn_bwd_kernel(const fl
                               float inv_count, const float* __restrict__ dskip, int B, int Hx,
                               int Wx, int C, float* __restrict__ dx,
                               float* __restrict__ nw_partial, int nw_with_skip,
-                              float* __restrict__ amax_out) {
+                              float* __restrict__ amax_out, const unsigned long long* epoch) {
     extern __shared__ float red[];  // [lanes][C]
+    if (HAS_NOISE) noise_seed = eff_noise_seed(noise_seed, epoch);
     const int cg = C >> 2;
     const int lanes = blockDim.x / cg;
     const int g = threadIdx.x % cg, pl = threadIdx.x / cg;
@@ -607,7 +613,7 @@ extern "C" int dsee_grad_prep(const float* dy, void* out_hi, void* out_lo, float
     }
     grad_prep_kernel<<<cdivb(npix, GP_PIX), 256, sm, st>>>(dy, (__half*)out_hi, (__half*)out_lo,
                                                            inv_scale, noise0, noise1, seed0, seed1, npix,
-                                                           C, partial, nq, amax_in);
+                                                           C, partial, nq, amax_in, noise_epoch_ptr());
     LAUNCH_END();
 }
 
@@ -634,7 +640,7 @@ extern "C" int dsee_spade_modulate_bwd_saved(const float* x, int x_ups, const fl
     modulate_bwd_saved_kernel<<<cdivb(npix, GP_PIX), 256, sm, (cudaStream_t)stream>>>(
         x, x_ups, noise, noise_seed, noise_w, bn_scale, bn_shift, (const __half*)g_hi, (const __half*)g_lo, dt,
         dt_amax,
-        B, H, W, C, dxhat, (__half*)dgb_hi, (__half*)dgb_lo, dgb_inv_scale, partial);
+        B, H, W, C, dxhat, (__half*)dgb_hi, (__half*)dgb_lo, dgb_inv_scale, partial, noise_epoch_ptr());
     LAUNCH_END();
 }
 
@@ -670,7 +676,7 @@ extern "C" int dsee_bn_bwd(const float* dxhat, const float* x, int x_ups, const 
     auto kern = noise_w ? bn_bwd_kernel<true> : bn_bwd_kernel<false>;
     kern<<<dsee_bn_bwd_blocks(B, Hx, Wx), 256, sm, (cudaStream_t)stream>>>(
         dxhat, x, x_ups, noise, noise_seed, noise_w, bn_scale, bn_shift, sums, inv_count, dskip, B, Hx, Wx,
-        C, dx, nw_partial, noise_grad_with_skip, amax_out);
+        C, dx, nw_partial, noise_grad_with_skip, amax_out, noise_epoch_ptr());
     LAUNCH_END();
 }
 

@@ -43,6 +43,12 @@ const char* get_error();
 // Checks the current device is sm_100 (B200). Returns 0 or a negative error.
 int require_sm100();
 
+// Device address of the current device's noise epoch: a 64-bit counter every noise-regenerating
+// kernel folds into its seed (eff_noise_seed below).  dsee_noise_epoch_advance bumps it with a
+// one-thread kernel, so a CUDA graph that replays launches with baked-in seeds still draws fresh
+// noise on every replay, consistently across the forward and backward kernels of one step.
+const unsigned long long* noise_epoch_ptr();
+
 // Encodes a tiled tensor map (rank <= 5) for a 16-bit element tensor with 128B swizzle.
 // dims/strides innermost-first; strides[0] is implied (= 2 bytes).
 // elem_strides (optional, per dimension): traversal stride; the box then lands
@@ -230,6 +236,10 @@ __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
 // "Parallel random numbers: as easy as 1, 2, 3", SC'11, table 2); cuRAND's default of 10 adds safety
 // margin the noise injection does not need, and the generator sits in compute-bound epilogues.
 constexpr int NOISE_PHILOX_ROUNDS = 7;
+__device__ __forceinline__ unsigned long long eff_noise_seed(unsigned long long seed,
+                                                             const unsigned long long* epoch) {
+    return seed ? seed + __ldg(epoch) * 0x9E3779B97F4A7C15ull : 0ull;
+}
 __device__ __forceinline__ float4 noise_normal4(unsigned long long seed, unsigned long long idx4) {
     uint32_t c0 = (uint32_t)idx4, c1 = (uint32_t)(idx4 >> 32), c2 = 0u, c3 = 0u;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);

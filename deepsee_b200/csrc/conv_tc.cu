@@ -105,6 +105,7 @@ struct alignas(64) ConvParams {
     const float* noise;
     const float* noise_w;
     unsigned long long noise_seed;
+    const unsigned long long* noise_epoch;  // device counter folded into every noise seed
     const float* bn_scale;
     const float* bn_shift;
     const float* gamma_bias;
@@ -320,6 +321,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
         const int m = q * 32 + lane;
         const int ly = m / TILE_W, lx = m % TILE_W;
         const float inv_scale = __ldg(p.w_inv_scale) * (p.a_inv_scale ? __ldg(p.a_inv_scale) : 1.f);
+        const unsigned long long nseed = eff_noise_seed(p.noise_seed, p.noise_epoch);
+        const unsigned long long rseed0 = eff_noise_seed(p.rnoise_seed[0], p.noise_epoch);
+        const unsigned long long rseed1 = eff_noise_seed(p.rnoise_seed[1], p.noise_epoch);
         int lt = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
             const int as = lt & 1;
@@ -405,11 +409,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         }
                         o[0] += rq[st].x; o[1] += rq[st].y; o[2] += rq[st].z; o[3] += rq[st].w;
                         if (p.rnoise_w[0]) {
-                            const float4 r4 = load_noise4(p.rnoise[0], p.rnoise_seed[0], oe);
+                            const float4 r4 = load_noise4(p.rnoise[0], rseed0, oe);
                             o[0] += nw0.x * r4.x; o[1] += nw0.y * r4.y; o[2] += nw0.z * r4.z; o[3] += nw0.w * r4.w;
                         }
                         if (p.rnoise_w[1]) {
-                            const float4 r4 = load_noise4(p.rnoise[1], p.rnoise_seed[1], oe);
+                            const float4 r4 = load_noise4(p.rnoise[1], rseed1, oe);
                             o[0] += nw1.x * r4.x; o[1] += nw1.y * r4.y; o[2] += nw1.z * r4.z; o[3] += nw1.w * r4.w;
                         }
                         *reinterpret_cast<float4*>(p.out + oe) = make_float4(o[0], o[1], o[2], o[3]);
@@ -594,7 +598,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         float4 xv = xq[st];
                         const uint2 mv = mq[st], gv = gq[st], lv = lq[st];
                         if (has_noise) {
-                            const float4 nv = load_noise4(p.noise, p.noise_seed, pe);
+                            const float4 nv = load_noise4(p.noise, nseed, pe);
                             xv.x += nw4.x * nv.x; xv.y += nw4.y * nv.y; xv.z += nw4.z * nv.z; xv.w += nw4.w * nv.w;
                         }
                         const float xh[4] = {xv.x * sc4.x + sh4.x, xv.y * sc4.y + sh4.y, xv.z * sc4.z + sh4.z,
@@ -712,7 +716,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         const size_t pe = pix * p.C + cc;
                         float4 xv = xq[st];
                         if (has_noise) {
-                            const float4 nv = load_noise4(p.noise, p.noise_seed, pe);
+                            const float4 nv = load_noise4(p.noise, nseed, pe);
                             xv.x += nw4.x * nv.x; xv.y += nw4.y * nv.y; xv.z += nw4.z * nv.z; xv.w += nw4.w * nv.w;
                         }
                         const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -820,6 +824,7 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
     DSEE_CHECK_ARG(ops->w_batch_rows == 0 || ops->n_total % BLOCK_N == 0,
                    "per-image weights need n_total to be a multiple of %d", BLOCK_N);
     p.w_brows = ops->w_batch_rows;
+    p.noise_epoch = noise_epoch_ptr();
     p.tiles_w = (ops->W + TILE_W - 1) / TILE_W;
     p.tiles_h = (ops->H + TILE_H - 1) / TILE_H;
     p.n_tiles = (ops->n_total + BLOCK_N - 1) / BLOCK_N;
@@ -974,6 +979,7 @@ extern "C" int dsee_conv2d_tc(const dsee_conv2d_tc_args* a, const dsee_conv_epil
     base.Hm = a->Ho;
     base.Wm = a->Wo;
     base.cb0 = base.cb_total = cpad / BLOCK_K;
+    base.noise_epoch = noise_epoch_ptr();
     base.passes = a->passes;
     base.n_total = a->n_total;
     base.w_inv_scale = a->w_inv_scale;

@@ -133,7 +133,47 @@ static int encode_tmap_any(CUtensorMap* out, CUtensorMapDataType dtype, const vo
     return 0;
 }
 
+__device__ unsigned long long g_noise_epoch = 0ull;
+__global__ void noise_epoch_kernel(unsigned long long* e, unsigned long long add, int set) {
+    *e = set ? add : *e + add;
+}
+
+const unsigned long long* noise_epoch_ptr() {
+    static std::mutex mu;
+    static unsigned long long* cached[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 64 && cached[dev]) return cached[dev];
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_noise_epoch) != cudaSuccess) return nullptr;
+    if (dev < 64) cached[dev] = (unsigned long long*)p;
+    return (unsigned long long*)p;
+}
+
 }  // namespace dsee
+
+extern "C" int dsee_noise_epoch_advance(void* stream) {
+    int rc = dsee::require_sm100();
+    if (rc) return rc;
+    unsigned long long* e = const_cast<unsigned long long*>(dsee::noise_epoch_ptr());
+    DSEE_CHECK_ARG(e != nullptr, "noise epoch symbol not found");
+    dsee::noise_epoch_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(e, 1ull, 0);
+    dsee::count_launch();
+    DSEE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dsee_noise_epoch_set(unsigned long long value, void* stream) {
+    int rc = dsee::require_sm100();
+    if (rc) return rc;
+    unsigned long long* e = const_cast<unsigned long long*>(dsee::noise_epoch_ptr());
+    DSEE_CHECK_ARG(e != nullptr, "noise epoch symbol not found");
+    dsee::noise_epoch_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(e, value, 1);
+    dsee::count_launch();
+    DSEE_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int dsee_version(void) { return DSEE_ABI_VERSION; }
 extern "C" const char* dsee_last_error(void) { return dsee::get_error(); }

@@ -64,6 +64,57 @@ __global__ void labels_from_onehot_kernel(const float* __restrict__ oh, uint8_t*
     labels[i] = (uint8_t)found;
 }
 
+// int64 label map (the dataloader's) -> uint8, flagging values outside [0, L) (the reference's
+// scatter_ would raise on those, preprocessor.py:40)
+__global__ void labels_u8_kernel(const int64_t* __restrict__ label, uint8_t* __restrict__ out, int64_t n,
+                                 int L, int* bad) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t l = label[i];
+    if (l < 0 || l >= L) {
+        *bad = 1;
+        l = 0;
+    }
+    out[i] = (uint8_t)l;
+}
+
+// F.interpolate(mode='bicubic', align_corners=False) + clamp(-1, 1) (preprocessor.py:29-32), NCHW fp32.
+// Same arithmetic as ATen's upsample_bicubic2d: source index scale * (dst + 0.5) - 0.5 (scale =
+// in / out as float), cubic convolution coefficients with A = -0.75, border taps clamped to the image.
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+    const float A = -0.75f;
+    c[0] = cubic2(t + 1.f, A);
+    c[1] = cubic1(t, A);
+    const float x2 = 1.f - t;
+    c[2] = cubic1(x2, A);
+    c[3] = cubic2(x2 + 1.f, A);
+}
+__global__ void bicubic_clamp_kernel(const float* __restrict__ in, float* __restrict__ out, int BC, int Hi,
+                                     int Wi, int Ho, int Wo, float sh, float sw) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)BC * Ho * Wo) return;
+    const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho), bc = (int)(i / ((int64_t)Wo * Ho));
+    const float ry = sh * (oy + 0.5f) - 0.5f, rx = sw * (ox + 0.5f) - 0.5f;
+    const int iy = (int)floorf(ry), ix = (int)floorf(rx);
+    float cy[4], cx[4];
+    cubic_coeffs(ry - iy, cy);
+    cubic_coeffs(rx - ix, cx);
+    const float* img = in + (size_t)bc * Hi * Wi;
+    float rows[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int y = min(max(iy - 1 + k, 0), Hi - 1);
+        const float* r = img + (size_t)y * Wi;
+        const float v0 = r[min(max(ix - 1, 0), Wi - 1)], v1 = r[min(max(ix, 0), Wi - 1)];
+        const float v2 = r[min(max(ix + 1, 0), Wi - 1)], v3 = r[min(max(ix + 2, 0), Wi - 1)];
+        rows[k] = v0 * cx[0] + v1 * cx[1] + v2 * cx[2] + v3 * cx[3];
+    }
+    const float v = rows[0] * cy[0] + rows[1] * cy[1] + rows[2] * cy[2] + rows[3] * cy[3];
+    out[i] = fminf(fmaxf(v, -1.f), 1.f);
+}
+
 __global__ void resize_labels_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                      int B, int Hin, int Win, int Hout, int Wout, float sh,
                                      float sw) {
@@ -332,17 +383,21 @@ __global__ void fold2x2_kernel(const float* __restrict__ in, float* __restrict__
 constexpr int STAT_PIX = 256;  // pixels per partial
 
 // block = 256 threads: thread t owns channels 4*(t % (C/4)) .. +3 and every (256/(C/4))-th pixel.
-__global__ void noise_fill_kernel(unsigned long long seed, float* __restrict__ out, int64_t n4) {
+__global__ void noise_fill_kernel(unsigned long long seed, float* __restrict__ out, int64_t n4,
+                                  const unsigned long long* epoch) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
+    seed = eff_noise_seed(seed, epoch);
     reinterpret_cast<float4*>(out)[i] = noise_normal4(seed, (unsigned long long)i);
 }
 
 template <bool HAS_NOISE>
 __global__ void bn_stats_kernel(const float* __restrict__ x, int x_ups, const float* __restrict__ noise,
                                 unsigned long long noise_seed, const float* __restrict__ noise_w, int B,
-                                int H, int W, int C, float* __restrict__ partial) {
+                                int H, int W, int C, float* __restrict__ partial,
+                                const unsigned long long* epoch) {
     extern __shared__ float red[];  // [pix_lanes][C][2]
+    if (HAS_NOISE) noise_seed = eff_noise_seed(noise_seed, epoch);
     const int cg = C >> 2;
     const int pix_lanes = blockDim.x / cg;
     const int g = threadIdx.x % cg, pl = threadIdx.x / cg;
@@ -646,6 +701,26 @@ extern "C" int dsee_labels_from_onehot(const float* onehot, uint8_t* labels, int
     LAUNCH_END();
 }
 
+extern "C" int dsee_labels_u8(const int64_t* label, uint8_t* out, int64_t n, int L, int* bad_flag,
+                              void* stream) {
+    DSEE_CHECK_ARG(label && out && bad_flag && n > 0 && L > 0 && L <= 255, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    labels_u8_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(label, out, n, L, bad_flag);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_bicubic_clamp(const float* in, float* out, int B, int C, int Hi, int Wi, int Ho, int Wo,
+                                  void* stream) {
+    DSEE_CHECK_ARG(in && out && B > 0 && C > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int64_t n = (int64_t)B * C * Ho * Wo;
+    bicubic_clamp_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        in, out, B * C, Hi, Wi, Ho, Wo, (float)Hi / (float)Ho, (float)Wi / (float)Wo);
+    LAUNCH_END();
+}
+
 extern "C" int dsee_resize_labels(const uint8_t* in, uint8_t* out, int B, int Hin, int Win, int Hout,
                                   int Wout, void* stream) {
     DSEE_CHECK_ARG(in && out && B > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, "bad argument");
@@ -798,7 +873,7 @@ extern "C" int dsee_noise_fill(unsigned long long seed, float* out, int64_t n, v
     DSEE_CHECK_ARG(out && n > 0 && n % 4 == 0, "bad argument (n must be a multiple of 4)");
     int rc = require_sm100();
     if (rc) return rc;
-    noise_fill_kernel<<<cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(seed, out, n / 4);
+    noise_fill_kernel<<<cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(seed, out, n / 4, noise_epoch_ptr());
     LAUNCH_END();
 }
 
@@ -819,7 +894,7 @@ extern "C" int dsee_bn_stats(const float* x, int x_ups, const float* noise, unsi
     size_t sm = (size_t)pix_lanes * C * 2 * sizeof(float);
     auto kern = noise_w ? bn_stats_kernel<true> : bn_stats_kernel<false>;
     kern<<<*n_partials, 256, sm, (cudaStream_t)stream>>>(x, x_ups, noise, noise_seed, noise_w,
-                                                                    B, H, W, C, stats_partial);
+                                                                    B, H, W, C, stats_partial, noise_epoch_ptr());
     LAUNCH_END();
 }
 

@@ -48,8 +48,8 @@ class AbtractStyleEncoder(BaseNetwork):
             nn.Tanh())
 
     def _labels(self, seg):
-        labels, _ = ops.labels_from_onehot(seg.contiguous().float())
-        return labels
+        from ...data.onehot import labels_of
+        return labels_of(seg)[0]
 
     def extract_style_matrix(self, x_nhwc, labels_full, n_regions=None):
         """encoder.py:36-49 (divides by H*W of the feature map, not by the region area).  One row per

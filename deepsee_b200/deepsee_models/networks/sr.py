@@ -88,9 +88,9 @@ class DeepSEESR(BaseNetwork):
     def forward(self, x_downsized, seg=None, z=None):
         if not x_downsized.is_cuda:
             raise RuntimeError('DeepSEESR (B200 path) needs CUDA tensors; there is no CPU fallback')
+        from ...data.onehot import labels_of
         x_downsized = x_downsized.contiguous().float()
-        seg = seg.contiguous().float()
-        labels, bad = ops.labels_from_onehot(seg)
+        labels, bad = labels_of(seg)   # free for the preprocessor's OneHotLabels
         ctx = GenContext(labels, z.contiguous().float() if z is not None else None)
 
         blocks = [self.head_0, self.G_middle_0, self.G_middle_1] + [self.up_list[i] for i in range(self.n_blocks - 1)]
@@ -102,7 +102,7 @@ class DeepSEESR(BaseNetwork):
             for i in range(self.n_blocks - 1):
                 x, st = self.up_list[i].forward_nhwc(x, ctx, ups=1, stats_in=st)
         out = _HeadFn.apply(x, self.conv_img.weight, self.conv_img.bias)
-        if config.check_onehot:
+        if config.check_onehot and bad is not None:
             self._check_onehot(bad)
         return out
 

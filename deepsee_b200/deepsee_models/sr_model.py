@@ -277,10 +277,14 @@ class SRModel(torch.nn.Module):
         beta1, beta2 = opt.beta1, opt.beta2
         SR_lr, D_lr = (opt.lr, opt.lr) if opt.no_TTUR else (opt.lr / 2, opt.lr * 2)
         print("lr G: {}, lr D: {}".format(SR_lr, D_lr))
+        from ..config import config
+        # capturable: the step counters live on the device, so optimizer.step() can be part of a
+        # captured CUDA graph (config.cuda_graphs); same arithmetic
+        kw = {"capturable": True} if config.cuda_graphs else {}
         optimizer_SR = torch.optim.Adam([{"params": SR_params},
                                          {"params": SR_params_low_lr, "lr": SR_lr / 4}],
-                                        lr=SR_lr, betas=(beta1, beta2))
-        optimizer_D = torch.optim.Adam(D_params, lr=D_lr, betas=(beta1, beta2))
+                                        lr=SR_lr, betas=(beta1, beta2), **kw)
+        optimizer_D = torch.optim.Adam(D_params, lr=D_lr, betas=(beta1, beta2), **kw)
         return optimizer_SR, optimizer_D
 
     def save(self, epoch):
@@ -393,7 +397,8 @@ class SRModel(torch.nn.Module):
     def discriminate(self, input_semantics, fake_image, real_image, for_generator=False):
         """sr_model.py:655-668: D sees [seg | fake] and [seg | real] in one batch. The two cats and
         the NCHW->NHWC conversion are one kernel (ops.disc_input) on the uint8 label map."""
-        labels, _ = ops.labels_from_onehot(input_semantics.contiguous().float())
+        from ..data.onehot import labels_of
+        labels, _ = labels_of(input_semantics)
         L = input_semantics.shape[1]
         cp = (L + 3 + 31) // 32 * 32  # zero channels up to a multiple of 32 (tcgen05 epilogue width)
         x = ops.DiscInputFn.apply(labels, fake_image.contiguous().float(),

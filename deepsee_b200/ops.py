@@ -91,6 +91,12 @@ def _noise(n):
     return _p(n), 0
 
 
+def noise_epoch_advance():
+    """Bumps the device-side noise epoch (see dsee_noise_epoch_advance): seeds baked into a captured
+    CUDA graph then stand for a fresh noise tensor on every replay."""
+    _lib.check(_lib.load().dsee_noise_epoch_advance(_stream()))
+
+
 def noise_fill(seed, shape, device="cuda"):
     """Materialises the noise tensor a NoiseSeed stands for (tests)."""
     out = torch.empty(shape, dtype=torch.float32, device=device)
@@ -120,6 +126,28 @@ def onehot_from_labels(label, num_classes):
     _lib.check(_lib.load().dsee_onehot_from_labels(_p(label), _p(out), B, num_classes, H, W, _p(bad),
                                                    _stream()))
     return out, bad
+
+
+def labels_u8(label, num_classes):
+    """int64 label map [B,1,H,W] (or [B,H,W]) -> (uint8 [B,H,W], device flag: 1 if out of range)."""
+    _chk_cuda(label)
+    assert label.dtype == torch.int64
+    shape = label.shape if label.dim() == 3 else (label.shape[0],) + tuple(label.shape[2:])
+    assert label.dim() == 3 or label.size(1) == 1
+    out = torch.empty(shape, dtype=torch.uint8, device=label.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=label.device)
+    _lib.check(_lib.load().dsee_labels_u8(_p(label), _p(out), label.numel(), num_classes, _p(bad), _stream()))
+    return out, bad
+
+
+def bicubic_clamp(x, size):
+    """F.interpolate(x, size, mode='bicubic').clamp(-1, 1) (data/preprocessor.py:29-32), NCHW fp32."""
+    _chk_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 4
+    B, Cc, Hi, Wi = x.shape
+    out = torch.empty((B, Cc, size[0], size[1]), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().dsee_bicubic_clamp(_p(x), _p(out), B, Cc, Hi, Wi, size[0], size[1], _stream()))
+    return out
 
 
 def labels_from_onehot(onehot):

@@ -79,6 +79,24 @@ int dsee_shared_mlp_fwd(const uint8_t* labels, const float* table, const float* 
 int dsee_style_gather_fwd(const uint8_t* labels, const float* style, void* out_hi, void* out_lo,
                           int B, int H, int W, int L, int d, void* stream);
 
+/* Input side of the path.
+ * dsee_labels_u8: the dataloader's int64 label map -> the uint8 map every kernel consumes;
+ *   *bad_flag = 1 if a label is outside [0, L) (the reference's scatter_ raises there,
+ *   data/preprocessor.py:40).  The fp32 one-hot tensor is only materialised if a caller asks for it.
+ * dsee_bicubic_clamp: Preprocessor.downsample_image (data/preprocessor.py:17-33):
+ *   F.interpolate(hr, (Ho, Wo), mode='bicubic') (align_corners=False, A = -0.75, no antialias)
+ *   followed by clamp(-1, 1); fp32 NCHW in and out. */
+int dsee_labels_u8(const int64_t* label, uint8_t* out, int64_t n, int L, int* bad_flag, void* stream);
+int dsee_bicubic_clamp(const float* in, float* out, int B, int C, int Hi, int Wi, int Ho, int Wo,
+                       void* stream);
+
+/* Noise epoch: a per-device 64-bit counter that every kernel regenerating NoiseInjection noise
+ * from a seed folds into that seed.  Advancing it (a one-thread kernel on `stream`) makes launches
+ * whose seeds are baked into a captured CUDA graph draw fresh noise on every replay; forward and
+ * backward kernels launched between two advances see the same tensor.  Starts at 0. */
+int dsee_noise_epoch_advance(void* stream);
+int dsee_noise_epoch_set(unsigned long long value, void* stream);
+
 /* ---- tensor-core operand preparation -------------------------------------------------------- */
 /* Conv weight fp32 [N][C][3][3] (PyTorch layout; spectral normalisation already applied,
  * architecture.py:40-44) -> GEMM B-operand planes fp16 [N][9*C] with k = (ky*3+kx)*C + c,

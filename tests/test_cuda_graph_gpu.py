@@ -1,0 +1,76 @@
+"""GPU: TrainerManager with config.cuda_graphs - every optimizer sub-step captured per encoder
+coin-flip variant and replayed - must train exactly like the eager path: same losses step by step and
+the same parameters afterwards (no noise injection / style noise here, so both runs are deterministic;
+every reduction in the library has a fixed order).  Also: the device-side noise epoch that lets a
+replayed graph draw fresh NoiseInjection noise."""
+import random
+
+import pytest
+import torch
+
+from oracle import deepsee_oracle as O
+from test_generator_gpu import _mk_opt
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(graphs, steps, name, over):
+    from deepsee_b200.config import config
+    from deepsee_b200.managers.trainer_manager import TrainerManager
+    saved = config.cuda_graphs
+    config.cuda_graphs = graphs
+    try:
+        o = O.make_opt(name, is_train=True, **over)
+        mgr = TrainerManager(_mk_opt(o))
+        m = mgr.sr_model
+        m.netSR.load_state_dict(O.make_generator_state(o, 0), strict=True)
+        m.netE.load_state_dict(O.make_encoder_state(o, 1), strict=True)
+        m.netD.load_state_dict(O.make_discriminator_state(o, 2), strict=True)
+        m.train()
+        random.seed(123)
+        losses = []
+        for i in range(steps):
+            raw = O.synthetic_batch(o, 2, seed=500 + i)
+            data = {k: (v.float() if "label" in k else v) for k, v in raw.items()}
+            mgr.run_generator_one_step(dict(data))
+            mgr.run_discriminator_one_step(dict(data))
+            losses.append({k: float(v.detach().mean()) for k, v in mgr.get_latest_losses().items()})
+        torch.cuda.synchronize()
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        return losses, sd, mgr
+    finally:
+        config.cuda_graphs = saved
+
+
+@pytest.mark.parametrize("name,over", [
+    ("8x_independent_256x256", dict(ngf=8, nef=8, ndf=8, start_size=8, crop_size=64, load_size=64,
+                                    add_noise=False, noisy_style_scale=0.0)),
+    ("32x_guided_512x512", dict(ngf=8, nef=8, ndf=8, start_size=4, crop_size=128, load_size=512,
+                                max_fm_size=64)),
+])
+def test_graphed_training_equals_eager(name, over):
+    steps = 9
+    l_eager, sd_eager, _ = _run(False, steps, name, over)
+    l_graph, sd_graph, mgr = _run(True, steps, name, over)
+    assert mgr.graphs_active() and mgr.graph_replays > 0, "the graphed path did not engage"
+    variants = {m: len(s.graphs) for m, s in mgr._graphed.items()}
+    print("captured variants:", variants, "replayed sub-steps:", mgr.graph_replays)
+    for i, (a, b) in enumerate(zip(l_eager, l_graph)):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-6 * max(1.0, abs(a[k])), (i, k, a[k], b[k])
+    for k in sd_eager:
+        if sd_eager[k].dtype.is_floating_point:
+            torch.testing.assert_close(sd_graph[k], sd_eager[k], rtol=1e-6, atol=1e-7, msg=k)
+        else:
+            assert torch.equal(sd_graph[k], sd_eager[k]), k
+
+
+def test_noise_epoch_changes_the_stream():
+    from deepsee_b200 import ops
+    a = ops.noise_fill(1234, (1, 4, 4, 8))
+    b = ops.noise_fill(1234, (1, 4, 4, 8))
+    assert torch.equal(a, b)
+    ops.noise_epoch_advance()
+    c = ops.noise_fill(1234, (1, 4, 4, 8))
+    assert not torch.equal(a, c)
+    assert abs(float(c.mean())) < 1.0 and 0.3 < float(c.std()) < 2.0
