@@ -80,7 +80,7 @@ struct alignas(64) ConvParams {
     int8_t tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
     int tap_k[MAX_TAPS];  // K offset of the tap's weight block
     int b_rows;        // weight rows per TMA box (= MMA N)
-    int lrelu;         // EPI_CONV: fuse LeakyReLU(0.2) after the bias
+    int lrelu;         // EPI_CONV: activation fused after the bias: 1 LeakyReLU(0.2), 2 ReLU
     int tiles_w, tiles_h, n_tiles, num_tiles;
     int cb0, cb_total;  // 64-channel blocks in source 0 / in total
     int passes;
@@ -394,8 +394,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         float o[4] = {tp[0] * inv_scale + bias4.x, tp[1] * inv_scale + bias4.y,
                                       tp[2] * inv_scale + bias4.z, tp[3] * inv_scale + bias4.w};
                         if (p.lrelu) {
+                            const float slope = p.lrelu == 2 ? 0.f : 0.2f;
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) o[e] = o[e] > 0.f ? o[e] : 0.2f * o[e];
+                            for (int e = 0; e < 4; ++e) o[e] = o[e] > 0.f ? o[e] : slope * o[e];
                         }
                         const size_t pix = ((size_t)b * p.Hm + (yy * p.o_step + p.o_offy)) * p.Wm +
                                            (xx * p.o_step + p.o_offx);

@@ -350,7 +350,8 @@ extern "C" int dsee_conv2d_direct_fwd(const float* x, const float* w, const floa
     if (Cout % 4 == 0) {
         int64_t n = (int64_t)B * Ho * ((Wo + DC_PX - 1) / DC_PX) * (Cout / 4);
         direct_conv_kernel<<<cdiv2(n, 128), 128, 0, (cudaStream_t)stream>>>(
-            x, w, bias, out, B, Hi, Wi, Cin, Ho, Wo, Cout, KH, KW, stride, pad, ups, 0.2f, lrelu);
+            x, w, bias, out, B, Hi, Wi, Cin, Ho, Wo, Cout, KH, KW, stride, pad, ups, lrelu == 2 ? 0.f : 0.2f,
+            lrelu);
     } else {
         DSEE_CHECK_ARG(Cout <= 4 && ups == 0 && !lrelu, "Cout %% 4 != 0 only supported for Cout <= 4");
         int64_t n = (int64_t)B * Ho * Wo * 32;
@@ -461,13 +462,13 @@ extern "C" int dsee_avgpool3s2_fwd(const float* in, float* out, int B, int Hi, i
 // =================================================================================================
 namespace dsee {
 
-// dx = dy * act'(.) from the layer OUTPUT: act 1 LeakyReLU (sign of out), 2 tanh (1 - out^2)
+// dx = dy * act'(.) from the layer OUTPUT: act 1 LeakyReLU / 3 ReLU (sign of out), 2 tanh (1 - out^2)
 __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ out,
                                float* __restrict__ dx, int64_t n, int act, float slope) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float o = out[i];
-    dx[i] = dy[i] * (act == 1 ? (o > 0.f ? 1.f : slope) : (1.f - o * o));
+    dx[i] = dy[i] * (act != 2 ? (o > 0.f ? 1.f : slope) : (1.f - o * o));
 }
 
 // backward-data of direct_conv_kernel: thread = one (pre-upsample) input pixel x 4 input channels
@@ -737,6 +738,72 @@ __global__ void region_pool_bwd_kernel(const float* __restrict__ dstyle, const u
     reinterpret_cast<float4*>(dx)[i] = v;
 }
 
+// nn.MaxPool2d(kernel_size=2, stride=2) of VGG19 (architecture.py:151-181 via torchvision), NHWC;
+// the backward pass recomputes the arg-max from the input (first maximum in row-major window order,
+// like ATen) instead of storing indices.  thread = (output pixel, 4 channels)
+__global__ void maxpool2_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int Hi, int Wi,
+                                int C4, int Ho, int Wo) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * Ho * Wo * C4) return;
+    const uint32_t iu = (uint32_t)i;
+    const int g = (int)(iu % (uint32_t)C4);
+    uint32_t r = iu / (uint32_t)C4;
+    const int xo = (int)(r % (uint32_t)Wo);
+    r /= (uint32_t)Wo;
+    const int yo = (int)(r % (uint32_t)Ho);
+    const int b = (int)(r / (uint32_t)Ho);
+    const float4* p = reinterpret_cast<const float4*>(in) + (((size_t)b * Hi + 2 * yo) * Wi + 2 * xo) * C4 + g;
+    const float4 a = __ldg(p), bq = __ldg(p + C4), c = __ldg(p + (size_t)Wi * C4), d = __ldg(p + (size_t)Wi * C4 + C4);
+    float4 m;
+    m.x = fmaxf(fmaxf(a.x, bq.x), fmaxf(c.x, d.x));
+    m.y = fmaxf(fmaxf(a.y, bq.y), fmaxf(c.y, d.y));
+    m.z = fmaxf(fmaxf(a.z, bq.z), fmaxf(c.z, d.z));
+    m.w = fmaxf(fmaxf(a.w, bq.w), fmaxf(c.w, d.w));
+    reinterpret_cast<float4*>(out)[i] = m;
+}
+
+__device__ __forceinline__ void route_max(float a, float b, float c, float d, float g, float& ga, float& gb,
+                                          float& gc, float& gd) {
+    int k = 0;
+    float m = a;
+    if (b > m) { m = b; k = 1; }
+    if (c > m) { m = c; k = 2; }
+    if (d > m) { m = d; k = 3; }
+    ga = k == 0 ? g : 0.f;
+    gb = k == 1 ? g : 0.f;
+    gc = k == 2 ? g : 0.f;
+    gd = k == 3 ? g : 0.f;
+}
+
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout,
+                                    float* __restrict__ din, int B, int Hi, int Wi, int C4, int Ho, int Wo) {
+    // thread = (output pixel, 4 channels): writes the 2x2 window of din (windows do not overlap);
+    // rows / columns beyond 2*Ho, 2*Wo (odd sizes) are zeroed by the host wrapper
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * Ho * Wo * C4) return;
+    const uint32_t iu = (uint32_t)i;
+    const int g = (int)(iu % (uint32_t)C4);
+    uint32_t r = iu / (uint32_t)C4;
+    const int xo = (int)(r % (uint32_t)Wo);
+    r /= (uint32_t)Wo;
+    const int yo = (int)(r % (uint32_t)Ho);
+    const int b = (int)(r / (uint32_t)Ho);
+    const size_t o00 = (((size_t)b * Hi + 2 * yo) * Wi + 2 * xo) * C4 + g;
+    const float4* p = reinterpret_cast<const float4*>(in) + o00;
+    const float4 a = __ldg(p), bq = __ldg(p + C4), c = __ldg(p + (size_t)Wi * C4), d = __ldg(p + (size_t)Wi * C4 + C4);
+    const float4 gq = __ldg(reinterpret_cast<const float4*>(dout) + i);
+    float4 ga, gb, gc, gd;
+    route_max(a.x, bq.x, c.x, d.x, gq.x, ga.x, gb.x, gc.x, gd.x);
+    route_max(a.y, bq.y, c.y, d.y, gq.y, ga.y, gb.y, gc.y, gd.y);
+    route_max(a.z, bq.z, c.z, d.z, gq.z, ga.z, gb.z, gc.z, gd.z);
+    route_max(a.w, bq.w, c.w, d.w, gq.w, ga.w, gb.w, gc.w, gd.w);
+    float4* q = reinterpret_cast<float4*>(din) + o00;
+    q[0] = ga;
+    q[C4] = gb;
+    q[(size_t)Wi * C4] = gc;
+    q[(size_t)Wi * C4 + C4] = gd;
+}
+
 // backward of avgpool3s2 (count_include_pad=False): din[yi,xi] = sum over outputs covering it of
 // dout / count(output)
 __global__ void avgpool3s2_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din, int B,
@@ -779,10 +846,11 @@ __global__ void disc_input_bwd_kernel(const float* __restrict__ dx, float* __res
 
 extern "C" int dsee_act_bwd(const float* dy, const float* out, float* dx, int64_t n, int act,
                             void* stream) {
-    DSEE_CHECK_ARG(dy && out && dx && n > 0 && (act == 1 || act == 2), "bad argument");
+    DSEE_CHECK_ARG(dy && out && dx && n > 0 && act >= 1 && act <= 3, "bad argument");
     int rc = require_sm100();
     if (rc) return rc;
-    act_bwd_kernel<<<cdiv2(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, out, dx, n, act, 0.2f);
+    act_bwd_kernel<<<cdiv2(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, out, dx, n, act,
+                                                                    act == 3 ? 0.f : 0.2f);
     LAUNCH_END();
 }
 
@@ -901,6 +969,31 @@ extern "C" int dsee_avgpool3s2_bwd(const float* dout, float* din, int B, int Hi,
     const int64_t n = (int64_t)B * Hi * Wi * C;
     avgpool3s2_bwd_kernel<<<cdiv2(n, 256), 256, 0, (cudaStream_t)stream>>>(dout, din, B, Hi, Wi, C, Ho,
                                                                            Wo);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_maxpool2_fwd(const float* in, float* out, int B, int Hi, int Wi, int C, void* stream) {
+    DSEE_CHECK_ARG(in && out && B > 0 && Hi >= 2 && Wi >= 2 && C > 0 && C % 4 == 0, "bad argument");
+    DSEE_CHECK_ARG((int64_t)B * Hi * Wi * C < ((int64_t)1 << 31), "more than 2^31 elements");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
+    maxpool2_kernel<<<cdiv2(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, Hi, Wi, C / 4, Ho, Wo);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_maxpool2_bwd(const float* in, const float* dout, float* din, int B, int Hi, int Wi, int C,
+                                 void* stream) {
+    DSEE_CHECK_ARG(in && dout && din && B > 0 && Hi >= 2 && Wi >= 2 && C > 0 && C % 4 == 0, "bad argument");
+    DSEE_CHECK_ARG((int64_t)B * Hi * Wi * C < ((int64_t)1 << 31), "more than 2^31 elements");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    if ((Hi & 1) || (Wi & 1))
+        DSEE_CUDA(cudaMemsetAsync(din, 0, (size_t)B * Hi * Wi * C * sizeof(float), (cudaStream_t)stream));
+    const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
+    maxpool2_bwd_kernel<<<cdiv2(n, 256), 256, 0, (cudaStream_t)stream>>>(in, dout, din, B, Hi, Wi, C / 4, Ho, Wo);
     LAUNCH_END();
 }
 

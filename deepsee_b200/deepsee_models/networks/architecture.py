@@ -419,3 +419,78 @@ class SPADEResnetBlock(nn.Module):
     def forward(self, x, seg, style=None, split_location=-1):
         raise RuntimeError('SPADEResnetBlock is driven by DeepSEESR.forward on the B200 path '
                            '(NHWC activations, fused kernels); use forward_nhwc')
+
+
+# VGG19 feature stack of the perceptual loss (reference: architecture.py:151-181).  The reference
+# slices torchvision.models.vgg19(pretrained=True).features; the module tree below has the same
+# children names (slice1.0, slice1.1, slice2.2, ... slice5.29), so a state_dict of that model - or
+# torchvision's `features.N.*` keys - loads unchanged.  The forward runs on the deepsee_b200 kernels:
+# NHWC activations, 3x3 convs with the ReLU fused on the tcgen05 implicit-GEMM kernel (the 3-channel
+# first layer on the direct kernel), 2x2 max pooling as its own kernel.  The weights are frozen
+# (architecture.py:170-172): the backward pass is backward-data only.
+_VGG19_CFG = [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 256, 'M', 512, 512, 512, 512, 'M', 512]
+_VGG19_SLICES = ((0, 2), (2, 7), (7, 12), (12, 21), (21, 30))
+
+
+class VGG19(nn.Module):
+    def __init__(self, requires_grad=False, weights=None):
+        """weights: a state_dict (this module's keys or torchvision's `features.N.weight/bias`), a path
+        to one, or None = look for torchvision's vgg19 checkpoint in $DSEE_VGG19_WEIGHTS and the torch
+        hub cache; there is no network here, so a missing checkpoint raises."""
+        super().__init__()
+        layers, cin = [], 3
+        for v in _VGG19_CFG:
+            if v == 'M':
+                layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
+            else:
+                layers += [nn.Conv2d(cin, v, kernel_size=3, padding=1), nn.ReLU(inplace=True)]
+                cin = v
+        for si, (a, b) in enumerate(_VGG19_SLICES):
+            seq = nn.Sequential()
+            for i in range(a, b):
+                seq.add_module(str(i), layers[i])
+            setattr(self, 'slice%d' % (si + 1), seq)
+        self._load(weights)
+        if not requires_grad:
+            for p in self.parameters():
+                p.requires_grad = False
+
+    def _load(self, weights):
+        import os
+        if weights is None:
+            cands = [os.environ.get('DSEE_VGG19_WEIGHTS'),
+                     os.path.join(torch.hub.get_dir(), 'checkpoints', 'vgg19-dcbb9e9d.pth')]
+            weights = next((c for c in cands if c and os.path.exists(c)), None)
+            if weights is None:
+                raise RuntimeError(
+                    'VGG19: no pretrained weights found (set DSEE_VGG19_WEIGHTS to torchvision\'s '
+                    'vgg19-dcbb9e9d.pth, or pass weights=...); the perceptual loss cannot be downloaded here - '
+                    'train with --no_vgg_loss or provide the file')
+        if isinstance(weights, str):
+            weights = torch.load(weights, map_location='cpu')
+        own = {}
+        for si, (a, b) in enumerate(_VGG19_SLICES):
+            for i in range(a, b):
+                for nm in ('weight', 'bias'):
+                    for key in ('slice%d.%d.%s' % (si + 1, i, nm), 'features.%d.%s' % (i, nm)):
+                        if key in weights:
+                            own['slice%d.%d.%s' % (si + 1, i, nm)] = weights[key]
+        self.load_state_dict(own, strict=True)
+
+    def forward(self, X):
+        """X: fp32 NCHW [B,3,H,W] -> [h_relu1 ... h_relu5] as NCHW views of the NHWC feature maps."""
+        if not X.is_cuda:
+            raise RuntimeError('VGG19 (B200 path) needs CUDA tensors; there is no CPU fallback')
+        # NHWC with the 3 colour channels padded to 4 (the direct conv kernel's input-gradient path
+        # works on channel quads); plain torch layout ops so autograd reaches the fake image
+        x = torch.nn.functional.pad(X.float().permute(0, 2, 3, 1), (0, 1)).contiguous()
+        outs = []
+        for si in range(5):
+            for m in getattr(self, 'slice%d' % (si + 1)):
+                if isinstance(m, nn.Conv2d):
+                    x = ops.conv_layer(x, m.weight, m.bias, 1, 1, lrelu=2)   # conv + ReLU fused
+                elif isinstance(m, nn.MaxPool2d):
+                    x = ops.MaxPool2Fn.apply(x)
+                # nn.ReLU: fused into the conv above
+            outs.append(x.permute(0, 3, 1, 2))
+        return outs

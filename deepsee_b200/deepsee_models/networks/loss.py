@@ -1,8 +1,9 @@
 """GAN / feature-matching losses (reference: deepsee_models/networks/loss.py:19-101).
 
 Scalar reductions over the discriminator's small output maps; SURVEY.md section 8 (a13) keeps
-them in PyTorch ("negligible").  VGG perceptual loss needs pretrained torchvision weights that
-cannot be downloaded offline and is out of scope: constructing it raises.
+them in PyTorch ("negligible").  The VGG perceptual loss (loss.py:104-119) runs its VGG19 feature
+stack on the deepsee_b200 conv kernels (networks/architecture.py:VGG19); its pretrained torchvision
+weights cannot be downloaded here and must be supplied as a file (DSEE_VGG19_WEIGHTS).
 """
 import torch
 import torch.nn as nn
@@ -50,8 +51,23 @@ class GANLoss(nn.Module):
 
 
 class VGGLoss(nn.Module):
-    def __init__(self, gpu_ids):
+    """Perceptual loss (loss.py:104-119): L1 distances between the VGG19 feature maps of the fake and
+    the real image at relu1_1 ... relu5_1, weights 1/32, 1/16, 1/8, 1/4, 1.  Both images go through
+    the feature stack as ONE batch of 2B (half the launches); only the fake half carries a gradient."""
+
+    def __init__(self, gpu_ids, weights=None):
         super().__init__()
-        raise NotImplementedError(
-            'VGGLoss needs pretrained torchvision VGG19 weights (network download) and is outside '
-            'the B200 hot path; run with --no_vgg_loss')
+        from .architecture import VGG19
+        self.vgg = VGG19(weights=weights)
+        if gpu_ids or torch.cuda.is_available():
+            self.vgg.cuda()
+        self.criterion = nn.L1Loss()
+        self.weights = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
+
+    def forward(self, x, y):
+        B = x.size(0)
+        feats = self.vgg(torch.cat([x, y.detach()], 0))
+        loss = 0
+        for w, f in zip(self.weights, feats):
+            loss = loss + w * self.criterion(f[:B], f[B:].detach())
+        return loss

@@ -1014,7 +1014,7 @@ class Conv2dTCFn(torch.autograd.Function):
         N, Cw, KH, KW = w.shape
         dy = dy.contiguous()
         if lrelu:
-            dy = act_bwd(dy, out, 1)
+            dy = act_bwd(dy, out, 3 if lrelu == 2 else 1)
         g, sums = grad_prep(dy, want_lo=want_lo)
         dx = dw = db = None
         if ctx.needs_input_grad[1]:
@@ -1069,7 +1069,7 @@ class Conv2dDirectFn(torch.autograd.Function):
         stride, pad, ups, lrelu, has_bias = ctx.cfg
         dy = dy.contiguous()
         if lrelu:
-            dy = act_bwd(dy, out, 1)
+            dy = act_bwd(dy, out, 3 if lrelu == 2 else 1)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = conv2d_direct_dgrad(dy, w, tuple(x.shape), stride, pad, ups)
@@ -1134,6 +1134,28 @@ class AvgPool3s2Fn(torch.autograd.Function):
         dout = dout.contiguous()
         din = torch.empty(ctx.shape, dtype=torch.float32, device=dout.device)
         _lib.check(_lib.load().dsee_avgpool3s2_bwd(_p(dout), _p(din), B, Hi, Wi, Cc, _stream()))
+        return din
+
+
+class MaxPool2Fn(torch.autograd.Function):
+    """nn.MaxPool2d(2, 2) on NHWC fp32 (VGG19)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _chk_cuda(x)
+        B, Hi, Wi, Cc = x.shape
+        out = torch.empty((B, Hi // 2, Wi // 2, Cc), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().dsee_maxpool2_fwd(_p(x), _p(out), B, Hi, Wi, Cc, _stream()))
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        B, Hi, Wi, Cc = x.shape
+        dout = dout.contiguous()
+        din = torch.empty_like(x)
+        _lib.check(_lib.load().dsee_maxpool2_bwd(_p(x), _p(dout), _p(din), B, Hi, Wi, Cc, _stream()))
         return din
 
 

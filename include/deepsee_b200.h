@@ -90,6 +90,14 @@ int dsee_labels_u8(const int64_t* label, uint8_t* out, int64_t n, int L, int* ba
 int dsee_bicubic_clamp(const float* in, float* out, int B, int C, int Hi, int Wi, int Ho, int Wo,
                        void* stream);
 
+/* VGG19 perceptual loss (loss.py:104-119, architecture.py:151-181): its 3x3 convs run on
+ * dsee_conv2d_tc / dsee_conv2d_direct_fwd with the ReLU fused (dsee_conv_epilogue.lrelu = 2;
+ * dsee_act_bwd act = 3 in the backward pass); nn.MaxPool2d(2, 2) is this pair (NHWC fp32, C % 4 == 0;
+ * the backward pass recomputes the arg-max from `in`, first maximum in window order like ATen). */
+int dsee_maxpool2_fwd(const float* in, float* out, int B, int Hi, int Wi, int C, void* stream);
+int dsee_maxpool2_bwd(const float* in, const float* dout, float* din, int B, int Hi, int Wi, int C,
+                      void* stream);
+
 /* Noise epoch: a per-device 64-bit counter that every kernel regenerating NoiseInjection noise
  * from a seed folds into that seed.  Advancing it (a one-thread kernel on `stream`) makes launches
  * whose seeds are baked into a captured CUDA graph draw fresh noise on every replay; forward and
@@ -204,7 +212,7 @@ typedef struct {
     /* optional device float: receives max |out| (what the next gradient-plane scale is chosen
      * from); zeroed by the call. */
     float* amax_out;
-    /* fuse LeakyReLU(0.2) after the bias (discriminator.py:84-85) */
+    /* activation fused after the bias: 1 = LeakyReLU(0.2) (discriminator.py:84-85), 2 = ReLU (VGG19) */
     int lrelu;
     /* when noise[i] is NULL and noise_seed[i] != 0 the noise tensor is regenerated in the kernel
      * from the counter-based generator (see dsee_noise_fill) instead of being read from HBM */

@@ -477,6 +477,51 @@ def inference(sdG, sdE, opt, image_lr, seg, image_hr=None):
 
 
 # =================================================================================================
+# VGG19 perceptual loss (loss.py:104-119, architecture.py:151-181)
+# =================================================================================================
+VGG19_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512]
+VGG19_SLICE_ENDS = (2, 7, 12, 21, 30)   # architecture.py:160-169: features[0:2], [2:7], [7:12], [12:21], [21:30]
+
+
+def make_vgg19_state(seed=3):
+    """Seeded stand-in for torchvision's pretrained vgg19 `features` (He-scaled so activations keep
+    O(1) magnitude through 13 layers); keys `features.N.weight / bias` like torchvision's."""
+    g = torch.Generator().manual_seed(seed)
+    sd, cin, i = OrderedDict(), 3, 0
+    for v in VGG19_CFG:
+        if v == "M":
+            i += 1
+            continue
+        sd["features.%d.weight" % i] = torch.randn(v, cin, 3, 3, generator=g) * math.sqrt(2.0 / (cin * 9))
+        sd["features.%d.bias" % i] = torch.randn(v, generator=g) * 0.05
+        cin = v
+        i += 2
+    return sd
+
+
+def vgg19_features(sd, x):
+    """VGG19.forward (architecture.py:174-181): [h_relu1_1, h_relu2_1, h_relu3_1, h_relu4_1, h_relu5_1]."""
+    outs, i = [], 0
+    for v in VGG19_CFG:
+        if v == "M":
+            x = F.max_pool2d(x, 2, 2)
+            i += 1
+        else:
+            x = F.relu(F.conv2d(x, sd["features.%d.weight" % i], sd["features.%d.bias" % i], padding=1))
+            i += 2
+        if i in VGG19_SLICE_ENDS:
+            outs.append(x)
+    return outs
+
+
+def vgg_loss(sd, x, y):
+    """VGGLoss.forward (loss.py:114-119)."""
+    weights = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
+    fx, fy = vgg19_features(sd, x), vgg19_features(sd, y)
+    return sum(w * F.l1_loss(a, b.detach()) for w, a, b in zip(weights, fx, fy))
+
+
+# =================================================================================================
 # deterministic "conditioned" weights
 # =================================================================================================
 def _spectral_conv(sd, pfx, cout, cin, k, g, gain, bias=True):

@@ -18,10 +18,13 @@ def _run(graphs, steps, name, over):
     from deepsee_b200.config import config
     from deepsee_b200.managers.trainer_manager import TrainerManager
     saved = config.cuda_graphs
-    config.cuda_graphs = graphs
+    # both runs build their optimizers with capturable Adam (device-side step counters and bias
+    # corrections), so the eager reference executes exactly the kernels the graphs replay
+    config.cuda_graphs = True
     try:
         o = O.make_opt(name, is_train=True, **over)
         mgr = TrainerManager(_mk_opt(o))
+        config.cuda_graphs = graphs
         m = mgr.sr_model
         m.netSR.load_state_dict(O.make_generator_state(o, 0), strict=True)
         m.netE.load_state_dict(O.make_encoder_state(o, 1), strict=True)
@@ -51,6 +54,7 @@ def _run(graphs, steps, name, over):
 def test_graphed_training_equals_eager(name, over):
     steps = 9
     l_eager, sd_eager, _ = _run(False, steps, name, over)
+    assert _.graph_replays == 0
     l_graph, sd_graph, mgr = _run(True, steps, name, over)
     assert mgr.graphs_active() and mgr.graph_replays > 0, "the graphed path did not engage"
     variants = {m: len(s.graphs) for m, s in mgr._graphed.items()}
