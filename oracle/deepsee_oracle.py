@@ -476,6 +476,46 @@ def inference(sdG, sdE, opt, image_lr, seg, image_hr=None):
         return generator_forward(sdG, opt, image_lr, seg, z, training=False), z
 
 
+def sweep_interpolation(sdG, sdE, opt, image_lr, seg, image_hr, n, delta, region_idx=None):
+    """SRModel.forward(mode='inference_interpolation'), sr_model.py:219-261: per sample, n renderings
+    with the style of `region_idx` shifted by -delta ... +delta, one batch-1 generator call each, laid
+    out side by side.  -> (fake [B,3,S,n*S], applied styles [B][n,L,d])."""
+    rng = _random.Random(0)
+    with torch.no_grad():
+        style, _ = encode_style(sdE, opt, rng, False, image_lr, seg, image_hr, None, None, no_noise=True)
+        ridx = list(region_idx) if region_idx else list(range(seg.size(1)))
+        rows, applied = [], []
+        for b in range(seg.size(0)):
+            samples, styles = [], []
+            for step in np.linspace(-delta, delta, num=n):
+                z = style[b].clone()
+                z[ridx] = (z[ridx] + step).clamp(-1, 1)
+                samples.append(generator_forward(sdG, opt, image_lr[b:b + 1], seg[b:b + 1], z[None], training=False))
+                styles.append(z)
+            rows.append(torch.cat(samples, -1))
+            applied.append(torch.stack(styles))
+        return torch.cat(rows, 0), applied
+
+
+def sweep_reference(sdG, sdE, opt, image_lr, seg, image_hr, region_idx=None):
+    """SRModel.forward(mode='inference_reference'), sr_model.py:381-410: the HR image's own style
+    (encoder_full) with the `region_idx` rows replaced by every sample's in turn."""
+    rng = _random.Random(0)
+    with torch.no_grad():
+        full, _ = encode_style(sdE, opt, rng, False, None, seg, image_hr, None, None, no_noise=True,
+                               encode_full=True)
+        ridx = list(region_idx) if region_idx else list(range(seg.size(1)))
+        rows = []
+        for b in range(seg.size(0)):
+            samples = []
+            for other in range(seg.size(0)):
+                z = full[b].clone()
+                z[ridx] = full[other, ridx].clamp(-1, 1)
+                samples.append(generator_forward(sdG, opt, image_lr[b:b + 1], seg[b:b + 1], z[None], training=False))
+            rows.append(torch.cat(samples, -1))
+        return torch.cat(rows, 0)
+
+
 # =================================================================================================
 # VGG19 perceptual loss (loss.py:104-119, architecture.py:151-181)
 # =================================================================================================

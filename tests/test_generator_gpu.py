@@ -280,3 +280,40 @@ def test_srmodel_style_sweep_modes_match_demo_mode(tmp_path):
     assert (out["fake_image"][1, 2] - demo(1, out["style"][1][2])).abs().max().item() < 2e-5
     with pytest.raises(NotImplementedError):
         model(dict(data), "inference_replace_semantics")
+
+
+def test_style_sweep_modes_vs_oracle(tmp_path):
+    """The demo-time modes against the ORACLE's restatement of the reference loops (sr_model.py:219-261
+    'inference_interpolation', :381-410 'inference_reference'): one batch-1 generator call per variant
+    there, one batched call here."""
+    from deepsee_b200.managers.base_manager import BaseManager
+    o = O.make_opt("8x_independent_256x256", ngf=8, start_size=8, crop_size=64, load_size=64)
+    sdG, sdE = O.make_generator_state(o, 0), O.make_encoder_state(o, 1)
+    ck = tmp_path / o.name
+    ck.mkdir()
+    torch.save({"model": sdG}, str(ck / "latest_net_SR.pth"))
+    torch.save({"model": sdE}, str(ck / "latest_net_E.pth"))
+    opt = _mk_opt(o, checkpoints_dir=str(tmp_path), n_interpolation=3, noise_delta=0.25, region_idx=[1, 2, 5],
+                  dont_merge_fake=False, manipulate_scale=1.0, batchSize=2)
+    mgr = BaseManager(opt)
+    model = mgr.sr_model.eval()
+    raw = O.synthetic_batch(o, 2, seed=41)
+    ref_in = O.preprocess(o, raw)
+    data = mgr.preprocess({"label": raw["label"].clone().float(), "image": raw["image"].clone()},
+                          from_dataloader=True)
+    ref, ref_styles = O.sweep_interpolation(sdG, sdE, o, ref_in["image_lr"], ref_in["input_semantics"],
+                                            ref_in["image_hr"], 3, 0.25, [1, 2, 5])
+    out = model(dict(data), "inference_interpolation")
+    err = (out["fake_image"].cpu() - ref).abs().max().item()
+    print("inference_interpolation max-abs vs oracle: %.3e" % err)
+    assert tuple(out["fake_image"].shape) == tuple(ref.shape) and err < 3e-4
+    ref = O.sweep_reference(sdG, sdE, o, ref_in["image_lr"], ref_in["input_semantics"], ref_in["image_hr"],
+                            [1, 2, 5])
+    out = model(dict(data), "inference_reference")
+    err = (out["fake_image"].cpu() - ref).abs().max().item()
+    print("inference_reference max-abs vs oracle: %.3e" % err)
+    assert tuple(out["fake_image"].shape) == tuple(ref.shape) and err < 3e-4
+    opt.dont_merge_fake = True
+    out = model(dict(data), "inference_interpolation")
+    for b in range(2):
+        assert (out["style"][b].cpu() - ref_styles[b]).abs().max().item() < 2e-5
