@@ -16,7 +16,8 @@ SYMBOLS = [
     "dsee_labels_u8", "dsee_bicubic_clamp", "dsee_maxpool2_fwd", "dsee_maxpool2_bwd", "dsee_noise_fill", "dsee_noise_epoch_advance", "dsee_noise_epoch_set", "dsee_onehot_from_labels", "dsee_labels_from_onehot", "dsee_resize_labels",
     "dsee_shared_mlp_fwd", "dsee_style_gather_fwd",
     "dsee_prep_conv_weight", "dsee_prep_conv_weight_f8", "dsee_prep_mod_weight_batched", "dsee_split_f16",
-    "dsee_conv3x3_wgrad_per_image_workspace_floats", "dsee_conv3x3_wgrad2_per_image", "dsee_prep_conv_weight_ex", "dsee_split_f16_ups2",
+    "dsee_conv3x3_wgrad_per_image_workspace_floats", "dsee_conv3x3_wgrad2_per_image",
+    "dsee_subpixel_wgrad_workspace_floats", "dsee_subpixel_wgrad", "dsee_subpixel_dgrad", "dsee_prep_conv_weight_ex", "dsee_split_f16_ups2",
     "dsee_fold2x2", "dsee_conv2d_tc", "dsee_conv2d_tc_wgrad_workspace_floats", "dsee_conv2d_tc_wgrad",
     "dsee_conv3x3_fwd", "dsee_conv3x3_stats_tiles", "dsee_spade_modulate_fwd",
     "dsee_spade_modulate_bwd", "dsee_spade_modulate_bwd_saved", "dsee_dgrad_modulate_bwd", "dsee_grad_prep_blocks", "dsee_grad_prep", "dsee_reduce_partials",
@@ -44,7 +45,7 @@ class ConvOperands(C.Structure):
         ("n_total", C.c_int), ("passes", C.c_int), ("a_dtype", C.c_int), ("w_dtype", C.c_int),
         ("a_inv_scale", C.c_void_p),
         ("a8_lo", C.c_void_p), ("a8_hi", C.c_void_p), ("w8", C.c_void_p),
-        ("w_batch_rows", C.c_int),
+        ("w_batch_rows", C.c_int), ("a_sub", C.c_int), ("sub_py", C.c_int), ("sub_px", C.c_int),
     ]
 
 
@@ -156,6 +157,9 @@ def load():
         "dsee_prep_mod_weight_batched": [vp, vp, vp, vp, vp, i, i, i, i, i, vp],
         "dsee_conv3x3_wgrad2_per_image": [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i), i, i, i, i,
                                           i, i, vp, vp, vp],
+        "dsee_subpixel_wgrad": [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i), i, i, i, i, i, i, i,
+                                vp, vp, vp],
+        "dsee_subpixel_dgrad": [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, vp, vp],
         "dsee_split_f16": [vp, vp, vp, i64, vp],
         "dsee_prep_conv_weight_ex": [vp, vp, vp, vp, i, i, i, i, i, vp],
         "dsee_split_f16_ups2": [vp, vp, vp, i, i, i, i, vp],
@@ -228,6 +232,8 @@ def load():
     lib.dsee_conv3x3_wgrad_workspace_floats.restype = C.c_int64
     lib.dsee_conv3x3_wgrad_per_image_workspace_floats.argtypes = [i, i, i, i, i]
     lib.dsee_conv3x3_wgrad_per_image_workspace_floats.restype = C.c_int64
+    lib.dsee_subpixel_wgrad_workspace_floats.argtypes = [i, i, i, i, i]
+    lib.dsee_subpixel_wgrad_workspace_floats.restype = C.c_int64
     lib.dsee_spectral_workspace_floats.argtypes = [i, i]
     lib.dsee_spectral_workspace_floats.restype = C.c_int64
     lib.dsee_modweight_bwd_workspace_bytes.argtypes = [i, i, i]

@@ -67,6 +67,12 @@ class _Config:
     # halves (no gradient flows into a one-hot plane) and the gathered style_map is never built.
     # Needs save_gamma.  0 = the gathered 128-channel style_map.
     fold_style = os.environ.get("DSEE_FOLD_STYLE", "1") != "0"
+    # Conditional-norm layers above max_fm_size convolve the nearest-2x-upsampled mlp_shared activation
+    # (normalization.py:188-190,275-277: the 512x512 PureSEAN block of the 32x models).  Sub-pixel
+    # form: keep the activation at half resolution and run four 2x2-tap GEMMs, one per output parity
+    # class (ops.collapse_subpixel): 4/9 of the FLOPs forward and backward, and the upsampled tensor is
+    # never built.  Needs save_gamma.  0 = materialise the upsampled activation.
+    subpixel = os.environ.get("DSEE_SUBPIXEL", "1") != "0"
     # Training: K1 saves G = gamma + gamma_bias (fp16 planes, +1-2 B per activation element) so its
     # backward is one streaming pass instead of re-running the gamma GEMM (0 = recompute).
     save_gamma = os.environ.get("DSEE_SAVE_GAMMA", "1") != "0"

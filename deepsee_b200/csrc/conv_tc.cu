@@ -663,7 +663,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                 // EPI_MODULATE: columns [0,128) gamma, [128,256) beta for channels nt*128 + j.
                 // Both 32 x 32 chunks go through the transpose tile (gamma first, kept in registers).
                 const int c0 = nt * 128;
-                const int Hx = p.H >> p.x_ups, Wx = p.W >> p.x_ups;
+                // tile pixel (yy, xx) lives at (yy * o_step + o_offy, xx * o_step + o_offx) of the [Hm, Wm]
+                // output (o_step = 2: one parity class of the sub-pixel form; 1 otherwise)
+                const int Hx = p.Hm >> p.x_ups, Wx = p.Wm >> p.x_ups;
                 const bool has_noise = p.noise_w != nullptr;
 #pragma unroll 1
                 for (int ch = eh; ch < 4; ch += ESTEP) {
@@ -703,7 +705,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         const int yy = h0 + mm / TILE_W, xx = w0 + mm % TILE_W;
                         xq[st] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (yy < p.H && xx < p.W) {
-                            const size_t xp = ((size_t)b * Hx + (yy >> p.x_ups)) * Wx + (xx >> p.x_ups);
+                            const int fy = yy * p.o_step + p.o_offy, fx = xx * p.o_step + p.o_offx;
+                            const size_t xp = ((size_t)b * Hx + (fy >> p.x_ups)) * Wx + (fx >> p.x_ups);
                             xq[st] = __ldg(reinterpret_cast<const float4*>(p.x + xp * p.C + cc));
                         }
                     }
@@ -713,7 +716,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         const int mm = q * 32 + pi;
                         const int yy = h0 + mm / TILE_W, xx = w0 + mm % TILE_W;
                         if (yy >= p.H || xx >= p.W) continue;
-                        const size_t pix = ((size_t)b * p.H + yy) * p.W + xx;
+                        const size_t pix = ((size_t)b * p.Hm + (yy * p.o_step + p.o_offy)) * p.Wm +
+                                           (xx * p.o_step + p.o_offx);
                         const size_t pe = pix * p.C + cc;
                         float4 xv = xq[st];
                         if (has_noise) {
@@ -779,7 +783,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_f8 = false) {
+static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_f8 = false,
+                       bool allow_sub = false) {
     DSEE_CHECK_ARG(ops != nullptr, "conv operands are NULL");
     DSEE_CHECK_ARG(ops->B > 0 && ops->H > 0 && ops->W > 0, "bad geometry B=%d H=%d W=%d", ops->B,
                    ops->H, ops->W);
@@ -843,6 +848,30 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
     p.idesc = (1u << 4) | ((uint32_t)ops->a_dtype << 7) | ((uint32_t)ops->w_dtype << 10) |
               ((uint32_t)(p.b_rows >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 
+    const int sub = ops->a_sub ? 1 : 0;
+    if (sub) {
+        DSEE_CHECK_ARG(allow_sub, "a_sub (sub-pixel form) is implemented for dsee_spade_modulate_fwd only");
+        DSEE_CHECK_ARG(ops->H % 2 == 0 && ops->W % 2 == 0 && (ops->sub_py | 1) == 1 && (ops->sub_px | 1) == 1 &&
+                           ops->passes != 2,
+                       "sub-pixel form needs even H, W, a parity class in {0,1}^2 and passes 1 or 3");
+        // tile space = the class's output pixels = the half-resolution grid
+        p.H = ops->H / 2;
+        p.W = ops->W / 2;
+        p.o_step = 2;
+        p.o_offy = ops->sub_py;
+        p.o_offx = ops->sub_px;
+        p.ntaps = 4;
+        const int ctot = ops->a_channels[0] + ops->a_channels[1];
+        for (int t = 0; t < 4; ++t) {
+            p.tap_dy[t] = (int8_t)(t / 2 + ops->sub_py - 1);
+            p.tap_dx[t] = (int8_t)(t % 2 + ops->sub_px - 1);
+            p.tap_k[t] = t * ctot;
+        }
+        p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
+        p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
+        p.num_tiles = p.B * p.tiles_h * p.tiles_w * p.n_tiles;
+    }
+    const int Ha = ops->H >> sub, Wa = ops->W >> sub;   // resolution of the A planes
     for (int src = 0; src < 2; ++src) {
         const int C = ops->a_channels[src];
         for (int pl = 0; pl < 2; ++pl) {
@@ -852,9 +881,8 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
                 p.tmA[src * 2 + pl] = p.tmA[0];
                 continue;
             }
-            uint64_t dims[4] = {(uint64_t)C, (uint64_t)ops->W, (uint64_t)ops->H, (uint64_t)ops->B};
-            uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)ops->W * C * 2,
-                                   (uint64_t)ops->H * ops->W * C * 2};
+            uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wa, (uint64_t)Ha, (uint64_t)ops->B};
+            uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)Wa * C * 2, (uint64_t)Ha * Wa * C * 2};
             uint32_t box[4] = {BLOCK_K, TILE_W, TILE_H, 1};
             rc = encode_tmap_16b(&p.tmA[src * 2 + pl], base, 4, dims, strides, box, ops->a_dtype == 1);
             if (rc) return rc;
@@ -879,7 +907,7 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
         rc = encode_tmap_8b(&p.tmB8, ops->w8, 2, dims, strides, box);
         if (rc) return rc;
     }
-    const uint64_t Ktot = (uint64_t)9 * (ops->a_channels[0] + ops->a_channels[1]);
+    const uint64_t Ktot = (uint64_t)(sub ? 4 : 9) * (ops->a_channels[0] + ops->a_channels[1]);
     // the weight matrix is padded by the caller to a multiple of BLOCK_N rows? No: TMA zero-fills
     // rows >= n_total, and the epilogue never stores those columns.
     for (int pl = 0; pl < 2; ++pl) {
@@ -1068,11 +1096,81 @@ extern "C" int dsee_conv2d_tc(const dsee_conv2d_tc_args* a, const dsee_conv_epil
     return 0;
 }
 
+extern "C" int dsee_subpixel_dgrad(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale,
+                                   const void* w_hi, const void* w_lo, const float* w_inv_scale, int B, int H,
+                                   int W, int n_total, int C, int passes, float* out, float* amax_out,
+                                   void* stream) {
+    DSEE_CHECK_ARG(dy_hi && w_hi && w_inv_scale && out, "NULL pointer");
+    DSEE_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bad geometry (H, W even)");
+    DSEE_CHECK_ARG(n_total > 0 && n_total % BLOCK_K == 0 && C > 0 && C % 32 == 0, "bad channel counts");
+    DSEE_CHECK_ARG(passes == 1 || (passes == 3 && dy_lo && w_lo), "passes must be 1, or 3 with lo planes");
+    int rc = require_sm100();
+    if (rc) return rc;
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B;
+    p.H = p.Hm = H / 2;   // output = the half-resolution gradient
+    p.W = p.Wm = W / 2;
+    p.o_step = 1;
+    p.a_step = 2;         // A = dY planes at full resolution, element stride 2
+    p.ntaps = 16;
+    for (int k = 0; k < 4; ++k)          // parity class (py, px)
+        for (int t = 0; t < 4; ++t) {    // its 2x2 tap (ty, tx) at half-resolution offset r = t + p - 1
+            const int py = k >> 1, px = k & 1;
+            const int ry = (t >> 1) + py - 1, rx = (t & 1) + px - 1;
+            // dA[Y] += dY[2 (Y - ry) + py] * wc: box origin = 2 * Y0 + (py - 2 ry)
+            p.tap_dy[k * 4 + t] = (int8_t)(py - 2 * ry);
+            p.tap_dx[k * 4 + t] = (int8_t)(px - 2 * rx);
+            p.tap_k[k * 4 + t] = (k * 4 + t) * n_total;
+        }
+    p.cb0 = p.cb_total = n_total / BLOCK_K;
+    p.passes = passes;
+    p.n_total = C;
+    p.w_inv_scale = w_inv_scale;
+    p.a_inv_scale = dy_inv_scale;
+    p.noise_epoch = noise_epoch_ptr();
+    p.b_rows = round_up(C < BLOCK_N ? C : BLOCK_N, 16);
+    p.idesc = (1u << 4) | ((uint32_t)(p.b_rows >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    p.n_tiles = (C + BLOCK_N - 1) / BLOCK_N;
+    p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
+    p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
+    p.num_tiles = p.B * p.tiles_h * p.tiles_w * p.n_tiles;
+    p.out = out;
+    p.amax_out = amax_out;
+    if (amax_out) DSEE_CUDA(cudaMemsetAsync(amax_out, 0, sizeof(float), (cudaStream_t)stream));
+    for (int pl = 0; pl < 2; ++pl) {
+        const void* ab = pl ? dy_lo : dy_hi;
+        if (ab) {
+            uint64_t dims[4] = {(uint64_t)n_total, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+            uint64_t strides[3] = {(uint64_t)n_total * 2, (uint64_t)W * n_total * 2, (uint64_t)H * W * n_total * 2};
+            uint32_t box[4] = {BLOCK_K, (uint32_t)(TILE_W * 2), (uint32_t)(TILE_H * 2), 1};
+            uint32_t es[4] = {1, 2, 2, 1};
+            rc = encode_tmap_16b(&p.tmA[pl], ab, 4, dims, strides, box, false, es);
+            if (rc) return rc;
+        } else {
+            p.tmA[pl] = p.tmA[0];
+        }
+        p.tmA[2 + pl] = p.tmA[pl];
+        const void* wb = pl ? w_lo : w_hi;
+        if (wb) {
+            const uint64_t Ktot = (uint64_t)16 * n_total;
+            uint64_t dims[2] = {Ktot, (uint64_t)C};
+            uint64_t strides[1] = {Ktot * 2};
+            uint32_t box[2] = {BLOCK_K, (uint32_t)p.b_rows};
+            rc = encode_tmap_16b(&p.tmB[pl], wb, 2, dims, strides, box, false);
+            if (rc) return rc;
+        } else {
+            p.tmB[pl] = p.tmB[0];
+        }
+    }
+    return launch<EPI_CONV>(p, (cudaStream_t)stream);
+}
+
 extern "C" int dsee_spade_modulate_fwd(const dsee_conv_operands* ops, const dsee_modulate_args* mod,
                                        void* stream) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
-    int rc = fill_common(p, ops);
+    int rc = fill_common(p, ops, false, true);
     if (rc) return rc;
     DSEE_CHECK_ARG(mod != nullptr, "modulate args are NULL");
     DSEE_CHECK_ARG(mod->C > 0 && mod->C % 128 == 0, "C must be a multiple of 128 (got %d)", mod->C);

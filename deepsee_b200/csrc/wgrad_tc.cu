@@ -49,6 +49,7 @@ struct alignas(64) WgradParams {
     int tiles_w, tiles_h, ptiles;  // pixel tiles
     int n_total, c_total;
     int ntaps, a_step;           // filter taps; A box origin = dY tile origin * a_step + tap offset
+    int d_step, d_offy, d_offx;  // dY box origin = tile origin * d_step + offset (sub-pixel classes: 2)
     int8_t tap_dy[16], tap_dx[16];
     int n_tiles, c_tiles, splits, num_units;
     int n_cols;  // activation channels per unit (<= 256)
@@ -141,7 +142,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                         uint8_t* sa = sd + (WG_M / 64) * WG_BOX_BYTES;
                         for (int i = 0; i < WG_M / 64; ++i)
                             tma_load_4d(&p.tmD[pd], &full_bar[s], sd + i * WG_BOX_BYTES,
-                                        nt * WG_M + i * 64, w0, h0, b);
+                                        nt * WG_M + i * 64, w0 * p.d_step + p.d_offx,
+                                        h0 * p.d_step + p.d_offy, b);
                         for (int i = 0; i < nboxA; ++i) {
                             const int c = ct * WG_NMAX + i * 64;
                             const bool second = c >= p.c_split;
@@ -312,7 +314,10 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
                       int Hi, int Wi, int n_total, int a_channels, int c_total, int KH, int KW,
                       int stride, int pad, int passes, float* workspace, float* dw, int layout_nc9,
                       void* stream, const void* a2_hi = nullptr, const void* a2_lo = nullptr,
-                      int a2_channels = 0, bool per_image = false) {
+                      int a2_channels = 0, bool per_image = false, int sub_py = -1, int sub_px = -1) {
+    // sub_py / sub_px >= 0: one parity class of the sub-pixel form - H, W are the HALF-resolution
+    // tile space, the dY planes are [B, 2H, 2W, n_total] read with element stride 2 from (sub_py,
+    // sub_px), the 2x2 taps sit at rows ty + sub_py - 1 of the half-resolution activation
     // H, W: dY (= forward output) size; Hi, Wi: activation (= forward input) size;
     // a_channels: channels stored in the activation planes, c_total: dW columns (a multiple of 64)
     const int T = KH * KW;
@@ -330,9 +335,13 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
     p.c_split = a2_channels > 0 ? a_channels : c_total;
     p.ntaps = T;
     p.a_step = stride;
+    const bool sub = sub_py >= 0;
+    p.d_step = sub ? 2 : 1;
+    p.d_offy = sub ? sub_py : 0;
+    p.d_offx = sub ? sub_px : 0;
     for (int t = 0; t < T; ++t) {
-        p.tap_dy[t] = (int8_t)(t / KW - pad);
-        p.tap_dx[t] = (int8_t)(t % KW - pad);
+        p.tap_dy[t] = (int8_t)(t / KW - (sub ? 1 - sub_py : pad));
+        p.tap_dx[t] = (int8_t)(t % KW - (sub ? 1 - sub_px : pad));
     }
     p.n_tiles = (n_total + WG_M - 1) / WG_M;
     p.c_tiles = (c_total + WG_NMAX - 1) / WG_NMAX;
@@ -346,16 +355,18 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
     // kind::f16, fp32 accumulate, both operands MN-major, M = 128, N = n_cols
     p.idesc = (1u << 4) | ((uint32_t)dtype << 7) | ((uint32_t)dtype << 10) | (1u << 15) | (1u << 16) |
               ((uint32_t)(p.n_cols >> 3) << 17) | ((uint32_t)(WG_M >> 4) << 24);
-    uint32_t boxd[4] = {64, WG_TW, WG_TH, 1};
+    uint32_t boxd[4] = {64, (uint32_t)(WG_TW * p.d_step), (uint32_t)(WG_TH * p.d_step), 1};
+    uint32_t esd[4] = {1, (uint32_t)p.d_step, (uint32_t)p.d_step, 1};
     uint32_t boxa[4] = {64, (uint32_t)(WG_TW * stride), (uint32_t)(WG_TH * stride), 1};
     uint32_t esa[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     for (int pl = 0; pl < 2; ++pl) {
         const void* d = pl ? dy_lo : dy_hi;
         const void* a = pl ? a_lo : a_hi;
         if (d) {
-            uint64_t dims[4] = {(uint64_t)n_total, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-            uint64_t st[3] = {(uint64_t)n_total * 2, (uint64_t)W * n_total * 2, (uint64_t)H * W * n_total * 2};
-            rc = encode_tmap_16b(&p.tmD[pl], d, 4, dims, st, boxd, dtype == 1);
+            const uint64_t Wd = (uint64_t)W * p.d_step, Hd = (uint64_t)H * p.d_step;
+            uint64_t dims[4] = {(uint64_t)n_total, Wd, Hd, (uint64_t)B};
+            uint64_t st[3] = {(uint64_t)n_total * 2, Wd * n_total * 2, Hd * Wd * n_total * 2};
+            rc = encode_tmap_16b(&p.tmD[pl], d, 4, dims, st, boxd, dtype == 1, esd);
             if (rc) return rc;
         } else {
             p.tmD[pl] = p.tmD[0];
@@ -468,6 +479,33 @@ extern "C" int dsee_conv3x3_wgrad2_per_image(const void* dy_hi, const void* dy_l
     return wgrad_impl(dy_hi, dy_lo, dy_inv_scale, a_hi[0], a_lo ? a_lo[0] : nullptr, nullptr, dtype, B, H,
                       W, H, W, n_total, a_channels[0], c_total, 3, 3, 1, 1, passes, workspace, dw, 1, stream,
                       a_hi[1], a_lo ? a_lo[1] : nullptr, a_channels[1], true);
+}
+
+extern "C" int64_t dsee_subpixel_wgrad_workspace_floats(int B, int H, int W, int n_total, int c_total) {
+    int splits;
+    wgrad_plan(B, H / 2, W / 2, n_total, c_total, &splits, 4);
+    return (int64_t)splits * n_total * 4 * c_total;
+}
+
+extern "C" int dsee_subpixel_wgrad(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale,
+                                   const void* const* a_hi, const void* const* a_lo, const int* a_channels,
+                                   int B, int H, int W, int n_total, int sub_py, int sub_px, int passes,
+                                   float* workspace, float* dwc, void* stream) {
+    DSEE_CHECK_ARG(dy_hi && a_hi && a_channels && a_hi[0] && workspace && dwc, "NULL pointer");
+    DSEE_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bad geometry (H, W even)");
+    DSEE_CHECK_ARG((sub_py | 1) == 1 && (sub_px | 1) == 1, "parity class must be in {0,1}^2");
+    DSEE_CHECK_ARG(n_total % 128 == 0, "n_total must be a multiple of 128 (got %d)", n_total);
+    DSEE_CHECK_ARG(a_channels[0] > 0 && a_channels[0] % 64 == 0 && a_channels[1] >= 0 &&
+                       a_channels[1] % 64 == 0 && (a_channels[1] == 0 || a_hi[1]),
+                   "source channel counts must be multiples of 64");
+    const int c_total = a_channels[0] + a_channels[1];
+    DSEE_CHECK_ARG(c_total <= 256 || c_total % 256 == 0,
+                   "total channels must be at most 256 or a multiple of 256 (got %d)", c_total);
+    DSEE_CHECK_ARG(passes == 1 || (passes == 3 && dy_lo && a_lo && a_lo[0] && (a_channels[1] == 0 || a_lo[1])),
+                   "passes must be 1, or 3 with lo planes");
+    return wgrad_impl(dy_hi, dy_lo, dy_inv_scale, a_hi[0], a_lo ? a_lo[0] : nullptr, nullptr, 0, B, H / 2,
+                      W / 2, H / 2, W / 2, n_total, a_channels[0], c_total, 2, 2, 1, 0, passes, workspace, dwc,
+                      1, stream, a_hi[1], a_lo ? a_lo[1] : nullptr, a_channels[1], false, sub_py, sub_px);
 }
 
 extern "C" int64_t dsee_conv2d_tc_wgrad_workspace_floats(int B, int Ho, int Wo, int n_total, int Ci,

@@ -92,17 +92,20 @@ def _norm_forward(blk, norm, pre, Wm, Ws, gb, bb, tab, tb, gctx, style, x, x_ups
     else:
         st.sc, st.sh = norm.eval_affine()
         st.inv_count = 0.0
+    sub = Wm is not None and Wm.dim() == 5   # collapsed filters [4, 2C, Cin, 2, 2]: sub-pixel form
     if pre is not None:
         pw = pre
+    elif sub:
+        pw = ops.prep_subpixel_weight(Wm, want_lo=want_lo)
     elif Ws is not None:  # folded style: shared actv columns + per-image one-hot columns
         pw = ops.prep_mod_weight_batched(Wm.contiguous(), Ws.contiguous(), want_lo=want_lo)
     else:
         pw = ops.prep_conv_weight(Wm.contiguous(), want_lo=want_lo)
     st.srcs, st.meta = norm.build_sources(gctx, style, H, W, want_lo, table=tab, bias=tb,
-                                          folded=Ws is not None)
+                                          folded=Ws is not None, sub=sub)
     st.Wm, st.Ws, st.gb = Wm, Ws, gb
     r = ops.spade_modulate(st.srcs, pw, x, x_ups, st.sc, st.sh, gb, bb, noise=noise, noise_w=noise_w,
-                           passes=passes, want_lo=out_lo, save_g=save_g, want_f8=out_f8)
+                           passes=passes, want_lo=out_lo, save_g=save_g, want_f8=out_f8, subpixel=sub)
     a, st.g = r if save_g else (r, None)
     return a, st
 
@@ -147,6 +150,23 @@ def _norm_backward_tail(st, dgb, L, passes, want_lo, ss):
     (mlp_shared table / bias, style matrix) -> (dWm, dtab, dtb, dstyle, dWs)."""
     Wm = st.Wm
     dWs = None
+    meta = st.meta
+    if meta.get('sub'):
+        # sub-pixel form: Wm holds the collapsed filters [4, 2C, Cin, 2, 2]; both backward GEMMs run at
+        # 4/9 of the 3x3 work and the source gradient comes out at the sources' (half) resolution
+        dWm = ss.run(lambda: ops.subpixel_wgrad(dgb, st.srcs, passes=passes), dgb, *st.srcs)
+        dsrc, dsrc_amax = ops.subpixel_dgrad(dgb, Wm, passes=passes, want_lo=want_lo)
+        del dgb
+        dtab = dtb = None
+        coff = 0
+        for src in st.srcs:          # every source of a layer above max_fm_size is the actv tensor
+            onehot = meta['ctx'].onehot_at(*meta['fm'])
+            t, b = ops.shared_mlp_bwd_tc(dsrc, dsrc_amax, coff, meta['actv'].hi, meta['labels'], onehot, 0, L,
+                                         passes=passes, side=ss)
+            dtab = t if dtab is None else ss.run(lambda: dtab + t)
+            dtb = b if dtb is None else dtb + b
+            coff += src.hi.shape[3]
+        return dWm, dtab, dtb, None, None
     if st.Ws is not None:
         # folded style: one weight gradient per image; the actv columns are shared (sum over images),
         # the label columns are the gradient of Ws.  Wm holds the actv columns only, so the
@@ -160,7 +180,6 @@ def _norm_backward_tail(st, dgb, L, passes, want_lo, ss):
     pwT = ops.prep_conv_weight(Wm.contiguous(), want_lo=want_lo, transpose=True)
     dsrc, dsrc_amax = ops.conv3x3([dgb], pwT, None, passes=passes, want_amax=True, tag="dgrad_mod")
     del dgb
-    meta = st.meta
     dtab = dtb = dstyle = None
     coff = 0
     for src, kind in zip(st.srcs, meta['kinds']):
@@ -390,18 +409,22 @@ class SPADEResnetBlock(nn.Module):
         # SEAN layers at or below max_fm_size: the style branch runs as per-image weights over the
         # one-hot label planes (config.fold_style), rebuilt from the style matrix on every call
         fold = [n.folds_style(H, W) and ctx.style is not None for n in (self.norm_0, self.norm_1)]
+        # layers above max_fm_size: sub-pixel form (collapsed 2x2 filters over the half-resolution actv)
+        subp = [n.uses_subpixel(H, W) for n in (self.norm_0, self.norm_1)]
         Wm, gbs, bbs, pwm = [None, None], [None, None], [None, None], [None, None]
         for i, n in enumerate((self.norm_0, self.norm_1)):
-            if cached and not fold[i]:
+            if cached and not fold[i] and not subp[i]:
                 pwm[i], gbs[i], bbs[i] = n.prepared(lo1)
             elif cached:
                 Wm[i], gbs[i], bbs[i] = n.combined_cached()
             else:
                 Wm[i], gbs[i], bbs[i] = n.combined_weight()
         Ws = [None, None]
-        for i in range(2):
+        for i, n in enumerate((self.norm_0, self.norm_1)):
             if fold[i]:
                 Wm[i], Ws[i] = fold_style_weight(Wm[i], ctx.style)
+            elif subp[i]:
+                Wm[i] = ops.collapse_subpixel(Wm[i])
         (Wm0, Wm1), (gb0, gb1), (bb0, bb1) = Wm, gbs, bbs
         pre = None
         if cached:

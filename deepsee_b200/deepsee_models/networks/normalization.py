@@ -190,7 +190,15 @@ class _CondNormBase(nn.Module):
         return (self.kind == 'sean' and config.fold_style and config.save_gamma and
                 self.fm_size(H, W) == (H, W))
 
-    def build_sources(self, ctx, style, H, W, want_lo, table=None, bias=None, folded=False):
+    def uses_subpixel(self, H, W):
+        """True when this layer runs in the sub-pixel form (config.subpixel): its sources are
+        convolved through a 2x upsample (feature map above max_fm_size)."""
+        from ...config import config
+        fh, fw = self.fm_size(H, W)
+        return (config.subpixel and config.save_gamma and self.kind != 'spade' and
+                (fh * 2, fw * 2) == (H, W))
+
+    def build_sources(self, ctx, style, H, W, want_lo, table=None, bias=None, folded=False, sub=False):
         """-> (list of SplitPlanes feeding K1's A operand at resolution (H, W), meta). ``meta``
         records what each source is ('actv' = mlp_shared output, 'style' = gathered style matrix),
         the label map and the folded-upsample flag - what the backward pass needs."""
@@ -208,8 +216,10 @@ class _CondNormBase(nn.Module):
         if need_actv:
             if table is None:
                 table, bias = self.table_and_bias()
-            actv = ops.shared_mlp(labels, table.detach(), bias.detach(), ups=ups, want_lo=want_lo)
-        meta = {'labels': labels, 'ups': ups, 'actv': actv, 'fm': (fh, fw), 'ctx': ctx}
+            # sub-pixel form: the activation stays at the label map's resolution (K1 reads it through
+            # the collapsed 2x2 filters); otherwise the 2x upsample is materialised here
+            actv = ops.shared_mlp(labels, table.detach(), bias.detach(), ups=0 if sub else ups, want_lo=want_lo)
+        meta = {'labels': labels, 'ups': ups, 'actv': actv, 'fm': (fh, fw), 'ctx': ctx, 'sub': bool(sub)}
         if self.kind == 'spade':
             meta['kinds'] = ['actv']
             return [actv], meta

@@ -253,9 +253,13 @@ def split_f16(x, want_lo=True):
 _DTYPE_CODE = {torch.float16: 0, torch.bfloat16: 1}
 
 
-def _operands(sources, pw, passes):
+def _operands(sources, pw, passes, sub=None):
+    """sub: None, or (py, px) - the sources are at half resolution and this call computes one parity
+    class of the sub-pixel form with the class's rows of the collapsed weight (collapse_subpixel)."""
     a0 = sources[0]
     B, H, W, C0 = a0.hi.shape
+    if sub is not None:
+        H, W = 2 * H, 2 * W
     ops = _lib.ConvOperands()
     ops.B, ops.H, ops.W = B, H, W
     ctot = 0
@@ -264,7 +268,7 @@ def _operands(sources, pw, passes):
         if i < len(sources):
             s = sources[i]
             _chk_cuda(s.hi, s.lo)
-            assert s.hi.dtype == a0.hi.dtype and tuple(s.hi.shape[:3]) == (B, H, W)
+            assert s.hi.dtype == a0.hi.dtype and tuple(s.hi.shape[:3]) == tuple(a0.hi.shape[:3])
             ops.a_hi[i] = s.hi.data_ptr()
             ops.a_lo[i] = s.lo.data_ptr() if s.lo is not None else 0
             ops.a_channels[i] = s.hi.shape[3]
@@ -275,8 +279,14 @@ def _operands(sources, pw, passes):
             ops.a_lo[i] = 0
             ops.a_channels[i] = 0
     assert ctot == pw.cin, "weight prepared for %d input channels, operands have %d" % (pw.cin, ctot)
-    ops.w_hi = pw.hi.data_ptr()
-    ops.w_lo = pw.lo.data_ptr() if pw.lo is not None else 0
+    woff = 0
+    ops.a_sub = ops.sub_py = ops.sub_px = 0
+    if sub is not None:
+        ops.a_sub, ops.sub_py, ops.sub_px = 1, sub[0], sub[1]
+        assert pw.hi.shape[0] == 4 * pw.n_total, "sub-pixel form needs the 4-class collapsed weight"
+        woff = (sub[0] * 2 + sub[1]) * pw.n_total * pw.hi.shape[1] * 2   # bytes to the class's rows
+    ops.w_hi = pw.hi.data_ptr() + woff
+    ops.w_lo = pw.lo.data_ptr() + woff if pw.lo is not None else 0
     ops.w_inv_scale = pw.inv_scale.data_ptr()
     ops.n_total = pw.n_total
     ops.passes = passes
@@ -343,12 +353,52 @@ def conv3x3(sources, pw, bias, residual=None, res_ups=0, noises=(), passes=3, wa
     return (out, stats) if want_stats else out
 
 
+_SUBPIX_M = {}
+
+
+def subpixel_matrix(device):
+    """M[class, tap2x2, tap3x3] in {0, 1}: which taps of a 3x3 filter over a nearest-2x-upsampled
+    tensor land on the same half-resolution pixel, per output parity class (py, px) = divmod(class, 2)
+    and 2x2 tap (ty, tx) = divmod(tap2x2, 2): 3x3 tap (ky, kx) reads half-resolution row
+    (py + ky - 1) // 2 = ty + py - 1."""
+    m = _SUBPIX_M.get(device)
+    if m is None:
+        m = torch.zeros(4, 4, 9)
+        for py in range(2):
+            for px in range(2):
+                for ky in range(3):
+                    for kx in range(3):
+                        ty, tx = (py + ky - 1) // 2 - (py - 1), (px + kx - 1) // 2 - (px - 1)
+                        m[py * 2 + px, ty * 2 + tx, ky * 3 + kx] = 1.0
+        m = _SUBPIX_M[device] = m.to(device)
+    return m
+
+
+def collapse_subpixel(w):
+    """[N, C, 3, 3] -> [4, N, C, 2, 2]: the four 2x2 filters that, applied to a half-resolution tensor,
+    equal the 3x3 filter applied to its nearest 2x upsampling (one per output parity class).  A torch
+    einsum, so autograd turns the gradient of the collapsed filters back into the 3x3 gradient."""
+    N, Cc = w.shape[:2]
+    wc = torch.einsum('ncp,ktp->knct', w.reshape(N, Cc, 9), subpixel_matrix(w.device))
+    return wc.reshape(4, N, Cc, 2, 2)
+
+
+def prep_subpixel_weight(wc, want_lo=True):
+    """collapse_subpixel output [4, N, C, 2, 2] -> planes [4N, 4C] (one scale for the four classes)."""
+    _, N, Cc = wc.shape[:3]
+    pw = prep_conv_weight_ex(wc.reshape(4 * N, Cc, 2, 2).contiguous(), want_lo)
+    return PreparedWeight(pw.hi, pw.lo, pw.inv_scale, N, Cc)
+
+
 def spade_modulate(sources, pw, x, x_ups, bn_scale, bn_shift, gamma_bias, beta_bias, noise=None,
-                   noise_w=None, passes=3, want_lo=True, save_g=False, want_f8=False):
+                   noise_w=None, passes=3, want_lo=True, save_g=False, want_f8=False, subpixel=False):
     """K1: gamma/beta conv + batch-norm apply + modulation + LeakyReLU -> fp16 split planes.
     save_g: also return G = gamma + gamma_bias as split planes (what K1's backward multiplies by).
-    want_f8: also the e5m2 planes a passes == 2 main conv reads (fp8 correction GEMM)."""
-    ops, (B, H, W) = _operands(sources, pw, passes)
+    want_f8: also the e5m2 planes a passes == 2 main conv reads (fp8 correction GEMM).
+    subpixel: the sources are at HALF the output resolution (the reference convolves their nearest 2x
+    upsampling, normalization.py:188-190,275-277) and pw is prep_subpixel_weight's: four launches,
+    one per output parity class, 4/9 of the FLOPs."""
+    ops, (B, H, W) = _operands(sources, pw, passes, (0, 0) if subpixel else None)
     _chk_cuda(x, bn_scale, bn_shift, gamma_bias, beta_bias, noise, noise_w)
     Cc = x.shape[3]
     assert tuple(x.shape[:3]) == (B, H >> x_ups, W >> x_ups)
@@ -377,9 +427,16 @@ def spade_modulate(sources, pw, x, x_ups, bn_scale, bn_shift, gamma_bias, beta_b
               torch.empty((B, H, W, Cc), dtype=torch.uint8, device=dev))
     m.out8_lo = f8[0].data_ptr() if f8 is not None else 0
     m.out8_hi = f8[1].data_ptr() if f8 is not None else 0
-    flops = 2.0 * 9 * pw.cin * pw.n_total * B * H * W
-    _timed("modulate_%dx%d" % (H, W), flops,
-           lambda: _lib.check(_lib.load().dsee_spade_modulate_fwd(C.byref(ops), C.byref(m), _stream())))
+    flops = 2.0 * 9 * pw.cin * pw.n_total * B * H * W   # reference-equivalent (sub-pixel executes 4/9)
+
+    def launch():
+        if not subpixel:
+            _lib.check(_lib.load().dsee_spade_modulate_fwd(C.byref(ops), C.byref(m), _stream()))
+            return
+        for cls in range(4):
+            o2, _ = _operands(sources, pw, passes, divmod(cls, 2))
+            _lib.check(_lib.load().dsee_spade_modulate_fwd(C.byref(o2), C.byref(m), _stream()))
+    _timed("modulate_%dx%d" % (H, W), flops, launch)
     if save_g:
         return SplitPlanes(hi, lo, f8), SplitPlanes(ghi, glo)
     return SplitPlanes(hi, lo, f8)
@@ -538,6 +595,50 @@ def conv3x3_wgrad_per_image(dy, sources, passes=3):
         _p(dy.hi), _p(dy.lo), _p(getattr(dy, "inv_scale", None)), a_hi, a_lo, ach,
         _DTYPE_CODE[dy.hi.dtype], B, H, W, N, passes, _p(ws), _p(dw), _stream())))
     return dw
+
+
+def subpixel_wgrad(dy, sources, passes=3):
+    """Weight gradient of the sub-pixel form: dy GradPlanes [B,H,W,N] (full resolution), sources at
+    half resolution -> d(collapsed filters) [4, N, C0 + C1, 2, 2]."""
+    srcs = list(sources) + [None] * (2 - len(sources))
+    _chk_cuda(dy.hi, dy.lo, *[t for s_ in sources for t in (s_.hi, s_.lo)])
+    B, H, W, N = dy.hi.shape
+    chans = [s_.hi.shape[3] if s_ is not None else 0 for s_ in srcs]
+    ctot = sum(chans)
+    lib = _lib.load()
+    ws = torch.empty(lib.dsee_subpixel_wgrad_workspace_floats(B, H, W, N, ctot), dtype=torch.float32,
+                     device=dy.hi.device)
+    dwc = torch.empty((4, N, ctot, 2, 2), dtype=torch.float32, device=dy.hi.device)
+    a_hi = (C.c_void_p * 2)(*[(s_.hi.data_ptr() if s_ is not None else 0) for s_ in srcs])
+    a_lo = (C.c_void_p * 2)(*[(s_.lo.data_ptr() if s_ is not None and s_.lo is not None else 0) for s_ in srcs])
+    ach = (C.c_int * 2)(*chans)
+    flops = 2.0 * 9 * ctot * N * B * H * W
+
+    def launch():
+        for cls in range(4):
+            py, px = divmod(cls, 2)
+            _lib.check(lib.dsee_subpixel_wgrad(_p(dy.hi), _p(dy.lo), _p(getattr(dy, "inv_scale", None)), a_hi,
+                                               a_lo, ach, B, H, W, N, py, px, passes, _p(ws), _p(dwc[cls]),
+                                               _stream()))
+    _timed("wgrad_%dx%d" % (H, W), flops, launch)
+    return dwc
+
+
+def subpixel_dgrad(dy, wc, passes=3, want_lo=True):
+    """Gradient wrt the half-resolution sources of the sub-pixel form: dy GradPlanes [B,H,W,N], wc the
+    collapsed filters [4, N, C, 2, 2] -> (dsrc fp32 [B,H/2,W/2,C], device max|dsrc|)."""
+    _chk_cuda(dy.hi, dy.lo, wc)
+    B, H, W, N = dy.hi.shape
+    Cc = wc.shape[2]
+    # [C, N, class, tap]: one "16-tap" filter bank per source channel
+    pwt = prep_conv_weight_ex(wc.reshape(4, N, Cc, 4).permute(2, 1, 0, 3).contiguous(), want_lo)
+    out = torch.empty((B, H // 2, W // 2, Cc), dtype=torch.float32, device=dy.hi.device)
+    amax = torch.empty(1, dtype=torch.float32, device=dy.hi.device)
+    flops = 2.0 * 9 * Cc * N * B * H * W
+    _timed("dgrad_mod_%dx%d" % (H, W), flops, lambda: _lib.check(_lib.load().dsee_subpixel_dgrad(
+        _p(dy.hi), _p(dy.lo), _p(getattr(dy, "inv_scale", None)), _p(pwt.hi), _p(pwt.lo), _p(pwt.inv_scale),
+        B, H, W, N, Cc, passes, _p(out), _p(amax), _stream())))
+    return out, amax
 
 
 def spade_modulate_bwd(sources, pw_gamma, x, x_ups, bn_scale, bn_shift, gamma_bias, dt, dt_amax,

@@ -181,6 +181,16 @@ typedef struct {
      * [B * n_total][K] and image b reads rows b * w_batch_rows ... (the SEAN style branch folded into
      * per-image weights over the one-hot label planes, dsee_prep_mod_weight_batched) */
     int w_batch_rows;
+    /* Sub-pixel form of a 3x3 conv over a nearest-2x-upsampled tensor (normalization.py:188-190,
+     * 275-277: above max_fm_size the style branch convolves the upsampled mlp_shared activation):
+     * the A planes hold the tensor at HALF resolution [B, H/2, W/2, C] and this call computes the
+     * output pixels of one parity class (y % 2, x % 2) = (sub_py, sub_px) as a 2x2-tap conv over the
+     * half-resolution planes: 4/9 of the FLOPs, and the upsampled tensor is never built.  The weight
+     * planes are the class's collapsed filter [n_total][4 * C_total], k = (ty*2+tx)*C_total + c, with
+     *   wc[ty][tx] = sum of w[ky][kx] over the taps with floor((sub_py + ky - 1) / 2) == ty + (sub_py - 1)
+     * (likewise in x); H, W stay the OUTPUT size (even).  0 = ordinary 3x3 conv.
+     * dsee_spade_modulate_fwd only. */
+    int a_sub, sub_py, sub_px;
 } dsee_conv_operands;
 
 /* K2.  Replaces conv_0 / conv_1 of SPADEResnetBlock (architecture.py:34-35,98,122) plus what the
@@ -262,6 +272,24 @@ int dsee_conv3x3_wgrad2_per_image(const void* dy_hi, const void* dy_lo, const fl
                                   const void* const* a_hi, const void* const* a_lo, const int* a_channels,
                                   int dtype, int B, int H, int W, int n_total, int passes,
                                   float* workspace, float* dw, void* stream);
+
+/* Backward of the sub-pixel form (dsee_conv_operands.a_sub) for one parity class:
+ * dsee_subpixel_wgrad: dwc[n][c][ty][tx] = sum over the class's output pixels (2Y+py, 2X+px) of
+ *   dY[b,2Y+py,2X+px,n] * A[b, Y + ty + py - 1, X + tx + px - 1, c]   (A at half resolution, 1 or 2
+ *   channel-concatenated sources; dY planes at full resolution [B,H,W,n_total]); dwc fp32
+ *   [n_total][C_total][2][2]; workspace from dsee_subpixel_wgrad_workspace_floats.
+ * dsee_subpixel_dgrad: gradient wrt the half-resolution A, all four classes in one GEMM:
+ *   dA[b,Y,X,c] = sum_{class, tap, n} dY[b, 2(Y - ry) + py, 2(X - rx) + px, n] * wc[class][n][c][tap],
+ *   weights as planes [C][16 * n_total] from dsee_prep_conv_weight_ex on a [C][n_total][4][4] tensor
+ *   (KH index = class py*2+px, KW index = tap ty*2+tx); out fp32 [B,H/2,W/2,C]; optional amax_out. */
+int64_t dsee_subpixel_wgrad_workspace_floats(int B, int H, int W, int n_total, int c_total);
+int dsee_subpixel_wgrad(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale,
+                        const void* const* a_hi, const void* const* a_lo, const int* a_channels, int B,
+                        int H, int W, int n_total, int sub_py, int sub_px, int passes, float* workspace,
+                        float* dwc, void* stream);
+int dsee_subpixel_dgrad(const void* dy_hi, const void* dy_lo, const float* dy_inv_scale, const void* w_hi,
+                        const void* w_lo, const float* w_inv_scale, int B, int H, int W, int n_total,
+                        int C, int passes, float* out, float* amax_out, void* stream);
 
 /* Weight gradient of dsee_conv2d_tc: dY planes [B,Ho,Wo,n_total], activation planes
  * [B,Hi,Wi,Ci] (the forward input) -> dw fp32 [n_total][Cp][KH][KW], Cp = Ci rounded up to 64

@@ -49,7 +49,7 @@ def _run(graphs, steps, name, over):
     ("8x_independent_256x256", dict(ngf=8, nef=8, ndf=8, start_size=8, crop_size=64, load_size=64,
                                     add_noise=False, noisy_style_scale=0.0)),
     ("32x_guided_512x512", dict(ngf=8, nef=8, ndf=8, start_size=4, crop_size=128, load_size=512,
-                                max_fm_size=64)),
+                                max_fm_size=64, noisy_style_scale=0.0)),
 ])
 def test_graphed_training_equals_eager(name, over):
     steps = 9

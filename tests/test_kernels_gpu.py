@@ -313,6 +313,50 @@ def test_per_image_weights_and_wgrad(B, H, W):
     assert err < 1e-4, err
 
 
+@pytest.mark.parametrize("B,H,W,two", [(2, 32, 32, False), (1, 48, 80, True)])
+def test_subpixel_form_matches_the_upsampled_conv(B, H, W, two):
+    """Layers above max_fm_size (normalization.py:188-190,275-277): K1 over the half-resolution
+    activation with the collapsed 2x2 filters (config.subpixel) equals K1 over the materialised
+    nearest-2x upsample, and its two backward GEMMs equal autograd of conv(upsample(a), W)."""
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B + H + W)
+    C, nh = 128, 128
+    cin = nh * (2 if two else 1)
+    a_low = torch.randn(B, H // 2, W // 2, nh, generator=g).relu().cuda()
+    wm = (torch.randn(2 * C, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).cuda()
+    x = torch.randn(B, H // 2, W // 2, C, generator=g).cuda()       # read through the folded upsample too
+    one, zero = torch.ones(C).cuda(), torch.zeros(C).cuda()
+    pl_low = ops.split_f16(a_low)
+    a_up = a_low.repeat_interleave(2, 1).repeat_interleave(2, 2).contiguous()
+    pl_up = ops.split_f16(a_up)
+    srcs_up, srcs_low = ([pl_up, pl_up], [pl_low, pl_low]) if two else ([pl_up], [pl_low])
+    ref = ops.spade_modulate(srcs_up, ops.prep_conv_weight(wm), x, 1, one, zero, one, zero, passes=3)
+    wc = ops.collapse_subpixel(wm)
+    got = ops.spade_modulate(srcs_low, ops.prep_subpixel_weight(wc), x, 1, one, zero, one, zero, passes=3,
+                             subpixel=True)
+    rv = ref.hi.float() + ref.lo.float()
+    e = ((got.hi.float() + got.lo.float()) - rv).abs().max().item() / rv.abs().max().item()
+    print("sub-pixel vs upsampled K1 (3-pass) max-abs / max|ref| %.3e" % e)
+    assert e < 2e-5
+    # backward GEMMs vs autograd of conv(upsample(cat(sources)), W)
+    dy = torch.randn(B, H, W, 2 * C, generator=g).cuda() * 1e-2
+    gp, _ = ops.grad_prep(dy)
+    src = torch.cat([a_low] * (2 if two else 1), 3).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    w_ref = wm.clone().requires_grad_(True)
+    F.conv2d(F.interpolate(src, scale_factor=2, mode="nearest"), w_ref, padding=1).backward(dy.permute(0, 3, 1, 2))
+    dwc = ops.subpixel_wgrad(gp, srcs_low, passes=3)
+    wl = wm.clone().requires_grad_(True)          # chain rule through the collapse (what autograd does)
+    ops.collapse_subpixel(wl).backward(dwc)
+    err = (wl.grad - w_ref.grad).abs().max().item() / w_ref.grad.abs().max().item()
+    print("sub-pixel weight gradient rel err %.3e" % err)
+    assert err < 2e-4
+    dsrc, amax = ops.subpixel_dgrad(gp, wc, passes=3)
+    err = (dsrc.permute(0, 3, 1, 2) - src.grad).abs().max().item() / src.grad.abs().max().item()
+    print("sub-pixel source gradient rel err %.3e" % err)
+    assert err < 1e-4
+    assert abs(float(amax) - float(dsrc.abs().max())) <= 1e-6 * float(amax)
+
+
 def test_dgrad_leaky_relu_mask():
     from deepsee_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(5)
