@@ -61,6 +61,8 @@ class _Config:
     # discriminator, parameter-side kernels) are launch-bound otherwise.  Off in the library (eager
     # semantics, `.grad` readable after a step); bench.py turns it on.
     cuda_graphs = os.environ.get("DSEE_CUDA_GRAPHS", "0") == "1"
+    # DemoManager.run: replay the batch-1 generator forward as a CUDA graph (per input shape).
+    demo_graphs = os.environ.get("DSEE_DEMO_GRAPHS", "1") != "0"
     # SEAN layers: fold the style branch into per-image modulation weights over the exact one-hot
     # label planes (normalization.py:182-185,198-201: conv(style_map, W) = conv(onehot, W x style_b)),
     # so K1's K per tap drops from 256 to 192 channels, the backward-data GEMM of the modulation

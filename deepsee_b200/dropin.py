@@ -17,6 +17,7 @@ _ALIASES = {
     "managers.base_manager": "deepsee_b200.managers.base_manager",
     "managers.trainer_manager": "deepsee_b200.managers.trainer_manager",
     "managers.demo_manager": "deepsee_b200.managers.demo_manager",
+    "managers.inference_manager": "deepsee_b200.managers.inference_manager",
     "deepsee_models": "deepsee_b200.deepsee_models",
     "deepsee_models.sr_model": "deepsee_b200.deepsee_models.sr_model",
     "deepsee_models.networks": "deepsee_b200.deepsee_models.networks",
@@ -26,6 +27,7 @@ _ALIASES = {
     "deepsee_models.networks.encoder": "deepsee_b200.deepsee_models.networks.encoder",
     "deepsee_models.networks.discriminator": "deepsee_b200.deepsee_models.networks.discriminator",
     "deepsee_models.networks.loss": "deepsee_b200.deepsee_models.networks.loss",
+    "data": "deepsee_b200.data",
     "data.preprocessor": "deepsee_b200.data.preprocessor",
 }
 

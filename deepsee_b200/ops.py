@@ -380,7 +380,7 @@ def collapse_subpixel(w):
     einsum, so autograd turns the gradient of the collapsed filters back into the 3x3 gradient."""
     N, Cc = w.shape[:2]
     wc = torch.einsum('ncp,ktp->knct', w.reshape(N, Cc, 9), subpixel_matrix(w.device))
-    return wc.reshape(4, N, Cc, 2, 2)
+    return wc.contiguous().reshape(4, N, Cc, 2, 2)
 
 
 def prep_subpixel_weight(wc, want_lo=True):
@@ -627,7 +627,7 @@ def subpixel_wgrad(dy, sources, passes=3):
 def subpixel_dgrad(dy, wc, passes=3, want_lo=True):
     """Gradient wrt the half-resolution sources of the sub-pixel form: dy GradPlanes [B,H,W,N], wc the
     collapsed filters [4, N, C, 2, 2] -> (dsrc fp32 [B,H/2,W/2,C], device max|dsrc|)."""
-    _chk_cuda(dy.hi, dy.lo, wc)
+    _chk_cuda(dy.hi, dy.lo)
     B, H, W, N = dy.hi.shape
     Cc = wc.shape[2]
     # [C, N, class, tap]: one "16-tap" filter bank per source channel

@@ -317,3 +317,42 @@ def test_style_sweep_modes_vs_oracle(tmp_path):
     out = model(dict(data), "inference_interpolation")
     for b in range(2):
         assert (out["style"][b].cpu() - ref_styles[b]).abs().max().item() < 2e-5
+
+
+def test_demo_manager_run_graph_replay_equals_eager(tmp_path):
+    """DemoManager.run (demo.py:111-127): the CUDA-graphed batch-1 forward returns exactly what the
+    eager 'demo' mode returns, for changing inputs on the same graph; and it is faster."""
+    import time
+    from deepsee_b200.config import config
+    from deepsee_b200.managers.demo_manager import DemoManager
+    o = O.make_opt("8x_independent_256x256", ngf=8, start_size=8, crop_size=64, load_size=64)
+    ck = tmp_path / o.name
+    ck.mkdir()
+    torch.save({"model": O.make_generator_state(o, 0)}, str(ck / "latest_net_SR.pth"))
+    torch.save({"model": O.make_encoder_state(o, 1)}, str(ck / "latest_net_E.pth"))
+    mgr = DemoManager(_mk_opt(o, checkpoints_dir=str(tmp_path)))
+
+    def inputs(seed):
+        raw = O.synthetic_batch(o, 1, seed=seed)
+        d = O.preprocess(o, raw)
+        z = torch.rand(1, 19, 128, generator=torch.Generator().manual_seed(seed)) * 2 - 1
+        return {"image_lr": d["image_lr"], "semantics": raw["label"].clone(), "encoded_style": z}
+
+    outs = {}
+    for mode in (False, True):
+        config.demo_graphs = mode
+        try:
+            outs[mode] = [mgr.run(inputs(s))["fake_image"].clone() for s in (1, 2, 3, 4)]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                mgr.run(inputs(5))
+            torch.cuda.synchronize()
+            outs[(mode, "ms")] = (time.perf_counter() - t0) / 20 * 1e3
+        finally:
+            config.demo_graphs = True
+    for a, b in zip(outs[False], outs[True]):
+        assert torch.equal(a, b)
+    assert any(isinstance(v, tuple) for v in mgr._demo_graphs.values()), "no graph was captured"
+    print("DemoManager.run batch-1 latency (incl. input synthesis): eager %.2f ms, graph replay %.2f ms"
+          % (outs[(False, "ms")], outs[(True, "ms")]))
