@@ -72,6 +72,9 @@ struct alignas(64) ConvParams {
     CUtensorMap tmB8;
     int cb8;           // 128-channel blocks per fp8 plane (0 = no fp8 phase)
     int w_brows;       // per-image weights: row offset of image b is b * w_brows (0 = shared)
+    int m2;            // 1: a tile is 16 x 16 pixels = two 128-pixel halves sharing one <= 128-row weight
+                       // box (two MMAs per K step into TMEM columns [0,128) and [128,256)): narrow-N
+                       // GEMMs then move as few operand bytes per FLOP as the N = 256 tile
     uint32_t idesc8;
     int B, H, W;       // tile space: the output pixels this launch computes, per image
     int Hm, Wm;        // output tensor dims in memory; pixel (y,x) of the tile space lives at
@@ -140,7 +143,7 @@ __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& 
     mt /= p.tiles_w;
     int th = mt % p.tiles_h;
     b = mt / p.tiles_h;
-    h0 = th * TILE_H;
+    h0 = th * (TILE_H << p.m2);
     w0 = tw * TILE_W;
 }
 
@@ -245,9 +248,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                             const int s = it % STAGES;
                             const uint32_t ph = (it / STAGES) & 1;
                             mbar_wait(&empty_bar[s], ph ^ 1);
-                            mbar_expect_tx(&full_bar[s], A_BYTES + p.b_rows * BLOCK_K * 2);
+                            mbar_expect_tx(&full_bar[s], (A_BYTES << p.m2) + p.b_rows * BLOCK_K * 2);
                             uint8_t* sa = smem + s * STAGE_BYTES;
-                            uint8_t* sb = sa + A_BYTES;
+                            uint8_t* sb = sa + (A_BYTES << p.m2);
                             const int src = (cb >= p.cb0) ? 1 : 0;
                             const int cl = src ? cb - p.cb0 : cb;
                             tma_load_4d(&p.tmA[src * 2 + pa], &full_bar[s], sa, cl * BLOCK_K,
@@ -294,7 +297,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                    const uint32_t sb = sa + A_BYTES;
+                    const uint32_t sb = sa + (A_BYTES << p.m2);
                     const uint64_t da = umma_desc_sw128(sa, 1024);
                     const uint64_t db = umma_desc_sw128(sb, 1024);
                     if (kit < k16) {
@@ -302,6 +305,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         for (int k = 0; k < BLOCK_K / 16; ++k) {
                             // advance 16 elements (32 B) along K inside the swizzle atom: +2 (16 B units)
                             umma_f16(tmem_d, da + 2 * k, db + 2 * k, p.idesc, (kit | k) != 0);
+                        }
+                        if (p.m2) {  // second pixel half of the 16 x 16 tile: A rows 128..255, same weights
+                            const uint64_t da2 = umma_desc_sw128(sa + A_BYTES, 1024);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                umma_f16(tmem_d + 128, da2 + 2 * k, db + 2 * k, p.idesc, (kit | k) != 0);
                         }
                     } else {
 #pragma unroll
@@ -340,12 +349,19 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
             const int er = lane >> 3, ecq = lane & 7;  // transposed layout: pixel sub-row, channel quad
             if (EPI == EPI_CONV) {
                 const int n0 = nt * BLOCK_N;
+                const int h0t = h0;
                 const int Hr = p.H >> p.res_ups, Wr = p.W >> p.res_ups;
                 float tmax = 0.f;
 #pragma unroll 1
                 for (int ch = eh; ch < BLOCK_N / 32; ch += ESTEP) {
-                    const int n = n0 + ch * 32;
-                    if (n >= p.n_total) break;  // warp-uniform
+                    // m2: TMEM columns [0,128) hold the tile's upper 8 pixel rows, [128,256) the lower 8
+                    const int sub = p.m2 ? (ch >> 2) : 0;
+                    const int n = n0 + (p.m2 ? (ch & 3) : ch) * 32;
+                    if (n >= p.n_total) {  // warp-uniform
+                        if (p.m2) continue;
+                        break;
+                    }
+                    const int h0 = h0t + sub * TILE_H;
                     {
                         uint32_t v[32];
                         tmem_ld32(taddr + ch * 32, v);
@@ -784,7 +800,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
 // host side
 // ------------------------------------------------------------------------------------------------
 static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_f8 = false,
-                       bool allow_sub = false) {
+                       bool allow_sub = false, bool m2 = false) {
     DSEE_CHECK_ARG(ops != nullptr, "conv operands are NULL");
     DSEE_CHECK_ARG(ops->B > 0 && ops->H > 0 && ops->W > 0, "bad geometry B=%d H=%d W=%d", ops->B,
                    ops->H, ops->W);
@@ -831,8 +847,9 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
                    "per-image weights need n_total to be a multiple of %d", BLOCK_N);
     p.w_brows = ops->w_batch_rows;
     p.noise_epoch = noise_epoch_ptr();
+    p.m2 = m2 ? 1 : 0;
     p.tiles_w = (ops->W + TILE_W - 1) / TILE_W;
-    p.tiles_h = (ops->H + TILE_H - 1) / TILE_H;
+    p.tiles_h = (ops->H + (TILE_H << p.m2) - 1) / (TILE_H << p.m2);
     p.n_tiles = (ops->n_total + BLOCK_N - 1) / BLOCK_N;
     p.num_tiles = p.B * p.tiles_h * p.tiles_w * p.n_tiles;
     p.cb0 = ops->a_channels[0] / BLOCK_K;
@@ -883,7 +900,7 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
             }
             uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wa, (uint64_t)Ha, (uint64_t)ops->B};
             uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)Wa * C * 2, (uint64_t)Ha * Wa * C * 2};
-            uint32_t box[4] = {BLOCK_K, TILE_W, TILE_H, 1};
+            uint32_t box[4] = {BLOCK_K, TILE_W, (uint32_t)(TILE_H << p.m2), 1};
             rc = encode_tmap_16b(&p.tmA[src * 2 + pl], base, 4, dims, strides, box, ops->a_dtype == 1);
             if (rc) return rc;
         }
@@ -956,9 +973,12 @@ extern "C" int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_e
                                 void* stream) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
-    int rc = fill_common(p, ops, true);
-    if (rc) return rc;
     DSEE_CHECK_ARG(epi && epi->out, "epilogue/out is NULL");
+    // narrow outputs (the modulation's backward-data GEMM, N = 128): 16 x 16-pixel tiles
+    const bool m2 = ops && ops->n_total <= 128 && !epi->stats_partial && ops->passes != 2 &&
+                    ops->w_batch_rows == 0;
+    int rc = fill_common(p, ops, true, false, m2);
+    if (rc) return rc;
     DSEE_CHECK_ARG(epi->res_ups == 0 || epi->res_ups == 1, "res_ups must be 0 or 1");
     DSEE_CHECK_ARG(!epi->residual || epi->res_ups == 0 || (ops->H % 2 == 0 && ops->W % 2 == 0),
                    "folded upsample needs even H, W");
@@ -1015,6 +1035,7 @@ extern "C" int dsee_conv2d_tc(const dsee_conv2d_tc_args* a, const dsee_conv_epil
     base.a_inv_scale = a->a_inv_scale;
     base.b_rows = round_up(a->n_total < BLOCK_N ? a->n_total : BLOCK_N, 16);
     base.idesc = (1u << 4) | ((uint32_t)(base.b_rows >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    base.m2 = a->n_total <= 128 ? 1 : 0;   // narrow layers (32 ... 128 output channels): 16 x 16-pixel tiles
     base.n_tiles = (a->n_total + BLOCK_N - 1) / BLOCK_N;
     base.bias = epi->bias;
     base.out = epi->out;
@@ -1029,7 +1050,7 @@ extern "C" int dsee_conv2d_tc(const dsee_conv2d_tc_args* a, const dsee_conv_epil
             uint64_t dims[4] = {(uint64_t)a->Ci, (uint64_t)a->Wi, (uint64_t)a->Hi, (uint64_t)a->B};
             uint64_t strides[3] = {(uint64_t)a->Ci * 2, (uint64_t)a->Wi * a->Ci * 2,
                                    (uint64_t)a->Hi * a->Wi * a->Ci * 2};
-            uint32_t box[4] = {BLOCK_K, (uint32_t)(TILE_W * a_step), (uint32_t)(TILE_H * a_step), 1};
+            uint32_t box[4] = {BLOCK_K, (uint32_t)(TILE_W * a_step), (uint32_t)((TILE_H << base.m2) * a_step), 1};
             uint32_t es[4] = {1, (uint32_t)a_step, (uint32_t)a_step, 1};
             rc = encode_tmap_16b(&base.tmA[pl], ab, 4, dims, strides, box, false, es);
             if (rc) return rc;
@@ -1088,7 +1109,7 @@ extern "C" int dsee_conv2d_tc(const dsee_conv2d_tc_args* a, const dsee_conv_epil
             if (p.H <= 0 || p.W <= 0) continue;
             DSEE_CHECK_ARG(nt > 0, "a parity class of the transposed conv has no taps (kernel < stride)");
             p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
-            p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
+            p.tiles_h = (p.H + (TILE_H << p.m2) - 1) / (TILE_H << p.m2);
             p.num_tiles = p.B * p.tiles_h * p.tiles_w * p.n_tiles;
             rc = launch<EPI_CONV>(p, (cudaStream_t)stream);
             if (rc) return rc;
@@ -1132,8 +1153,9 @@ extern "C" int dsee_subpixel_dgrad(const void* dy_hi, const void* dy_lo, const f
     p.b_rows = round_up(C < BLOCK_N ? C : BLOCK_N, 16);
     p.idesc = (1u << 4) | ((uint32_t)(p.b_rows >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
     p.n_tiles = (C + BLOCK_N - 1) / BLOCK_N;
+    p.m2 = C <= 128 ? 1 : 0;
     p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
-    p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
+    p.tiles_h = (p.H + (TILE_H << p.m2) - 1) / (TILE_H << p.m2);
     p.num_tiles = p.B * p.tiles_h * p.tiles_w * p.n_tiles;
     p.out = out;
     p.amax_out = amax_out;
@@ -1143,7 +1165,7 @@ extern "C" int dsee_subpixel_dgrad(const void* dy_hi, const void* dy_lo, const f
         if (ab) {
             uint64_t dims[4] = {(uint64_t)n_total, (uint64_t)W, (uint64_t)H, (uint64_t)B};
             uint64_t strides[3] = {(uint64_t)n_total * 2, (uint64_t)W * n_total * 2, (uint64_t)H * W * n_total * 2};
-            uint32_t box[4] = {BLOCK_K, (uint32_t)(TILE_W * 2), (uint32_t)(TILE_H * 2), 1};
+            uint32_t box[4] = {BLOCK_K, (uint32_t)(TILE_W * 2), (uint32_t)((TILE_H << p.m2) * 2), 1};
             uint32_t es[4] = {1, 2, 2, 1};
             rc = encode_tmap_16b(&p.tmA[pl], ab, 4, dims, strides, box, false, es);
             if (rc) return rc;

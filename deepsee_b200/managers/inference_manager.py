@@ -18,7 +18,7 @@ def frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
     """evaluator/pytorch_fid/fid_score.py:calculate_frechet_distance."""
     from scipy import linalg
     diff = mu1 - mu2
-    covmean, _ = linalg.sqrtm(sigma1.dot(sigma2), disp=False)
+    covmean = linalg.sqrtm(sigma1.dot(sigma2))
     if not np.isfinite(covmean).all():
         offset = np.eye(sigma1.shape[0]) * eps
         covmean = linalg.sqrtm((sigma1 + offset).dot(sigma2 + offset))
