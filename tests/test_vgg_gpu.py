@@ -33,8 +33,9 @@ def test_vgg19_features_loss_and_gradient_vs_oracle():
         assert err < 5e-4
     loss = crit(xg, y.cuda())
     loss.backward()
-    print("VGG loss ours %.6f oracle %.6f" % (float(loss), float(ref_loss)))
-    assert abs(float(loss) - float(ref_loss)) < 1e-5 * max(1.0, abs(float(ref_loss)))
+    print("VGG loss ours %.6f oracle %.6f" % (float(loss.detach()), float(ref_loss.detach())))
+    # a mean of |feature differences|: inherits the features' ~1e-4 relative accuracy
+    assert abs(float(loss.detach()) - float(ref_loss.detach())) < 2e-4 * abs(float(ref_loss.detach()))
     gerr = (xg.grad.cpu() - x.grad).abs().max().item() / x.grad.abs().max().item()
     print("d loss / d fake image: max-abs / max|ref| %.2e" % gerr)
     assert gerr < 5e-3    # ReLU / max-pool / L1 kinks: a 1e-6 forward difference flips isolated elements
