@@ -263,6 +263,7 @@ def ddp_parity_leg(world, rank, local):
                "loss_rel_diff": max(abs(loss_ddp[k] - loss_ref[k]) / max(1.0, abs(loss_ref[k])) for k in loss_ref),
                "grad_max_rel_diff": worst, "grad_worst": worst_name, "grad_tensors": len(g_ref),
                "grads_only_where_single_process_has_them": set(g_ddp) == set(g_ref),
+               "sync_bn_over_peer_memory": parallel.peer_exchange_active(),
                "bn_running_var_rel_diff": float((rs_ddp - rs_ref).abs().max() / rs_ref.abs().max()),
                "what": "1 training iteration, %d ranks x %d samples (NCCL gradient buckets%s) vs 1 process x %d "
                        "samples, passes=3" % (world, per, " + Sync-BN" if config.sync_bn_for("syncbatch") else "",

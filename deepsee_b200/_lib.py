@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("DSEE_LIB_PATH") or os.path.join(_HERE, "lib", "libdee
 # every symbol include/deepsee_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "dsee_version", "dsee_last_error", "dsee_launch_count",
-    "dsee_labels_u8", "dsee_bicubic_clamp", "dsee_maxpool2_fwd", "dsee_maxpool2_bwd", "dsee_noise_fill", "dsee_noise_epoch_advance", "dsee_noise_epoch_set", "dsee_onehot_from_labels", "dsee_labels_from_onehot", "dsee_resize_labels",
+    "dsee_peer_exchange_bytes", "dsee_peer_allreduce_small", "dsee_labels_u8", "dsee_bicubic_clamp", "dsee_maxpool2_fwd", "dsee_maxpool2_bwd", "dsee_noise_fill", "dsee_noise_epoch_advance", "dsee_noise_epoch_set", "dsee_onehot_from_labels", "dsee_labels_from_onehot", "dsee_resize_labels",
     "dsee_shared_mlp_fwd", "dsee_style_gather_fwd",
     "dsee_prep_conv_weight", "dsee_prep_conv_weight_f8", "dsee_prep_mod_weight_batched", "dsee_split_f16",
     "dsee_conv3x3_wgrad_per_image_workspace_floats", "dsee_conv3x3_wgrad2_per_image",
@@ -176,6 +176,7 @@ def load():
         "dsee_noise_fill": [u64, vp, i64, vp],
         "dsee_noise_epoch_advance": [vp],
         "dsee_labels_u8": [vp, vp, i64, i, vp, vp],
+        "dsee_peer_allreduce_small": [C.POINTER(vp), i, i, i, i, vp, vp, i, vp],
         "dsee_maxpool2_fwd": [vp, vp, i, i, i, i, vp],
         "dsee_maxpool2_bwd": [vp, vp, vp, i, i, i, i, vp],
         "dsee_bicubic_clamp": [vp, vp, i, i, i, i, i, i, vp],
@@ -234,6 +235,8 @@ def load():
     lib.dsee_conv3x3_wgrad_per_image_workspace_floats.restype = C.c_int64
     lib.dsee_subpixel_wgrad_workspace_floats.argtypes = [i, i, i, i, i]
     lib.dsee_subpixel_wgrad_workspace_floats.restype = C.c_int64
+    lib.dsee_peer_exchange_bytes.argtypes = [i, i, i]
+    lib.dsee_peer_exchange_bytes.restype = C.c_int64
     lib.dsee_spectral_workspace_floats.argtypes = [i, i]
     lib.dsee_spectral_workspace_floats.restype = C.c_int64
     lib.dsee_modweight_bwd_workspace_bytes.argtypes = [i, i, i]

@@ -100,6 +100,10 @@ class _Config:
     # DSEE_SYNC_BN=1: always synchronise.
     sync_bn = {"0": False, "1": True}.get(os.environ.get("DSEE_SYNC_BN", "auto"), "auto")
 
+    # Sync-BN statistics over NVLink peer memory (one library kernel per exchange, parallel._PeerExchange)
+    # instead of an NCCL all-reduce per norm layer; 0 = NCCL.
+    peer_sync_bn = os.environ.get("DSEE_PEER_SYNC_BN", "1") != "0"
+
     def sync_bn_for(self, norm_G):
         """Whether the conditional-norm layers of a generator with this norm_G string exchange their
         batch statistics across ranks (the caller still checks that a process group exists)."""

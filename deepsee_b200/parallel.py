@@ -64,10 +64,79 @@ def init_from_env(backend=None):
     dist.init_process_group(backend=backend, init_method="env://", **kw)
 
 
+class _PeerExchange:
+    """Sum of small fp32 vectors across the GPUs of this node through NVLink peer memory: one kernel
+    of the library per exchange (csrc/peer_kernels.cu) instead of an NCCL launch.  The symmetric
+    buffer comes from torch.distributed._symmetric_memory (CUDA virtual-memory handles exchanged
+    through the process group's store)."""
+    RING, MAXN = 4, 4096
+
+    def __init__(self):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.lib = _lib.load()
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        nbytes = int(self.lib.dsee_peer_exchange_bytes(self.world, self.RING, self.MAXN))
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, dist.group.WORLD)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        assert len(ptrs) == self.world and all(ptrs)
+        self.ptrs = (C.c_void_p * self.world)(*ptrs)
+        torch.cuda.synchronize()
+        dist.barrier()     # every rank's buffer is zeroed before anyone pushes
+
+    def allreduce_sum_(self, t):
+        import ctypes as C
+        from . import _lib, ops
+        stream = ops._stream()
+        _lib.check(self.lib.dsee_peer_allreduce_small(self.ptrs, self.world, self.rank, self.RING, self.MAXN,
+                                                      C.c_void_p(t.data_ptr()), C.c_void_p(t.data_ptr()),
+                                                      t.numel(), stream))
+        return t
+
+
+_PEER = {"obj": None, "failed": False}
+
+
+def _peer_exchange():
+    """The node-local peer-memory exchange, or None (disabled, not NCCL, more than 8 ranks, or
+    symmetric memory unavailable: then the statistics go through NCCL like the gradients)."""
+    from .config import config
+    if not config.peer_sync_bn or _PEER["failed"]:
+        return None
+    if _PEER["obj"] is None:
+        try:
+            if dist.get_backend() != "nccl" or dist.get_world_size() > 8:
+                raise RuntimeError("needs the nccl backend and at most 8 ranks on one node")
+            _PEER["obj"] = _PeerExchange()
+        except Exception as e:  # noqa: BLE001
+            import sys
+            print("deepsee_b200: peer-memory statistics exchange unavailable (%r); using NCCL" % (e,),
+                  file=sys.stderr)
+            _PEER["failed"] = True
+            return None
+    return _PEER["obj"]
+
+
+def peer_exchange_active():
+    """True once the NVLink peer-memory exchange has been set up in this process."""
+    return _PEER["obj"] is not None
+
+
 def allreduce_sum_(t):
-    """In-place sum over ranks of a small statistics tensor (Sync-BN mode); identity for one rank."""
+    """In-place sum over ranks of a small statistics tensor (Sync-BN mode); identity for one rank.
+    fp32 CUDA vectors of up to 4096 elements go through the NVLink peer-memory kernel, everything
+    else (and the gloo tests) through the process group."""
     if is_dist():
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        px = None
+        if t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= _PeerExchange.MAXN:
+            px = _peer_exchange()
+        if px is not None:
+            px.allreduce_sum_(t)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
 
 

@@ -98,6 +98,17 @@ int dsee_maxpool2_fwd(const float* in, float* out, int B, int Hi, int Wi, int C,
 int dsee_maxpool2_bwd(const float* in, const float* dout, float* din, int B, int Hi, int Wi, int C,
                       void* stream);
 
+/* Sync-BN statistics exchange over NVLink peer memory (replaces the reference's master/slave pipes,
+ * sync_batchnorm/batchnorm.py:80-93 + comm.py): all-reduce(sum) of a vector of n <= maxn floats
+ * across the `world` GPUs of one node in ONE kernel - push my vector into every peer's slot, release
+ * a sequence flag, acquire-wait for all peers, sum in rank order from local memory.  peer_bufs[r] is
+ * rank r's symmetric allocation (dsee_peer_exchange_bytes(world, ring, maxn) bytes, zero-initialised,
+ * e.g. torch.distributed._symmetric_memory) as mapped in this process.  Every rank must issue the
+ * same sequence of calls.  in == out is allowed.  Capturable in a CUDA graph. */
+int64_t dsee_peer_exchange_bytes(int world, int ring, int maxn);
+int dsee_peer_allreduce_small(const void* const* peer_bufs, int world, int rank, int ring, int maxn,
+                              const float* in, float* out, int n, void* stream);
+
 /* Noise epoch: a per-device 64-bit counter that every kernel regenerating NoiseInjection noise
  * from a seed folds into that seed.  Advancing it (a one-thread kernel on `stream`) makes launches
  * whose seeds are baked into a captured CUDA graph draw fresh noise on every replay; forward and

@@ -62,6 +62,7 @@ def main():
             t /= world
         res["loss_" + k] = t.cpu()
     res["gradD"] = next(p for n, p in m.netD.named_parameters() if p.grad is not None).grad.detach().cpu().clone()
+    res["peer_exchange"] = torch.tensor([1.0 if parallel.peer_exchange_active() else 0.0])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -35,6 +35,8 @@ def test_two_rank_sync_bn_matches_single_process(tmp_path):
     two = _run(tmp_path, 2, True, "two")
     assert set(one) == set(two)
     assert any(k.startswith("grad_") for k in one)
+    # the Sync-BN statistics went through the NVLink peer-memory kernel, not an NCCL fallback
+    assert float(two.pop("peer_exchange")) == 1.0 and float(one.pop("peer_exchange")) == 0.0
     for k in sorted(one):
         a, b = one[k], two[k]
         scale = float(a.abs().max()) + 1e-12
@@ -50,5 +52,6 @@ def test_two_rank_local_bn_runs(tmp_path):
     """Default mode (per-rank BN statistics, gradient all-reduce only): runs and produces finite,
     rank-averaged results."""
     two = _run(tmp_path, 2, False, "two_local")
+    assert float(two.pop("peer_exchange")) == 0.0
     for k, v in two.items():
         assert torch.isfinite(v).all(), k
