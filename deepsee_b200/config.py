@@ -100,6 +100,9 @@ class _Config:
     # DSEE_SYNC_BN=1: always synchronise.
     sync_bn = {"0": False, "1": True}.get(os.environ.get("DSEE_SYNC_BN", "auto"), "auto")
 
+    # Gradient buckets: launch each chunk's all-reduce from the backward pass as soon as its last
+    # gradient has landed (1), or all chunks after the backward pass (0).
+    grad_overlap = os.environ.get("DSEE_GRAD_OVERLAP", "1") != "0"
     # Sync-BN statistics over NVLink peer memory (one library kernel per exchange, parallel._PeerExchange)
     # instead of an NCCL all-reduce per norm layer; 0 = NCCL.
     peer_sync_bn = os.environ.get("DSEE_PEER_SYNC_BN", "1") != "0"

@@ -201,6 +201,8 @@ class GradBucket:
                 lo, cnt = end, 0
         self._active = False
         self._pending, self._touched, self._works, self._launched = [], [], [], []
+        from .config import config
+        self._overlap = config.grad_overlap
         for i, p in enumerate(self.params):
             p.register_post_accumulate_grad_hook(self._make_hook(i))
 
@@ -215,7 +217,7 @@ class GradBucket:
                 self._touched[i] = True
                 c = self.chunk_of[i]
                 self._pending[c] -= 1
-                if self._pending[c] == 0:
+                if self._pending[c] == 0 and self._overlap:
                     self._launch(c)
         return hook
 
