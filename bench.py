@@ -467,6 +467,29 @@ def main():
             pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(70)
             pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(45)
             open(args.cprofile, "w").write(buf.getvalue())
+        isolated = None
+        if headline and world > 1 and train:
+            # every rank alone: the same eager step with the process group ignored (no gradient
+            # exchange, per-rank BN statistics).  The job runs at the pace of its slowest GPU, so the
+            # spread of these times bounds what data parallelism can reach on this box.
+            was = config.cuda_graphs
+            config.cuda_graphs = False
+            try:
+                with parallel.local_mode():
+                    iteration(dev)
+                    torch.cuda.synchronize()
+                    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    l0.record()
+                    for _ in range(4):
+                        iteration(dev)
+                    l1.record()
+                    torch.cuda.synchronize()
+                mine = torch.tensor([l0.elapsed_time(l1) / 4], device="cuda", dtype=torch.float64)
+            finally:
+                config.cuda_graphs = was
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            isolated = [round(float(t.item()), 2) for t in allr]
         e2e = None
         if not args.no_e2e:
             for _ in range(2):
@@ -490,6 +513,7 @@ def main():
         value = b * world * steps / (ms / 1000.0)
         flops_per_img = cfg["train_flops"] if train else cfg["fwd_flops"]
         return dict(cfg=cfg, b=b, S=S, steps=steps, ms=ms, value=value, ksum=ksum, launches=launches,
+                    isolated=isolated,
                     graphed=graphed, roof_ms=roof_ms, roof_steps=roof_steps,
                     clocks=clocks, e2e=e2e, peak_mem=peak_mem, sync_bn=sync_bn,
                     whole_step={"algorithmic_tflops_per_gpu": value / world * flops_per_img / 1e12,
@@ -599,6 +623,8 @@ def main():
         line["configs"] = extras
     if ddp_parity is not None:
         line["ddp_parity"] = ddp_parity
+    if R["isolated"] is not None:
+        line["rank_isolated_eager_ms_per_step"] = R["isolated"]
     if not args.no_cpu_baseline and train and world == 1:
         cores = os.cpu_count()
         step = cpu_train_iteration_timer(cfg, cores)

@@ -72,6 +72,8 @@ struct alignas(64) ConvParams {
     CUtensorMap tmB8;
     int cb8;           // 128-channel blocks per fp8 plane (0 = no fp8 phase)
     int w_brows;       // per-image weights: row offset of image b is b * w_brows (0 = shared)
+    int sub4;          // 1: sub-pixel form, all four parity classes in this launch: the class is a tile
+                       // index (fastest after the N tile), taps [cls*4, cls*4+4), weight rows + cls*n_total
     int m2;            // 1: a tile is 16 x 16 pixels = two 128-pixel halves sharing one <= 128-row weight
                        // box (two MMAs per K step into TMEM columns [0,128) and [128,256)): narrow-N
                        // GEMMs then move as few operand bytes per FLOP as the N = 256 tile
@@ -136,9 +138,14 @@ struct alignas(64) ConvParams {
 };
 
 __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& b, int& h0, int& w0,
-                                            int& nt) {
+                                            int& nt, int& cls) {
     nt = tile % p.n_tiles;
     int mt = tile / p.n_tiles;
+    cls = 0;
+    if (p.sub4) {  // the four classes of one pixel tile run back to back: x and the sources stay in L2
+        cls = mt & 3;
+        mt >>= 2;
+    }
     int tw = mt % p.tiles_w;
     mt /= p.tiles_w;
     int th = mt % p.tiles_h;
@@ -236,14 +243,14 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                int b, h0, w0, nt;
-                decode_tile(p, tile, b, h0, w0, nt);
-                const int n0 = nt * BLOCK_N;
+                int b, h0, w0, nt, cls;
+                decode_tile(p, tile, b, h0, w0, nt, cls);
+                const int n0 = nt * BLOCK_N + cls * p.n_total;   // (cls != 0 only in the sub4 form)
                 for (int pass = 0; pass < p.passes; ++pass) {
                     const int pa = (pass == 1) ? 1 : 0;
                     const int pb = (pass == 2) ? 1 : 0;
                     for (int tap = 0; tap < p.ntaps; ++tap) {
-                        const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
+                        const int dy = p.tap_dy[cls * 4 + tap], dx = p.tap_dx[cls * 4 + tap];
                         for (int cb = 0; cb < p.cb_total; ++cb, ++it) {
                             const int s = it % STAGES;
                             const uint32_t ph = (it / STAGES) & 1;
@@ -337,8 +344,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
             const int as = lt & 1;
             const uint32_t aph = (lt >> 1) & 1;
-            int b, h0, w0, nt;
-            decode_tile(p, tile, b, h0, w0, nt);
+            int b, h0, w0, nt, cls;
+            decode_tile(p, tile, b, h0, w0, nt, cls);
             const int y = h0 + ly, x = w0 + lx;
             const bool valid = (y < p.H) && (x < p.W);
             mbar_wait(&tfull_bar[as], aph);
@@ -682,6 +689,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                 // tile pixel (yy, xx) lives at (yy * o_step + o_offy, xx * o_step + o_offx) of the [Hm, Wm]
                 // output (o_step = 2: one parity class of the sub-pixel form; 1 otherwise)
                 const int Hx = p.Hm >> p.x_ups, Wx = p.Wm >> p.x_ups;
+                const int ooy = p.sub4 ? (cls >> 1) : p.o_offy, oox = p.sub4 ? (cls & 1) : p.o_offx;
                 const bool has_noise = p.noise_w != nullptr;
 #pragma unroll 1
                 for (int ch = eh; ch < 4; ch += ESTEP) {
@@ -721,7 +729,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         const int yy = h0 + mm / TILE_W, xx = w0 + mm % TILE_W;
                         xq[st] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (yy < p.H && xx < p.W) {
-                            const int fy = yy * p.o_step + p.o_offy, fx = xx * p.o_step + p.o_offx;
+                            const int fy = yy * p.o_step + ooy, fx = xx * p.o_step + oox;
                             const size_t xp = ((size_t)b * Hx + (fy >> p.x_ups)) * Wx + (fx >> p.x_ups);
                             xq[st] = __ldg(reinterpret_cast<const float4*>(p.x + xp * p.C + cc));
                         }
@@ -732,8 +740,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         const int mm = q * 32 + pi;
                         const int yy = h0 + mm / TILE_W, xx = w0 + mm % TILE_W;
                         if (yy >= p.H || xx >= p.W) continue;
-                        const size_t pix = ((size_t)b * p.Hm + (yy * p.o_step + p.o_offy)) * p.Wm +
-                                           (xx * p.o_step + p.o_offx);
+                        const size_t pix = ((size_t)b * p.Hm + (yy * p.o_step + ooy)) * p.Wm + (xx * p.o_step + oox);
                         const size_t pe = pix * p.C + cc;
                         float4 xv = xq[st];
                         if (has_noise) {
@@ -868,25 +875,31 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
     const int sub = ops->a_sub ? 1 : 0;
     if (sub) {
         DSEE_CHECK_ARG(allow_sub, "a_sub (sub-pixel form) is implemented for dsee_spade_modulate_fwd only");
-        DSEE_CHECK_ARG(ops->H % 2 == 0 && ops->W % 2 == 0 && (ops->sub_py | 1) == 1 && (ops->sub_px | 1) == 1 &&
-                           ops->passes != 2,
-                       "sub-pixel form needs even H, W, a parity class in {0,1}^2 and passes 1 or 3");
+        const bool all4 = ops->sub_py < 0;
+        DSEE_CHECK_ARG(ops->H % 2 == 0 && ops->W % 2 == 0 &&
+                           (all4 || ((ops->sub_py | 1) == 1 && (ops->sub_px | 1) == 1)) && ops->passes != 2,
+                       "sub-pixel form needs even H, W, a parity class in {0,1}^2 (or sub_py < 0 = all "
+                       "four in one launch) and passes 1 or 3");
         // tile space = the class's output pixels = the half-resolution grid
         p.H = ops->H / 2;
         p.W = ops->W / 2;
         p.o_step = 2;
-        p.o_offy = ops->sub_py;
-        p.o_offx = ops->sub_px;
+        p.o_offy = all4 ? 0 : ops->sub_py;
+        p.o_offx = all4 ? 0 : ops->sub_px;
+        p.sub4 = all4 ? 1 : 0;
         p.ntaps = 4;
         const int ctot = ops->a_channels[0] + ops->a_channels[1];
-        for (int t = 0; t < 4; ++t) {
-            p.tap_dy[t] = (int8_t)(t / 2 + ops->sub_py - 1);
-            p.tap_dx[t] = (int8_t)(t % 2 + ops->sub_px - 1);
-            p.tap_k[t] = t * ctot;
+        for (int c = 0; c < (all4 ? 4 : 1); ++c) {
+            const int py = all4 ? (c >> 1) : ops->sub_py, px = all4 ? (c & 1) : ops->sub_px;
+            for (int t = 0; t < 4; ++t) {
+                p.tap_dy[c * 4 + t] = (int8_t)(t / 2 + py - 1);
+                p.tap_dx[c * 4 + t] = (int8_t)(t % 2 + px - 1);
+                p.tap_k[c * 4 + t] = t * ctot;
+            }
         }
         p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
         p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
-        p.num_tiles = p.B * p.tiles_h * p.tiles_w * p.n_tiles;
+        p.num_tiles = p.B * p.tiles_h * p.tiles_w * p.n_tiles * (all4 ? 4 : 1);
     }
     const int Ha = ops->H >> sub, Wa = ops->W >> sub;   // resolution of the A planes
     for (int src = 0; src < 2; ++src) {
@@ -933,7 +946,7 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
             p.tmB[pl] = p.tmB[0];
             continue;
         }
-        uint64_t dims[2] = {Ktot, (uint64_t)ops->n_total * (ops->w_batch_rows ? ops->B : 1)};
+        uint64_t dims[2] = {Ktot, (uint64_t)ops->n_total * (ops->w_batch_rows ? ops->B : 1) * (p.sub4 ? 4 : 1)};
         uint64_t strides[1] = {Ktot * 2};
         uint32_t box[2] = {BLOCK_K, (uint32_t)p.b_rows};
         rc = encode_tmap_16b(&p.tmB[pl], base, 2, dims, strides, box, ops->w_dtype == 1);

@@ -284,7 +284,8 @@ def _operands(sources, pw, passes, sub=None):
     if sub is not None:
         ops.a_sub, ops.sub_py, ops.sub_px = 1, sub[0], sub[1]
         assert pw.hi.shape[0] == 4 * pw.n_total, "sub-pixel form needs the 4-class collapsed weight"
-        woff = (sub[0] * 2 + sub[1]) * pw.n_total * pw.hi.shape[1] * 2   # bytes to the class's rows
+        if sub[0] >= 0:   # one class per launch; (-1, -1) = all four classes in one launch
+            woff = (sub[0] * 2 + sub[1]) * pw.n_total * pw.hi.shape[1] * 2   # bytes to the class's rows
     ops.w_hi = pw.hi.data_ptr() + woff
     ops.w_lo = pw.lo.data_ptr() + woff if pw.lo is not None else 0
     ops.w_inv_scale = pw.inv_scale.data_ptr()
@@ -396,9 +397,10 @@ def spade_modulate(sources, pw, x, x_ups, bn_scale, bn_shift, gamma_bias, beta_b
     save_g: also return G = gamma + gamma_bias as split planes (what K1's backward multiplies by).
     want_f8: also the e5m2 planes a passes == 2 main conv reads (fp8 correction GEMM).
     subpixel: the sources are at HALF the output resolution (the reference convolves their nearest 2x
-    upsampling, normalization.py:188-190,275-277) and pw is prep_subpixel_weight's: four launches,
-    one per output parity class, 4/9 of the FLOPs."""
-    ops, (B, H, W) = _operands(sources, pw, passes, (0, 0) if subpixel else None)
+    upsampling, normalization.py:188-190,275-277) and pw is prep_subpixel_weight's: the four output
+    parity classes are tiles of one launch (the classes of a pixel tile run back to back, so x and the
+    sources are read from HBM once), 4/9 of the FLOPs."""
+    ops, (B, H, W) = _operands(sources, pw, passes, (-1, -1) if subpixel else None)
     _chk_cuda(x, bn_scale, bn_shift, gamma_bias, beta_bias, noise, noise_w)
     Cc = x.shape[3]
     assert tuple(x.shape[:3]) == (B, H >> x_ups, W >> x_ups)
@@ -429,14 +431,8 @@ def spade_modulate(sources, pw, x, x_ups, bn_scale, bn_shift, gamma_bias, beta_b
     m.out8_hi = f8[1].data_ptr() if f8 is not None else 0
     flops = 2.0 * 9 * pw.cin * pw.n_total * B * H * W   # reference-equivalent (sub-pixel executes 4/9)
 
-    def launch():
-        if not subpixel:
-            _lib.check(_lib.load().dsee_spade_modulate_fwd(C.byref(ops), C.byref(m), _stream()))
-            return
-        for cls in range(4):
-            o2, _ = _operands(sources, pw, passes, divmod(cls, 2))
-            _lib.check(_lib.load().dsee_spade_modulate_fwd(C.byref(o2), C.byref(m), _stream()))
-    _timed("modulate_%dx%d" % (H, W), flops, launch)
+    _timed("modulate_%dx%d" % (H, W), flops,
+           lambda: _lib.check(_lib.load().dsee_spade_modulate_fwd(C.byref(ops), C.byref(m), _stream())))
     if save_g:
         return SplitPlanes(hi, lo, f8), SplitPlanes(ghi, glo)
     return SplitPlanes(hi, lo, f8)

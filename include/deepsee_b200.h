@@ -200,7 +200,9 @@ typedef struct {
      * planes are the class's collapsed filter [n_total][4 * C_total], k = (ty*2+tx)*C_total + c, with
      *   wc[ty][tx] = sum of w[ky][kx] over the taps with floor((sub_py + ky - 1) / 2) == ty + (sub_py - 1)
      * (likewise in x); H, W stay the OUTPUT size (even).  0 = ordinary 3x3 conv.
-     * dsee_spade_modulate_fwd only. */
+     * sub_py < 0: all four classes in ONE launch - the weight planes then hold the four collapsed
+     * filters one after the other, [4 * n_total][4 * C_total] (class = py*2 + px), and the class is a
+     * tile index next to the pixel tile.  dsee_spade_modulate_fwd only. */
     int a_sub, sub_py, sub_px;
 } dsee_conv_operands;
 
