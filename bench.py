@@ -1,18 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the DeepSEE hot path on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c4]
-                    [--passes 1|3] [--mode train|infer]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5]
+                    [--batch B] [--passes 1|3] [--mode train|infer] [--no-graph] [--no-extra]
 
 One JSON line on stdout (rank 0).  A "step" is ONE TRAINING ITERATION of the reference's loop
 (train.py:60-68: TrainerManager.run_generator_one_step + run_discriminator_one_step) over one
 per-GPU batch of synthetic input: style encoder + SPADE/SEAN generator forward and backward,
 multi-scale discriminator forward/backward, hinge + feature-matching losses, both Adam updates and,
-for N > 1, the NCCL all-reduce of the G+E and D gradients.  Default workload = BASELINE.json config
-c2 (8x SR, 256x256, independent model, batch 8 per GPU); c4 = 32x SR 512x512 independent, batch 2
-per GPU.  `value` is measured with the raw batch resident in HBM; `e2e` feeds pinned HOST buffers
-through the same TrainerManager calls (H2D copies inside the timed region) and reads the losses
-back to the host every step.
+for N > 1, the NCCL all-reduce of the G+E and D gradients plus the Sync-BN statistics exchange.
+Headline workload = BASELINE.json config c2 (8x SR, 256x256, independent model, batch 8 per GPU).
+The default run also measures, into the line's `configs` block, c4 weak (32x SR 512x512 independent,
+2 images per GPU), c4 strong (global batch 8 split over the GPUs) and c5 (32x guided, 4 images per
+GPU), each with img/s, ms/step, whole-step fraction of the tensor peak and e2e.
+
+`value`: the raw batch resident in HBM; every optimizer sub-step a CUDA graph replay (--no-graph:
+eager).  `e2e`: pinned HOST buffers through the same TrainerManager calls (H2D copies inside the timed
+region), losses read back to the host every step.  `roofline`: CUDA events around every tensor-core
+launch (eager steps right after the timed region when the timed steps are graph replays).
+`parity`: max-abs of this configuration's full-size generator in this run's precision mode against
+the CPU oracle (rank 0, N = 1, next to `cpu_baseline`).  `ddp_parity` / `rank_isolated_eager_ms_per_step`
+(N > 1): sharded-vs-single-process agreement on the real NCCL ranks, and every rank's step time alone.
 """
 import argparse
 import json
@@ -579,11 +587,24 @@ def main():
     top = max(ksum.items(), key=lambda kv: kv[1][1])
     top_tflops = top[1][2] / (top[1][1] / 1000.0) / 1e12
     traffic, traffic_src = kernel_traffic(top[0], args.config)
+    # fp16-pass equivalents the dominant launch group executes per algorithmic FLOP: forward main convs
+    # (tag conv3x3_*) run `k2_fwd_passes` of them in the benched mode (2 = one fp16 pass + the fp8
+    # correction GEMM: twice the K at twice the MMA rate), everything is 3 in the fp32-class mode
+    if config.passes == 3:
+        exec_factor = 3
+    elif top[0].startswith("conv3x3_"):
+        exec_factor = config.k2_fwd_passes
+    else:
+        exec_factor = 1
     roofline = {
         "bound": "tensor", "kernel": "tcgen05 implicit-GEMM family; dominant launch group: %s" % top[0],
         "achieved": top_tflops, "peak": sust, "unit": "TFLOP/s", "frac": top_tflops / sust,
         "peak_source": "%s: bf16 dense sustained; kind::f16 operands run on the same pipe at the same rate" % how,
-        "executed_passes": config.passes,
+        "executed": {"fp16_pass_equivalents_per_algorithmic_flop": exec_factor,
+                     "tflops_equivalent": top_tflops * exec_factor, "frac": top_tflops * exec_factor / sust,
+                     "note": "`achieved` / `frac` count the reference's dense conv FLOPs once (algorithmic); the "
+                             "kernel's tensor-pipe work is this many fp16-pass equivalents of them - the price of "
+                             "the 1e-3 parity bound (DESIGN.md section 4)"},
         # per-launch CUDA-event brackets: over the timed steps when they run eagerly; with CUDA graphs
         # (the default) over `rsteps` eager steps of the same model / batch right after the timed region
         "timed_over": ("%d eager steps after the timed region (the timed steps are CUDA graph replays)" % rsteps)
