@@ -659,6 +659,9 @@ def main():
                                 "sample": "%d training iteration(s) at batch 1 of the same workload "
                                           "(oracle port of trainer_manager.py:32-61, torch CPU fp32)" % n}
         line["parity"] = parity_leg(cfg)
+        for ex in extras:   # the 512x512 generator in the same mode (c4 and c5 share it)
+            if ex["config"] == "c4" and ex["scaling"] == "weak":
+                ex["parity"] = parity_leg(CONFIGS["c4"])
     print(json.dumps(line), file=real_stdout, flush=True)
 
 

@@ -19,9 +19,11 @@ class _Config:
     #   * K1 runs 3 passes in stages up to `passes3_upto` pixels high ("auto" = a quarter of the output
     #     size: ~5 % of the FLOPs), 1 pass above;
     #   * every backward GEMM (dgrad, wgrad) runs 1 pass: gradients carry no 1e-3 forward bound.
-    #   * style encoder / discriminator convs: forward `ed_fwd_passes` (3), backward 1 pass.
+    #   * style encoder convs (their output feeds the generator): forward `ed_fwd_passes` (3), backward
+    #     1 pass; discriminator convs (they only feed the losses): `d_fwd_passes` (1).
     k2_fwd_passes = int(os.environ.get("DSEE_K2_FWD_PASSES", "2"))
     ed_fwd_passes = int(os.environ.get("DSEE_ED_FWD_PASSES", "3"))
+    d_fwd_passes = int(os.environ.get("DSEE_D_FWD_PASSES", "1"))
     passes3_upto = os.environ.get("DSEE_PASSES3_UPTO", "auto")
     # test / probe hook: {("k1" | "k2" | "k2b", H): passes} overrides of the rule above
     pass_overrides = {}
@@ -51,8 +53,8 @@ class _Config:
         k2 = {1: "1 pass", 2: "1 fp16 pass + fp8 correction of both operand-rounding terms",
               3: "hi+lo split operands x3 passes"}[self.k2_fwd_passes]
         return ("fp16 operands, fp32 accumulate (TF32-class) for the gamma/beta GEMMs and all backward GEMMs; "
-                "forward main convs: %s; forward gamma/beta GEMMs of stages <= %s and forward encoder / "
-                "discriminator convs: x3 passes" %
+                "forward main convs: %s; forward gamma/beta GEMMs of stages <= %s and forward style-encoder "
+                "convs: x3 passes" %
                 (k2, "1/4 of the output size" if self.passes3_upto == "auto" else "%s px" % self.passes3_upto))
 
     # Training: capture each optimizer sub-step (forward, backward, gradient all-reduce, Adam) of

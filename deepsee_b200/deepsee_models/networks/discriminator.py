@@ -95,19 +95,21 @@ class NLayerDiscriminator(BaseNetwork):
     def forward_nhwc(self, x, detach_params=False):
         """x NHWC [B,H,W,Cp] (channels beyond input_nc are zero) -> list of NHWC feature maps."""
         det = (lambda t: t.detach() if t is not None else None) if detach_params else (lambda t: t)
+        from ...config import config
+        fp = config.d_fwd_passes   # 1-pass mode: the discriminator only feeds the losses
         outs = []
         conv0 = self.model0[0]
-        x = ops.conv_layer(x, det(conv0.weight), det(conv0.bias), 2, 2, lrelu=True)
+        x = ops.conv_layer(x, det(conv0.weight), det(conv0.bias), 2, 2, lrelu=True, fwd_passes=fp)
         outs.append(x)
         for n in range(1, self.n_layers):
             seq = getattr(self, 'model%d' % n)[0]  # Sequential(spectral conv, InstanceNorm2d)
             conv = seq[0]
             stride = 1 if n == self.n_layers - 1 else 2
-            y = ops.conv_layer(x, det(effective_weight(conv)), None, stride, 2)
+            y = ops.conv_layer(x, det(effective_weight(conv)), None, stride, 2, fwd_passes=fp)
             x = ops.InstanceNormFn.apply(y, 1)
             outs.append(x)
         last = getattr(self, 'model%d' % self.n_layers)[0]
-        x = ops.conv_layer(x, det(last.weight), det(last.bias), 1, 2)
+        x = ops.conv_layer(x, det(last.weight), det(last.bias), 1, 2, fwd_passes=fp)
         outs.append(x)
         return outs
 

@@ -1083,11 +1083,12 @@ class Conv2dTCFn(torch.autograd.Function):
     padding channels); out fp32 NHWC."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, stride, pad, ups, lrelu):
+    def forward(ctx, x, w, bias, stride, pad, ups, lrelu, fwd_passes=None):
         from .config import config
-        # forward at config.ed_fwd_passes (3 by default: predictions, features and hinge / LeakyReLU
-        # kink decisions are fp32-class, 0.4 % of the step's FLOPs); backward GEMMs at config.passes
-        passes_f = 3 if config.passes == 3 else config.ed_fwd_passes
+        # 1-pass mode: the forward GEMM runs `fwd_passes` (default config.ed_fwd_passes = 3: the style
+        # encoder's output feeds the generator, whose output carries the 1e-3 bound; the discriminator,
+        # which only feeds the losses, passes 1); backward GEMMs at config.passes
+        passes_f = 3 if config.passes == 3 else (fwd_passes or config.ed_fwd_passes)
         passes = config.passes
         want_lo = passes_f == 3
         N, Cw, KH, KW = w.shape
@@ -1128,21 +1129,22 @@ class Conv2dTCFn(torch.autograd.Function):
                 dx = dx[..., :Cx].contiguous()
             if ups:
                 dx = fold2x2(dx)
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
-def conv_layer(x, w, bias, stride, pad, ups=0, lrelu=False):
+def conv_layer(x, w, bias, stride, pad, ups=0, lrelu=False, fwd_passes=None):
     """Dispatch of an encoder / discriminator conv: tcgen05 path when eligible, else the direct fp32
-    kernels. w in PyTorch layout [N,Cw,KH,KW] (autograd tensor)."""
+    kernels. w in PyTorch layout [N,Cw,KH,KW] (autograd tensor).  fwd_passes: operand passes of the
+    forward GEMM in 1-pass mode (None = config.ed_fwd_passes)."""
     if tc_conv_eligible(x.shape[3], w.shape[0]):
-        return Conv2dTCFn.apply(x, w, bias, stride, pad, ups, lrelu)
+        return Conv2dTCFn.apply(x, w, bias, stride, pad, ups, lrelu, fwd_passes)
     if tc_conv_eligible(x.shape[3], 32) and w.shape[0] < 32:
         # narrow outputs (the discriminator's 1-channel prediction conv): zero-pad the filter bank to
         # the 32 columns the tensor-core epilogue stores and slice; autograd un-pads the gradients
         n = w.shape[0]
         wp = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, 32 - n))
         bp = torch.nn.functional.pad(bias, (0, 32 - n)) if bias is not None else None
-        return Conv2dTCFn.apply(x, wp, bp, stride, pad, ups, lrelu)[..., :n].contiguous()
+        return Conv2dTCFn.apply(x, wp, bp, stride, pad, ups, lrelu, fwd_passes)[..., :n].contiguous()
     wk = w.permute(2, 3, 1, 0)
     if x.shape[3] > wk.shape[2]:
         wk = torch.nn.functional.pad(wk, (0, 0, 0, x.shape[3] - wk.shape[2]))
