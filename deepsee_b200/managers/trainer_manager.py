@@ -118,6 +118,16 @@ class _GraphedStep:
                 random.random = real
             self.n_draws = counter['n']
             return out
+        if self.static_in is not None and any(
+                torch.is_tensor(v) and (k not in self.static_in or v.shape != self.static_in[k].shape)
+                for k, v in data.items()):
+            # a batch of another shape (the last, smaller one of an epoch): this call runs eagerly
+            draws = [real() for _ in range(self.n_draws)]
+            random.random = _ReplayRandom(draws, real)
+            try:
+                return self._eager(data)
+            finally:
+                random.random = real
         draws = [real() for _ in range(self.n_draws)]
         return self._run_variant(draws, data)
 
@@ -136,6 +146,7 @@ class _GraphedStep:
         real = random.random
         if self.lr_sig != self._lr_signature():    # learning rates are baked into the Adam nodes
             self.graphs.clear()
+            self.captured_launches.clear()
             self.lr_sig = self._lr_signature()
         key = tuple(v < 0.5 for v in draws)
         static = self._stage(data)

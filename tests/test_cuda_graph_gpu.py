@@ -33,7 +33,12 @@ def _run(graphs, steps, name, over):
         random.seed(123)
         losses = []
         for i in range(steps):
-            raw = O.synthetic_batch(o, 2, seed=500 + i)
+            if i == 5:      # a learning-rate change (baked into the captured Adam nodes: forces a re-capture)
+                for opt_ in (mgr.optimizer_G, mgr.optimizer_D):
+                    for grp in opt_.param_groups:
+                        grp['lr'] = grp['lr'] * 0.5
+            # step 7: a batch of another size (the last batch of an epoch) runs eagerly in graph mode
+            raw = O.synthetic_batch(o, 1 if i == 7 else 2, seed=500 + i)
             data = {k: (v.float() if "label" in k else v) for k, v in raw.items()}
             mgr.run_generator_one_step(dict(data))
             mgr.run_discriminator_one_step(dict(data))
