@@ -145,8 +145,10 @@ class _GraphedStep:
         mgr = self.mgr
         real = random.random
         if self.lr_sig != self._lr_signature():    # learning rates are baked into the Adam nodes
+            # (destroying the last graph of a private pool releases the pool: start a new one)
             self.graphs.clear()
             self.captured_launches.clear()
+            self.pool = None
             self.lr_sig = self._lr_signature()
         key = tuple(v < 0.5 for v in draws)
         static = self._stage(data)
