@@ -19,7 +19,7 @@ SYMBOLS = [
     "dsee_conv3x3_wgrad_per_image_workspace_floats", "dsee_conv3x3_wgrad2_per_image",
     "dsee_subpixel_wgrad_workspace_floats", "dsee_subpixel_wgrad", "dsee_subpixel_dgrad", "dsee_prep_conv_weight_ex", "dsee_split_f16_ups2",
     "dsee_fold2x2", "dsee_conv2d_tc", "dsee_conv2d_tc_wgrad_workspace_floats", "dsee_conv2d_tc_wgrad",
-    "dsee_conv3x3_fwd", "dsee_conv3x3_stats_tiles", "dsee_spade_modulate_fwd",
+    "dsee_conv3x3_fwd", "dsee_conv_pair_mode", "dsee_conv3x3_stats_tiles", "dsee_spade_modulate_fwd",
     "dsee_spade_modulate_bwd", "dsee_spade_modulate_bwd_saved", "dsee_dgrad_modulate_bwd", "dsee_grad_prep_blocks", "dsee_grad_prep", "dsee_reduce_partials",
     "dsee_conv3x3_wgrad_workspace_floats", "dsee_conv3x3_wgrad", "dsee_conv3x3_wgrad2", "dsee_bn_bwd_blocks", "dsee_bn_bwd",
     "dsee_actv_grad_prep", "dsee_onehot_planes", "dsee_shared_mlp_bwd_blocks", "dsee_shared_mlp_bwd", "dsee_style_gather_bwd",
@@ -167,6 +167,7 @@ def load():
         "dsee_conv2d_tc": [C.POINTER(Conv2dTCArgs), C.POINTER(ConvEpilogue), vp],
         "dsee_conv2d_tc_wgrad": [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, i, i, vp, vp, vp],
         "dsee_conv3x3_fwd": [C.POINTER(ConvOperands), C.POINTER(ConvEpilogue), vp],
+        "dsee_conv_pair_mode": [i],
         "dsee_conv3x3_stats_tiles": [i, i, i],
         "dsee_spade_modulate_fwd": [C.POINTER(ConvOperands), C.POINTER(ModulateArgs), vp],
         "dsee_spade_modulate_bwd": [C.POINTER(ConvOperands), C.POINTER(ModulateBwdArgs), vp],
@@ -249,6 +250,8 @@ def load():
     lib.dsee_conv2d_direct_wgrad_workspace_floats.restype = C.c_int64
     if lib.dsee_version() != ABI_VERSION:
         raise RuntimeError("deepsee_b200: ABI version mismatch")
+    if os.environ.get("DSEE_CTA_PAIR", "0") == "1":   # opt-in cta_group::2 main convs
+        lib.dsee_conv_pair_mode(1)
     _lib = lib
     return lib
 

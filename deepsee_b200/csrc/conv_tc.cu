@@ -74,6 +74,7 @@ struct alignas(64) ConvParams {
     int w_brows;       // per-image weights: row offset of image b is b * w_brows (0 = shared)
     int sub4;          // 1: sub-pixel form, all four parity classes in this launch: the class is a tile
                        // index (fastest after the N tile), taps [cls*4, cls*4+4), weight rows + cls*n_total
+    int pair;          // 1: CTA-pair form (cta_group::2): 16 x 16-pixel tiles, 8 rows and 128 weight rows per CTA
     int m2;            // 1: a tile is 16 x 16 pixels = two 128-pixel halves sharing one <= 128-row weight
                        // box (two MMAs per K step into TMEM columns [0,128) and [128,256)): narrow-N
                        // GEMMs then move as few operand bytes per FLOP as the N = 256 tile
@@ -150,7 +151,7 @@ __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& 
     mt /= p.tiles_w;
     int th = mt % p.tiles_h;
     b = mt / p.tiles_h;
-    h0 = th * (TILE_H << p.m2);
+    h0 = th * (TILE_H << (p.m2 | p.pair));
     w0 = tw * TILE_W;
 }
 
@@ -189,7 +190,15 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
     return v[0];
 }
 
-template <int EPI>
+// CTA2 = true: the kernel runs as 2-CTA clusters (one TPC each).  A pair owns a 16 x 16-pixel tile: CTA
+// r computes rows h0 + 8 r .. of it (its own A boxes, its own TMEM accumulator, its own epilogue) and
+// stages rows [128 r, 128 r + 128) of the 256-row weight box; the leader issues ONE
+// tcgen05.mma.cta_group::2 (M = 256, N = 256) per K step that reads both CTAs' shared memory.  Per
+// CTA and K block 32 KB come from L2 instead of 48 KB.  Barrier protocol: both producers
+// arrive.expect_tx on the LEADER's full barrier (count 2) and their TMA loads complete_tx there; the
+// leader's commits are multicast to both CTAs' empty / accumulator-full barriers; the peer's epilogue
+// warps release the accumulator on the leader's accumulator-empty barrier (count 2 x EPI_WARPS).
+template <int EPI, bool CTA2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -205,6 +214,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int crank = CTA2 ? (int)cluster_ctarank() : 0;      // 0 = leader
+    const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tstep = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmA[i]);
@@ -216,21 +228,27 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
             tma_prefetch_desc(&p.tmB8);
         }
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], CTA2 ? 2 : 1);   // pair: one arrive.expect_tx per producer
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[s], CTA2 ? 2 * EPI_WARPS : EPI_WARPS);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
+        if (CTA2) {
+            tmem_alloc_pair(tmem_slot, TMEM_COLS);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_slot, TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CTA2) cluster_sync_all();   // the peer's barriers exist before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -242,10 +260,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < p.num_tiles; tile += tstep) {
                 int b, h0, w0, nt, cls;
                 decode_tile(p, tile, b, h0, w0, nt, cls);
-                const int n0 = nt * BLOCK_N + cls * p.n_total;   // (cls != 0 only in the sub4 form)
+                if (CTA2) h0 += crank * TILE_H;   // my 8 rows of the pair's 16 x 16-pixel tile
+                // (cls != 0 only in the sub4 form; pair: my half of the weight rows)
+                const int n0 = nt * BLOCK_N + cls * p.n_total + (CTA2 ? crank * (BLOCK_N / 2) : 0);
                 for (int pass = 0; pass < p.passes; ++pass) {
                     const int pa = (pass == 1) ? 1 : 0;
                     const int pb = (pass == 2) ? 1 : 0;
@@ -255,11 +275,18 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                             const int s = it % STAGES;
                             const uint32_t ph = (it / STAGES) & 1;
                             mbar_wait(&empty_bar[s], ph ^ 1);
-                            mbar_expect_tx(&full_bar[s], (A_BYTES << p.m2) + p.b_rows * BLOCK_K * 2);
                             uint8_t* sa = smem + s * STAGE_BYTES;
                             uint8_t* sb = sa + (A_BYTES << p.m2);
                             const int src = (cb >= p.cb0) ? 1 : 0;
                             const int cl = src ? cb - p.cb0 : cb;
+                            if (CTA2) {
+                                mbar_expect_tx_leader(&full_bar[s], A_BYTES + p.b_rows * BLOCK_K * 2);
+                                tma_load_4d_pair(&p.tmA[src * 2 + pa], &full_bar[s], sa, cl * BLOCK_K,
+                                                 w0 * p.a_step + dx, h0 * p.a_step + dy, b);
+                                tma_load_2d_pair(&p.tmB[pb], &full_bar[s], sb, p.tap_k[tap] + cb * BLOCK_K, n0);
+                                continue;
+                            }
+                            mbar_expect_tx(&full_bar[s], (A_BYTES << p.m2) + p.b_rows * BLOCK_K * 2);
                             tma_load_4d(&p.tmA[src * 2 + pa], &full_bar[s], sa, cl * BLOCK_K,
                                         w0 * p.a_step + dx, h0 * p.a_step + dy, b);
                             tma_load_2d(&p.tmB[pb], &full_bar[s], sb, p.tap_k[tap] + cb * BLOCK_K,
@@ -275,10 +302,17 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                             const int s = it % STAGES;
                             const uint32_t ph = (it / STAGES) & 1;
                             mbar_wait(&empty_bar[s], ph ^ 1);
-                            mbar_expect_tx(&full_bar[s], A_BYTES + p.b_rows * 128);
                             uint8_t* sa = smem + s * STAGE_BYTES;
                             uint8_t* sb = sa + A_BYTES;
                             const int pl = cb >= p.cb8 ? 1 : 0;
+                            if (CTA2) {
+                                mbar_expect_tx_leader(&full_bar[s], A_BYTES + p.b_rows * 128);
+                                tma_load_4d_pair(&p.tmA8[pl], &full_bar[s], sa, (cb - pl * p.cb8) * 128,
+                                                 w0 * p.a_step + dx, h0 * p.a_step + dy, b);
+                                tma_load_2d_pair(&p.tmB8, &full_bar[s], sb, (tap * 2 * p.cb8 + cb) * 128, n0);
+                                continue;
+                            }
+                            mbar_expect_tx(&full_bar[s], A_BYTES + p.b_rows * 128);
                             tma_load_4d(&p.tmA8[pl], &full_bar[s], sa, (cb - pl * p.cb8) * 128,
                                         w0 * p.a_step + dx, h0 * p.a_step + dy, b);
                             tma_load_2d(&p.tmB8, &full_bar[s], sb, (tap * 2 * p.cb8 + cb) * 128, n0);
@@ -289,10 +323,10 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && crank == 0) {   // pair: the leader issues for both CTAs
             uint32_t it = 0;
             int lt = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+            for (int tile = tile0; tile < p.num_tiles; tile += tstep, ++lt) {
                 const int as = lt & 1;
                 const uint32_t aph = (lt >> 1) & 1;
                 mbar_wait(&tempty_bar[as], aph ^ 1);
@@ -307,6 +341,19 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                     const uint32_t sb = sa + (A_BYTES << p.m2);
                     const uint64_t da = umma_desc_sw128(sa, 1024);
                     const uint64_t db = umma_desc_sw128(sb, 1024);
+                    if (CTA2) {
+                        if (kit < k16) {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                umma_f16_pair(tmem_d, da + 2 * k, db + 2 * k, p.idesc, (kit | k) != 0);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_f8_pair(tmem_d, da + 2 * k, db + 2 * k, p.idesc8, 1u);
+                        }
+                        umma_commit_pair(&empty_bar[s]);
+                        continue;
+                    }
                     if (kit < k16) {
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / 16; ++k) {
@@ -326,7 +373,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                     }
                     umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
                 }
-                umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (of both CTAs in the pair form)
+                if (CTA2) umma_commit_pair(&tfull_bar[as]);
+                else umma_commit(&tfull_bar[as]);
             }
         }
     } else {
@@ -341,11 +390,14 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
         const unsigned long long rseed0 = eff_noise_seed(p.rnoise_seed[0], p.noise_epoch);
         const unsigned long long rseed1 = eff_noise_seed(p.rnoise_seed[1], p.noise_epoch);
         int lt = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+        for (int tile = tile0; tile < p.num_tiles; tile += tstep, ++lt) {
             const int as = lt & 1;
             const uint32_t aph = (lt >> 1) & 1;
             int b, h0, w0, nt, cls;
             decode_tile(p, tile, b, h0, w0, nt, cls);
+            if (CTA2) h0 += crank * TILE_H;
+            // pixel tile index for the per-tile statistics slots (pair: two 8-row halves per tile)
+            const int ptile = CTA2 ? (tile / p.n_tiles) * 2 + crank : tile / p.n_tiles;
             const int y = h0 + ly, x = w0 + lx;
             const bool valid = (y < p.H) && (x < p.W);
             mbar_wait(&tfull_bar[as], aph);
@@ -459,7 +511,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                             s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
                         }
                         if (lane < 8) {
-                            const size_t slot = (size_t)(tile / p.n_tiles) * 4 + q;
+                            const size_t slot = (size_t)ptile * 4 + q;
                             float4* sp = reinterpret_cast<float4*>(p.stats_partial + (slot * p.n_total + nc) * 2);
                             sp[0] = make_float4(s1[0], s2[0], s1[1], s2[1]);
                             sp[1] = make_float4(s1[2], s2[2], s1[3], s2[3]);
@@ -552,7 +604,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                     const float r1 = warp_transpose_reduce(s_dxx, lane);
                     const float r2 = warp_transpose_reduce(s_dg, lane);
                     const float r3 = warp_transpose_reduce(s_db, lane);
-                    const size_t slot = (size_t)(tile / p.n_tiles) * 4 + q;
+                    const size_t slot = (size_t)ptile * 4 + q;
                     *reinterpret_cast<float4*>(p.bwd_partial + (slot * p.C + c + lane) * 4) =
                         make_float4(r0, r1, r2, r3);
                 }
@@ -675,7 +727,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                             sm[k][e] += __shfl_xor_sync(0xffffffffu, sm[k][e], 16);
                         }
                     if (lane < 8) {
-                        const size_t slot = (size_t)(tile / p.n_tiles) * 4 + q;
+                        const size_t slot = (size_t)ptile * 4 + q;
                         float4* bp = reinterpret_cast<float4*>(p.bwd_partial + (slot * p.C + cc) * 4);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) bp[e] = make_float4(sm[0][e], sm[1][e], sm[2][e], sm[3][e]);
@@ -794,20 +846,27 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
             // all TMEM reads of this accumulator stage are complete (wait::ld above)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) {
+                if (CTA2) mbar_arrive_leader(&tempty_bar[as]);
+                else mbar_arrive(&tempty_bar[as]);
+            }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTA2) cluster_sync_all();   // nobody leaves while the peer can still signal or read this CTA
+    if (warp == 1) {
+        if (CTA2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_f8 = false,
-                       bool allow_sub = false, bool m2 = false) {
+                       bool allow_sub = false, bool m2 = false, bool pair = false) {
     DSEE_CHECK_ARG(ops != nullptr, "conv operands are NULL");
     DSEE_CHECK_ARG(ops->B > 0 && ops->H > 0 && ops->W > 0, "bad geometry B=%d H=%d W=%d", ops->B,
                    ops->H, ops->W);
@@ -855,8 +914,9 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
     p.w_brows = ops->w_batch_rows;
     p.noise_epoch = noise_epoch_ptr();
     p.m2 = m2 ? 1 : 0;
+    p.pair = pair ? 1 : 0;
     p.tiles_w = (ops->W + TILE_W - 1) / TILE_W;
-    p.tiles_h = (ops->H + (TILE_H << p.m2) - 1) / (TILE_H << p.m2);
+    p.tiles_h = (ops->H + (TILE_H << (p.m2 | p.pair)) - 1) / (TILE_H << (p.m2 | p.pair));
     p.n_tiles = (ops->n_total + BLOCK_N - 1) / BLOCK_N;
     p.num_tiles = p.B * p.tiles_h * p.tiles_w * p.n_tiles;
     p.cb0 = ops->a_channels[0] / BLOCK_K;
@@ -870,7 +930,7 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
                    "operand dtypes must both be 0 (fp16) or both 1 (bf16): tcgen05 kind::f16 rejects "
                    "mixed A/B formats");
     p.idesc = (1u << 4) | ((uint32_t)ops->a_dtype << 7) | ((uint32_t)ops->w_dtype << 10) |
-              ((uint32_t)(p.b_rows >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+              ((uint32_t)(p.b_rows >> 3) << 17) | ((uint32_t)((BLOCK_M << p.pair) >> 4) << 24);
 
     const int sub = ops->a_sub ? 1 : 0;
     if (sub) {
@@ -923,7 +983,7 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
         p.cb8 = C / 128;
         // kind::f8f6f4: fp32 accumulate, A = e5m2, B = e4m3, K-major both
         p.idesc8 = (1u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(p.b_rows >> 3) << 17) |
-                   ((uint32_t)(BLOCK_M >> 4) << 24);
+                   ((uint32_t)((BLOCK_M << p.pair) >> 4) << 24);
         for (int pl = 0; pl < 2; ++pl) {
             uint64_t dims[4] = {(uint64_t)C, (uint64_t)ops->W, (uint64_t)ops->H, (uint64_t)ops->B};
             uint64_t strides[3] = {(uint64_t)C, (uint64_t)ops->W * C, (uint64_t)ops->H * ops->W * C};
@@ -933,7 +993,7 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
         }
         uint64_t dims[2] = {(uint64_t)18 * C, (uint64_t)ops->n_total};
         uint64_t strides[1] = {(uint64_t)18 * C};
-        uint32_t box[2] = {128, (uint32_t)p.b_rows};
+        uint32_t box[2] = {128, (uint32_t)(p.b_rows >> p.pair)};
         rc = encode_tmap_8b(&p.tmB8, ops->w8, 2, dims, strides, box);
         if (rc) return rc;
     }
@@ -948,15 +1008,60 @@ static int fill_common(ConvParams& p, const dsee_conv_operands* ops, bool allow_
         }
         uint64_t dims[2] = {Ktot, (uint64_t)ops->n_total * (ops->w_batch_rows ? ops->B : 1) * (p.sub4 ? 4 : 1)};
         uint64_t strides[1] = {Ktot * 2};
-        uint32_t box[2] = {BLOCK_K, (uint32_t)p.b_rows};
+        uint32_t box[2] = {BLOCK_K, (uint32_t)(p.b_rows >> p.pair)};
         rc = encode_tmap_16b(&p.tmB[pl], base, 2, dims, strides, box, ops->w_dtype == 1);
         if (rc) return rc;
     }
+    if (p.pair) p.b_rows >>= 1;   // from here on: weight rows staged per CTA (the descriptors hold N = 256)
+    return 0;
+}
+
+// CTA-pair launch: 2-CTA clusters, one per TPC
+static int g_cta_pair = 0;   // dsee_conv_pair_mode
+
+template <int EPI>
+static int launch_pair(const ConvParams& p, cudaStream_t stream) {
+    static bool configured[64] = {false};
+    static int max_clusters[64] = {0};
+    int dev = 0;
+    DSEE_CUDA(cudaGetDevice(&dev));
+    DSEE_CHECK_ARG(dev < 64, "device index %d out of range", dev);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (!configured[dev]) {
+        DSEE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<EPI, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        int sms = 0;
+        DSEE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        cfg.gridDim = dim3(sms / 2 * 2, 1, 1);
+        int nc = 0;
+        DSEE_CUDA(cudaOccupancyMaxActiveClusters(&nc, conv3x3_tc_kernel<EPI, true>, &cfg));
+        DSEE_CHECK_ARG(nc > 0, "no 2-CTA cluster of the pair kernel fits on this device");
+        max_clusters[dev] = nc < sms / 2 ? nc : sms / 2;
+        configured[dev] = true;
+    }
+    const int clusters = p.num_tiles < max_clusters[dev] ? p.num_tiles : max_clusters[dev];
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
+    DSEE_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<EPI, true>, p));
+    count_launch();
     return 0;
 }
 
 template <int EPI>
 static int launch(const ConvParams& p, cudaStream_t stream) {
+    if constexpr (EPI == EPI_CONV) {
+        if (p.pair) return launch_pair<EPI>(p, stream);
+    }
     static bool configured[64] = {false};
     int dev = 0;
     DSEE_CUDA(cudaGetDevice(&dev));
@@ -978,6 +1083,12 @@ static int launch(const ConvParams& p, cudaStream_t stream) {
 
 using namespace dsee;
 
+extern "C" int dsee_conv_pair_mode(int on) {
+    const int prev = g_cta_pair;
+    if (on >= 0) g_cta_pair = on ? 1 : 0;
+    return prev;
+}
+
 extern "C" int dsee_conv3x3_stats_tiles(int B, int H, int W) {
     return B * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W) * 4;
 }
@@ -990,7 +1101,10 @@ extern "C" int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_e
     // narrow outputs (the modulation's backward-data GEMM, N = 128): 16 x 16-pixel tiles
     const bool m2 = ops && ops->n_total <= 128 && !epi->stats_partial && ops->passes != 2 &&
                     ops->w_batch_rows == 0;
-    int rc = fill_common(p, ops, true, false, m2);
+    // wide outputs on 16-row-aligned images: CTA pairs sharing the weight box (opt-in)
+    const bool pair = g_cta_pair && ops && ops->n_total % BLOCK_N == 0 && ops->H % (2 * TILE_H) == 0 &&
+                      ops->w_batch_rows == 0 && !ops->a_sub;
+    int rc = fill_common(p, ops, true, false, m2, pair);
     if (rc) return rc;
     DSEE_CHECK_ARG(epi->res_ups == 0 || epi->res_ups == 1, "res_ups must be 0 or 1");
     DSEE_CHECK_ARG(!epi->residual || epi->res_ups == 0 || (ops->H % 2 == 0 && ops->W % 2 == 0),

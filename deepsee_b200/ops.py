@@ -97,6 +97,12 @@ def noise_epoch_advance():
     _lib.check(_lib.load().dsee_noise_epoch_advance(_stream()))
 
 
+def conv_pair_mode(on=None):
+    """Switches dsee_conv3x3_fwd's CTA-pair form (tcgen05 cta_group::2) on / off for the process; returns
+    the previous mode.  on=None only queries."""
+    return bool(_lib.load().dsee_conv_pair_mode(-1 if on is None else int(bool(on))))
+
+
 def noise_fill(seed, shape, device="cuda"):
     """Materialises the noise tensor a NoiseSeed stands for (tests)."""
     out = torch.empty(shape, dtype=torch.float32, device=device)

@@ -206,6 +206,13 @@ typedef struct {
     int a_sub, sub_py, sub_px;
 } dsee_conv_operands;
 
+/* Opt-in CTA-pair form of dsee_conv3x3_fwd (tcgen05 cta_group::2: two SMs of a TPC share one 256-row
+ * weight box; used when n_total % 256 == 0 and H % 16 == 0).  on = 1 / 0 sets the process-wide mode,
+ * on < 0 only queries; returns the previous mode.  Results are bit-identical to the single-CTA form
+ * (same accumulation order per output element).  No reference counterpart (cuDNN picks its own
+ * kernels). */
+int dsee_conv_pair_mode(int on);
+
 /* K2.  Replaces conv_0 / conv_1 of SPADEResnetBlock (architecture.py:34-35,98,122) plus what the
  * reference does to the conv output before the next layer reads it:
  *   - the residual add `out = x_s + dx` (architecture.py:127), the shortcut read through a folded

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--S", type=int, default=256)
     ap.add_argument("--sub", action="store_true")
     ap.add_argument("--no-warm", action="store_true")
+    ap.add_argument("--pair", action="store_true", help="also time K2 in the CTA-pair (cta_group::2) form")
     a = ap.parse_args()
     B, S, C, L, nh, d = a.B, a.S, 512, 19, 128, 128
     dev = "cuda"
@@ -91,6 +92,15 @@ def main():
     timed("K2 1-pass (same epilogue)", lambda: ops.conv3x3(
         [act1], pw2, bias, residual=x_lo, res_ups=1,
         noises=[(ops.NoiseSeed(5), nw), (ops.NoiseSeed(6), nw)], passes=1, want_stats=True), 2 * 9 * C * C * px)
+    if a.pair:
+        ops.conv_pair_mode(True)
+        timed("K2 fp16 + fp8 corr., CTA pair", lambda: ops.conv3x3(
+            [act], pw2, bias, residual=x_lo, res_ups=1,
+            noises=[(ops.NoiseSeed(5), nw), (ops.NoiseSeed(6), nw)], passes=2, want_stats=True), 2 * 9 * C * C * px)
+        timed("K2 1-pass, CTA pair", lambda: ops.conv3x3(
+            [act1], pw2, bias, residual=x_lo, res_ups=1,
+            noises=[(ops.NoiseSeed(5), nw), (ops.NoiseSeed(6), nw)], passes=1, want_stats=True), 2 * 9 * C * C * px)
+        ops.conv_pair_mode(False)
     gp, _ = ops.grad_prep(dy, want_lo=False)
     pwT = ops.prep_conv_weight(w, want_lo=False, transpose=True)
     dxhat, dgb, sums = timed("dgrad + K1 backward (fused)", lambda: ops.dgrad_modulate_bwd(

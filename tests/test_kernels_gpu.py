@@ -754,3 +754,36 @@ def test_modweight_node_vs_torch_ops(kind):
     assert set(got) == set(ref_grads), (sorted(got), sorted(ref_grads))
     for k, r in ref_grads.items():
         assert (got[k] - r).abs().max().item() <= 1e-4 * max(r.abs().max().item(), 1e-6), k
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,passes", [(1, 16, 16, 128, 256, 1), (2, 32, 48, 256, 512, 3),
+                                                   (3, 48, 40, 512, 512, 2), (1, 64, 64, 256, 256, 2)])
+def test_conv3x3_cta_pair_is_bit_identical(B, H, W, Cin, Cout, passes):
+    """The cta_group::2 form (two SMs of a TPC share one weight box) accumulates every output element in
+    the same order as the single-CTA kernel: outputs and batch-norm partial sums must agree exactly."""
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(H + Cin + Cout + passes)
+    x = torch.randn(B, Cin, H, W, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda()
+    bias = torch.randn(Cout, generator=g).cuda()
+    xn = _nhwc(x)
+    a = ops.split_f16(xn)
+    if passes == 2:
+        lo = xn - a.hi.float()
+        a = ops.SplitPlanes(a.hi, None, ((lo * 256).to(torch.float8_e5m2).view(torch.uint8),
+                                         xn.to(torch.float8_e5m2).view(torch.uint8)))
+    pw = ops.prep_conv_weight(w, want_lo=passes == 3, want_f8=passes == 2)
+    res = torch.randn(B, H, W, Cout, generator=g).cuda()
+    prev = ops.conv_pair_mode(False)
+    try:
+        o0, s0 = ops.conv3x3([a], pw, bias, passes=passes, residual=res, want_stats=True)
+        ops.conv_pair_mode(True)
+        o1, s1 = ops.conv3x3([a], pw, bias, passes=passes, residual=res, want_stats=True)
+    finally:
+        ops.conv_pair_mode(prev)
+    ref = F.conv2d(x, w, bias, padding=1) + _nchw(res)
+    assert (_nchw(o1) - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+    assert torch.equal(o0, o1)
+    # same per-tile partial sums in a different slot order (16-row tiles, two halves each)
+    torch.testing.assert_close(s0.double().sum(0), s1.double().sum(0), rtol=1e-6, atol=1e-6)
+    assert torch.equal(s0.sort(0).values, s1.sort(0).values)
