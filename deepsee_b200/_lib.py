@@ -19,7 +19,7 @@ SYMBOLS = [
     "dsee_conv3x3_wgrad_per_image_workspace_floats", "dsee_conv3x3_wgrad2_per_image",
     "dsee_subpixel_wgrad_workspace_floats", "dsee_subpixel_wgrad", "dsee_subpixel_dgrad", "dsee_prep_conv_weight_ex", "dsee_split_f16_ups2",
     "dsee_fold2x2", "dsee_conv2d_tc", "dsee_conv2d_tc_wgrad_workspace_floats", "dsee_conv2d_tc_wgrad",
-    "dsee_conv3x3_fwd", "dsee_conv_pair_mode", "dsee_conv3x3_stats_tiles", "dsee_spade_modulate_fwd",
+    "dsee_head_gather_fwd", "dsee_head_scatter_bwd", "dsee_conv3x3_fwd", "dsee_conv_pair_mode", "dsee_conv3x3_stats_tiles", "dsee_spade_modulate_fwd",
     "dsee_spade_modulate_bwd", "dsee_spade_modulate_bwd_saved", "dsee_dgrad_modulate_bwd", "dsee_grad_prep_blocks", "dsee_grad_prep", "dsee_reduce_partials",
     "dsee_conv3x3_wgrad_workspace_floats", "dsee_conv3x3_wgrad", "dsee_conv3x3_wgrad2", "dsee_bn_bwd_blocks", "dsee_bn_bwd",
     "dsee_actv_grad_prep", "dsee_onehot_planes", "dsee_shared_mlp_bwd_blocks", "dsee_shared_mlp_bwd", "dsee_style_gather_bwd",
@@ -55,6 +55,7 @@ class ConvEpilogue(C.Structure):
         ("noise", C.c_void_p * 2), ("noise_w", C.c_void_p * 2),
         ("out", C.c_void_p), ("stats_partial", C.c_void_p), ("act_mask", C.c_void_p),
         ("amax_out", C.c_void_p), ("lrelu", C.c_int), ("noise_seed", C.c_uint64 * 2),
+        ("act16_hi", C.c_void_p), ("act16_lo", C.c_void_p),
     ]
 
 
@@ -128,7 +129,7 @@ class ModWeightGrads(C.Structure):
     ]
 
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 
@@ -168,6 +169,8 @@ def load():
         "dsee_conv2d_tc_wgrad": [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, i, i, vp, vp, vp],
         "dsee_conv3x3_fwd": [C.POINTER(ConvOperands), C.POINTER(ConvEpilogue), vp],
         "dsee_conv_pair_mode": [i],
+        "dsee_head_gather_fwd": [vp, vp, vp, i, i, i, vp],
+        "dsee_head_scatter_bwd": [vp, vp, vp, i, i, i, vp],
         "dsee_conv3x3_stats_tiles": [i, i, i],
         "dsee_spade_modulate_fwd": [C.POINTER(ConvOperands), C.POINTER(ModulateArgs), vp],
         "dsee_spade_modulate_bwd": [C.POINTER(ConvOperands), C.POINTER(ModulateBwdArgs), vp],

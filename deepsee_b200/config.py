@@ -79,6 +79,9 @@ class _Config:
     subpixel = os.environ.get("DSEE_SUBPIXEL", "1") != "0"
     # Training: K1 saves G = gamma + gamma_bias (fp16 planes, +1-2 B per activation element) so its
     # backward is one streaming pass instead of re-running the gamma GEMM (0 = recompute).
+    # the image head (leaky_relu -> conv_img -> tanh, sr.py:94-95) as a 1x1 tensor-core GEMM over fp16
+    # planes written by the last main conv's epilogue + a 9-tap shift-add; 0 = the fp32 CUDA-core kernels
+    head_tc = os.environ.get("DSEE_HEAD_TC", "1") != "0"
     save_gamma = os.environ.get("DSEE_SAVE_GAMMA", "1") != "0"
     # Backward: run the backward-data GEMM of a main conv and K1's backward of the norm layer in front
     # of it as one kernel (needs save_gamma); 0 = dgrad -> dt in HBM -> streaming K1 backward.

@@ -493,6 +493,22 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                             o[0] += nw1.x * r4.x; o[1] += nw1.y * r4.y; o[2] += nw1.z * r4.z; o[3] += nw1.w * r4.w;
                         }
                         *reinterpret_cast<float4*>(p.out + oe) = make_float4(o[0], o[1], o[2], o[3]);
+                        if (p.out_hi) {  // leaky_relu(out) as fp16 planes for the tensor-core image head
+                            uint32_t hh[2], ll[2];
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const float v0 = o[2 * e] > 0.f ? o[2 * e] : 0.2f * o[2 * e];
+                                const float v1 = o[2 * e + 1] > 0.f ? o[2 * e + 1] : 0.2f * o[2 * e + 1];
+                                const __half h0 = __float2half_rn(fminf(fmaxf(v0, -65504.f), 65504.f));
+                                const __half h1 = __float2half_rn(fminf(fmaxf(v1, -65504.f), 65504.f));
+                                const __half l0 = __float2half_rn(v0 - __half2float(h0));
+                                const __half l1 = __float2half_rn(v1 - __half2float(h1));
+                                hh[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                                ll[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                            }
+                            *reinterpret_cast<uint2*>(p.out_hi + oe) = make_uint2(hh[0], hh[1]);
+                            if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + oe) = make_uint2(ll[0], ll[1]);
+                        }
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             tmax = fmaxf(tmax, fabsf(o[e]));
@@ -1124,6 +1140,9 @@ extern "C" int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_e
     p.act_mask = (const __half*)epi->act_mask;
     p.lrelu = epi->lrelu;
     p.amax_out = epi->amax_out;
+    DSEE_CHECK_ARG(epi->act16_hi || !epi->act16_lo, "act16_lo without act16_hi");
+    p.out_hi = (__half*)epi->act16_hi;
+    p.out_lo = (__half*)epi->act16_lo;
     if (p.amax_out) DSEE_CUDA(cudaMemsetAsync(p.amax_out, 0, sizeof(float), (cudaStream_t)stream));
     return launch<EPI_CONV>(p, (cudaStream_t)stream);
 }

@@ -669,6 +669,61 @@ head_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
     }
 }
 
+// ---- tensor-core image head: the 512 -> 3 conv as a 1x1 GEMM into 27 (tap, channel) partial products
+// per input pixel (dsee_conv2d_tc, N = 32) and these two HBM-trivial kernels around it ------------
+// out[b,c,y,x] = tanh(bias[c] + sum_tap P[b, y+dy, x+dx, tap*3 + c])   (P zero outside the image)
+__global__ void head_gather_kernel(const float* __restrict__ P, const float* __restrict__ bias,
+                                   float* __restrict__ out, int B, int H, int W) {
+    const int64_t npix = (int64_t)B * H * W;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const int64_t b = i / ((int64_t)W * H);
+    float acc[3] = {__ldg(bias), __ldg(bias + 1), __ldg(bias + 2)};
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const float* r = P + ((b * H + yy) * W + xx) * 32 + tap * 3;
+        acc[0] += __ldg(r);
+        acc[1] += __ldg(r + 1);
+        acc[2] += __ldg(r + 2);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[((b * 3 + c) * H + y) * W + x] = tanhf(acc[c]);
+}
+
+// dP[b,y,x,tap*3+c] = dpre[b,c,y-dy,x-dx], dpre = dout * (1 - out^2); columns 27..31 zero
+__global__ void head_scatter_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                    float* __restrict__ dP, int B, int H, int W) {
+    const int64_t npix = (int64_t)B * H * W;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const int64_t b = i / ((int64_t)W * H);
+    float v[32];
+#pragma unroll
+    for (int j = 27; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y - (tap / 3 - 1), xx = x - (tap % 3 - 1);
+        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float d = 0.f;
+            if (ok) {
+                const int64_t e = ((b * 3 + c) * H + yy) * W + xx;
+                const float o = __ldg(out + e);
+                d = __ldg(dout + e) * (1.f - o * o);
+            }
+            v[tap * 3 + c] = d;
+        }
+    }
+    float4* dst = reinterpret_cast<float4*>(dP + i * 32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+
 }  // namespace dsee
 
 using namespace dsee;
@@ -930,6 +985,26 @@ extern "C" int dsee_stem_fwd(const float* x, const float* w, const float* bias, 
     int rc = require_sm100();
     if (rc) return rc;
     stem_kernel<<<B * H * W, 128, 0, (cudaStream_t)stream>>>(x, w, bias, out, B, H, W, C);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_head_gather_fwd(const float* P, const float* bias, float* out, int B, int H, int W,
+                                    void* stream) {
+    DSEE_CHECK_ARG(P && bias && out && B > 0 && H > 0 && W > 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int64_t npix = (int64_t)B * H * W;
+    head_gather_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, bias, out, B, H, W);
+    LAUNCH_END();
+}
+
+extern "C" int dsee_head_scatter_bwd(const float* dout, const float* out, float* dP, int B, int H, int W,
+                                     void* stream) {
+    DSEE_CHECK_ARG(dout && out && dP && B > 0 && H > 0 && W > 0, "bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int64_t npix = (int64_t)B * H * W;
+    head_scatter_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, (cudaStream_t)stream>>>(dout, out, dP, B, H, W);
     LAUNCH_END();
 }
 

@@ -289,7 +289,10 @@ static int wgrad_plan(int B, int H, int W, int n_total, int c_total, int* splits
     long best = -1;
     // per_image: split boundaries must coincide with image boundaries (ptiles = B * tiles per image,
     // image-major), so the split count is a multiple of B
-    const int step = per_image ? B : 1, smax = per_image ? (B > 16 ? B : 16 / B * B) : 16;
+    // (few units per split - a narrow 1x1 layer like the image head, base = 2 - may split further, up
+    // to one unit per SM)
+    const int wide = sms / base > 16 ? sms / base : 16;
+    const int step = per_image ? B : 1, smax = per_image ? (B > 16 ? B : 16 / B * B) : wide;
     for (int s = step; s <= smax && s <= ptiles; s += step) {
         const long waves = ((long)base * s + sms - 1) / sms;
         const long steps = (ptiles + s - 1) / s;

@@ -265,10 +265,14 @@ class _ResBlockFn(torch.autograd.Function):
                                 p1 == 3, save_g, out_lo=p2 == 3, out_f8=p2 == 2)
         # ---- conv_1 + shortcut ------------------------------------------------------------------
         pw1 = pre.get('pw1') or ops.prep_conv_weight(W1.contiguous(), want_lo=p2 == 3, want_f8=p2 == 2)
+        # the block in front of the image head also writes leaky_relu(out) as fp16 planes (sr.py:94)
+        act16 = getattr(gctx, 'head_act_block', None) is blk
         r = ops.conv3x3([a1], pw1, b1, residual=x, res_ups=ups,
                         noises=[(n_in, nw_in), (n_skip, nw_skip)] if noisy else (), passes=p2,
-                        want_stats=training)
+                        want_stats=training, act16=act16)
         out, stats = r if training else (r, None)
+        if act16:
+            gctx.head_act = out._dsee_act16
 
         if need_bwd:
             # (the e5m2 planes of a passes == 2 forward are not needed again)

@@ -36,17 +36,32 @@ class _HeadFn(torch.autograd.Function):
     """F.tanh(conv_img(F.leaky_relu(x, 0.2))) (sr.py:56,94-95), NHWC in, NCHW out."""
 
     @staticmethod
-    def forward(ctx, x_nhwc, w, b):
+    def forward(ctx, x_nhwc, w, b, planes=None):
         w = w.contiguous()
+        if planes is not None:
+            # tensor-core form (config.head_tc): `planes` = leaky_relu(x) as fp16 hi / lo planes from the
+            # epilogue of the kernel that produced x; x itself is not read again.  The forward GEMM
+            # always uses both planes (fp32-class: it is the last layer in front of the 1e-3 bound)
+            out = ops.head_tc(planes, w, b, passes=3)
+            ctx.planes = ops.SplitPlanes(planes.hi, planes.lo if config.passes == 3 else None)
+            ctx.save_for_backward(w, out)
+            return out
+        ctx.planes = None
         out = ops.head(x_nhwc, w, b)
         ctx.save_for_backward(x_nhwc, w, out)
         return out
 
     @staticmethod
     def backward(ctx, dout):
+        if ctx.planes is not None:
+            w, out = ctx.saved_tensors
+            planes, ctx.planes = ctx.planes, None
+            dx, amax, dw, db = ops.head_tc_bwd(planes, w, out, dout.contiguous(), passes=config.passes)
+            dx._dsee_amax = (amax, dx._version)   # the top block's grad_prep skips its max|dout| pass
+            return dx, dw, db, None
         x_nhwc, w, out = ctx.saved_tensors
         dx, dw, db = ops.head_bwd(x_nhwc, w, out, dout.contiguous())
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 class DeepSEESR(BaseNetwork):
@@ -94,6 +109,8 @@ class DeepSEESR(BaseNetwork):
         ctx = GenContext(labels, z.contiguous().float() if z is not None else None)
 
         blocks = [self.head_0, self.G_middle_0, self.G_middle_1] + [self.up_list[i] for i in range(self.n_blocks - 1)]
+        if config.head_tc and self.conv_img.weight.shape[1] % 64 == 0:
+            ctx.head_act_block = blocks[-1]   # its last kernel also writes the head's fp16 operand planes
         x = _StemFn.apply(x_downsized, self.initial.weight, self.initial.bias)
         with spectral_prepass([c for blk in blocks for c in (blk.conv_0, blk.conv_1)]):
             x, st = self.head_0.forward_nhwc(x, ctx, ups=0)
@@ -101,7 +118,7 @@ class DeepSEESR(BaseNetwork):
             x, st = self.G_middle_1.forward_nhwc(x, ctx, ups=0, stats_in=st)
             for i in range(self.n_blocks - 1):
                 x, st = self.up_list[i].forward_nhwc(x, ctx, ups=1, stats_in=st)
-        out = _HeadFn.apply(x, self.conv_img.weight, self.conv_img.bias)
+        out = _HeadFn.apply(x, self.conv_img.weight, self.conv_img.bias, getattr(ctx, 'head_act', None))
         if config.check_onehot and bad is not None:
             self._check_onehot(bad)
         return out

@@ -314,11 +314,14 @@ def _operands(sources, pw, passes, sub=None):
 
 
 def conv3x3(sources, pw, bias, residual=None, res_ups=0, noises=(), passes=3, want_stats=False,
-            act_mask=None, want_amax=False, tag="conv3x3"):
+            act_mask=None, want_amax=False, tag="conv3x3", act16=False):
     """K2: 3x3 conv + bias (+ residual through an optional folded 2x upsample, + up to two
     NoiseInjection terms ``(noise NHWC, weight[C])``) -> fp32 NHWC.
     Backward-data use: ``sources`` = gradient planes (bf16), ``pw`` prepared with transpose=True,
     bias None, ``act_mask`` = fp16 hi plane of the forward activation (LeakyReLU' folded in).
+
+    act16: also write leaky_relu(out, 0.2) as fp16 hi / lo planes (for the tensor-core image head);
+    they come back as ``out._dsee_act16`` (SplitPlanes).
 
     Returns out, or (out, stats_partial) when want_stats (partials for bn_finalize), or
     (out, amax) when want_amax (device scalar max|out|)."""
@@ -352,6 +355,11 @@ def conv3x3(sources, pw, bias, residual=None, res_ups=0, noises=(), passes=3, wa
     epi.stats_partial = stats.data_ptr() if stats is not None else 0
     amax = torch.empty(1, dtype=torch.float32, device=dev) if want_amax else None
     epi.amax_out = amax.data_ptr() if amax is not None else 0
+    if act16:
+        planes = SplitPlanes(torch.empty(out.shape, dtype=torch.float16, device=dev),
+                             torch.empty(out.shape, dtype=torch.float16, device=dev))
+        epi.act16_hi, epi.act16_lo = planes.hi.data_ptr(), planes.lo.data_ptr()
+        out._dsee_act16 = planes
     flops = 2.0 * 9 * pw.cin * pw.n_total * B * H * W  # reference-equivalent dense conv FLOPs
     _timed("%s_%dx%d" % (tag, H, W), flops,
            lambda: _lib.check(_lib.load().dsee_conv3x3_fwd(C.byref(ops), C.byref(epi), _stream())))
@@ -871,6 +879,50 @@ def head(x_nhwc, w, bias):
     return out
 
 
+def _head_w27(w):
+    """conv_img weight [3,C,3,3] -> the 1x1 form [32,C,1,1]: row tap*3 + o = w[o,:,tap], rows 27..31 zero."""
+    Cc = w.shape[1]
+    w27 = w.permute(2, 3, 0, 1).reshape(27, Cc)
+    return torch.nn.functional.pad(w27, (0, 0, 0, 5)).reshape(32, Cc, 1, 1).contiguous()
+
+
+def head_tc(a, w, bias, passes=3):
+    """The image head on the tensor cores: a = SplitPlanes of leaky_relu(x, 0.2) (NHWC [B,H,W,C], written by
+    the last conv3x3 with act16=True), w [3,C,3,3] -> tanh(conv_img(.)) fp32 NCHW [B,3,H,W].
+    One 1x1 GEMM into the 27 (tap, channel) partial products per pixel, then a 9-tap shift-add."""
+    _chk_cuda(a.hi, a.lo, w, bias)
+    B, H, W, Cc = a.hi.shape
+    if passes == 3 and a.lo is None:
+        passes = 1
+    pw = prep_conv_weight_ex(_head_w27(w), want_lo=passes == 3)
+    P = conv2d_tc(a if passes == 3 else SplitPlanes(a.hi, None), pw, None, 1, 1, 1, 0, (H, W), passes=passes,
+                  tag="head_gemm")
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=w.device)
+    _lib.check(_lib.load().dsee_head_gather_fwd(_p(P), _p(bias), _p(out), B, H, W, _stream()))
+    return out
+
+
+def head_tc_bwd(a, w, out, dout, passes=1):
+    """Backward of head_tc -> (dx fp32 NHWC [B,H,W,C] with max|dx| as a device scalar, dW [3,C,3,3], db [3])."""
+    _chk_cuda(a.hi, a.lo, w, out, dout)
+    B, H, W, Cc = a.hi.shape
+    if passes == 3 and a.lo is None:
+        passes = 1
+    want_lo = passes == 3
+    dP = torch.empty((B, H, W, 32), dtype=torch.float32, device=w.device)
+    _lib.check(_lib.load().dsee_head_scatter_bwd(_p(dout), _p(out), _p(dP), B, H, W, _stream()))
+    g, sums = grad_prep(dP, want_lo=want_lo)
+    db = sums[0][12:15].contiguous()   # centre tap: sum over all pixels of dout * (1 - out^2)
+    w27 = _head_w27(w)
+    ap = a if want_lo else SplitPlanes(a.hi, None)
+    dw27 = conv2d_tc_wgrad(g, ap, (32, Cc, 1, 1), 1, 0, passes=passes)
+    dw = dw27[:27].reshape(3, 3, 3, Cc).permute(2, 3, 0, 1).contiguous()
+    pwT = prep_conv_weight_ex(w27, want_lo, transpose=True, rows=Cc)
+    dx, amax = conv2d_tc(g, pwT, None, 1, 1, 1, 0, (H, W), passes=passes, transposed=True, tag="head_dgrad",
+                         act_mask=a.hi, want_amax=True)
+    return dx, amax, dw, db
+
+
 # ---------------------------------------------------------------------------------------------
 # style encoder / discriminator layers (fp32 NHWC)
 # ---------------------------------------------------------------------------------------------
@@ -1029,9 +1081,10 @@ def prep_conv_weight_ex(w, want_lo=True, transpose=False, rows=None):
 
 
 def conv2d_tc(a, pw, bias, KH, KW, stride, pad, out_hw, passes=3, lrelu=False, transposed=False,
-              tag="conv2d_tc"):
+              tag="conv2d_tc", act_mask=None, want_amax=False):
     """General strided conv (or its backward-data when transposed) on the tcgen05 kernel.
-    a: SplitPlanes / GradPlanes NHWC; out_hw: output (Ho, Wo)."""
+    a: SplitPlanes / GradPlanes NHWC; out_hw: output (Ho, Wo).  act_mask (stride 1): fp16 plane of the
+    forward activation, the result is multiplied by LeakyReLU'(0.2) of it.  want_amax -> (out, max|out|)."""
     _chk_cuda(a.hi, a.lo, bias)
     B, Hi, Wi, Ci = a.hi.shape
     args = _lib.Conv2dTCArgs()
@@ -1049,11 +1102,14 @@ def conv2d_tc(a, pw, bias, KH, KW, stride, pad, out_hw, passes=3, lrelu=False, t
     epi.bias = bias.data_ptr() if bias is not None else 0
     epi.out = out.data_ptr()
     epi.lrelu = int(lrelu)
+    epi.act_mask = act_mask.data_ptr() if act_mask is not None else 0
+    amax = torch.empty(1, dtype=torch.float32, device=a.hi.device) if want_amax else None
+    epi.amax_out = amax.data_ptr() if amax is not None else 0
     npix = B * (Hi * Wi if transposed else out_hw[0] * out_hw[1])
     flops = 2.0 * KH * KW * pw.cin * pw.n_total * npix
     _timed(tag, flops, lambda: _lib.check(_lib.load().dsee_conv2d_tc(C.byref(args), C.byref(epi),
                                                                      _stream())))
-    return out
+    return (out, amax) if want_amax else out
 
 
 def conv2d_tc_wgrad(dy, a, w_shape, stride, pad, passes=3):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DSEE_ABI_VERSION 3
+#define DSEE_ABI_VERSION 4
 
 /* ---- library ------------------------------------------------------------------------------ */
 int dsee_version(void);
@@ -247,6 +247,11 @@ typedef struct {
     /* when noise[i] is NULL and noise_seed[i] != 0 the noise tensor is regenerated in the kernel
      * from the counter-based generator (see dsee_noise_fill) instead of being read from HBM */
     unsigned long long noise_seed[2];
+    /* optional second output for the tensor-core image head: fp16 hi / lo planes of
+     * leaky_relu(out, 0.2) (sr.py:94: `F.leaky_relu(x, 2e-1)` in front of conv_img), NHWC
+     * [B,H,W,n_total]; act16_lo may be NULL.  dsee_conv3x3_fwd only. */
+    void* act16_hi;
+    void* act16_lo;
 } dsee_conv_epilogue;
 int dsee_conv3x3_fwd(const dsee_conv_operands* ops, const dsee_conv_epilogue* epi, void* stream);
 int dsee_conv3x3_stats_tiles(int B, int H, int W);
@@ -558,6 +563,17 @@ int dsee_stem_fwd(const float* x, const float* w, const float* bias, float* out,
  * x fp32 NHWC [B,H,W,C]; w fp32 [3,C,3,3]; out fp32 NCHW [B,3,H,W]. */
 int dsee_head_fwd(const float* x, const float* w, const float* bias, float* out, int B, int H,
                   int W, int C, void* stream);
+
+/* The same head on the tensor cores (sr.py:56,94-95): the last dsee_conv3x3_fwd of the generator writes
+ * leaky_relu(x) as fp16 planes (dsee_conv_epilogue.act16_hi/lo), dsee_conv2d_tc multiplies them by the
+ * 1x1 weight W27[tap*3+o][c] = w[o][c][tap] (27 rows padded to 32) into P fp32 NHWC [B,H,W,32], and
+ *   dsee_head_gather_fwd:  out[b,o,y,x] = tanh(bias[o] + sum_tap P[b,y+dy,x+dx,tap*3+o])  (NCHW [B,3,H,W]).
+ * Backward: dsee_head_scatter_bwd writes dP[b,y,x,tap*3+o] = (dout * (1 - out^2))[b,o,y-dy,x-dx]
+ * (fp32 NHWC [B,H,W,32], columns 27..31 zero); the weight and data gradients are then
+ * dsee_conv2d_tc_wgrad / dsee_conv2d_tc(transposed, act_mask = the hi plane) on dP's planes, and the
+ * bias gradient is the column sum of the centre tap (columns 12..14). */
+int dsee_head_gather_fwd(const float* P, const float* bias, float* out, int B, int H, int W, void* stream);
+int dsee_head_scatter_bwd(const float* dout, const float* out, float* dP, int B, int H, int W, void* stream);
 
 /* ---- style encoder / discriminator layers (fp32, NHWC) -------------------------------------- */
 /* Replaces the nn.Conv2d calls of encoder.py:84-98,142-157 and discriminator.py:84-96.

@@ -45,7 +45,7 @@ def _run_case(name, over, passes, batch=2, train=True, seed=31):
                                 d["input_semantics"], z_ref, train, noise_fn)
     from deepsee_b200 import ops
     masks = []
-    orig_mod, orig_head = ops.spade_modulate, ops.head
+    orig_mod, orig_head, orig_head_tc = ops.spade_modulate, ops.head, ops.head_tc
 
     def rec_mod(*a, **k):
         r = orig_mod(*a, **k)
@@ -56,6 +56,10 @@ def _run_case(name, over, passes, batch=2, train=True, seed=31):
     def rec_head(x, *a, **k):
         masks.append((x > 0).permute(0, 3, 1, 2).cpu())
         return orig_head(x, *a, **k)
+
+    def rec_head_tc(planes, *a, **k):   # tensor-core head: the mask its backward uses is the hi plane's sign
+        masks.append((planes.hi > 0).permute(0, 3, 1, 2).cpu())
+        return orig_head_tc(planes, *a, **k)
 
     old = config.passes
     config.passes = passes
@@ -69,13 +73,13 @@ def _run_case(name, over, passes, batch=2, train=True, seed=31):
                     n = noises[pfx + nm].permute(0, 2, 3, 1).contiguous().cuda()
                     getattr(blk, nm).sample = (lambda t: (lambda B, H, W: t))(n)
         z = z_ref.detach().clone().cuda().requires_grad_(True)
-        ops.spade_modulate, ops.head = rec_mod, rec_head
+        ops.spade_modulate, ops.head, ops.head_tc = rec_mod, rec_head, rec_head_tc
         out = G(d["image_lr"].cuda(), seg=d["input_semantics"].cuda(), z=z)
         (out * proj.cuda()).sum().backward()
         torch.cuda.synchronize()
     finally:
         config.passes = old
-        ops.spade_modulate, ops.head = orig_mod, orig_head
+        ops.spade_modulate, ops.head, ops.head_tc = orig_mod, orig_head, orig_head_tc
     keys = []
     for pfx, _, _ in O.generator_layout(o):
         keys += [pfx + "act_0", pfx + "act_1"]

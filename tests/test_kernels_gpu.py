@@ -787,3 +787,39 @@ def test_conv3x3_cta_pair_is_bit_identical(B, H, W, Cin, Cout, passes):
     # same per-tile partial sums in a different slot order (16-row tiles, two halves each)
     torch.testing.assert_close(s0.double().sum(0), s1.double().sum(0), rtol=1e-6, atol=1e-6)
     assert torch.equal(s0.sort(0).values, s1.sort(0).values)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 12, 20, 128), (1, 40, 24, 512)])
+def test_tensor_core_head_forward_and_backward(B, H, W, C):
+    """tanh(conv_img(leaky_relu(x))) as a 1x1 tcgen05 GEMM over the fp16 planes the last main conv writes
+    (dsee_conv_epilogue.act16_*) + the 9-tap shift-add, against torch (sr.py:94-95)."""
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(C + H)
+    # the planes come out of a real conv3x3 launch: x = conv(a) + bias, planes = split(leaky_relu(x))
+    a = ops.split_f16(torch.randn(B, H, W, C, generator=g).cuda())
+    wk = (torch.randn(C, C, 3, 3, generator=g) / (3 * C ** 0.5)).cuda()
+    x_nhwc = ops.conv3x3([a], ops.prep_conv_weight(wk), torch.randn(C, generator=g).cuda(), passes=3, act16=True)
+    planes = x_nhwc._dsee_act16
+    act = F.leaky_relu(x_nhwc, 0.2)
+    assert torch.equal(planes.hi, act.half())
+    torch.testing.assert_close(planes.hi.float() + planes.lo.float(), act, rtol=0, atol=2e-7 * act.abs().max().item())
+
+    xh = _nchw(x_nhwc).detach().clone().requires_grad_(True)
+    wh = (torch.randn(3, C, 3, 3, generator=g) / (3 * C ** 0.5)).cuda().requires_grad_(True)
+    bh = torch.randn(3, generator=g).cuda().requires_grad_(True)
+    dout = torch.randn(B, 3, H, W, generator=g).cuda() * 1e-4
+    ref = torch.tanh(F.conv2d(F.leaky_relu(xh, 0.2), wh, bh, padding=1))
+    ref.backward(dout)
+    out = ops.head_tc(planes, wh.detach(), bh.detach(), passes=3)
+    # fp32-class: both operand planes, fp32 accumulation in the tensor core (which truncates when it
+    # aligns addends: ~1e-5 at |pre-activation| ~ 1; the CUDA-core head it replaces reaches 2e-6)
+    assert (out - ref).abs().max().item() <= 3e-5
+    out1 = ops.head_tc(ops.SplitPlanes(planes.hi, None), wh.detach(), bh.detach(), passes=1)
+    assert (out1 - ref).abs().max().item() <= 2e-3
+    for passes, tol in ((3, 1e-4), (1, 4e-3)):
+        dx, amax, dw, db = ops.head_tc_bwd(planes, wh.detach(), out, dout, passes=passes)
+        s = xh.grad.abs().max().item()
+        assert (_nchw(dx) - xh.grad).abs().max().item() <= tol * s, passes
+        assert abs(amax.item() - dx.abs().max().item()) <= 1e-6 * s
+        assert (dw - wh.grad).abs().max().item() <= tol * wh.grad.abs().max().item(), passes
+        torch.testing.assert_close(db, bh.grad, rtol=1e-4, atol=1e-7)
