@@ -293,6 +293,42 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo
     return d;
 }
 
+// Two fp32 -> one packed fp16x2 word (a0 in the low half), round-to-nearest with saturation to
+// +-65504: a single full-rate F2FP.SATFINITE.F16.F32.PACK_AB instead of two clamps and two quarter-rate F2F.
+__device__ __forceinline__ uint32_t pack_half2_sat(float a0, float a1) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a1), "f"(a0));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t h) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&h));
+}
+// hi = fp16(a), lo = fp16(a - hi) for two values
+__device__ __forceinline__ void split_half2_sat(float a0, float a1, uint32_t& hi, uint32_t& lo) {
+    hi = pack_half2_sat(a0, a1);
+    const float2 f = unpack_half2(hi);
+    lo = pack_half2_sat(a0 - f.x, a1 - f.y);
+}
+// two fp32 -> packed e5m2x2 (a0 in the low byte), saturating
+__device__ __forceinline__ uint32_t pack_e5m2x2_sat(float a0, float a1) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(r) : "f"(a1), "f"(a0));
+    return (uint32_t)r;
+}
+
+// 32 x 32 fp32 transpose tile of one warp in shared memory (4 KB): the 16-byte granule g of row r sits at
+// granule g ^ (r & 7).  A row write (lane = row, 8 x 128 bit) and the transposed read (8 lanes share a
+// row, one granule each) are both conflict-free 128-bit accesses.
+__device__ __forceinline__ void tile_put_row(float* T, int row, const uint32_t (&v)[32]) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<uint4*>(T + row * 32 + ((g ^ (row & 7)) << 2)) =
+            make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+}
+__device__ __forceinline__ float4 tile_get4(const float* T, int row, int g) {
+    return *reinterpret_cast<const float4*>(T + row * 32 + ((g ^ (row & 7)) << 2));
+}
+
 // 2^e with amax * 2^e in [2^(top-1), 2^top): the power-of-two operand scale that keeps the hi plane
 // of an fp16 split well inside the normal range (and the lo plane out of the subnormals).
 __device__ __forceinline__ float pow2_scale_for(float amax, int top) {

@@ -53,7 +53,7 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
 constexpr int EPI_WARPS = 8;              // two per TMEM lane quarter, alternating 32-column chunks
-constexpr int EPI_TILE_FLOATS = 32 * 33;  // per-warp 32 pixel x 32 channel transpose tile (padded rows)
+constexpr int EPI_TILE_FLOATS = 32 * 32;  // per-warp 32 pixel x 32 channel transpose tile (tile_put_row / tile_get4)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
                            EPI_WARPS * EPI_TILE_FLOATS * 4;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -159,15 +159,7 @@ __device__ __forceinline__ void store_split8(__half* hi, __half* lo, const float
     // 8 consecutive channels -> one 16-byte store per plane
     uint32_t ph[4], pl[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float a0 = fminf(fmaxf(a[2 * j], -65504.f), 65504.f);
-        float a1 = fminf(fmaxf(a[2 * j + 1], -65504.f), 65504.f);
-        __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
-        __half l0 = __float2half_rn(a0 - __half2float(h0));
-        __half l1 = __float2half_rn(a1 - __half2float(h1));
-        ph[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-        pl[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-    }
+    for (int j = 0; j < 4; ++j) split_half2_sat(a[2 * j], a[2 * j + 1], ph[j], pl[j]);
     *reinterpret_cast<uint4*>(hi) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
 }
@@ -425,8 +417,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         uint32_t v[32];
                         tmem_ld32(taddr + ch * 32, v);
                         tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
+                        tile_put_row(T, lane, v);
                     }
                     __syncwarp();
                     const int nc = n + ecq * 4;  // this lane's 4 channels
@@ -465,9 +456,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         const int pi = st * 4 + er;
                         const int mm = q * 32 + pi;
                         const int yy = h0 + mm / TILE_W, xx = w0 + mm % TILE_W;
-                        const float* tp = T + pi * 33 + ecq * 4;
-                        float o[4] = {tp[0] * inv_scale + bias4.x, tp[1] * inv_scale + bias4.y,
-                                      tp[2] * inv_scale + bias4.z, tp[3] * inv_scale + bias4.w};
+                        const float4 t4 = tile_get4(T, pi, ecq);
+                        float o[4] = {t4.x * inv_scale + bias4.x, t4.y * inv_scale + bias4.y,
+                                      t4.z * inv_scale + bias4.z, t4.w * inv_scale + bias4.w};
                         if (p.lrelu) {
                             const float slope = p.lrelu == 2 ? 0.f : 0.2f;
 #pragma unroll
@@ -495,17 +486,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         *reinterpret_cast<float4*>(p.out + oe) = make_float4(o[0], o[1], o[2], o[3]);
                         if (p.out_hi) {  // leaky_relu(out) as fp16 planes for the tensor-core image head
                             uint32_t hh[2], ll[2];
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const float v0 = o[2 * e] > 0.f ? o[2 * e] : 0.2f * o[2 * e];
-                                const float v1 = o[2 * e + 1] > 0.f ? o[2 * e + 1] : 0.2f * o[2 * e + 1];
-                                const __half h0 = __float2half_rn(fminf(fmaxf(v0, -65504.f), 65504.f));
-                                const __half h1 = __float2half_rn(fminf(fmaxf(v1, -65504.f), 65504.f));
-                                const __half l0 = __float2half_rn(v0 - __half2float(h0));
-                                const __half l1 = __float2half_rn(v1 - __half2float(h1));
-                                hh[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                                ll[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-                            }
+                            split_half2_sat(fmaxf(o[0], 0.2f * o[0]), fmaxf(o[1], 0.2f * o[1]), hh[0], ll[0]);
+                            split_half2_sat(fmaxf(o[2], 0.2f * o[2]), fmaxf(o[3], 0.2f * o[3]), hh[1], ll[1]);
                             *reinterpret_cast<uint2*>(p.out_hi + oe) = make_uint2(hh[0], hh[1]);
                             if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + oe) = make_uint2(ll[0], ll[1]);
                         }
@@ -643,8 +625,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         uint32_t v[32];
                         tmem_ld32(taddr + ch * 32, v);
                         tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
+                        tile_put_row(T, lane, v);
                     }
                     __syncwarp();
                     const int cc = c + ecq * 4;  // this lane's 4 channels
@@ -698,7 +679,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         const uint32_t m16[4] = {mv.x & 0xffffu, mv.x >> 16, mv.y & 0xffffu, mv.y >> 16};
                         const uint32_t g16[4] = {gv.x & 0xffffu, gv.x >> 16, gv.y & 0xffffu, gv.y >> 16};
                         const uint32_t l16[4] = {lv.x & 0xffffu, lv.x >> 16, lv.y & 0xffffu, lv.y >> 16};
-                        const float* tp = T + pi * 33 + ecq * 4;
+                        const float4 t4 = tile_get4(T, pi, ecq);
+                        const float tp[4] = {t4.x, t4.y, t4.z, t4.w};
                         float d[4], dxh[4], dG[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -767,18 +749,17 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         uint32_t v[32];
                         tmem_ld32(taddr + ch * 32, v);
                         tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
+                        tile_put_row(T, lane, v);
                         __syncwarp();
 #pragma unroll
-                        for (int st = 0; st < 8; ++st)
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) gt[st][e] = T[(st * 4 + er) * 33 + ecq * 4 + e];
+                        for (int st = 0; st < 8; ++st) {
+                            const float4 g4 = tile_get4(T, st * 4 + er, ecq);
+                            gt[st][0] = g4.x; gt[st][1] = g4.y; gt[st][2] = g4.z; gt[st][3] = g4.w;
+                        }
                         __syncwarp();
                         tmem_ld32(taddr + 128 + ch * 32, v);
                         tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = __uint_as_float(v[j]);
+                        tile_put_row(T, lane, v);
                         __syncwarp();
                     }
                     const int cc = c + ecq * 4;  // this lane's 4 channels
@@ -816,36 +797,43 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                             xv.x += nw4.x * nv.x; xv.y += nw4.y * nv.y; xv.z += nw4.z * nv.z; xv.w += nw4.w * nv.w;
                         }
                         const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-                        const float* tp = T + pi * 33 + ecq * 4;
-                        uint32_t ah[2], al[2], gh[2], gl[2];
+                        const float4 t4 = tile_get4(T, pi, ecq);
+                        const float tp[4] = {t4.x, t4.y, t4.z, t4.w};
+                        float t[4], Gv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float xh = xs[e] * scv[e] + shv[e];
+                            Gv[e] = gt[st][e] * inv_scale + gbv[e];
+                            const float Bv = tp[e] * inv_scale + bbv[e];
+                            const float tt = xh * Gv[e] + Bv;
+                            t[e] = fmaxf(tt, 0.2f * tt);   // LeakyReLU(0.2)
+                        }
+                        // packed saturating conversions (pack_half2_sat): hi = fp16(t), lo = fp16(t - hi)
+                        uint32_t ah[2], al[2] = {0u, 0u}, gh[2] = {0u, 0u}, gl[2] = {0u, 0u};
                         uint32_t q_lo = 0u, q_hi = 0u;
-#pragma unroll
-                        for (int e2 = 0; e2 < 2; ++e2) {
-                            __half hh[2], ll[2], ghh[2], gll[2];
-#pragma unroll
-                            for (int k = 0; k < 2; ++k) {
-                                const int e = e2 * 2 + k;
-                                const float xh = xs[e] * scv[e] + shv[e];
-                                const float G = gt[st][e] * inv_scale + gbv[e];
-                                const float Bv = tp[e] * inv_scale + bbv[e];
-                                float t = xh * G + Bv;
-                                t = t > 0.f ? t : 0.2f * t;
-                                t = fminf(fmaxf(t, -65504.f), 65504.f);
-                                const float Gc = fminf(fmaxf(G, -65504.f), 65504.f);
-                                hh[k] = __float2half_rn(t);
-                                ll[k] = __float2half_rn(t - __half2float(hh[k]));
-                                if (p.out8_hi) {
-                                    q_lo |= (uint32_t)__nv_cvt_float_to_fp8((t - __half2float(hh[k])) * 256.f,
-                                                                            __NV_SATFINITE, __NV_E5M2) << (8 * e);
-                                    q_hi |= (uint32_t)__nv_cvt_float_to_fp8(t, __NV_SATFINITE, __NV_E5M2) << (8 * e);
-                                }
-                                ghh[k] = __float2half_rn(Gc);
-                                gll[k] = __float2half_rn(Gc - __half2float(ghh[k]));
+                        ah[0] = pack_half2_sat(t[0], t[1]);
+                        ah[1] = pack_half2_sat(t[2], t[3]);
+                        if (p.out_lo || p.out8_hi) {
+                            const float2 f0 = unpack_half2(ah[0]), f1 = unpack_half2(ah[1]);
+                            const float r[4] = {t[0] - f0.x, t[1] - f0.y, t[2] - f1.x, t[3] - f1.y};
+                            if (p.out_lo) {
+                                al[0] = pack_half2_sat(r[0], r[1]);
+                                al[1] = pack_half2_sat(r[2], r[3]);
                             }
-                            ah[e2] = (uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16);
-                            al[e2] = (uint32_t)__half_as_ushort(ll[0]) | ((uint32_t)__half_as_ushort(ll[1]) << 16);
-                            gh[e2] = (uint32_t)__half_as_ushort(ghh[0]) | ((uint32_t)__half_as_ushort(ghh[1]) << 16);
-                            gl[e2] = (uint32_t)__half_as_ushort(gll[0]) | ((uint32_t)__half_as_ushort(gll[1]) << 16);
+                            if (p.out8_hi) {
+                                q_lo = pack_e5m2x2_sat(r[0] * 256.f, r[1] * 256.f) |
+                                       (pack_e5m2x2_sat(r[2] * 256.f, r[3] * 256.f) << 16);
+                                q_hi = pack_e5m2x2_sat(t[0], t[1]) | (pack_e5m2x2_sat(t[2], t[3]) << 16);
+                            }
+                        }
+                        if (p.g_hi) {
+                            if (p.g_lo) {
+                                split_half2_sat(Gv[0], Gv[1], gh[0], gl[0]);
+                                split_half2_sat(Gv[2], Gv[3], gh[1], gl[1]);
+                            } else {
+                                gh[0] = pack_half2_sat(Gv[0], Gv[1]);
+                                gh[1] = pack_half2_sat(Gv[2], Gv[3]);
+                            }
                         }
                         *reinterpret_cast<uint2*>(p.out_hi + pe) = make_uint2(ah[0], ah[1]);
                         if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + pe) = make_uint2(al[0], al[1]);
