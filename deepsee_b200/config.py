@@ -79,6 +79,8 @@ class _Config:
     subpixel = os.environ.get("DSEE_SUBPIXEL", "1") != "0"
     # Training: K1 saves G = gamma + gamma_bias (fp16 planes, +1-2 B per activation element) so its
     # backward is one streaming pass instead of re-running the gamma GEMM (0 = recompute).
+    # torch.optim.Adam(fused=True): the whole update of a parameter group in one multi-tensor kernel
+    fused_adam = os.environ.get("DSEE_FUSED_ADAM", "1") != "0"
     # the image head (leaky_relu -> conv_img -> tanh, sr.py:94-95) as a 1x1 tensor-core GEMM over fp16
     # planes written by the last main conv's epilogue + a 9-tap shift-add; 0 = the fp32 CUDA-core kernels
     head_tc = os.environ.get("DSEE_HEAD_TC", "1") != "0"

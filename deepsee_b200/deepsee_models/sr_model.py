@@ -281,6 +281,8 @@ class SRModel(torch.nn.Module):
         # capturable: the step counters live on the device, so optimizer.step() can be part of a
         # captured CUDA graph (config.cuda_graphs); same arithmetic
         kw = {"capturable": True} if config.cuda_graphs else {}
+        if config.fused_adam:
+            kw["fused"] = True   # one multi-tensor kernel per parameter group instead of ~10 foreach passes
         optimizer_SR = torch.optim.Adam([{"params": SR_params},
                                          {"params": SR_params_low_lr, "lr": SR_lr / 4}],
                                         lr=SR_lr, betas=(beta1, beta2), **kw)
