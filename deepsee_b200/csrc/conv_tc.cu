@@ -469,10 +469,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         const size_t oe = pix * p.n_total + nc;
                         if (p.act_mask) {
                             const uint2 mv = mq[st];
-                            const uint32_t m16[4] = {mv.x & 0xffffu, mv.x >> 16, mv.y & 0xffffu, mv.y >> 16};
+                            // fp16 > 0 <=> the half, moved to the top of a 32-bit word, is a positive integer
+                            const bool pos[4] = {(int)(mv.x << 16) > 0, (int)(mv.x & 0xffff0000u) > 0,
+                                                 (int)(mv.y << 16) > 0, (int)(mv.y & 0xffff0000u) > 0};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)  // fp16 > 0 <=> sign clear and magnitude non-zero
-                                if (!(m16[e] != 0 && m16[e] < 0x8000u)) o[e] *= 0.2f;
+                            for (int e = 0; e < 4; ++e) o[e] *= pos[e] ? 1.f : 0.2f;
                         }
                         o[0] += rq[st].x; o[1] += rq[st].y; o[2] += rq[st].z; o[3] += rq[st].w;
                         if (p.rnoise_w[0]) {
@@ -676,19 +677,19 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         }
                         const float xh[4] = {xv.x * sc4.x + sh4.x, xv.y * sc4.y + sh4.y, xv.z * sc4.z + sh4.z,
                                              xv.w * sc4.w + sh4.w};
-                        const uint32_t m16[4] = {mv.x & 0xffffu, mv.x >> 16, mv.y & 0xffffu, mv.y >> 16};
-                        const uint32_t g16[4] = {gv.x & 0xffffu, gv.x >> 16, gv.y & 0xffffu, gv.y >> 16};
-                        const uint32_t l16[4] = {lv.x & 0xffffu, lv.x >> 16, lv.y & 0xffffu, lv.y >> 16};
+                        // fp16 > 0 <=> the half, moved to the top of a 32-bit word, is a positive integer
+                        const bool pos[4] = {(int)(mv.x << 16) > 0, (int)(mv.x & 0xffff0000u) > 0,
+                                             (int)(mv.y << 16) > 0, (int)(mv.y & 0xffff0000u) > 0};
+                        const float2 ga = unpack_half2(gv.x), gb2 = unpack_half2(gv.y);
+                        const float2 la = unpack_half2(lv.x), lb2 = unpack_half2(lv.y);
+                        const float Gs[4] = {ga.x + la.x, ga.y + la.y, gb2.x + lb2.x, gb2.y + lb2.y};
                         const float4 t4 = tile_get4(T, pi, ecq);
                         const float tp[4] = {t4.x, t4.y, t4.z, t4.w};
                         float d[4], dxh[4], dG[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float mk = (m16[e] != 0 && m16[e] < 0x8000u) ? 1.f : 0.2f;  // fp16 > 0
-                            const float G = __half2float(__ushort_as_half((unsigned short)g16[e])) +
-                                            __half2float(__ushort_as_half((unsigned short)l16[e]));
-                            d[e] = tp[e] * inv_scale * mk;
-                            dxh[e] = d[e] * G;
+                            d[e] = tp[e] * inv_scale * (pos[e] ? 1.f : 0.2f);
+                            dxh[e] = d[e] * Gs[e];
                             dG[e] = d[e] * xh[e];
                             sm[0][e] += dxh[e];
                             sm[1][e] += dxh[e] * xh[e];
@@ -702,18 +703,15 @@ conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
                         for (int half = 0; half < 2; ++half) {
                             const float* src = half ? d : dG;
                             uint32_t ph[2], plw[2];
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const float v0 = fminf(fmaxf(src[2 * e] * gscale, -65504.f), 65504.f);
-                                const float v1 = fminf(fmaxf(src[2 * e + 1] * gscale, -65504.f), 65504.f);
-                                const __half hh0 = __float2half_rn(v0), hh1 = __float2half_rn(v1);
-                                const __half ll0 = __float2half_rn(v0 - __half2float(hh0));
-                                const __half ll1 = __float2half_rn(v1 - __half2float(hh1));
-                                ph[e] = (uint32_t)__half_as_ushort(hh0) | ((uint32_t)__half_as_ushort(hh1) << 16);
-                                plw[e] = (uint32_t)__half_as_ushort(ll0) | ((uint32_t)__half_as_ushort(ll1) << 16);
+                            if (rowl) {
+                                split_half2_sat(src[0] * gscale, src[1] * gscale, ph[0], plw[0]);
+                                split_half2_sat(src[2] * gscale, src[3] * gscale, ph[1], plw[1]);
+                                *reinterpret_cast<uint2*>(rowl + half * 128) = make_uint2(plw[0], plw[1]);
+                            } else {
+                                ph[0] = pack_half2_sat(src[0] * gscale, src[1] * gscale);
+                                ph[1] = pack_half2_sat(src[2] * gscale, src[3] * gscale);
                             }
                             *reinterpret_cast<uint2*>(rowh + half * 128) = make_uint2(ph[0], ph[1]);
-                            if (rowl) *reinterpret_cast<uint2*>(rowl + half * 128) = make_uint2(plw[0], plw[1]);
                         }
                     }
                     // fold the 4 pixel sub-rows; lanes 0..7 write their 4 channels x 4 sums
