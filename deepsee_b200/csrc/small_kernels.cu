@@ -228,6 +228,31 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, __half* __restri
     if (out_lo) out_lo[o] = l;
 }
 
+// Non-transposed form, one block per filter n: w[n] (C x 9 floats, contiguous) staged in shared memory,
+// written tap-major as half2 pairs (coalesced on both sides).
+__global__ void __launch_bounds__(256) prep_weight_rows_kernel(const float* __restrict__ w,
+                                                               __half* __restrict__ out_hi,
+                                                               __half* __restrict__ out_lo, float* inv_scale,
+                                                               int C) {
+    extern __shared__ float srow[];  // [C * 9]
+    const float scale = pow2_scale_for(inv_scale[1], 14);
+    if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[0] = 1.f / scale;
+    const int n = blockIdx.x, len = C * 9;
+    const float* r = w + (size_t)n * len;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) srow[i] = r[i];
+    __syncthreads();
+    const int hp = C >> 1;
+    uint32_t* oh = reinterpret_cast<uint32_t*>(out_hi + (size_t)n * len);
+    uint32_t* ol = out_lo ? reinterpret_cast<uint32_t*>(out_lo + (size_t)n * len) : nullptr;
+    for (int e = threadIdx.x; e < 9 * hp; e += blockDim.x) {
+        const int tap = e / hp, c = 2 * (e - tap * hp);
+        uint32_t h, l;
+        split_half2_sat(srow[c * 9 + tap] * scale, srow[(c + 1) * 9 + tap] * scale, h, l);
+        oh[e] = h;
+        if (ol) ol[e] = l;
+    }
+}
+
 // fp8 companion planes of a prepared weight (dsee_conv_operands.passes == 2):
 // out8[n][tap][0][c] = e4m3(ws * 2^-8), out8[n][tap][1][c] = e4m3(ws - fp16(ws)), ws = w * 2^e
 __global__ void prep_weight_f8_kernel(const float* __restrict__ w, const float* __restrict__ inv_scale,
@@ -247,27 +272,38 @@ __global__ void prep_weight_f8_kernel(const float* __restrict__ w, const float* 
 
 // Batched modulation weight (see dsee_prep_mod_weight_batched): out[b*N + n][tap][c],
 // c < Ca: wa[n][c][tap];  Ca <= c < Ca+Ls: ws[b][n][c-Ca][tap];  else 0.
-__global__ void prep_mod_weight_batched_kernel(const float* __restrict__ wa, const float* __restrict__ ws,
-                                               __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                               float* inv_scale, int B, int N, int Ca, int Ls, int Lp) {
+// One block per output row (b, n): the row's sources (contiguous in c-major / tap-minor order) are
+// staged in shared memory with coalesced loads, then written out tap-major as half2 pairs.
+__global__ void __launch_bounds__(256) prep_mod_weight_batched_kernel(
+    const float* __restrict__ wa, const float* __restrict__ ws, __half* __restrict__ out_hi,
+    __half* __restrict__ out_lo, float* inv_scale, int B, int N, int Ca, int Ls, int Lp) {
+    extern __shared__ float srow[];  // [Ca * 9] from wa, then [Ls * 9] from ws
     const float scale = pow2_scale_for(inv_scale[1], 14);
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) inv_scale[0] = 1.f / scale;
-    const uint32_t Ct = (uint32_t)(Ca + Lp);
-    if (i >= (uint32_t)B * N * 9u * Ct) return;
-    const int c = (int)(i % Ct);
-    const int tap = (int)((i / Ct) % 9u);
-    const uint32_t row = i / (9u * Ct);
-    const int n = (int)(row % (uint32_t)N), b = (int)(row / (uint32_t)N);
-    float v = 0.f;
-    if (c < Ca)
-        v = wa[((size_t)n * Ca + c) * 9 + tap];
-    else if (c - Ca < Ls)
-        v = ws[(((size_t)b * N + n) * Ls + (c - Ca)) * 9 + tap];
-    __half h, l;
-    split_f16(v * scale, h, l);
-    out_hi[i] = h;
-    if (out_lo) out_lo[i] = l;
+    if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[0] = 1.f / scale;
+    const int row = blockIdx.x;  // b * N + n
+    const int n = row % N;
+    const int na = Ca * 9, ns = Ls * 9;
+    const float* ra = wa + (size_t)n * na;
+    const float* rs = ws + (size_t)row * ns;
+    for (int i = threadIdx.x; i < na; i += blockDim.x) srow[i] = ra[i];
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) srow[na + i] = rs[i];
+    __syncthreads();
+    const int Ct = Ca + Lp, hp = Ct >> 1;
+    uint32_t* oh = reinterpret_cast<uint32_t*>(out_hi + (size_t)row * 9 * Ct);
+    uint32_t* ol = out_lo ? reinterpret_cast<uint32_t*>(out_lo + (size_t)row * 9 * Ct) : nullptr;
+    for (int e = threadIdx.x; e < 9 * hp; e += blockDim.x) {
+        const int tap = e / hp, c = 2 * (e - tap * hp);
+        float v[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int cc = c + k;   // (Ca and Ls + Ca boundaries are even or the pair straddles into zeros)
+            v[k] = cc < Ca + Ls ? srow[cc * 9 + tap] * scale : 0.f;
+        }
+        uint32_t h, l;
+        split_half2_sat(v[0], v[1], h, l);
+        oh[e] = h;
+        if (ol) ol[e] = l;
+    }
 }
 
 // max over rows of sum_k |hi[row][k]| * inv_scale: one block per row of the prepared (scaled fp16)
@@ -828,8 +864,12 @@ extern "C" int dsee_prep_conv_weight(const float* w, void* out_hi, void* out_lo,
     if (blocks > 1024) blocks = 1024;
     amax_kernel<<<blocks, 256, 0, st>>>(w, n, inv_scale + 1);
     count_launch();
-    prep_weight_kernel<<<cdiv(n, 256), 256, 0, st>>>(w, (__half*)out_hi, (__half*)out_lo, inv_scale,
-                                                     N, C, transpose);
+    if (!transpose && C % 2 == 0 && (size_t)C * 9 * sizeof(float) <= 48 * 1024)
+        prep_weight_rows_kernel<<<N, 256, (size_t)C * 9 * sizeof(float), st>>>(w, (__half*)out_hi, (__half*)out_lo,
+                                                                              inv_scale, C);
+    else
+        prep_weight_kernel<<<cdiv(n, 256), 256, 0, st>>>(w, (__half*)out_hi, (__half*)out_lo, inv_scale,
+                                                         N, C, transpose);
     if (transpose) {
         count_launch();
         DSEE_CUDA(cudaGetLastError());
@@ -869,8 +909,8 @@ extern "C" int dsee_prep_mod_weight_batched(const float* wa, const float* ws, vo
     blocks = cdiv(ns, 256 * 8);
     amax_kernel<<<blocks > 1024 ? 1024 : blocks, 256, 0, st>>>(ws, ns, inv_scale + 1);
     count_launch();
-    prep_mod_weight_batched_kernel<<<cdiv(total, 256), 256, 0, st>>>(wa, ws, (__half*)out_hi, (__half*)out_lo,
-                                                                     inv_scale, B, N, Ca, Ls, Lp);
+    prep_mod_weight_batched_kernel<<<B * N, 256, (size_t)(Ca + Ls) * 9 * sizeof(float), st>>>(
+        wa, ws, (__half*)out_hi, (__half*)out_lo, inv_scale, B, N, Ca, Ls, Lp);
     LAUNCH_END();
 }
 

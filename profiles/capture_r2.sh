@@ -3,7 +3,7 @@
 # (numbers printed by anything running under ncu are never bench values)
 set -x
 mkdir -p gpurun_out
-K='regex:conv3x3_tc_kernel|wgrad_tc_kernel'
+K='regex:conv3x3_tc_kernel|wgrad_tc_kernel|head_gather_kernel|head_scatter_kernel'
 # 1. launch list of ONE eager training iteration of the default workload (c2)
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/r2_train_step_launches.csv \

@@ -10,6 +10,9 @@ block (c2: 256x256, batch 8; c4/c5: --S 512 --B 2), for `ncu --set full` and CUD
   dgrad+K1bwd     backward-data of a main conv fused with K1's backward
   wgrad           main-conv weight gradient;  wgrad per image: the folded modulation weight gradient
   dgrad_mod       backward-data of the modulation GEMM, N = 128 (only the mlp_shared activation)
+  head            the image head on the tensor cores: K2 writing leaky_relu(x) as fp16 planes, the 1x1 GEMM
+                  [pixels x 512] x [512 x 27], the 9-tap shift-add + tanh, and its backward (scatter, 1x1
+                  wgrad, 1x1 dgrad with the LeakyReLU' mask)
   K1 sub-pixel    (--sub) the layer above max_fm_size: four 2x2-tap GEMMs over the half-resolution actv,
                   with its backward pair (subpixel_wgrad, subpixel_dgrad)
 
@@ -116,6 +119,19 @@ def main():
         timed("sub-pixel wgrad (4 classes)", lambda: ops.subpixel_wgrad(dgb, [actv], passes=1), 2 * 9 * nh * 2 * C * px)
         timed("sub-pixel dgrad (16 taps)", lambda: ops.subpixel_dgrad(dgb, wc, passes=1, want_lo=False),
               2 * 9 * nh * 2 * C * px)
+    # ---- image head (sr.py:94-95) on the tensor cores ----------------------------------------------
+    xt = timed("K2 fp8corr + act16 planes (head producer)", lambda: ops.conv3x3(
+        [act], pw2, bias, residual=x_lo, res_ups=1,
+        noises=[(ops.NoiseSeed(5), nw), (ops.NoiseSeed(6), nw)], passes=2, want_stats=True, act16=True),
+        2 * 9 * C * C * px)[0]
+    planes = xt._dsee_act16
+    wh = rn(3, C, 3, 3) / (3 * C ** 0.5)
+    bh = torch.zeros(3, device=dev)
+    out = timed("head forward (1x1 GEMM 3-pass + gather)", lambda: ops.head_tc(planes, wh, bh, passes=3),
+                2 * 27 * C * px)
+    dout = rn(B, 3, S, S) * 1e-4
+    timed("head backward (scatter, wgrad, dgrad)", lambda: ops.head_tc_bwd(
+        ops.SplitPlanes(planes.hi, None), wh, out, dout, passes=1), 2 * 2 * 27 * C * px)
     torch.cuda.profiler.stop()
 
 
