@@ -209,23 +209,65 @@ __global__ void modulate_bwd_saved_kernel(const float* __restrict__ x, int x_ups
     }
 }
 
-// out[k][c] = sum_s partial[s][c][k] (double, fixed order). grid = (C/32, nq), block = 32 x 32.
+// out[k][c] = sum_s partial[s][c][k] (double, fixed order).  Block = 8 channels x 128 row lanes: a warp
+// reads 4 rows x (8 channels x NQ values) = whole 32 B x NQ segments with one vector load per thread,
+// folds its 4 row lanes by shuffles, and the 32 warp partials are summed in warp order.
+template <int NQ>
 __global__ void __launch_bounds__(1024)
-reduce_partials_kernel(const float* __restrict__ partial, int n, int C, int nq, float scale,
-                       float* __restrict__ out) {
-    __shared__ double sh[32][33];
-    const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl;
-    const int k = blockIdx.y;
-    double a = 0.0;
-    if (c < C)
-        for (int s = g; s < n; s += 32) a += (double)__ldg(partial + ((size_t)s * C + c) * nq + k);
-    sh[g][cl] = a;
+reduce_partials_kernel(const float* __restrict__ partial, int n, int C, float scale, float* __restrict__ out) {
+    __shared__ double sh[32][8 * NQ];
+    const int cl = threadIdx.x & 7, g = threadIdx.x >> 3;
+    const int c = blockIdx.x * 8 + cl;
+    double a[NQ];
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) a[k] = 0.0;
+    if (c < C) {
+#pragma unroll 4
+        for (int s = g; s < n; s += 128) {
+            const float* p = partial + ((size_t)s * C + c) * NQ;
+            float v[NQ];
+            if (NQ == 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+                v[0] = t.x; v[1 % NQ] = t.y; v[2 % NQ] = t.z; v[3 % NQ] = t.w;
+            } else if (NQ == 2) {
+                const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+                v[0] = t.x; v[1 % NQ] = t.y;
+            } else {
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) v[k] = __ldg(p + k);
+            }
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) a[k] += (double)v[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {   // the warp's 4 row lanes (lane bits 3, 4)
+        a[k] += __shfl_xor_sync(0xffffffffu, a[k], 8);
+        a[k] += __shfl_xor_sync(0xffffffffu, a[k], 16);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < 8)
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) sh[warp][lane * NQ + k] = a[k];
     __syncthreads();
-    if (g == 0 && c < C) {
-        double t = 0.0;
-        for (int j = 0; j < 32; ++j) t += sh[j][cl];
-        out[(size_t)k * C + c] = (float)(t * scale);
+    if (threadIdx.x < 8 * NQ) {
+        const int cc = blockIdx.x * 8 + threadIdx.x / NQ, k = threadIdx.x % NQ;
+        if (cc < C) {
+            double t = 0.0;
+            for (int j = 0; j < 32; ++j) t += sh[j][threadIdx.x];
+            out[(size_t)k * C + cc] = (float)(t * scale);
+        }
+    }
+}
+
+static void launch_reduce_partials(const float* partial, int n, int C, int nq, float scale, float* out,
+                                   cudaStream_t st) {
+    const int blocks = (C + 7) / 8;
+    switch (nq) {
+        case 1: reduce_partials_kernel<1><<<blocks, 1024, 0, st>>>(partial, n, C, scale, out); break;
+        case 2: reduce_partials_kernel<2><<<blocks, 1024, 0, st>>>(partial, n, C, scale, out); break;
+        case 3: reduce_partials_kernel<3><<<blocks, 1024, 0, st>>>(partial, n, C, scale, out); break;
+        default: reduce_partials_kernel<4><<<blocks, 1024, 0, st>>>(partial, n, C, scale, out); break;
     }
 }
 
@@ -649,8 +691,8 @@ extern "C" int dsee_reduce_partials(const float* partial, int n, int C, int nq, 
     DSEE_CHECK_ARG(partial && out && n > 0 && C > 0 && nq > 0, "bad argument");
     int rc = require_sm100();
     if (rc) return rc;
-    reduce_partials_kernel<<<dim3(cdivb(C, 32), nq), 1024, 0, (cudaStream_t)stream>>>(partial, n, C, nq,
-                                                                                    scale, out);
+    DSEE_CHECK_ARG(nq <= 4, "at most 4 quantities per channel (got %d)", nq);
+    launch_reduce_partials(partial, n, C, nq, scale, out, (cudaStream_t)stream);
     LAUNCH_END();
 }
 
@@ -735,8 +777,7 @@ extern "C" int dsee_shared_mlp_bwd(const float* dsrc, int ld, int coff, const vo
         dsrc, ld, coff, (const __half*)actv_hi, labels, B, Hl, Wl, ups, L, nh, partial);
     count_launch();
     // [blocks][rows*nh][1] -> [rows*nh]
-    reduce_partials_kernel<<<dim3(cdivb(rows * nh, 32), 1), 1024, 0, st>>>(partial, blocks, rows * nh, 1,
-                                                                            1.f, dtable_dbias);
+    launch_reduce_partials(partial, blocks, rows * nh, 1, 1.f, dtable_dbias, st);
     LAUNCH_END();
 }
 
@@ -752,8 +793,7 @@ extern "C" int dsee_stem_bwd(const float* x, const float* dy, int B, int H, int 
     stem_bwd_kernel<<<blocks, 128, 0, st>>>(x, dy, B, H, W, C, partial);
     count_launch();
     // partial [blocks][C*28] -> dw_db [C*28]  (per channel: 27 weight grads then the bias grad)
-    reduce_partials_kernel<<<dim3(cdivb(C * 28, 32), 1), 1024, 0, st>>>(partial, blocks, C * 28, 1, 1.f,
-                                                                         dw_db);
+    launch_reduce_partials(partial, blocks, C * 28, 1, 1.f, dw_db, st);
     LAUNCH_END();
 }
 
@@ -773,7 +813,6 @@ extern "C" int dsee_head_bwd(const float* x, const float* w, const float* out, c
     const int blocks = dsee_head_bwd_blocks(B, H, W);
     head_bwd_kernel<<<blocks, C / 2, 0, st>>>(x, w, out, dout, B, H, W, C, dx, partial);
     count_launch();
-    reduce_partials_kernel<<<dim3(cdivb(C * 28, 32), 1), 1024, 0, st>>>(partial, blocks, C * 28, 1, 1.f,
-                                                                         dw_db);
+    launch_reduce_partials(partial, blocks, C * 28, 1, 1.f, dw_db, st);
     LAUNCH_END();
 }

@@ -76,6 +76,30 @@ class _GraphedStep:
         self.disabled = False
         self.captured_launches = {}
 
+    def _materialize_optimizer_state(self):
+        """Creates the Adam state of every parameter that has none yet, exactly as torch.optim.Adam would
+        on its first gradient (zeros, step 0), BEFORE anything is captured.  A parameter that received no
+        gradient in the eager calls (the style-noise weights when both coin flips came out 'clean', the
+        branch of the encoder the flips skipped) would otherwise get its state allocated from the graph's
+        private pool in the middle of a capture: that block is scratch memory of the graphs captured
+        earlier into the same pool, whose replays then overwrite the moments (NaN parameters some
+        iterations later, depending on the order of the coin flips)."""
+        opt = self.optimizer
+        with torch.cuda.stream(self.mgr._train_stream):
+            for group in opt.param_groups:
+                for p in group['params']:
+                    if not p.requires_grad or len(opt.state.get(p, {})) != 0:
+                        continue
+                    st = opt.state[p]
+                    on_device = group.get('capturable') or group.get('fused')
+                    st['step'] = (torch.zeros((), dtype=torch.get_default_dtype(), device=p.device) if on_device
+                                  else torch.tensor(0.0, dtype=torch.get_default_dtype()))
+                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    if group.get('amsgrad'):
+                        st['max_exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        self.mgr._train_stream.synchronize()
+
     def _lr_signature(self):
         return tuple(float(g['lr']) for g in self.optimizer.param_groups)
 
@@ -153,6 +177,8 @@ class _GraphedStep:
         key = tuple(v < 0.5 for v in draws)
         static = self._stage(data)
         if key not in self.graphs:
+            if not self.graphs:
+                self._materialize_optimizer_state()
             replay = _ReplayRandom(draws, real)
             random.random = replay
             saved_check, saved_timer = config.check_onehot, ops.KernelTimer.active
