@@ -370,6 +370,9 @@ def main():
         buffers (e2e).  Returns the result dict."""
         cfg = CONFIGS[cfg_key]
         torch.manual_seed(0)                         # same random-init weights on every rank
+        import random
+        random.seed(1234)                            # the encoder coin flips (sr_model.py:616,643): same on every
+                                                     # rank (they must agree) and the same in every run
         o = make_opt(cfg["name"], isTrain=True, gpu_ids=[local], batchSize=b)
         mgr = TrainerManager(o)                      # random-init weights of the named architecture
         model = mgr.sr_model
@@ -508,6 +511,9 @@ def main():
                 last = e2e_iteration()
             torch.cuda.synchronize()
             e2e_s = max_over_ranks(time.perf_counter() - t0)
+            import math
+            if not all(math.isfinite(v) and abs(v) < 1e6 for v in last.values()):
+                raise RuntimeError("bench: the training iteration diverged (losses %r)" % (last,))
             e2e = {"value": b * world * steps / e2e_s, "unit": "images/sec",
                    "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())) * (2 if train else 1),
                    "d2h_bytes_per_step": 4 * len(last), "last_losses": last}
