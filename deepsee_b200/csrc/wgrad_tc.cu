@@ -20,25 +20,32 @@
 #include "common.cuh"
 #include "../../include/deepsee_b200.h"
 #include "launch_count.h"
+#include <stdlib.h>
 #include <string.h>
 
 namespace dsee {
 
 constexpr int WG_M = 128;        // dY channels per unit
 constexpr int WG_NMAX = 256;     // activation channels per unit
-#ifndef DSEE_WG_TH
-#define DSEE_WG_TH 8
-#endif
-#ifndef DSEE_WG_STAGES
-#define DSEE_WG_STAGES 2
-#endif
-constexpr int WG_TW = 16, WG_TH = DSEE_WG_TH;
-constexpr int WG_KPIX = WG_TW * WG_TH;                         // pixels per K step
-constexpr int WG_BOX_BYTES = WG_KPIX * 64 * 2;                 // pixel rows x 64 ch
-constexpr int WG_STAGE_BYTES = (WG_M / 64 + WG_NMAX / 64) * WG_BOX_BYTES;
-constexpr int WG_STAGES = DSEE_WG_STAGES;
-constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
-constexpr int WG_THREADS = 192;
+constexpr int WG_TW = 16;
+constexpr int WG_PRODUCERS = 3;   // warp 0 and warps 6, 7: one elected thread each issues a third of a stage's boxes
+constexpr int WG_THREADS = 192 + 32 * (WG_PRODUCERS - 1);
+// Two forms of the kernel:
+//   <TH 8, 2 stages, MT 1>  K step = 8 x 16 pixels, one 128-channel dY tile per unit: 6 boxes of 16 KB per
+//                           stage (96 KB), accumulators double-buffered in TMEM;
+//   <TH 4, 3 stages, MT 2>  K step = 4 x 16 pixels, TWO dY tiles per unit sharing the activation boxes
+//                           (two MMA groups per K step into TMEM columns [0,256) / [256,512)): 8 boxes of
+//                           8 KB per stage (64 KB) for the same MMA time - 2/3 of the L2 -> SM bytes per
+//                           FLOP, one more stage in flight.  The unit's accumulators fill TMEM, so its
+//                           epilogue is not overlapped (a unit's main loop is hundreds of K steps).
+template <int TH, int STAGES, int MT>
+struct WgCfg {
+    static constexpr int KPIX = WG_TW * TH;                      // pixels per K step
+    static constexpr int BOX_BYTES = KPIX * 64 * 2;              // pixel rows x 64 ch
+    static constexpr int NBOX_D = MT * WG_M / 64;                // dY boxes per stage
+    static constexpr int STAGE_BYTES = (NBOX_D + WG_NMAX / 64) * BOX_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+};
 
 struct alignas(64) WgradParams {
     CUtensorMap tmD[2];  // dY planes (hi, lo)
@@ -60,10 +67,10 @@ struct alignas(64) WgradParams {
 };
 
 // MN-major, 128B-swizzled operand descriptor (see header comment).
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t box_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((WG_BOX_BYTES >> 4) & 0x3FFF) << 16;  // LBO: next 64-channel block
+    d |= (uint64_t)((box_bytes >> 4) & 0x3FFF) << 16;  // LBO: next 64-channel block
     d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;          // SBO: next 8 pixel rows
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
@@ -80,7 +87,11 @@ __device__ __forceinline__ void wg_decode(const WgradParams& p, int unit, int& n
     split = unit / p.n_tiles;
 }
 
+template <int TH, int STAGES, int MT>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+    using Cfg = WgCfg<TH, STAGES, MT>;
+    constexpr int WG_STAGES = STAGES, WG_STAGE_BYTES = Cfg::STAGE_BYTES, WG_BOX_BYTES = Cfg::BOX_BYTES;
+    constexpr int WG_KPIX = Cfg::KPIX, WG_TH = TH, NBOX_D = Cfg::NBOX_D;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~uintptr_t(1023));
@@ -115,9 +126,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const uint32_t tmem_base = *tmem_slot;
 
     const int nboxA = p.n_cols / 64;
-    const uint32_t stage_tx = (uint32_t)(WG_M / 64 + nboxA) * WG_BOX_BYTES;
+    const uint32_t stage_tx = (uint32_t)(NBOX_D + nboxA) * WG_BOX_BYTES;
 
-    if (warp == 0) {
+    if (warp == 0 || warp >= 6) {
+        // TMA producers.  A stage is 2 + nboxA boxes of 64 channels; one thread issuing all of them needs
+        // ~1100 cycles of address arithmetic and uniform-register moves per stage - as long as the MMAs
+        // of the stage (ncu source view: the MMA warp waited for data a third of the time).  Three
+        // elected threads in three warps issue every third box each; producer 0 posts the byte count.
+        const int prod = warp == 0 ? 0 : warp - 5;
         if (lane == 0) {
             uint32_t it = 0;
             for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
@@ -126,10 +142,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                 const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
                 const int pt0 = (int)((int64_t)p.ptiles * split / p.splits);
                 const int pt1 = (int)((int64_t)p.ptiles * (split + 1) / p.splits);
+                int tw = pt0 % p.tiles_w, th = (pt0 / p.tiles_w) % p.tiles_h, b = pt0 / (p.tiles_w * p.tiles_h);
                 for (int pt = pt0; pt < pt1; ++pt) {
-                    const int tw = pt % p.tiles_w;
-                    const int th = (pt / p.tiles_w) % p.tiles_h;
-                    const int b = pt / (p.tiles_w * p.tiles_h);
                     const int h0 = th * WG_TH, w0 = tw * WG_TW;
                     for (int pass = 0; pass < p.passes; ++pass, ++it) {
                         const int pd = (pass == 1) ? 1 : 0;  // dY plane
@@ -137,19 +151,31 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                         const int s = it % WG_STAGES;
                         const uint32_t ph = (it / WG_STAGES) & 1;
                         mbar_wait(&empty_bar[s], ph ^ 1);
-                        mbar_expect_tx(&full_bar[s], stage_tx);
+                        if (prod == 0) mbar_expect_tx(&full_bar[s], stage_tx);
                         uint8_t* sd = smem + s * WG_STAGE_BYTES;
-                        uint8_t* sa = sd + (WG_M / 64) * WG_BOX_BYTES;
-                        for (int i = 0; i < WG_M / 64; ++i)
+                        uint8_t* sa = sd + NBOX_D * WG_BOX_BYTES;
+#pragma unroll
+                        for (int i = 0; i < NBOX_D; ++i) {
+                            if (i % WG_PRODUCERS != prod) continue;
                             tma_load_4d(&p.tmD[pd], &full_bar[s], sd + i * WG_BOX_BYTES,
-                                        nt * WG_M + i * 64, w0 * p.d_step + p.d_offx,
+                                        nt * (WG_M * MT) + i * 64, w0 * p.d_step + p.d_offx,
                                         h0 * p.d_step + p.d_offy, b);
-                        for (int i = 0; i < nboxA; ++i) {
+                        }
+#pragma unroll
+                        for (int i = 0; i < WG_NMAX / 64; ++i) {
+                            if (i >= nboxA || (i + NBOX_D) % WG_PRODUCERS != prod) continue;
                             const int c = ct * WG_NMAX + i * 64;
                             const bool second = c >= p.c_split;
                             tma_load_4d(second ? &p.tmA2[pa] : &p.tmA[pa], &full_bar[s],
                                         sa + i * WG_BOX_BYTES, second ? c - p.c_split : c,
                                         w0 * p.a_step + dx, h0 * p.a_step + dy, b);
+                        }
+                    }
+                    if (++tw == p.tiles_w) {
+                        tw = 0;
+                        if (++th == p.tiles_h) {
+                            th = 0;
+                            ++b;
                         }
                     }
                 }
@@ -165,8 +191,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                 const int pt0 = (int)((int64_t)p.ptiles * split / p.splits);
                 const int pt1 = (int)((int64_t)p.ptiles * (split + 1) / p.splits);
                 const int kiters = (pt1 - pt0) * p.passes;
-                const int as = lu & 1;
-                const uint32_t aph = (lu >> 1) & 1;
+                // MT == 1: two accumulator stages of 256 columns; MT == 2: the unit's two tiles fill TMEM
+                const int as = MT == 2 ? 0 : (lu & 1);
+                const uint32_t aph = MT == 2 ? (lu & 1) : ((lu >> 1) & 1);
                 mbar_wait(&tempty_bar[as], aph ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * WG_NMAX;
@@ -176,13 +203,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sd = smem_u32(smem + s * WG_STAGE_BYTES);
-                    const uint32_t sa = sd + (WG_M / 64) * WG_BOX_BYTES;
-                    const uint64_t da = umma_desc_mn_sw128(sd);
-                    const uint64_t db = umma_desc_mn_sw128(sa);
+                    const uint32_t sa = sd + NBOX_D * WG_BOX_BYTES;
+                    const uint64_t db = umma_desc_mn_sw128(sa, WG_BOX_BYTES);
 #pragma unroll
-                    for (int k = 0; k < WG_KPIX / 16; ++k) {
-                        // advance 16 pixel rows = 2048 B = 128 (16 B units) along K
-                        umma_f16(tmem_d, da + 128 * k, db + 128 * k, p.idesc, (kit | k) != 0);
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint64_t da = umma_desc_mn_sw128(sd + mt * (WG_M / 64) * WG_BOX_BYTES, WG_BOX_BYTES);
+#pragma unroll
+                        for (int k = 0; k < WG_KPIX / 16; ++k) {
+                            // advance 16 pixel rows = 2048 B = 128 (16 B units) along K
+                            umma_f16(tmem_d + mt * WG_NMAX, da + 128 * k, db + 128 * k, p.idesc, (kit | k) != 0);
+                        }
                     }
                     umma_commit(&empty_bar[s]);
                 }
@@ -193,7 +223,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                 umma_commit(&tfull_bar[as]);
             }
         }
-    } else {
+    } else if (warp < 6) {
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const float scale = (p.inv_scale[0] ? __ldg(p.inv_scale[0]) : 1.f) *
@@ -205,28 +235,31 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             const int pt0 = (int)((int64_t)p.ptiles * split / p.splits);
             const int pt1 = (int)((int64_t)p.ptiles * (split + 1) / p.splits);
             const bool empty = pt1 <= pt0;
-            const int as = lu & 1;
-            const uint32_t aph = (lu >> 1) & 1;
+            const int as = MT == 2 ? 0 : (lu & 1);
+            const uint32_t aph = MT == 2 ? (lu & 1) : ((lu >> 1) & 1);
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * WG_NMAX;
-            const int n = nt * WG_M + m;
-            float* orow = p.partial + (((size_t)split * p.n_total + n) * p.ntaps + tap) * p.c_total +
-                          (size_t)ct * WG_NMAX;
 #pragma unroll 1
-            for (int ch = 0; ch < p.n_cols / 32; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(taddr + ch * 32, v);
-                tmem_ld_wait();
-                if (n < p.n_total) {
+            for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as + mt) * WG_NMAX;
+                const int n = (nt * MT + mt) * WG_M + m;
+                float* orow = p.partial + (((size_t)split * p.n_total + n) * p.ntaps + tap) * p.c_total +
+                              (size_t)ct * WG_NMAX;
+#pragma unroll 1
+                for (int ch = 0; ch < p.n_cols / 32; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + ch * 32, v);
+                    tmem_ld_wait();
+                    if (n < p.n_total) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 o = make_float4(__uint_as_float(v[4 * j]) * scale,
-                                               __uint_as_float(v[4 * j + 1]) * scale,
-                                               __uint_as_float(v[4 * j + 2]) * scale,
-                                               __uint_as_float(v[4 * j + 3]) * scale);
-                        if (empty) o = make_float4(0.f, 0.f, 0.f, 0.f);
-                        reinterpret_cast<float4*>(orow + ch * 32)[j] = o;
+                        for (int j = 0; j < 8; ++j) {
+                            float4 o = make_float4(__uint_as_float(v[4 * j]) * scale,
+                                                   __uint_as_float(v[4 * j + 1]) * scale,
+                                                   __uint_as_float(v[4 * j + 2]) * scale,
+                                                   __uint_as_float(v[4 * j + 3]) * scale);
+                            if (empty) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                            reinterpret_cast<float4*>(orow + ch * 32)[j] = o;
+                        }
                     }
                 }
             }
@@ -273,10 +306,22 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 
 using namespace dsee;
 
+// dY tiles per unit: two whenever the dY channels come in pairs of 128-channel tiles (see WgCfg)
+static int g_wgrad_pairs = -1;
+static int wgrad_mt(int n_total) {
+    if (g_wgrad_pairs < 0) {
+        const char* e = getenv("DSEE_WGRAD_PAIRS");
+        g_wgrad_pairs = (e && e[0] == '0') ? 0 : 1;
+    }
+    return (g_wgrad_pairs && n_total % (2 * WG_M) == 0) ? 2 : 1;
+}
+static int wgrad_th(int mt) { return mt == 2 ? 4 : 8; }
+
 static int wgrad_plan(int B, int H, int W, int n_total, int c_total, int* splits_out, int T = 9,
                       bool per_image = false) {
-    const int ptiles = B * ((H + WG_TH - 1) / WG_TH) * ((W + WG_TW - 1) / WG_TW);
-    const int n_tiles = (n_total + WG_M - 1) / WG_M;
+    const int mt = wgrad_mt(n_total), th_ = wgrad_th(mt);
+    const int ptiles = B * ((H + th_ - 1) / th_) * ((W + WG_TW - 1) / WG_TW);
+    const int n_tiles = (n_total + WG_M * mt - 1) / (WG_M * mt);
     const int c_tiles = (c_total + WG_NMAX - 1) / WG_NMAX;
     const int base = n_tiles * T * c_tiles;
     // Pixel splits: units = base * splits run as ceil(units / 148) waves of ceil(ptiles / splits)
@@ -332,7 +377,8 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
     p.H = H;
     p.W = W;
     p.tiles_w = (W + WG_TW - 1) / WG_TW;
-    p.tiles_h = (H + WG_TH - 1) / WG_TH;
+    const int mt = wgrad_mt(n_total), th_ = wgrad_th(mt);
+    p.tiles_h = (H + th_ - 1) / th_;
     p.n_total = n_total;
     p.c_total = c_total;
     p.c_split = a2_channels > 0 ? a_channels : c_total;
@@ -346,7 +392,7 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
         p.tap_dy[t] = (int8_t)(t / KW - (sub ? 1 - sub_py : pad));
         p.tap_dx[t] = (int8_t)(t % KW - (sub ? 1 - sub_px : pad));
     }
-    p.n_tiles = (n_total + WG_M - 1) / WG_M;
+    p.n_tiles = (n_total + WG_M * mt - 1) / (WG_M * mt);
     p.c_tiles = (c_total + WG_NMAX - 1) / WG_NMAX;
     p.n_cols = c_total < WG_NMAX ? c_total : WG_NMAX;
     p.ptiles = wgrad_plan(B, H, W, n_total, c_total, &p.splits, T, per_image);
@@ -358,9 +404,9 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
     // kind::f16, fp32 accumulate, both operands MN-major, M = 128, N = n_cols
     p.idesc = (1u << 4) | ((uint32_t)dtype << 7) | ((uint32_t)dtype << 10) | (1u << 15) | (1u << 16) |
               ((uint32_t)(p.n_cols >> 3) << 17) | ((uint32_t)(WG_M >> 4) << 24);
-    uint32_t boxd[4] = {64, (uint32_t)(WG_TW * p.d_step), (uint32_t)(WG_TH * p.d_step), 1};
+    uint32_t boxd[4] = {64, (uint32_t)(WG_TW * p.d_step), (uint32_t)(th_ * p.d_step), 1};
     uint32_t esd[4] = {1, (uint32_t)p.d_step, (uint32_t)p.d_step, 1};
-    uint32_t boxa[4] = {64, (uint32_t)(WG_TW * stride), (uint32_t)(WG_TH * stride), 1};
+    uint32_t boxa[4] = {64, (uint32_t)(WG_TW * stride), (uint32_t)(th_ * stride), 1};
     uint32_t esa[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     for (int pl = 0; pl < 2; ++pl) {
         const void* d = pl ? dy_lo : dy_hi;
@@ -394,19 +440,26 @@ static int wgrad_impl(const void* dy_hi, const void* dy_lo, const float* dy_inv_
             p.tmA2[pl] = p.tmA[pl];
         }
     }
+    using Cfg1 = WgCfg<8, 2, 1>;
+    using Cfg2 = WgCfg<4, 3, 2>;
     static bool configured[64] = {false};
     int dev = 0;
     DSEE_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !configured[dev]) {
-        DSEE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       WG_SMEM));
+        DSEE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<8, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg1::SMEM));
+        DSEE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<4, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg2::SMEM));
         configured[dev] = true;
     }
     int sms = 0;
     DSEE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = p.num_units < sms ? p.num_units : sms;
     cudaStream_t st = (cudaStream_t)stream;
-    wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM, st>>>(p);
+    if (mt == 2)
+        wgrad_tc_kernel<4, 3, 2><<<grid, WG_THREADS, Cfg2::SMEM, st>>>(p);
+    else
+        wgrad_tc_kernel<8, 2, 1><<<grid, WG_THREADS, Cfg1::SMEM, st>>>(p);
     count_launch();
     DSEE_CUDA(cudaGetLastError());
     const int64_t total = (int64_t)n_total * T * c_total;
