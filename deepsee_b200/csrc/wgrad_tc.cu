@@ -10,10 +10,12 @@
 // column blocks one box = 16 KB apart along M/N).  The shifted box of the activation supplies the
 // tap offset and, through TMA out-of-bounds zero fill, the convolution's zero padding.
 //
-// Work unit = (128 dY-channels) x (tap) x (<=256 A-channels) x (pixel split); the K loop walks the
-// split's pixel tiles.  Units are spread over persistent CTAs; each writes its fp32 accumulator
-// tile to a per-split partial buffer that a small kernel reduces in a fixed order (deterministic,
-// no atomics).  Same warp roles / mbarrier pipeline as conv_tc.cu.
+// Work unit = (128 or 2 x 128 dY-channels) x (tap) x (<=256 A-channels) x (pixel split); the K loop walks
+// the split's pixel tiles.  Units are spread over persistent CTAs; each writes its fp32 accumulator
+// tile(s) to a per-split partial buffer that a small kernel reduces in a fixed order (deterministic,
+// no atomics).  Same warp roles / mbarrier pipeline as conv_tc.cu, with three TMA-issuing warps.
+// The two-tile form (WgCfg<4, 3, 2>, used whenever n_total is a multiple of 256) exists because the
+// one-tile form is bound by the L2 -> SM feed: see WgCfg.
 //
 // Reference semantics: autograd of nn.Conv2d at architecture.py:98,122 and
 // normalization.py:116-117,198-201,283-284.
