@@ -151,7 +151,7 @@ def load():
         "dsee_onehot_from_labels": [vp, vp, i, i, i, i, vp, vp],
         "dsee_labels_from_onehot": [vp, vp, i, i, i, i, vp, vp],
         "dsee_resize_labels": [vp, vp, i, i, i, i, i, vp],
-        "dsee_shared_mlp_fwd": [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp],
+        "dsee_shared_mlp_fwd": [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, vp],
         "dsee_style_gather_fwd": [vp, vp, vp, vp, i, i, i, i, i, vp],
         "dsee_prep_conv_weight": [vp, vp, vp, vp, i, i, i, vp],
         "dsee_prep_conv_weight_f8": [vp, vp, vp, i, i, vp],

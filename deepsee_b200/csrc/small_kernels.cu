@@ -133,10 +133,28 @@ __global__ void resize_labels_kernel(const uint8_t* __restrict__ in, uint8_t* __
 // conditional-norm operand builders
 // ------------------------------------------------------------------------------------------------
 // actv = relu(bias + sum_tap table[tap][label(tap)]) ; thread = (pixel, 4 hidden channels)
+// rows[l][o] = bias[o] + sum_{tap = 0..8} table[tap][l][o], added in the order the gather kernel uses:
+// the pre-activation of a pixel whose whole 3x3 window carries label l (the interior of a region)
+__global__ void shared_mlp_rows_kernel(const float* __restrict__ table, const float* __restrict__ bias,
+                                       float* __restrict__ rows, int L, int nh) {
+    const int l = blockIdx.x, g = threadIdx.x;  // g: group of 4 channels
+    if (g >= (nh >> 2)) return;
+    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + g);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(table + ((size_t)tap * L + l) * nh) + g);
+        acc.x += t.x;
+        acc.y += t.y;
+        acc.z += t.z;
+        acc.w += t.w;
+    }
+    reinterpret_cast<float4*>(rows + (size_t)l * nh)[g] = acc;
+}
+
 __global__ void shared_mlp_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ table,
-                                  const float* __restrict__ bias, __half* __restrict__ out_hi,
-                                  __half* __restrict__ out_lo, int B, int Hl, int Wl, int ups, int L,
-                                  int nh) {
+                                  const float* __restrict__ bias, const float* __restrict__ rows,
+                                  __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B, int Hl,
+                                  int Wl, int ups, int L, int nh) {
     // 32-bit index arithmetic (the host wrapper checks the element count): five 64-bit div/mod per
     // thread cost more than the 8 bytes the thread produces
     const uint32_t groups = (uint32_t)nh >> 2;
@@ -151,17 +169,32 @@ __global__ void shared_mlp_kernel(const uint8_t* __restrict__ labels, const floa
     const int b = (int)(t2 / (uint32_t)H);
     const int yl = y >> ups, xl = x >> ups;
     const uint8_t* lb = labels + (size_t)b * Hl * Wl;
-    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + g);
+    // the window's nine labels (255 = outside the image: zero padding)
+    int lab[9];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-        int yy = yl + tap / 3 - 1, xx = xl + tap % 3 - 1;
-        if (yy < 0 || yy >= Hl || xx < 0 || xx >= Wl) continue;  // zero padding
-        int l = lb[yy * Wl + xx];
-        float4 t = __ldg(reinterpret_cast<const float4*>(table + ((size_t)tap * L + l) * nh) + g);
-        acc.x += t.x;
-        acc.y += t.y;
-        acc.z += t.z;
-        acc.w += t.w;
+        const int yy = yl + tap / 3 - 1, xx = xl + tap % 3 - 1;
+        lab[tap] = (yy < 0 || yy >= Hl || xx < 0 || xx >= Wl) ? 255 : (int)lb[yy * Wl + xx];
+    }
+    bool uniform = rows != nullptr;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) uniform = uniform && lab[tap] == lab[4];
+    float4 acc;
+    if (uniform) {
+        // interior of a region (most pixels of a face parse): one precomputed row instead of nine - the same
+        // fp32 additions in the same order, so the result is bit-identical to the general path
+        acc = __ldg(reinterpret_cast<const float4*>(rows + (size_t)lab[4] * nh) + g);
+    } else {
+        acc = __ldg(reinterpret_cast<const float4*>(bias) + g);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            if (lab[tap] == 255) continue;  // zero padding
+            float4 t = __ldg(reinterpret_cast<const float4*>(table + ((size_t)tap * L + lab[tap]) * nh) + g);
+            acc.x += t.x;
+            acc.y += t.y;
+            acc.z += t.z;
+            acc.w += t.w;
+        }
     }
     float a[4] = {fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f)};
     __half h[4], l4[4];
@@ -825,16 +858,22 @@ extern "C" int dsee_resize_labels(const uint8_t* in, uint8_t* out, int B, int Hi
 
 extern "C" int dsee_shared_mlp_fwd(const uint8_t* labels, const float* table, const float* bias,
                                    void* out_hi, void* out_lo, int B, int Hl, int Wl, int ups, int L,
-                                   int nh, void* stream) {
+                                   int nh, float* uniform_rows, void* stream) {
     DSEE_CHECK_ARG(labels && table && bias && out_hi, "NULL pointer");
-    DSEE_CHECK_ARG(B > 0 && Hl > 0 && Wl > 0 && (ups == 0 || ups == 1) && L > 0 && nh % 4 == 0,
+    DSEE_CHECK_ARG(B > 0 && Hl > 0 && Wl > 0 && (ups == 0 || ups == 1) && L > 0 && L < 255 && nh % 4 == 0 &&
+                       nh <= 4096,
                    "bad shape");
     int rc = require_sm100();
     if (rc) return rc;
     int64_t n = (int64_t)B * (Hl << ups) * (Wl << ups) * (nh / 4);
     DSEE_CHECK_ARG(n < ((int64_t)1 << 31), "more than 2^31 output quads");
-    shared_mlp_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        labels, table, bias, (__half*)out_hi, (__half*)out_lo, B, Hl, Wl, ups, L, nh);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (uniform_rows) {
+        shared_mlp_rows_kernel<<<L, (nh / 4 + 31) / 32 * 32, 0, st>>>(table, bias, uniform_rows, L, nh);
+        count_launch();
+    }
+    shared_mlp_kernel<<<cdiv(n, 256), 256, 0, st>>>(labels, table, bias, uniform_rows, (__half*)out_hi,
+                                                   (__half*)out_lo, B, Hl, Wl, ups, L, nh);
     LAUNCH_END();
 }
 

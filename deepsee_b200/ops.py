@@ -183,16 +183,18 @@ def resize_labels(labels, Hout, Wout):
 # ---------------------------------------------------------------------------------------------
 # operand builders
 # ---------------------------------------------------------------------------------------------
-def shared_mlp(labels, table, bias, ups=0, want_lo=True):
-    """relu(conv3x3(onehot(labels), W) + b) as a table gather. table fp32 [9,L,nh]."""
+def shared_mlp(labels, table, bias, ups=0, want_lo=True, uniform_rows=True):
+    """relu(conv3x3(onehot(labels), W) + b) as a table gather. table fp32 [9,L,nh].
+    uniform_rows: pixels whose 3x3 window carries a single label read one precomputed row (bit-identical)."""
     _chk_cuda(labels, table, bias)
     B, Hl, Wl = labels.shape
     _, L, nh = table.shape
     H, W = Hl << ups, Wl << ups
     hi = torch.empty((B, H, W, nh), dtype=torch.float16, device=labels.device)
     lo = torch.empty_like(hi) if want_lo else None
+    rows = torch.empty((L, nh), dtype=torch.float32, device=labels.device) if uniform_rows else None
     _lib.check(_lib.load().dsee_shared_mlp_fwd(_p(labels), _p(table), _p(bias), _p(hi), _p(lo), B, Hl,
-                                               Wl, ups, L, nh, _stream()))
+                                               Wl, ups, L, nh, _p(rows), _stream()))
     return SplitPlanes(hi, lo)
 
 

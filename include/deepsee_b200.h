@@ -69,10 +69,14 @@ int dsee_noise_fill(unsigned long long seed, float* out, int64_t n, void* stream
  *   (yl,xl) = (y >> ups, x >> ups)   [ups=1 reproduces F.interpolate(actv, size=out_size),
  *   normalization.py:188-189, for feature maps larger than max_fm_size]
  * table fp32 [9][L][nh] (= weight[o][l][ky][kx] transposed), labels uint8 [B,Hl,Wl],
- * out_hi/out_lo fp16 NHWC [B, Hl<<ups, Wl<<ups, nh]. out_lo may be NULL. */
+ * out_hi/out_lo fp16 NHWC [B, Hl<<ups, Wl<<ups, nh]. out_lo may be NULL.
+ * uniform_rows: optional scratch fp32 [L][nh]; when given, the call first fills it with the pre-activation
+ * of a uniform 3x3 window per label (same additions, same order) and pixels whose window carries one
+ * label - the interior of every region of a parse map - read one row instead of nine.  Bit-identical
+ * results with or without it. */
 int dsee_shared_mlp_fwd(const uint8_t* labels, const float* table, const float* bias,
                         void* out_hi, void* out_lo, int B, int Hl, int Wl, int ups, int L, int nh,
-                        void* stream);
+                        float* uniform_rows, void* stream);
 /* Replaces style_map = (style[:,:,:,None,None] * seg[:,:,None]).sum(1)
  * (normalization.py:182-185 / 269-272): out[b,y,x,:] = style[b, labels[b,y,x], :].
  * style fp32 [B,L,d]; out_hi/out_lo fp16 NHWC [B,H,W,d]. */

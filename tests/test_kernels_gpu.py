@@ -823,3 +823,28 @@ def test_tensor_core_head_forward_and_backward(B, H, W, C):
         assert abs(amax.item() - dx.abs().max().item()) <= 1e-6 * s
         assert (dw - wh.grad).abs().max().item() <= tol * wh.grad.abs().max().item(), passes
         torch.testing.assert_close(db, bh.grad, rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("ups", [0, 1])
+def test_shared_mlp_uniform_window_fast_path_is_bit_identical(ups):
+    """Piecewise-constant label maps (a face parse): pixels whose 3x3 window carries one label take the
+    precomputed-row path of dsee_shared_mlp_fwd; planes must equal the nine-tap gather bit for bit."""
+    from deepsee_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(11)
+    B, L, nh, S = 2, 19, 128, 48
+    grid = torch.randint(0, L, (B, 1, 6, 6), generator=g)
+    lab = F.interpolate(grid.float(), size=(S, S), mode="nearest").long().cuda()   # 8 x 8 blocks
+    lab[0, 0, 5, 7] = (lab[0, 0, 5, 7] + 1) % L                                    # and an isolated pixel
+    w = torch.randn(nh, L, 3, 3, generator=g).cuda() * 0.2
+    b = torch.randn(nh, generator=g).cuda() * 0.1
+    table = w.permute(2, 3, 1, 0).reshape(9, L, nh).contiguous()
+    labels = lab[:, 0].to(torch.uint8).contiguous()
+    fast = ops.shared_mlp(labels, table, b, ups=ups, uniform_rows=True)
+    slow = ops.shared_mlp(labels, table, b, ups=ups, uniform_rows=False)
+    assert torch.equal(fast.hi, slow.hi) and torch.equal(fast.lo, slow.lo)
+    oh = torch.zeros(B, L, S, S, device="cuda").scatter_(1, lab, 1.0)
+    ref = F.relu(F.conv2d(oh, w, b, padding=1))
+    if ups:
+        ref = F.interpolate(ref, scale_factor=2, mode="nearest")
+    got = _nchw(fast.hi.float() + fast.lo.float())
+    assert (got - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())
