@@ -206,6 +206,74 @@ __global__ void shared_mlp_kernel(const uint8_t* __restrict__ labels, const floa
         *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack2(l4[0], l4[1]), pack2(l4[2], l4[3]));
 }
 
+// The same gather with four consecutive output pixels of a row per thread (W % 4 == 0): the 3 x 6 (ups = 0)
+// or 3 x 4 (ups = 1: the four pixels share two low-resolution columns) label strip is loaded once, the
+// index arithmetic is paid once per quad, and four 8-byte stores leave per thread.  Same additions in the
+// same order as shared_mlp_kernel: bit-identical planes.
+__global__ void shared_mlp_x4_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ table,
+                                     const float* __restrict__ bias, const float* __restrict__ rows,
+                                     __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B, int Hl,
+                                     int Wl, int ups, int L, int nh) {
+    const uint32_t groups = (uint32_t)nh >> 2;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int H = Hl << ups, W = Wl << ups, Wq = W >> 2;
+    if (i >= (uint32_t)B * H * Wq * groups) return;
+    const int g = (int)(i % groups);
+    const uint32_t quad = i / groups;
+    const int x0 = (int)(quad % (uint32_t)Wq) * 4;
+    const uint32_t t2 = quad / (uint32_t)Wq;
+    const int y = (int)(t2 % (uint32_t)H);
+    const int b = (int)(t2 / (uint32_t)H);
+    const int yl = y >> ups, xl0 = x0 >> ups;
+    const int ncol = ups ? 2 : 4;   // low-resolution columns under the quad
+    const uint8_t* lb = labels + (size_t)b * Hl * Wl;
+    int lab[3][6];   // rows yl-1 .. yl+1, columns xl0-1 .. xl0+ncol (255 = outside the image: zero padding)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const int yy = yl - 1 + r, xx = xl0 - 1 + c;
+            lab[r][c] = (c >= ncol + 2 || yy < 0 || yy >= Hl || xx < 0 || xx >= Wl) ? 255 : (int)lb[yy * Wl + xx];
+        }
+    const float4 bias4 = __ldg(reinterpret_cast<const float4*>(bias) + g);
+    const size_t o0 = ((size_t)(((size_t)b * H + y) * W + x0)) * nh + (size_t)g * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j >= ncol) break;
+        bool uniform = rows != nullptr;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) uniform = uniform && lab[tap / 3][j + tap % 3] == lab[1][j + 1];
+        float4 acc;
+        if (uniform) {
+            acc = __ldg(reinterpret_cast<const float4*>(rows + (size_t)lab[1][j + 1] * nh) + g);
+        } else {
+            acc = bias4;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int l = lab[tap / 3][j + tap % 3];
+                if (l == 255) continue;  // zero padding
+                const float4 t = __ldg(reinterpret_cast<const float4*>(table + ((size_t)tap * L + l) * nh) + g);
+                acc.x += t.x;
+                acc.y += t.y;
+                acc.z += t.z;
+                acc.w += t.w;
+            }
+        }
+        const float a[4] = {fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f)};
+        __half h[4], l4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_f16(a[e], h[e], l4[e]);
+        const uint2 vh = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+        const uint2 vl = make_uint2(pack2(l4[0], l4[1]), pack2(l4[2], l4[3]));
+        const int reps = ups ? 2 : 1;   // ups: the low-resolution column covers two output pixels
+        for (int k = 0; k < reps; ++k) {
+            const size_t o = o0 + (size_t)(j * reps + k) * nh;
+            *reinterpret_cast<uint2*>(out_hi + o) = vh;
+            if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = vl;
+        }
+    }
+}
+
 __global__ void style_gather_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ style,
                                     __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B,
                                     int HW, int L, int d) {
@@ -872,8 +940,12 @@ extern "C" int dsee_shared_mlp_fwd(const uint8_t* labels, const float* table, co
         shared_mlp_rows_kernel<<<L, (nh / 4 + 31) / 32 * 32, 0, st>>>(table, bias, uniform_rows, L, nh);
         count_launch();
     }
-    shared_mlp_kernel<<<cdiv(n, 256), 256, 0, st>>>(labels, table, bias, uniform_rows, (__half*)out_hi,
-                                                   (__half*)out_lo, B, Hl, Wl, ups, L, nh);
+    if ((Wl << ups) % 4 == 0)
+        shared_mlp_x4_kernel<<<cdiv(n / 4, 256), 256, 0, st>>>(labels, table, bias, uniform_rows, (__half*)out_hi,
+                                                              (__half*)out_lo, B, Hl, Wl, ups, L, nh);
+    else
+        shared_mlp_kernel<<<cdiv(n, 256), 256, 0, st>>>(labels, table, bias, uniform_rows, (__half*)out_hi,
+                                                       (__half*)out_lo, B, Hl, Wl, ups, L, nh);
     LAUNCH_END();
 }
 
