@@ -142,3 +142,30 @@ def test_style_sweep_layout_with_stub_networks():
     mid = 0.5 * style[0, [1, 2]].mean() + 0.5 * style[1, [1, 2]].mean() + 10 * 1
     assert abs(float(out["fake_image"][0, 1, 0, 0, 0]) - float(mid)) < 1e-5
     assert len(out["style"]) == B and tuple(out["style"][0].shape) == (3, 19, 4)
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """The bench lines committed under profiles/ are what DESIGN.md quotes: each must be one JSON object with
+    the keys of the bench contract (metric / value / e2e / roofline / cpu_baseline / clocks / gpu_launches),
+    a parity figure inside the bound, and - for the multi-GPU lines - the sharded-vs-whole-batch check."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for n in (1, 2, 8):
+        path = os.path.join(root, "profiles", "r2_bench_c2_n%d_final.json" % n)
+        d = json.load(open(path))
+        assert d["n_gpus"] == n and d["unit"] == "images/sec" and d["higher_is_better"] is True
+        assert d["value"] > 0 and d["ms_per_step"] > 0 and d["gpu_launches"] > 0
+        assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+        r = d["roofline"]
+        assert r["bound"] in ("hbm", "tensor") and 0 < r["frac"] <= 1.05 and r["peak"] > 0
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        assert "workload" in d["config"] and "model" not in d["config"]
+        if n == 1:
+            assert d["parity"]["within_tolerance"] and d["parity"]["max_abs"] < d["parity"]["tolerance"] == 1e-3
+            assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+            assert d["value"] > 100 * d["cpu_baseline"]["value"]
+        else:
+            assert d["ddp_parity"]["grads_only_where_single_process_has_them"]
+            assert d["ddp_parity"]["loss_rel_diff"] < 1e-5
